@@ -1,0 +1,433 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.  See oracle/oracle.h for the rules.
+ *
+ * CPU restatement (plain C, fp32, no FMA contraction: build with -ffp-contract=off) of the
+ * reference's MPM particle<->sparse-grid path.  Paths cited are relative to
+ * /root/reference/include/zensim/.  Operation ORDER follows the reference expression by expression
+ * so that, on the host, results are bit-identical to the reference's seq_exec path
+ * (tests/test_oracle_vs_ref.py checks exactly that).
+ */
+#include "oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------ */
+/* container/HashTable.hpp                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+int zo_next_2pow(int n) { /* math/bit/Bits.h:177-184: 1 << bit_length(n-1) */
+  int p = 1;
+  if (n <= 0) return 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+int zo_table_size_for(int expected) { /* HashTable.hpp:87-90, reserve_ratio_v = 16 (:70) */
+  return expected == 0 ? 0 : zo_next_2pow(expected) * 16;
+}
+/* do_hash (HashTable.hpp:496-500) + math/Hash.hpp:17-27 (64-bit hash_combine), then the
+ * "(h % size + size) % size" of insert/query (:358, :449).  key[d] is int -> sign-extended. */
+int zo_hash_slot0(const int key[3], int table_size) {
+  uint64_t seed = (uint64_t)(int64_t)key[0];
+  for (int d = 1; d < 3; ++d)
+    seed ^= ((uint64_t)(int64_t)key[d] + 0x9e3779b97f4a7c15ULL + (seed << 12) + (seed >> 4));
+  int e = (int)(uint32_t)seed; /* static_cast<value_t>(size_t) */
+  return (e % table_size + table_size) % table_size;
+}
+void zo_table_clear(int table_size, int *keys, int *indices, int *status, int *cnt) {
+  for (int e = 0; e < table_size; ++e) { /* SparsityOp.hpp:46-52 */
+    keys[3 * e] = keys[3 * e + 1] = keys[3 * e + 2] = INT_MAX;
+    indices[e] = -1;
+    if (status) status[e] = -1;
+  }
+  *cnt = 0;
+}
+static int key_eq(const int *a, const int *b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
+int zo_table_insert(const int key[3], int table_size, int *keys, int *indices, int *active_keys,
+                    int *cnt) { /* HashTable.hpp:376-398, single-threaded semantics */
+  static const int sentinel[3] = {INT_MAX, INT_MAX, INT_MAX};
+  int slot = zo_hash_slot0(key, table_size);
+  for (;;) {
+    int *stored = keys + 3 * slot;
+    if (key_eq(stored, sentinel)) {
+      memcpy(stored, key, 3 * sizeof(int));
+      int no = (*cnt)++;
+      indices[slot] = no;
+      memcpy(active_keys + 3 * no, key, 3 * sizeof(int));
+      return no;
+    }
+    if (key_eq(stored, key)) return -1;
+    slot = (slot + 127) % table_size; /* :386 */
+  }
+}
+int zo_table_query(const int key[3], int table_size, const int *keys, const int *indices) {
+  int slot = zo_hash_slot0(key, table_size); /* HashTable.hpp:447-456 */
+  for (;;) {
+    if (key_eq(keys + 3 * slot, key)) return indices[slot];
+    if (indices[slot] == -1) return -1;
+    slot += 127;
+    if (slot > table_size) slot = slot % table_size; /* sic: '>' not '>=' (:454) */
+    if (slot == table_size) return -1; /* the reference reads out of bounds here; never hit in tests */
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* simulation/sparsity/SparsityOp.hpp                                                         */
+/* ------------------------------------------------------------------------------------------ */
+void zo_block_of_particle(const float x[3], float dx, int blockid[3]) { /* :58-79 */
+  const float dxinv = (float)1.0 / dx; /* :66 */
+  for (int d = 0; d < 3; ++d) {
+    int coord = (int)floorf(x[d] * dxinv + 0.5f) + (-2); /* :73-74, offset=-2 displacement=.5 */
+    int b = coord + (coord < 0 ? -4 + 1 : 0);            /* :76 */
+    blockid[d] = b / 4;                                  /* :77 (C truncation on the shifted value) */
+  }
+}
+int zo_partition_build(int n, const float *x, float dx, int table_size, int *keys, int *indices,
+                       int *status, int *active_keys, int *cnt) {
+  zo_table_clear(table_size, keys, indices, status, cnt);
+  for (int p = 0; p < n; ++p) {
+    int b[3];
+    zo_block_of_particle(x + 3 * p, dx, b);
+    zo_table_insert(b, table_size, keys, indices, active_keys, cnt);
+  }
+  const int first = *cnt; /* EnlargeSparsity{lo=0, hi=2} over the first table.size() entries, :88-112 */
+  for (int i = 0; i < first; ++i) {
+    int base[3] = {active_keys[3 * i], active_keys[3 * i + 1], active_keys[3 * i + 2]};
+    for (int ox = 0; ox < 2; ++ox)
+      for (int oy = 0; oy < 2; ++oy)
+        for (int oz = 0; oz < 2; ++oz) {
+          int k[3] = {base[0] + ox, base[1] + oy, base[2] + oz};
+          zo_table_insert(k, table_size, keys, indices, active_keys, cnt);
+        }
+  }
+  return *cnt;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* math/matrix/SVD.hpp:15-1026  — McAdams/Selle/Tamstorf/Teran/Sifakis 3x3 SVD, 4 Jacobi sweeps  */
+/* ------------------------------------------------------------------------------------------ */
+static float rsqrt_host(float v) { return 1.0f / sqrtf(v); } /* ZpcMathUtils.hpp:842-846 */
+
+/* rsqrt with one Newton-Raphson refinement as written at SVD.hpp:386-392, 701-708 */
+static float rsqrt_refined(float t2) {
+  float t1 = rsqrt_host(t2);
+  float t4 = t1 * 0.5f;
+  float t3 = t1 * t4;
+  t3 = t1 * t3;
+  t3 = t2 * t3;
+  t1 = t1 + t4;
+  t1 = t1 - t3;
+  return t1;
+}
+
+/* One cyclic Jacobi step on the symmetric matrix (SVD.hpp:96-178 and its two rotated copies).
+ * pp,qq = the two diagonal entries, off = the entry coupling them, rr = the third diagonal entry,
+ * a,b = the two remaining off-diagonals in the order the reference updates them.
+ * q = quaternion (s,x,y,z); axis = which vector component takes "+sh*qs". */
+static void jacobi_step(float *pp, float *qq, float *off, float *rr, float *a, float *b, float q[4],
+                        int axis) {
+  const float tiny = 1.e-20f, gamma = 5.8284273147583007813f;
+  union { float f; uint32_t u; } sp8 = {.u = 1053028117u}, cp8 = {.u = 1064076127u};
+  float sh = *off * 0.5f;
+  float t5 = *pp - *qq;
+  float t2 = sh * sh;
+  int big = t2 >= tiny;
+  sh = big ? sh : 0.0f;
+  float ch = big ? t5 : 1.0f;
+  float t1 = sh * sh;
+  t2 = ch * ch;
+  float t3 = t1 + t2;
+  float t4 = rsqrt_host(t3);
+  sh = t4 * sh;
+  ch = t4 * ch;
+  t1 = gamma * t1;
+  if (t2 <= t1) { sh = sp8.f; ch = cp8.f; }
+  t1 = sh * sh;
+  t2 = ch * ch;
+  float c = t2 - t1;
+  float s = ch * sh;
+  s = s + s;
+  /* conjugation */
+  t3 = t1 + t2;
+  *rr = *rr * t3; *a = *a * t3; *b = *b * t3; *rr = *rr * t3;
+  t1 = s * *a; t2 = s * *b;
+  *a = c * *a; *b = c * *b;
+  *a = t2 + *a; *b = *b - t1;
+  t2 = s * s;
+  t1 = *qq * t2; t3 = *pp * t2;
+  t4 = c * c;
+  *pp = *pp * t4; *qq = *qq * t4;
+  *pp = *pp + t1; *qq = *qq + t3;
+  t4 = t4 - t2;
+  t2 = *off + *off;
+  *off = *off * t4;
+  t4 = c * s;
+  t2 = t2 * t4; t5 = t5 * t4;
+  *pp = *pp + t2; *off = *off - t5; *qq = *qq - t2;
+  /* quaternion accumulation */
+  float t[3] = {sh * q[1], sh * q[2], sh * q[3]};
+  sh = sh * q[0];
+  for (int i = 0; i < 4; ++i) q[i] = ch * q[i];
+  const int bx = (axis + 1) % 3, cx = (axis + 2) % 3;
+  q[1 + axis] = q[1 + axis] + sh;
+  q[0] = q[0] - t[axis];
+  q[1 + bx] = q[1 + bx] + t[cx];
+  q[1 + cx] = q[1 + cx] - t[bx];
+}
+
+/* Givens quaternion zeroing `low` against pivot `piv` (SVD.hpp:688-738 and two copies) */
+static void qr_givens(float piv, float low, float *c, float *s) {
+  const float small = 1.e-12f;
+  float sh = low * low;
+  sh = (sh >= small) ? low : 0.0f;
+  float ch = 0.0f - piv;
+  ch = piv > ch ? piv : ch;       /* math::max(ch, piv) = y > x ? y : x, ZpcMathUtils.hpp:299 */
+  ch = small > ch ? small : ch;
+  int nonneg = piv >= 0.0f;
+  float t1 = ch * ch, t2 = sh * sh;
+  t2 = t1 + t2;
+  t1 = rsqrt_refined(t2);
+  t1 = t1 * t2;
+  ch = ch + t1;
+  if (!nonneg) { float tmp = ch; ch = sh; sh = tmp; }
+  t1 = ch * ch; t2 = sh * sh;
+  t2 = t1 + t2;
+  t1 = rsqrt_refined(t2);
+  ch = ch * t1; sh = sh * t1;
+  *c = ch * ch; *s = sh * sh;
+  *c = *c - *s;
+  *s = sh * ch;
+  *s = *s + *s;
+}
+static void rot_pair(float *x, float *y, float c, float s) { /* x' = c x + s y ; y' = c y - s x */
+  float t1 = s * *x, t2 = s * *y;
+  *x = c * *x; *y = c * *y;
+  *x = *x + t2; *y = *y - t1;
+}
+
+/* F,U,V column-major 9-vectors (F[3*col+row]) as passed by ConstitutiveModel_Vol_dP.hpp:14-16 */
+void zo_svd3(const float F[9], float U[9], float S[3], float V[9]) {
+#define A_(r, c) a[(r)*3 + (c)] /* row-major local copies, 0-based */
+  float a[9], v[9], u[9];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A_(r, c) = F[3 * c + r];
+  /* normal equations S = A^T A, lower triangle (SVD.hpp:54-88) */
+  float s11 = (A_(1,0)*A_(1,0) + A_(0,0)*A_(0,0)); s11 = A_(2,0)*A_(2,0) + s11;
+  float s21 = (A_(1,1)*A_(1,0) + A_(0,1)*A_(0,0)); s21 = A_(2,1)*A_(2,0) + s21;
+  float s31 = (A_(1,2)*A_(1,0) + A_(0,2)*A_(0,0)); s31 = A_(2,2)*A_(2,0) + s31;
+  float s22 = (A_(1,1)*A_(1,1) + A_(0,1)*A_(0,1)); s22 = A_(2,1)*A_(2,1) + s22;
+  float s32 = (A_(1,2)*A_(1,1) + A_(0,2)*A_(0,1)); s32 = A_(2,2)*A_(2,1) + s32;
+  float s33 = (A_(1,2)*A_(1,2) + A_(0,2)*A_(0,2)); s33 = A_(2,2)*A_(2,2) + s33;
+  float q[4] = {1.f, 0.f, 0.f, 0.f};
+  for (int sweep = 0; sweep < 4; ++sweep) { /* :96 */
+    jacobi_step(&s11, &s22, &s21, &s33, &s31, &s32, q, 2); /* (1,2), :97-178 */
+    jacobi_step(&s22, &s33, &s32, &s11, &s21, &s31, q, 0); /* (2,3), :183-262 */
+    jacobi_step(&s33, &s11, &s31, &s22, &s32, &s21, q, 1); /* (3,1), :269-371 */
+  }
+  { /* normalise quaternion, :378-397 */
+    float t2 = q[0] * q[0];
+    t2 = q[1] * q[1] + t2; t2 = q[2] * q[2] + t2; t2 = q[3] * q[3] + t2;
+    float t1 = rsqrt_refined(t2);
+    for (int i = 0; i < 4; ++i) q[i] = q[i] * t1;
+  }
+  { /* quaternion -> V, :403-430 */
+    float t1 = q[1]*q[1], t2 = q[2]*q[2], t3 = q[3]*q[3];
+    float v11 = q[0]*q[0];
+    float v22 = v11 - t1;
+    float v33 = v22 - t2; v33 = v33 + t3;
+    v22 = v22 + t2; v22 = v22 - t3;
+    v11 = v11 + t1; v11 = v11 - t2; v11 = v11 - t3;
+    t1 = q[1] + q[1]; t2 = q[2] + q[2]; t3 = q[3] + q[3];
+    float v32 = q[0]*t1, v13 = q[0]*t2, v21 = q[0]*t3;
+    t1 = q[2]*t1; t2 = q[3]*t2; t3 = q[1]*t3;
+    float v12 = t1 - v21, v23 = t2 - v32, v31 = t3 - v13;
+    v21 = t1 + v21; v32 = t2 + v32; v13 = t3 + v13;
+    v[0]=v11; v[1]=v12; v[2]=v13; v[3]=v21; v[4]=v22; v[5]=v23; v[6]=v31; v[7]=v32; v[8]=v33;
+  }
+#define V_(r, c) v[(r)*3 + (c)]
+  for (int r = 0; r < 3; ++r) { /* A <- A V, :436-488 */
+    float x = A_(r,0), y = A_(r,1), z = A_(r,2);
+    for (int c = 0; c < 3; ++c) {
+      float acc = V_(0,c) * x;
+      acc = acc + V_(1,c) * y;
+      acc = acc + V_(2,c) * z;
+      A_(r,c) = acc;
+    }
+  }
+  /* sort columns by norm, :494-676 */
+  float rho[3];
+  for (int c = 0; c < 3; ++c) {
+    float t = A_(0,c)*A_(0,c);
+    t = t + A_(1,c)*A_(1,c);
+    t = t + A_(2,c)*A_(2,c);
+    rho[c] = t;
+  }
+  static const int swp[3][3] = {{0, 1, 1}, {0, 2, 0}, {1, 2, 2}}; /* (i, j, column to negate) */
+  for (int k = 0; k < 3; ++k) {
+    int i = swp[k][0], j = swp[k][1], neg = swp[k][2];
+    if (rho[i] < rho[j]) {
+      for (int r = 0; r < 3; ++r) {
+        float t = A_(r,i); A_(r,i) = A_(r,j); A_(r,j) = t;
+        t = V_(r,i); V_(r,i) = V_(r,j); V_(r,j) = t;
+      }
+      float t = rho[i]; rho[i] = rho[j]; rho[j] = t;
+      for (int r = 0; r < 3; ++r) { A_(r,neg) = A_(r,neg) * -1.0f; V_(r,neg) = V_(r,neg) * -1.0f; }
+    }
+  }
+  /* QR of A V by three Givens rotations, :682-1000 */
+  for (int i = 0; i < 9; ++i) u[i] = (i % 4 == 0) ? 1.f : 0.f;
+#define U_(r, c) u[(r)*3 + (c)]
+  static const int piv[3][3] = {{0, 0, 1}, {0, 0, 2}, {1, 1, 2}}; /* pivot (r,c) ... and lower row */
+  for (int k = 0; k < 3; ++k) {
+    int p = piv[k][0], lo = piv[k][2];
+    float c, s;
+    qr_givens(A_(p, piv[k][1]), A_(lo, piv[k][1]), &c, &s);
+    for (int col = 0; col < 3; ++col) rot_pair(&A_(p,col), &A_(lo,col), c, s);
+    for (int row = 0; row < 3; ++row) rot_pair(&U_(row,p), &U_(row,lo), c, s);
+  }
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { U[3*c + r] = U_(r,c); V[3*c + r] = V_(r,c); }
+  S[0] = A_(0,0); S[1] = A_(1,1); S[2] = A_(2,2);
+#undef A_
+#undef V_
+#undef U_
+}
+
+void zo_lame(float E, float nu, float *mu, float *lam) { /* ConstitutiveModel.hpp:34-38, T=float */
+  *mu = (float)(0.5 * E / (1 + nu));               /* 0.5 is a double literal; (1+nu) is float */
+  *lam = (float)(E * nu / ((1 + nu) * (1 - 2 * nu)));
+}
+
+void zo_stress_fixedcorotated(float volume, float mu, float lam, const float F[9], float PF[9]) {
+  float U[9], S[3], V[9], P[9], Ph[3]; /* ConstitutiveModel_Vol_dP.hpp:10-47 */
+  zo_svd3(F, U, S, V);
+  float J = S[0] * S[1] * S[2];
+  float smu = 2.f * mu, sl = lam * (J - 1.f);
+  Ph[0] = smu * (S[0] - 1.f) + sl * (S[1] * S[2]);
+  Ph[1] = smu * (S[1] - 1.f) + sl * (S[0] * S[2]);
+  Ph[2] = smu * (S[2] - 1.f) + sl * (S[0] * S[1]);
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) /* P[3c+r] = sum_k Ph[k] U[3k+r] V[3k+c], :26-34 */
+      P[3*c + r] = (Ph[0]*U[r]*V[c] + Ph[1]*U[3 + r]*V[3 + c]) + Ph[2]*U[6 + r]*V[6 + c];
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) /* PF' : PF[3c+r] = sum_k P[3k+r] F[3k+c], :37-45 */
+      PF[3*c + r] = ((P[r]*F[c] + P[3 + r]*F[3 + c]) + P[6 + r]*F[6 + c]) * volume;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* simulation/Utils.hpp:30-174 LocalArena (collocated, quadratic) + InterpolationKernel.hpp   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int corner[3]; float local[3]; float w[3][3]; float dx; } zo_arena;
+static void arena_init(zo_arena *a, float dx, const float pos[3]) {
+  a->dx = dx;
+  for (int d = 0; d < 3; ++d) {
+    float X = pos[d] / dx;                                  /* Utils.hpp:56 */
+    a->corner[d] = (int)floorf(X - 0.5f);                   /* base_node<1>, InterpolationKernel.hpp:46-55 */
+    float lp = X - (float)a->corner[d];                     /* Utils.hpp:60 */
+    float d0 = lp - (float)(int)floorf(lp - 0.5f);          /* InterpolationKernel.hpp:106 */
+    a->w[d][0] = 0.5f * (1.5f - d0) * (1.5f - d0);          /* :107 */
+    float d1 = d0 - 1.0f;
+    a->w[d][1] = 0.75f - d1 * d1;
+    float zz = 0.5f + d1;
+    a->w[d][2] = 0.5f * zz * zz;
+    a->local[d] = lp * dx;                                  /* Utils.hpp:67 */
+  }
+}
+static int floor_div4(int c, int *loc) { /* Utils.hpp:20-28: loc = c & 3 ; block = (c - loc)/4 */
+  *loc = c & 3;
+  return (c - *loc) / 4;
+}
+
+void zo_clean_grid(int nblocks, float *grid) { /* GridOp.hpp:54-69 */
+  memset(grid, 0, sizeof(float) * 7 * 64 * (size_t)nblocks);
+}
+
+void zo_p2g_fcr(int n, const float *x, const float *v, const float *m, const float *C,
+                const float *F, float dx, float dt, float E, float nu, float volume, int table_size,
+                const int *keys, const int *indices, float *grid) {
+  const float dx_inv = (float)1.0 / dx;        /* P2G.hpp:43 */
+  const float D_inv = 4.f * dx_inv * dx_inv;   /* :51 */
+  float mu, lam;
+  zo_lame(E, nu, &mu, &lam);                   /* :84 */
+  for (int p = 0; p < n; ++p) {
+    float contrib[9];
+    const float *Cp = C + 9 * p, *vel = v + 3 * p;
+    const float mass = m[p];
+    zo_stress_fixedcorotated(volume, mu, lam, F + 9 * p, contrib);            /* :87 */
+    for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;        /* :104 */
+    zo_arena ar;
+    arena_init(&ar, dx, x + 3 * p);                                           /* :107 */
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) { /* :108 */
+      int o[3] = {i, j, k}, loc[3], blk[3];
+      float xixp[3];
+      for (int d = 0; d < 3; ++d) {
+        blk[d] = floor_div4(ar.corner[d] + o[d], &loc[d]);
+        xixp[d] = (float)o[d] * ar.dx - ar.local[d];                          /* Utils.hpp:163-165 */
+      }
+      float W = 1.f; W *= ar.w[0][i]; W *= ar.w[1][j]; W *= ar.w[2][k];       /* Utils.hpp:77-82 */
+      int bno = zo_table_query(blk, table_size, keys, indices);
+      float *tile = grid + (size_t)bno * 7 * 64;
+      int cell = (loc[0] << 4) | (loc[1] << 2) | loc[2];                      /* Structure.hpp:851-859 */
+      tile[cell] += mass * W;                                                 /* P2G.hpp:114 */
+      for (int d = 0; d < 3; ++d) {
+        tile[(1 + d) * 64 + cell] += W * mass * (vel[d] + (Cp[d] * xixp[0] + Cp[3 + d] * xixp[1] + Cp[6 + d] * xixp[2])); /* :117-119 */
+        tile[(4 + d) * 64 + cell] += (contrib[d] * xixp[0] + contrib[3 + d] * xixp[1] + contrib[6 + d] * xixp[2]) * W;     /* :121-123 */
+      }
+    }
+  }
+}
+
+void zo_grid_update(int nblocks, float *grid, float dt, const float extf[3], int mode,
+                    float *max_vel_sqr) {
+  float mx = *max_vel_sqr;
+  for (int b = 0; b < nblocks; ++b) {
+    float *tile = grid + (size_t)b * 7 * 64;
+    for (int c = 0; c < 64; ++c) {
+      if (mode == 1) for (int d = 0; d < 3; ++d) tile[(1 + d) * 64 + c] += tile[(4 + d) * 64 + c];
+      float mass = tile[c];                       /* GridOp.hpp:94 */
+      if (mass != 0.f) {
+        mass = 1.f / mass;                        /* :96 */
+        float nrm = 0.f;
+        for (int d = 0; d < 3; ++d) {
+          float vd = tile[(1 + d) * 64 + c] * mass + extf[d] * dt;  /* :97 */
+          tile[(1 + d) * 64 + c] = vd;
+          nrm += vd * vd;                         /* l2NormSqr: sequential sum from 0 */
+        }
+        if (nrm > mx) mx = nrm;                   /* atomic_max, :104 */
+      }
+    }
+  }
+  *max_vel_sqr = mx;
+}
+
+void zo_g2p(int n, float *x, float *v, float *C, float *F, float dx, float dt, int table_size,
+            const int *keys, const int *indices, const float *grid) {
+  const float dx_inv = (float)1 / dx;            /* G2P.hpp:45 */
+  const float D_inv = 4.f * dx_inv * dx_inv;     /* :47 */
+  for (int p = 0; p < n; ++p) {
+    float pos[3] = {x[3*p], x[3*p+1], x[3*p+2]}, vel[3] = {0, 0, 0}, Cn[9] = {0};
+    zo_arena ar;
+    arena_init(&ar, dx, pos);                    /* :56 */
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) {
+      int o[3] = {i, j, k}, loc[3], blk[3];
+      float xixp[3], vi[3];
+      for (int d = 0; d < 3; ++d) {
+        blk[d] = floor_div4(ar.corner[d] + o[d], &loc[d]);
+        xixp[d] = (float)o[d] * ar.dx - ar.local[d];
+      }
+      float W = 1.f; W *= ar.w[0][i]; W *= ar.w[1][j]; W *= ar.w[2][k];
+      int bno = zo_table_query(blk, table_size, keys, indices);
+      const float *tile = grid + (size_t)bno * 7 * 64;
+      int cell = (loc[0] << 4) | (loc[1] << 2) | loc[2];
+      for (int d = 0; d < 3; ++d) { vi[d] = tile[(1 + d) * 64 + cell]; vel[d] += vi[d] * W; } /* :63-64 */
+      for (int d = 0; d < 9; ++d) Cn[d] += W * vi[d % 3] * xixp[d / 3] * D_inv;               /* :65 */
+    }
+    for (int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;                                        /* :67 */
+    float tmp[9], Fo[9], Fn[9];
+    memcpy(Fo, F + 9 * p, sizeof Fo);
+    for (int d = 0; d < 9; ++d) tmp[d] = Cn[d] * dt + ((d & 0x3) ? 0.f : 1.f);                /* :76 */
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) /* MatrixUtils.h:136-146, column-major a*b */
+      Fn[3*c + r] = (tmp[r] * Fo[3*c] + tmp[3 + r] * Fo[3*c + 1]) + tmp[6 + r] * Fo[3*c + 2];
+    memcpy(F + 9 * p, Fn, sizeof Fn);
+    memcpy(x + 3 * p, pos, sizeof pos);
+    memcpy(v + 3 * p, vel, sizeof vel);
+    memcpy(C + 9 * p, Cn, sizeof Cn);
+  }
+}

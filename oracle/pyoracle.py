@@ -1,0 +1,304 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes bindings for the two checkers:
+  * ``Oracle``  -> oracle/libzpcoracle.so  (plain-C restatement, oracle/*.c)
+  * ``Ref``     -> oracle/_ref/libzpcref.so (the unmodified reference compiled by oracle/Makefile;
+                   present only if it was built where /root/reference is mounted)
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libzpcoracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libzpcref.so")
+
+_f = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(HERE, f) for f in ("mpm_oracle.c", "prims_oracle.c", "oracle.h")]
+    if (not force and os.path.exists(ORACLE_SO)
+            and all(os.path.getmtime(ORACLE_SO) >= os.path.getmtime(s) for s in srcs)):
+        return ORACLE_SO
+    subprocess.check_call(["make", "-s", "-C", HERE, "-B", "oracle"])
+    return ORACLE_SO
+
+
+def build_ref():
+    """(Re)build oracle/_ref from /root/reference when it is mounted; no-op otherwise."""
+    if os.path.isdir("/root/reference/include/zensim"):
+        subprocess.check_call(["make", "-s", "-C", HERE, "-j8", "ref"])
+    return REF_SO if os.path.exists(REF_SO) else None
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_KT = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64}
+_ST = {"i32": np.int32, "u32": np.uint32, "i64": np.int64, "f32": np.float32}
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        L = self.lib
+        L.zo_table_size_for.restype = C.c_int
+        L.zo_partition_build.restype = C.c_int
+        L.zo_table_query.restype = C.c_int
+        L.zo_hash_slot0.restype = C.c_int
+
+    # ---- hash / partition ----
+    def table_size_for(self, expected):
+        return int(self.lib.zo_table_size_for(C.c_int(expected)))
+
+    def hash_slot0(self, key, table_size):
+        k = np.ascontiguousarray(key, np.int32)
+        return int(self.lib.zo_hash_slot0(_ptr(k), C.c_int(table_size)))
+
+    def partition_build(self, x, dx, table_size):
+        x = np.ascontiguousarray(x, np.float32)
+        n = x.shape[0]
+        keys = np.empty((table_size, 3), np.int32)
+        indices = np.empty(table_size, np.int32)
+        status = np.empty(table_size, np.int32)
+        active = np.zeros((table_size, 3), np.int32)
+        cnt = np.zeros(1, np.int32)
+        nb = self.lib.zo_partition_build(C.c_int(n), _ptr(x), C.c_float(dx), C.c_int(table_size),
+                                         _ptr(keys), _ptr(indices), _ptr(status), _ptr(active),
+                                         _ptr(cnt))
+        return dict(keys=keys, indices=indices, status=status, active_keys=active[:nb].copy(),
+                    nblocks=int(nb), table_size=table_size)
+
+    def table_query(self, key, tab):
+        k = np.ascontiguousarray(key, np.int32)
+        return int(self.lib.zo_table_query(_ptr(k), C.c_int(tab["table_size"]), _ptr(tab["keys"]),
+                                           _ptr(tab["indices"])))
+
+    # ---- per particle math ----
+    def lame(self, E, nu):
+        mu, lam = C.c_float(), C.c_float()
+        self.lib.zo_lame(C.c_float(E), C.c_float(nu), C.byref(mu), C.byref(lam))
+        return mu.value, lam.value
+
+    def svd3(self, F):
+        F = np.ascontiguousarray(F, np.float32)
+        U = np.empty(9, np.float32); S = np.empty(3, np.float32); V = np.empty(9, np.float32)
+        self.lib.zo_svd3(_ptr(F), _ptr(U), _ptr(S), _ptr(V))
+        return U, S, V
+
+    def stress_fixedcorotated(self, volume, E, nu, F):
+        mu, lam = self.lame(E, nu)
+        F = np.ascontiguousarray(F, np.float32)
+        PF = np.empty(9, np.float32)
+        self.lib.zo_stress_fixedcorotated(C.c_float(volume), C.c_float(mu), C.c_float(lam), _ptr(F),
+                                          _ptr(PF))
+        return PF
+
+    # ---- transfer ----
+    def p2g(self, P, tab, dx, dt, E, nu, volume, grid=None):
+        nb = tab["nblocks"]
+        if grid is None:
+            grid = np.zeros((nb, 7, 64), np.float32)
+        n = P["x"].shape[0]
+        self.lib.zo_p2g_fcr(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["m"]), _ptr(P["C"]),
+                            _ptr(P["F"]), C.c_float(dx), C.c_float(dt), C.c_float(E), C.c_float(nu),
+                            C.c_float(volume), C.c_int(tab["table_size"]), _ptr(tab["keys"]),
+                            _ptr(tab["indices"]), _ptr(grid))
+        return grid
+
+    def grid_update(self, grid, dt, extf, mode):
+        e = np.ascontiguousarray(extf, np.float32)
+        mx = np.zeros(1, np.float32)
+        self.lib.zo_grid_update(C.c_int(grid.shape[0]), _ptr(grid), C.c_float(dt), _ptr(e),
+                                C.c_int(mode), _ptr(mx))
+        return float(mx[0])
+
+    def g2p(self, P, tab, grid, dx, dt):
+        n = P["x"].shape[0]
+        self.lib.zo_g2p(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["C"]), _ptr(P["F"]),
+                        C.c_float(dx), C.c_float(dt), C.c_int(tab["table_size"]), _ptr(tab["keys"]),
+                        _ptr(tab["indices"]), _ptr(grid))
+
+    def substep(self, P, dx, dt, E, nu, volume, gravity, mode, expected_blocks=None):
+        """Composed explicit APIC substep of SURVEY §3.1; P is updated in place."""
+        n = P["x"].shape[0]
+        ts = self.table_size_for(expected_blocks or max(n // 8, 1))
+        tab = self.partition_build(P["x"], dx, ts)
+        grid = self.p2g(P, tab, dx, dt, E, nu, volume)
+        grid_p2g = grid.copy()
+        mx = self.grid_update(grid, dt, (0.0, gravity, 0.0), mode)
+        self.g2p(P, tab, grid, dx, dt)
+        return dict(tab=tab, grid_p2g=grid_p2g, grid=grid, max_vel_sqr=mx)
+
+    # ---- primitives ----
+    def radix_sort_pair(self, kind, keys, vals, sbit=0, ebit=None):
+        kt = _KT[kind]
+        keys = np.ascontiguousarray(keys, kt); vals = np.ascontiguousarray(vals, np.int32)
+        ko = np.empty_like(keys); vo = np.empty_like(vals)
+        ebit = keys.itemsize * 8 if ebit is None else ebit
+        getattr(self.lib, "zo_radix_sort_pair_" + kind)(_ptr(keys), _ptr(vals), _ptr(ko), _ptr(vo),
+                                                        C.c_size_t(keys.size), C.c_int(sbit),
+                                                        C.c_int(ebit))
+        return ko, vo
+
+    def radix_sort(self, kind, keys, sbit=0, ebit=None):
+        kt = _KT[kind]
+        keys = np.ascontiguousarray(keys, kt)
+        ko = np.empty_like(keys)
+        ebit = keys.itemsize * 8 if ebit is None else ebit
+        getattr(self.lib, "zo_radix_sort_" + kind)(_ptr(keys), _ptr(ko), C.c_size_t(keys.size),
+                                                   C.c_int(sbit), C.c_int(ebit))
+        return ko
+
+    def scan(self, which, kind, a):
+        a = np.ascontiguousarray(a, _ST[kind])
+        out = np.empty_like(a)
+        getattr(self.lib, "zo_%s_scan_sum_%s" % (which, kind))(_ptr(a), _ptr(out),
+                                                               C.c_size_t(a.size))
+        return out
+
+    def reduce(self, op, kind, a):
+        a = np.ascontiguousarray(a, _ST[kind])
+        out = np.zeros(1, _ST[kind])
+        getattr(self.lib, "zo_reduce_%s_%s" % (op, kind))(_ptr(a), _ptr(out), C.c_size_t(a.size))
+        return out[0]
+
+
+class Ref:
+    """The unmodified reference (seq_exec when nthreads == 0, omp_exec().threads(n) otherwise)."""
+
+    def __init__(self, path=None):
+        path = path or REF_SO
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.zpcref_mpm_create.restype = C.c_void_p
+        L.zpcref_mpm_partition.restype = C.c_int
+        L.zpcref_mpm_table_size.restype = C.c_int
+        L.zpcref_mpm_get_maxvel.restype = C.c_float
+        L.zpcref_max_threads.restype = C.c_int
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def max_threads(self):
+        return int(self.lib.zpcref_max_threads())
+
+    class Mpm:
+        def __init__(self, ref, n, dx, nthreads, expected_blocks):
+            self.L = ref.lib
+            self.n = n
+            self.h = C.c_void_p(self.L.zpcref_mpm_create(C.c_int(n), C.c_float(dx),
+                                                         C.c_int(nthreads),
+                                                         C.c_int(expected_blocks)))
+            self.nblocks = 0
+
+        def close(self):
+            if self.h:
+                self.L.zpcref_mpm_destroy(self.h)
+                self.h = None
+
+        def set_particles(self, P):
+            self.L.zpcref_mpm_set_particles(self.h, _ptr(P["x"]), _ptr(P["v"]), _ptr(P["m"]),
+                                            _ptr(P["C"]), _ptr(P["F"]))
+
+        def get_particles(self):
+            n = self.n
+            x = np.empty((n, 3), np.float32); v = np.empty((n, 3), np.float32)
+            Cm = np.empty((n, 9), np.float32); F = np.empty((n, 9), np.float32)
+            self.L.zpcref_mpm_get_particles(self.h, _ptr(x), _ptr(v), _ptr(Cm), _ptr(F))
+            return dict(x=x, v=v, C=Cm, F=F)
+
+        def partition(self):
+            self.nblocks = int(self.L.zpcref_mpm_partition(self.h))
+            return self.nblocks
+
+        def keys(self):
+            k = np.empty((self.nblocks, 3), np.int32)
+            self.L.zpcref_mpm_get_keys(self.h, _ptr(k))
+            return k
+
+        def table(self):
+            ts = int(self.L.zpcref_mpm_table_size(self.h))
+            keys = np.empty((ts, 3), np.int32); idx = np.empty(ts, np.int32)
+            self.L.zpcref_mpm_get_table(self.h, _ptr(keys), _ptr(idx))
+            return dict(keys=keys, indices=idx, table_size=ts, nblocks=self.nblocks,
+                        active_keys=self.keys())
+
+        def clean_grid(self):
+            self.L.zpcref_mpm_clean_grid(self.h)
+
+        def p2g(self, dt, E, nu, volume):
+            self.L.zpcref_mpm_p2g(self.h, C.c_float(dt), C.c_float(E), C.c_float(nu),
+                                  C.c_float(volume))
+
+        def grid_update(self, dt, gravity, mode):
+            self.L.zpcref_mpm_grid_update(self.h, C.c_float(dt), C.c_float(gravity), C.c_int(mode))
+            return float(self.L.zpcref_mpm_get_maxvel(self.h))
+
+        def g2p(self, dt):
+            self.L.zpcref_mpm_g2p(self.h, C.c_float(dt))
+
+        def grid(self):
+            g = np.empty((self.nblocks, 7, 64), np.float32)
+            self.L.zpcref_mpm_get_grid(self.h, _ptr(g))
+            return g
+
+    def mpm(self, n, dx, nthreads=0, expected_blocks=None):
+        return Ref.Mpm(self, n, dx, nthreads, expected_blocks or max(n // 8, 1))
+
+    def radix_sort_pair(self, kind, keys, vals, sbit=0, ebit=None, nthreads=0):
+        kt = _KT[kind]
+        keys = np.ascontiguousarray(keys, kt); vals = np.ascontiguousarray(vals, np.int32)
+        ko = np.empty_like(keys); vo = np.empty_like(vals)
+        ebit = keys.itemsize * 8 if ebit is None else ebit
+        getattr(self.lib, "zpcref_radix_sort_pair_" + kind)(C.c_int(nthreads), _ptr(keys),
+                                                            _ptr(vals), _ptr(ko), _ptr(vo),
+                                                            C.c_size_t(keys.size), C.c_int(sbit),
+                                                            C.c_int(ebit))
+        return ko, vo
+
+    def radix_sort(self, kind, keys, sbit=0, ebit=None, nthreads=0):
+        kt = _KT[kind]
+        keys = np.ascontiguousarray(keys, kt)
+        ko = np.empty_like(keys)
+        ebit = keys.itemsize * 8 if ebit is None else ebit
+        getattr(self.lib, "zpcref_radix_sort_" + kind)(C.c_int(nthreads), _ptr(keys), _ptr(ko),
+                                                       C.c_size_t(keys.size), C.c_int(sbit),
+                                                       C.c_int(ebit))
+        return ko
+
+    def scan(self, which, kind, a, nthreads=0):
+        a = np.ascontiguousarray(a, _ST[kind])
+        out = np.empty_like(a)
+        getattr(self.lib, "zpcref_%s_scan_sum_%s" % (which, kind))(C.c_int(nthreads), _ptr(a),
+                                                                   _ptr(out), C.c_size_t(a.size))
+        return out
+
+    def reduce(self, op, kind, a, nthreads=0):
+        a = np.ascontiguousarray(a, _ST[kind])
+        out = np.zeros(1, _ST[kind])
+        getattr(self.lib, "zpcref_reduce_%s_%s" % (op, kind))(C.c_int(nthreads), _ptr(a), _ptr(out),
+                                                              C.c_size_t(a.size))
+        return out[0]
+
+    def svd3(self, F):
+        F = np.ascontiguousarray(F, np.float32)
+        U = np.empty(9, np.float32); S = np.empty(3, np.float32); V = np.empty(9, np.float32)
+        self.lib.zpcref_svd3(_ptr(F), _ptr(U), _ptr(S), _ptr(V))
+        return U, S, V
+
+    def stress_fixedcorotated(self, volume, E, nu, F):
+        F = np.ascontiguousarray(F, np.float32)
+        PF = np.empty(9, np.float32)
+        self.lib.zpcref_stress_fixedcorotated(C.c_float(volume), C.c_float(E), C.c_float(nu),
+                                              _ptr(F), _ptr(PF))
+        return PF

@@ -1,0 +1,231 @@
+// TEST INFRASTRUCTURE — not product code.
+//
+// Thin C-ABI driver around the UNMODIFIED reference (zenustech/zpc) headers, compiled in place from
+// /root/reference by oracle/Makefile into oracle/_ref/libzpcref.so (git-ignored).  It composes the
+// explicit APIC substep exactly as SURVEY.md §3.1 lists it, on the reference's own host policies
+// (seq_exec / omp_exec), and exposes the reference's serial/OpenMP sort / scan / reduce.
+// Used only by tests/ (to pin oracle/*.c) and by bench.py's reference arm.  No reference source is
+// copied: every functor below is the reference's, instantiated here.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "zensim/container/HashTable.hpp"
+#include "zensim/container/Vector.hpp"
+#include "zensim/execution/ExecutionPolicy.hpp"
+#include "zensim/geometry/SparseLevelSet.hpp"
+#include "zensim/geometry/Structure.hpp"
+#include "zensim/geometry/Structurefree.hpp"
+#include "zensim/omp/execution/ExecutionPolicy.hpp"
+#include "zensim/physics/ConstitutiveModel_Vol_dP.hpp"
+#include "zensim/simulation/grid/GridOp.hpp"        // patched copy (template disambiguator) on -I path
+#include "zensim/simulation/sparsity/SparsityOp.hpp"
+#include "zensim/simulation/transfer/G2P.hpp"       // patched copy on -I path
+#include "zensim/simulation/transfer/P2G.hpp"
+
+using namespace zs;
+
+namespace {
+  struct RefMpm {
+    int n;
+    float dx;
+    int nthreads;  // 0 → seq_exec(), else omp_exec().threads(nthreads)
+    Particles<f32, 3> pars;
+    HashTable<i32, 3, int> table;
+    Grids<f32, 3, 4> grids;
+    Vector<float> maxVel;
+    int nblocks{0};
+    RefMpm(int n_, float dx_, int nthreads_, int expectedBlocks)
+        : n{n_},
+          dx{dx_},
+          nthreads{nthreads_},
+          pars{(size_t)n_},
+          table{(size_t)expectedBlocks},
+          grids{{{"m", 1}, {"v", 3}, {"rhs", 3}}, dx_, (size_t)expectedBlocks},
+          maxVel{1} {
+      pars.addAttr("m", attrib_e::scalar);
+      pars.addAttr("v", attrib_e::vector);
+      pars.addAttr("F", attrib_e::matrix);
+      pars.addAttr("C", attrib_e::matrix);
+    }
+  };
+
+  template <typename F> void with_policy(int nthreads, F &&f) {
+    if (nthreads <= 0) {
+      auto pol = seq_exec();
+      f(pol, exec_seq);
+    } else {
+      auto pol = omp_exec().threads(nthreads);
+      f(pol, exec_omp);
+    }
+  }
+}  // namespace
+
+extern "C" {
+
+void *zpcref_mpm_create(int n, float dx, int nthreads, int expectedBlocks) {
+  return new RefMpm(n, dx, nthreads, expectedBlocks);
+}
+void zpcref_mpm_destroy(void *h) { delete (RefMpm *)h; }
+
+void zpcref_mpm_set_particles(void *h, const float *x, const float *v, const float *m,
+                              const float *C, const float *F) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(s.pars.attrVector("x").data(), x, sizeof(float) * 3 * s.n);
+  std::memcpy(s.pars.attrVector("v").data(), v, sizeof(float) * 3 * s.n);
+  std::memcpy(s.pars.attrScalar("m").data(), m, sizeof(float) * s.n);
+  std::memcpy(s.pars.attrMatrix("C").data(), C, sizeof(float) * 9 * s.n);
+  std::memcpy(s.pars.attrMatrix("F").data(), F, sizeof(float) * 9 * s.n);
+}
+void zpcref_mpm_get_particles(void *h, float *x, float *v, float *C, float *F) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(x, s.pars.attrVector("x").data(), sizeof(float) * 3 * s.n);
+  std::memcpy(v, s.pars.attrVector("v").data(), sizeof(float) * 3 * s.n);
+  std::memcpy(C, s.pars.attrMatrix("C").data(), sizeof(float) * 9 * s.n);
+  std::memcpy(F, s.pars.attrMatrix("F").data(), sizeof(float) * 9 * s.n);
+}
+
+/// SURVEY §3.1 lines 1-4: CleanSparsity, ComputeSparsity, EnlargeSparsity{0,2}; returns table.size()
+int zpcref_mpm_partition(void *h) {
+  auto &s = *(RefMpm *)h;
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(range(s.table._tableSize), CleanSparsity{tag, s.table});
+    pol(range(s.n), ComputeSparsity{tag, s.dx, 4, s.table, s.pars.attrVector("x")});
+    const int cnt = s.table.size();
+    pol(range(cnt),
+        EnlargeSparsity{tag, s.table, vec<int, 3>{0, 0, 0}, vec<int, 3>{2, 2, 2}});
+  });
+  s.nblocks = s.table.size();
+  if ((size_t)s.nblocks > s.grids.grid(collocated_c).numBlocks())
+    s.grids.grid(collocated_c).resize(s.nblocks);
+  return s.nblocks;
+}
+void zpcref_mpm_get_keys(void *h, int *keys) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(keys, s.table._activeKeys.data(), sizeof(int) * 3 * s.nblocks);
+}
+int zpcref_mpm_table_size(void *h) { return ((RefMpm *)h)->table._tableSize; }
+/// raw table arrays: keys[tableSize*3], indices[tableSize]
+void zpcref_mpm_get_table(void *h, int *keys, int *indices) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(keys, s.table._table.keys.data(), sizeof(int) * 3 * s.table._tableSize);
+  std::memcpy(indices, s.table._table.indices.data(), sizeof(int) * s.table._tableSize);
+}
+
+void zpcref_mpm_clean_grid(void *h) {
+  auto &s = *(RefMpm *)h;
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(Collapse{(size_t)s.nblocks, (size_t)64}, CleanGridBlocks{tag, s.grids});
+  });
+}
+void zpcref_mpm_p2g(void *h, float dt, float E, float nu, float volume) {
+  auto &s = *(RefMpm *)h;
+  FixedCorotatedConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.volume = volume;
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(range(s.n),
+        P2GTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.pars, s.table, s.grids});
+  });
+}
+/// mode 0: ComputeGridBlockVelocity as shipped (v = mv/m + g dt; rhs ignored, GridOp.hpp:71-110).
+/// mode 1: explicit update v = (mv + rhs)/m + g dt, composed as "mv += rhs" then the functor.
+void zpcref_mpm_grid_update(void *h, float dt, float gravity, int mode) {
+  auto &s = *(RefMpm *)h;
+  s.maxVel.setVal(0.f);
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    if (mode == 1) {
+      auto gv = proxy<decltype(tag)::value>(s.grids);
+      pol(Collapse{(size_t)s.nblocks, (size_t)64}, [gv](int b, int c) mutable {
+        auto block = gv[b];
+        for (int d = 0; d != 3; ++d) block(1 + d, c) += block(4 + d, c);
+      });
+    }
+    pol(Collapse{(size_t)s.nblocks, (size_t)64},
+        ComputeGridBlockVelocity{tag, wrapv<transfer_scheme_e::apic>{}, s.grids, dt, gravity,
+                                 s.maxVel.data()});
+  });
+}
+float zpcref_mpm_get_maxvel(void *h) { return ((RefMpm *)h)->maxVel.getVal(); }
+void zpcref_mpm_g2p(void *h, float dt) {
+  auto &s = *(RefMpm *)h;
+  FixedCorotatedConfig model{};
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(range(s.n),
+        G2PTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.grids, s.table, s.pars});
+  });
+}
+/// grid tiles in table numbering: out[nblocks][7][64]
+void zpcref_mpm_get_grid(void *h, float *out) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(out, s.grids.grid(collocated_c).blocks.data(), sizeof(float) * 7 * 64 * s.nblocks);
+}
+
+/// ---- primitives (reference serial / OpenMP policies) ----
+#define ZPCREF_SORT_PAIR(SUFFIX, KT)                                                               \
+  void zpcref_radix_sort_pair_##SUFFIX(int nthreads, const KT *kin, const int *vin, KT *kout,     \
+                                       int *vout, size_t n, int sbit, int ebit) {                 \
+    KT *ki = const_cast<KT *>(kin);                                                                \
+    int *vi = const_cast<int *>(vin);                                                              \
+    with_policy(nthreads, [&](auto &pol, auto) {                                                   \
+      radix_sort_pair(pol, ki, vi, kout, vout, (std::ptrdiff_t)n, sbit, ebit);                     \
+    });                                                                                            \
+  }                                                                                                \
+  void zpcref_radix_sort_##SUFFIX(int nthreads, const KT *kin, KT *kout, size_t n, int sbit,       \
+                                  int ebit) {                                                      \
+    const KT *ke = kin + n;                                                                        \
+    with_policy(nthreads, [&](auto &pol, auto) { radix_sort(pol, kin, ke, kout, sbit, ebit); });   \
+  }
+ZPCREF_SORT_PAIR(u32, uint32_t)
+ZPCREF_SORT_PAIR(i32, int32_t)
+ZPCREF_SORT_PAIR(u64, uint64_t)
+
+#define ZPCREF_SCAN_REDUCE(SUFFIX, T)                                                             \
+  void zpcref_exclusive_scan_sum_##SUFFIX(int nthreads, const T *in, T *out, size_t n) {\
+    const T *e = in + n;\
+    with_policy(nthreads,                                                                          \
+                [&](auto &pol, auto) { exclusive_scan(pol, in, e, out, (T)0, plus<T>{}); });  \
+  }                                                                                                \
+  void zpcref_inclusive_scan_sum_##SUFFIX(int nthreads, const T *in, T *out, size_t n) {\
+    const T *e = in + n;\
+    with_policy(nthreads,                                                                          \
+                [&](auto &pol, auto) { inclusive_scan(pol, in, e, out, plus<T>{}); });        \
+  }                                                                                                \
+  void zpcref_reduce_sum_##SUFFIX(int nthreads, const T *in, T *out, size_t n) {\
+    const T *e = in + n;\
+    with_policy(nthreads,                                                                          \
+                [&](auto &pol, auto) { reduce(pol, in, e, out, (T)0, plus<T>{}); });          \
+  }                                                                                                \
+  void zpcref_reduce_min_##SUFFIX(int nthreads, const T *in, T *out, size_t n) {\
+    const T *e = in + n;\
+    with_policy(nthreads, [&](auto &pol, auto) {                                                   \
+      reduce(pol, in, e, out, detail::deduce_numeric_max<T>(), getmin<T>{});                  \
+    });                                                                                            \
+  }                                                                                                \
+  void zpcref_reduce_max_##SUFFIX(int nthreads, const T *in, T *out, size_t n) {\
+    const T *e = in + n;\
+    with_policy(nthreads, [&](auto &pol, auto) {                                                   \
+      reduce(pol, in, e, out, detail::deduce_numeric_lowest<T>(), getmax<T>{});               \
+    });                                                                                            \
+  }
+ZPCREF_SCAN_REDUCE(i32, int32_t)
+ZPCREF_SCAN_REDUCE(f32, float)
+ZPCREF_SCAN_REDUCE(u32, uint32_t)
+ZPCREF_SCAN_REDUCE(i64, int64_t)
+
+/// ---- per-particle math ----
+void zpcref_svd3(const float *F, float *U, float *S, float *V) {  // column-major 9-vectors
+  math::svd_3d(F[0], F[3], F[6], F[1], F[4], F[7], F[2], F[5], F[8], U[0], U[3], U[6], U[1], U[4],
+               U[7], U[2], U[5], U[8], S[0], S[1], S[2], V[0], V[3], V[6], V[1], V[4], V[7], V[2],
+               V[5], V[8]);
+}
+void zpcref_stress_fixedcorotated(float volume, float E, float nu, const float *F, float *PF) {
+  const auto [mu, lambda] = lame_parameters(E, nu);
+  vec<float, 9> f{}, pf{};
+  for (int d = 0; d != 9; ++d) f[d] = F[d];
+  compute_stress_fixedcorotated(volume, mu, lambda, f, pf);
+  for (int d = 0; d != 9; ++d) PF[d] = pf[d];
+}
+int zpcref_max_threads() { return (int)std::thread::hardware_concurrency(); }
+}
