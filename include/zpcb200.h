@@ -1,0 +1,232 @@
+/* zpcb200 — C ABI of the B200-native (sm_100a) MPM transfer path and the parallel primitives it
+ * rides on.  Drop-in boundary for zenustech/zpc's CUDA backend on this path.
+ *
+ * Conventions (mirroring the reference's own thin C layers):
+ *   - plain pointers, sizes and POD views; no C++/torch types cross this boundary;
+ *   - every entry returns int: 0 = ok, otherwise a cudaError_t value (or ZPCB200_E_* < 0 for misuse)
+ *     — nothing throws (reference: u32 error code out of Cuda::launchKernel, cuda/Cuda.h:81-84,
+ *     latched per context, cuda/Cuda.h:291-312);
+ *   - every entry is asynchronous on the `stream` it is given (reference: pol.getStream(),
+ *     cuda/execution/ExecutionPolicy.cuh:888-890); the library owns no streams, contexts or
+ *     persistent memory;
+ *   - scratch memory follows CUB's two-phase protocol that the reference already uses
+ *     (ExecutionPolicy.cuh:803-812): call with temp == NULL to get *temp_bytes, then call again.
+ *
+ * All pointers are DEVICE pointers unless a name ends in _host.  Paths cited below are relative to
+ * /root/reference/include/zensim/.
+ */
+#ifndef ZPCB200_H
+#define ZPCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *zpc_stream_t; /* cudaStream_t */
+
+#define ZPCB200_OK 0
+#define ZPCB200_E_BADARG (-1)
+#define ZPCB200_E_TEMP_TOO_SMALL (-2)
+#define ZPCB200_E_UNSUPPORTED (-3)
+
+/* ------------------------------------------------------------------------------------------ */
+/* Iterator port — replaces py_interop/GenericIterator.hpp:11-16 (aosoa_iterator_port) 1:1.     */
+/* Element k of the range lives at                                                              */
+/*   base + ((( (idx+k) >> numTileBits) * numChns) << numTileBits | ((idx+k) & tileMask))       */
+/* (GenericIterator.hpp:84-98).  A contiguous pointer is {ptr, 0, 0, 0, 1}.                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct zpc_port {
+  void *base;
+  uint32_t idx, numTileBits, tileMask, numChns;
+} zpc_port;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Parallel primitives — replace the CUB calls under CudaExecutionPolicy                        */
+/* (cuda/execution/ExecutionPolicy.cuh: reduce :649-681, inclusive_scan :552-590,               */
+/*  exclusive_scan :601-632, radix_sort_pair :755-826, radix_sort :828-866).                     */
+/* <T> in {i32,u32,i64,f32}; scans/reductions use the identities the reference's C ABI passes     */
+/* (py_interop/cuda/ExecutionPolicy.cpp:41-90): 0 for sum, numeric max for min, lowest for max.  */
+/* `out` of a reduce is one element on the device.  Ranges are zpc_ports; n = last - first.      */
+/* ------------------------------------------------------------------------------------------ */
+#define ZPCB200_DECL_REDUCE_SCAN(S)                                                              \
+  int zpcb200_reduce_sum_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_t n, \
+                             zpc_stream_t stream);                                               \
+  int zpcb200_reduce_min_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_t n, \
+                             zpc_stream_t stream);                                               \
+  int zpcb200_reduce_max_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_t n, \
+                             zpc_stream_t stream);                                               \
+  int zpcb200_exclusive_scan_sum_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out,  \
+                                     size_t n, zpc_stream_t stream);                             \
+  int zpcb200_inclusive_scan_sum_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out,  \
+                                     size_t n, zpc_stream_t stream);
+ZPCB200_DECL_REDUCE_SCAN(i32)
+ZPCB200_DECL_REDUCE_SCAN(u32)
+ZPCB200_DECL_REDUCE_SCAN(i64)
+ZPCB200_DECL_REDUCE_SCAN(f32)
+
+/* Stable LSD radix sort on bits [sbit, ebit) of the key (ExecutionPolicy.hpp:765-781).  Signed
+ * keys order as signed.  keys_in/vals_in are not modified; out may not alias in.  n <= 2^30. */
+#define ZPCB200_DECL_SORT(S, KT)                                                                 \
+  int zpcb200_radix_sort_pair_##S(void *temp, size_t *temp_bytes, zpc_port keys_in,              \
+                                  zpc_port vals_in, zpc_port keys_out, zpc_port vals_out,        \
+                                  size_t n, int sbit, int ebit, zpc_stream_t stream);            \
+  int zpcb200_radix_sort_##S(void *temp, size_t *temp_bytes, zpc_port keys_in, zpc_port keys_out, \
+                             size_t n, int sbit, int ebit, zpc_stream_t stream);
+ZPCB200_DECL_SORT(u32, uint32_t)
+ZPCB200_DECL_SORT(i32, int32_t)
+ZPCB200_DECL_SORT(u64, uint64_t)
+
+/* ------------------------------------------------------------------------------------------ */
+/* View PODs (non-owning)                                                 */
+/* ------------------------------------------------------------------------------------------ */
+/* ParticlesView<cuda, Particles<f32,3>> — geometry/Structurefree.hpp:242-251,278-283.
+ * AoS per attribute: X,V = vec3 (12 B stride), F,C = column-major vec9 (36 B), M,J,logJp scalars. */
+typedef struct zpc_particles_view {
+  float *M, *X, *V, *Dinv, *J, *F, *C, *logJp;
+  size_t count;
+} zpc_particles_view;
+
+/* HashTableView<cuda, HashTable<i32,3,int>> — container/HashTable.hpp:332-347,487-490.
+ * keys/activeKeys are packed vec3i (12 B); tableSize = next_2pow(expected) * 16 (:70,87-90). */
+typedef struct zpc_hashtable_view {
+  int *keys, *indices, *status; /* table_t */
+  int *activeKeys;
+  int tableSize;
+  int *cnt;
+} zpc_hashtable_view;
+
+/* The collocated grid of GridsView<cuda, Grids<f32,3,4>> — geometry/Structure.hpp:876-880: a
+ * TileVector<f32,64> whose tile b holds block b as [numChannels][64] floats, channels
+ * {m, v(3), rhs(3)} (simulation/mpm/Simulator.cpp:116), cell id (x<<4)|(y<<2)|z (:851-859). */
+typedef struct zpc_grids_view {
+  float *tiles;
+  size_t numBlocks; /* capacity in blocks */
+  int numChannels;  /* 7 */
+  float dx;
+} zpc_grids_view;
+
+/* TileVectorUnnamedView<cuda, TileVector<f32,32>> — container/TileVector.hpp:693-723: AoSoA,
+ * element (chn,i) at base[(i/32*numChannels + chn)*32 + i%32] (:108,768-769).  For particle bins the
+ * channel order is fixed below (Structurefree.hpp:220 "mass, pos, vel, J, F, C, logJp" minus J/logJp). */
+typedef struct zpc_tilevector_view {
+  float *base;
+  size_t size;
+  int numChannels;
+} zpc_tilevector_view;
+enum { ZPC_PB_M = 0, ZPC_PB_X = 1, ZPC_PB_V = 4, ZPC_PB_C = 7, ZPC_PB_F = 16, ZPC_PB_NCH = 25 };
+
+/* FixedCorotatedConfig — physics/ConstitutiveModel.hpp:725-742 */
+typedef struct zpc_fixed_corotated {
+  float rho, volume;
+  int dim;
+  float E, nu;
+} zpc_fixed_corotated;
+
+/* ------------------------------------------------------------------------------------------ */
+/* MPM path                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+/* partition_for_particles / CleanSparsity + ComputeSparsity + EnlargeSparsity{0,2}
+ * (simulation/sparsity/SparsityOp.hpp:41-112, SparsityCompute.tpp:6-24).  x = port over vec3
+ * positions (AoS: {X,0,0,0,3}; AoSoA bin channel: {base+ZPC_PB_X*32, 0, 5, 31, 25}).  Writes keys /
+ * indices / status / activeKeys / *cnt so that the unmodified HashTableView::query (:447-456)
+ * resolves every active block.  Block numbering is DETERMINISTIC here: index = rank of the block key
+ * in lexicographic (x,y,z) order (the reference's is insertion-order and racy).
+ * *overflow (device int, may be NULL) is set to 1 if the table is too small. */
+int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx,
+                            zpc_hashtable_view table, int *overflow, zpc_stream_t stream);
+
+/* CleanGridBlocks (simulation/grid/GridOp.hpp:54-69) over blocks [0, *cnt). */
+int zpcb200_clean_grid(zpc_grids_view grids, const int *cnt, zpc_stream_t stream);
+
+/* P2GTransfer<apic, FixedCorotatedConfig> (simulation/transfer/P2G.hpp:45-127) on the reference's
+ * own AoS Particles layout, any particle order.  One thread per particle, 27x7 float reds. */
+int zpcb200_p2g_apic_fcr(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
+                         float dt, zpc_fixed_corotated model, zpc_stream_t stream);
+
+/* ComputeGridBlockVelocity (GridOp.hpp:71-110): v = mv/m + extf*dt, *maxVelSqr = max |v|^2.
+ * mode 0 = as shipped (rhs ignored); mode 1 = explicit update v = (mv + rhs)/m + extf*dt. */
+int zpcb200_grid_update(zpc_grids_view grids, const int *cnt, float dt, const float extf_host[3],
+                        int mode, float *maxVelSqr, zpc_stream_t stream);
+
+/* G2PTransfer<apic> (simulation/transfer/G2P.hpp:43-84), AoS layout, any order. */
+int zpcb200_g2p_apic(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
+                     float dt, zpc_stream_t stream);
+
+/* ---- binned (block-sorted AoSoA) fast path ------------------------------------------------- */
+/* Bins: particles sorted by home block (the block ComputeSparsity assigns, SparsityOp.hpp:68-79),
+ * stored densely in a 25-channel TileVector<f32,32>; bin b covers particles
+ * [binStart[b], binStart[b+1]) and has home block coordinates binKey[3b..3b+2].  A block with more
+ * than ZPCB200_BIN_MAX particles is split into several bins. */
+#define ZPCB200_BIN_MAX 1024
+typedef struct zpc_bins_view {
+  zpc_tilevector_view pars; /* numChannels == ZPC_PB_NCH */
+  int *binStart;            /* [binCapacity + 1] */
+  int *binKey;              /* [binCapacity * 3] */
+  int *numBins;             /* device scalar */
+  int binCapacity;
+} zpc_bins_view;
+
+/* Sort AoS particles into bins (radix_sort_pair on the block rank + gather into AoSoA).  Requires a
+ * partition built from the same positions.  order_out (may be NULL) receives the permutation:
+ * binned particle i came from AoS particle order_out[i]. */
+int zpcb200_bin_particles(void *temp, size_t *temp_bytes, zpc_particles_view pars,
+                          zpc_hashtable_view table, float dx, zpc_bins_view bins, int *order_out,
+                          zpc_stream_t stream);
+/* Re-bin an already binned set in place after particles moved (src -> dst, both AoSoA). */
+int zpcb200_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src,
+                            zpc_hashtable_view table, float dx, zpc_bins_view dst,
+                            zpc_stream_t stream);
+/* Copy binned AoSoA particles back to the AoS view, slot i -> pars[i]. */
+int zpcb200_unbin_particles(zpc_bins_view bins, zpc_particles_view pars, zpc_stream_t stream);
+
+/* Same functors as above on the binned layout: one CTA per bin, the 2x2x2 block arena staged in
+ * shared memory, cell-grouped register accumulation, bulk reduce-add of whole grid tiles. */
+int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,
+                                float dt, zpc_fixed_corotated model, zpc_stream_t stream);
+int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,
+                            float dt, zpc_stream_t stream);
+
+/* ---- multi-GPU one-ring halo; no reference counterpart ----------------------- */
+/* pack: copy tiles listed in blockIds[0..n) into a contiguous buffer (nch channels from chn0);
+ * unpack_add / unpack_set: add / overwrite them back.  The exchange itself is NCCL send/recv (host). */
+int zpcb200_halo_pack(zpc_grids_view grids, const int *blockIds, int n, int chn0, int nch,
+                      float *buf, zpc_stream_t stream);
+int zpcb200_halo_unpack_add(zpc_grids_view grids, const int *blockIds, int n, int chn0, int nch,
+                            const float *buf, zpc_stream_t stream);
+int zpcb200_halo_unpack_set(zpc_grids_view grids, const int *blockIds, int n, int chn0, int nch,
+                            const float *buf, zpc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Reference-style object ABI (py_interop/cuda/ExecutionPolicy.cpp:8-9, 39-134): an opaque policy   */
+/* carrying {device, stream, sync} and primitives named <op>__b200_<T>_1 taking iterator ports.   */
+/* Scratch comes from the stream-ordered pool (cudaMallocAsync), like ExecutionPolicy.cuh:806-815. */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct zpcb200_policy zpcb200_policy;
+zpcb200_policy *policy__b200(void);
+void del_policy__b200(zpcb200_policy *);
+void policy_set__b200(zpcb200_policy *, int device, zpc_stream_t stream, int sync);
+int policy_last_error__b200(const zpcb200_policy *);
+#define ZPCB200_DECL_POLICY_PRIMS(T, CT)                                                          \
+  void reduce_sum__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);   \
+  void reduce_min__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);   \
+  void reduce_max__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);   \
+  void exclusive_scan_sum__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last,          \
+                                        zpc_port out);                                            \
+  void inclusive_scan_sum__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last,          \
+                                        zpc_port out);
+ZPCB200_DECL_POLICY_PRIMS(int, int32_t)
+ZPCB200_DECL_POLICY_PRIMS(float, float)
+void radix_sort__b200_int_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);
+void radix_sort_pair__b200_int_1(zpcb200_policy *, zpc_port keysIn, zpc_port valsIn,
+                                 zpc_port keysOut, zpc_port valsOut, size_t count);
+
+/* library info */
+const char *zpcb200_version(void);
+int zpcb200_kernel_launch_count(void); /* launches issued by this library since load (bench.py) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,91 @@
+"""Generates tests/golden/*.npz by executing the REFERENCE itself (oracle/_ref/libzpcref.so, built by
+oracle/Makefile from /root/reference).  Run in the build container only:  python tests/golden/make_golden.py
+The fixtures pin the oracle (tests/test_golden.py) and, through it, the CUDA path on the GPU box, where
+neither /root/reference nor (necessarily) oracle/_ref exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle.pyoracle import Ref  # noqa: E402
+from zpc_b200 import synth  # noqa: E402
+
+
+def mpm_case(ref, name, s, G, mode, **kw):
+    P = synth.elastic_cube(s, G, **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    h = ref.mpm(n, dx, 0)
+    h.set_particles(P)
+    nb = h.partition()
+    tab = h.table()
+    h.clean_grid()
+    h.p2g(synth.DT, synth.MODEL["E"], synth.MODEL["nu"], P["volume"])
+    g1 = h.grid()
+    mx = h.grid_update(synth.DT, synth.GRAVITY, mode)
+    g2 = h.grid()
+    h.g2p(synth.DT)
+    out = h.get_particles()
+    h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), s=s, G=G, mode=mode, kw=repr(sorted(kw.items())),
+                        nblocks=nb, active_keys=tab["active_keys"], table_keys=tab["keys"],
+                        table_indices=tab["indices"], grid_p2g=g1, grid_upd=g2, max_vel_sqr=mx,
+                        x=out["x"], v=out["v"], C=out["C"], F=out["F"])
+    print(name, "n", n, "blocks", nb, "maxvel2", mx)
+
+
+def prims_case(ref):
+    rs = np.random.RandomState(12345)
+    out = {}
+    for n in (0, 1, 7, 1000, 4096, 10007):
+        ku = rs.randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+        ki = ku.view(np.int32)
+        k64 = rs.randint(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rs.randint(0, 2, size=n).astype(np.uint64)
+        v = np.arange(n, dtype=np.int32)
+        for kind, k in (("u32", ku), ("i32", ki), ("u64", k64)):
+            ko, vo = ref.radix_sort_pair(kind, k, v)
+            out["sortpair_%s_%d_k" % (kind, n)] = ko
+            out["sortpair_%s_%d_v" % (kind, n)] = vo
+        ko, vo = ref.radix_sort_pair("u32", ku, v, 4, 20)
+        out["sortpair_u32_%d_bits4_20_k" % n] = ko
+        out["sortpair_u32_%d_bits4_20_v" % n] = vo
+        a = rs.randint(-1000, 1000, size=n).astype(np.int32)
+        out["in_i32_%d" % n] = a
+        out["in_u32_%d" % n] = ku
+        out["in_u64_%d" % n] = k64
+        out["exscan_i32_%d" % n] = ref.scan("exclusive", "i32", a)
+        out["inscan_i32_%d" % n] = ref.scan("inclusive", "i32", a)
+        for op in ("sum", "min", "max"):
+            out["reduce_%s_i32_%d" % (op, n)] = np.array([ref.reduce(op, "i32", a)])
+    np.savez_compressed(os.path.join(HERE, "prims.npz"), **out)
+    print("prims", len(out), "arrays")
+
+
+def svd_case(ref):
+    rs = np.random.RandomState(3)
+    Fs = np.concatenate([
+        (np.eye(3).reshape(1, 9) + rs.uniform(-0.3, 0.3, (200, 9))).astype(np.float32),
+        rs.uniform(-2, 2, (50, 9)).astype(np.float32),
+        np.eye(3, dtype=np.float32).reshape(1, 9),
+        np.diag([2.0, 0.5, 1.0]).astype(np.float32).reshape(1, 9),
+        np.zeros((1, 9), np.float32),
+    ])
+    U = np.empty_like(Fs); V = np.empty_like(Fs); S = np.empty((Fs.shape[0], 3), np.float32)
+    PF = np.empty_like(Fs)
+    for i, F in enumerate(Fs):
+        U[i], S[i], V[i] = ref.svd3(F)
+        PF[i] = ref.stress_fixedcorotated(1.0e-6, 5.0e4, 0.4, F)
+    np.savez_compressed(os.path.join(HERE, "svd.npz"), F=Fs, U=U, S=S, V=V, PF=PF)
+    print("svd", Fs.shape[0])
+
+
+if __name__ == "__main__":
+    r = Ref()
+    mpm_case(r, "mpm_cube6_mode0", 6, 32, 0, jitter_F=0.05, jitter_C=0.5, shuffle_seed=11)
+    mpm_case(r, "mpm_cube6_mode1", 6, 32, 1, jitter_F=0.05, jitter_C=0.5, shuffle_seed=11)
+    mpm_case(r, "mpm_cube8_rest", 8, 32, 1)
+    mpm_case(r, "mpm_cube5_neg", 5, 16, 1, jitter_F=0.02, jitter_C=0.2, origin_cells=-9)
+    prims_case(r)
+    svd_case(r)

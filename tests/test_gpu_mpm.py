@@ -1,0 +1,289 @@
+"""CUDA MPM path (through the C ABI) against the oracle and the reference-generated golden vectors."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from zpc_b200 import synth  # noqa: E402
+from tests.parity import check_channels, grid_by_key  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+E, NU = synth.MODEL["E"], synth.MODEL["nu"]
+
+
+def _copy(P):
+    return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in P.items()}
+
+
+def host_table(table):
+    nb = table.size()
+    return dict(keys=table.keys.cpu().numpy(), indices=table.indices.cpu().numpy(), table_size=table.table_size,
+                nblocks=nb, active_keys=table.active_keys[:nb].cpu().numpy())
+
+
+def build_partition(P, expected=None):
+    from zpc_b200 import api
+    n = P["x"].shape[0]
+    pars = api.Particles(P)
+    table = api.HashTable(expected or max(n // 8, 64))
+    api.partition_for_particles(api.vec3_port(pars.x), n, P["dx"], table)
+    torch.cuda.synchronize()
+    assert table.overflow.item() == 0
+    return pars, table
+
+
+CASES = {
+    "cube8": dict(s=8, G=32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=11),
+    "cube12_sorted": dict(s=12, G=32, jitter_F=0.03, jitter_C=0.3),
+    "cube7_negative_coords": dict(s=7, G=16, jitter_F=0.05, jitter_C=0.5, shuffle_seed=3, origin_cells=-13),
+    "cube16_rest": dict(s=16, G=64),
+}
+
+
+def make(case):
+    kw = dict(CASES[case])
+    return synth.elastic_cube(kw.pop("s"), kw.pop("G"), **kw)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_partition_matches_oracle(oracle, case):
+    P = make(case)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    tab_o = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    ko = tab_o["active_keys"]
+    order = np.lexsort((ko[:, 2], ko[:, 1], ko[:, 0]))
+    assert ht["nblocks"] == tab_o["nblocks"]
+    # same active block set; our numbering is deterministic: index == lexicographic rank
+    assert np.array_equal(ht["active_keys"], ko[order])
+    # the table is readable by the reference's query (oracle restatement of HashTable.hpp:447-456): bijection onto [0,cnt)
+    got = np.array([oracle.table_query(k, ht) for k in ht["active_keys"]])
+    assert np.array_equal(got, np.arange(ht["nblocks"]))
+    assert oracle.table_query(np.array([999, 999, 999], np.int32), ht) == -1
+    # untouched slots keep the CleanSparsity sentinels
+    free = ht["indices"] == -1
+    assert free.sum() == ht["table_size"] - ht["nblocks"]
+    assert (ht["keys"][free] == np.iinfo(np.int32).max).all() and (table.status.cpu().numpy() == -1).all()
+
+
+def test_partition_empty_and_aosoa_port(oracle):
+    from zpc_b200 import api
+    table = api.HashTable(64)
+    x = torch.zeros(0, 3, device="cuda")
+    api.partition_for_particles(api.zpc_port(x.data_ptr(), 0, 0, 0, 3), 0, 0.1, table)
+    assert table.size() == 0
+    P = make("cube8")
+    n = P["x"].shape[0]
+    tv = api.TileVector(n, api.PB_NCH)
+    tv.set_channel(api.PB_X, torch.from_numpy(P["x"]).cuda())
+    t2 = api.HashTable(max(n // 8, 64))
+    api.partition_for_particles(tv.port(api.PB_X), n, P["dx"], t2)
+    _, t1 = build_partition(P)
+    assert t1.size() == t2.size() and torch.equal(t1.active_keys[: t1.size()], t2.active_keys[: t2.size()])
+
+
+def run_oracle_on_table(oracle, P, ht, mode):
+    dx = P["dx"]
+    g1 = oracle.p2g(P, ht, dx, synth.DT, E, NU, P["volume"])
+    g2 = g1.copy()
+    mx = oracle.grid_update(g2, synth.DT, (0.0, synth.GRAVITY, 0.0), mode)
+    Po = _copy(P)
+    oracle.g2p(Po, ht, g2, dx, synth.DT)
+    return g1, g2, mx, Po
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", list(CASES))
+def test_aos_path_matches_oracle(oracle, case, mode):
+    """drop-in path: reference Particles layout, any order (P2G.hpp / GridOp.hpp / G2P.hpp)."""
+    from zpc_b200 import api
+    P = make(case)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    grids = api.Grids(dx, ht["nblocks"] + 3)
+    grids.tiles.fill_(123.0)                                   # CleanGridBlocks must clear exactly cnt blocks
+    api.clean_grid_blocks(grids, table)
+    assert float(grids.tiles[: ht["nblocks"]].abs().max()) == 0.0 and float(grids.tiles[ht["nblocks"]:].min()) == 123.0
+    model = api.model_fcr(P["volume"], E, NU)
+    api.p2g_transfer(pars, table, grids, synth.DT, model)
+    g1 = grids.tiles[: ht["nblocks"]].cpu().numpy()
+    o1, o2, omx, Po = run_oracle_on_table(oracle, P, ht, mode)
+    check_channels(g1, o1, 1, "p2g")
+    # mass conservation (size independent)
+    assert abs(g1[:, 0].sum(dtype=np.float64) / P["m"].sum(dtype=np.float64) - 1) < 1e-5
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), mode, mx)
+    g2 = grids.tiles[: ht["nblocks"]].cpu().numpy()
+    check_channels(g2[:, 1:4], o2[:, 1:4], 1, "grid velocity")
+    assert abs(mx.item() - omx) <= 1e-5 * omx
+    api.g2p_transfer(pars, table, grids, synth.DT)
+    out = pars.to_host()
+    for k in "xvCF":
+        check_channels(out[k], Po[k], 1, "g2p " + k)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_binned_path_matches_oracle(oracle, case):
+    """fast path: bin -> P2G (smem arena, bulk reduce-add) -> update -> G2P (TMA staged) -> unbin."""
+    from zpc_b200 import api
+    P = make(case)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    bins = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    api.bin_particles(pars, table, dx, bins, order)
+    torch.cuda.synchronize()
+    perm = order.cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(n))                        # a permutation
+    nbins = bins.num_bins.item()
+    bs = bins.bin_start[: nbins + 1].cpu().numpy()
+    assert bs[0] == 0 and bs[-1] == n and (np.diff(bs) > 0).all() and (np.diff(bs) <= api.BIN_MAX).all()
+    # binned attributes are the permuted inputs, bit for bit, and every particle sits in its home block's bin
+    for k in "xvCF":
+        assert np.array_equal(bins.attr(k).cpu().numpy(), P[k][perm]), k
+    bk = bins.bin_key[:nbins].cpu().numpy()
+    home = np.empty((n, 3), np.int32)
+    import ctypes as C
+    for i in range(0, n, max(n // 200, 1)):
+        b = np.zeros(3, np.int32)
+        oracle.lib.zo_block_of_particle(P["x"][perm[i]].ctypes.data_as(C.c_void_p), C.c_float(dx), b.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(bk[np.searchsorted(bs, i, side="right") - 1], b)
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    model = api.model_fcr(P["volume"], E, NU)
+    api.p2g_transfer(bins, table, grids, synth.DT, model)
+    g1 = grids.tiles.cpu().numpy()
+    o1, o2, omx, Po = run_oracle_on_table(oracle, P, ht, 1)
+    check_channels(g1, o1, 1, "binned p2g")
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    api.g2p_transfer(bins, table, grids, synth.DT)
+    for k in "xvCF":
+        check_channels(bins.attr(k).cpu().numpy(), Po[k][perm], 1, "binned g2p " + k)
+    # unbin restores slot order
+    back = api.Particles(P)
+    api.unbin_particles(bins, back)
+    assert np.array_equal(back.x.cpu().numpy(), bins.attr("x").cpu().numpy())
+
+
+def test_binned_multistep_with_strays_matches_oracle(oracle):
+    """5 substeps without re-binning (particles drift across cells and blocks -> stray path + arena margin),
+    then a re-bin, then 2 more; the oracle runs the reference's composed substep on the same particles."""
+    from zpc_b200.solver import MpmSolver
+    P = synth.elastic_cube(10, 32, jitter_F=0.03, jitter_C=0.3, seed=5)
+    P["v"][:] = P["v"] * 8.0                      # ~0.26 cell per step: plenty of cell and block crossings
+    n0 = P["m"].shape[0]
+    P["m"] = (P["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)   # unique masses = particle identity
+    assert np.unique(P["m"]).size == n0
+    dx = P["dx"]
+    sol = MpmSolver(P, dx, P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, layout="binned", rebin_every=5)
+    perm = sol.order.cpu().numpy()
+    Po = {k: (np.ascontiguousarray(v[perm]) if isinstance(v, np.ndarray) else v) for k, v in P.items()}
+    for step in range(7):
+        sol.substep()
+        oracle.substep(Po, dx, synth.DT * 10, E, NU, P["volume"], synth.GRAVITY, 1)
+    torch.cuda.synchronize()
+    got = sol.particles_host()
+    # the re-bin permuted the slots again: match particles through their (unique, never modified) mass
+    def canon(Q):
+        o = np.argsort(Q["m"], kind="stable")
+        return {k: Q[k][o] for k in "xvCF"}
+    a, b = canon(got), canon(Po)
+    for k in "xvCF":
+        check_channels(a[k], b[k], 1, "multistep " + k, rtol=5e-5, strict_frac=0.95)
+
+
+def test_aos_multistep_matches_oracle(oracle):
+    from zpc_b200.solver import MpmSolver
+    P = synth.elastic_cube(8, 32, jitter_F=0.03, jitter_C=0.3, seed=6, shuffle_seed=2)
+    sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="aos")
+    Po = _copy(P)
+    for _ in range(3):
+        sol.substep()
+        oracle.substep(Po, P["dx"], synth.DT, E, NU, P["volume"], synth.GRAVITY, 1)
+    got = sol.particles_host()
+    for k in "xvCF":
+        check_channels(got[k], Po[k], 1, "aos multistep " + k, rtol=3e-5)
+
+
+@pytest.mark.parametrize("name", ["mpm_cube6_mode0", "mpm_cube6_mode1", "mpm_cube8_rest", "mpm_cube5_neg"])
+@pytest.mark.parametrize("layout", ["aos", "binned"])
+def test_against_reference_golden(name, layout):
+    """golden vectors produced by executing the reference (tests/golden/make_golden.py); compared by block key."""
+    from zpc_b200 import api
+    z = np.load(os.path.join(G, name + ".npz"))
+    kw = dict(ast.literal_eval(str(z["kw"])))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **kw)
+    n, dx, mode = P["x"].shape[0], P["dx"], int(z["mode"])
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    kr, g1r = grid_by_key(z["active_keys"], z["grid_p2g"])
+    _, g2r = grid_by_key(z["active_keys"], z["grid_upd"])
+    assert np.array_equal(ht["active_keys"], kr)              # ours are already in key order
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    model = api.model_fcr(P["volume"], E, NU)
+    perm = np.arange(n)
+    src = pars
+    if layout == "binned":
+        src = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
+        order = torch.empty(n, dtype=torch.int32, device="cuda")
+        api.bin_particles(pars, table, dx, src, order)
+        perm = order.cpu().numpy()
+    api.p2g_transfer(src, table, grids, synth.DT, model)
+    check_channels(grids.tiles.cpu().numpy(), g1r, 1, "golden p2g")
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), mode, mx)
+    check_channels(grids.tiles.cpu().numpy()[:, 1:4], g2r[:, 1:4], 1, "golden grid v")
+    assert abs(mx.item() - float(z["max_vel_sqr"])) <= 1e-5 * float(z["max_vel_sqr"])
+    api.g2p_transfer(src, table, grids, synth.DT)
+    out = {k: src.attr(k).cpu().numpy() for k in "xvCF"} if layout == "binned" else pars.to_host()
+    for k in "xvCF":
+        check_channels(out[k], z[k][perm], 1, "golden g2p " + k)
+
+
+def test_full_size_properties_c2():
+    """8 M particles (BASELINE configs[1]): size-independent checks — mass and momentum conservation through
+    P2G, binned == AoS grid, G2P of a uniform velocity field returns it, run-to-run determinism of the binned P2G."""
+    from zpc_b200 import api
+    P = synth.config("C2")
+    n, dx = P["x"].shape[0], P["dx"]
+    pars = api.Particles(P)
+    table = api.HashTable(max(n // 256, 1024))
+    api.partition_for_particles(api.vec3_port(pars.x), n, dx, table)
+    nb = table.size()
+    assert table.overflow.item() == 0 and 15625 <= nb <= 20000
+    grids = api.Grids(dx, nb)
+    model = api.model_fcr(P["volume"], E, NU)
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(pars, table, grids, synth.DT, model)
+    g_aos = grids.tiles.clone()
+    M = float(pars.m.double().sum())
+    assert abs(float(g_aos[:, 0].double().sum()) / M - 1) < 1e-5
+    mom = g_aos[:, 1:4].double().sum(dim=(0, 2))
+    assert abs(float(mom[1]) / (-M) - 1) < 1e-5 and abs(float(mom[0])) < 1e-5 * M and abs(float(mom[2])) < 1e-5 * M
+    bins = api.ParticleBins(n, 2 * nb)
+    api.bin_particles(pars, table, dx, bins)
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(bins, table, grids, synth.DT, model)
+    g_bin = grids.tiles.clone()
+    scale = g_aos.abs().amax(dim=(0, 2), keepdim=True).clamp_min(1e-30)
+    assert float(((g_bin - g_aos).abs() / scale).max()) < 1e-5
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(bins, table, grids, synth.DT, model)
+    # per-CTA sums are deterministic; only the order of the <= 8 bulk reductions per tile varies
+    assert float(((grids.tiles - g_bin).abs() / scale).max()) < 1e-6
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, 0.0, 0.0), 1, mx)
+    assert abs(mx.item() - 1.0) < 1e-4                               # |v|^2 of the uniform (0,-1,0) field
+    api.g2p_transfer(bins, table, grids, synth.DT)
+    v = bins.attr("v")
+    assert float((v - torch.tensor([0.0, -1.0, 0.0], device="cuda")).abs().max()) < 1e-4
+    assert float(bins.attr("C").abs().max()) < 1e-1 / dx * 1e-3      # affine part of a uniform field vanishes

@@ -1,0 +1,78 @@
+"""Oracle against the reference itself (oracle/_ref/libzpcref.so) on fresh seeded inputs, larger than the
+committed golden vectors, and against the reference's OpenMP policy.  Skipped where the reference library
+was not built (it needs /root/reference at build time)."""
+import numpy as np
+import pytest
+
+from zpc_b200 import synth
+from tests.parity import check_channels, grid_by_key
+
+
+def _copy(P):
+    return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in P.items()}
+
+
+@pytest.mark.parametrize("seed,s,G,origin", [(1, 10, 32, 7), (2, 7, 16, -11)])
+def test_substep_bit_exact_vs_reference_seq(oracle, ref, seed, s, G, origin):
+    P = synth.elastic_cube(s, G, seed=seed, jitter_F=0.08, jitter_C=1.0, shuffle_seed=seed + 5, origin_cells=origin)
+    n, dx = P["x"].shape[0], P["dx"]
+    h = ref.mpm(n, dx, 0)
+    h.set_particles(P)
+    nb = h.partition()
+    tab_r = h.table()
+    tab_o = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    assert nb == tab_o["nblocks"] and np.array_equal(tab_r["active_keys"], tab_o["active_keys"])
+    assert np.array_equal(tab_r["keys"], tab_o["keys"]) and np.array_equal(tab_r["indices"], tab_o["indices"])
+    h.clean_grid()
+    h.p2g(synth.DT, 5e4, 0.4, P["volume"])
+    g_o = oracle.p2g(P, tab_o, dx, synth.DT, 5e4, 0.4, P["volume"])
+    assert np.array_equal(h.grid(), g_o)
+    for mode in (1,):
+        mx_r = h.grid_update(synth.DT, synth.GRAVITY, mode)
+        mx_o = oracle.grid_update(g_o, synth.DT, (0, synth.GRAVITY, 0), mode)
+        assert np.array_equal(h.grid(), g_o) and mx_r == mx_o
+    h.g2p(synth.DT)
+    Po = _copy(P)
+    oracle.g2p(Po, tab_o, g_o, dx, synth.DT)
+    Pr = h.get_particles()
+    h.close()
+    for k in "xvCF":
+        assert np.array_equal(Pr[k], Po[k]), k
+
+
+def test_reference_openmp_agrees_within_tolerance(oracle, ref):
+    """The reference's own parallel path re-orders the float atomics and renumbers blocks: compare by block
+    key with the fp32 tolerance — this is the rule the GPU tests apply."""
+    P = synth.elastic_cube(9, 32, seed=3, jitter_F=0.05, jitter_C=0.5, shuffle_seed=8)
+    n, dx = P["x"].shape[0], P["dx"]
+    h = ref.mpm(n, dx, 4)
+    h.set_particles(P)
+    h.partition()
+    keys_r = h.keys()
+    h.clean_grid()
+    h.p2g(synth.DT, 5e4, 0.4, P["volume"])
+    kr, gr = grid_by_key(keys_r, h.grid())
+    tab_o = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    ko, go = grid_by_key(tab_o["active_keys"], oracle.p2g(P, tab_o, dx, synth.DT, 5e4, 0.4, P["volume"]))
+    h.close()
+    assert np.array_equal(kr, ko)
+    check_channels(gr, go, 1, "omp p2g")
+
+
+@pytest.mark.parametrize("nthreads", [0, 4])
+def test_primitives_vs_reference(oracle, ref, nthreads):
+    rs = np.random.RandomState(9)
+    for n in (0, 1, 100, 70001):
+        k = rs.randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+        v = np.arange(n, dtype=np.int32)
+        for kind, kk in (("u32", k), ("i32", k.view(np.int32))):
+            a, b = oracle.radix_sort_pair(kind, kk, v), ref.radix_sort_pair(kind, kk, v, nthreads=nthreads)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        a, b = oracle.radix_sort_pair("u32", k, v, 3, 17), ref.radix_sort_pair("u32", k, v, 3, 17, nthreads=nthreads)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        x = rs.randint(-99, 99, size=n).astype(np.int32)
+        if n:
+            assert np.array_equal(oracle.scan("exclusive", "i32", x), ref.scan("exclusive", "i32", x, nthreads))
+            assert np.array_equal(oracle.scan("inclusive", "i32", x), ref.scan("inclusive", "i32", x, nthreads))
+        for op in ("sum", "min", "max"):
+            assert oracle.reduce(op, "i32", x) == ref.reduce(op, "i32", x, nthreads)

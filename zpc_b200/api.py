@@ -1,0 +1,383 @@
+"""Host-side mirror of the reference interface for the MPM transfer path, over the C ABI in
+include/zpcb200.h (ctypes).  torch is used for device memory and streams only.
+
+Mirrors (reference paths relative to /root/reference/include/zensim/):
+  CudaExecutionPolicy  <- cuda/execution/ExecutionPolicy.cuh:362-912 (reduce / *_scan / radix_sort(_pair),
+                          chained setters device().stream().sync(), sync defaults to True)
+  HashTable            <- container/HashTable.hpp:15-206        (keys/indices/status/_activeKeys/_cnt)
+  Grids                <- geometry/Structure.hpp:140-260        (collocated TileVector<f32,64>, {m,v,rhs})
+  Particles            <- geometry/Structurefree.hpp:22-224     (AoS per attribute)
+  TileVector           <- container/TileVector.hpp:14-561       (AoSoA, length-32 tiles)
+  partition_for_particles, CleanGridBlocks, P2GTransfer, ComputeGridBlockVelocity, G2PTransfer
+                       <- simulation/{sparsity,grid,transfer}/*.hpp as free functions taking a policy.
+There is no CPU fallback: a missing libzpcb200.so or a missing GPU raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libzpcb200.so")
+
+BIN_MAX = 1024
+PB_M, PB_X, PB_V, PB_C, PB_F, PB_NCH = 0, 1, 4, 7, 16, 25
+
+
+class ZpcError(RuntimeError):
+    pass
+
+
+class zpc_port(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("idx", C.c_uint32), ("numTileBits", C.c_uint32),
+                ("tileMask", C.c_uint32), ("numChns", C.c_uint32)]
+
+
+class zpc_particles_view(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("M", "X", "V", "Dinv", "J", "F", "C", "logJp")] + [("count", C.c_size_t)]
+
+
+class zpc_hashtable_view(C.Structure):
+    _fields_ = [("keys", C.c_void_p), ("indices", C.c_void_p), ("status", C.c_void_p),
+                ("activeKeys", C.c_void_p), ("tableSize", C.c_int), ("cnt", C.c_void_p)]
+
+
+class zpc_grids_view(C.Structure):
+    _fields_ = [("tiles", C.c_void_p), ("numBlocks", C.c_size_t), ("numChannels", C.c_int), ("dx", C.c_float)]
+
+
+class zpc_tilevector_view(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("size", C.c_size_t), ("numChannels", C.c_int)]
+
+
+class zpc_fixed_corotated(C.Structure):
+    _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("E", C.c_float), ("nu", C.c_float)]
+
+
+class zpc_bins_view(C.Structure):
+    _fields_ = [("pars", zpc_tilevector_view), ("binStart", C.c_void_p), ("binKey", C.c_void_p),
+                ("numBins", C.c_void_p), ("binCapacity", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """The C-ABI library.  Fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZpcError("libzpcb200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(or python zpc_b200/build.py); there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.zpcb200_version.restype = C.c_char_p
+        _lib.policy__b200.restype = C.c_void_p
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise ZpcError("%s failed with code %d" % (what, rc))
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def port(t, idx=0):
+    """Iterator port over a contiguous 1-D device tensor (GenericIterator.hpp: aos, numTileBits 0)."""
+    if t is None:
+        return zpc_port(None, 0, 0, 0, 1)
+    assert t.is_cuda and t.is_contiguous()
+    return zpc_port(t.data_ptr(), idx, 0, 0, 1)
+
+
+def vec3_port(x):
+    """Port over an AoS [N,3] float tensor seen as vec3 elements."""
+    assert x.is_cuda and x.is_contiguous() and x.shape[-1] == 3
+    return zpc_port(x.data_ptr(), 0, 0, 0, 3)
+
+
+_SUFFIX = {torch.int32: "i32", torch.float32: "f32", torch.int64: "i64", torch.uint32: "u32",
+           torch.uint64: "u64"}
+
+
+class TileVector:
+    """AoSoA container (TileVector.hpp:108): element (chn,i) at base[(i//L*nch + chn)*L + i%L]."""
+
+    def __init__(self, size, num_channels, L=32, device="cuda", dtype=torch.float32):
+        self.size, self.nch, self.L = int(size), int(num_channels), L
+        ntiles = (self.size + L - 1) // L
+        self.data = torch.zeros(max(ntiles, 1) * self.nch * L, dtype=dtype, device=device)
+
+    def view(self):
+        return zpc_tilevector_view(self.data.data_ptr(), self.size, self.nch)
+
+    def port(self, chn, idx=0):
+        """get_iterator_1__tv_<T>_<L>(v, id, chnOffset) (py_interop/TileVectorInstantiations.cpp:24-120)"""
+        L = self.L
+        bits = L.bit_length() - 1
+        return zpc_port(self.data.data_ptr() + chn * L * self.data.element_size(), idx, bits, L - 1, self.nch)
+
+    def channel(self, chn, width=1):
+        """host-side gather of channels [chn, chn+width) as a [size, width] tensor (for tests)."""
+        L = self.L
+        t = self.data.view(-1, self.nch, L)[:, chn:chn + width, :]          # [tiles, width, L]
+        return t.permute(0, 2, 1).reshape(-1, width)[: self.size].contiguous()
+
+    def set_channel(self, chn, values):
+        L = self.L
+        values = values.reshape(self.size, -1)
+        width = values.shape[1]
+        ntiles = self.data.numel() // (self.nch * L)
+        pad = torch.zeros(ntiles * L, width, dtype=self.data.dtype, device=self.data.device)
+        pad[: self.size] = values
+        self.data.view(ntiles, self.nch, L)[:, chn:chn + width, :] = pad.view(ntiles, L, width).permute(0, 2, 1)
+
+
+class CudaExecutionPolicy:
+    """cuda_exec(): reduce / scans / radix sorts on B200.  Inputs are contiguous device tensors or
+    (TileVector, channel) pairs; outputs likewise.  Scratch is cached per policy."""
+
+    def __init__(self):
+        self._device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self._stream = None
+        self._sync = True
+        self._scratch = None
+
+    def device(self, i):
+        self._device = int(i)
+        return self
+
+    def stream(self, s):
+        self._stream = s
+        return self
+
+    def sync(self, b):
+        self._sync = bool(b)
+        return self
+
+    # -- helpers
+    def _tmp(self, nbytes):
+        if self._scratch is None or self._scratch.numel() < nbytes:
+            self._scratch = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device="cuda:%d" % self._device)
+        return self._scratch
+
+    @staticmethod
+    def _as_port(a):
+        if isinstance(a, tuple):
+            tv, chn = a
+            return tv.port(chn), tv.data.dtype, tv.size
+        return port(a), a.dtype, a.numel()
+
+    def _two_phase(self, fn, *args):
+        nbytes = C.c_size_t(0)
+        st = _stream_ptr(self._stream)
+        _check(fn(None, C.byref(nbytes), *args, st), fn.__name__ + "(size)")
+        tmp = self._tmp(nbytes.value)
+        cap = C.c_size_t(tmp.numel())
+        _check(fn(C.c_void_p(tmp.data_ptr()), C.byref(cap), *args, st), fn.__name__)
+        if self._sync:
+            (self._stream or torch.cuda.current_stream()).synchronize()
+
+    # -- primitives (ExecutionPolicy.cuh:552-866)
+    def reduce(self, src, out, op="sum"):
+        p, dt, n = self._as_port(src)
+        po, _, _ = self._as_port(out)
+        fn = getattr(lib(), "zpcb200_reduce_%s_%s" % (op, _SUFFIX[dt]))
+        self._two_phase(fn, p, po, C.c_size_t(n))
+
+    def exclusive_scan(self, src, out):
+        p, dt, n = self._as_port(src)
+        po, _, _ = self._as_port(out)
+        self._two_phase(getattr(lib(), "zpcb200_exclusive_scan_sum_" + _SUFFIX[dt]), p, po, C.c_size_t(n))
+
+    def inclusive_scan(self, src, out):
+        p, dt, n = self._as_port(src)
+        po, _, _ = self._as_port(out)
+        self._two_phase(getattr(lib(), "zpcb200_inclusive_scan_sum_" + _SUFFIX[dt]), p, po, C.c_size_t(n))
+
+    def radix_sort_pair(self, keys_in, vals_in, keys_out, vals_out, count=None, sbit=0, ebit=None, kind=None):
+        pk, dt, n = self._as_port(keys_in)
+        pv, _, _ = self._as_port(vals_in)
+        pko, _, _ = self._as_port(keys_out)
+        pvo, _, _ = self._as_port(vals_out)
+        kind = kind or _SUFFIX[dt]
+        n = n if count is None else count
+        ebit = {"u32": 32, "i32": 32, "u64": 64}[kind] if ebit is None else ebit
+        self._two_phase(getattr(lib(), "zpcb200_radix_sort_pair_" + kind), pk, pv, pko, pvo, C.c_size_t(n),
+                        C.c_int(sbit), C.c_int(ebit))
+
+    def radix_sort(self, keys_in, keys_out, sbit=0, ebit=None, kind=None):
+        pk, dt, n = self._as_port(keys_in)
+        pko, _, _ = self._as_port(keys_out)
+        kind = kind or _SUFFIX[dt]
+        ebit = {"u32": 32, "i32": 32, "u64": 64}[kind] if ebit is None else ebit
+        self._two_phase(getattr(lib(), "zpcb200_radix_sort_" + kind), pk, pko, C.c_size_t(n), C.c_int(sbit),
+                        C.c_int(ebit))
+
+
+def cuda_exec():
+    return CudaExecutionPolicy()
+
+
+def next_2pow(n):
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+class HashTable:
+    """HashTable<i32,3,int>: tableSize = next_2pow(expected) * 16 (HashTable.hpp:70,87-90)."""
+
+    def __init__(self, expected_entries, device="cuda"):
+        self.table_size = next_2pow(int(expected_entries)) * 16
+        ts = self.table_size
+        self.keys = torch.empty(ts, 3, dtype=torch.int32, device=device)
+        self.indices = torch.empty(ts, dtype=torch.int32, device=device)
+        self.status = torch.empty(ts, dtype=torch.int32, device=device)
+        self.active_keys = torch.zeros(ts, 3, dtype=torch.int32, device=device)
+        self.cnt = torch.zeros(1, dtype=torch.int32, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def view(self):
+        return zpc_hashtable_view(self.keys.data_ptr(), self.indices.data_ptr(), self.status.data_ptr(),
+                                  self.active_keys.data_ptr(), self.table_size, self.cnt.data_ptr())
+
+    def size(self):
+        return int(self.cnt.item())  # the one D2H read the reference also does (HashTable.hpp:152)
+
+
+class Grids:
+    """Grids<f32,3,4> collocated grid: one [7][64] tile per block, channels {m, v(3), rhs(3)}."""
+
+    def __init__(self, dx, num_blocks, num_channels=7, device="cuda"):
+        self.dx, self.num_blocks, self.nch = float(dx), int(num_blocks), num_channels
+        self.tiles = torch.zeros(self.num_blocks, num_channels, 64, dtype=torch.float32, device=device)
+
+    def view(self):
+        return zpc_grids_view(self.tiles.data_ptr(), self.num_blocks, self.nch, self.dx)
+
+
+class Particles:
+    """Particles<f32,3>: AoS attribute arrays x,v (vec3), m, C,F (column-major vec9)."""
+
+    def __init__(self, P, device="cuda"):
+        self.n = int(P["x"].shape[0])
+        self.x = torch.as_tensor(P["x"]).to(device).contiguous()
+        self.v = torch.as_tensor(P["v"]).to(device).contiguous()
+        self.m = torch.as_tensor(P["m"]).to(device).contiguous()
+        self.C = torch.as_tensor(P["C"]).to(device).contiguous()
+        self.F = torch.as_tensor(P["F"]).to(device).contiguous()
+
+    def view(self):
+        return zpc_particles_view(self.m.data_ptr(), self.x.data_ptr(), self.v.data_ptr(), None, None,
+                                  self.F.data_ptr(), self.C.data_ptr(), None, self.n)
+
+    def to_host(self):
+        return {k: getattr(self, k).cpu().numpy() for k in ("x", "v", "m", "C", "F")}
+
+
+class ParticleBins:
+    """Block-binned AoSoA particles (include/zpcb200.h: zpc_bins_view)."""
+
+    def __init__(self, n, bin_capacity, device="cuda"):
+        self.n = int(n)
+        self.pars = TileVector(n, PB_NCH, 32, device)
+        self.cap = int(bin_capacity)
+        self.bin_start = torch.zeros(self.cap + 1, dtype=torch.int32, device=device)
+        self.bin_key = torch.zeros(self.cap, 3, dtype=torch.int32, device=device)
+        self.num_bins = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def view(self):
+        return zpc_bins_view(self.pars.view(), self.bin_start.data_ptr(), self.bin_key.data_ptr(),
+                             self.num_bins.data_ptr(), self.cap)
+
+    def attr(self, name):
+        chn, w = {"m": (PB_M, 1), "x": (PB_X, 3), "v": (PB_V, 3), "C": (PB_C, 9), "F": (PB_F, 9)}[name]
+        t = self.pars.channel(chn, w)
+        return t[:, 0].contiguous() if w == 1 else t
+
+
+def model_fcr(volume, E=5.0e4, nu=0.4, rho=1000.0):
+    return zpc_fixed_corotated(rho, volume, 3, E, nu)
+
+
+class _Scratch:
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_scratch = _Scratch()
+
+
+def _two_phase(fn, args_before, args_after, stream, device="cuda"):
+    nbytes = C.c_size_t(0)
+    st = _stream_ptr(stream)
+    _check(fn(None, C.byref(nbytes), *args_before, *args_after, st), fn.__name__ + "(size)")
+    tmp = _scratch.get(nbytes.value, device)
+    cap = C.c_size_t(tmp.numel())
+    _check(fn(C.c_void_p(tmp.data_ptr()), C.byref(cap), *args_before, *args_after, st), fn.__name__)
+
+
+# ---- functors as free functions (policy = stream holder; all calls asynchronous) -------------------
+def partition_for_particles(x_port, n, dx, table, stream=None):
+    """SparsityCompute.tpp:6-24 / SparsityOp.hpp:41-112."""
+    _two_phase(lib().zpcb200_partition_build, (x_port, C.c_size_t(n), C.c_float(dx), table.view(),
+                                               C.c_void_p(table.overflow.data_ptr())), (), stream)
+
+
+def clean_grid_blocks(grids, table, stream=None):
+    _check(lib().zpcb200_clean_grid(grids.view(), C.c_void_p(table.cnt.data_ptr()), _stream_ptr(stream)),
+           "clean_grid")
+
+
+def p2g_transfer(pars, table, grids, dt, model, stream=None):
+    if isinstance(pars, ParticleBins):
+        rc = lib().zpcb200_p2g_apic_fcr_binned(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
+                                               _stream_ptr(stream))
+    else:
+        rc = lib().zpcb200_p2g_apic_fcr(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
+                                        _stream_ptr(stream))
+    _check(rc, "p2g")
+
+
+def compute_grid_block_velocity(grids, table, dt, extf, mode, max_vel_sqr, stream=None):
+    e = (C.c_float * 3)(*[float(v) for v in extf])
+    _check(lib().zpcb200_grid_update(grids.view(), C.c_void_p(table.cnt.data_ptr()), C.c_float(dt), e,
+                                     C.c_int(mode), C.c_void_p(max_vel_sqr.data_ptr()), _stream_ptr(stream)),
+           "grid_update")
+
+
+def g2p_transfer(pars, table, grids, dt, stream=None):
+    if isinstance(pars, ParticleBins):
+        rc = lib().zpcb200_g2p_apic_binned(pars.view(), table.view(), grids.view(), C.c_float(dt),
+                                           _stream_ptr(stream))
+    else:
+        rc = lib().zpcb200_g2p_apic(pars.view(), table.view(), grids.view(), C.c_float(dt), _stream_ptr(stream))
+    _check(rc, "g2p")
+
+
+def bin_particles(pars, table, dx, bins, order_out=None, stream=None):
+    _two_phase(lib().zpcb200_bin_particles, (pars.view(), table.view(), C.c_float(dx), bins.view(),
+                                             C.c_void_p(order_out.data_ptr() if order_out is not None else None)),
+               (), stream)
+
+
+def rebin_particles(src, table, dx, dst, stream=None):
+    _two_phase(lib().zpcb200_rebin_particles, (src.view(), table.view(), C.c_float(dx), dst.view()), (), stream)
+
+
+def unbin_particles(bins, pars, stream=None):
+    _check(lib().zpcb200_unbin_particles(bins.view(), pars.view(), _stream_ptr(stream)), "unbin")
+
+
+def kernel_launch_count():
+    return int(lib().zpcb200_kernel_launch_count())

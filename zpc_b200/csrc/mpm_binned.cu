@@ -1,0 +1,590 @@
+// MPM fast path on block-binned AoSoA particles (sm_100a).
+//
+// Particles live in a 25-channel TileVector<f32,32> (AoSoA, reference container/TileVector.hpp:108),
+// sorted by HOME BLOCK = the block ComputeSparsity assigns (reference SparsityOp.hpp:68-79, the block
+// holding base_node-1).  With side-4 blocks the whole 3^3 stencil of such a particle lies in the 2x2x2
+// block arena {b, b+1}^3, and a particle that has since drifted by one cell in any
+// direction still lies inside it.  One CTA per bin:
+//
+//   P2G  (a) counting-sort the bin's particles by (column, z) of their CURRENT home cell in shared
+//            memory (warp match ranking, deterministic);
+//        (b) warp w owns column (x,y) = (w>>2, w&3): lanes first act as 32 particles (coalesced AoSoA
+//            loads, SVD stress, 28-float record -> shared), then as the 27 stencil offsets that sweep
+//            the records with 7 broadcast LDS.128 each, accumulating the 7 grid channels in registers
+//            per cell and folding them into a warp-private column arena — no atomics, no barriers;
+//        (c) the 16 column arenas are summed per node into the eight [7][64] grid tiles in shared
+//            memory and added to HBM with eight 1792-byte TMA bulk reductions
+//            (cp.reduce.async.bulk.global.shared::cta.add.f32) instead of 27*7 REDs per particle;
+//        (d) particles that left the arena's reach since the last re-bin take the per-particle RED path.
+//   G2P  the arena's three velocity channels (8 x 768 contiguous bytes) are staged with TMA bulk
+//        copies on an mbarrier, then one thread per particle gathers with a separable (z, then y,
+//        then x) contraction: 240 FMAs instead of 27*16.
+//
+// Results equal P2G.hpp / G2P.hpp up to fp32 re-association (tests: <= 1e-5 relative).
+#include <climits>
+
+#include "common.cuh"
+#include "mpm_math.cuh"
+#include "mpm_particle.cuh"
+
+namespace {
+
+constexpr int TS = 32;                  // particle tile length
+constexpr int NCH = ZPC_PB_NCH;         // 25 channels
+constexpr int BIN_MAX = ZPCB200_BIN_MAX;
+constexpr int P2G_NT = 512, P2G_NW = P2G_NT / 32;
+constexpr int NGRP = 16 * 6 + 1;        // (nominal column, z in [-1,4]) groups + stray group
+constexpr int GRP_STRAY = 96;
+constexpr int NCHUNK = BIN_MAX / 32;
+constexpr int REC_F = 28;               // floats per particle record
+constexpr int COL_F = 7 * 72;           // column arena: 7 channels x (8 z x 3 x 3) nodes
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ size_t pslot(size_t i) { return ((i >> 5) * NCH) * TS + (i & 31); }  // channel 0 of particle i
+
+struct P2GSmem {
+  float rec[P2G_NW][32][REC_F];     // 57344 B; reused as the 8 output tiles [8][7][64] (14336 B)
+  float col[P2G_NW][COL_F];         // 32256 B
+  unsigned short hist[NCHUNK][NGRP + 1];
+  unsigned short order[BIN_MAX];
+  unsigned char grp_of[BIN_MAX];
+  int gstart[NGRP + 1];
+  int tile_id[8];
+  int nstray;
+};
+
+__global__ void __launch_bounds__(P2G_NT, 2)
+p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
+                  const int *__restrict__ numBins, zpc_hashtable_view tb, float *__restrict__ tiles, float dx, float dt,
+                  float volume, float mu, float lam) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  P2GSmem &S = *reinterpret_cast<P2GSmem *>(smem_raw);
+  const int bin = blockIdx.x;
+  if (bin >= *numBins) return;
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const int p0 = binStart[bin], np = min(binStart[bin + 1] - p0, BIN_MAX);
+  const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+
+  // ---- (0) arena blocks, zero scratch ------------------------------------------------------------------
+  if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
+  for (int i = tid; i < NCHUNK * (NGRP + 1); i += P2G_NT) (&S.hist[0][0])[i] = 0;
+  for (int i = tid; i < P2G_NW * COL_F; i += P2G_NT) (&S.col[0][0])[i] = 0.f;
+  __syncthreads();
+
+  // ---- (a) counting sort by (column, z) of the current home cell -------------------------------------
+  // chunk c = 32 consecutive particles; thread handles chunks w, w+16
+  int my_grp[NCHUNK / P2G_NW], my_rank[NCHUNK / P2G_NW];
+#pragma unroll
+  for (int it = 0; it < NCHUNK / P2G_NW; ++it) {
+    const int c = w + it * P2G_NW, i = c * 32 + l;
+    int g = NGRP;  // invalid
+    if (i < np) {
+      const size_t s = pslot((size_t)p0 + i);
+      // current base node (division form, as LocalArena does) relative to the bin's block origin
+      const int cx = (int)floorf(pars[s + (ZPC_PB_X + 0) * TS] / dx - 0.5f) - 1 - 4 * kx;
+      const int cy = (int)floorf(pars[s + (ZPC_PB_X + 1) * TS] / dx - 0.5f) - 1 - 4 * ky;
+      const int cz = (int)floorf(pars[s + (ZPC_PB_X + 2) * TS] / dx - 0.5f) - 1 - 4 * kz;
+      g = ((unsigned)cx < 4u && (unsigned)cy < 4u && (unsigned)(cz + 1) < 6u) ? (cx * 4 + cy) * 6 + (cz + 1) : GRP_STRAY;
+      S.grp_of[i] = (unsigned char)g;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, g);
+    my_grp[it] = g;
+    my_rank[it] = __popc(peers & lanemask_lt());
+    if (g < NGRP && l == __ffs(peers) - 1) S.hist[c][g] = (unsigned short)__popc(peers);
+  }
+  __syncthreads();
+  if (tid < NGRP) {  // exclusive prefix over chunks for group tid
+    int run = 0;
+    for (int c = 0; c < NCHUNK; ++c) { const int t = S.hist[c][tid]; S.hist[c][tid] = (unsigned short)run; run += t; }
+    S.gstart[tid] = run;  // count for now
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int g = 0; g < NGRP; ++g) { const int t = S.gstart[g]; S.gstart[g] = run; run += t; }
+    S.gstart[NGRP] = run;
+    S.nstray = run - S.gstart[GRP_STRAY];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < NCHUNK / P2G_NW; ++it) {
+    const int c = w + it * P2G_NW, i = c * 32 + l, g = my_grp[it];
+    if (g < NGRP) S.order[S.gstart[g] + S.hist[c][g] + my_rank[it]] = (unsigned short)i;
+  }
+  __syncthreads();
+
+  // ---- (b) column sweep: warp w owns column (w>>2, w&3) -----------------------------------------------
+  {
+    const int cs = S.gstart[w * 6], ce = S.gstart[w * 6 + 6];
+    // lane as stencil offset (ox,oy,oz); quadratic B-spline as a polynomial in d0 with per-lane coefficients:
+    //   o=0: .5 d^2 - 1.5 d + 1.125 ; o=1: -d^2 + 2 d - .25 ; o=2: .5 d^2 - .5 d + .125
+    const bool lane_on = l < 27;
+    const int lc = lane_on ? l : 0;  // lanes 27..31 shadow lane 0 and never write
+    const int ox = lc / 9, oy = (lc / 3) % 3, oz = lc % 3;
+    const float qa[3] = {0.5f, -1.0f, 0.5f}, qb[3] = {-1.5f, 2.0f, -0.5f}, qc[3] = {1.125f, -0.25f, 0.125f};
+    const float ax = qa[ox], bx = qb[ox], cx_ = qc[ox], ay = qa[oy], by = qb[oy], cy_ = qc[oy], az = qa[oz], bz = qb[oz],
+                cz_ = qc[oz];
+    const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
+    float *colw = S.col[w];
+    const int node_lane = oz * 9 + ox * 3 + oy;  // + zc*9 at flush time
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int cur = -1;
+    for (int b0 = cs; b0 < ce; b0 += 32) {
+      const int nb = min(32, ce - b0);
+      int my_zc = 0;
+      if (l < nb) {  // lane as particle
+        const int i = S.order[b0 + l];
+        my_zc = (int)S.grp_of[i] - w * 6;
+        const size_t s = pslot((size_t)p0 + i);
+        float pos[3], vel[3], C[9], F[9], K[9];
+        const float mass = pars[s + ZPC_PB_M * TS];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
+#pragma unroll
+        for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
+        zpcm::stress_fcr(volume, mu, lam, F, K);
+#pragma unroll
+        for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
+        float d0[3], loc[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float X = pos[d] / dx;
+          const float lp = X - floorf(X - 0.5f);
+          d0[d] = lp;
+          loc[d] = lp * dx;
+        }
+        // record: {d0, m} {A, B col0.x} ... see header comment; mv_d = W (A_d + sum_e B_de o_e), rhs_d = W (a_d + sum_e K_de o_e)
+        float r[REC_F];
+        r[0] = d0[0]; r[1] = d0[1]; r[2] = d0[2]; r[3] = mass;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          r[4 + d] = mass * (vel[d] - (C[d] * loc[0] + C[3 + d] * loc[1] + C[6 + d] * loc[2]));  // A_d
+          r[16 + d] = -(K[d] * loc[0] + K[3 + d] * loc[1] + K[6 + d] * loc[2]);                    // a_d
+#pragma unroll
+          for (int e = 0; e < 3; ++e) {
+            r[7 + 3 * d + e] = mass * C[d + 3 * e] * dx;   // B_de
+            r[19 + 3 * d + e] = K[d + 3 * e] * dx;         // K_de (scaled)
+          }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(S.rec[w][l]);
+#pragma unroll
+        for (int k = 0; k < REC_F / 4; ++k) dst[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+      }
+      __syncwarp();
+      for (int j = 0; j < nb; ++j) {  // lane as stencil offset
+        const int zc = __shfl_sync(0xffffffffu, my_zc, j);
+        if (zc != cur) {
+          if (cur >= 0 && lane_on) {
+            float *dstc = colw + cur * 9 + node_lane;
+#pragma unroll
+            for (int ch = 0; ch < 7; ++ch) { dstc[ch * 72] += acc[ch]; acc[ch] = 0.f; }
+          }
+          cur = zc;
+        }
+        const float4 *rp = reinterpret_cast<const float4 *>(S.rec[w][j]);
+        const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3], r4 = rp[4], r5 = rp[5], r6 = rp[6];
+        const float wx = fmaf(fmaf(ax, r0.x, bx), r0.x, cx_), wy = fmaf(fmaf(ay, r0.y, by), r0.y, cy_),
+                    wz = fmaf(fmaf(az, r0.z, bz), r0.z, cz_);
+        const float W = wx * wy * wz;
+        acc[0] = fmaf(W, r0.w, acc[0]);
+        // A = r1.xyz ; B row d = (r1.w r2.x r2.y), (r2.z r2.w r3.x), (r3.y r3.z r3.w)
+        acc[1] = fmaf(W, fmaf(r2.y, fz, fmaf(r2.x, fy, fmaf(r1.w, fx, r1.x))), acc[1]);
+        acc[2] = fmaf(W, fmaf(r3.x, fz, fmaf(r2.w, fy, fmaf(r2.z, fx, r1.y))), acc[2]);
+        acc[3] = fmaf(W, fmaf(r3.w, fz, fmaf(r3.z, fy, fmaf(r3.y, fx, r1.z))), acc[3]);
+        // a = r4.xyz ; K row d = (r4.w r5.x r5.y), (r5.z r5.w r6.x), (r6.y r6.z r6.w)
+        acc[4] = fmaf(W, fmaf(r5.y, fz, fmaf(r5.x, fy, fmaf(r4.w, fx, r4.x))), acc[4]);
+        acc[5] = fmaf(W, fmaf(r6.x, fz, fmaf(r5.w, fy, fmaf(r5.z, fx, r4.y))), acc[5]);
+        acc[6] = fmaf(W, fmaf(r6.w, fz, fmaf(r6.z, fy, fmaf(r6.y, fx, r4.z))), acc[6]);
+      }
+      __syncwarp();
+    }
+    if (cur >= 0 && lane_on) {
+      float *dstc = colw + cur * 9 + node_lane;
+#pragma unroll
+      for (int ch = 0; ch < 7; ++ch) dstc[ch * 72] += acc[ch];
+    }
+  }
+  __syncthreads();
+
+  // ---- (c) merge column arenas -> eight [7][64] tiles in shared memory ----------------------------------
+  float *out = &S.rec[0][0][0];
+  {
+    const int axn = tid >> 6, ayn = (tid >> 3) & 7, azn = tid & 7;  // arena node
+    float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int oxm = 0; oxm < 3; ++oxm) {
+      const int x = axn - 1 - oxm;
+      if ((unsigned)x >= 4u) continue;
+#pragma unroll
+      for (int oym = 0; oym < 3; ++oym) {
+        const int y = ayn - 1 - oym;
+        if ((unsigned)y >= 4u) continue;
+        const float *c = S.col[x * 4 + y] + azn * 9 + oxm * 3 + oym;
+#pragma unroll
+        for (int ch = 0; ch < 7; ++ch) v[ch] += c[ch * 72];
+      }
+    }
+    const int blk = ((axn >> 2) << 2) | ((ayn >> 2) << 1) | (azn >> 2);
+    const int cell = ((axn & 3) << 4) | ((ayn & 3) << 2) | (azn & 3);
+#pragma unroll
+    for (int ch = 0; ch < 7; ++ch) out[blk * 448 + ch * 64 + cell] = v[ch];
+  }
+  // make the generic-proxy writes visible to the async proxy, then bulk-reduce each tile into HBM/L2
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid < 8) {
+    const int id = S.tile_id[tid];
+    if (id >= 0) {
+      float *g = tiles + (size_t)id * 448;
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
+                   "r"(smem_u32(out + tid * 448)), "r"(1792)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+
+  // ---- (d) strays: per-particle scatter with REDs ------------------------------------------------------------
+  {
+    const int s0 = S.gstart[GRP_STRAY], ns = S.nstray;
+    for (int t = tid; t < ns; t += P2G_NT) {
+      const int i = S.order[s0 + t];
+      const size_t s = pslot((size_t)p0 + i);
+      float pos[3], vel[3], C[9], F[9];
+      const float mass = pars[s + ZPC_PB_M * TS];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
+#pragma unroll
+      for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
+      zpcp::p2g_scatter_particle(pos, vel, mass, C, F, tb, tiles, 7, dx, dt, volume, mu, lam);
+    }
+  }
+  if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int G2P_NT = 256;
+struct G2PSmem {
+  float v[8][3][64];  // 6144 B: channels 1..3 of the eight arena tiles
+  unsigned long long bar;
+  int tile_id[8];
+};
+
+__global__ void __launch_bounds__(G2P_NT)
+g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
+                  const int *__restrict__ numBins, zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx,
+                  float dt) {
+  __shared__ __align__(128) G2PSmem S;
+  const int bin = blockIdx.x;
+  if (bin >= *numBins) return;
+  const int tid = threadIdx.x;
+  const int p0 = binStart[bin], np = binStart[bin + 1] - p0;
+  const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
+  if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(&S.bar)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned bytes = 0;
+    for (int b = 0; b < 8; ++b) bytes += S.tile_id[b] >= 0 ? 768u : 0u;
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.bar)), "r"(bytes) : "memory");
+    for (int b = 0; b < 8; ++b)
+      if (S.tile_id[b] >= 0) {
+        const float *g = tiles + ((size_t)S.tile_id[b] * nch + 1) * 64;
+        asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&S.v[b][0][0])),
+                     "l"(g), "r"(768), "r"(smem_u32(&S.bar))
+                     : "memory");
+      }
+  }
+  // blocks missing from the partition read as zero velocity
+  for (int b = 0; b < 8; ++b)
+    if (S.tile_id[b] < 0 && tid < 192) (&S.v[b][0][0])[tid] = 0.f;
+  {  // wait for the TMA bytes (phase 0)
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                   : "=r"(done)
+                   : "r"(smem_u32(&S.bar)), "r"(0)
+                   : "memory");
+    }
+  }
+  __syncthreads();
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  const float *sv = &S.v[0][0][0];
+  for (int i = tid; i < np; i += G2P_NT) {
+    const size_t s = pslot((size_t)p0 + i);
+    float pos[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pos[d] = pars[s + (ZPC_PB_X + d) * TS];
+    zpcm::Arena ar;
+    zpcm::arena_init(ar, dx, pos);
+    const int ax0 = ar.corner[0] - 4 * kx, ay0 = ar.corner[1] - 4 * ky, az0 = ar.corner[2] - 4 * kz;
+    float vel[3], G[9];  // G[r + 3e] = sum W v_r o_e
+    if ((unsigned)ax0 < 6u && (unsigned)ay0 < 6u && (unsigned)az0 < 6u) {
+      int fo[3], go[3], ho[3];
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const int a = ax0 + o, b = ay0 + o, c = az0 + o;
+        fo[o] = (a >> 2) * (4 * 192) + ((a & 3) << 4);
+        go[o] = (b >> 2) * (2 * 192) + ((b & 3) << 2);
+        ho[o] = (c >> 2) * 192 + (c & 3);
+      }
+      // separable contraction: z, then y, then x
+      float px[3][3], pz[3][3], py[3][3];  // [i][r]
+#pragma unroll
+      for (int ii = 0; ii < 3; ++ii) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { px[ii][r] = 0.f; py[ii][r] = 0.f; pz[ii][r] = 0.f; }
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+          const int base = fo[ii] + go[jj];
+          float u[3], uz[3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float v0 = sv[base + ho[0] + r * 64], v1 = sv[base + ho[1] + r * 64], v2 = sv[base + ho[2] + r * 64];
+            const float t1 = ar.w[2][1] * v1, t2 = ar.w[2][2] * v2;
+            u[r] = fmaf(ar.w[2][0], v0, t1 + t2);
+            uz[r] = fmaf(2.f, t2, t1);
+          }
+          const float wyj = ar.w[1][jj];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float t = wyj * u[r];
+            px[ii][r] += t;
+            py[ii][r] = fmaf((float)jj, t, py[ii][r]);
+            pz[ii][r] = fmaf(wyj, uz[r], pz[ii][r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float t0 = ar.w[0][0] * px[0][r], t1 = ar.w[0][1] * px[1][r], t2 = ar.w[0][2] * px[2][r];
+        vel[r] = t0 + t1 + t2;
+        G[r] = fmaf(2.f, t2, t1);
+        G[r + 3] = ar.w[0][0] * py[0][r] + ar.w[0][1] * py[1][r] + ar.w[0][2] * py[2][r];
+        G[r + 6] = ar.w[0][0] * pz[0][r] + ar.w[0][1] * pz[1][r] + ar.w[0][2] * pz[2][r];
+      }
+    } else {
+      zpcp::g2p_gather_particle(ar, tb, tiles, nch, vel, G);
+    }
+    // C[r + 3e] = D_inv * sum W v_r (o_e dx - local_e) = D_inv * (dx G_re - local_e v_r)
+    float C[9], Fo[9], tmp[9];
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) C[r + 3 * e] = (dx * G[r + 3 * e] - ar.local[e] * vel[r]) * D_inv;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
+#pragma unroll
+    for (int d = 0; d < 9; ++d) { Fo[d] = pars[s + (ZPC_PB_F + d) * TS]; tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f); }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        pars[s + (ZPC_PB_F + 3 * c + r) * TS] = tmp[r] * Fo[3 * c] + tmp[3 + r] * Fo[3 * c + 1] + tmp[6 + r] * Fo[3 * c + 2];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { pars[s + (ZPC_PB_X + d) * TS] = pos[d]; pars[s + (ZPC_PB_V + d) * TS] = vel[d]; }
+#pragma unroll
+    for (int d = 0; d < 9; ++d) pars[s + (ZPC_PB_C + d) * TS] = C[d];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// binning
+// ----------------------------------------------------------------------------------------------------------------
+// key = (block rank << 6) | cell id of the home cell ; val = particle index
+template <bool AOSOA>
+__global__ void bin_keys_kernel(const float *__restrict__ X, size_t n, float dxinv, zpc_hashtable_view tb, unsigned *keys,
+                                int *vals, int *err) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x[3];
+  if (AOSOA) {
+    const size_t s = pslot(i);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = X[s + (ZPC_PB_X + d) * TS];
+  } else {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = X[3 * i + d];
+  }
+  const int c0 = zpcm::sparsity_coord(x[0], dxinv), c1 = zpcm::sparsity_coord(x[1], dxinv), c2 = zpcm::sparsity_coord(x[2], dxinv);
+  int b = zpcm::table_query(c0 >> 2, c1 >> 2, c2 >> 2, tb.tableSize, tb.keys, tb.indices);
+  if (b < 0) { if (err) *err = 2; b = 0; }
+  keys[i] = ((unsigned)b << 6) | (unsigned)(((c0 & 3) << 4) | ((c1 & 3) << 2) | (c2 & 3));
+  vals[i] = (int)i;
+}
+__global__ void bin_bounds_kernel(const unsigned *__restrict__ keys, size_t n, int *start, int *end) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned b = keys[i] >> 6;
+  if (i == 0 || (keys[i - 1] >> 6) != b) start[b] = (int)i;
+  if (i == n - 1 || (keys[i + 1] >> 6) != b) end[b] = (int)i + 1;
+}
+__global__ void bin_count_kernel(const int *start, const int *end, const int *cnt, int cap, int *nbins) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= cap) return;
+  nbins[b] = b < *cnt ? (end[b] - start[b] + BIN_MAX - 1) / BIN_MAX : 0;
+}
+__global__ void bin_fill_kernel(const int *start, const int *end, const int *nbins, const int *binoff, const int *cnt, int cap,
+                                const int *active_keys, int n, int *binStart, int *binKey, int *numBins, int binCapacity,
+                                int *err) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = min(*cnt, cap);
+  if (b == 0) {
+    const int total = nb > 0 ? binoff[nb - 1] + nbins[nb - 1] : 0;
+    if (total > binCapacity) { if (err) *err = 3; *numBins = 0; }
+    else { *numBins = total; binStart[total] = n; }
+  }
+  if (b >= nb) return;
+  const int k = nbins[b], o = binoff[b];
+  if (o + k > binCapacity) return;
+  for (int j = 0; j < k; ++j) {
+    binStart[o + j] = start[b] + j * BIN_MAX;
+    binKey[3 * (o + j)] = active_keys[3 * b];
+    binKey[3 * (o + j) + 1] = active_keys[3 * b + 1];
+    binKey[3 * (o + j) + 2] = active_keys[3 * b + 2];
+  }
+}
+// dst slot i <- src particle perm[i]
+template <bool SRC_AOSOA>
+__global__ void bin_gather_kernel(zpc_particles_view A, const float *__restrict__ srcT, const int *__restrict__ perm, size_t n,
+                                  float *__restrict__ dstT) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t j = (size_t)perm[i], d = pslot(i);
+  if (SRC_AOSOA) {
+    const size_t s = pslot(j);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) dstT[d + c * TS] = srcT[s + c * TS];
+  } else {
+    dstT[d + ZPC_PB_M * TS] = A.M[j];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { dstT[d + (ZPC_PB_X + c) * TS] = A.X[3 * j + c]; dstT[d + (ZPC_PB_V + c) * TS] = A.V[3 * j + c]; }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) { dstT[d + (ZPC_PB_C + c) * TS] = A.C[9 * j + c]; dstT[d + (ZPC_PB_F + c) * TS] = A.F[9 * j + c]; }
+  }
+}
+__global__ void unbin_kernel(const float *__restrict__ srcT, size_t n, zpc_particles_view A) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t s = pslot(i);
+  if (A.M) A.M[i] = srcT[s + ZPC_PB_M * TS];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { A.X[3 * i + c] = srcT[s + (ZPC_PB_X + c) * TS]; A.V[3 * i + c] = srcT[s + (ZPC_PB_V + c) * TS]; }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) { A.C[9 * i + c] = srcT[s + (ZPC_PB_C + c) * TS]; A.F[9 * i + c] = srcT[s + (ZPC_PB_F + c) * TS]; }
+}
+
+int bit_length(unsigned v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+
+// shared pipeline of bin_particles / rebin_particles
+template <bool SRC_AOSOA>
+int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const float *srcT, size_t n, zpc_hashtable_view tb, float dx,
+                 zpc_bins_view dst, int *order_out, cudaStream_t s) {
+  if (!temp_bytes) return ZPCB200_E_BADARG;
+  if (dst.pars.numChannels != NCH || dst.binCapacity <= 0) return ZPCB200_E_BADARG;
+  if (n > (size_t)INT_MAX) return ZPCB200_E_UNSUPPORTED;
+  const int cap = dst.binCapacity;                          // also the bound on the number of blocks
+  const int ebit = 6 + bit_length((unsigned)(cap - 1));
+  if (ebit > 32) return ZPCB200_E_UNSUPPORTED;
+  size_t sort_bytes = 0, scan_bytes = 0;
+  zpc_port none = {nullptr, 0, 0, 0, 1};
+  int rc = zpcb200_radix_sort_pair_u32(nullptr, &sort_bytes, none, none, none, none, n, 0, ebit, nullptr);
+  if (rc) return rc;
+  rc = zpcb200_exclusive_scan_sum_i32(nullptr, &scan_bytes, none, none, (size_t)cap, nullptr);
+  if (rc) return rc;
+  const size_t o_keys = 256, o_vals = zpc_align_up(o_keys + 4 * n, 256), o_skeys = zpc_align_up(o_vals + 4 * n, 256),
+               o_svals = zpc_align_up(o_skeys + 4 * n, 256), o_start = zpc_align_up(o_svals + 4 * n, 256),
+               o_end = o_start + zpc_align_up(4 * (size_t)cap, 256), o_nb = o_end + zpc_align_up(4 * (size_t)cap, 256),
+               o_off = o_nb + zpc_align_up(4 * (size_t)cap, 256), o_scan = o_off + zpc_align_up(4 * (size_t)cap, 256),
+               o_sort = zpc_align_up(o_scan + scan_bytes, 256), need = o_sort + sort_bytes;
+  if (!temp) { *temp_bytes = need; return ZPCB200_OK; }
+  if (*temp_bytes < need) return ZPCB200_E_TEMP_TOO_SMALL;
+  char *t = (char *)temp;
+  int *err = (int *)t;
+  unsigned *keys = (unsigned *)(t + o_keys), *skeys = (unsigned *)(t + o_skeys);
+  int *vals = (int *)(t + o_vals), *svals = order_out ? order_out : (int *)(t + o_svals);
+  int *start = (int *)(t + o_start), *end = (int *)(t + o_end), *nbins = (int *)(t + o_nb), *binoff = (int *)(t + o_off);
+  ZPC_CUDA(cudaMemsetAsync(t, 0, 256, s));
+  ZPC_CUDA(cudaMemsetAsync(start, 0, o_off - o_start, s));
+  const unsigned gp = (unsigned)((n + 255) / 256), gb = (unsigned)((cap + 255) / 256);
+  if (n) {
+    bin_keys_kernel<SRC_AOSOA><<<gp, 256, 0, s>>>(SRC_AOSOA ? srcT : A.X, n, 1.0f / dx, tb, keys, vals, err);
+    ZPC_CHECK_LAUNCH();
+    zpc_port pk = {keys, 0, 0, 0, 1}, pv = {vals, 0, 0, 0, 1}, psk = {skeys, 0, 0, 0, 1}, psv = {svals, 0, 0, 0, 1};
+    size_t sb = sort_bytes;
+    rc = zpcb200_radix_sort_pair_u32(t + o_sort, &sb, pk, pv, psk, psv, n, 0, ebit, s);
+    if (rc) return rc;
+    bin_bounds_kernel<<<gp, 256, 0, s>>>(skeys, n, start, end);
+    ZPC_CHECK_LAUNCH();
+  }
+  bin_count_kernel<<<gb, 256, 0, s>>>(start, end, tb.cnt, cap, nbins);
+  ZPC_CHECK_LAUNCH();
+  {
+    zpc_port pi = {nbins, 0, 0, 0, 1}, po = {binoff, 0, 0, 0, 1};
+    size_t sb = scan_bytes;
+    rc = zpcb200_exclusive_scan_sum_i32(t + o_scan, &sb, pi, po, (size_t)cap, s);
+    if (rc) return rc;
+  }
+  bin_fill_kernel<<<gb, 256, 0, s>>>(start, end, nbins, binoff, tb.cnt, cap, tb.activeKeys, (int)n, dst.binStart, dst.binKey,
+                                      dst.numBins, dst.binCapacity, err);
+  ZPC_CHECK_LAUNCH();
+  if (n) {
+    bin_gather_kernel<SRC_AOSOA><<<gp, 256, 0, s>>>(A, srcT, svals, n, dst.pars.base);
+    ZPC_CHECK_LAUNCH();
+  }
+  return ZPCB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zpcb200_bin_particles(void *temp, size_t *temp_bytes, zpc_particles_view pars, zpc_hashtable_view table, float dx,
+                          zpc_bins_view bins, int *order_out, zpc_stream_t stream) {
+  if (temp && (!pars.X || !pars.V || !pars.M || !pars.C || !pars.F)) return ZPCB200_E_BADARG;
+  if (temp && bins.pars.size < pars.count) return ZPCB200_E_BADARG;
+  return bin_pipeline<false>(temp, temp_bytes, pars, nullptr, pars.count, table, dx, bins, order_out, (cudaStream_t)stream);
+}
+int zpcb200_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src, zpc_hashtable_view table, float dx,
+                            zpc_bins_view dst, zpc_stream_t stream) {
+  zpc_particles_view none = {};
+  if (temp && (src.pars.base == dst.pars.base || dst.pars.size < src.pars.size)) return ZPCB200_E_BADARG;
+  return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, table, dx, dst, nullptr, (cudaStream_t)stream);
+}
+int zpcb200_unbin_particles(zpc_bins_view bins, zpc_particles_view pars, zpc_stream_t stream) {
+  if (!pars.X || !pars.V || !pars.C || !pars.F || pars.count > bins.pars.size) return ZPCB200_E_BADARG;
+  if (!pars.count) return ZPCB200_OK;
+  unbin_kernel<<<(unsigned)((pars.count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bins.pars.base, pars.count, pars);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_fixed_corotated model,
+                                zpc_stream_t stream) {
+  if (g.numChannels != 7 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
+    return ZPCB200_E_BADARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    attr_set = true;
+  }
+  float mu, lam;
+  zpcm::lame_host(model.E, model.nu, mu, lam);
+  p2g_binned_kernel<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
+      bins.pars.base, bins.binStart, bins.binKey, bins.numBins, tb, g.tiles, g.dx, dt, model.volume, mu, lam);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
+  if (g.numChannels < 4 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
+    return ZPCB200_E_BADARG;
+  g2p_binned_kernel<<<bins.binCapacity, G2P_NT, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey,
+                                                                           bins.numBins, tb, g.tiles, g.numChannels, g.dx, dt);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+}

@@ -1,0 +1,235 @@
+// Per-particle math of the MPM transfer path (registers only).
+//   svd3             : McAdams et al. 3x3 SVD, 4 cyclic Jacobi sweeps + Givens QR — the algorithm of
+//                      reference math/matrix/SVD.hpp:15-1026 (constants :27-32), with ::rsqrtf as the
+//                      reference's device build uses (ZpcMathUtils.hpp:812-816).
+//   stress_fcr       : fixed-corotated  P F^T vol  (physics/ConstitutiveModel_Vol_dP.hpp:10-47).
+//   bspline weights  : quadratic B-spline (math/curve/InterpolationKernel.hpp:91-128) around
+//                      base_node<1> (:46-55) as used by LocalArena (simulation/Utils.hpp:51-70).
+// Matrices are column-major 9-vectors M[3*col+row], exactly the reference's vec9 convention.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace zpcm {
+
+template <int AXIS>
+__device__ __forceinline__ void jacobi_step(float &pp, float &qq, float &off, float &rr, float &a, float &b,
+                                            float (&q)[4]) {
+  const float tiny = 1.e-20f, gamma = 5.8284273147583007813f;
+  const float sin_pi8 = __uint_as_float(1053028117u), cos_pi8 = __uint_as_float(1064076127u);
+  float sh = off * 0.5f;
+  float t5 = pp - qq;
+  const bool big = sh * sh >= tiny;
+  sh = big ? sh : 0.0f;
+  float ch = big ? t5 : 1.0f;
+  float t1 = sh * sh, t2 = ch * ch;
+  const float r = rsqrtf(t1 + t2);
+  sh = r * sh;
+  ch = r * ch;
+  if (t2 <= gamma * t1) { sh = sin_pi8; ch = cos_pi8; }
+  t1 = sh * sh;
+  t2 = ch * ch;
+  const float c = t2 - t1;
+  float s = ch * sh;
+  s = s + s;
+  // conjugate the symmetric matrix (the (sh^2+ch^2) factors keep it consistent when the pair is unnormalised)
+  const float n2 = t1 + t2;
+  rr = rr * n2 * n2;
+  a = a * n2;
+  b = b * n2;
+  const float ta = s * a, tb = s * b;
+  a = c * a + tb;
+  b = c * b - ta;
+  const float s2 = s * s, c2 = c * c, cs = c * s;
+  const float npp = pp * c2 + qq * s2, nqq = qq * c2 + pp * s2;
+  const float twice = (off + off) * cs;
+  off = off * (c2 - s2) - t5 * cs;
+  pp = npp + twice;
+  qq = nqq - twice;
+  // accumulate the rotation as a quaternion (s, x, y, z)
+  const float tx = sh * q[1], ty = sh * q[2], tz = sh * q[3];
+  const float t[3] = {tx, ty, tz};
+  sh = sh * q[0];
+  q[0] = ch * q[0];
+  q[1] = ch * q[1];
+  q[2] = ch * q[2];
+  q[3] = ch * q[3];
+  constexpr int B = (AXIS + 1) % 3, C = (AXIS + 2) % 3;
+  q[1 + AXIS] += sh;
+  q[0] -= t[AXIS];
+  q[1 + B] += t[C];
+  q[1 + C] -= t[B];
+}
+
+__device__ __forceinline__ float rsqrt_refined(float x) {  // one Newton step, SVD.hpp:386-392
+  const float r = rsqrtf(x);
+  const float h = r * 0.5f;
+  return (r + h) - x * (r * (r * h));
+}
+
+__device__ __forceinline__ void qr_givens(float piv, float low, float &c, float &s) {
+  const float small = 1.e-12f;
+  float sh = (low * low >= small) ? low : 0.0f;
+  float ch = fmaxf(fmaxf(-piv, piv), small);
+  const bool nonneg = piv >= 0.0f;
+  float n2 = ch * ch + sh * sh;
+  ch = ch + rsqrt_refined(n2) * n2;
+  if (!nonneg) { const float t = ch; ch = sh; sh = t; }
+  n2 = ch * ch + sh * sh;
+  const float r = rsqrt_refined(n2);
+  ch *= r;
+  sh *= r;
+  c = ch * ch - sh * sh;
+  s = sh * ch;
+  s = s + s;
+}
+__device__ __forceinline__ void rot_pair(float &x, float &y, float c, float s) {
+  const float t1 = s * x, t2 = s * y;
+  x = c * x + t2;
+  y = c * y - t1;
+}
+
+// F, U, V column-major; S the three singular values (signed so that U,V are rotations)
+__device__ __forceinline__ void svd3(const float (&F)[9], float (&U)[9], float (&S)[3], float (&V)[9]) {
+  // row-major local copy a[r][c] = F[3c+r]
+  float a00 = F[0], a01 = F[3], a02 = F[6], a10 = F[1], a11 = F[4], a12 = F[7], a20 = F[2], a21 = F[5], a22 = F[8];
+  float s11 = a00 * a00 + a10 * a10 + a20 * a20;
+  float s21 = a01 * a00 + a11 * a10 + a21 * a20;
+  float s31 = a02 * a00 + a12 * a10 + a22 * a20;
+  float s22 = a01 * a01 + a11 * a11 + a21 * a21;
+  float s32 = a02 * a01 + a12 * a11 + a22 * a21;
+  float s33 = a02 * a02 + a12 * a12 + a22 * a22;
+  float q[4] = {1.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int sweep = 0; sweep < 4; ++sweep) {
+    jacobi_step<2>(s11, s22, s21, s33, s31, s32, q);
+    jacobi_step<0>(s22, s33, s32, s11, s21, s31, q);
+    jacobi_step<1>(s33, s11, s31, s22, s32, s21, q);
+  }
+  {
+    const float r = rsqrt_refined(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] *= r; q[1] *= r; q[2] *= r; q[3] *= r;
+  }
+  float v00, v01, v02, v10, v11, v12, v20, v21, v22;
+  {
+    const float xx = q[1] * q[1], yy = q[2] * q[2], zz = q[3] * q[3], ww = q[0] * q[0];
+    v00 = ww + xx - yy - zz;
+    v11 = ww - xx + yy - zz;
+    v22 = ww - xx - yy + zz;
+    const float x2 = q[1] + q[1], y2 = q[2] + q[2], z2 = q[3] + q[3];
+    const float wx = q[0] * x2, wy = q[0] * y2, wz = q[0] * z2;
+    const float xy = q[2] * x2, yz = q[3] * y2, zx = q[1] * z2;
+    v01 = xy - wz; v12 = yz - wx; v20 = zx - wy;
+    v10 = xy + wz; v21 = yz + wx; v02 = zx + wy;
+  }
+  // B = A V
+  float b00 = a00 * v00 + a01 * v10 + a02 * v20, b01 = a00 * v01 + a01 * v11 + a02 * v21, b02 = a00 * v02 + a01 * v12 + a02 * v22;
+  float b10 = a10 * v00 + a11 * v10 + a12 * v20, b11 = a10 * v01 + a11 * v11 + a12 * v21, b12 = a10 * v02 + a11 * v12 + a12 * v22;
+  float b20 = a20 * v00 + a21 * v10 + a22 * v20, b21 = a20 * v01 + a21 * v11 + a22 * v21, b22 = a20 * v02 + a21 * v12 + a22 * v22;
+  float r0 = b00 * b00 + b10 * b10 + b20 * b20, r1 = b01 * b01 + b11 * b11 + b21 * b21, r2 = b02 * b02 + b12 * b12 + b22 * b22;
+#define ZPC_SWAPNEG(cond, xa, ya, za, xb, yb, zb, va, vb, vc, wa, wb, wc, ra, rb, NEG_FIRST)          \
+  if (cond) {                                                                                           \
+    float t;                                                                                            \
+    t = xa; xa = xb; xb = t; t = ya; ya = yb; yb = t; t = za; za = zb; zb = t;                          \
+    t = va; va = wa; wa = t; t = vb; vb = wb; wb = t; t = vc; vc = wc; wc = t;                          \
+    t = ra; ra = rb; rb = t;                                                                            \
+    if (NEG_FIRST) { xa = -xa; ya = -ya; za = -za; va = -va; vb = -vb; vc = -vc; }                      \
+    else { xb = -xb; yb = -yb; zb = -zb; wa = -wa; wb = -wb; wc = -wc; }                                \
+  }
+  // swap (1,2) negate col 2; swap (1,3) negate col 1; swap (2,3) negate col 3  (SVD.hpp:516-676)
+  ZPC_SWAPNEG(r0 < r1, b00, b10, b20, b01, b11, b21, v00, v10, v20, v01, v11, v21, r0, r1, false)
+  ZPC_SWAPNEG(r0 < r2, b00, b10, b20, b02, b12, b22, v00, v10, v20, v02, v12, v22, r0, r2, true)
+  ZPC_SWAPNEG(r1 < r2, b01, b11, b21, b02, b12, b22, v01, v11, v21, v02, v12, v22, r1, r2, false)
+#undef ZPC_SWAPNEG
+  float u00 = 1.f, u01 = 0.f, u02 = 0.f, u10 = 0.f, u11 = 1.f, u12 = 0.f, u20 = 0.f, u21 = 0.f, u22 = 1.f;
+  float c, s;
+  qr_givens(b00, b10, c, s);  // rows (0,1)
+  rot_pair(b00, b10, c, s); rot_pair(b01, b11, c, s); rot_pair(b02, b12, c, s);
+  rot_pair(u00, u01, c, s); rot_pair(u10, u11, c, s); rot_pair(u20, u21, c, s);
+  qr_givens(b00, b20, c, s);  // rows (0,2)
+  rot_pair(b00, b20, c, s); rot_pair(b01, b21, c, s); rot_pair(b02, b22, c, s);
+  rot_pair(u00, u02, c, s); rot_pair(u10, u12, c, s); rot_pair(u20, u22, c, s);
+  qr_givens(b11, b21, c, s);  // rows (1,2)
+  rot_pair(b10, b20, c, s); rot_pair(b11, b21, c, s); rot_pair(b12, b22, c, s);
+  rot_pair(u01, u02, c, s); rot_pair(u11, u12, c, s); rot_pair(u21, u22, c, s);
+  U[0] = u00; U[1] = u10; U[2] = u20; U[3] = u01; U[4] = u11; U[5] = u21; U[6] = u02; U[7] = u12; U[8] = u22;
+  V[0] = v00; V[1] = v10; V[2] = v20; V[3] = v01; V[4] = v11; V[5] = v21; V[6] = v02; V[7] = v12; V[8] = v22;
+  S[0] = b00; S[1] = b11; S[2] = b22;
+}
+
+// lame_parameters<float> (physics/ConstitutiveModel.hpp:34-38): mu goes through double because of the
+// 0.5 literal, lambda is all-float.  Evaluated once on the host and passed to the kernels.
+inline void lame_host(float E, float nu, float &mu, float &lam) {
+  mu = (float)(0.5 * E / (1 + nu));
+  lam = E * nu / ((1 + nu) * (1 - 2 * nu));
+}
+
+// PF = P(F) F^T * volume for the fixed-corotated model
+__device__ __forceinline__ void stress_fcr(float volume, float mu, float lam, const float (&F)[9], float (&PF)[9]) {
+  float U[9], S[3], V[9];
+  svd3(F, U, S, V);
+  const float J = S[0] * S[1] * S[2];
+  const float smu = 2.f * mu, sl = lam * (J - 1.f);
+  const float Ph[3] = {smu * (S[0] - 1.f) + sl * (S[1] * S[2]), smu * (S[1] - 1.f) + sl * (S[0] * S[2]),
+                       smu * (S[2] - 1.f) + sl * (S[0] * S[1])};
+  float P[9];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      P[3 * c + r] = Ph[0] * U[r] * V[c] + Ph[1] * U[3 + r] * V[3 + c] + Ph[2] * U[6 + r] * V[6 + c];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) PF[3 * c + r] = (P[r] * F[c] + P[3 + r] * F[3 + c] + P[6 + r] * F[6 + c]) * volume;
+}
+
+// LocalArena::init (simulation/Utils.hpp:51-70): base node, in-cell offset (scaled by dx), 3x3 weights
+struct Arena {
+  int corner[3];
+  float local[3];   // (X - corner) * dx
+  float w[3][3];
+};
+__device__ __forceinline__ void arena_init(Arena &a, float dx, const float (&pos)[3]) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float X = pos[d] / dx;  // reference divides (Utils.hpp:56), it does not multiply by 1/dx
+    const int cn = (int)floorf(X - 0.5f);
+    const float lp = X - (float)cn;
+    const float d0 = lp - floorf(lp - 0.5f);
+    a.corner[d] = cn;
+    a.w[d][0] = 0.5f * (1.5f - d0) * (1.5f - d0);
+    const float d1 = d0 - 1.0f;
+    a.w[d][1] = 0.75f - d1 * d1;
+    const float zz = 0.5f + d1;
+    a.w[d][2] = 0.5f * zz * zz;
+    a.local[d] = lp * dx;
+  }
+}
+
+// home block of a particle as ComputeSparsity assigns it (SparsityOp.hpp:68-79): floor_div(floor(x/dx+.5)-2, 4)
+__device__ __forceinline__ int sparsity_coord(float x, float dxinv) { return (int)floorf(x * dxinv + 0.5f) - 2; }
+__device__ __forceinline__ int floor_div4(int c) { return c >> 2; }  // arithmetic shift == floor division by 4
+
+// ---- legacy hash table lookups (container/HashTable.hpp) -----------------------------------------
+// do_hash (:496-500) + 64-bit hash_combine (math/Hash.hpp:17-27), then "(h % size + size) % size" (:358)
+__device__ __forceinline__ int hash_slot0(int kx, int ky, int kz, int table_size) {
+  unsigned long long seed = (unsigned long long)(long long)kx;
+  seed ^= ((unsigned long long)(long long)ky + 0x9e3779b97f4a7c15ULL + (seed << 12) + (seed >> 4));
+  seed ^= ((unsigned long long)(long long)kz + 0x9e3779b97f4a7c15ULL + (seed << 12) + (seed >> 4));
+  const int e = (int)(unsigned)seed;
+  return (e % table_size + table_size) % table_size;
+}
+// HashTableView::query (:447-456) along insert's probe sequence (:386)
+__device__ __forceinline__ int table_query(int kx, int ky, int kz, int table_size, const int *__restrict__ keys,
+                                           const int *__restrict__ indices) {
+  int slot = hash_slot0(kx, ky, kz, table_size);
+  while (true) {
+    const int ix = indices[slot];
+    if (ix == -1) return -1;
+    const int *k = keys + 3 * (size_t)slot;
+    if (k[0] == kx && k[1] == ky && k[2] == kz) return ix;
+    slot = (slot + 127) % table_size;
+  }
+}
+
+}  // namespace zpcm

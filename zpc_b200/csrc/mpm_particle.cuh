@@ -1,0 +1,92 @@
+// Per-particle scatter / gather straight against the hashed grid in global memory — the reference's
+// own formulation (simulation/transfer/P2G.hpp:107-125, G2P.hpp:56-66) with the 27 hash probes of
+// unpack_coord_in_grid (simulation/Utils.hpp:20-28) reduced to the <= 8 distinct blocks of the stencil.
+// Used by the any-order AoS kernels (mpm.cu) and as the stray path of the binned kernels.
+#pragma once
+#include "mpm_math.cuh"
+
+namespace zpcp {
+
+// tile offsets (in floats) of the 2x2x2 blocks around the stencil; -1 where not needed / absent
+__device__ __forceinline__ void resolve_blocks(const int (&corner)[3], const zpc_hashtable_view &tb, int nch, long long (&off)[8]) {
+  const int b0x = corner[0] >> 2, b0y = corner[1] >> 2, b0z = corner[2] >> 2;
+  const bool nx = (corner[0] & 3) >= 2, ny = (corner[1] & 3) >= 2, nz = (corner[2] & 3) >= 2;  // stencil spills over
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ox = i >> 2, oy = (i >> 1) & 1, oz = i & 1;
+    const bool need = (!ox || nx) && (!oy || ny) && (!oz || nz);
+    int id = -1;
+    if (need) id = zpcm::table_query(b0x + ox, b0y + oy, b0z + oz, tb.tableSize, tb.keys, tb.indices);
+    off[i] = id < 0 ? -1 : (long long)id * nch * 64;
+  }
+}
+
+static __device__ __noinline__ void p2g_scatter_particle(const float (&pos)[3], const float (&vel)[3], float mass, const float (&C)[9],
+                                                  const float (&F)[9], const zpc_hashtable_view &tb, float *tiles, int nch,
+                                                  float dx, float dt, float volume, float mu, float lam) {
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  float contrib[9];
+  zpcm::stress_fcr(volume, mu, lam, F, contrib);
+#pragma unroll
+  for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+  zpcm::Arena ar;
+  zpcm::arena_init(ar, dx, pos);
+  long long off[8];
+  resolve_blocks(ar.corner, tb, nch, off);
+  const int lx0 = ar.corner[0] & 3, ly0 = ar.corner[1] & 3, lz0 = ar.corner[2] & 3;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int lx = lx0 + i, ly = ly0 + j, lz = lz0 + k;
+        const long long o = off[((lx >> 2) << 2) | ((ly >> 2) << 1) | (lz >> 2)];
+        if (o < 0) continue;  // block absent from the partition: cannot happen after partition_build on these positions
+        float *t = tiles + o + (((lx & 3) << 4) | ((ly & 3) << 2) | (lz & 3));
+        const float x0 = (float)i * dx - ar.local[0], x1 = (float)j * dx - ar.local[1], x2 = (float)k * dx - ar.local[2];
+        const float W = ar.w[0][i] * ar.w[1][j] * ar.w[2][k];
+        atomicAdd(t, mass * W);
+        const float Wm = W * mass;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          atomicAdd(t + (1 + d) * 64, Wm * (vel[d] + (C[d] * x0 + C[3 + d] * x1 + C[6 + d] * x2)));
+          atomicAdd(t + (4 + d) * 64, (contrib[d] * x0 + contrib[3 + d] * x1 + contrib[6 + d] * x2) * W);
+        }
+      }
+}
+
+// vel = sum W v_i ; G[r + 3e] = sum W v_i[r] * o_e   (o = stencil offset 0..2), so that
+// C[r + 3e] = D_inv * (dx * G[r+3e] - local_e * vel[r])  ==  sum W v_i[r] * xixp[e] * D_inv  (G2P.hpp:65)
+static __device__ __noinline__ void g2p_gather_particle(const zpcm::Arena &ar, const zpc_hashtable_view &tb, const float *tiles, int nch,
+                                                 float (&vel)[3], float (&G)[9]) {
+  long long off[8];
+  resolve_blocks(ar.corner, tb, nch, off);
+  const int lx0 = ar.corner[0] & 3, ly0 = ar.corner[1] & 3, lz0 = ar.corner[2] & 3;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) vel[d] = 0.f;
+#pragma unroll
+  for (int d = 0; d < 9; ++d) G[d] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int lx = lx0 + i, ly = ly0 + j, lz = lz0 + k;
+        const long long o = off[((lx >> 2) << 2) | ((ly >> 2) << 1) | (lz >> 2)];
+        if (o < 0) continue;
+        const float *t = tiles + o + (((lx & 3) << 4) | ((ly & 3) << 2) | (lz & 3));
+        const float W = ar.w[0][i] * ar.w[1][j] * ar.w[2][k];
+        const float oe[3] = {(float)i, (float)j, (float)k};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float wv = W * __ldg(t + (1 + r) * 64);
+          vel[r] += wv;
+#pragma unroll
+          for (int e = 0; e < 3; ++e) G[r + 3 * e] = fmaf(wv, oe[e], G[r + 3 * e]);
+        }
+      }
+}
+
+}  // namespace zpcp

@@ -1,0 +1,81 @@
+"""Composed explicit APIC substep on one GPU, through the public functor API.
+
+    partition_for_particles -> CleanGridBlocks -> P2GTransfer -> ComputeGridBlockVelocity -> G2PTransfer
+
+`layout="aos"` keeps the reference's Particles layout and order (drop-in path); `layout="binned"` keeps
+particles in block-binned AoSoA TileVectors and re-bins every `rebin_every` substeps.
+"""
+import torch
+
+from . import api
+
+
+def default_expected_blocks(n):
+    return max(n // 256, 1024)
+
+
+class MpmSolver:
+    def __init__(self, P, dx, volume, dt, gravity=-9.8, mode=1, layout="binned", expected_blocks=None,
+                 rebin_every=8, E=5.0e4, nu=0.4, device="cuda", shuffle_free=True):
+        self.device = device
+        self.dx, self.dt, self.mode = float(dx), float(dt), int(mode)
+        self.extf = (0.0, float(gravity), 0.0)
+        self.model = api.model_fcr(volume, E, nu)
+        self.layout = layout
+        self.n = int(P["x"].shape[0])
+        eb = expected_blocks or default_expected_blocks(self.n)
+        self.table = api.HashTable(eb, device)
+        self.block_cap = self.table.table_size // 16
+        self.grids = api.Grids(dx, self.block_cap, 7, device)
+        self.max_vel_sqr = torch.zeros(1, dtype=torch.float32, device=device)
+        self.rebin_every = int(rebin_every)
+        self.step_no = 0
+        self.aos = api.Particles(P, device)
+        if layout == "binned":
+            self.bins = api.ParticleBins(self.n, self.block_cap, device)
+            self.bins_alt = api.ParticleBins(self.n, self.block_cap, device)
+            self.order = torch.empty(self.n, dtype=torch.int32, device=device)
+            api.partition_for_particles(api.vec3_port(self.aos.x), self.n, self.dx, self.table)
+            api.bin_particles(self.aos, self.table, self.dx, self.bins, self.order)
+            self.aos = None if shuffle_free else self.aos
+        elif layout != "aos":
+            raise ValueError(layout)
+
+    # positions as an iterator port for the partition build
+    def _x_port(self):
+        if self.layout == "binned":
+            return self.bins.pars.port(api.PB_X)
+        return api.vec3_port(self.aos.x)
+
+    def _pars(self):
+        return self.bins if self.layout == "binned" else self.aos
+
+    def partition(self, stream=None):
+        api.partition_for_particles(self._x_port(), self.n, self.dx, self.table, stream)
+
+    def transfer(self, stream=None):
+        """the fused P2G + grid + G2P part of the substep (the roofline-quoted part)"""
+        api.clean_grid_blocks(self.grids, self.table, stream)
+        api.p2g_transfer(self._pars(), self.table, self.grids, self.dt, self.model, stream)
+        self.max_vel_sqr.zero_()
+        api.compute_grid_block_velocity(self.grids, self.table, self.dt, self.extf, self.mode, self.max_vel_sqr, stream)
+        api.g2p_transfer(self._pars(), self.table, self.grids, self.dt, stream)
+
+    def rebin(self, stream=None):
+        self.partition(stream)
+        api.rebin_particles(self.bins, self.table, self.dx, self.bins_alt, stream)
+        self.bins, self.bins_alt = self.bins_alt, self.bins
+
+    def substep(self, stream=None):
+        if self.layout == "binned" and self.step_no > 0 and self.rebin_every > 0 and self.step_no % self.rebin_every == 0:
+            self.rebin(stream)  # leaves a partition built from the current positions
+        else:
+            self.partition(stream)
+        self.transfer(stream)
+        self.step_no += 1
+
+    def particles_host(self):
+        """AoS dict on the host, in the solver's CURRENT particle order."""
+        if self.layout == "binned":
+            return {k: self.bins.attr(k).cpu().numpy() for k in ("x", "v", "m", "C", "F")}
+        return self.aos.to_host()
