@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — MPM particle<->sparse-grid substep throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3|C2|C1] [--impl ours|reference]
+
+One "step" = one explicit APIC substep over the whole synthetic particle cloud:
+  partition build -> clear grid -> P2G -> grid update -> G2P   (+ the re-bin every `--rebin-every` substeps).
+value   = particle-substeps / s, inputs resident in HBM (whole job, all ranks; max-over-ranks time).
+e2e     = the same metric through the reference-facing host-buffer call (MpmSolver.substep_host): pinned host
+          arrays -> H2D -> substep on the reference's AoS layout -> D2H of the particle state, every step.
+roofline= the dominant kernel (binned P2G): algorithmic bytes (100 B/particle read + 28 B per
+          active cell written at 8 ppc = 103.5 B/particle) / its CUDA-event time, against MEASURED_PEAKS.json.
+cpu_baseline = the reference's own OpenMP path (oracle/_ref, built from /root/reference) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mpm_particle_substeps_per_sec"
+UNIT = "particle-substeps/s"
+BYTES_PER_PARTICLE = dict(clean=28 / 8, p2g=100 + 28 / 8, grid_update=(28 + 12) / 8, g2p=48 + 96 + 12 / 8)  # sum 257.5
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU implementation on a bounded sample
+# ---------------------------------------------------------------------------------------------------------
+def run_reference_sample(G, steps, warmup, sample_s=50):
+    """Times the reference (oracle/_ref = unmodified reference headers on omp_exec, all host threads; falls back to
+    the single-thread C port when the reference library was not built) on an s^3-cell sub-cube of the workload."""
+    import numpy as np  # noqa: F401
+    from oracle.pyoracle import Oracle, Ref
+    from zpc_b200 import synth
+    cores = os.cpu_count() or 1
+    if Ref.available():
+        P = synth.elastic_cube(sample_s, G)
+        n = P["x"].shape[0]
+        r = Ref()
+        h = r.mpm(n, P["dx"], cores, max(n // 8, 1))
+        h.set_particles(P)
+
+        def step():
+            h.partition(); h.clean_grid(); h.p2g(synth.DT, synth.MODEL["E"], synth.MODEL["nu"], P["volume"])
+            h.grid_update(synth.DT, synth.GRAVITY, 1); h.g2p(synth.DT)
+        kind = "reference"
+        sample = "%d-particle sub-cube (%d^3 cells, 8 ppc, dx=1/%d) of the workload, omp_exec().threads(%d)" % (n, sample_s, G, cores)
+    else:
+        sample_s = min(sample_s, 20)
+        P = synth.elastic_cube(sample_s, G)
+        n = P["x"].shape[0]
+        o = Oracle()
+        cores = 1
+
+        def step():
+            o.substep(P, P["dx"], synth.DT, synth.MODEL["E"], synth.MODEL["nu"], P["volume"], synth.GRAVITY, 1)
+        kind = "port"
+        sample = "%d-particle sub-cube (%d^3 cells, 8 ppc, dx=1/%d), scalar C port, 1 thread" % (n, sample_s, G)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(value=n / dt, unit=UNIT, cores=cores, kind=kind, sample=sample, ms_per_step=dt * 1e3, n=n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default=os.environ.get("ZPC_BENCH_CONFIG", "C3"))
+    ap.add_argument("--rebin-every", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from zpc_b200 import synth
+    G, s = synth.CONFIGS[args.config]
+    n_total = 8 * s ** 3
+    workload = "%s: %d particles (%d^3 cells x 8 ppc), %d^3 sparse grid (dx=1/%d), fixed-corotated APIC fp32" % (
+        args.config, n_total, s, G, G)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_reference_sample(G, max(args.steps, 1), max(args.warmup, 0))
+        line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+                    data="synthetic", impl="reference",
+                    config=dict(workload=workload, sample=r["sample"]),
+                    cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"]),
+                    e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    from zpc_b200 import api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hbm_peak, peak_src = peaks()
+
+    # ---- build the (rank's shard of the) workload ----------------------------------------------------------
+    if world == 1:
+        from zpc_b200.solver import MpmSolver
+        P = synth.elastic_cube(s, G)
+        sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="binned", rebin_every=args.rebin_every)
+        n_local = sol.n
+    else:
+        from zpc_b200.dist_solver import DistMpmSolver
+        P = synth.elastic_cube_slab(s, G, rank, world)
+        sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, rebin_every=args.rebin_every)
+        n_local = sol.n
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sol.substep()
+    barrier()
+    launches0 = api.kernel_launch_count()
+    sol.stage_events = []
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sol.substep()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = api.kernel_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    stage = sol.stage_times_ms()
+    sol.stage_events = None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        cnt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(cnt)
+        launches = int(cnt.item())
+    ms_per_step = ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+    nblocks = sol.table.size()
+
+    # ---- per-kernel roofline from the live CUDA-event stage times ---------------------------------------------
+    per_step = {k: v / args.steps for k, v in stage.items()}
+    n_rebins = sum(1 for i in range(args.warmup, args.warmup + args.steps) if i > 0 and args.rebin_every > 0 and i % args.rebin_every == 0)
+    fused_ms = sum(per_step.get(k, 0.0) for k in ("clean", "p2g", "grid_update", "g2p"))
+    kern = {}
+    for k, bpp in BYTES_PER_PARTICLE.items():
+        if per_step.get(k):
+            gbs = bpp * n_local / (per_step[k] * 1e-3) / 1e9
+            kern[k] = dict(ms=per_step[k], algorithmic_gbps=gbs, frac=gbs / hbm_peak)
+    dom = "p2g"
+    roof = dict(bound="hbm", kernel="p2g_binned_kernel", achieved=kern.get(dom, {}).get("algorithmic_gbps"), peak=hbm_peak, unit="GB/s",
+                frac=kern.get(dom, {}).get("frac"), traffic=None, peak_source=peak_src,
+                algorithmic_bytes_per_launch=BYTES_PER_PARTICLE[dom] * n_local)
+    fused_gbps = 257.5 * n_local / (fused_ms * 1e-3) / 1e9 if fused_ms else None
+    fused = dict(ms=fused_ms, bytes_per_particle=257.5, achieved=fused_gbps, frac=(fused_gbps / hbm_peak) if fused_gbps else None,
+                 kernels=kern, partition_ms=per_step.get("partition"), rebin_ms_each=(stage.get("rebin", 0.0) / n_rebins) if n_rebins else None,
+                 rebins_in_timed_region=n_rebins)
+
+    # ---- e2e: host buffers in, host buffers out, through the reference-facing call (N = 1) -----------------------
+    e2e = None
+    if world == 1 and args.e2e_steps > 0:
+        del sol
+        torch.cuda.empty_cache()
+        from zpc_b200.solver import MpmSolver
+        sol2 = MpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="aos")
+        hin = {k: torch.from_numpy(P[k]).pin_memory() for k in ("x", "v", "m", "C", "F")}
+        hout = {k: torch.empty_like(hin[k]).pin_memory() for k in ("x", "v", "C", "F")}
+        bi = sum(hin[k].numel() * 4 for k in hin)
+        bo = sum(hout[k].numel() * 4 for k in hout) + 4
+        sol2.substep_host(hin, hout)           # warm-up (allocations, first-touch)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            sol2.substep_host(hin, hout)
+            torch.cuda.synchronize()
+            for k in ("x", "v", "C", "F"):     # feed the result back like a host-side caller would
+                hin[k], hout[k] = hout[k], hin[k]
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        e2e = dict(value=n_total / dt, unit=UNIT, h2d_bytes_per_step=bi, d2h_bytes_per_step=bo, ms_per_step=dt * 1e3,
+                   steps=args.e2e_steps, path="MpmSolver.substep_host (AoS drop-in kernels)")
+        del sol2
+    elif world > 1:
+        e2e = dict(value=None, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0, note="host-buffer call measured at N=1 only")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_reference_sample(G, 2, 1)
+            cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"], ms_per_step=r["ms_per_step"])
+        except Exception as ex:  # the checker is optional; never let it break the GPU number
+            cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(ex))
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
+                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=workload, layout="block-binned AoSoA TileVector<f32,32>, re-bin every %d substeps" % args.rebin_every,
+                                active_blocks=nblocks, l2="inputs (%.1f GB particle state) exceed the 126 MB L2; no explicit flush" % (n_local * 100 / 1e9),
+                                parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, NCCL halo exchange of shared grid blocks" % world),
+                    substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,
+                    clocks=clocks)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

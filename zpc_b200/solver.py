@@ -30,6 +30,7 @@ class MpmSolver:
         self.max_vel_sqr = torch.zeros(1, dtype=torch.float32, device=device)
         self.rebin_every = int(rebin_every)
         self.step_no = 0
+        self.stage_events = None
         self.aos = api.Particles(P, device)
         if layout == "binned":
             self.bins = api.ParticleBins(self.n, self.block_cap, device)
@@ -50,21 +51,46 @@ class MpmSolver:
     def _pars(self):
         return self.bins if self.layout == "binned" else self.aos
 
+    # ---- optional per-stage CUDA-event timing (bench.py) ----
+    def _mark(self, name):
+        if self.stage_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.stage_events.append((name, e))
+
+    def stage_times_ms(self):
+        """sum of elapsed ms per stage over everything recorded since stage_events was reset"""
+        out = {}
+        ev = self.stage_events or []
+        for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
+            if n1 != "begin":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
     def partition(self, stream=None):
+        self._mark("begin")
         api.partition_for_particles(self._x_port(), self.n, self.dx, self.table, stream)
+        self._mark("partition")
 
     def transfer(self, stream=None):
         """the fused P2G + grid + G2P part of the substep (the roofline-quoted part)"""
+        self._mark("begin")
         api.clean_grid_blocks(self.grids, self.table, stream)
+        self._mark("clean")
         api.p2g_transfer(self._pars(), self.table, self.grids, self.dt, self.model, stream)
+        self._mark("p2g")
         self.max_vel_sqr.zero_()
         api.compute_grid_block_velocity(self.grids, self.table, self.dt, self.extf, self.mode, self.max_vel_sqr, stream)
+        self._mark("grid_update")
         api.g2p_transfer(self._pars(), self.table, self.grids, self.dt, stream)
+        self._mark("g2p")
 
     def rebin(self, stream=None):
         self.partition(stream)
+        self._mark("begin")
         api.rebin_particles(self.bins, self.table, self.dx, self.bins_alt, stream)
         self.bins, self.bins_alt = self.bins_alt, self.bins
+        self._mark("rebin")
 
     def substep(self, stream=None):
         if self.layout == "binned" and self.step_no > 0 and self.rebin_every > 0 and self.step_no % self.rebin_every == 0:
@@ -73,6 +99,23 @@ class MpmSolver:
             self.partition(stream)
         self.transfer(stream)
         self.step_no += 1
+
+    def substep_host(self, hin, hout, stream=None):
+        """Reference-facing call with HOST buffers (pinned torch tensors x,v,m,C,F in; x,v,C,F out), any particle
+        order: upload -> partition -> clean -> P2G -> grid update -> G2P on the reference's AoS layout -> download.
+        Returns max |v|^2 (the CFL scalar the reference reads back every substep, simulation/mpm/Simulator.hpp:19-26)."""
+        a = self.aos
+        for k in ("x", "v", "m", "C", "F"):
+            getattr(a, k).copy_(hin[k], non_blocking=True)
+        api.partition_for_particles(api.vec3_port(a.x), self.n, self.dx, self.table, stream)
+        api.clean_grid_blocks(self.grids, self.table, stream)
+        api.p2g_transfer(a, self.table, self.grids, self.dt, self.model, stream)
+        self.max_vel_sqr.zero_()
+        api.compute_grid_block_velocity(self.grids, self.table, self.dt, self.extf, self.mode, self.max_vel_sqr, stream)
+        api.g2p_transfer(a, self.table, self.grids, self.dt, stream)
+        for k in ("x", "v", "C", "F"):
+            hout[k].copy_(getattr(a, k), non_blocking=True)
+        return float(self.max_vel_sqr.item())   # D2H read = sync point
 
     def particles_host(self):
         """AoS dict on the host, in the solver's CURRENT particle order."""
