@@ -33,9 +33,10 @@ constexpr int TS = 32;                  // particle tile length
 constexpr int NCH = ZPC_PB_NCH;         // 25 channels
 constexpr int BIN_MAX = ZPCB200_BIN_MAX;
 constexpr int P2G_NT = 512, P2G_NW = P2G_NT / 32;
-constexpr int NGRP = 16 * 6 + 1;        // (nominal column, z in [-1,4]) groups + stray group
-constexpr int GRP_STRAY = 96;
-constexpr int NCHUNK = BIN_MAX / 32;
+constexpr int CHUNK = P2G_NT;           // particles staged per pass (one record per thread)
+constexpr int NCOL6 = 36;               // (x,y) columns of home cells in [-1,4]^2: 16 nominal + 20 ring
+constexpr int NGRP = NCOL6 * 6 + 1;     // (column, z in [-1,4]) groups + far-stray group
+constexpr int GRP_FAR = NCOL6 * 6;
 constexpr int REC_F = 28;               // floats per particle record
 constexpr int COL_F = 7 * 72;           // column arena: 7 channels x (8 z x 3 x 3) nodes
 
@@ -43,15 +44,44 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ size_t pslot(size_t i) { return ((i >> 5) * NCH) * TS + (i & 31); }  // channel 0 of particle i
 
 struct P2GSmem {
-  float rec[P2G_NW][32][REC_F];     // 57344 B; reused as the 8 output tiles [8][7][64] (14336 B)
-  float col[P2G_NW][COL_F];         // 32256 B
-  unsigned short hist[NCHUNK][NGRP + 1];
+  float rec[CHUNK][REC_F];          // 57344 B; reused as the 8 output tiles [8][7][64] (14336 B) at the end
+  float col[16][COL_F];             // 32256 B: private arenas of the 16 nominal columns
+  float ring[8 * 448];              // 14336 B: tile-layout arena for the (rare) ring-column particles
   unsigned short order[BIN_MAX];
   unsigned char grp_of[BIN_MAX];
-  int gstart[NGRP + 1];
+  int cnt[NGRP + 3];
+  int gstart[NGRP + 3];
   int tile_id[8];
-  int nstray;
 };
+static_assert(sizeof(P2GSmem) <= 113 * 1024, "two CTAs per SM");
+
+// 6x6 column index of the 20 ring columns (x or y outside [0,3]); c6 = (x+1)*6 + (y+1)
+__constant__ unsigned char c_ring_c6[20] = {0, 1, 2, 3, 4, 5, 6, 11, 12, 17, 18, 23, 24, 29, 30, 31, 32, 33, 34, 35};
+
+// lanes = the 27 stencil offsets.  Sweeps the records of sorted positions [lo,hi) (all in one cell) and returns the
+// 7 channel sums of this lane's node.
+struct LaneCoef {
+  float ax, bx, cx, ay, by, cy, az, bz, cz, fx, fy, fz;
+};
+__device__ __forceinline__ void sweep_cell(const float (*rec)[REC_F], int lo, int hi, const LaneCoef &L, float (&acc)[7]) {
+#pragma unroll 2
+  for (int p = lo; p < hi; ++p) {
+    const float4 *rp = reinterpret_cast<const float4 *>(rec[p]);
+    const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3], r4 = rp[4], r5 = rp[5], r6 = rp[6];
+    const float wx = fmaf(fmaf(L.ax, r0.x, L.bx), r0.x, L.cx), wy = fmaf(fmaf(L.ay, r0.y, L.by), r0.y, L.cy),
+                wz = fmaf(fmaf(L.az, r0.z, L.bz), r0.z, L.cz);
+    const float W = wx * wy * wz;
+    acc[0] = fmaf(W, r0.w, acc[0]);
+    // A = r1.xyz ; B row d = (r1.w r2.x r2.y), (r2.z r2.w r3.x), (r3.y r3.z r3.w)
+    acc[1] = fmaf(W, fmaf(r2.y, L.fz, fmaf(r2.x, L.fy, fmaf(r1.w, L.fx, r1.x))), acc[1]);
+    acc[2] = fmaf(W, fmaf(r3.x, L.fz, fmaf(r2.w, L.fy, fmaf(r2.z, L.fx, r1.y))), acc[2]);
+    acc[3] = fmaf(W, fmaf(r3.w, L.fz, fmaf(r3.z, L.fy, fmaf(r3.y, L.fx, r1.z))), acc[3]);
+    // a = r4.xyz ; K row d = (r4.w r5.x r5.y), (r5.z r5.w r6.x), (r6.y r6.z r6.w)
+    acc[4] = fmaf(W, fmaf(r5.y, L.fz, fmaf(r5.x, L.fy, fmaf(r4.w, L.fx, r4.x))), acc[4]);
+    acc[5] = fmaf(W, fmaf(r6.x, L.fz, fmaf(r5.w, L.fy, fmaf(r5.z, L.fx, r4.y))), acc[5]);
+    acc[6] = fmaf(W, fmaf(r6.w, L.fz, fmaf(r6.z, L.fy, fmaf(r6.y, L.fx, r4.z))), acc[6]);
+  }
+}
 
 __global__ void __launch_bounds__(P2G_NT, 2)
 p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
@@ -68,150 +98,163 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 
   // ---- (0) arena blocks, zero scratch ------------------------------------------------------------------
   if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
-  for (int i = tid; i < NCHUNK * (NGRP + 1); i += P2G_NT) (&S.hist[0][0])[i] = 0;
-  for (int i = tid; i < P2G_NW * COL_F; i += P2G_NT) (&S.col[0][0])[i] = 0.f;
-  __syncthreads();
-
-  // ---- (a) counting sort by (column, z) of the current home cell -------------------------------------
-  // chunk c = 32 consecutive particles; thread handles chunks w, w+16
-  int my_grp[NCHUNK / P2G_NW], my_rank[NCHUNK / P2G_NW];
-#pragma unroll
-  for (int it = 0; it < NCHUNK / P2G_NW; ++it) {
-    const int c = w + it * P2G_NW, i = c * 32 + l;
-    int g = NGRP;  // invalid
-    if (i < np) {
-      const size_t s = pslot((size_t)p0 + i);
-      // current base node (division form, as LocalArena does) relative to the bin's block origin
-      const int cx = (int)floorf(pars[s + (ZPC_PB_X + 0) * TS] / dx - 0.5f) - 1 - 4 * kx;
-      const int cy = (int)floorf(pars[s + (ZPC_PB_X + 1) * TS] / dx - 0.5f) - 1 - 4 * ky;
-      const int cz = (int)floorf(pars[s + (ZPC_PB_X + 2) * TS] / dx - 0.5f) - 1 - 4 * kz;
-      g = ((unsigned)cx < 4u && (unsigned)cy < 4u && (unsigned)(cz + 1) < 6u) ? (cx * 4 + cy) * 6 + (cz + 1) : GRP_STRAY;
-      S.grp_of[i] = (unsigned char)g;
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, g);
-    my_grp[it] = g;
-    my_rank[it] = __popc(peers & lanemask_lt());
-    if (g < NGRP && l == __ffs(peers) - 1) S.hist[c][g] = (unsigned short)__popc(peers);
-  }
-  __syncthreads();
-  if (tid < NGRP) {  // exclusive prefix over chunks for group tid
-    int run = 0;
-    for (int c = 0; c < NCHUNK; ++c) { const int t = S.hist[c][tid]; S.hist[c][tid] = (unsigned short)run; run += t; }
-    S.gstart[tid] = run;  // count for now
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int g = 0; g < NGRP; ++g) { const int t = S.gstart[g]; S.gstart[g] = run; run += t; }
-    S.gstart[NGRP] = run;
-    S.nstray = run - S.gstart[GRP_STRAY];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int it = 0; it < NCHUNK / P2G_NW; ++it) {
-    const int c = w + it * P2G_NW, i = c * 32 + l, g = my_grp[it];
-    if (g < NGRP) S.order[S.gstart[g] + S.hist[c][g] + my_rank[it]] = (unsigned short)i;
-  }
-  __syncthreads();
-
-  // ---- (b) column sweep: warp w owns column (w>>2, w&3) -----------------------------------------------
+  for (int i = tid; i < NGRP + 3; i += P2G_NT) S.cnt[i] = 0;
   {
-    const int cs = S.gstart[w * 6], ce = S.gstart[w * 6 + 6];
-    // lane as stencil offset (ox,oy,oz); quadratic B-spline as a polynomial in d0 with per-lane coefficients:
+    float4 *z = reinterpret_cast<float4 *>(&S.col[0][0]);  // col and ring are contiguous
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < (16 * COL_F + 8 * 448) / 4; i += P2G_NT) z[i] = zero;
+  }
+  __syncthreads();
+
+  // ---- (a) counting sort by (column, z) of the CURRENT home cell ----------------------------------------
+  for (int i = tid; i < np; i += P2G_NT) {
+    const size_t s = pslot((size_t)p0 + i);
+    // current base node (division form, as LocalArena does), minus one = home cell, relative to the bin's block origin
+    const int cx = (int)floorf(pars[s + (ZPC_PB_X + 0) * TS] / dx - 0.5f) - 1 - 4 * kx;
+    const int cy = (int)floorf(pars[s + (ZPC_PB_X + 1) * TS] / dx - 0.5f) - 1 - 4 * ky;
+    const int cz = (int)floorf(pars[s + (ZPC_PB_X + 2) * TS] / dx - 0.5f) - 1 - 4 * kz;
+    const int g = ((unsigned)(cx + 1) < 6u && (unsigned)(cy + 1) < 6u && (unsigned)(cz + 1) < 6u)
+                      ? ((cx + 1) * 6 + (cy + 1)) * 6 + (cz + 1)
+                      : GRP_FAR;
+    S.grp_of[i] = (unsigned char)g;
+    atomicAdd(&S.cnt[g], 1);
+  }
+  __syncthreads();
+  if (w == 0) {  // exclusive scan of the 217 counters, 7 per lane
+    int c[7], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { const int g = l * 7 + k; c[k] = g < NGRP ? S.cnt[g] : 0; sum += c[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (l >= d) inc += t; }
+    int run = inc - sum;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int g = l * 7 + k;
+      if (g <= NGRP) { S.gstart[g] = run; S.cnt[g] = run; }
+      run += c[k];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < np; i += P2G_NT) S.order[atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
+  __syncthreads();
+  if (tid < NGRP) {  // make the order inside each group deterministic (ascending slot); groups are ~8 long
+    const int lo = S.gstart[tid], hi = S.gstart[tid + 1];
+    if (hi - lo <= 96)
+      for (int a = lo + 1; a < hi; ++a) {
+        const unsigned short v = S.order[a];
+        int b = a - 1;
+        while (b >= lo && S.order[b] > v) { S.order[b + 1] = S.order[b]; --b; }
+        S.order[b + 1] = v;
+      }
+  }
+  __syncthreads();
+
+  // ---- (b) per chunk: records (one thread per particle), then column sweeps (lanes = stencil offsets) ------
+  const int n_fast = S.gstart[GRP_FAR];
+  const bool lane_on = l < 27;
+  const int lc = lane_on ? l : 0;  // lanes 27..31 shadow lane 0 and never write
+  const int ox = lc / 9, oy = (lc / 3) % 3, oz = lc % 3;
+  LaneCoef L;
+  {
+    // quadratic B-spline as a polynomial in d0 (InterpolationKernel.hpp:105-113):
     //   o=0: .5 d^2 - 1.5 d + 1.125 ; o=1: -d^2 + 2 d - .25 ; o=2: .5 d^2 - .5 d + .125
-    const bool lane_on = l < 27;
-    const int lc = lane_on ? l : 0;  // lanes 27..31 shadow lane 0 and never write
-    const int ox = lc / 9, oy = (lc / 3) % 3, oz = lc % 3;
     const float qa[3] = {0.5f, -1.0f, 0.5f}, qb[3] = {-1.5f, 2.0f, -0.5f}, qc[3] = {1.125f, -0.25f, 0.125f};
-    const float ax = qa[ox], bx = qb[ox], cx_ = qc[ox], ay = qa[oy], by = qb[oy], cy_ = qc[oy], az = qa[oz], bz = qb[oz],
-                cz_ = qc[oz];
-    const float fx = (float)ox, fy = (float)oy, fz = (float)oz;
-    float *colw = S.col[w];
-    const int node_lane = oz * 9 + ox * 3 + oy;  // + zc*9 at flush time
-    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int cur = -1;
-    for (int b0 = cs; b0 < ce; b0 += 32) {
-      const int nb = min(32, ce - b0);
-      int my_zc = 0;
-      if (l < nb) {  // lane as particle
-        const int i = S.order[b0 + l];
-        my_zc = (int)S.grp_of[i] - w * 6;
-        const size_t s = pslot((size_t)p0 + i);
-        float pos[3], vel[3], C[9], F[9], K[9];
-        const float mass = pars[s + ZPC_PB_M * TS];
+    L.ax = qa[ox]; L.bx = qb[ox]; L.cx = qc[ox];
+    L.ay = qa[oy]; L.by = qb[oy]; L.cy = qc[oy];
+    L.az = qa[oz]; L.bz = qb[oz]; L.cz = qc[oz];
+    L.fx = (float)ox; L.fy = (float)oy; L.fz = (float)oz;
+  }
+  for (int cb = 0; cb < n_fast; cb += CHUNK) {
+    {  // records
+      const int pos = cb + tid;
+      if (pos < n_fast) {
+        const size_t s = pslot((size_t)p0 + S.order[pos]);
+        float F[9], K[9];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
-#pragma unroll
-        for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
+        for (int d = 0; d < 9; ++d) F[d] = pars[s + (ZPC_PB_F + d) * TS];
         zpcm::stress_fcr(volume, mu, lam, F, K);
 #pragma unroll
         for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
-        float d0[3], loc[3];
+        float d0[3], loc[3], vel[3], C[9];
+        const float mass = pars[s + ZPC_PB_M * TS];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const float X = pos[d] / dx;
+          const float X = pars[s + (ZPC_PB_X + d) * TS] / dx;
           const float lp = X - floorf(X - 0.5f);
           d0[d] = lp;
           loc[d] = lp * dx;
+          vel[d] = pars[s + (ZPC_PB_V + d) * TS];
         }
-        // record: {d0, m} {A, B col0.x} ... see header comment; mv_d = W (A_d + sum_e B_de o_e), rhs_d = W (a_d + sum_e K_de o_e)
-        float r[REC_F];
-        r[0] = d0[0]; r[1] = d0[1]; r[2] = d0[2]; r[3] = mass;
+#pragma unroll
+        for (int d = 0; d < 9; ++d) C[d] = pars[s + (ZPC_PB_C + d) * TS];
+        // mv_d = W (A_d + sum_e B_de o_e), rhs_d = W (a_d + sum_e K_de o_e), o = stencil offset (0,1,2)^3
+        float4 *dst = reinterpret_cast<float4 *>(S.rec[tid]);
+        float A[3], a[3], B[9], Kd[9];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          r[4 + d] = mass * (vel[d] - (C[d] * loc[0] + C[3 + d] * loc[1] + C[6 + d] * loc[2]));  // A_d
-          r[16 + d] = -(K[d] * loc[0] + K[3 + d] * loc[1] + K[6 + d] * loc[2]);                    // a_d
+          A[d] = mass * (vel[d] - (C[d] * loc[0] + C[3 + d] * loc[1] + C[6 + d] * loc[2]));
+          a[d] = -(K[d] * loc[0] + K[3 + d] * loc[1] + K[6 + d] * loc[2]);
 #pragma unroll
-          for (int e = 0; e < 3; ++e) {
-            r[7 + 3 * d + e] = mass * C[d + 3 * e] * dx;   // B_de
-            r[19 + 3 * d + e] = K[d + 3 * e] * dx;         // K_de (scaled)
-          }
+          for (int e = 0; e < 3; ++e) { B[3 * d + e] = mass * C[d + 3 * e] * dx; Kd[3 * d + e] = K[d + 3 * e] * dx; }
         }
-        float4 *dst = reinterpret_cast<float4 *>(S.rec[w][l]);
-#pragma unroll
-        for (int k = 0; k < REC_F / 4; ++k) dst[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        dst[0] = make_float4(d0[0], d0[1], d0[2], mass);
+        dst[1] = make_float4(A[0], A[1], A[2], B[0]);
+        dst[2] = make_float4(B[1], B[2], B[3], B[4]);
+        dst[3] = make_float4(B[5], B[6], B[7], B[8]);
+        dst[4] = make_float4(a[0], a[1], a[2], Kd[0]);
+        dst[5] = make_float4(Kd[1], Kd[2], Kd[3], Kd[4]);
+        dst[6] = make_float4(Kd[5], Kd[6], Kd[7], Kd[8]);
       }
-      __syncwarp();
-      for (int j = 0; j < nb; ++j) {  // lane as stencil offset
-        const int zc = __shfl_sync(0xffffffffu, my_zc, j);
-        if (zc != cur) {
-          if (cur >= 0 && lane_on) {
-            float *dstc = colw + cur * 9 + node_lane;
+    }
+    __syncthreads();
+    const int ce = min(cb + CHUNK, n_fast);
+    const float(*rec)[REC_F] = S.rec - cb;  // rec[pos] for pos in [cb, ce)
+    {  // nominal column (w>>2, w&3): private arena, plain read-modify-write
+      const int c6 = ((w >> 2) + 1) * 6 + (w & 3) + 1;
+      float *colw = S.col[w] + oz * 9 + ox * 3 + oy;
+#pragma unroll 1
+      for (int zc = 0; zc < 6; ++zc) {
+        const int lo = max(S.gstart[c6 * 6 + zc], cb), hi = min(S.gstart[c6 * 6 + zc + 1], ce);
+        if (lo >= hi) continue;
+        float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        sweep_cell(rec, lo, hi, L, acc);
+        if (lane_on) {
 #pragma unroll
-            for (int ch = 0; ch < 7; ++ch) { dstc[ch * 72] += acc[ch]; acc[ch] = 0.f; }
-          }
-          cur = zc;
+          for (int ch = 0; ch < 7; ++ch) colw[zc * 9 + ch * 72] += acc[ch];
         }
-        const float4 *rp = reinterpret_cast<const float4 *>(S.rec[w][j]);
-        const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3], r4 = rp[4], r5 = rp[5], r6 = rp[6];
-        const float wx = fmaf(fmaf(ax, r0.x, bx), r0.x, cx_), wy = fmaf(fmaf(ay, r0.y, by), r0.y, cy_),
-                    wz = fmaf(fmaf(az, r0.z, bz), r0.z, cz_);
-        const float W = wx * wy * wz;
-        acc[0] = fmaf(W, r0.w, acc[0]);
-        // A = r1.xyz ; B row d = (r1.w r2.x r2.y), (r2.z r2.w r3.x), (r3.y r3.z r3.w)
-        acc[1] = fmaf(W, fmaf(r2.y, fz, fmaf(r2.x, fy, fmaf(r1.w, fx, r1.x))), acc[1]);
-        acc[2] = fmaf(W, fmaf(r3.x, fz, fmaf(r2.w, fy, fmaf(r2.z, fx, r1.y))), acc[2]);
-        acc[3] = fmaf(W, fmaf(r3.w, fz, fmaf(r3.z, fy, fmaf(r3.y, fx, r1.z))), acc[3]);
-        // a = r4.xyz ; K row d = (r4.w r5.x r5.y), (r5.z r5.w r6.x), (r6.y r6.z r6.w)
-        acc[4] = fmaf(W, fmaf(r5.y, fz, fmaf(r5.x, fy, fmaf(r4.w, fx, r4.x))), acc[4]);
-        acc[5] = fmaf(W, fmaf(r6.x, fz, fmaf(r5.w, fy, fmaf(r5.z, fx, r4.y))), acc[5]);
-        acc[6] = fmaf(W, fmaf(r6.w, fz, fmaf(r6.z, fy, fmaf(r6.y, fx, r4.z))), acc[6]);
       }
-      __syncwarp();
     }
-    if (cur >= 0 && lane_on) {
-      float *dstc = colw + cur * 9 + node_lane;
+    for (int r = w; r < 20; r += P2G_NW) {  // ring columns: rare, shared-memory float atomics into the ring arena
+      const int c6 = c_ring_c6[r];
+      if (S.gstart[c6 * 6 + 6] <= cb || S.gstart[c6 * 6] >= ce || S.gstart[c6 * 6 + 6] == S.gstart[c6 * 6]) continue;
+      const int axn = c6 / 6 + ox, ayn = c6 % 6 + oy;  // (x+1) + ox
+#pragma unroll 1
+      for (int zc = 0; zc < 6; ++zc) {
+        const int lo = max(S.gstart[c6 * 6 + zc], cb), hi = min(S.gstart[c6 * 6 + zc + 1], ce);
+        if (lo >= hi) continue;
+        float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        sweep_cell(rec, lo, hi, L, acc);
+        if (lane_on) {
+          const int azn = zc + oz;
+          float *dstn = S.ring + (((axn >> 2) << 2) | ((ayn >> 2) << 1) | (azn >> 2)) * 448 + (((axn & 3) << 4) | ((ayn & 3) << 2) | (azn & 3));
 #pragma unroll
-      for (int ch = 0; ch < 7; ++ch) dstc[ch * 72] += acc[ch];
+          for (int ch = 0; ch < 7; ++ch) atomicAdd(dstn + ch * 64, acc[ch]);
+        }
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
-  // ---- (c) merge column arenas -> eight [7][64] tiles in shared memory ----------------------------------
-  float *out = &S.rec[0][0][0];
+  // ---- (c) merge column arenas + ring arena -> eight [7][64] tiles in shared memory -----------------------
+  float *out = &S.rec[0][0];
   {
     const int axn = tid >> 6, ayn = (tid >> 3) & 7, azn = tid & 7;  // arena node
-    float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int blk = ((axn >> 2) << 2) | ((ayn >> 2) << 1) | (azn >> 2);
+    const int cell = ((axn & 3) << 4) | ((ayn & 3) << 2) | (azn & 3);
+    float v[7];
+#pragma unroll
+    for (int ch = 0; ch < 7; ++ch) v[ch] = S.ring[blk * 448 + ch * 64 + cell];
 #pragma unroll
     for (int oxm = 0; oxm < 3; ++oxm) {
       const int x = axn - 1 - oxm;
@@ -225,8 +268,6 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
         for (int ch = 0; ch < 7; ++ch) v[ch] += c[ch * 72];
       }
     }
-    const int blk = ((axn >> 2) << 2) | ((ayn >> 2) << 1) | (azn >> 2);
-    const int cell = ((axn & 3) << 4) | ((ayn & 3) << 2) | (azn & 3);
 #pragma unroll
     for (int ch = 0; ch < 7; ++ch) out[blk * 448 + ch * 64 + cell] = v[ch];
   }
@@ -244,20 +285,16 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
 
-  // ---- (d) strays: per-particle scatter with REDs ------------------------------------------------------------
-  {
-    const int s0 = S.gstart[GRP_STRAY], ns = S.nstray;
-    for (int t = tid; t < ns; t += P2G_NT) {
-      const int i = S.order[s0 + t];
-      const size_t s = pslot((size_t)p0 + i);
-      float pos[3], vel[3], C[9], F[9];
-      const float mass = pars[s + ZPC_PB_M * TS];
+  // ---- (d) far strays (moved more than one cell since the re-bin): per-particle scatter with REDs --------------
+  for (int t = n_fast + tid; t < np; t += P2G_NT) {
+    const size_t s = pslot((size_t)p0 + S.order[t]);
+    float pos[3], vel[3], C[9], F[9];
+    const float mass = pars[s + ZPC_PB_M * TS];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
+    for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
 #pragma unroll
-      for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
-      zpcp::p2g_scatter_particle(pos, vel, mass, C, F, tb, tiles, 7, dx, dt, volume, mu, lam);
-    }
+    for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
+    zpcp::p2g_scatter_particle(pos, vel, mass, C, F, tb, tiles, 7, dx, dt, volume, mu, lam);
   }
   if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
 }
