@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default=os.environ.get("ZPC_BENCH_CONFIG", "C3"))
     ap.add_argument("--rebin-every", type=int, default=8)
+    ap.add_argument("--partition", default="with_rebin", choices=["with_rebin", "every_step"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -176,7 +177,8 @@ def main():
     if world == 1:
         from zpc_b200.solver import MpmSolver
         P = synth.elastic_cube(s, G)
-        sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="binned", rebin_every=args.rebin_every)
+        sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="binned", rebin_every=args.rebin_every,
+                        partition=args.partition)
         n_local = sol.n
     else:
         from zpc_b200.dist_solver import DistMpmSolver
@@ -233,7 +235,7 @@ def main():
                 algorithmic_bytes_per_launch=BYTES_PER_PARTICLE[dom] * n_local)
     fused_gbps = 257.5 * n_local / (fused_ms * 1e-3) / 1e9 if fused_ms else None
     fused = dict(ms=fused_ms, bytes_per_particle=257.5, achieved=fused_gbps, frac=(fused_gbps / hbm_peak) if fused_gbps else None,
-                 kernels=kern, partition_ms=per_step.get("partition"), rebin_ms_each=(stage.get("rebin", 0.0) / n_rebins) if n_rebins else None,
+                 kernels=kern, partition_ms=per_step.get("partition"), halo_ms=per_step.get("halo"), rebin_ms_each=(stage.get("rebin", 0.0) / n_rebins) if n_rebins else None,
                  rebins_in_timed_region=n_rebins)
 
     # ---- e2e: host buffers in, host buffers out, through the reference-facing call (N = 1) -----------------------
@@ -274,6 +276,8 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=workload, layout="block-binned AoSoA TileVector<f32,32>, re-bin every %d substeps" % args.rebin_every,
+                                partition=("hash-grid partition rebuilt every substep (EnlargeSparsity{0,2})" if (args.partition == "every_step" and world == 1)
+                                           else "hash-grid partition rebuilt with each re-bin, one extra ring (EnlargeSparsity{-1,3})"),
                                 active_blocks=nblocks, l2="inputs (%.1f GB particle state) exceed the 126 MB L2; no explicit flush" % (n_local * 100 / 1e9),
                                 parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, NCCL halo exchange of shared grid blocks" % world),
                     substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,

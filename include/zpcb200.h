@@ -127,15 +127,18 @@ typedef struct zpc_fixed_corotated {
 /* ------------------------------------------------------------------------------------------ */
 /* MPM path                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
-/* partition_for_particles / CleanSparsity + ComputeSparsity + EnlargeSparsity{0,2}
- * (simulation/sparsity/SparsityOp.hpp:41-112, SparsityCompute.tpp:6-24).  x = port over vec3
+/* partition_for_particles / CleanSparsity + ComputeSparsity + EnlargeSparsity{lo,hi}
+ * (simulation/sparsity/SparsityOp.hpp:41-112, SparsityCompute.tpp:6-24); the reference's substep uses
+ * enlarge {0,2} (every block the 3^3 stencil can touch).  {-1,3} adds one more ring so that the partition stays
+ * sufficient while particles drift by up to a block between re-binnings.  x = port over vec3
  * positions (AoS: {X,0,0,0,3}; AoSoA bin channel: {base+ZPC_PB_X*32, 0, 5, 31, 25}).  Writes keys /
  * indices / status / activeKeys / *cnt so that the unmodified HashTableView::query (:447-456)
  * resolves every active block.  Block numbering is DETERMINISTIC here: index = rank of the block key
  * in lexicographic (x,y,z) order (the reference's is insertion-order and racy).
  * *overflow (device int, may be NULL) is set to 1 if the table is too small. */
 int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx,
-                            zpc_hashtable_view table, int *overflow, zpc_stream_t stream);
+                            zpc_hashtable_view table, int enlarge_lo, int enlarge_hi, int *overflow,
+                            zpc_stream_t stream);
 
 /* CleanGridBlocks (simulation/grid/GridOp.hpp:54-69) over blocks [0, *cnt). */
 int zpcb200_clean_grid(zpc_grids_view grids, const int *cnt, zpc_stream_t stream);

@@ -1,0 +1,65 @@
+"""torchrun --nproc-per-node N tests/dist_check.py : N-GPU sharded substeps against the single-GPU solver on
+the same cloud (rank 0 holds both).  Exit code 0 = parity within the multi-step tolerance."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests.parity import check_particles  # noqa: E402
+from zpc_b200 import synth  # noqa: E402
+from zpc_b200.dist_solver import DistMpmSolver  # noqa: E402
+from zpc_b200.solver import MpmSolver  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    s, G, steps = 24, 64, 6
+    kw = dict(jitter_F=0.03, jitter_C=0.3)
+    P = synth.elastic_cube_slab(s, G, rank, world)   # jitter needs the global stream: apply it from the full cloud below
+    full = synth.elastic_cube(s, G, **kw)
+    full["v"] *= 6.0                                  # particles cross cells, blocks and the slab cut
+    n0 = full["m"].shape[0]
+    full["m"] = (full["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)   # identity tag
+    c0, c1 = synth.slab_cell_range(s, rank, world)
+    P = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
+    sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, rebin_every=3)
+    for _ in range(steps):
+        sol.substep()
+    torch.cuda.synchronize()
+    mine = sol.local.particles_host()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    mx = float(sol.local.max_vel_sqr.item())
+    ok = True
+    if rank == 0:
+        got = {k: np.concatenate([g[k] for g in gathered]) for k in ("x", "v", "m", "C", "F")}
+        one = MpmSolver(full, full["dx"], full["volume"], synth.DT * 10, synth.GRAVITY, mode=1, layout="binned", rebin_every=3,
+                        partition="with_rebin")
+        for _ in range(steps):
+            one.substep()
+        want = one.particles_host()
+
+        def canon(Q):
+            o = np.argsort(Q["m"], kind="stable")
+            return {k: Q[k][o] for k in "xvCF"}
+        try:
+            check_particles(canon(got), canon(want), full["dx"], "%d-GPU vs 1-GPU (%d substeps)" % (world, steps), rtol=5e-5)
+            assert abs(mx - float(one.max_vel_sqr.item())) <= 1e-4 * mx
+            print("dist_check ok: world %d, shared blocks on rank 0: %d" % (world, sol.halo.shared_blocks()))
+        except AssertionError as e:
+            print("dist_check FAILED:", e)
+            ok = False
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

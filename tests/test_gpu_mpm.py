@@ -280,3 +280,15 @@ def test_full_size_properties_c2():
     v = bins.attr("v")
     assert float((v - torch.tensor([0.0, -1.0, 0.0], device="cuda")).abs().max()) < 1e-4
     assert float(bins.attr("C").abs().max()) < 1e-1 / dx * 1e-3      # affine part of a uniform field vanishes
+
+
+def test_multi_gpu_substeps_match_single_gpu():
+    """2 ranks over NCCL (needs >= 2 GPUs; the 1-GPU driver tier skips it — run with gpurun --gpus 2)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tests", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -328,9 +328,10 @@ def _two_phase(fn, args_before, args_after, stream, device="cuda"):
 
 
 # ---- functors as free functions (policy = stream holder; all calls asynchronous) -------------------
-def partition_for_particles(x_port, n, dx, table, stream=None):
-    """SparsityCompute.tpp:6-24 / SparsityOp.hpp:41-112."""
+def partition_for_particles(x_port, n, dx, table, stream=None, enlarge=(0, 2)):
+    """SparsityCompute.tpp:6-24 / SparsityOp.hpp:41-112 (CleanSparsity, ComputeSparsity, EnlargeSparsity{lo,hi})."""
     _two_phase(lib().zpcb200_partition_build, (x_port, C.c_size_t(n), C.c_float(dx), table.view(),
+                                               C.c_int(enlarge[0]), C.c_int(enlarge[1]),
                                                C.c_void_p(table.overflow.data_ptr())), (), stream)
 
 

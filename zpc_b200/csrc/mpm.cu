@@ -86,16 +86,20 @@ __global__ void part_mark_kernel(PortAcc<const float> x, size_t n, float dxinv, 
       set_insert(code, set, set_mask, list, list_cap, list_cnt, overflow);
   }
 }
-// EnlargeSparsity{lo = 0, hi = 2}: every block present after the particle pass adds its 2x2x2 upper neighbours
+// EnlargeSparsity{lo, hi} (SparsityOp.hpp:88-112): every block present after the particle pass adds its
+// neighbours at offsets [lo, hi)^3; the reference's substep uses {0, 2}
 __global__ void part_enlarge_kernel(unsigned *set, unsigned set_mask, unsigned *list, int list_cap,
-                                    const int *cnt_before, int *list_cnt, int *overflow) {
+                                    const int *cnt_before, int *list_cnt, int lo, int hi, int *overflow) {
   const int n0 = min(*cnt_before, list_cap);
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n0 * 7; t += gridDim.x * blockDim.x) {
-    const int i = t / 7, o = t % 7 + 1;
+  const int w = hi - lo, w3 = w * w * w;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)n0 * w3; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / w3), o = (int)(t % w3);
+    const int ox = lo + o / (w * w), oy = lo + (o / w) % w, oz = lo + o % w;
+    if ((ox | oy | oz) == 0) continue;
     int bx, by, bz;
     code_unpack(list[i], bx, by, bz);
     unsigned code;
-    if (code_pack(bx + (o >> 2), by + ((o >> 1) & 1), bz + (o & 1), code))
+    if (code_pack(bx + ox, by + oy, bz + oz, code))
       set_insert(code, set, set_mask, list, list_cap, list_cnt, overflow);
     else if (overflow) *overflow = 1;
   }
@@ -245,8 +249,8 @@ __global__ void halo_kernel(float *tiles, int nch_grid, const int *ids, int n, i
 extern "C" {
 
 int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, zpc_hashtable_view tb,
-                            int *overflow, zpc_stream_t stream) {
-  if (!temp_bytes || tb.tableSize <= 0) return ZPCB200_E_BADARG;
+                            int enlarge_lo, int enlarge_hi, int *overflow, zpc_stream_t stream) {
+  if (!temp_bytes || tb.tableSize <= 0 || enlarge_hi < enlarge_lo || enlarge_hi - enlarge_lo > 8) return ZPCB200_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   // scratch set: power of two >= tableSize/2 ; list capacity = tableSize/8 block codes
   size_t set_n = 1;
@@ -278,8 +282,11 @@ int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n
   }
   part_snapshot_kernel<<<1, 1, 0, s>>>(counters, counters + 1);
   ZPC_CHECK_LAUNCH();
-  part_enlarge_kernel<<<G, 256, 0, s>>>(set, (unsigned)(set_n - 1), list, list_cap, counters + 1, counters, overflow);
-  ZPC_CHECK_LAUNCH();
+  if (enlarge_hi - enlarge_lo > 0) {
+    part_enlarge_kernel<<<G, 256, 0, s>>>(set, (unsigned)(set_n - 1), list, list_cap, counters + 1, counters, enlarge_lo,
+                                           enlarge_hi, overflow);
+    ZPC_CHECK_LAUNCH();
+  }
   zpc_port pl = {list, 0, 0, 0, 1}, ps = {sorted, 0, 0, 0, 1};
   size_t sb = sort_bytes;
   rc = zpcb200_radix_sort_u32(t + off_sort, &sb, pl, ps, (size_t)list_cap, 0, 30, stream);

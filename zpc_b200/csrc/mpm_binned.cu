@@ -32,6 +32,11 @@ namespace {
 constexpr int TS = 32;                  // particle tile length
 constexpr int NCH = ZPC_PB_NCH;         // 25 channels
 constexpr int BIN_MAX = ZPCB200_BIN_MAX;
+// 1: sort each cell group by slot so that per-CTA sums are bit-reproducible run to run (costs a serial phase);
+// 0: summation order inside a cell follows the shared-memory atomics (the reference's CUDA path is itself unordered).
+#ifndef ZPC_P2G_DETERMINISTIC
+#define ZPC_P2G_DETERMINISTIC 0
+#endif
 constexpr int P2G_NT = 512, P2G_NW = P2G_NT / 32;
 constexpr int CHUNK = P2G_NT;           // particles staged per pass (one record per thread)
 constexpr int NCOL6 = 36;               // (x,y) columns of home cells in [-1,4]^2: 16 nominal + 20 ring
@@ -138,6 +143,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   __syncthreads();
   for (int i = tid; i < np; i += P2G_NT) S.order[atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
   __syncthreads();
+#if ZPC_P2G_DETERMINISTIC
   if (tid < NGRP) {  // make the order inside each group deterministic (ascending slot); groups are ~8 long
     const int lo = S.gstart[tid], hi = S.gstart[tid + 1];
     if (hi - lo <= 96)
@@ -149,6 +155,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
       }
   }
   __syncthreads();
+#endif
 
   // ---- (b) per chunk: records (one thread per particle), then column sweeps (lanes = stencil offsets) ------
   const int n_fast = S.gstart[GRP_FAR];

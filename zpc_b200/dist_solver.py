@@ -1,0 +1,141 @@
+"""Multi-GPU substep: one process per GPU, particles sharded by spatial slab, one grid-block halo exchange per
+substep over NCCL (the reference has no counterpart — Specification.md lists it as future work).
+
+Each rank runs the single-GPU solver on its own particles.  A grid block that more than one rank's particles touch
+("shared") holds only PARTIAL sums after the local P2G, so after P2G every pair of ranks exchanges the 7 channels of
+the blocks they share and adds what it receives; every rank then runs the grid update redundantly on its (now
+complete) copies — one message per neighbour per substep instead of two — and G2P stays local.  The CFL scalar
+max|v|^2 is an all_reduce(max).  Ownership of particles never changes, so a particle that wanders into another
+rank's slab is still correct (its blocks simply become shared); migrating it for load balance is future work.
+
+The exchange topology (which blocks are shared with which rank) is rebuilt only when the partition is, i.e.
+with the re-bin every `rebin_every` substeps (partition="with_rebin").
+"""
+import torch
+import torch.distributed as dist
+
+from . import api
+from .solver import MpmSolver
+
+_BIAS = 1 << 20
+
+
+def pack_keys(keys):
+    """int32 [n,3] block keys -> int64 codes whose order is the lexicographic (x,y,z) order"""
+    k = keys.to(torch.int64) + _BIAS
+    return (k[:, 0] << 42) | (k[:, 1] << 21) | k[:, 2]
+
+
+class HaloExchange:
+    """Host-side plumbing of the one-ring grid-block exchange.  `pack(ids, buf)` / `unpack_add(ids, buf)` move
+    the tiles listed in ids between the grid and a contiguous buffer; the CUDA versions call the C ABI
+    (zpcb200_halo_pack / zpcb200_halo_unpack_add)."""
+
+    def __init__(self, group=None, nch=7, device="cuda", pack=None, unpack_add=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.nch = nch
+        self.device = device
+        self._pack = pack
+        self._unpack_add = unpack_add
+        self.peers = []       # [(rank, ids int32 tensor, send buf, recv buf)]
+
+    def build(self, active_keys):
+        """active_keys: int32 [nb,3] of this rank (rows in ascending key order).  Collective."""
+        mine = pack_keys(active_keys)
+        cnt = torch.tensor([mine.numel()], dtype=torch.int64, device=mine.device)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(cnts, cnt, group=self.group)
+        mx = int(max(int(c.item()) for c in cnts))
+        pad = torch.full((max(mx, 1),), -1, dtype=torch.int64, device=mine.device)
+        pad[: mine.numel()] = mine
+        allk = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(allk, pad, group=self.group)
+        self.peers = []
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            theirs = allk[q][: int(cnts[q].item())]
+            ids = torch.nonzero(torch.isin(mine, theirs)).flatten().to(torch.int32)   # ascending key order on both sides
+            if ids.numel():
+                n = ids.numel()
+                self.peers.append((q, ids.contiguous(),
+                                   torch.empty(n, self.nch, 64, dtype=torch.float32, device=mine.device),
+                                   torch.empty(n, self.nch, 64, dtype=torch.float32, device=mine.device)))
+        return self.peers
+
+    def shared_blocks(self):
+        return sum(p[1].numel() for p in self.peers)
+
+    def exchange_add(self, grids):
+        """after the local P2G: send my partial sums of every shared block, add what the peers send"""
+        if not self.peers:
+            return
+        ops = []
+        for q, ids, sbuf, rbuf in self.peers:
+            self._pack(grids, ids, sbuf)
+            ops.append(dist.P2POp(dist.isend, sbuf, q, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, rbuf, q, group=self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for q, ids, sbuf, rbuf in self.peers:      # ascending rank order: the same summation order every step
+            self._unpack_add(grids, ids, rbuf)
+
+
+def _cuda_pack(grids, ids, buf):
+    import ctypes as C
+    api._check(api.lib().zpcb200_halo_pack(grids.view(), C.c_void_p(ids.data_ptr()), C.c_int(ids.numel()), C.c_int(0),
+                                           C.c_int(grids.nch), C.c_void_p(buf.data_ptr()), api._stream_ptr()), "halo_pack")
+
+
+def _cuda_unpack_add(grids, ids, buf):
+    import ctypes as C
+    api._check(api.lib().zpcb200_halo_unpack_add(grids.view(), C.c_void_p(ids.data_ptr()), C.c_int(ids.numel()), C.c_int(0),
+                                                 C.c_int(grids.nch), C.c_void_p(buf.data_ptr()), api._stream_ptr()),
+               "halo_unpack_add")
+
+
+class DistMpmSolver:
+    def __init__(self, P_local, dx, volume, dt, gravity=-9.8, mode=1, rebin_every=8, group=None, device="cuda", **kw):
+        self.local = MpmSolver(P_local, dx, volume, dt, gravity, mode, layout="binned", rebin_every=rebin_every,
+                               device=device, partition="with_rebin", **kw)
+        self.n = self.local.n
+        self.table = self.local.table
+        self.halo = HaloExchange(group, 7, device, _cuda_pack, _cuda_unpack_add)
+        self.group = group
+        self._rebuild_topology()
+
+    @property
+    def stage_events(self):
+        return self.local.stage_events
+
+    @stage_events.setter
+    def stage_events(self, v):
+        self.local.stage_events = v
+
+    def stage_times_ms(self):
+        return self.local.stage_times_ms()
+
+    def _rebuild_topology(self):
+        nb = self.local.table.size()
+        self.halo.build(self.local.table.active_keys[:nb])
+
+    def substep(self):
+        L = self.local
+        if L.prepare():
+            self._rebuild_topology()
+        L._mark("begin")
+        api.clean_grid_blocks(L.grids, L.table)
+        L._mark("clean")
+        api.p2g_transfer(L.bins, L.table, L.grids, L.dt, L.model)
+        L._mark("p2g")
+        self.halo.exchange_add(L.grids)
+        L._mark("halo")
+        L.max_vel_sqr.zero_()
+        api.compute_grid_block_velocity(L.grids, L.table, L.dt, L.extf, L.mode, L.max_vel_sqr)
+        dist.all_reduce(L.max_vel_sqr, op=dist.ReduceOp.MAX, group=self.group)
+        L._mark("grid_update")
+        api.g2p_transfer(L.bins, L.table, L.grids, L.dt)
+        L._mark("g2p")
+        L.step_no += 1

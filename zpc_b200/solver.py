@@ -4,6 +4,11 @@
 
 `layout="aos"` keeps the reference's Particles layout and order (drop-in path); `layout="binned"` keeps
 particles in block-binned AoSoA TileVectors and re-bins every `rebin_every` substeps.
+
+`partition="every_step"` rebuilds the hash-grid partition each substep exactly like the reference's composed step
+(EnlargeSparsity{0,2}).  `partition="with_rebin"` (binned layout only) rebuilds it only together with the re-bin,
+enlarged by one more ring (EnlargeSparsity{-1,3}): a particle that has drifted by less than a block since then
+still finds every block of its stencil, the extra blocks stay empty (mass 0) and results are unchanged.
 """
 import torch
 
@@ -16,7 +21,11 @@ def default_expected_blocks(n):
 
 class MpmSolver:
     def __init__(self, P, dx, volume, dt, gravity=-9.8, mode=1, layout="binned", expected_blocks=None,
-                 rebin_every=8, E=5.0e4, nu=0.4, device="cuda", shuffle_free=True):
+                 rebin_every=8, E=5.0e4, nu=0.4, device="cuda", shuffle_free=True, partition="every_step"):
+        if partition not in ("every_step", "with_rebin") or (partition == "with_rebin" and layout != "binned"):
+            raise ValueError(partition)
+        self.partition_mode = partition
+        self.enlarge = (0, 2) if partition == "every_step" else (-1, 3)
         self.device = device
         self.dx, self.dt, self.mode = float(dx), float(dt), int(mode)
         self.extf = (0.0, float(gravity), 0.0)
@@ -36,7 +45,7 @@ class MpmSolver:
             self.bins = api.ParticleBins(self.n, self.block_cap, device)
             self.bins_alt = api.ParticleBins(self.n, self.block_cap, device)
             self.order = torch.empty(self.n, dtype=torch.int32, device=device)
-            api.partition_for_particles(api.vec3_port(self.aos.x), self.n, self.dx, self.table)
+            api.partition_for_particles(api.vec3_port(self.aos.x), self.n, self.dx, self.table, enlarge=self.enlarge)
             api.bin_particles(self.aos, self.table, self.dx, self.bins, self.order)
             self.aos = None if shuffle_free else self.aos
         elif layout != "aos":
@@ -69,7 +78,7 @@ class MpmSolver:
 
     def partition(self, stream=None):
         self._mark("begin")
-        api.partition_for_particles(self._x_port(), self.n, self.dx, self.table, stream)
+        api.partition_for_particles(self._x_port(), self.n, self.dx, self.table, stream, enlarge=self.enlarge)
         self._mark("partition")
 
     def transfer(self, stream=None):
@@ -92,11 +101,21 @@ class MpmSolver:
         self.bins, self.bins_alt = self.bins_alt, self.bins
         self._mark("rebin")
 
-    def substep(self, stream=None):
-        if self.layout == "binned" and self.step_no > 0 and self.rebin_every > 0 and self.step_no % self.rebin_every == 0:
+    def rebin_due(self):
+        return self.layout == "binned" and self.step_no > 0 and self.rebin_every > 0 and self.step_no % self.rebin_every == 0
+
+    def prepare(self, stream=None):
+        """partition (+ re-bin when due) for the coming substep; returns True when the partition was rebuilt"""
+        if self.rebin_due():
             self.rebin(stream)  # leaves a partition built from the current positions
-        else:
+            return True
+        if self.partition_mode == "every_step":
             self.partition(stream)
+            return True
+        return False
+
+    def substep(self, stream=None):
+        self.prepare(stream)
         self.transfer(stream)
         self.step_no += 1
 

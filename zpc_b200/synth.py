@@ -26,18 +26,40 @@ def _mt19937_u24(n, seed):
     return (raw >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
 
 
-def elastic_cube(s, G, seed=7, shuffle_seed=None, jitter_F=0.0, jitter_C=0.0, origin_cells=7):
-    """Returns dict of AoS float32 arrays x[N,3] v[N,3] m[N] C[N,9] F[N,9] plus dx, volume."""
+def _mt19937_u24_slice(first, count, seed, chunk=1 << 24):
+    """elements [first, first+count) of the _mt19937_u24 stream without holding the whole stream"""
+    rs = np.random.RandomState(seed)
+    out = np.empty(count, np.float32)
+    pos, filled = 0, 0
+    end = first + count
+    while pos < end:
+        m = min(chunk, end - pos)
+        raw = rs.randint(0, 2 ** 32, size=m, dtype=np.uint64)
+        lo, hi = max(first, pos), min(end, pos + m)
+        if hi > lo:
+            seg = raw[lo - pos:hi - pos].astype(np.uint32)
+            out[filled:filled + (hi - lo)] = (seg >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+            filled += hi - lo
+        pos += m
+    return out
+
+
+def elastic_cube(s, G, seed=7, shuffle_seed=None, jitter_F=0.0, jitter_C=0.0, origin_cells=7, cell_range=None):
+    """Returns dict of AoS float32 arrays x[N,3] v[N,3] m[N] C[N,9] F[N,9] plus dx, volume.
+    cell_range=(c0,c1) keeps only the cells with global index (i*s*s + j*s + k) in [c0,c1): the same particles,
+    bit for bit, as that slice of the full cube (used to shard the cloud over ranks)."""
     dx = np.float32(1.0 / G)
-    n = 8 * s ** 3
-    cell = np.arange(s ** 3, dtype=np.int64)
+    c0, c1 = cell_range if cell_range is not None else (0, s ** 3)
+    ncell = c1 - c0
+    n = 8 * ncell
+    cell = np.arange(c0, c1, dtype=np.int64)
     ci = np.stack([cell // (s * s), (cell // s) % s, cell % s], axis=1)  # (i,j,k), k fastest
     sig = np.arange(8, dtype=np.int64)
     sbit = np.stack([(sig >> 2) & 1, (sig >> 1) & 1, sig & 1], axis=1)
-    u = _mt19937_u24(3 * n, seed).reshape(n, 3)
+    u = _mt19937_u24_slice(c0 * 24, 3 * n, seed).reshape(n, 3)
     base = (ci[:, None, :] + origin_cells).astype(np.float32)          # [cells,1,3]
     sub = sbit[None, :, :].astype(np.float32)                          # [1,8,3]
-    x = (base + (sub + u.reshape(s ** 3, 8, 3)) * np.float32(0.5)) * dx
+    x = (base + (sub + u.reshape(ncell, 8, 3)) * np.float32(0.5)) * dx
     x = np.ascontiguousarray(x.reshape(n, 3), np.float32)
     vol = np.float32(dx * dx * dx / np.float32(8.0))
     P = dict(
@@ -61,6 +83,16 @@ def elastic_cube(s, G, seed=7, shuffle_seed=None, jitter_F=0.0, jitter_C=0.0, or
     P["dx"] = float(dx)
     P["volume"] = float(vol)
     return P
+
+
+def slab_cell_range(s, rank, world):
+    """x-slab decomposition: rank r owns the cells with i in [r*s//world, (r+1)*s//world)"""
+    i0, i1 = rank * s // world, (rank + 1) * s // world
+    return i0 * s * s, i1 * s * s
+
+
+def elastic_cube_slab(s, G, rank, world, **kw):
+    return elastic_cube(s, G, cell_range=slab_cell_range(s, rank, world), **kw)
 
 
 def config(name, **kw):
