@@ -163,12 +163,21 @@ int zpcb200_g2p_apic(zpc_particles_view pars, zpc_hashtable_view table, zpc_grid
  * [binStart[b], binStart[b+1]) and has home block coordinates binKey[3b..3b+2].  A block with more
  * than ZPCB200_BIN_MAX particles is split into several bins. */
 #define ZPCB200_BIN_MAX 1024
+#define ZPCB200_CELL_GROUPS 217     /* 6x6 columns x 6 z-levels of home cells around a block + 1 far-stray group */
+#define ZPCB200_CELL_GROUPS_PAD 224 /* row stride of cellStart */
 typedef struct zpc_bins_view {
   zpc_tilevector_view pars; /* numChannels == ZPC_PB_NCH */
   int *binStart;            /* [binCapacity + 1] */
   int *binKey;              /* [binCapacity * 3] */
   int *numBins;             /* device scalar */
   int binCapacity;
+  /* Optional cell-order cache (all three NULL to disable).  The binned G2P knows every particle's NEW home cell,
+   * so it leaves, per bin, the particle slots grouped by (column, z) for the next binned P2G, which then skips its
+   * own in-kernel counting sort.  cellOrderValid is set (non-zero) by the binned G2P and cleared by
+   * bin_particles / rebin_particles; anything else that moves particles must clear it. */
+  unsigned short *cellOrder; /* [pars.size]: k-th particle of its bin in group order -> slot relative to binStart */
+  unsigned short *cellStart; /* [binCapacity * ZPCB200_CELL_GROUPS_PAD]: group offsets, entry 217 = bin count */
+  int *cellOrderValid;       /* device flag */
 } zpc_bins_view;
 
 /* Sort AoS particles into bins (radix_sort_pair on the block rank + gather into AoSoA).  Requires a

@@ -56,7 +56,8 @@ class zpc_fixed_corotated(C.Structure):
 
 class zpc_bins_view(C.Structure):
     _fields_ = [("pars", zpc_tilevector_view), ("binStart", C.c_void_p), ("binKey", C.c_void_p),
-                ("numBins", C.c_void_p), ("binCapacity", C.c_int)]
+                ("numBins", C.c_void_p), ("binCapacity", C.c_int), ("cellOrder", C.c_void_p),
+                ("cellStart", C.c_void_p), ("cellOrderValid", C.c_void_p)]
 
 
 _lib = None
@@ -283,17 +284,26 @@ class Particles:
 class ParticleBins:
     """Block-binned AoSoA particles (include/zpcb200.h: zpc_bins_view)."""
 
-    def __init__(self, n, bin_capacity, device="cuda"):
+    def __init__(self, n, bin_capacity, device="cuda", cell_order_cache=True):
         self.n = int(n)
         self.pars = TileVector(n, PB_NCH, 32, device)
         self.cap = int(bin_capacity)
         self.bin_start = torch.zeros(self.cap + 1, dtype=torch.int32, device=device)
         self.bin_key = torch.zeros(self.cap, 3, dtype=torch.int32, device=device)
         self.num_bins = torch.zeros(1, dtype=torch.int32, device=device)
+        self.cell_order = self.cell_start = self.cell_order_valid = None
+        if cell_order_cache:
+            self.cell_order = torch.zeros(max(self.n, 1), dtype=torch.int16, device=device)
+            self.cell_start = torch.zeros(self.cap * 224, dtype=torch.int16, device=device)
+            self.cell_order_valid = torch.zeros(1, dtype=torch.int32, device=device)
 
     def view(self):
+        co = self.cell_order
         return zpc_bins_view(self.pars.view(), self.bin_start.data_ptr(), self.bin_key.data_ptr(),
-                             self.num_bins.data_ptr(), self.cap)
+                             self.num_bins.data_ptr(), self.cap,
+                             co.data_ptr() if co is not None else None,
+                             self.cell_start.data_ptr() if co is not None else None,
+                             self.cell_order_valid.data_ptr() if co is not None else None)
 
     def attr(self, name):
         chn, w = {"m": (PB_M, 1), "x": (PB_X, 3), "v": (PB_V, 3), "C": (PB_C, 9), "F": (PB_F, 9)}[name]

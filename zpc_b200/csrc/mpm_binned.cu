@@ -90,8 +90,9 @@ __device__ __forceinline__ void sweep_cell(const float (*rec)[REC_F], int lo, in
 
 __global__ void __launch_bounds__(P2G_NT, 2)
 p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
-                  const int *__restrict__ numBins, zpc_hashtable_view tb, float *__restrict__ tiles, float dx, float dt,
-                  float volume, float mu, float lam) {
+                  const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
+                  const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
+                  float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GSmem &S = *reinterpret_cast<P2GSmem *>(smem_raw);
   const int bin = blockIdx.x;
@@ -111,7 +112,14 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   }
   __syncthreads();
 
-  // ---- (a) counting sort by (column, z) of the CURRENT home cell ----------------------------------------
+  // ---- (a) group the bin's particles by (column, z) of their CURRENT home cell ----------------------------
+  // either read the grouping the last binned G2P left behind, or counting-sort here
+  const bool pre = cellOrder != nullptr && *cellOrderValid != 0;
+  const unsigned short *gorder = pre ? cellOrder + p0 : S.order;
+  if (pre) {
+    if (tid <= NGRP) S.gstart[tid] = cellStart[(size_t)bin * ZPCB200_CELL_GROUPS_PAD + tid];
+    __syncthreads();
+  } else {
   for (int i = tid; i < np; i += P2G_NT) {
     const size_t s = pslot((size_t)p0 + i);
     // current base node (division form, as LocalArena does), minus one = home cell, relative to the bin's block origin
@@ -143,8 +151,9 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   __syncthreads();
   for (int i = tid; i < np; i += P2G_NT) S.order[atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
   __syncthreads();
+  }
 #if ZPC_P2G_DETERMINISTIC
-  if (tid < NGRP) {  // make the order inside each group deterministic (ascending slot); groups are ~8 long
+  if (!pre && tid < NGRP) {  // make the order inside each group deterministic (ascending slot); groups are ~8 long
     const int lo = S.gstart[tid], hi = S.gstart[tid + 1];
     if (hi - lo <= 96)
       for (int a = lo + 1; a < hi; ++a) {
@@ -176,7 +185,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     {  // records
       const int pos = cb + tid;
       if (pos < n_fast) {
-        const size_t s = pslot((size_t)p0 + S.order[pos]);
+        const size_t s = pslot((size_t)p0 + gorder[pos]);
         float F[9], K[9];
 #pragma unroll
         for (int d = 0; d < 9; ++d) F[d] = pars[s + (ZPC_PB_F + d) * TS];
@@ -294,7 +303,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 
   // ---- (d) far strays (moved more than one cell since the re-bin): per-particle scatter with REDs --------------
   for (int t = n_fast + tid; t < np; t += P2G_NT) {
-    const size_t s = pslot((size_t)p0 + S.order[t]);
+    const size_t s = pslot((size_t)p0 + gorder[t]);
     float pos[3], vel[3], C[9], F[9];
     const float mass = pars[s + ZPC_PB_M * TS];
 #pragma unroll
@@ -312,19 +321,22 @@ struct G2PSmem {
   float v[8][3][64];  // 6144 B: channels 1..3 of the eight arena tiles
   unsigned long long bar;
   int tile_id[8];
+  int cnt[NGRP + 3];               // cell-order cache for the next P2G
+  unsigned char grp_of[BIN_MAX];
 };
 
 __global__ void __launch_bounds__(G2P_NT)
 g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
-                  const int *__restrict__ numBins, zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx,
-                  float dt) {
+                  const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder, unsigned short *__restrict__ cellStart,
+                  zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx, float dt) {
   __shared__ __align__(128) G2PSmem S;
   const int bin = blockIdx.x;
   if (bin >= *numBins) return;
   const int tid = threadIdx.x;
-  const int p0 = binStart[bin], np = binStart[bin + 1] - p0;
+  const int p0 = binStart[bin], np = min(binStart[bin + 1] - p0, BIN_MAX);
   const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
   if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
+  if (tid < NGRP + 3) S.cnt[tid] = 0;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(&S.bar)), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -421,6 +433,15 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
       for (int r = 0; r < 3; ++r) C[r + 3 * e] = (dx * G[r + 3 * e] - ar.local[e] * vel[r]) * D_inv;
 #pragma unroll
     for (int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
+    if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
+      const int cx = (int)floorf(pos[0] / dx - 0.5f) - 1 - 4 * kx, cy = (int)floorf(pos[1] / dx - 0.5f) - 1 - 4 * ky,
+                cz = (int)floorf(pos[2] / dx - 0.5f) - 1 - 4 * kz;
+      const int g = ((unsigned)(cx + 1) < 6u && (unsigned)(cy + 1) < 6u && (unsigned)(cz + 1) < 6u)
+                        ? ((cx + 1) * 6 + (cy + 1)) * 6 + (cz + 1)
+                        : GRP_FAR;
+      S.grp_of[i] = (unsigned char)g;
+      atomicAdd(&S.cnt[g], 1);
+    }
 #pragma unroll
     for (int d = 0; d < 9; ++d) { Fo[d] = pars[s + (ZPC_PB_F + d) * TS]; tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f); }
 #pragma unroll
@@ -432,6 +453,30 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
     for (int d = 0; d < 3; ++d) { pars[s + (ZPC_PB_X + d) * TS] = pos[d]; pars[s + (ZPC_PB_V + d) * TS] = vel[d]; }
 #pragma unroll
     for (int d = 0; d < 9; ++d) pars[s + (ZPC_PB_C + d) * TS] = C[d];
+  }
+  if (cellOrder) {  // counting sort of the bin by new cell group -> global cache for the next P2G
+    __syncthreads();
+    const int w = tid >> 5, l = tid & 31;
+    if (w == 0) {
+      int c[7], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { const int g = l * 7 + k; c[k] = g < NGRP ? S.cnt[g] : 0; sum += c[k]; }
+      int inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (l >= d) inc += t; }
+      int run = inc - sum;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int g = l * 7 + k;
+        if (g <= NGRP) {
+          S.cnt[g] = run;
+          cellStart[(size_t)bin * ZPCB200_CELL_GROUPS_PAD + g] = (unsigned short)run;
+        }
+        run += c[k];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < np; i += G2P_NT) cellOrder[p0 + atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
   }
 }
 
@@ -553,6 +598,7 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
   int *start = (int *)(t + o_start), *end = (int *)(t + o_end), *nbins = (int *)(t + o_nb), *binoff = (int *)(t + o_off);
   ZPC_CUDA(cudaMemsetAsync(t, 0, 256, s));
   ZPC_CUDA(cudaMemsetAsync(start, 0, o_off - o_start, s));
+  if (dst.cellOrderValid) ZPC_CUDA(cudaMemsetAsync(dst.cellOrderValid, 0, sizeof(int), s));  // new slots: cache is stale
   const unsigned gp = (unsigned)((n + 255) / 256), gb = (unsigned)((cap + 255) / 256);
   if (n) {
     bin_keys_kernel<SRC_AOSOA><<<gp, 256, 0, s>>>(SRC_AOSOA ? srcT : A.X, n, 1.0f / dx, tb, keys, vals, err);
@@ -617,8 +663,10 @@ int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_g
   }
   float mu, lam;
   zpcm::lame_host(model.E, model.nu, mu, lam);
+  const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
   p2g_binned_kernel<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
-      bins.pars.base, bins.binStart, bins.binKey, bins.numBins, tb, g.tiles, g.dx, dt, model.volume, mu, lam);
+      bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
+      bins.cellOrderValid, tb, g.tiles, g.dx, dt, model.volume, mu, lam);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }
@@ -626,9 +674,12 @@ int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_g
 int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
   if (g.numChannels < 4 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
     return ZPCB200_E_BADARG;
-  g2p_binned_kernel<<<bins.binCapacity, G2P_NT, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey,
-                                                                           bins.numBins, tb, g.tiles, g.numChannels, g.dx, dt);
+  const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
+  g2p_binned_kernel<<<bins.binCapacity, G2P_NT, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
+                                                                           cache ? bins.cellOrder : nullptr, bins.cellStart, tb,
+                                                                           g.tiles, g.numChannels, g.dx, dt);
   ZPC_CHECK_LAUNCH();
+  if (cache) ZPC_CUDA(cudaMemsetAsync(bins.cellOrderValid, 1, sizeof(int), (cudaStream_t)stream));  // non-zero = valid
   return ZPCB200_OK;
 }
 }
