@@ -36,6 +36,7 @@ template <typename T> struct PortAcc {
   __host__ __device__ bool contiguous() const { return bits == 0 && chns == 1; }
   __device__ __forceinline__ T &operator[](size_t k) const {
     size_t i = (size_t)idx + k;
+    if (chns == 1) return base[i];  // one channel: the tile formula is the identity (warp-uniform branch)
     return base[(((i >> bits) * chns) << bits) | (i & mask)];
   }
   // component d of a vector element (aosoa_iterator<T, N>: stride tileMask+1 between components)

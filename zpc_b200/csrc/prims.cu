@@ -417,7 +417,7 @@ __global__ void rs_scan_hist_kernel(unsigned *ghist) {
 }
 
 template <typename K, bool PAIRS, int ITEMS>
-__global__ void __launch_bounds__(RS_NT) rs_onesweep_kernel(PortAcc<K> kin, PortAcc<int> vin, PortAcc<K> kout,
+__global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? 3 : 2) rs_onesweep_kernel(PortAcc<K> kin, PortAcc<int> vin, PortAcc<K> kout,
                                                             PortAcc<int> vout, size_t n, int shift, unsigned mask,
                                                             const unsigned *gbase /*[256] exclusive*/,
                                                             unsigned *lookback /*[tiles][256]*/, unsigned *ticket) {
@@ -446,15 +446,23 @@ __global__ void __launch_bounds__(RS_NT) rs_onesweep_kernel(PortAcc<K> kin, Port
     size_t e = wbase + (size_t)i * 32 + l;
     key[i] = e < n ? kin[e] : (K)0;
   }
-  // warp-synchronous stable ranking
+  // warp-synchronous stable ranking.  MATCH.ANY has a long latency: issue all of them first (independent), then
+  // run the serial per-item counter updates on the masks.
+  unsigned peers_of[ITEMS];
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    size_t e = wbase + (size_t)i * 32 + l;
+    const size_t e = wbase + (size_t)i * 32 + l;
+    const unsigned d = e < n ? digit_of(key[i], shift, mask) : RS_BINS;  // invalid lanes match only each other
+    peers_of[i] = __match_any_sync(0xffffffffu, d);
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const size_t e = wbase + (size_t)i * 32 + l;
     const bool valid = e < n;
-    unsigned d = valid ? digit_of(key[i], shift, mask) : RS_BINS;  // invalid lanes match only each other
-    unsigned peers = __match_any_sync(0xffffffffu, d);
-    unsigned before = __popc(peers & lanemask_lt());
-    int leader = __ffs(peers) - 1;
+    const unsigned d = digit_of(key[i], shift, mask);
+    const unsigned peers = peers_of[i];
+    const unsigned before = __popc(peers & lanemask_lt());
+    const int leader = __ffs(peers) - 1;
     unsigned c = 0;
     if (valid && l == leader) {
       c = warp_hist[w][d];
@@ -483,16 +491,32 @@ __global__ void __launch_bounds__(RS_NT) rs_onesweep_kernel(PortAcc<K> kin, Port
       asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lb), "r"(RS_FLAG_INCL | tcount) : "memory");
     } else {
       asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lb), "r"(RS_FLAG_AGG | tcount) : "memory");
+      // walk back over the predecessors' descriptors, LB independent loads in flight per round (the walk is pure
+      // L2 latency: one load at a time would make every tile wait ~#tiles-in-flight round trips)
+      constexpr int LB = 8;
       long long pred = (long long)tile - 1;
-      while (true) {
-        unsigned v;
-        const unsigned *pp = lookback + (size_t)pred * RS_BINS + d;
-        do {
-          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pp) : "memory");
-        } while ((v >> 30) == 0);
-        excl += v & RS_VAL_MASK;
-        if ((v >> 30) == 2) break;
-        --pred;
+      bool done = false;
+      while (!done) {
+        unsigned v[LB];
+#pragma unroll
+        for (int k = 0; k < LB; ++k) {
+          const long long pk = pred - k;
+          v[k] = RS_FLAG_INCL;  // before tile 0: inclusive 0 terminates the walk
+          if (pk >= 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[k]) : "l"(lookback + (size_t)pk * RS_BINS + d) : "memory");
+        }
+#pragma unroll
+        for (int k = 0; k < LB; ++k) {
+          if (done) break;
+          if ((v[k] >> 30) == 0) {  // not published yet: spin on this one
+            const unsigned *pp = lookback + (size_t)(pred - k) * RS_BINS + d;
+            do {
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[k]) : "l"(pp) : "memory");
+            } while ((v[k] >> 30) == 0);
+          }
+          excl += v[k] & RS_VAL_MASK;
+          if ((v[k] >> 30) == 2) done = true;
+        }
+        pred -= LB;
       }
       asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lb), "r"(RS_FLAG_INCL | ((excl + tcount) & RS_VAL_MASK))
                    : "memory");
