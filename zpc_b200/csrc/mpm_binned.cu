@@ -32,36 +32,31 @@ namespace {
 constexpr int TS = 32;                  // particle tile length
 constexpr int NCH = ZPC_PB_NCH;         // 25 channels
 constexpr int BIN_MAX = ZPCB200_BIN_MAX;
-// 1: sort each cell group by slot so that per-CTA sums are bit-reproducible run to run (costs a serial phase);
-// 0: summation order inside a cell follows the shared-memory atomics (the reference's CUDA path is itself unordered).
-#ifndef ZPC_P2G_DETERMINISTIC
-#define ZPC_P2G_DETERMINISTIC 0
-#endif
-constexpr int P2G_NT = 512, P2G_NW = P2G_NT / 32;
+constexpr int P2G_NT = 256, P2G_NW = P2G_NT / 32;
 constexpr int CHUNK = P2G_NT;           // particles staged per pass (one record per thread)
 constexpr int NCOL6 = 36;               // (x,y) columns of home cells in [-1,4]^2: 16 nominal + 20 ring
 constexpr int NGRP = NCOL6 * 6 + 1;     // (column, z in [-1,4]) groups + far-stray group
 constexpr int GRP_FAR = NCOL6 * 6;
 constexpr int REC_F = 28;               // floats per particle record
-constexpr int COL_F = 7 * 72;           // column arena: 7 channels x (8 z x 3 x 3) nodes
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ size_t pslot(size_t i) { return ((i >> 5) * NCH) * TS + (i & 31); }  // channel 0 of particle i
 
 struct P2GSmem {
-  float rec[CHUNK][REC_F];          // 57344 B; reused as the 8 output tiles [8][7][64] (14336 B) at the end
-  float col[16][COL_F];             // 32256 B: private arenas of the 16 nominal columns
-  float ring[8 * 448];              // 14336 B: tile-layout arena for the (rare) ring-column particles
-  unsigned short order[BIN_MAX];
+  float rec[CHUNK][REC_F];          // 28672 B
+  float out[8 * 448];               // 14336 B: the arena as eight [7][64] grid tiles, accumulated with shared atomics
+  unsigned short order[BIN_MAX];    // fallback grouping only (no cell-order cache)
   unsigned char grp_of[BIN_MAX];
   int cnt[NGRP + 3];
   int gstart[NGRP + 3];
   int tile_id[8];
+  int next_unit;
 };
-static_assert(sizeof(P2GSmem) <= 113 * 1024, "two CTAs per SM");
+static_assert(sizeof(P2GSmem) <= 56 * 1024, "four CTAs per SM");
 
-// 6x6 column index of the 20 ring columns (x or y outside [0,3]); c6 = (x+1)*6 + (y+1)
-__constant__ unsigned char c_ring_c6[20] = {0, 1, 2, 3, 4, 5, 6, 11, 12, 17, 18, 23, 24, 29, 30, 31, 32, 33, 34, 35};
+// sweep units in scheduling order: the 16 nominal columns first, then the 20 ring columns; c6 = (x+1)*6 + (y+1)
+__constant__ unsigned char c_unit_c6[NCOL6] = {7,  8,  9,  10, 13, 14, 15, 16, 19, 20, 21, 22, 25, 26, 27, 28,
+                                              0,  1,  2,  3,  4,  5,  6,  11, 12, 17, 18, 23, 24, 29, 30, 31, 32, 33, 34, 35};
 
 // lanes = the 27 stencil offsets.  Sweeps the records of sorted positions [lo,hi) (all in one cell) and returns the
 // 7 channel sums of this lane's node.
@@ -88,7 +83,7 @@ __device__ __forceinline__ void sweep_cell(const float (*rec)[REC_F], int lo, in
   }
 }
 
-__global__ void __launch_bounds__(P2G_NT, 2)
+__global__ void __launch_bounds__(P2G_NT, 4)
 p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
                   const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
@@ -102,15 +97,14 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
   const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
 
-  // ---- (0) arena blocks, zero scratch ------------------------------------------------------------------
+  // ---- (0) arena blocks, zero the accumulation tiles ---------------------------------------------------
   if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
-  for (int i = tid; i < NGRP + 3; i += P2G_NT) S.cnt[i] = 0;
   {
-    float4 *z = reinterpret_cast<float4 *>(&S.col[0][0]);  // col and ring are contiguous
+    float4 *z = reinterpret_cast<float4 *>(S.out);
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < (16 * COL_F + 8 * 448) / 4; i += P2G_NT) z[i] = zero;
+    for (int i = tid; i < 8 * 448 / 4; i += P2G_NT) z[i] = zero;
   }
-  __syncthreads();
+  if (tid == 0) S.next_unit = 0;
 
   // ---- (a) group the bin's particles by (column, z) of their CURRENT home cell ----------------------------
   // either read the grouping the last binned G2P left behind, or counting-sort here
@@ -120,53 +114,42 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     if (tid <= NGRP) S.gstart[tid] = cellStart[(size_t)bin * ZPCB200_CELL_GROUPS_PAD + tid];
     __syncthreads();
   } else {
-  for (int i = tid; i < np; i += P2G_NT) {
-    const size_t s = pslot((size_t)p0 + i);
-    // current base node (division form, as LocalArena does), minus one = home cell, relative to the bin's block origin
-    const int cx = (int)floorf(pars[s + (ZPC_PB_X + 0) * TS] / dx - 0.5f) - 1 - 4 * kx;
-    const int cy = (int)floorf(pars[s + (ZPC_PB_X + 1) * TS] / dx - 0.5f) - 1 - 4 * ky;
-    const int cz = (int)floorf(pars[s + (ZPC_PB_X + 2) * TS] / dx - 0.5f) - 1 - 4 * kz;
-    const int g = ((unsigned)(cx + 1) < 6u && (unsigned)(cy + 1) < 6u && (unsigned)(cz + 1) < 6u)
-                      ? ((cx + 1) * 6 + (cy + 1)) * 6 + (cz + 1)
-                      : GRP_FAR;
-    S.grp_of[i] = (unsigned char)g;
-    atomicAdd(&S.cnt[g], 1);
-  }
-  __syncthreads();
-  if (w == 0) {  // exclusive scan of the 217 counters, 7 per lane
-    int c[7], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) { const int g = l * 7 + k; c[k] = g < NGRP ? S.cnt[g] : 0; sum += c[k]; }
-    int inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (l >= d) inc += t; }
-    int run = inc - sum;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int g = l * 7 + k;
-      if (g <= NGRP) { S.gstart[g] = run; S.cnt[g] = run; }
-      run += c[k];
+    for (int i = tid; i < NGRP + 3; i += P2G_NT) S.cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < np; i += P2G_NT) {
+      const size_t s = pslot((size_t)p0 + i);
+      // current base node (division form, as LocalArena does), minus one = home cell, relative to the bin's block origin
+      const int cx = (int)floorf(pars[s + (ZPC_PB_X + 0) * TS] / dx - 0.5f) - 1 - 4 * kx;
+      const int cy = (int)floorf(pars[s + (ZPC_PB_X + 1) * TS] / dx - 0.5f) - 1 - 4 * ky;
+      const int cz = (int)floorf(pars[s + (ZPC_PB_X + 2) * TS] / dx - 0.5f) - 1 - 4 * kz;
+      const int g = ((unsigned)(cx + 1) < 6u && (unsigned)(cy + 1) < 6u && (unsigned)(cz + 1) < 6u)
+                        ? ((cx + 1) * 6 + (cy + 1)) * 6 + (cz + 1)
+                        : GRP_FAR;
+      S.grp_of[i] = (unsigned char)g;
+      atomicAdd(&S.cnt[g], 1);
     }
-  }
-  __syncthreads();
-  for (int i = tid; i < np; i += P2G_NT) S.order[atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
-  __syncthreads();
-  }
-#if ZPC_P2G_DETERMINISTIC
-  if (!pre && tid < NGRP) {  // make the order inside each group deterministic (ascending slot); groups are ~8 long
-    const int lo = S.gstart[tid], hi = S.gstart[tid + 1];
-    if (hi - lo <= 96)
-      for (int a = lo + 1; a < hi; ++a) {
-        const unsigned short v = S.order[a];
-        int b = a - 1;
-        while (b >= lo && S.order[b] > v) { S.order[b + 1] = S.order[b]; --b; }
-        S.order[b + 1] = v;
+    __syncthreads();
+    if (w == 0) {  // exclusive scan of the 217 counters, 7 per lane
+      int c[7], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { const int g = l * 7 + k; c[k] = g < NGRP ? S.cnt[g] : 0; sum += c[k]; }
+      int inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (l >= d) inc += t; }
+      int run = inc - sum;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int g = l * 7 + k;
+        if (g <= NGRP) { S.gstart[g] = run; S.cnt[g] = run; }
+        run += c[k];
       }
+    }
+    __syncthreads();
+    for (int i = tid; i < np; i += P2G_NT) S.order[atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
+    __syncthreads();
   }
-  __syncthreads();
-#endif
 
-  // ---- (b) per chunk: records (one thread per particle), then column sweeps (lanes = stencil offsets) ------
+  // ---- (b) per chunk: records (one thread per particle), then cell sweeps (lanes = stencil offsets) --------
   const int n_fast = S.gstart[GRP_FAR];
   const bool lane_on = l < 27;
   const int lc = lane_on ? l : 0;  // lanes 27..31 shadow lane 0 and never write
@@ -175,10 +158,9 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   {
     // quadratic B-spline as a polynomial in d0 (InterpolationKernel.hpp:105-113):
     //   o=0: .5 d^2 - 1.5 d + 1.125 ; o=1: -d^2 + 2 d - .25 ; o=2: .5 d^2 - .5 d + .125
-    const float qa[3] = {0.5f, -1.0f, 0.5f}, qb[3] = {-1.5f, 2.0f, -0.5f}, qc[3] = {1.125f, -0.25f, 0.125f};
-    L.ax = qa[ox]; L.bx = qb[ox]; L.cx = qc[ox];
-    L.ay = qa[oy]; L.by = qb[oy]; L.cy = qc[oy];
-    L.az = qa[oz]; L.bz = qb[oz]; L.cz = qc[oz];
+    L.ax = ox == 1 ? -1.0f : 0.5f; L.bx = ox == 0 ? -1.5f : (ox == 1 ? 2.0f : -0.5f); L.cx = ox == 0 ? 1.125f : (ox == 1 ? -0.25f : 0.125f);
+    L.ay = oy == 1 ? -1.0f : 0.5f; L.by = oy == 0 ? -1.5f : (oy == 1 ? 2.0f : -0.5f); L.cy = oy == 0 ? 1.125f : (oy == 1 ? -0.25f : 0.125f);
+    L.az = oz == 1 ? -1.0f : 0.5f; L.bz = oz == 0 ? -1.5f : (oz == 1 ? 2.0f : -0.5f); L.cz = oz == 0 ? 1.125f : (oz == 1 ? -0.25f : 0.125f);
     L.fx = (float)ox; L.fy = (float)oy; L.fz = (float)oz;
   }
   for (int cb = 0; cb < n_fast; cb += CHUNK) {
@@ -226,76 +208,45 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     __syncthreads();
     const int ce = min(cb + CHUNK, n_fast);
     const float(*rec)[REC_F] = S.rec - cb;  // rec[pos] for pos in [cb, ce)
-    {  // nominal column (w>>2, w&3): private arena, plain read-modify-write
-      const int c6 = ((w >> 2) + 1) * 6 + (w & 3) + 1;
-      float *colw = S.col[w] + oz * 9 + ox * 3 + oy;
+    // columns are handed out dynamically (one shared counter): warps that finish early take the next column, the
+    // per-cell sums go straight into the arena tiles with shared-memory float atomics (no private arenas, no merge)
+    while (true) {
+      int u = 0;
+      if (l == 0) u = atomicAdd(&S.next_unit, 1);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= NCOL6) break;
+      const int c6 = c_unit_c6[u];
+      const int g0 = c6 * 6;
+      if (S.gstart[g0 + 6] <= cb || S.gstart[g0] >= ce) continue;  // nothing of this column in the chunk
+      const int axn = c6 / 6 + ox, ayn = c6 % 6 + oy;              // arena node (x+1+ox, y+1+oy, zc+oz)
+      const int xy_off = (((axn >> 2) << 2) | ((ayn >> 2) << 1)) * 448 + (((axn & 3) << 4) | ((ayn & 3) << 2));
 #pragma unroll 1
       for (int zc = 0; zc < 6; ++zc) {
-        const int lo = max(S.gstart[c6 * 6 + zc], cb), hi = min(S.gstart[c6 * 6 + zc + 1], ce);
-        if (lo >= hi) continue;
-        float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        sweep_cell(rec, lo, hi, L, acc);
-        if (lane_on) {
-#pragma unroll
-          for (int ch = 0; ch < 7; ++ch) colw[zc * 9 + ch * 72] += acc[ch];
-        }
-      }
-    }
-    for (int r = w; r < 20; r += P2G_NW) {  // ring columns: rare, shared-memory float atomics into the ring arena
-      const int c6 = c_ring_c6[r];
-      if (S.gstart[c6 * 6 + 6] <= cb || S.gstart[c6 * 6] >= ce || S.gstart[c6 * 6 + 6] == S.gstart[c6 * 6]) continue;
-      const int axn = c6 / 6 + ox, ayn = c6 % 6 + oy;  // (x+1) + ox
-#pragma unroll 1
-      for (int zc = 0; zc < 6; ++zc) {
-        const int lo = max(S.gstart[c6 * 6 + zc], cb), hi = min(S.gstart[c6 * 6 + zc + 1], ce);
+        const int lo = max(S.gstart[g0 + zc], cb), hi = min(S.gstart[g0 + zc + 1], ce);
         if (lo >= hi) continue;
         float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         sweep_cell(rec, lo, hi, L, acc);
         if (lane_on) {
           const int azn = zc + oz;
-          float *dstn = S.ring + (((axn >> 2) << 2) | ((ayn >> 2) << 1) | (azn >> 2)) * 448 + (((axn & 3) << 4) | ((ayn & 3) << 2) | (azn & 3));
+          float *dstn = S.out + xy_off + (azn >> 2) * 448 + (azn & 3);
 #pragma unroll
           for (int ch = 0; ch < 7; ++ch) atomicAdd(dstn + ch * 64, acc[ch]);
         }
       }
     }
     __syncthreads();
+    if (tid == 0) S.next_unit = 0;  // ordered before the next sweep by the barrier after the next records phase
   }
 
-  // ---- (c) merge column arenas + ring arena -> eight [7][64] tiles in shared memory -----------------------
-  float *out = &S.rec[0][0];
-  {
-    const int axn = tid >> 6, ayn = (tid >> 3) & 7, azn = tid & 7;  // arena node
-    const int blk = ((axn >> 2) << 2) | ((ayn >> 2) << 1) | (azn >> 2);
-    const int cell = ((axn & 3) << 4) | ((ayn & 3) << 2) | (azn & 3);
-    float v[7];
-#pragma unroll
-    for (int ch = 0; ch < 7; ++ch) v[ch] = S.ring[blk * 448 + ch * 64 + cell];
-#pragma unroll
-    for (int oxm = 0; oxm < 3; ++oxm) {
-      const int x = axn - 1 - oxm;
-      if ((unsigned)x >= 4u) continue;
-#pragma unroll
-      for (int oym = 0; oym < 3; ++oym) {
-        const int y = ayn - 1 - oym;
-        if ((unsigned)y >= 4u) continue;
-        const float *c = S.col[x * 4 + y] + azn * 9 + oxm * 3 + oym;
-#pragma unroll
-        for (int ch = 0; ch < 7; ++ch) v[ch] += c[ch * 72];
-      }
-    }
-#pragma unroll
-    for (int ch = 0; ch < 7; ++ch) out[blk * 448 + ch * 64 + cell] = v[ch];
-  }
-  // make the generic-proxy writes visible to the async proxy, then bulk-reduce each tile into HBM/L2
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  // ---- (c) add the eight arena tiles to the grid: TMA bulk reductions --------------------------------------------
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
   __syncthreads();
   if (tid < 8) {
     const int id = S.tile_id[tid];
     if (id >= 0) {
       float *g = tiles + (size_t)id * 448;
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
-                   "r"(smem_u32(out + tid * 448)), "r"(1792)
+                   "r"(smem_u32(S.out + tid * 448)), "r"(1792)
                    : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
