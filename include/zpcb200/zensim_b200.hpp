@@ -1,0 +1,230 @@
+// C++ host-side mirror of the reference interface for the MPM transfer path, over the C ABI (zpcb200.h).
+//
+// Header-only; needs only <cuda_runtime.h> and libzpcb200.so.  Names, argument meaning and error behaviour follow
+// zenustech/zpc (paths relative to include/zensim/):
+//   CudaExecutionPolicy + free functions reduce / exclusive_scan / inclusive_scan / radix_sort / radix_sort_pair
+//       <- cuda/execution/ExecutionPolicy.cuh:362-912, execution/ExecutionPolicy.hpp:684-781
+//          (chained setters device().stream().sync(); sync defaults to true; errors are latched, never thrown)
+//   plus<T>, getmax<T>, getmin<T>          <- ZpcFunctional.hpp:60-117
+//   Vector<T>                               <- container/Vector.hpp            (device memory, getVal/setVal)
+//   HashTable (i32,3,int)                   <- container/HashTable.hpp:15-206  (tableSize = next_2pow(n) * 16)
+//   Grids (f32,3,4) {m, v, rhs}             <- geometry/Structure.hpp:140-260
+//   Particles (f32,3) AoS x,v,m,C,F         <- geometry/Structurefree.hpp:22-224
+//   partition_for_particles, CleanGridBlocks, P2GTransfer, ComputeGridBlockVelocity, G2PTransfer
+//       <- simulation/{sparsity,grid,transfer}/*.hpp; invoked as pol(functor) instead of pol(range, functor).
+// There is no host fallback: every call lands in the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <type_traits>
+#include <vector>
+
+#include "../zpcb200.h"
+
+namespace zsb200 {
+
+template <typename T = void> struct plus {};
+template <typename T = void> struct getmax {};
+template <typename T = void> struct getmin {};
+
+template <typename T> struct Vector {  // device vector
+  T *_ptr{nullptr};
+  size_t _n{0};
+  Vector() = default;
+  explicit Vector(size_t n) : _n{n} {
+    if (cudaMalloc((void **)&_ptr, sizeof(T) * (n ? n : 1)) != cudaSuccess) throw std::runtime_error("cudaMalloc failed");
+  }
+  explicit Vector(const std::vector<T> &h) : Vector(h.size()) { cudaMemcpy(_ptr, h.data(), sizeof(T) * _n, cudaMemcpyHostToDevice); }
+  Vector(const Vector &) = delete;
+  Vector &operator=(const Vector &) = delete;
+  Vector(Vector &&o) noexcept : _ptr{o._ptr}, _n{o._n} { o._ptr = nullptr; o._n = 0; }
+  ~Vector() { if (_ptr) cudaFree(_ptr); }
+  T *data() { return _ptr; }
+  const T *data() const { return _ptr; }
+  T *begin() { return _ptr; }
+  T *end() { return _ptr + _n; }
+  size_t size() const { return _n; }
+  T getVal(size_t i = 0) const { T v; cudaMemcpy(&v, _ptr + i, sizeof(T), cudaMemcpyDeviceToHost); return v; }  // Vector.hpp getVal
+  void setVal(T v, size_t i = 0) { cudaMemcpy(_ptr + i, &v, sizeof(T), cudaMemcpyHostToDevice); }
+  std::vector<T> toHost() const { std::vector<T> h(_n); cudaMemcpy(h.data(), _ptr, sizeof(T) * _n, cudaMemcpyDeviceToHost); return h; }
+};
+
+template <typename T> inline zpc_port make_port(const T *p) { return zpc_port{(void *)p, 0, 0, 0, 1}; }
+
+struct CudaExecutionPolicy {
+  int _device{0};
+  cudaStream_t _stream{nullptr};
+  bool _sync{true};
+  mutable int _lastError{0};
+  mutable void *_scratch{nullptr};
+  mutable size_t _scratchBytes{0};
+  CudaExecutionPolicy() = default;
+  CudaExecutionPolicy(const CudaExecutionPolicy &o) : _device{o._device}, _stream{o._stream}, _sync{o._sync} {}
+  ~CudaExecutionPolicy() { if (_scratch) cudaFree(_scratch); }
+  CudaExecutionPolicy &device(int d) { _device = d; return *this; }
+  CudaExecutionPolicy &stream(cudaStream_t s) { _stream = s; return *this; }
+  CudaExecutionPolicy &sync(bool b) { _sync = b; return *this; }
+  bool shouldSync() const { return _sync; }
+  void *getStream() const { return (void *)_stream; }
+  int lastError() const { return _lastError; }
+
+  void *scratch(size_t bytes) const {
+    if (bytes > _scratchBytes) {
+      if (_scratch) cudaFree(_scratch);
+      _scratchBytes = bytes + bytes / 4 + 256;
+      if (cudaMalloc(&_scratch, _scratchBytes) != cudaSuccess) { _scratch = nullptr; _scratchBytes = 0; }
+    }
+    return _scratch;
+  }
+  template <typename Fn> void twoPhase(Fn fn) const {  // CUB-style size query then run (ExecutionPolicy.cuh:803-812)
+    cudaSetDevice(_device);
+    size_t bytes = 0;
+    int rc = fn(nullptr, &bytes);
+    if (!rc) {
+      void *t = scratch(bytes ? bytes : 1);
+      size_t cap = _scratchBytes;
+      rc = t ? fn(t, &cap) : (int)cudaErrorMemoryAllocation;
+    }
+    finish(rc);
+  }
+  void finish(int rc) const {
+    if (rc) _lastError = rc;  // latched like CudaContext::errorStatus (cuda/Cuda.h:291-312)
+    if (_sync) { cudaError_t e = cudaStreamSynchronize(_stream); if (e != cudaSuccess) _lastError = (int)e; }
+  }
+
+  // ---- primitives -----------------------------------------------------------------------------------------
+#define ZSB_DISPATCH_T(CALL_I32, CALL_U32, CALL_I64, CALL_F32)                                              \
+  if constexpr (std::is_same_v<T, int32_t>) { twoPhase([&](void *t, size_t *b) { return CALL_I32; }); }      \
+  else if constexpr (std::is_same_v<T, uint32_t>) { twoPhase([&](void *t, size_t *b) { return CALL_U32; }); } \
+  else if constexpr (std::is_same_v<T, int64_t>) { twoPhase([&](void *t, size_t *b) { return CALL_I64; }); }  \
+  else if constexpr (std::is_same_v<T, float>) { twoPhase([&](void *t, size_t *b) { return CALL_F32; }); }    \
+  else static_assert(sizeof(T) == 0, "unsupported element type");
+  template <typename T, template <class> class Op, typename U>
+  void reduce(const T *first, const T *last, T *d_first, T /*init = identity*/, Op<U>) const {
+    const size_t n = (size_t)(last - first);
+    const zpc_port in = make_port(first), out = make_port(d_first);
+    if constexpr (std::is_same_v<Op<U>, plus<U>>) {
+      ZSB_DISPATCH_T(zpcb200_reduce_sum_i32(t, b, in, out, n, _stream), zpcb200_reduce_sum_u32(t, b, in, out, n, _stream),
+                     zpcb200_reduce_sum_i64(t, b, in, out, n, _stream), zpcb200_reduce_sum_f32(t, b, in, out, n, _stream))
+    } else if constexpr (std::is_same_v<Op<U>, getmax<U>>) {
+      ZSB_DISPATCH_T(zpcb200_reduce_max_i32(t, b, in, out, n, _stream), zpcb200_reduce_max_u32(t, b, in, out, n, _stream),
+                     zpcb200_reduce_max_i64(t, b, in, out, n, _stream), zpcb200_reduce_max_f32(t, b, in, out, n, _stream))
+    } else {
+      ZSB_DISPATCH_T(zpcb200_reduce_min_i32(t, b, in, out, n, _stream), zpcb200_reduce_min_u32(t, b, in, out, n, _stream),
+                     zpcb200_reduce_min_i64(t, b, in, out, n, _stream), zpcb200_reduce_min_f32(t, b, in, out, n, _stream))
+    }
+  }
+  template <typename T> void exclusive_scan(const T *first, const T *last, T *d_first) const {
+    const size_t n = (size_t)(last - first);
+    const zpc_port in = make_port(first), out = make_port(d_first);
+    ZSB_DISPATCH_T(zpcb200_exclusive_scan_sum_i32(t, b, in, out, n, _stream), zpcb200_exclusive_scan_sum_u32(t, b, in, out, n, _stream),
+                   zpcb200_exclusive_scan_sum_i64(t, b, in, out, n, _stream), zpcb200_exclusive_scan_sum_f32(t, b, in, out, n, _stream))
+  }
+  template <typename T> void inclusive_scan(const T *first, const T *last, T *d_first) const {
+    const size_t n = (size_t)(last - first);
+    const zpc_port in = make_port(first), out = make_port(d_first);
+    ZSB_DISPATCH_T(zpcb200_inclusive_scan_sum_i32(t, b, in, out, n, _stream), zpcb200_inclusive_scan_sum_u32(t, b, in, out, n, _stream),
+                   zpcb200_inclusive_scan_sum_i64(t, b, in, out, n, _stream), zpcb200_inclusive_scan_sum_f32(t, b, in, out, n, _stream))
+  }
+#undef ZSB_DISPATCH_T
+  template <typename K>
+  void radix_sort_pair(const K *keysIn, const int *valsIn, K *keysOut, int *valsOut, size_t count, int sbit = 0,
+                       int ebit = sizeof(K) * 8) const {
+    const zpc_port ki = make_port(keysIn), vi = make_port(valsIn), ko = make_port(keysOut), vo = make_port(valsOut);
+    if constexpr (std::is_same_v<K, uint32_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_radix_sort_pair_u32(t, b, ki, vi, ko, vo, count, sbit, ebit, _stream); });
+    else if constexpr (std::is_same_v<K, int32_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_radix_sort_pair_i32(t, b, ki, vi, ko, vo, count, sbit, ebit, _stream); });
+    else if constexpr (std::is_same_v<K, uint64_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_radix_sort_pair_u64(t, b, ki, vi, ko, vo, count, sbit, ebit, _stream); });
+    else static_assert(sizeof(K) == 0, "radix sort keys: u32, i32, u64");
+  }
+  template <typename K> void radix_sort(const K *first, const K *last, K *d_first, int sbit = 0, int ebit = sizeof(K) * 8) const {
+    const size_t n = (size_t)(last - first);
+    const zpc_port ki = make_port(first), ko = make_port(d_first);
+    if constexpr (std::is_same_v<K, uint32_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_radix_sort_u32(t, b, ki, ko, n, sbit, ebit, _stream); });
+    else if constexpr (std::is_same_v<K, int32_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_radix_sort_i32(t, b, ki, ko, n, sbit, ebit, _stream); });
+    else if constexpr (std::is_same_v<K, uint64_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_radix_sort_u64(t, b, ki, ko, n, sbit, ebit, _stream); });
+    else static_assert(sizeof(K) == 0, "radix sort keys: u32, i32, u64");
+  }
+  // pol(functor): one C call per functor (the reference writes pol(range, functor))
+  template <typename F> void operator()(F &&f) const { finish(f.launch(*this)); }
+};
+inline CudaExecutionPolicy cuda_exec() { return CudaExecutionPolicy{}; }
+
+// free-function wrappers (execution/ExecutionPolicy.hpp:684-781)
+template <typename T, typename Op> void reduce(const CudaExecutionPolicy &p, const T *f, const T *l, T *o, T init, Op op) { p.reduce(f, l, o, init, op); }
+template <typename T> void exclusive_scan(const CudaExecutionPolicy &p, const T *f, const T *l, T *o) { p.exclusive_scan(f, l, o); }
+template <typename T> void inclusive_scan(const CudaExecutionPolicy &p, const T *f, const T *l, T *o) { p.inclusive_scan(f, l, o); }
+template <typename K> void radix_sort(const CudaExecutionPolicy &p, const K *f, const K *l, K *o, int sbit = 0, int ebit = sizeof(K) * 8) { p.radix_sort(f, l, o, sbit, ebit); }
+template <typename K>
+void radix_sort_pair(const CudaExecutionPolicy &p, const K *ki, const int *vi, K *ko, int *vo, size_t count, int sbit = 0, int ebit = sizeof(K) * 8) {
+  p.radix_sort_pair(ki, vi, ko, vo, count, sbit, ebit);
+}
+
+// ---- containers of the MPM path -----------------------------------------------------------------------------
+inline size_t next_2pow(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+
+struct HashTable {  // HashTable<i32,3,int>
+  int _tableSize;
+  Vector<int> keys, indices, status, _activeKeys, _cnt, _overflow;
+  explicit HashTable(size_t numExpectedEntries)
+      : _tableSize{(int)(next_2pow(numExpectedEntries) * 16)}, keys((size_t)_tableSize * 3), indices(_tableSize), status(_tableSize),
+        _activeKeys((size_t)_tableSize * 3), _cnt(1), _overflow(1) { _cnt.setVal(0); _overflow.setVal(0); }
+  int size() const { return _cnt.getVal(); }  // the D2H read of HashTable.hpp:152
+  zpc_hashtable_view view() { return zpc_hashtable_view{keys.data(), indices.data(), status.data(), _activeKeys.data(), _tableSize, _cnt.data()}; }
+};
+struct Grids {  // Grids<f32,3,4>, channels {"m",1},{"v",3},{"rhs",3}
+  float _dx;
+  size_t _numBlocks;
+  Vector<float> blocks;
+  Grids(float dx, size_t numBlocks) : _dx{dx}, _numBlocks{numBlocks}, blocks(numBlocks * 7 * 64) {}
+  zpc_grids_view view() { return zpc_grids_view{blocks.data(), _numBlocks, 7, _dx}; }
+};
+struct Particles {  // Particles<f32,3>, AoS attributes
+  size_t _n;
+  Vector<float> X, V, M, C, F;
+  explicit Particles(size_t n) : _n{n}, X(3 * n), V(3 * n), M(n), C(9 * n), F(9 * n) {}
+  size_t size() const { return _n; }
+  zpc_particles_view view() { return zpc_particles_view{M.data(), X.data(), V.data(), nullptr, nullptr, F.data(), C.data(), nullptr, _n}; }
+};
+struct FixedCorotatedConfig { float rho{1e3f}, volume{1.f}; int dim{3}; float E{5e4f}, nu{0.4f}; };  // ConstitutiveModel.hpp:739-742
+
+// ---- functors ---------------------------------------------------------------------------------------------------
+struct PartitionForParticles {  // CleanSparsity + ComputeSparsity + EnlargeSparsity{lo,hi}
+  Particles &pars; float dx; HashTable &table; int lo{0}, hi{2};
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_port x{pars.X.data(), 0, 0, 0, 3};
+    size_t bytes = 0;
+    int rc = zpcb200_partition_build(nullptr, &bytes, x, pars.size(), dx, table.view(), lo, hi, table._overflow.data(), pol._stream);
+    if (rc) return rc;
+    void *t = pol.scratch(bytes);
+    size_t cap = pol._scratchBytes;
+    return t ? zpcb200_partition_build(t, &cap, x, pars.size(), dx, table.view(), lo, hi, table._overflow.data(), pol._stream)
+             : (int)cudaErrorMemoryAllocation;
+  }
+};
+struct CleanGridBlocks {
+  Grids &grids; HashTable &table;
+  int launch(const CudaExecutionPolicy &pol) { return zpcb200_clean_grid(grids.view(), table._cnt.data(), pol._stream); }
+};
+struct P2GTransfer {  // P2GTransfer{cuda_c, wrapv<apic>{}, dt, model, pars, table, grids}
+  float dt; FixedCorotatedConfig model; Particles &pars; HashTable &table; Grids &grids;
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
+    return zpcb200_p2g_apic_fcr(pars.view(), table.view(), grids.view(), dt, m, pol._stream);
+  }
+};
+struct ComputeGridBlockVelocity {  // {cuda_c, wrapv<apic>{}, grids, dt, gravity, maxVel}; mode 1 adds rhs (explicit update)
+  Grids &grids; HashTable &table; float dt; float gravity; float *maxVel; int mode{0};
+  int launch(const CudaExecutionPolicy &pol) {
+    const float extf[3] = {0.f, gravity, 0.f};
+    return zpcb200_grid_update(grids.view(), table._cnt.data(), dt, extf, mode, maxVel, pol._stream);
+  }
+};
+struct G2PTransfer {
+  float dt; Grids &grids; HashTable &table; Particles &pars;
+  int launch(const CudaExecutionPolicy &pol) { return zpcb200_g2p_apic(pars.view(), table.view(), grids.view(), dt, pol._stream); }
+};
+
+}  // namespace zsb200
