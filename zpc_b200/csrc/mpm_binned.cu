@@ -276,7 +276,7 @@ struct G2PSmem {
   unsigned char grp_of[BIN_MAX];
 };
 
-__global__ void __launch_bounds__(G2P_NT)
+__global__ void __launch_bounds__(G2P_NT, 4)
 g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder, unsigned short *__restrict__ cellStart,
                   zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx, float dt) {
@@ -322,9 +322,11 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
   const float *sv = &S.v[0][0][0];
   for (int i = tid; i < np; i += G2P_NT) {
     const size_t s = pslot((size_t)p0 + i);
-    float pos[3];
+    float pos[3], Fo[9];
 #pragma unroll
     for (int d = 0; d < 3; ++d) pos[d] = pars[s + (ZPC_PB_X + d) * TS];
+#pragma unroll
+    for (int d = 0; d < 9; ++d) Fo[d] = pars[s + (ZPC_PB_F + d) * TS];  // issued early: consumed after the contraction
     zpcm::Arena ar;
     zpcm::arena_init(ar, dx, pos);
     const int ax0 = ar.corner[0] - 4 * kx, ay0 = ar.corner[1] - 4 * ky, az0 = ar.corner[2] - 4 * kz;
@@ -377,7 +379,7 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
       zpcp::g2p_gather_particle(ar, tb, tiles, nch, vel, G);
     }
     // C[r + 3e] = D_inv * sum W v_r (o_e dx - local_e) = D_inv * (dx G_re - local_e v_r)
-    float C[9], Fo[9], tmp[9];
+    float C[9], tmp[9];
 #pragma unroll
     for (int e = 0; e < 3; ++e)
 #pragma unroll
@@ -394,7 +396,7 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
       atomicAdd(&S.cnt[g], 1);
     }
 #pragma unroll
-    for (int d = 0; d < 9; ++d) { Fo[d] = pars[s + (ZPC_PB_F + d) * TS]; tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f); }
+    for (int d = 0; d < 9; ++d) tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f);
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
