@@ -416,9 +416,23 @@ __global__ void rs_scan_hist_kernel(unsigned *ghist) {
   h[threadIdx.x] = off + inc - v;
 }
 
-template <typename K, bool PAIRS, int ITEMS>
+// element access of one tile: raw pointers when every range is contiguous (FAST), iterator ports otherwise
+template <typename T, bool FAST> struct TileAcc;
+template <typename T> struct TileAcc<T, true> {
+  T *p;
+  __device__ __forceinline__ TileAcc(const PortAcc<T> &a, size_t base) : p(a.base + a.idx + base) {}
+  __device__ __forceinline__ T &operator[](long long i) const { return p[i]; }
+};
+template <typename T> struct TileAcc<T, false> {
+  PortAcc<T> a;
+  size_t base;
+  __device__ __forceinline__ TileAcc(const PortAcc<T> &a_, size_t base_) : a(a_), base(base_) {}
+  __device__ __forceinline__ T &operator[](long long i) const { return a[(size_t)((long long)base + i)]; }
+};
+
+template <typename K, bool PAIRS, int ITEMS, bool FAST>
 __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? 3 : 2) rs_onesweep_kernel(PortAcc<K> kin, PortAcc<int> vin, PortAcc<K> kout,
-                                                            PortAcc<int> vout, size_t n, int shift, unsigned mask,
+                                                            PortAcc<int> vout, size_t n, int shift, unsigned mask, int nbits,
                                                             const unsigned *gbase /*[256] exclusive*/,
                                                             unsigned *lookback /*[tiles][256]*/, unsigned *ticket) {
   constexpr int TILE = RS_NT * ITEMS;
@@ -436,31 +450,27 @@ __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? 3 : 2) rs_onesweep_ker
   const unsigned tile = s_tile;
   const size_t base = (size_t)tile * TILE;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  const size_t wbase = base + (size_t)w * (32 * ITEMS);
+  const int wofs = w * (32 * ITEMS) + l;  // tile-local index of this thread's item i: wofs + 32 i
   const int cnt_tile = (int)min((size_t)TILE, n - base);
+  const TileAcc<K, FAST> tk(kin, base);
 
   K key[ITEMS];
   unsigned rank[ITEMS];  // rank among same-digit keys of this warp (then of this tile)
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    size_t e = wbase + (size_t)i * 32 + l;
-    key[i] = e < n ? kin[e] : (K)0;
-  }
-  // warp-synchronous stable ranking.  MATCH.ANY has a long latency: issue all of them first (independent), then
-  // run the serial per-item counter updates on the masks.
-  unsigned peers_of[ITEMS];
+  for (int i = 0; i < ITEMS; ++i) key[i] = (wofs + 32 * i) < cnt_tile ? tk[wofs + 32 * i] : (K)0;
+  // warp-synchronous stable ranking: lanes holding the same digit are found with one ballot per digit bit
+  // (MATCH.ANY has a long, poorly pipelined latency on sm_100), then one shared-memory counter per (warp, digit)
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    const size_t e = wbase + (size_t)i * 32 + l;
-    const unsigned d = e < n ? digit_of(key[i], shift, mask) : RS_BINS;  // invalid lanes match only each other
-    peers_of[i] = __match_any_sync(0xffffffffu, d);
-  }
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const size_t e = wbase + (size_t)i * 32 + l;
-    const bool valid = e < n;
+    const bool valid = (wofs + 32 * i) < cnt_tile;
     const unsigned d = digit_of(key[i], shift, mask);
-    const unsigned peers = peers_of[i];
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+    if (!valid) peers = ~peers;
+    for (int b = 0; b < nbits; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const unsigned vote = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? vote : ~vote;
+    }
     const unsigned before = __popc(peers & lanemask_lt());
     const int leader = __ffs(peers) - 1;
     unsigned c = 0;
@@ -541,44 +551,40 @@ __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? 3 : 2) rs_onesweep_ker
   // scatter into shared memory in tile-sorted order
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    size_t e = wbase + (size_t)i * 32 + l;
-    if (e < n) {
-      unsigned d = digit_of(key[i], shift, mask);
+    if ((wofs + 32 * i) < cnt_tile) {
+      const unsigned d = digit_of(key[i], shift, mask);
       rank[i] = tile_base[d] + warp_hist[w][d] + rank[i];
       skeys[rank[i]] = key[i];
     }
   }
   __syncthreads();
   // coalesced write-out: slot j goes to j + gofs[digit(key_j)]
-  for (int j = threadIdx.x; j < cnt_tile; j += RS_NT) {
-    K k = skeys[j];
-    kout[(size_t)((long long)j + gofs[digit_of(k, shift, mask)])] = k;
+  const TileAcc<K, FAST> ok(kout, 0);
+  unsigned dj[ITEMS];  // digit of the key in tile slot threadIdx.x + i*RS_NT (reused for the values)
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int j = threadIdx.x + i * RS_NT;
+    dj[i] = 0;
+    if (j < cnt_tile) {
+      const K k = skeys[j];
+      dj[i] = digit_of(k, shift, mask);
+      ok[(long long)j + gofs[dj[i]]] = k;
+    }
   }
   if constexpr (PAIRS) {
+    const TileAcc<int, FAST> tv(vin, base), ov(vout, 0);
     int val[ITEMS];
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      size_t e = wbase + (size_t)i * 32 + l;
-      val[i] = e < n ? vin[e] : 0;
-    }
-    // need the digit of slot j again after skeys is overwritten: keep it in a register first
-    unsigned dj[ITEMS];
+    for (int i = 0; i < ITEMS; ++i) val[i] = (wofs + 32 * i) < cnt_tile ? tv[wofs + 32 * i] : 0;
+    __syncthreads();  // every thread is done reading skeys
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      int j = threadIdx.x + i * RS_NT;
-      dj[i] = j < cnt_tile ? digit_of(skeys[j], shift, mask) : 0;
-    }
+    for (int i = 0; i < ITEMS; ++i)
+      if ((wofs + 32 * i) < cnt_tile) svals[rank[i]] = val[i];
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-      size_t e = wbase + (size_t)i * 32 + l;
-      if (e < n) svals[rank[i]] = val[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      int j = threadIdx.x + i * RS_NT;
-      if (j < cnt_tile) vout[(size_t)((long long)j + gofs[dj[i]])] = svals[j];
+      const int j = threadIdx.x + i * RS_NT;
+      if (j < cnt_tile) ov[(long long)j + gofs[dj[i]]] = svals[j];
     }
   }
 }
@@ -632,9 +638,15 @@ int radix_sort_impl(void *temp, size_t *temp_bytes, zpc_port keys_in, zpc_port v
     const int shift = sbit + 8 * p;
     const int bits = npass > 0 ? ((ebit - shift) < 8 ? (ebit - shift) : 8) : 0;
     const unsigned mask = (1u << bits) - 1;
-    rs_onesweep_kernel<K, PAIRS, ITEMS><<<(unsigned)tiles, RS_NT, 0, s>>>(
-        PortAcc<K>(src_k), PortAcc<int>(src_v), PortAcc<K>(dst_k), PortAcc<int>(dst_v), n, shift, mask,
-        ghist + p * RS_BINS, lookback + (size_t)p * tiles * RS_BINS, ticket + p);
+    const bool fast = src_k.numChns == 1 && dst_k.numChns == 1 && (!PAIRS || (src_v.numChns == 1 && dst_v.numChns == 1));
+    if (fast)
+      rs_onesweep_kernel<K, PAIRS, ITEMS, true><<<(unsigned)tiles, RS_NT, 0, s>>>(
+          PortAcc<K>(src_k), PortAcc<int>(src_v), PortAcc<K>(dst_k), PortAcc<int>(dst_v), n, shift, mask, bits,
+          ghist + p * RS_BINS, lookback + (size_t)p * tiles * RS_BINS, ticket + p);
+    else
+      rs_onesweep_kernel<K, PAIRS, ITEMS, false><<<(unsigned)tiles, RS_NT, 0, s>>>(
+          PortAcc<K>(src_k), PortAcc<int>(src_v), PortAcc<K>(dst_k), PortAcc<int>(dst_v), n, shift, mask, bits,
+          ghist + p * RS_BINS, lookback + (size_t)p * tiles * RS_BINS, ticket + p);
     ZPC_CHECK_LAUNCH();
     src_k = dst_k;
     src_v = dst_v;
