@@ -35,7 +35,7 @@ def main():
     mine = sol.local.particles_host()
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
-    mx = float(sol.local.max_vel_sqr.item())
+    mx = float(sol.max_vel_sqr().item())
     ok = True
     if rank == 0:
         got = {k: np.concatenate([g[k] for g in gathered]) for k in ("x", "v", "m", "C", "F")}

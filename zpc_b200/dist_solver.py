@@ -42,27 +42,39 @@ class HaloExchange:
         self.peers = []       # [(rank, ids int32 tensor, send buf, recv buf)]
 
     def build(self, active_keys):
-        """active_keys: int32 [nb,3] of this rank (rows in ascending key order).  Collective."""
+        """active_keys: int32 [nb,3] of this rank (rows in ascending key order).  Collective.
+        Two all_gathers and one device->host read: every rank's keys are gathered (padded, rows stay sorted), the
+        intersections with all peers come from one batched searchsorted, one nonzero splits them per peer."""
         mine = pack_keys(active_keys)
-        cnt = torch.tensor([mine.numel()], dtype=torch.int64, device=mine.device)
-        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
-        dist.all_gather(cnts, cnt, group=self.group)
-        mx = int(max(int(c.item()) for c in cnts))
-        pad = torch.full((max(mx, 1),), -1, dtype=torch.int64, device=mine.device)
+        dev = mine.device
+        cnt = torch.tensor([mine.numel()], dtype=torch.int64, device=dev)
+        cnts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(cnts, cnt, group=self.group)
+        cnts_h = cnts.tolist()
+        mx = max(max(cnts_h), 1)
+        pad = torch.full((mx,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
         pad[: mine.numel()] = mine
-        allk = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(allk, pad, group=self.group)
+        allk = torch.empty(self.world * mx, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allk, pad, group=self.group)
+        allk = allk.view(self.world, mx)
         self.peers = []
-        for q in range(self.world):
-            if q == self.rank:
-                continue
-            theirs = allk[q][: int(cnts[q].item())]
-            ids = torch.nonzero(torch.isin(mine, theirs)).flatten().to(torch.int32)   # ascending key order on both sides
-            if ids.numel():
-                n = ids.numel()
-                self.peers.append((q, ids.contiguous(),
-                                   torch.empty(n, self.nch, 64, dtype=torch.float32, device=mine.device),
-                                   torch.empty(n, self.nch, 64, dtype=torch.float32, device=mine.device)))
+        if mine.numel() == 0:
+            return self.peers
+        q = mine.unsqueeze(0).expand(self.world, -1).contiguous()
+        pos = torch.searchsorted(allk, q).clamp_(max=mx - 1)
+        hit = torch.gather(allk, 1, pos) == q                      # [world, nb]: my block b is also active on rank r
+        hit[self.rank] = False
+        rows, cols = torch.nonzero(hit, as_tuple=True)             # row-major: per peer, ascending key order
+        per = torch.bincount(rows, minlength=self.world).tolist()
+        cols = cols.to(torch.int32)
+        off = 0
+        for r in range(self.world):
+            n = per[r]
+            if n:
+                ids = cols[off:off + n].contiguous()
+                self.peers.append((r, ids, torch.empty(n, self.nch, 64, dtype=torch.float32, device=dev),
+                                   torch.empty(n, self.nch, 64, dtype=torch.float32, device=dev)))
+            off += n
         return self.peers
 
     def shared_blocks(self):
@@ -104,6 +116,7 @@ class DistMpmSolver:
         self.table = self.local.table
         self.halo = HaloExchange(group, 7, device, _cuda_pack, _cuda_unpack_add)
         self.group = group
+        self._cfl_work = None
         self._rebuild_topology()
 
     @property
@@ -121,8 +134,18 @@ class DistMpmSolver:
         nb = self.local.table.size()
         self.halo.build(self.local.table.active_keys[:nb])
 
+    def max_vel_sqr(self):
+        """global max |v|^2 of the last substep (CFL input); waits for the in-flight all_reduce"""
+        if self._cfl_work is not None:
+            self._cfl_work.wait()
+            self._cfl_work = None
+        return self.local.max_vel_sqr
+
     def substep(self):
         L = self.local
+        if self._cfl_work is not None:      # the previous step's CFL reduction must be done before the scalar is reused
+            self._cfl_work.wait()
+            self._cfl_work = None
         if L.prepare():
             self._rebuild_topology()
         L._mark("begin")
@@ -134,7 +157,8 @@ class DistMpmSolver:
         L._mark("halo")
         L.max_vel_sqr.zero_()
         api.compute_grid_block_velocity(L.grids, L.table, L.dt, L.extf, L.mode, L.max_vel_sqr)
-        dist.all_reduce(L.max_vel_sqr, op=dist.ReduceOp.MAX, group=self.group)
+        # nothing downstream in the substep consumes the CFL scalar: reduce it off the critical path
+        self._cfl_work = dist.all_reduce(L.max_vel_sqr, op=dist.ReduceOp.MAX, group=self.group, async_op=True)
         L._mark("grid_update")
         api.g2p_transfer(L.bins, L.table, L.grids, L.dt)
         L._mark("g2p")
