@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--rebin-every", type=int, default=8)
     ap.add_argument("--partition", default="with_rebin", choices=["with_rebin", "every_step"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -183,7 +184,8 @@ def main():
     else:
         from zpc_b200.dist_solver import DistMpmSolver
         P = synth.elastic_cube_slab(s, G, rank, world)
-        sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, rebin_every=args.rebin_every)
+        sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, rebin_every=args.rebin_every,
+                            transport=args.halo)
         n_local = sol.n
     torch.cuda.synchronize()
 
@@ -279,7 +281,8 @@ def main():
                                 partition=("hash-grid partition rebuilt every substep (EnlargeSparsity{0,2})" if (args.partition == "every_step" and world == 1)
                                            else "hash-grid partition rebuilt with each re-bin, one extra ring (EnlargeSparsity{-1,3})"),
                                 active_blocks=nblocks, l2="inputs (%.1f GB particle state) exceed the 126 MB L2; no explicit flush" % (n_local * 100 / 1e9),
-                                parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, NCCL halo exchange of shared grid blocks" % world),
+                                parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, halo exchange of shared grid blocks via %s" % (
+                                    world, "peer stores into symmetric memory over NVLink + device barrier" if sol.transport == "p2p" else "NCCL send/recv")),
                     substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,
                     clocks=clocks)
         print(json.dumps(line))

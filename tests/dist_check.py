@@ -28,7 +28,8 @@ def main():
     full["m"] = (full["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)   # identity tag
     c0, c1 = synth.slab_cell_range(s, rank, world)
     P = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
-    sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, rebin_every=3)
+    sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, rebin_every=3,
+                        transport=os.environ.get("ZPC_HALO", "auto"))
     for _ in range(steps):
         sol.substep()
     torch.cuda.synchronize()
@@ -51,7 +52,7 @@ def main():
         try:
             check_particles(canon(got), canon(want), full["dx"], "%d-GPU vs 1-GPU (%d substeps)" % (world, steps), rtol=5e-5)
             assert abs(mx - float(one.max_vel_sqr.item())) <= 1e-4 * mx
-            print("dist_check ok: world %d, shared blocks on rank 0: %d" % (world, sol.halo.shared_blocks()))
+            print("dist_check ok: world %d, transport %s, shared blocks on rank 0: %d" % (world, sol.transport, sol.halo.shared_blocks()))
         except AssertionError as e:
             print("dist_check FAILED:", e)
             ok = False

@@ -95,6 +95,59 @@ class HaloExchange:
             self._unpack_add(grids, ids, rbuf)
 
 
+class HaloExchangeP2P(HaloExchange):
+    """Same exchange without NCCL point-to-point: every rank owns a symmetric receive buffer (torch symmetric memory,
+    peer-mapped over NVLink); the pack kernel stores the shared tiles STRAIGHT INTO THE PEER'S buffer, one
+    device-side barrier makes them visible, the unpack kernel adds them locally.  The two halves of the buffer
+    alternate by step so that one barrier per substep suffices."""
+
+    def __init__(self, group=None, nch=7, device="cuda", pack_ptr=None, unpack_add=None, capacity_blocks=16384):
+        super().__init__(group, nch, device, None, unpack_add)
+        import torch.distributed._symmetric_memory as symm_mem
+        self._pack_ptr = pack_ptr
+        self.cap = int(capacity_blocks)
+        self.tile = nch * 64
+        self.buf = symm_mem.empty(2 * self.cap * self.tile, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        self.ptrs = list(self.hdl.buffer_ptrs)
+        self.step = 0
+        self.plan = []   # [(peer, ids, n, offset in the peer's buffer, offset in my buffer)]  offsets in tiles
+
+    def build(self, active_keys):
+        peers = super().build(active_keys)            # reuses the key exchange; drops the NCCL staging buffers below
+        dev = active_keys.device
+        row = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        for q, ids, _, _ in peers:
+            row[q] = ids.numel()
+        mat = torch.zeros(self.world * self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(mat, row, group=self.group)
+        M = mat.view(self.world, self.world).tolist()  # M[a][b] = number of blocks ranks a and b share
+        if max(sum(r) for r in M) > self.cap:
+            raise api.ZpcError("halo buffer too small: %d shared blocks > capacity %d" % (max(sum(r) for r in M), self.cap))
+        self.plan = []
+        for q, ids, _, _ in peers:
+            off_in_peer = sum(M[q][r] for r in range(self.rank))   # receiver q lays senders out in ascending rank order
+            off_in_mine = sum(M[self.rank][r] for r in range(q))
+            self.plan.append((q, ids, ids.numel(), off_in_peer, off_in_mine))
+        self.peers = [(q, ids, None, None) for q, ids, _, _ in peers]
+        return self.peers
+
+    def exchange_add(self, grids):
+        half = (self.step & 1) * self.cap
+        self.step += 1
+        for q, ids, n, off_peer, _ in self.plan:       # pack + transfer in one kernel: stores land in rank q's HBM
+            self._pack_ptr(grids, ids, self.ptrs[q] + 4 * (half + off_peer) * self.tile)
+        self.hdl.barrier(channel=0)                    # device-side, on the current stream
+        for q, ids, n, _, off_mine in self.plan:
+            self._unpack_add(grids, ids, self.buf[(half + off_mine) * self.tile:(half + off_mine + n) * self.tile])
+
+
+def _cuda_pack_ptr(grids, ids, dst_ptr):
+    import ctypes as C
+    api._check(api.lib().zpcb200_halo_pack(grids.view(), C.c_void_p(ids.data_ptr()), C.c_int(ids.numel()), C.c_int(0),
+                                           C.c_int(grids.nch), C.c_void_p(dst_ptr), api._stream_ptr()), "halo_pack(p2p)")
+
+
 def _cuda_pack(grids, ids, buf):
     import ctypes as C
     api._check(api.lib().zpcb200_halo_pack(grids.view(), C.c_void_p(ids.data_ptr()), C.c_int(ids.numel()), C.c_int(0),
@@ -109,12 +162,23 @@ def _cuda_unpack_add(grids, ids, buf):
 
 
 class DistMpmSolver:
-    def __init__(self, P_local, dx, volume, dt, gravity=-9.8, mode=1, rebin_every=8, group=None, device="cuda", **kw):
+    def __init__(self, P_local, dx, volume, dt, gravity=-9.8, mode=1, rebin_every=8, group=None, device="cuda",
+                 transport="auto", **kw):
         self.local = MpmSolver(P_local, dx, volume, dt, gravity, mode, layout="binned", rebin_every=rebin_every,
                                device=device, partition="with_rebin", **kw)
         self.n = self.local.n
         self.table = self.local.table
-        self.halo = HaloExchange(group, 7, device, _cuda_pack, _cuda_unpack_add)
+        self.halo = None
+        if transport in ("auto", "p2p"):
+            try:
+                self.halo = HaloExchangeP2P(group, 7, device, _cuda_pack_ptr, _cuda_unpack_add)
+            except Exception as ex:  # no symmetric memory on this system: same exchange over NCCL send/recv
+                if transport == "p2p":
+                    raise
+                self.halo_fallback_reason = repr(ex)
+        if self.halo is None:
+            self.halo = HaloExchange(group, 7, device, _cuda_pack, _cuda_unpack_add)
+        self.transport = "p2p" if isinstance(self.halo, HaloExchangeP2P) else "nccl"
         self.group = group
         self._cfl_work = None
         self._rebuild_topology()
