@@ -101,17 +101,23 @@ class HaloExchangeP2P(HaloExchange):
     device-side barrier makes them visible, the unpack kernel adds them locally.  The two halves of the buffer
     alternate by step so that one barrier per substep suffices."""
 
-    def __init__(self, group=None, nch=7, device="cuda", pack_ptr=None, unpack_add=None, capacity_blocks=16384):
+    def __init__(self, group=None, nch=7, device="cuda", pack_ptr=None, unpack_add=None, capacity_blocks=4096):
         super().__init__(group, nch, device, None, unpack_add)
-        import torch.distributed._symmetric_memory as symm_mem
         self._pack_ptr = pack_ptr
-        self.cap = int(capacity_blocks)
         self.tile = nch * 64
-        self.buf = symm_mem.empty(2 * self.cap * self.tile, dtype=torch.float32, device=device)
-        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD if group is None else group)
-        self.ptrs = list(self.hdl.buffer_ptrs)
+        self.cap = 0
+        self.buf = self.hdl = self.ptrs = None
         self.step = 0
         self.plan = []   # [(peer, ids, n, offset in the peer's buffer, offset in my buffer)]  offsets in tiles
+        self._allocate(int(capacity_blocks))
+
+    def _allocate(self, capacity_blocks):
+        """(re)allocate the symmetric receive buffer; collective (every rank calls it with the same capacity)"""
+        import torch.distributed._symmetric_memory as symm_mem
+        self.cap = capacity_blocks
+        self.buf = symm_mem.empty(2 * self.cap * self.tile, dtype=torch.float32, device=self.device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD if self.group is None else self.group)
+        self.ptrs = list(self.hdl.buffer_ptrs)
 
     def build(self, active_keys):
         peers = super().build(active_keys)            # reuses the key exchange; drops the NCCL staging buffers below
@@ -122,8 +128,10 @@ class HaloExchangeP2P(HaloExchange):
         mat = torch.zeros(self.world * self.world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(mat, row, group=self.group)
         M = mat.view(self.world, self.world).tolist()  # M[a][b] = number of blocks ranks a and b share
-        if max(sum(r) for r in M) > self.cap:
-            raise api.ZpcError("halo buffer too small: %d shared blocks > capacity %d" % (max(sum(r) for r in M), self.cap))
+        need = max(sum(r) for r in M)                  # the same number on every rank
+        if need > self.cap:
+            torch.cuda.synchronize()
+            self._allocate(int(need * 1.5) + 64)
         self.plan = []
         for q, ids, _, _ in peers:
             off_in_peer = sum(M[q][r] for r in range(self.rank))   # receiver q lays senders out in ascending rank order
