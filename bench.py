@@ -231,9 +231,17 @@ def main():
         if per_step.get(k):
             gbs = bpp * n_local / (per_step[k] * 1e-3) / 1e9
             kern[k] = dict(ms=per_step[k], algorithmic_gbps=gbs, frac=gbs / hbm_peak)
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this config (per launch)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr.get("config") == args.config and world == 1:
+            traffic = tr["kernels"]["p2g_binned_kernel"]["dram_bytes"]
+    except Exception:
+        pass
     dom = "p2g"
     roof = dict(bound="hbm", kernel="p2g_binned_kernel", achieved=kern.get(dom, {}).get("algorithmic_gbps"), peak=hbm_peak, unit="GB/s",
-                frac=kern.get(dom, {}).get("frac"), traffic=None, peak_source=peak_src,
+                frac=kern.get(dom, {}).get("frac"), traffic=traffic, peak_source=peak_src,
                 algorithmic_bytes_per_launch=BYTES_PER_PARTICLE[dom] * n_local)
     fused_gbps = 257.5 * n_local / (fused_ms * 1e-3) / 1e9 if fused_ms else None
     fused = dict(ms=fused_ms, bytes_per_particle=257.5, achieved=fused_gbps, frac=(fused_gbps / hbm_peak) if fused_gbps else None,
