@@ -124,6 +124,13 @@ typedef struct zpc_fixed_corotated {
   float E, nu;
 } zpc_fixed_corotated;
 
+/* EquationOfStateConfig — physics/ConstitutiveModel.hpp:730-734 (gamma is forced to 7 by P2G.hpp:72-75) */
+typedef struct zpc_equation_of_state {
+  float rho, volume;
+  int dim;
+  float bulk, gamma, viscosity;
+} zpc_equation_of_state;
+
 /* ------------------------------------------------------------------------------------------ */
 /* MPM path                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
@@ -156,6 +163,13 @@ int zpcb200_grid_update(zpc_grids_view grids, const int *cnt, float dt, const fl
 /* G2PTransfer<apic> (simulation/transfer/G2P.hpp:43-84), AoS layout, any order. */
 int zpcb200_g2p_apic(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
                      float dt, zpc_stream_t stream);
+
+/* The same two functors for EquationOfStateConfig (weakly compressible fluid: per-particle J instead of F;
+ * P2G.hpp:66-87, G2P.hpp:69-73).  pars.J must be set; F is not touched. */
+int zpcb200_p2g_apic_eos(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
+                         float dt, zpc_equation_of_state model, zpc_stream_t stream);
+int zpcb200_g2p_apic_eos(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
+                         float dt, zpc_stream_t stream);
 
 /* ---- binned (block-sorted AoSoA) fast path ------------------------------------------------- */
 /* Bins: particles sorted by home block (the block ComputeSparsity assigns, SparsityOp.hpp:68-79),

@@ -374,6 +374,56 @@ void zo_p2g_fcr(int n, const float *x, const float *v, const float *m, const flo
   }
 }
 
+/* EquationOfStateConfig branch of P2GTransfer, P2G.hpp:66-87 (weakly compressible fluid: J instead of F) */
+void zo_p2g_eos(int n, const float *x, const float *v, const float *m, const float *C, const float *Jp,
+                float dx, float dt, float bulk, float viscosity, float volume, int table_size,
+                const int *keys, const int *indices, float *grid) {
+  const float dx_inv = (float)1.0 / dx;
+  const float D_inv = 4.f * dx_inv * dx_inv;
+  for (int p = 0; p < n; ++p) {
+    float contrib[9];
+    const float *Cp = C + 9 * p, *vel = v + 3 * p;
+    const float mass = m[p];
+    float J = Jp[p];
+    float vol = volume * J;                      /* :68 */
+    float pressure = bulk;
+    {
+      float J2 = J * J;
+      float J4 = J2 * J2;
+      pressure = pressure * (1 / (J * J2 * J4) - 1); /* :74 */
+    }
+    contrib[0] = ((Cp[0] + Cp[0]) * viscosity - pressure) * vol;
+    contrib[1] = (Cp[1] + Cp[3]) * viscosity * vol;
+    contrib[2] = (Cp[2] + Cp[6]) * viscosity * vol;
+    contrib[3] = (Cp[3] + Cp[1]) * viscosity * vol;
+    contrib[4] = ((Cp[4] + Cp[4]) * viscosity - pressure) * vol;
+    contrib[5] = (Cp[5] + Cp[7]) * viscosity * vol;
+    contrib[6] = (Cp[6] + Cp[2]) * viscosity * vol;
+    contrib[7] = (Cp[7] + Cp[5]) * viscosity * vol;
+    contrib[8] = ((Cp[8] + Cp[8]) * viscosity - pressure) * vol;
+    for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;        /* :104 */
+    zo_arena ar;
+    arena_init(&ar, dx, x + 3 * p);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) {
+      int o[3] = {i, j, k}, loc[3], blk[3];
+      float xixp[3];
+      for (int d = 0; d < 3; ++d) {
+        blk[d] = floor_div4(ar.corner[d] + o[d], &loc[d]);
+        xixp[d] = (float)o[d] * ar.dx - ar.local[d];
+      }
+      float W = 1.f; W *= ar.w[0][i]; W *= ar.w[1][j]; W *= ar.w[2][k];
+      int bno = zo_table_query(blk, table_size, keys, indices);
+      float *tile = grid + (size_t)bno * 7 * 64;
+      int cell = (loc[0] << 4) | (loc[1] << 2) | loc[2];
+      tile[cell] += mass * W;
+      for (int d = 0; d < 3; ++d) {
+        tile[(1 + d) * 64 + cell] += W * mass * (vel[d] + (Cp[d] * xixp[0] + Cp[3 + d] * xixp[1] + Cp[6 + d] * xixp[2]));
+        tile[(4 + d) * 64 + cell] += (contrib[d] * xixp[0] + contrib[3 + d] * xixp[1] + contrib[6 + d] * xixp[2]) * W;
+      }
+    }
+  }
+}
+
 void zo_grid_update(int nblocks, float *grid, float dt, const float extf[3], int mode,
                     float *max_vel_sqr) {
   float mx = *max_vel_sqr;
@@ -426,6 +476,37 @@ void zo_g2p(int n, float *x, float *v, float *C, float *F, float dx, float dt, i
     for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) /* MatrixUtils.h:136-146, column-major a*b */
       Fn[3*c + r] = (tmp[r] * Fo[3*c] + tmp[3 + r] * Fo[3*c + 1]) + tmp[6 + r] * Fo[3*c + 2];
     memcpy(F + 9 * p, Fn, sizeof Fn);
+    memcpy(x + 3 * p, pos, sizeof pos);
+    memcpy(v + 3 * p, vel, sizeof vel);
+    memcpy(C + 9 * p, Cn, sizeof Cn);
+  }
+}
+
+/* EquationOfStateConfig branch of G2PTransfer, G2P.hpp:69-73: J <- (1 + tr(C) dt) J, F untouched */
+void zo_g2p_eos(int n, float *x, float *v, float *C, float *Jp, float dx, float dt, int table_size,
+                const int *keys, const int *indices, const float *grid) {
+  const float dx_inv = (float)1 / dx;
+  const float D_inv = 4.f * dx_inv * dx_inv;
+  for (int p = 0; p < n; ++p) {
+    float pos[3] = {x[3*p], x[3*p+1], x[3*p+2]}, vel[3] = {0, 0, 0}, Cn[9] = {0};
+    zo_arena ar;
+    arena_init(&ar, dx, pos);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) {
+      int o[3] = {i, j, k}, loc[3], blk[3];
+      float xixp[3], vi[3];
+      for (int d = 0; d < 3; ++d) {
+        blk[d] = floor_div4(ar.corner[d] + o[d], &loc[d]);
+        xixp[d] = (float)o[d] * ar.dx - ar.local[d];
+      }
+      float W = 1.f; W *= ar.w[0][i]; W *= ar.w[1][j]; W *= ar.w[2][k];
+      int bno = zo_table_query(blk, table_size, keys, indices);
+      const float *tile = grid + (size_t)bno * 7 * 64;
+      int cell = (loc[0] << 4) | (loc[1] << 2) | loc[2];
+      for (int d = 0; d < 3; ++d) { vi[d] = tile[(1 + d) * 64 + cell]; vel[d] += vi[d] * W; }
+      for (int d = 0; d < 9; ++d) Cn[d] += W * vi[d % 3] * xixp[d / 3] * D_inv;
+    }
+    for (int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
+    Jp[p] = (1 + (Cn[0] + Cn[4] + Cn[8]) * dt) * Jp[p];   /* :71 */
     memcpy(x + 3 * p, pos, sizeof pos);
     memcpy(v + 3 * p, vel, sizeof vel);
     memcpy(C + 9 * p, Cn, sizeof Cn);

@@ -112,6 +112,22 @@ class Oracle:
                             _ptr(tab["indices"]), _ptr(grid))
         return grid
 
+    def p2g_eos(self, P, tab, dx, dt, bulk, viscosity, volume, grid=None):
+        nb = tab["nblocks"]
+        if grid is None:
+            grid = np.zeros((nb, 7, 64), np.float32)
+        n = P["x"].shape[0]
+        self.lib.zo_p2g_eos(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["m"]), _ptr(P["C"]), _ptr(P["J"]),
+                            C.c_float(dx), C.c_float(dt), C.c_float(bulk), C.c_float(viscosity), C.c_float(volume),
+                            C.c_int(tab["table_size"]), _ptr(tab["keys"]), _ptr(tab["indices"]), _ptr(grid))
+        return grid
+
+    def g2p_eos(self, P, tab, grid, dx, dt):
+        n = P["x"].shape[0]
+        self.lib.zo_g2p_eos(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["C"]), _ptr(P["J"]), C.c_float(dx),
+                            C.c_float(dt), C.c_int(tab["table_size"]), _ptr(tab["keys"]), _ptr(tab["indices"]),
+                            _ptr(grid))
+
     def grid_update(self, grid, dt, extf, mode):
         e = np.ascontiguousarray(extf, np.float32)
         mx = np.zeros(1, np.float32)
@@ -246,6 +262,21 @@ class Ref:
 
         def g2p(self, dt):
             self.L.zpcref_mpm_g2p(self.h, C.c_float(dt))
+
+        def set_J(self, J):
+            self.L.zpcref_mpm_set_J(self.h, _ptr(np.ascontiguousarray(J, np.float32)))
+
+        def get_J(self):
+            J = np.empty(self.n, np.float32)
+            self.L.zpcref_mpm_get_J(self.h, _ptr(J))
+            return J
+
+        def p2g_eos(self, dt, bulk, gamma, viscosity, volume):
+            self.L.zpcref_mpm_p2g_eos(self.h, C.c_float(dt), C.c_float(bulk), C.c_float(gamma), C.c_float(viscosity),
+                                      C.c_float(volume))
+
+        def g2p_eos(self, dt):
+            self.L.zpcref_mpm_g2p_eos(self.h, C.c_float(dt))
 
         def grid(self):
             g = np.empty((self.nblocks, 7, 64), np.float32)

@@ -47,6 +47,7 @@ namespace {
       pars.addAttr("v", attrib_e::vector);
       pars.addAttr("F", attrib_e::matrix);
       pars.addAttr("C", attrib_e::matrix);
+      pars.addAttr("J", attrib_e::scalar);
     }
   };
 
@@ -151,6 +152,35 @@ float zpcref_mpm_get_maxvel(void *h) { return ((RefMpm *)h)->maxVel.getVal(); }
 void zpcref_mpm_g2p(void *h, float dt) {
   auto &s = *(RefMpm *)h;
   FixedCorotatedConfig model{};
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(range(s.n),
+        G2PTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.grids, s.table, s.pars});
+  });
+}
+/// EquationOfStateConfig variants (P2G.hpp:66-87, G2P.hpp:69-73)
+void zpcref_mpm_set_J(void *h, const float *J) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(s.pars.attrScalar("J").data(), J, sizeof(float) * s.n);
+}
+void zpcref_mpm_get_J(void *h, float *J) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(J, s.pars.attrScalar("J").data(), sizeof(float) * s.n);
+}
+void zpcref_mpm_p2g_eos(void *h, float dt, float bulk, float gamma, float viscosity, float volume) {
+  auto &s = *(RefMpm *)h;
+  EquationOfStateConfig model{};
+  model.bulk = bulk;
+  model.gamma = gamma;
+  model.viscosity = viscosity;
+  model.volume = volume;
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(range(s.n),
+        P2GTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.pars, s.table, s.grids});
+  });
+}
+void zpcref_mpm_g2p_eos(void *h, float dt) {
+  auto &s = *(RefMpm *)h;
+  EquationOfStateConfig model{};
   with_policy(s.nthreads, [&](auto &pol, auto tag) {
     pol(range(s.n),
         G2PTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.grids, s.table, s.pars});

@@ -84,3 +84,20 @@ def test_oracle_prims_match_golden(oracle):
         assert np.array_equal(oracle.scan("inclusive", "i32", a), z["inscan_i32_%d" % n])
         for op in ("sum", "min", "max"):
             assert oracle.reduce(op, "i32", a) == z["reduce_%s_i32_%d" % (op, n)][0]
+
+
+def test_oracle_eos_substep_matches_reference_golden(oracle):
+    """EquationOfStateConfig branch (weakly compressible fluid, per-particle J)."""
+    z, P = load_case("mpm_cube6_eos")
+    n, dx = P["x"].shape[0], P["dx"]
+    P["J"] = z["J_in"].copy()
+    tab = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    grid = oracle.p2g_eos(P, tab, dx, synth.DT, 4.0e4, 0.01, P["volume"])
+    assert np.array_equal(grid, z["grid_p2g"])
+    mx = oracle.grid_update(grid, synth.DT, (0.0, synth.GRAVITY, 0.0), 1)
+    assert mx == float(z["max_vel_sqr"])
+    F0 = P["F"].copy()
+    oracle.g2p_eos(P, tab, grid, dx, synth.DT)
+    for k in ("x", "v", "C", "J"):
+        assert np.array_equal(P[k], z[k]), k
+    assert np.array_equal(P["F"], F0)

@@ -292,3 +292,38 @@ def test_multi_gpu_substeps_match_single_gpu():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(root, "tests", "dist_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_eos_fluid_model_matches_oracle_and_golden(oracle):
+    """EquationOfStateConfig (P2G.hpp:66-87, G2P.hpp:69-73) on the AoS drop-in path: vs oracle on the GPU-built table
+    and vs the reference-generated golden vectors by block key."""
+    from zpc_b200 import api
+    z = np.load(os.path.join(G, "mpm_cube6_eos.npz"))
+    kw = dict(ast.literal_eval(str(z["kw"])))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **kw)
+    P["J"] = z["J_in"].copy()
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    model = api.model_eos(P["volume"], 4.0e4, 7.15, 0.01)
+    api.p2g_transfer(pars, table, grids, synth.DT, model)
+    g1 = grids.tiles.cpu().numpy()
+    o1 = oracle.p2g_eos(P, ht, dx, synth.DT, 4.0e4, 0.01, P["volume"])
+    check_channels(g1, o1, 1, "eos p2g", RTOL, strict_frac=0.99)          # no SVD on this path: 1e-5 on all 7 channels
+    kr, g1r = grid_by_key(z["active_keys"], z["grid_p2g"])
+    assert np.array_equal(ht["active_keys"], kr)
+    check_channels(g1, g1r, 1, "eos golden p2g", RTOL)
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    F0 = pars.F.clone()
+    api.g2p_transfer(pars, table, grids, synth.DT, model=model)
+    assert abs(mx.item() - float(z["max_vel_sqr"])) <= 1e-5 * float(z["max_vel_sqr"])
+    out = pars.to_host()
+    vmax = float(np.abs(z["v"]).max())
+    check_channels(out["x"], z["x"], 1, "eos x", RTOL, floor=float(np.abs(z["x"]).max()))
+    check_channels(out["v"], z["v"], 1, "eos v", RTOL, floor=vmax)
+    check_channels(out["C"], z["C"], 1, "eos C", RTOL, floor=4.0 / dx * vmax)
+    assert np.abs(pars.J.cpu().numpy() - z["J"]).max() <= 1e-5
+    assert torch.equal(pars.F, F0)                                        # F is not touched by the fluid model

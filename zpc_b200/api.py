@@ -54,6 +54,11 @@ class zpc_fixed_corotated(C.Structure):
     _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("E", C.c_float), ("nu", C.c_float)]
 
 
+class zpc_equation_of_state(C.Structure):
+    _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("bulk", C.c_float), ("gamma", C.c_float),
+                ("viscosity", C.c_float)]
+
+
 class zpc_bins_view(C.Structure):
     _fields_ = [("pars", zpc_tilevector_view), ("binStart", C.c_void_p), ("binKey", C.c_void_p),
                 ("numBins", C.c_void_p), ("binCapacity", C.c_int), ("cellOrder", C.c_void_p),
@@ -272,9 +277,11 @@ class Particles:
         self.m = torch.as_tensor(P["m"]).to(device).contiguous()
         self.C = torch.as_tensor(P["C"]).to(device).contiguous()
         self.F = torch.as_tensor(P["F"]).to(device).contiguous()
+        self.J = torch.as_tensor(P["J"]).to(device).contiguous() if "J" in P else None   # EquationOfStateConfig only
 
     def view(self):
-        return zpc_particles_view(self.m.data_ptr(), self.x.data_ptr(), self.v.data_ptr(), None, None,
+        return zpc_particles_view(self.m.data_ptr(), self.x.data_ptr(), self.v.data_ptr(), None,
+                                  self.J.data_ptr() if self.J is not None else None,
                                   self.F.data_ptr(), self.C.data_ptr(), None, self.n)
 
     def to_host(self):
@@ -350,7 +357,15 @@ def clean_grid_blocks(grids, table, stream=None):
            "clean_grid")
 
 
+def model_eos(volume, bulk=4.0e4, gamma=7.15, viscosity=0.0, rho=1000.0):
+    return zpc_equation_of_state(rho, volume, 3, bulk, gamma, viscosity)
+
+
 def p2g_transfer(pars, table, grids, dt, model, stream=None):
+    if isinstance(model, zpc_equation_of_state):
+        _check(lib().zpcb200_p2g_apic_eos(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
+                                          _stream_ptr(stream)), "p2g(eos)")
+        return
     if isinstance(pars, ParticleBins):
         rc = lib().zpcb200_p2g_apic_fcr_binned(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
                                                _stream_ptr(stream))
@@ -367,7 +382,11 @@ def compute_grid_block_velocity(grids, table, dt, extf, mode, max_vel_sqr, strea
            "grid_update")
 
 
-def g2p_transfer(pars, table, grids, dt, stream=None):
+def g2p_transfer(pars, table, grids, dt, stream=None, model=None):
+    if isinstance(model, zpc_equation_of_state):
+        _check(lib().zpcb200_g2p_apic_eos(pars.view(), table.view(), grids.view(), C.c_float(dt), _stream_ptr(stream)),
+               "g2p(eos)")
+        return
     if isinstance(pars, ParticleBins):
         rc = lib().zpcb200_g2p_apic_binned(pars.view(), table.view(), grids.view(), C.c_float(dt),
                                            _stream_ptr(stream))

@@ -183,6 +183,19 @@ __global__ void __launch_bounds__(128) p2g_aos_kernel(zpc_particles_view P, zpc_
   zpcp::p2g_scatter_particle(pos, vel, P.M[p], C, F, tb, tiles, nch, dx, dt, volume, mu, lam);
 }
 
+__global__ void __launch_bounds__(128) p2g_aos_eos_kernel(zpc_particles_view P, zpc_hashtable_view tb, float *tiles, int nch,
+                                                          float dx, float dt, float volume, float bulk, float viscosity) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.count) return;
+  float pos[3], vel[3], C[9];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { pos[d] = P.X[3 * p + d]; vel[d] = P.V[3 * p + d]; }
+#pragma unroll
+  for (int d = 0; d < 9; ++d) C[d] = P.C[9 * p + d];
+  zpcp::p2g_scatter_particle_eos(pos, vel, P.M[p], C, P.J[p], tb, tiles, nch, dx, dt, volume, bulk, viscosity);
+}
+
+template <bool EOS>
 __global__ void __launch_bounds__(128) g2p_aos_kernel(zpc_particles_view P, zpc_hashtable_view tb, const float *tiles,
                                                       int nch, float dx, float dt) {
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,13 +231,17 @@ __global__ void __launch_bounds__(128) g2p_aos_kernel(zpc_particles_view P, zpc_
       }
 #pragma unroll
   for (int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
-  float Fo[9], tmp[9];
+  if constexpr (EOS) {  // G2P.hpp:69-73
+    P.J[p] = (1 + (C[0] + C[4] + C[8]) * dt) * P.J[p];
+  } else {
+    float Fo[9], tmp[9];
 #pragma unroll
-  for (int d = 0; d < 9; ++d) { Fo[d] = P.F[9 * p + d]; tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f); }
+    for (int d = 0; d < 9; ++d) { Fo[d] = P.F[9 * p + d]; tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f); }
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int r = 0; r < 3; ++r) P.F[9 * p + 3 * c + r] = tmp[r] * Fo[3 * c] + tmp[3 + r] * Fo[3 * c + 1] + tmp[6 + r] * Fo[3 * c + 2];
+      for (int r = 0; r < 3; ++r) P.F[9 * p + 3 * c + r] = tmp[r] * Fo[3 * c] + tmp[3 + r] * Fo[3 * c + 1] + tmp[6 + r] * Fo[3 * c + 2];
+  }
 #pragma unroll
   for (int d = 0; d < 3; ++d) { P.X[3 * p + d] = pos[d]; P.V[3 * p + d] = vel[d]; }
 #pragma unroll
@@ -329,7 +346,27 @@ int zpcb200_g2p_apic(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view
   if (g.numChannels < 4 || !P.X || !P.V || !P.C || !P.F) return ZPCB200_E_BADARG;
   if (P.count == 0) return ZPCB200_OK;
   const unsigned grid = (unsigned)((P.count + 127) / 128);
-  g2p_aos_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tb, g.tiles, g.numChannels, g.dx, dt);
+  g2p_aos_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(P, tb, g.tiles, g.numChannels, g.dx, dt);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_p2g_apic_eos(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_equation_of_state model,
+                         zpc_stream_t stream) {
+  if (g.numChannels != 7 || !P.X || !P.V || !P.M || !P.C || !P.J) return ZPCB200_E_BADARG;
+  if (P.count == 0) return ZPCB200_OK;
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  p2g_aos_eos_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tb, g.tiles, g.numChannels, g.dx, dt, model.volume, model.bulk,
+                                                             model.viscosity);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_g2p_apic_eos(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
+  if (g.numChannels < 4 || !P.X || !P.V || !P.C || !P.J) return ZPCB200_E_BADARG;
+  if (P.count == 0) return ZPCB200_OK;
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  g2p_aos_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(P, tb, g.tiles, g.numChannels, g.dx, dt);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }

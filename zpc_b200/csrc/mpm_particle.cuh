@@ -21,14 +21,10 @@ __device__ __forceinline__ void resolve_blocks(const int (&corner)[3], const zpc
   }
 }
 
-static __device__ __noinline__ void p2g_scatter_particle(const float (&pos)[3], const float (&vel)[3], float mass, const float (&C)[9],
-                                                  const float (&F)[9], const zpc_hashtable_view &tb, float *tiles, int nch,
-                                                  float dx, float dt, float volume, float mu, float lam) {
-  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
-  float contrib[9];
-  zpcm::stress_fcr(volume, mu, lam, F, contrib);
-#pragma unroll
-  for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+// scatter of one particle given its (already scaled: * -dt * D_inv) stress contribution — P2G.hpp:104-125
+static __device__ __noinline__ void p2g_scatter_core(const float (&pos)[3], const float (&vel)[3], float mass, const float (&C)[9],
+                                                     const float (&contrib)[9], const zpc_hashtable_view &tb, float *tiles, int nch,
+                                                     float dx) {
   zpcm::Arena ar;
   zpcm::arena_init(ar, dx, pos);
   long long off[8];
@@ -54,6 +50,42 @@ static __device__ __noinline__ void p2g_scatter_particle(const float (&pos)[3], 
           atomicAdd(t + (4 + d) * 64, (contrib[d] * x0 + contrib[3 + d] * x1 + contrib[6 + d] * x2) * W);
         }
       }
+}
+
+// FixedCorotatedConfig (P2G.hpp:88-91)
+static __device__ __forceinline__ void p2g_scatter_particle(const float (&pos)[3], const float (&vel)[3], float mass, const float (&C)[9],
+                                                  const float (&F)[9], const zpc_hashtable_view &tb, float *tiles, int nch,
+                                                  float dx, float dt, float volume, float mu, float lam) {
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  float contrib[9];
+  zpcm::stress_fcr(volume, mu, lam, F, contrib);
+#pragma unroll
+  for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+  p2g_scatter_core(pos, vel, mass, C, contrib, tb, tiles, nch, dx);
+}
+
+// EquationOfStateConfig (P2G.hpp:66-87): weakly compressible fluid, J instead of F; gamma is fixed to 7 by the reference
+static __device__ __forceinline__ void p2g_scatter_particle_eos(const float (&pos)[3], const float (&vel)[3], float mass,
+                                                                const float (&C)[9], float J, const zpc_hashtable_view &tb,
+                                                                float *tiles, int nch, float dx, float dt, float volume, float bulk,
+                                                                float viscosity) {
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  const float vol = volume * J;
+  const float J2 = J * J, J4 = J2 * J2;
+  const float pressure = bulk * (1.f / (J * J2 * J4) - 1.f);
+  float contrib[9];
+  contrib[0] = ((C[0] + C[0]) * viscosity - pressure) * vol;
+  contrib[1] = (C[1] + C[3]) * viscosity * vol;
+  contrib[2] = (C[2] + C[6]) * viscosity * vol;
+  contrib[3] = (C[3] + C[1]) * viscosity * vol;
+  contrib[4] = ((C[4] + C[4]) * viscosity - pressure) * vol;
+  contrib[5] = (C[5] + C[7]) * viscosity * vol;
+  contrib[6] = (C[6] + C[2]) * viscosity * vol;
+  contrib[7] = (C[7] + C[5]) * viscosity * vol;
+  contrib[8] = ((C[8] + C[8]) * viscosity - pressure) * vol;
+#pragma unroll
+  for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+  p2g_scatter_core(pos, vel, mass, C, contrib, tb, tiles, nch, dx);
 }
 
 // vel = sum W v_i ; G[r + 3e] = sum W v_i[r] * o_e   (o = stencil offset 0..2), so that
