@@ -131,6 +131,16 @@ typedef struct zpc_equation_of_state {
   float bulk, gamma, viscosity;
 } zpc_equation_of_state;
 
+/* A static analytic Collider — geometry/Collider.h:10-127 with its default rigid motion (R = I, s = 1, b = 0, no
+ * velocity) over AnalyticLevelSet<Plane> / <Sphere> (geometry/AnalyticLevelSet.h:11-43, 130-157). */
+enum { ZPC_GEOM_PLANE = 0, ZPC_GEOM_SPHERE = 1 };
+enum { ZPC_COLLIDER_STICKY = 0, ZPC_COLLIDER_SLIP = 1, ZPC_COLLIDER_SEPARATE = 2 }; /* collider_e, Collider.h:8 */
+typedef struct zpc_collider {
+  int geometry, type;
+  float origin[3]; /* plane origin | sphere centre */
+  float normal[3]; /* plane unit normal | {radius, -, -} */
+} zpc_collider;
+
 /* ------------------------------------------------------------------------------------------ */
 /* MPM path                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
@@ -159,6 +169,11 @@ int zpcb200_p2g_apic_fcr(zpc_particles_view pars, zpc_hashtable_view table, zpc_
  * mode 0 = as shipped (rhs ignored); mode 1 = explicit update v = (mv + rhs)/m + extf*dt. */
 int zpcb200_grid_update(zpc_grids_view grids, const int *cnt, float dt, const float extf_host[3],
                         int mode, float *maxVelSqr, zpc_stream_t stream);
+
+/* ApplyBoundaryConditionOnGridBlocks (GridOp.hpp:112-164): for every cell with mass > 0 of blocks [0, *cnt), project
+ * the grid velocity (channels 1-3) against the collider; node position = (blockkey*4 + cell coord) * dx. */
+int zpcb200_apply_boundary(zpc_grids_view grids, zpc_hashtable_view table, zpc_collider collider,
+                           zpc_stream_t stream);
 
 /* G2PTransfer<apic> (simulation/transfer/G2P.hpp:43-84), AoS layout, any order. */
 int zpcb200_g2p_apic(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,

@@ -512,3 +512,47 @@ void zo_g2p_eos(int n, float *x, float *v, float *C, float *Jp, float dx, float 
     memcpy(C + 9 * p, Cn, sizeof Cn);
   }
 }
+
+/* ApplyBoundaryConditionOnGridBlocks (GridOp.hpp:112-164) with a STATIC analytic collider (Collider.h:98-127 with the
+ * default R = I, s = 1, b = dbdt = omega = 0, so v_object = 0): geom 0 = Plane{origin p0, normal p1}
+ * (AnalyticLevelSet.h:11-43), geom 1 = Sphere{centre p0, radius p1[0]} (:130-157); type = collider_e
+ * {0 Sticky, 1 Slip, 2 Separate} (Collider.h:8). */
+void zo_apply_boundary(int nblocks, const int *active_keys, float *grid, float dx, int geom, int type,
+                       const float p0[3], const float p1[3]) {
+  for (int b = 0; b < nblocks; ++b) {
+    float *tile = grid + (size_t)b * 7 * 64;
+    for (int c = 0; c < 64; ++c) {
+      if (!(tile[c] > 0)) continue;                                    /* GridOp.hpp:141 */
+      const int cc[3] = {(c >> 4) & 3, (c >> 2) & 3, c & 3};           /* cellid_to_coord, Structure.hpp:836-847 */
+      float pos[3], vel[3], n[3], d[3];
+      for (int k = 0; k < 3; ++k) {
+        pos[k] = ((float)active_keys[3 * b + k] * 4.f + (float)cc[k]) * dx;   /* :143-144 */
+        vel[k] = tile[(1 + k) * 64 + c];
+        d[k] = pos[k] - p0[k];
+      }
+      float dist;
+      if (geom == 0) {
+        dist = 0.f;
+        for (int k = 0; k < 3; ++k) dist += p1[k] * d[k];              /* _normal.dot(x - _origin) */
+        for (int k = 0; k < 3; ++k) n[k] = p1[k];
+      } else {
+        float l2 = 0.f;
+        for (int k = 0; k < 3; ++k) l2 += d[k] * d[k];
+        const float len = sqrtf(l2);
+        dist = len - p1[0];
+        for (int k = 0; k < 3; ++k) n[k] = l2 < 1e-7f ? 0.f : d[k] / len;   /* :148-152 */
+      }
+      if (dist < 0.f) {                                                 /* Collider.h:110 (erosion 0) */
+        if (type == 0) {
+          vel[0] = vel[1] = vel[2] = 0.f;                               /* Sticky: v = v_object = 0 */
+        } else {
+          float proj = 0.f;
+          for (int k = 0; k < 3; ++k) proj += n[k] * vel[k];
+          if ((type == 2 && proj < 0.f) || type == 1)
+            for (int k = 0; k < 3; ++k) vel[k] -= proj * n[k];
+        }
+      }
+      for (int k = 0; k < 3; ++k) tile[(1 + k) * 64 + c] = vel[k];      /* block.set(1, cellid, vel) */
+    }
+  }
+}

@@ -135,6 +135,12 @@ class Oracle:
                                 C.c_int(mode), _ptr(mx))
         return float(mx[0])
 
+    def apply_boundary(self, grid, active_keys, dx, geom, ctype, p0, p1):
+        k = np.ascontiguousarray(active_keys, np.int32)
+        a = np.ascontiguousarray(p0, np.float32); b = np.ascontiguousarray(p1, np.float32)
+        self.lib.zo_apply_boundary(C.c_int(grid.shape[0]), _ptr(k), _ptr(grid), C.c_float(dx), C.c_int(geom),
+                                   C.c_int(ctype), _ptr(a), _ptr(b))
+
     def g2p(self, P, tab, grid, dx, dt):
         n = P["x"].shape[0]
         self.lib.zo_g2p(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["C"]), _ptr(P["F"]),
@@ -262,6 +268,10 @@ class Ref:
 
         def g2p(self, dt):
             self.L.zpcref_mpm_g2p(self.h, C.c_float(dt))
+
+        def apply_boundary(self, geom, ctype, p0, p1):
+            a = np.ascontiguousarray(p0, np.float32); b = np.ascontiguousarray(p1, np.float32)
+            self.L.zpcref_mpm_apply_boundary(self.h, C.c_int(geom), C.c_int(ctype), _ptr(a), _ptr(b))
 
         def set_J(self, J):
             self.L.zpcref_mpm_set_J(self.h, _ptr(np.ascontiguousarray(J, np.float32)))

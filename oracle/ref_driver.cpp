@@ -13,6 +13,8 @@
 #include "zensim/container/HashTable.hpp"
 #include "zensim/container/Vector.hpp"
 #include "zensim/execution/ExecutionPolicy.hpp"
+#include "zensim/geometry/AnalyticLevelSet.h"
+#include "zensim/geometry/Collider.h"
 #include "zensim/geometry/SparseLevelSet.hpp"
 #include "zensim/geometry/Structure.hpp"
 #include "zensim/geometry/Structurefree.hpp"
@@ -184,6 +186,21 @@ void zpcref_mpm_g2p_eos(void *h, float dt) {
   with_policy(s.nthreads, [&](auto &pol, auto tag) {
     pol(range(s.n),
         G2PTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.grids, s.table, s.pars});
+  });
+}
+/// ApplyBoundaryConditionOnGridBlocks with a static analytic collider (GridOp.hpp:112-164)
+void zpcref_mpm_apply_boundary(void *h, int geom, int type, const float *p0, const float *p1) {
+  auto &s = *(RefMpm *)h;
+  const auto ct = type == 0 ? collider_e::Sticky : (type == 1 ? collider_e::Slip : collider_e::Separate);
+  using TV = vec<float, 3>;
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    if (geom == 0) {
+      Collider col{AnalyticLevelSet<analytic_geometry_e::Plane, float, 3>{TV{p0[0], p0[1], p0[2]}, TV{p1[0], p1[1], p1[2]}}, ct};
+      pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
+    } else {
+      Collider col{AnalyticLevelSet<analytic_geometry_e::Sphere, float, 3>{TV{p0[0], p0[1], p0[2]}, p1[0]}, ct};
+      pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
+    }
   });
 }
 /// grid tiles in table numbering: out[nblocks][7][64]

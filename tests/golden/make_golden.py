@@ -36,6 +36,32 @@ def mpm_case(ref, name, s, G, mode, **kw):
     print(name, "n", n, "blocks", nb, "maxvel2", mx)
 
 
+BOUNDARY_CASES = [(0, 0, (0.0, 0.33, 0.0), (0.0, 1.0, 0.0)), (0, 1, (0.3, 0.3, 0.3), (0.6, 0.8, 0.0)),
+                  (0, 2, (0.0, 0.33, 0.0), (0.0, 1.0, 0.0)), (1, 0, (0.33, 0.3, 0.33), (0.08, 0.0, 0.0)),
+                  (1, 1, (0.33, 0.3, 0.33), (0.08, 0.0, 0.0)), (1, 2, (0.33, 0.3, 0.33), (0.08, 0.0, 0.0))]
+
+
+def boundary_case(ref, name, s, G, **kw):
+    """ApplyBoundaryConditionOnGridBlocks after P2G + update, every (geometry, collider type) of BOUNDARY_CASES"""
+    P = synth.elastic_cube(s, G, **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    out = {}
+    for i, (geom, ctype, p0, p1) in enumerate(BOUNDARY_CASES):
+        h = ref.mpm(n, dx, 0)
+        h.set_particles(P)
+        h.partition()
+        tab = h.table()
+        h.clean_grid()
+        h.p2g(synth.DT, synth.MODEL["E"], synth.MODEL["nu"], P["volume"])
+        h.grid_update(synth.DT, synth.GRAVITY, 1)
+        h.apply_boundary(geom, ctype, p0, p1)
+        out["grid_%d" % i] = h.grid()
+        out["active_keys"] = tab["active_keys"]
+        h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), s=s, G=G, kw=repr(sorted(kw.items())), **out)
+    print(name, "n", n, len(BOUNDARY_CASES), "colliders")
+
+
 def eos_case(ref, name, s, G, **kw):
     """EquationOfStateConfig{bulk=4e4, gamma=7.15, viscosity=0.01} substep (P2G.hpp:66-87, G2P.hpp:69-73)"""
     P = synth.elastic_cube(s, G, **kw)
@@ -112,6 +138,7 @@ if __name__ == "__main__":
     mpm_case(r, "mpm_cube8_rest", 8, 32, 1)
     mpm_case(r, "mpm_cube5_neg", 5, 16, 1, jitter_F=0.02, jitter_C=0.2, origin_cells=-9)
     eos_case(r, "mpm_cube6_eos", 6, 32, jitter_C=0.5, shuffle_seed=13)
+    boundary_case(r, "mpm_cube7_boundary", 7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
     if "--all" in sys.argv:   # the primitive / SVD vectors use unseeded-order-independent inputs: regenerate on demand
         prims_case(r)
         svd_case(r)

@@ -101,3 +101,19 @@ def test_oracle_eos_substep_matches_reference_golden(oracle):
     for k in ("x", "v", "C", "J"):
         assert np.array_equal(P[k], z[k]), k
     assert np.array_equal(P["F"], F0)
+
+
+def test_oracle_boundary_conditions_match_reference_golden(oracle):
+    """ApplyBoundaryConditionOnGridBlocks with static plane / sphere colliders, sticky / slip / separate."""
+    from tests.golden.make_golden import BOUNDARY_CASES
+    z, P = load_case("mpm_cube7_boundary")
+    n, dx = P["x"].shape[0], P["dx"]
+    tab = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    assert np.array_equal(tab["active_keys"], z["active_keys"])
+    g0 = oracle.p2g(P, tab, dx, synth.DT, synth.MODEL["E"], synth.MODEL["nu"], P["volume"])
+    oracle.grid_update(g0, synth.DT, (0.0, synth.GRAVITY, 0.0), 1)
+    for i, (geom, ctype, p0, p1) in enumerate(BOUNDARY_CASES):
+        g = g0.copy()
+        oracle.apply_boundary(g, tab["active_keys"], dx, geom, ctype, p0, p1)
+        assert np.array_equal(g, z["grid_%d" % i]), (geom, ctype)
+        assert (g != g0).any()          # the collider actually bites in every case

@@ -327,3 +327,36 @@ def test_eos_fluid_model_matches_oracle_and_golden(oracle):
     check_channels(out["C"], z["C"], 1, "eos C", RTOL, floor=4.0 / dx * vmax)
     assert np.abs(pars.J.cpu().numpy() - z["J"]).max() <= 1e-5
     assert torch.equal(pars.F, F0)                                        # F is not touched by the fluid model
+
+
+def test_boundary_conditions_match_oracle_and_golden(oracle):
+    """ApplyBoundaryConditionOnGridBlocks (GridOp.hpp:112-164): static plane / sphere x sticky / slip / separate.
+    The inside/outside decision is exact arithmetic on node positions, so the SAME cells must change; values 1e-5."""
+    from tests.golden.make_golden import BOUNDARY_CASES
+    from zpc_b200 import api
+    z = np.load(os.path.join(G, "mpm_cube7_boundary.npz"))
+    kw = dict(ast.literal_eval(str(z["kw"])))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    kr, _ = grid_by_key(z["active_keys"], z["grid_0"])
+    assert np.array_equal(ht["active_keys"], kr)
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(pars, table, grids, synth.DT, api.model_fcr(P["volume"], E, NU))
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    base = grids.tiles.clone()
+    for i, (geom, ctype, p0, p1) in enumerate(BOUNDARY_CASES):
+        grids.tiles.copy_(base)
+        col = api.plane_collider(p0, p1, ctype) if geom == 0 else api.sphere_collider(p0, p1[0], ctype)
+        api.apply_boundary_condition(col, table, grids)
+        got = grids.tiles.cpu().numpy()
+        want = base.cpu().numpy()
+        oracle.apply_boundary(want, ht["active_keys"], dx, geom, ctype, p0, p1)      # oracle on the GPU's own pre-state
+        assert np.array_equal(got[:, [0, 4, 5, 6]], want[:, [0, 4, 5, 6]])          # m and rhs untouched
+        check_channels(got[:, 1:4], want[:, 1:4], 1, "boundary %d/%d" % (geom, ctype))
+        assert np.array_equal((got != base.cpu().numpy()).any(axis=1), (want != base.cpu().numpy()).any(axis=1))
+        _, gold = grid_by_key(z["active_keys"], z["grid_%d" % i])
+        check_channels(got[:, 1:4], gold[:, 1:4], 1, "boundary golden %d/%d" % (geom, ctype))

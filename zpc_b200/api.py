@@ -59,6 +59,10 @@ class zpc_equation_of_state(C.Structure):
                 ("viscosity", C.c_float)]
 
 
+class zpc_collider(C.Structure):
+    _fields_ = [("geometry", C.c_int), ("type", C.c_int), ("origin", C.c_float * 3), ("normal", C.c_float * 3)]
+
+
 class zpc_bins_view(C.Structure):
     _fields_ = [("pars", zpc_tilevector_view), ("binStart", C.c_void_p), ("binKey", C.c_void_p),
                 ("numBins", C.c_void_p), ("binCapacity", C.c_int), ("cellOrder", C.c_void_p),
@@ -380,6 +384,23 @@ def compute_grid_block_velocity(grids, table, dt, extf, mode, max_vel_sqr, strea
     _check(lib().zpcb200_grid_update(grids.view(), C.c_void_p(table.cnt.data_ptr()), C.c_float(dt), e,
                                      C.c_int(mode), C.c_void_p(max_vel_sqr.data_ptr()), _stream_ptr(stream)),
            "grid_update")
+
+
+GEOM_PLANE, GEOM_SPHERE = 0, 1
+COLLIDER_STICKY, COLLIDER_SLIP, COLLIDER_SEPARATE = 0, 1, 2
+
+
+def plane_collider(origin, normal, ctype=COLLIDER_STICKY):
+    return zpc_collider(GEOM_PLANE, ctype, (C.c_float * 3)(*origin), (C.c_float * 3)(*normal))
+
+
+def sphere_collider(center, radius, ctype=COLLIDER_STICKY):
+    return zpc_collider(GEOM_SPHERE, ctype, (C.c_float * 3)(*center), (C.c_float * 3)(radius, 0.0, 0.0))
+
+
+def apply_boundary_condition(collider, table, grids, stream=None):
+    """ApplyBoundaryConditionOnGridBlocks{cuda_c, collider, table, grids} (GridOp.hpp:112-164)."""
+    _check(lib().zpcb200_apply_boundary(grids.view(), table.view(), collider, _stream_ptr(stream)), "apply_boundary")
 
 
 def g2p_transfer(pars, table, grids, dt, stream=None, model=None):

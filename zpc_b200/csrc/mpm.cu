@@ -170,6 +170,43 @@ __global__ void __launch_bounds__(256) grid_update_kernel(float *tiles, const in
   }
 }
 
+// ApplyBoundaryConditionOnGridBlocks with a static analytic collider: one thread per (block, cell)
+__global__ void __launch_bounds__(256) apply_boundary_kernel(float *tiles, const int *__restrict__ active_keys, const int *cnt,
+                                                             int nch, size_t cap_blocks, float dx, zpc_collider col) {
+  size_t nb = (size_t)*cnt;
+  if (nb > cap_blocks) nb = cap_blocks;
+  const int cell = threadIdx.x & 63;
+  const int cx = (cell >> 4) & 3, cy = (cell >> 2) & 3, cz = cell & 3;
+  for (size_t b = (size_t)blockIdx.x * 4 + (threadIdx.x >> 6); b < nb; b += (size_t)gridDim.x * 4) {
+    float *t = tiles + b * (size_t)nch * 64;
+    if (!(t[cell] > 0.f)) continue;
+    const float px = ((float)active_keys[3 * b] * 4.f + (float)cx) * dx, py = ((float)active_keys[3 * b + 1] * 4.f + (float)cy) * dx,
+                pz = ((float)active_keys[3 * b + 2] * 4.f + (float)cz) * dx;
+    const float d0 = px - col.origin[0], d1 = py - col.origin[1], d2 = pz - col.origin[2];
+    float n0, n1, n2, dist;
+    if (col.geometry == ZPC_GEOM_PLANE) {
+      n0 = col.normal[0]; n1 = col.normal[1]; n2 = col.normal[2];
+      dist = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));  // no contraction: the sign decides
+    } else {
+      const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+      const float len = sqrtf(l2);
+      dist = len - col.normal[0];
+      const bool tiny = l2 < 1e-7f;
+      n0 = tiny ? 0.f : d0 / len; n1 = tiny ? 0.f : d1 / len; n2 = tiny ? 0.f : d2 / len;
+    }
+    if (dist < 0.f) {
+      float vx = t[64 + cell], vy = t[128 + cell], vz = t[192 + cell];
+      if (col.type == ZPC_COLLIDER_STICKY) {
+        vx = vy = vz = 0.f;
+      } else {
+        const float proj = n0 * vx + n1 * vy + n2 * vz;
+        if (col.type == ZPC_COLLIDER_SLIP || proj < 0.f) { vx -= proj * n0; vy -= proj * n1; vz -= proj * n2; }
+      }
+      t[64 + cell] = vx; t[128 + cell] = vy; t[192 + cell] = vz;
+    }
+  }
+}
+
 // ---- P2G / G2P on AoS particles, any order -----------------------------------------------------------------
 __global__ void __launch_bounds__(128) p2g_aos_kernel(zpc_particles_view P, zpc_hashtable_view tb, float *tiles, int nch,
                                                       float dx, float dt, float volume, float mu, float lam) {
@@ -326,6 +363,15 @@ int zpcb200_grid_update(zpc_grids_view g, const int *cnt, float dt, const float 
   if (!g.tiles || !cnt || !maxVelSqr || g.numChannels < (mode == 1 ? 7 : 4)) return ZPCB200_E_BADARG;
   grid_update_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, cnt, g.numChannels, g.numBlocks, dt, extf[0],
                                                                         extf[1], extf[2], mode, maxVelSqr);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_apply_boundary(zpc_grids_view g, zpc_hashtable_view tb, zpc_collider col, zpc_stream_t stream) {
+  if (!g.tiles || !tb.activeKeys || !tb.cnt || g.numChannels < 4 || (unsigned)col.geometry > 1u || (unsigned)col.type > 2u)
+    return ZPCB200_E_BADARG;
+  apply_boundary_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks,
+                                                                           g.dx, col);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }
