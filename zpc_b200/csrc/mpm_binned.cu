@@ -64,7 +64,7 @@ struct LaneCoef {
   float ax, bx, cx, ay, by, cy, az, bz, cz, fx, fy, fz;
 };
 __device__ __forceinline__ void sweep_cell(const float (*rec)[REC_F], int lo, int hi, const LaneCoef &L, float (&acc)[7]) {
-#pragma unroll 2
+#pragma unroll 1
   for (int p = lo; p < hi; ++p) {
     const float4 *rp = reinterpret_cast<const float4 *>(rec[p]);
     const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3], r4 = rp[4], r5 = rp[5], r6 = rp[6];

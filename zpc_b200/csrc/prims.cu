@@ -157,7 +157,7 @@ int reduce_impl(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_
 // scan: single-pass decoupled look-back
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_NT = 256;
-constexpr int SCAN_VPT = 4;                           // 16-byte vectors per thread (4-byte T: 16 items)
+constexpr int SCAN_VPT = 16;                           // 16-byte vectors per thread (4-byte T: 16 items)
 enum : uint32_t { FLAG_EMPTY = 0, FLAG_AGG = 1, FLAG_INCL = 2 };
 
 // tile descriptor: one word holding {flag, value}
