@@ -196,6 +196,27 @@ def test_binned_multistep_with_strays_matches_oracle(oracle):
     check_particles(a, b, dx, "multistep (7 substeps)", rtol=5e-5)   # rounding differences compound over substeps
 
 
+def test_partition_with_rebin_equals_partition_every_step():
+    """partition="with_rebin" (one extra ring, rebuilt only at re-bin time) must give the same particles as rebuilding
+    the reference's EnlargeSparsity{0,2} partition every substep: the extra blocks stay empty."""
+    from zpc_b200.solver import MpmSolver
+    P = synth.elastic_cube(10, 32, jitter_F=0.03, jitter_C=0.3, seed=9)
+    P["v"][:] = P["v"] * 6.0
+    n0 = P["m"].shape[0]
+    P["m"] = (P["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)
+    res = []
+    for mode in ("every_step", "with_rebin"):
+        sol = MpmSolver(P, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, layout="binned", rebin_every=3, partition=mode)
+        for _ in range(6):
+            sol.substep()
+        torch.cuda.synchronize()
+        Q = sol.particles_host()
+        o = np.argsort(Q["m"], kind="stable")
+        res.append({k: Q[k][o] for k in "xvCF"})
+        assert sol.table.overflow.item() == 0
+    check_particles(res[0], res[1], P["dx"], "with_rebin vs every_step", rtol=1e-5)
+
+
 def test_aos_multistep_matches_oracle(oracle):
     from zpc_b200.solver import MpmSolver
     P = synth.elastic_cube(8, 32, jitter_F=0.03, jitter_C=0.3, seed=6, shuffle_seed=2)
@@ -360,3 +381,124 @@ def test_boundary_conditions_match_oracle_and_golden(oracle):
         assert np.array_equal((got != base.cpu().numpy()).any(axis=1), (want != base.cpu().numpy()).any(axis=1))
         _, gold = grid_by_key(z["active_keys"], z["grid_%d" % i])
         check_channels(got[:, 1:4], gold[:, 1:4], 1, "boundary golden %d/%d" % (geom, ctype))
+
+
+# ---- edge cases (ragged / empty / degenerate inputs) ---------------------------------------------------------------
+def _single_particle(pos=(0.3, 0.3, 0.3), G=32):
+    dx = 1.0 / G
+    vol = dx ** 3 / 8
+    return dict(x=np.array([pos], np.float32), v=np.array([[0.5, -1.0, 0.25]], np.float32), m=np.array([1000 * vol], np.float32),
+                C=np.zeros((1, 9), np.float32), F=np.eye(3, dtype=np.float32).reshape(1, 9).copy(), dx=dx, volume=vol)
+
+
+def test_empty_particle_set_is_a_noop():
+    from zpc_b200 import api
+    P = _single_particle()
+    for k in ("x", "v", "m", "C", "F"):
+        P[k] = P[k][:0].copy()
+    pars = api.Particles(P)
+    table = api.HashTable(64)
+    api.partition_for_particles(api.zpc_port(pars.x.data_ptr(), 0, 0, 0, 3), 0, P["dx"], table)
+    assert table.size() == 0
+    grids = api.Grids(P["dx"], 8)
+    grids.tiles.fill_(7.0)
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(pars, table, grids, synth.DT, api.model_fcr(P["volume"]))
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    api.g2p_transfer(pars, table, grids, synth.DT)
+    bins = api.ParticleBins(0, 16)
+    api.bin_particles(pars, table, P["dx"], bins)
+    api.p2g_transfer(bins, table, grids, synth.DT, api.model_fcr(P["volume"]))
+    api.g2p_transfer(bins, table, grids, synth.DT)
+    torch.cuda.synchronize()
+    assert bins.num_bins.item() == 0 and mx.item() == 0.0 and float(grids.tiles.min()) == 7.0   # nothing was touched
+
+
+@pytest.mark.parametrize("pos", [(0.3, 0.3, 0.3), (-0.41, 0.02, -0.77), (0.5 - 1e-7, 0.25, 0.125)])
+def test_single_particle_both_layouts(oracle, pos):
+    """one particle: 8 blocks, 27 nodes; negative coordinates and a position sitting on a cell boundary"""
+    from zpc_b200 import api
+    P = _single_particle(pos)
+    dx = P["dx"]
+    pars, table = build_partition(P, expected=64)
+    ht = host_table(table)
+    tab_o = oracle.partition_build(P["x"], dx, oracle.table_size_for(64))
+    assert ht["nblocks"] == tab_o["nblocks"] == 8
+    model = api.model_fcr(P["volume"], E, NU)
+    o1, o2, omx, Po = run_oracle_on_table(oracle, P, ht, 1)
+    for layout in ("aos", "binned"):
+        src = pars if layout == "aos" else api.ParticleBins(1, 64)
+        if layout == "binned":
+            api.bin_particles(api.Particles(P), table, dx, src)
+        else:
+            src = api.Particles(P)
+        grids = api.Grids(dx, 8)
+        api.clean_grid_blocks(grids, table)
+        api.p2g_transfer(src, table, grids, synth.DT, model)
+        g = grids.tiles.cpu().numpy()
+        check_channels(g, o1, 1, layout + " single p2g", GRID_RTOL)
+        assert (g[:, 0] > 0).sum() <= 27 and abs(g[:, 0].sum() / P["m"][0] - 1) < 1e-6
+        mx = torch.zeros(1, device="cuda")
+        api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+        api.g2p_transfer(src, table, grids, synth.DT)
+        out = {k: src.attr(k).cpu().numpy() for k in "xvCF"} if layout == "binned" else src.to_host()
+        check_particles(out, Po, dx, layout + " single g2p")
+
+
+def test_dense_cluster_splits_bins_and_groups(oracle):
+    """3 000 particles inside ONE cell: the home block exceeds ZPCB200_BIN_MAX (3 bins), every bin has a single
+    1 000-particle cell group spanning several record chunks; compared with the oracle."""
+    from zpc_b200 import api
+    G_, n = 32, 3000
+    dx = 1.0 / G_
+    rs = np.random.RandomState(5)
+    vol = dx ** 3 / 8
+    P = dict(x=((np.array([9.0, 9.0, 9.0]) + rs.uniform(0.02, 0.98, (n, 3))) * dx).astype(np.float32),
+             v=rs.uniform(-1, 1, (n, 3)).astype(np.float32), m=np.full(n, 1000 * vol / 300, np.float32),
+             C=rs.uniform(-0.5, 0.5, (n, 9)).astype(np.float32),
+             F=(np.eye(3).reshape(1, 9) + rs.uniform(-0.03, 0.03, (n, 9))).astype(np.float32), dx=dx, volume=vol / 300)
+    pars, table = build_partition(P, expected=64)
+    ht = host_table(table)
+    bins = api.ParticleBins(n, 64)
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    api.bin_particles(pars, table, dx, bins, order)
+    perm = order.cpu().numpy()
+    nb = bins.num_bins.item()
+    bs = bins.bin_start[: nb + 1].cpu().numpy()
+    assert nb >= 3 and (np.diff(bs) <= api.BIN_MAX).all() and bs[-1] == n
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    model = api.model_fcr(P["volume"], E, NU)
+    api.p2g_transfer(bins, table, grids, synth.DT, model)
+    o1, o2, omx, Po = run_oracle_on_table(oracle, P, ht, 1)
+    check_channels(grids.tiles.cpu().numpy(), o1, 1, "cluster p2g", GRID_RTOL)
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    api.g2p_transfer(bins, table, grids, synth.DT)
+    check_particles({k: bins.attr(k).cpu().numpy() for k in "xvCF"}, {k: Po[k][perm] for k in "xvCF"}, dx, "cluster g2p")
+    # second substep on the cached cell order (all particles still in one bin group each)
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(bins, table, grids, synth.DT, model)
+    P2 = {k: (np.ascontiguousarray(Po[k]) if isinstance(Po[k], np.ndarray) else Po[k]) for k in Po}
+    o1b = oracle.p2g(P2, ht, dx, synth.DT, E, NU, P["volume"])
+    check_channels(grids.tiles.cpu().numpy(), o1b, 1, "cluster p2g (cached order)", [3e-5] * 4 + [1e-4] * 3)
+
+
+def test_overflow_flags_are_raised_not_thrown():
+    """too small a table / too few bins: device flags, no exception, no out-of-bounds write (reference convention)"""
+    from zpc_b200 import api
+    P = make("cube8")
+    n, dx = P["x"].shape[0], P["dx"]
+    pars = api.Particles(P)
+    table = api.HashTable(2)                      # 32 slots, list capacity 64 < 125 blocks... force the flag
+    api.partition_for_particles(api.vec3_port(pars.x), n, dx, table)
+    torch.cuda.synchronize()
+    assert table.overflow.item() == 1
+    # domain beyond the packed block-code range (|block| >= 512)
+    far = dict(P)
+    far["x"] = (P["x"] + np.float32(100.0)).astype(np.float32)
+    t2 = api.HashTable(max(n // 8, 64))
+    api.partition_for_particles(api.vec3_port(api.Particles(far).x), n, dx, t2)
+    torch.cuda.synchronize()
+    assert t2.overflow.item() == 1

@@ -378,8 +378,8 @@ int zpcb200_apply_boundary(zpc_grids_view g, zpc_hashtable_view tb, zpc_collider
 
 int zpcb200_p2g_apic_fcr(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_fixed_corotated model,
                          zpc_stream_t stream) {
+  if (P.count == 0) return ZPCB200_OK;  // empty range: nothing to launch (pointers of an empty container may be null)
   if (g.numChannels != 7 || !P.X || !P.V || !P.M || !P.C || !P.F) return ZPCB200_E_BADARG;
-  if (P.count == 0) return ZPCB200_OK;
   float mu, lam;
   zpcm::lame_host(model.E, model.nu, mu, lam);
   const unsigned grid = (unsigned)((P.count + 127) / 128);
@@ -389,8 +389,8 @@ int zpcb200_p2g_apic_fcr(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_
 }
 
 int zpcb200_g2p_apic(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
-  if (g.numChannels < 4 || !P.X || !P.V || !P.C || !P.F) return ZPCB200_E_BADARG;
   if (P.count == 0) return ZPCB200_OK;
+  if (g.numChannels < 4 || !P.X || !P.V || !P.C || !P.F) return ZPCB200_E_BADARG;
   const unsigned grid = (unsigned)((P.count + 127) / 128);
   g2p_aos_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(P, tb, g.tiles, g.numChannels, g.dx, dt);
   ZPC_CHECK_LAUNCH();
@@ -399,8 +399,8 @@ int zpcb200_g2p_apic(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view
 
 int zpcb200_p2g_apic_eos(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_equation_of_state model,
                          zpc_stream_t stream) {
-  if (g.numChannels != 7 || !P.X || !P.V || !P.M || !P.C || !P.J) return ZPCB200_E_BADARG;
   if (P.count == 0) return ZPCB200_OK;
+  if (g.numChannels != 7 || !P.X || !P.V || !P.M || !P.C || !P.J) return ZPCB200_E_BADARG;
   const unsigned grid = (unsigned)((P.count + 127) / 128);
   p2g_aos_eos_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, tb, g.tiles, g.numChannels, g.dx, dt, model.volume, model.bulk,
                                                              model.viscosity);
@@ -409,8 +409,8 @@ int zpcb200_p2g_apic_eos(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_
 }
 
 int zpcb200_g2p_apic_eos(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
-  if (g.numChannels < 4 || !P.X || !P.V || !P.C || !P.J) return ZPCB200_E_BADARG;
   if (P.count == 0) return ZPCB200_OK;
+  if (g.numChannels < 4 || !P.X || !P.V || !P.C || !P.J) return ZPCB200_E_BADARG;
   const unsigned grid = (unsigned)((P.count + 127) / 128);
   g2p_aos_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(P, tb, g.tiles, g.numChannels, g.dx, dt);
   ZPC_CHECK_LAUNCH();

@@ -587,7 +587,7 @@ extern "C" {
 
 int zpcb200_bin_particles(void *temp, size_t *temp_bytes, zpc_particles_view pars, zpc_hashtable_view table, float dx,
                           zpc_bins_view bins, int *order_out, zpc_stream_t stream) {
-  if (temp && (!pars.X || !pars.V || !pars.M || !pars.C || !pars.F)) return ZPCB200_E_BADARG;
+  if (temp && pars.count && (!pars.X || !pars.V || !pars.M || !pars.C || !pars.F)) return ZPCB200_E_BADARG;
   if (temp && bins.pars.size < pars.count) return ZPCB200_E_BADARG;
   return bin_pipeline<false>(temp, temp_bytes, pars, nullptr, pars.count, table, dx, bins, order_out, (cudaStream_t)stream);
 }
