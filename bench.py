@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--p2g-sweep", type=int, default=-1, choices=[-1, 3, 4], help="binned P2G sweep variant (zpcb200_set_tuning)")
+    ap.add_argument("--g2p-staged", type=int, default=-1, choices=[-1, 0, 1], help="binned G2P particle staging variant")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,6 +175,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = peaks()
+    api.set_tuning(args.p2g_sweep, args.g2p_staged)
 
     # ---- build the (rank's shard of the) workload ----------------------------------------------------------
     if world == 1:
@@ -288,7 +291,7 @@ def main():
                     config=dict(workload=workload, layout="block-binned AoSoA TileVector<f32,32>, re-bin every %d substeps" % args.rebin_every,
                                 partition=("hash-grid partition rebuilt every substep (EnlargeSparsity{0,2})" if (args.partition == "every_step" and world == 1)
                                            else "hash-grid partition rebuilt with each re-bin, one extra ring (EnlargeSparsity{-1,3})"),
-                                active_blocks=nblocks, l2="inputs (%.1f GB particle state) exceed the 126 MB L2; no explicit flush" % (n_local * 100 / 1e9),
+                                kernel_variants=api.get_tuning(), active_blocks=nblocks, l2="inputs (%.1f GB particle state) exceed the 126 MB L2; no explicit flush" % (n_local * 100 / 1e9),
                                 parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, halo exchange of shared grid blocks via %s" % (
                                     world, "peer stores into symmetric memory over NVLink + device barrier" if sol.transport == "p2p" else "NCCL send/recv")),
                     substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,

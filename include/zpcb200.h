@@ -229,6 +229,15 @@ int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view table, zp
 int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,
                             float dt, zpc_stream_t stream);
 
+/* Kernel variants of the two binned functors (same results up to fp32 re-association; kept selectable so that each
+ * can be measured and parity-tested).  p2g_sweep: 4 = a warp sweeps three cells at a time, lanes = 3 cells x 9 (x,y)
+ * node columns, three z-nodes per lane (default); 3 = one cell at a time, lanes = the 27 nodes.  g2p_staged: 1 = the
+ * particle channels G2P reads are staged with TMA bulk copies, two stages of 8 tiles (default); 0 = plain loads.
+ * -1 leaves a setting unchanged.  Environment defaults: ZPCB200_P2G_SWEEP, ZPCB200_G2P_STAGED.  Not thread-safe
+ * against concurrent launches. */
+int zpcb200_set_tuning(int p2g_sweep, int g2p_staged);
+int zpcb200_get_tuning(int *p2g_sweep_host, int *g2p_staged_host);
+
 /* ---- multi-GPU one-ring halo; no reference counterpart ----------------------- */
 /* pack: copy tiles listed in blockIds[0..n) into a contiguous buffer (nch channels from chn0);
  * unpack_add / unpack_set: add / overwrite them back.  The exchange itself is NCCL send/recv (host). */

@@ -36,6 +36,15 @@ def build_partition(P, expected=None):
     return pars, table
 
 
+@pytest.fixture(params=[(4, 1), (3, 0)], ids=["sweep4-staged", "sweep3-plain"])
+def binned_variant(request):
+    """every binned-path test runs on both kernel variants of the binned P2G / G2P (zpcb200_set_tuning)"""
+    from zpc_b200 import api
+    api.set_tuning(*request.param)
+    yield request.param
+    api.set_tuning(4, 1)
+
+
 CASES = {
     "cube8": dict(s=8, G=32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=11),
     "cube12_sorted": dict(s=12, G=32, jitter_F=0.03, jitter_C=0.3),
@@ -127,7 +136,7 @@ def test_aos_path_matches_oracle(oracle, case, mode):
 
 
 @pytest.mark.parametrize("case", list(CASES))
-def test_binned_path_matches_oracle(oracle, case):
+def test_binned_path_matches_oracle(oracle, case, binned_variant):
     """fast path: bin -> P2G (smem arena, bulk reduce-add) -> update -> G2P (TMA staged) -> unbin."""
     from zpc_b200 import api
     P = make(case)
@@ -170,7 +179,7 @@ def test_binned_path_matches_oracle(oracle, case):
     assert np.array_equal(back.x.cpu().numpy(), bins.attr("x").cpu().numpy())
 
 
-def test_binned_multistep_with_strays_matches_oracle(oracle):
+def test_binned_multistep_with_strays_matches_oracle(oracle, binned_variant):
     """5 substeps without re-binning (particles drift across cells and blocks -> stray path + arena margin),
     then a re-bin, then 2 more; the oracle runs the reference's composed substep on the same particles."""
     from zpc_b200.solver import MpmSolver
@@ -230,7 +239,7 @@ def test_aos_multistep_matches_oracle(oracle):
 
 @pytest.mark.parametrize("name", ["mpm_cube6_mode0", "mpm_cube6_mode1", "mpm_cube8_rest", "mpm_cube5_neg"])
 @pytest.mark.parametrize("layout", ["aos", "binned"])
-def test_against_reference_golden(name, layout):
+def test_against_reference_golden(name, layout, binned_variant):
     """golden vectors produced by executing the reference (tests/golden/make_golden.py); compared by block key."""
     from zpc_b200 import api
     z = np.load(os.path.join(G, name + ".npz"))
@@ -416,7 +425,7 @@ def test_empty_particle_set_is_a_noop():
 
 
 @pytest.mark.parametrize("pos", [(0.3, 0.3, 0.3), (-0.41, 0.02, -0.77), (0.5 - 1e-7, 0.25, 0.125)])
-def test_single_particle_both_layouts(oracle, pos):
+def test_single_particle_both_layouts(oracle, pos, binned_variant):
     """one particle: 8 blocks, 27 nodes; negative coordinates and a position sitting on a cell boundary"""
     from zpc_b200 import api
     P = _single_particle(pos)
@@ -446,7 +455,7 @@ def test_single_particle_both_layouts(oracle, pos):
         check_particles(out, Po, dx, layout + " single g2p")
 
 
-def test_dense_cluster_splits_bins_and_groups(oracle):
+def test_dense_cluster_splits_bins_and_groups(oracle, binned_variant):
     """3 000 particles inside ONE cell: the home block exceeds ZPCB200_BIN_MAX (3 bins), every bin has a single
     1 000-particle cell group spanning several record chunks; compared with the oracle."""
     from zpc_b200 import api

@@ -322,6 +322,20 @@ class ParticleBins:
         return t[:, 0].contiguous() if w == 1 else t
 
 
+def set_tuning(p2g_sweep=-1, g2p_staged=-1):
+    """zpcb200_set_tuning: pick the kernel variant of the binned P2G sweep (4 | 3) and of the binned G2P (1 = TMA-staged
+    particles | 0 = plain loads); -1 keeps a setting."""
+    rc = lib().zpcb200_set_tuning(int(p2g_sweep), int(g2p_staged))
+    if rc:
+        raise RuntimeError("zpcb200_set_tuning(%d, %d) -> %d" % (p2g_sweep, g2p_staged, rc))
+
+
+def get_tuning():
+    a, b = C.c_int(0), C.c_int(0)
+    lib().zpcb200_get_tuning(C.byref(a), C.byref(b))
+    return dict(p2g_sweep=a.value, g2p_staged=b.value)
+
+
 def model_fcr(volume, E=5.0e4, nu=0.4, rho=1000.0):
     return zpc_fixed_corotated(rho, volume, 3, E, nu)
 

@@ -22,6 +22,7 @@
 //
 // Results equal P2G.hpp / G2P.hpp up to fp32 re-association (tests: <= 1e-5 relative).
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "mpm_math.cuh"
@@ -43,7 +44,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ size_t pslot(size_t i) { return ((i >> 5) * NCH) * TS + (i & 31); }  // channel 0 of particle i
 
 struct P2GSmem {
-  float rec[CHUNK][REC_F];          // 28672 B
+  float4 rec4[CHUNK * 7 + CHUNK / 8];  // 29184 B: 7 float4 per record (+1 pad granule per 8 records, used by VAR 4)
   float out[8 * 448];               // 14336 B: the arena as eight [7][64] grid tiles, accumulated with shared atomics
   unsigned short order[BIN_MAX];    // fallback grouping only (no cell-order cache)
   unsigned char grp_of[BIN_MAX];
@@ -51,6 +52,8 @@ struct P2GSmem {
   int gstart[NGRP + 3];
   int tile_id[8];
   int next_unit;
+  int ncells;                       // v4 sweep: non-empty cells of the current chunk, in group order
+  unsigned char cells[NGRP + 7];
 };
 static_assert(sizeof(P2GSmem) <= 56 * 1024, "four CTAs per SM");
 
@@ -58,15 +61,19 @@ static_assert(sizeof(P2GSmem) <= 56 * 1024, "four CTAs per SM");
 __constant__ unsigned char c_unit_c6[NCOL6] = {7,  8,  9,  10, 13, 14, 15, 16, 19, 20, 21, 22, 25, 26, 27, 28,
                                               0,  1,  2,  3,  4,  5,  6,  11, 12, 17, 18, 23, 24, 29, 30, 31, 32, 33, 34, 35};
 
+// record i of the chunk starts at float4 index rec_at<VAR>(i).  VAR 4 reads three records per LDS.128 (one per lane
+// group), typically 8 apart (8 particles per cell): a pad granule every 8 records puts them in different banks.
+template <int VAR> __device__ __forceinline__ int rec_at(int i) { return VAR == 4 ? 7 * i + (i >> 3) : 7 * i; }
+
 // lanes = the 27 stencil offsets.  Sweeps the records of sorted positions [lo,hi) (all in one cell) and returns the
 // 7 channel sums of this lane's node.
 struct LaneCoef {
   float ax, bx, cx, ay, by, cy, az, bz, cz, fx, fy, fz;
 };
-__device__ __forceinline__ void sweep_cell(const float (*rec)[REC_F], int lo, int hi, const LaneCoef &L, float (&acc)[7]) {
+__device__ __forceinline__ void sweep_cell(const float4 *rec, int lo, int hi, const LaneCoef &L, float (&acc)[7]) {
 #pragma unroll 1
   for (int p = lo; p < hi; ++p) {
-    const float4 *rp = reinterpret_cast<const float4 *>(rec[p]);
+    const float4 *rp = rec + 7 * p;
     const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3], r4 = rp[4], r5 = rp[5], r6 = rp[6];
     const float wx = fmaf(fmaf(L.ax, r0.x, L.bx), r0.x, L.cx), wy = fmaf(fmaf(L.ay, r0.y, L.by), r0.y, L.cy),
                 wz = fmaf(fmaf(L.az, r0.z, L.bz), r0.z, L.cz);
@@ -83,6 +90,56 @@ __device__ __forceinline__ void sweep_cell(const float (*rec)[REC_F], int lo, in
   }
 }
 
+
+// ---- v4 sweep: lanes = 3 cells x 9 (ox,oy) node columns -------------------------------------------------------
+// A warp takes three non-empty cells at a time.  Lane group gi = lane/9 owns one cell, lane j = lane%9 owns the node
+// column (ox,oy) = (j/3, j%3) of that cell's stencil and keeps the sums of its three z-nodes x 7 channels in
+// registers: the affine part A + B.o is evaluated once per column (12 FMA) and extended along z with 12 more, the
+// x/y weights are shared by the three nodes — 59 FP instructions per (particle, column) for 3 nodes instead of
+// 33 per node, and every LDS.128 of a record now serves three different particles.
+struct ColCoef {
+  float ax, bx, cx, ay, by, cy, fx, fy;
+};
+__device__ __forceinline__ void sweep_cells3(const float4 *rec, int lo, int hi, int nmax, const ColCoef &L,
+                                             float (&acc)[7][3]) {
+  // lo, hi: record indices relative to the chunk
+#pragma unroll 1
+  for (int it = 0; it < nmax; ++it) {
+    const int p = lo + it;
+    if (p < hi) {
+      const float4 *rp = rec + rec_at<4>(p);
+      const float4 r0 = rp[0];
+      const float wx = fmaf(fmaf(L.ax, r0.x, L.bx), r0.x, L.cx), wy = fmaf(fmaf(L.ay, r0.y, L.by), r0.y, L.cy);
+      const float wxy = wx * wy;
+      const float W0 = wxy * fmaf(fmaf(0.5f, r0.z, -1.5f), r0.z, 1.125f);
+      const float W1 = wxy * fmaf(fmaf(-1.0f, r0.z, 2.0f), r0.z, -0.25f);
+      const float W2 = wxy * fmaf(fmaf(0.5f, r0.z, -0.5f), r0.z, 0.125f);
+      acc[0][0] = fmaf(W0, r0.w, acc[0][0]);
+      acc[0][1] = fmaf(W1, r0.w, acc[0][1]);
+      acc[0][2] = fmaf(W2, r0.w, acc[0][2]);
+#define ZPC_COL3(CH, A0, BX, BY, BZ)                                    \
+  {                                                                     \
+    const float b0 = fmaf(BY, L.fy, fmaf(BX, L.fx, A0));                \
+    acc[CH][0] = fmaf(W0, b0, acc[CH][0]);                              \
+    acc[CH][1] = fmaf(W1, b0 + BZ, acc[CH][1]);                         \
+    acc[CH][2] = fmaf(W2, fmaf(2.0f, BZ, b0), acc[CH][2]);              \
+  }
+      // A = r1.xyz ; B row d = (r1.w r2.x r2.y), (r2.z r2.w r3.x), (r3.y r3.z r3.w)
+      const float4 r1 = rp[1], r2 = rp[2], r3 = rp[3];
+      ZPC_COL3(1, r1.x, r1.w, r2.x, r2.y)
+      ZPC_COL3(2, r1.y, r2.z, r2.w, r3.x)
+      ZPC_COL3(3, r1.z, r3.y, r3.z, r3.w)
+      // a = r4.xyz ; K row d = (r4.w r5.x r5.y), (r5.z r5.w r6.x), (r6.y r6.z r6.w)
+      const float4 r4 = rp[4], r5 = rp[5], r6 = rp[6];
+      ZPC_COL3(4, r4.x, r4.w, r5.x, r5.y)
+      ZPC_COL3(5, r4.y, r5.z, r5.w, r6.x)
+      ZPC_COL3(6, r4.z, r6.y, r6.z, r6.w)
+#undef ZPC_COL3
+    }
+  }
+}
+
+template <int VAR>
 __global__ void __launch_bounds__(P2G_NT, 4)
 p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
@@ -149,11 +206,13 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     __syncthreads();
   }
 
-  // ---- (b) per chunk: records (one thread per particle), then cell sweeps (lanes = stencil offsets) --------
+  // ---- (b) per chunk: records (one thread per particle), then cell sweeps ------------------------------------
   const int n_fast = S.gstart[GRP_FAR];
+  // VAR 3: lanes = the 27 stencil offsets of one cell.  VAR 4: lanes = 3 cells x 9 (ox,oy) node columns.
   const bool lane_on = l < 27;
-  const int lc = lane_on ? l : 0;  // lanes 27..31 shadow lane 0 and never write
-  const int ox = lc / 9, oy = (lc / 3) % 3, oz = lc % 3;
+  const int lc = lane_on ? l : 0;  // VAR 3: lanes 27..31 shadow lane 0 and never write
+  const int ox = VAR == 4 ? (lc % 9) / 3 : lc / 9, oy = VAR == 4 ? lc % 3 : (lc / 3) % 3, oz = lc % 3;
+  const int gi = l / 9;            // VAR 4: cell slot of this lane (3 = idle lanes 27..31)
   LaneCoef L;
   {
     // quadratic B-spline as a polynomial in d0 (InterpolationKernel.hpp:105-113):
@@ -164,6 +223,18 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     L.fx = (float)ox; L.fy = (float)oy; L.fz = (float)oz;
   }
   for (int cb = 0; cb < n_fast; cb += CHUNK) {
+    if (VAR == 4 && w == 0) {  // compact list of the cells that have particles in [cb, cb+CHUNK)
+      const int ce0 = min(cb + CHUNK, n_fast);
+      int base = 0;
+#pragma unroll 1
+      for (int g = l; g < GRP_FAR + 31 - (GRP_FAR + 31) % 32; g += 32) {
+        const bool ne = g < GRP_FAR && max(S.gstart[g], cb) < min(S.gstart[g + 1], ce0);
+        const unsigned m = __ballot_sync(0xffffffffu, ne);
+        if (ne) S.cells[base + __popc(m & lanemask_lt())] = (unsigned char)g;
+        base += __popc(m);
+      }
+      if (l == 0) S.ncells = base;
+    }
     {  // records
       const int pos = cb + tid;
       if (pos < n_fast) {
@@ -187,7 +258,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 #pragma unroll
         for (int d = 0; d < 9; ++d) C[d] = pars[s + (ZPC_PB_C + d) * TS];
         // mv_d = W (A_d + sum_e B_de o_e), rhs_d = W (a_d + sum_e K_de o_e), o = stencil offset (0,1,2)^3
-        float4 *dst = reinterpret_cast<float4 *>(S.rec[tid]);
+        float4 *dst = S.rec4 + rec_at<VAR>(tid);
         float A[3], a[3], B[9], Kd[9];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -207,30 +278,63 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     }
     __syncthreads();
     const int ce = min(cb + CHUNK, n_fast);
-    const float(*rec)[REC_F] = S.rec - cb;  // rec[pos] for pos in [cb, ce)
-    // columns are handed out dynamically (one shared counter): warps that finish early take the next column, the
-    // per-cell sums go straight into the arena tiles with shared-memory float atomics (no private arenas, no merge)
-    while (true) {
-      int u = 0;
-      if (l == 0) u = atomicAdd(&S.next_unit, 1);
-      u = __shfl_sync(0xffffffffu, u, 0);
-      if (u >= NCOL6) break;
-      const int c6 = c_unit_c6[u];
-      const int g0 = c6 * 6;
-      if (S.gstart[g0 + 6] <= cb || S.gstart[g0] >= ce) continue;  // nothing of this column in the chunk
-      const int axn = c6 / 6 + ox, ayn = c6 % 6 + oy;              // arena node (x+1+ox, y+1+oy, zc+oz)
-      const int xy_off = (((axn >> 2) << 2) | ((ayn >> 2) << 1)) * 448 + (((axn & 3) << 4) | ((ayn & 3) << 2));
-#pragma unroll 1
-      for (int zc = 0; zc < 6; ++zc) {
-        const int lo = max(S.gstart[g0 + zc], cb), hi = min(S.gstart[g0 + zc + 1], ce);
-        if (lo >= hi) continue;
-        float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        sweep_cell(rec, lo, hi, L, acc);
-        if (lane_on) {
-          const int azn = zc + oz;
-          float *dstn = S.out + xy_off + (azn >> 2) * 448 + (azn & 3);
+    if (VAR == 4) {
+      // cell triples are handed out dynamically (one shared counter); each lane group sweeps its own cell, the sums
+      // of the lane's three z-nodes go into the arena tiles with shared-memory float atomics
+      const int ncells = S.ncells;
+      ColCoef Lc = {L.ax, L.bx, L.cx, L.ay, L.by, L.cy, L.fx, L.fy};
+      while (true) {
+        int u = 0;
+        if (l == 0) u = atomicAdd(&S.next_unit, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (3 * u >= ncells) break;
+        const int ci = 3 * u + gi;
+        const bool have = gi < 3 && ci < ncells;
+        const int g = have ? (int)S.cells[ci] : 0;
+        const int lo = have ? max(S.gstart[g], cb) - cb : 0, hi = have ? min(S.gstart[g + 1], ce) - cb : 0;
+        const int nmax = __reduce_max_sync(0xffffffffu, hi - lo);
+        float acc[7][3];
 #pragma unroll
-          for (int ch = 0; ch < 7; ++ch) atomicAdd(dstn + ch * 64, acc[ch]);
+        for (int ch = 0; ch < 7; ++ch) { acc[ch][0] = 0.f; acc[ch][1] = 0.f; acc[ch][2] = 0.f; }
+        sweep_cells3(S.rec4, lo, hi, nmax, Lc, acc);
+        if (have) {
+          const int c6 = g / 6, zc = g - 6 * c6;                     // g = (cx+1)*36 + (cy+1)*6 + (cz+1)
+          const int axn = c6 / 6 + ox, ayn = c6 % 6 + oy;            // arena node (cx+1+ox, cy+1+oy, cz+1+k)
+          const int xy_off = (((axn >> 2) << 2) | ((ayn >> 2) << 1)) * 448 + (((axn & 3) << 4) | ((ayn & 3) << 2));
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int azn = zc + k;
+            float *dstn = S.out + xy_off + (azn >> 2) * 448 + (azn & 3);
+#pragma unroll
+            for (int ch = 0; ch < 7; ++ch) atomicAdd(dstn + ch * 64, acc[ch][k]);
+          }
+        }
+      }
+    } else {
+      // columns are handed out dynamically (one shared counter): warps that finish early take the next column, the
+      // per-cell sums go straight into the arena tiles with shared-memory float atomics (no private arenas, no merge)
+      while (true) {
+        int u = 0;
+        if (l == 0) u = atomicAdd(&S.next_unit, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= NCOL6) break;
+        const int c6 = c_unit_c6[u];
+        const int g0 = c6 * 6;
+        if (S.gstart[g0 + 6] <= cb || S.gstart[g0] >= ce) continue;  // nothing of this column in the chunk
+        const int axn = c6 / 6 + ox, ayn = c6 % 6 + oy;              // arena node (x+1+ox, y+1+oy, zc+oz)
+        const int xy_off = (((axn >> 2) << 2) | ((ayn >> 2) << 1)) * 448 + (((axn & 3) << 4) | ((ayn & 3) << 2));
+  #pragma unroll 1
+        for (int zc = 0; zc < 6; ++zc) {
+          const int lo = max(S.gstart[g0 + zc], cb), hi = min(S.gstart[g0 + zc + 1], ce);
+          if (lo >= hi) continue;
+          float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          sweep_cell(S.rec4 - 7 * cb, lo, hi, L, acc);
+          if (lane_on) {
+            const int azn = zc + oz;
+            float *dstn = S.out + xy_off + (azn >> 2) * 448 + (azn & 3);
+  #pragma unroll
+            for (int ch = 0; ch < 7; ++ch) atomicAdd(dstn + ch * 64, acc[ch]);
+          }
         }
       }
     }
@@ -267,6 +371,70 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// One particle of the binned G2P: gather against the staged arena velocities sv (= G2PSmem::v), APIC C, advect pos.
+__device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int ky, int kz, const zpc_hashtable_view &tb,
+                                                   const float *__restrict__ tiles, int nch, float dx, float dt, float D_inv,
+                                                   float (&pos)[3], float (&vel)[3], float (&C)[9]) {
+  zpcm::Arena ar;
+  zpcm::arena_init(ar, dx, pos);
+  const int ax0 = ar.corner[0] - 4 * kx, ay0 = ar.corner[1] - 4 * ky, az0 = ar.corner[2] - 4 * kz;
+  float G[9];  // G[r + 3e] = sum W v_r o_e
+  if ((unsigned)ax0 < 6u && (unsigned)ay0 < 6u && (unsigned)az0 < 6u) {
+    int fo[3], go[3], ho[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const int a = ax0 + o, b = ay0 + o, c = az0 + o;
+      fo[o] = (a >> 2) * (4 * 192) + ((a & 3) << 4);
+      go[o] = (b >> 2) * (2 * 192) + ((b & 3) << 2);
+      ho[o] = (c >> 2) * 192 + (c & 3);
+    }
+    // separable contraction: z, then y, then x
+    float px[3][3], pz[3][3], py[3][3];  // [i][r]
+#pragma unroll
+    for (int ii = 0; ii < 3; ++ii) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { px[ii][r] = 0.f; py[ii][r] = 0.f; pz[ii][r] = 0.f; }
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj) {
+        const int base = fo[ii] + go[jj];
+        float u[3], uz[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float v0 = sv[base + ho[0] + r * 64], v1 = sv[base + ho[1] + r * 64], v2 = sv[base + ho[2] + r * 64];
+          const float t1 = ar.w[2][1] * v1, t2 = ar.w[2][2] * v2;
+          u[r] = fmaf(ar.w[2][0], v0, t1 + t2);
+          uz[r] = fmaf(2.f, t2, t1);
+        }
+        const float wyj = ar.w[1][jj];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float t = wyj * u[r];
+          px[ii][r] += t;
+          py[ii][r] = fmaf((float)jj, t, py[ii][r]);
+          pz[ii][r] = fmaf(wyj, uz[r], pz[ii][r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float t0 = ar.w[0][0] * px[0][r], t1 = ar.w[0][1] * px[1][r], t2 = ar.w[0][2] * px[2][r];
+      vel[r] = t0 + t1 + t2;
+      G[r] = fmaf(2.f, t2, t1);
+      G[r + 3] = ar.w[0][0] * py[0][r] + ar.w[0][1] * py[1][r] + ar.w[0][2] * py[2][r];
+      G[r + 6] = ar.w[0][0] * pz[0][r] + ar.w[0][1] * pz[1][r] + ar.w[0][2] * pz[2][r];
+    }
+  } else {
+    zpcp::g2p_gather_particle(ar, tb, tiles, nch, vel, G);
+  }
+  // C[r + 3e] = D_inv * sum W v_r (o_e dx - local_e) = D_inv * (dx G_re - local_e v_r)
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) C[r + 3 * e] = (dx * G[r + 3 * e] - ar.local[e] * vel[r]) * D_inv;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
+}
+
 constexpr int G2P_NT = 256;
 struct G2PSmem {
   float v[8][3][64];  // 6144 B: channels 1..3 of the eight arena tiles
@@ -327,65 +495,8 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
     for (int d = 0; d < 3; ++d) pos[d] = pars[s + (ZPC_PB_X + d) * TS];
 #pragma unroll
     for (int d = 0; d < 9; ++d) Fo[d] = pars[s + (ZPC_PB_F + d) * TS];  // issued early: consumed after the contraction
-    zpcm::Arena ar;
-    zpcm::arena_init(ar, dx, pos);
-    const int ax0 = ar.corner[0] - 4 * kx, ay0 = ar.corner[1] - 4 * ky, az0 = ar.corner[2] - 4 * kz;
-    float vel[3], G[9];  // G[r + 3e] = sum W v_r o_e
-    if ((unsigned)ax0 < 6u && (unsigned)ay0 < 6u && (unsigned)az0 < 6u) {
-      int fo[3], go[3], ho[3];
-#pragma unroll
-      for (int o = 0; o < 3; ++o) {
-        const int a = ax0 + o, b = ay0 + o, c = az0 + o;
-        fo[o] = (a >> 2) * (4 * 192) + ((a & 3) << 4);
-        go[o] = (b >> 2) * (2 * 192) + ((b & 3) << 2);
-        ho[o] = (c >> 2) * 192 + (c & 3);
-      }
-      // separable contraction: z, then y, then x
-      float px[3][3], pz[3][3], py[3][3];  // [i][r]
-#pragma unroll
-      for (int ii = 0; ii < 3; ++ii) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { px[ii][r] = 0.f; py[ii][r] = 0.f; pz[ii][r] = 0.f; }
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-          const int base = fo[ii] + go[jj];
-          float u[3], uz[3];
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const float v0 = sv[base + ho[0] + r * 64], v1 = sv[base + ho[1] + r * 64], v2 = sv[base + ho[2] + r * 64];
-            const float t1 = ar.w[2][1] * v1, t2 = ar.w[2][2] * v2;
-            u[r] = fmaf(ar.w[2][0], v0, t1 + t2);
-            uz[r] = fmaf(2.f, t2, t1);
-          }
-          const float wyj = ar.w[1][jj];
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const float t = wyj * u[r];
-            px[ii][r] += t;
-            py[ii][r] = fmaf((float)jj, t, py[ii][r]);
-            pz[ii][r] = fmaf(wyj, uz[r], pz[ii][r]);
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float t0 = ar.w[0][0] * px[0][r], t1 = ar.w[0][1] * px[1][r], t2 = ar.w[0][2] * px[2][r];
-        vel[r] = t0 + t1 + t2;
-        G[r] = fmaf(2.f, t2, t1);
-        G[r + 3] = ar.w[0][0] * py[0][r] + ar.w[0][1] * py[1][r] + ar.w[0][2] * py[2][r];
-        G[r + 6] = ar.w[0][0] * pz[0][r] + ar.w[0][1] * pz[1][r] + ar.w[0][2] * pz[2][r];
-      }
-    } else {
-      zpcp::g2p_gather_particle(ar, tb, tiles, nch, vel, G);
-    }
-    // C[r + 3e] = D_inv * sum W v_r (o_e dx - local_e) = D_inv * (dx G_re - local_e v_r)
-    float C[9], tmp[9];
-#pragma unroll
-    for (int e = 0; e < 3; ++e)
-#pragma unroll
-      for (int r = 0; r < 3; ++r) C[r + 3 * e] = (dx * G[r + 3 * e] - ar.local[e] * vel[r]) * D_inv;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
+    float vel[3], C[9], tmp[9];
+    g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C);
     if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
       const int cx = (int)floorf(pos[0] / dx - 0.5f) - 1 - 4 * kx, cy = (int)floorf(pos[1] / dx - 0.5f) - 1 - 4 * ky,
                 cz = (int)floorf(pos[2] / dx - 0.5f) - 1 - 4 * kz;
@@ -426,6 +537,167 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
           cellStart[(size_t)bin * ZPCB200_CELL_GROUPS_PAD + g] = (unsigned short)run;
         }
         run += c[k];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < np; i += G2P_NT) cellOrder[p0 + atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Binned G2P, staged variant: the particle channels G2P reads (x: 3 x 128 B, F: 9 x 128 B per 32-particle tile, both
+// contiguous inside a TileVector tile) are brought in with TMA bulk copies, eight tiles (256 particles) per stage, two
+// stages.  One thread issues the copies of the first two stages before anything else happens, so a whole bin's reads
+// are in flight while the arena blocks are looked up and staged — the memory-level parallelism no longer depends on
+// how many loads a thread can hold in registers.  Threads map to (tile, lane) of the stage: every global store is a
+// full 128-byte line.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    if (!done && ++spins > (1u << 20)) __trap();  // never hang the GPU on a lost transaction
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int G2P_ST = 8;  // particle tiles per stage
+struct G2PStagedSmem {
+  float v[8][3][64];               // 6144 B: channels 1..3 of the eight arena tiles
+  float xs[2][G2P_ST][3][TS];      // 2 x 3072 B
+  float fs[2][G2P_ST][9][TS];      // 2 x 9216 B
+  unsigned long long bar_grid, bar_stage[2];
+  int tile_id[8];
+  int cnt[NGRP + 3];
+  unsigned char grp_of[BIN_MAX];
+};
+static_assert(sizeof(G2PStagedSmem) <= 48 * 1024, "static shared memory");
+
+__global__ void __launch_bounds__(G2P_NT, 4)
+g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
+                         const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder,
+                         unsigned short *__restrict__ cellStart, zpc_hashtable_view tb, const float *__restrict__ tiles, int nch,
+                         float dx, float dt) {
+  __shared__ __align__(128) G2PStagedSmem S;
+  const int bin = blockIdx.x;
+  if (bin >= *numBins) return;
+  const int tid = threadIdx.x;
+  const int p0 = binStart[bin], np = min(binStart[bin + 1] - p0, BIN_MAX);
+  const int t0 = p0 >> 5;                                            // first particle tile the bin overlaps
+  const int ntiles = np > 0 ? ((p0 + np - 1) >> 5) - t0 + 1 : 0;     // <= 33
+  const int nstages = (ntiles + G2P_ST - 1) / G2P_ST;
+  if (tid == 0) {
+    mbar_init(&S.bar_grid, 1);
+    mbar_init(&S.bar_stage[0], 1);
+    mbar_init(&S.bar_stage[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // stage c <- tiles [t0 + 8c, t0 + 8c + 8) ∩ the bin's tiles: x = channels 1..3, F = channels 16..24
+  auto issue_stage = [&](int c) {
+    const int b = c & 1, tb0 = c * G2P_ST, nt = min(G2P_ST, ntiles - tb0);
+    mbar_expect_tx(&S.bar_stage[b], (unsigned)nt * (3u + 9u) * TS * 4u);
+    for (int t = 0; t < nt; ++t) {
+      const float *src = pars + (size_t)(t0 + tb0 + t) * NCH * TS;
+      bulk_g2s(&S.xs[b][t][0][0], src + ZPC_PB_X * TS, 3 * TS * 4, &S.bar_stage[b]);
+      bulk_g2s(&S.fs[b][t][0][0], src + ZPC_PB_F * TS, 9 * TS * 4, &S.bar_stage[b]);
+    }
+  };
+  if (tid == 0) {  // the same thread initialised the barriers: program order suffices
+    if (nstages > 0) issue_stage(0);
+    if (nstages > 1) issue_stage(1);
+  }
+  const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
+  if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
+  if (tid < NGRP + 3) S.cnt[tid] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned bytes = 0;
+    for (int b = 0; b < 8; ++b) bytes += S.tile_id[b] >= 0 ? 768u : 0u;
+    mbar_expect_tx(&S.bar_grid, bytes);
+    for (int b = 0; b < 8; ++b)
+      if (S.tile_id[b] >= 0) bulk_g2s(&S.v[b][0][0], tiles + ((size_t)S.tile_id[b] * nch + 1) * 64, 768, &S.bar_grid);
+  }
+  for (int b = 0; b < 8; ++b)  // blocks missing from the partition read as zero velocity
+    if (S.tile_id[b] < 0 && tid < 192) (&S.v[b][0][0])[tid] = 0.f;
+  mbar_wait(&S.bar_grid, 0);
+  __syncthreads();
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  const float *sv = &S.v[0][0][0];
+  const int tl = tid >> 5, ln = tid & 31;
+  for (int c = 0; c < nstages; ++c) {
+    const int b = c & 1;
+    mbar_wait(&S.bar_stage[b], (unsigned)(c >> 1) & 1u);
+    const int gp = ((t0 + c * G2P_ST + tl) << 5) + ln;  // global particle slot of this thread
+    const int i = gp - p0;                              // slot relative to the bin
+    const bool mine = i >= 0 && i < np;
+    float pos[3], Fo[9];
+    if (mine) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) pos[d] = S.xs[b][tl][d][ln];
+#pragma unroll
+      for (int d = 0; d < 9; ++d) Fo[d] = S.fs[b][tl][d][ln];
+    }
+    if (c + 2 < nstages) {  // bins with more than 512 particles: refill this stage once everybody has read it
+      __syncthreads();
+      if (tid == 0) issue_stage(c + 2);
+    }
+    if (mine) {
+      const size_t s = pslot((size_t)gp);
+      float vel[3], C[9], tmp[9];
+      g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C);
+      if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
+        const int cx = (int)floorf(pos[0] / dx - 0.5f) - 1 - 4 * kx, cy = (int)floorf(pos[1] / dx - 0.5f) - 1 - 4 * ky,
+                  cz = (int)floorf(pos[2] / dx - 0.5f) - 1 - 4 * kz;
+        const int g = ((unsigned)(cx + 1) < 6u && (unsigned)(cy + 1) < 6u && (unsigned)(cz + 1) < 6u)
+                          ? ((cx + 1) * 6 + (cy + 1)) * 6 + (cz + 1)
+                          : GRP_FAR;
+        S.grp_of[i] = (unsigned char)g;
+        atomicAdd(&S.cnt[g], 1);
+      }
+#pragma unroll
+      for (int d = 0; d < 9; ++d) tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f);
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          pars[s + (ZPC_PB_F + 3 * cc + r) * TS] = tmp[r] * Fo[3 * cc] + tmp[3 + r] * Fo[3 * cc + 1] + tmp[6 + r] * Fo[3 * cc + 2];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { pars[s + (ZPC_PB_X + d) * TS] = pos[d]; pars[s + (ZPC_PB_V + d) * TS] = vel[d]; }
+#pragma unroll
+      for (int d = 0; d < 9; ++d) pars[s + (ZPC_PB_C + d) * TS] = C[d];
+    }
+  }
+  if (cellOrder) {  // counting sort of the bin by new cell group -> global cache for the next P2G
+    __syncthreads();
+    const int w = tid >> 5, l = tid & 31;
+    if (w == 0) {
+      int cn[7], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { const int g = l * 7 + k; cn[k] = g < NGRP ? S.cnt[g] : 0; sum += cn[k]; }
+      int inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (l >= d) inc += t; }
+      int run = inc - sum;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int g = l * 7 + k;
+        if (g <= NGRP) {
+          S.cnt[g] = run;
+          cellStart[(size_t)bin * ZPCB200_CELL_GROUPS_PAD + g] = (unsigned short)run;
+        }
+        run += cn[k];
       }
     }
     __syncthreads();
@@ -581,9 +853,36 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
   return ZPCB200_OK;
 }
 
+// Kernel variants (see zpcb200_set_tuning): defaults from the environment, once.
+struct Tuning {
+  int p2g_sweep;   // 4 = three cells x nine node columns per warp; 3 = one cell x 27 nodes
+  int g2p_staged;  // 1 = particle channels staged with TMA bulk copies; 0 = plain loads
+};
+Tuning &tuning() {
+  static Tuning t = [] {
+    Tuning d = {4, 1};
+    if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = e[0] == '3' ? 3 : 4;
+    if (const char *e = getenv("ZPCB200_G2P_STAGED")) d.g2p_staged = e[0] == '0' ? 0 : 1;
+    return d;
+  }();
+  return t;
+}
+
 }  // namespace
 
 extern "C" {
+
+int zpcb200_set_tuning(int p2g_sweep, int g2p_staged) {
+  if ((p2g_sweep != 3 && p2g_sweep != 4 && p2g_sweep != -1) || g2p_staged < -1 || g2p_staged > 1) return ZPCB200_E_BADARG;
+  if (p2g_sweep != -1) tuning().p2g_sweep = p2g_sweep;
+  if (g2p_staged != -1) tuning().g2p_staged = g2p_staged;
+  return ZPCB200_OK;
+}
+int zpcb200_get_tuning(int *p2g_sweep, int *g2p_staged) {
+  if (p2g_sweep) *p2g_sweep = tuning().p2g_sweep;
+  if (g2p_staged) *g2p_staged = tuning().g2p_staged;
+  return ZPCB200_OK;
+}
 
 int zpcb200_bin_particles(void *temp, size_t *temp_bytes, zpc_particles_view pars, zpc_hashtable_view table, float dx,
                           zpc_bins_view bins, int *order_out, zpc_stream_t stream) {
@@ -611,13 +910,16 @@ int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_g
     return ZPCB200_E_BADARG;
   static bool attr_set = false;
   if (!attr_set) {
-    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
     attr_set = true;
   }
+  const int variant = tuning().p2g_sweep;
   float mu, lam;
   zpcm::lame_host(model.E, model.nu, mu, lam);
   const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
-  p2g_binned_kernel<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
+  auto kern = variant == 3 ? p2g_binned_kernel<3> : p2g_binned_kernel<4>;
+  kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
       bins.cellOrderValid, tb, g.tiles, g.dx, dt, model.volume, mu, lam);
   ZPC_CHECK_LAUNCH();
@@ -628,9 +930,11 @@ int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids
   if (g.numChannels < 4 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
     return ZPCB200_E_BADARG;
   const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
-  g2p_binned_kernel<<<bins.binCapacity, G2P_NT, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
-                                                                           cache ? bins.cellOrder : nullptr, bins.cellStart, tb,
-                                                                           g.tiles, g.numChannels, g.dx, dt);
+  const int staged = tuning().g2p_staged;
+  auto kern = staged ? g2p_binned_staged_kernel : g2p_binned_kernel;
+  kern<<<bins.binCapacity, G2P_NT, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
+                                                              cache ? bins.cellOrder : nullptr, bins.cellStart, tb, g.tiles,
+                                                              g.numChannels, g.dx, dt);
   ZPC_CHECK_LAUNCH();
   if (cache) ZPC_CUDA(cudaMemsetAsync(bins.cellOrderValid, 1, sizeof(int), (cudaStream_t)stream));  // non-zero = valid
   return ZPCB200_OK;
