@@ -18,7 +18,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzpcb200.so")
+LIB_PATH = os.environ.get("ZPCB200_LIB") or os.path.join(HERE, "libzpcb200.so")
 
 BIN_MAX = 1024
 PB_M, PB_X, PB_V, PB_C, PB_F, PB_NCH = 0, 1, 4, 7, 16, 25

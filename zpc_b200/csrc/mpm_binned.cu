@@ -52,8 +52,8 @@ struct P2GSmem {
   int gstart[NGRP + 3];
   int tile_id[8];
   int next_unit;
-  int ncells;                       // v4 sweep: non-empty cells of the current chunk, in group order
-  unsigned char cells[NGRP + 7];
+  int ncells[2];                    // v4 sweep: non-empty cells of the current / next chunk
+  unsigned char cells[2][NGRP + 7];
 };
 static_assert(sizeof(P2GSmem) <= 56 * 1024, "four CTAs per SM");
 
@@ -139,8 +139,11 @@ __device__ __forceinline__ void sweep_cells3(const float4 *rec, int lo, int hi, 
   }
 }
 
+#ifndef ZPC_P2G_MINB
+#define ZPC_P2G_MINB 4
+#endif
 template <int VAR>
-__global__ void __launch_bounds__(P2G_NT, 4)
+__global__ void __launch_bounds__(P2G_NT, ZPC_P2G_MINB)
 p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
                   const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
@@ -222,19 +225,25 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     L.az = oz == 1 ? -1.0f : 0.5f; L.bz = oz == 0 ? -1.5f : (oz == 1 ? 2.0f : -0.5f); L.cz = oz == 0 ? 1.125f : (oz == 1 ? -0.25f : 0.125f);
     L.fx = (float)ox; L.fy = (float)oy; L.fz = (float)oz;
   }
-  for (int cb = 0; cb < n_fast; cb += CHUNK) {
-    if (VAR == 4 && w == 0) {  // compact list of the cells that have particles in [cb, cb+CHUNK)
-      const int ce0 = min(cb + CHUNK, n_fast);
-      int base = 0;
+  // VAR 4: list of the cells that have particles in the chunk [cb, cb+CHUNK), in group order; run by one whole warp.
+  // (Ordering the list by particle count — so that the three cells a warp sweeps in lockstep have equal length — was
+  // measured slower: 8.0 ms vs 7.8 ms at C3; consecutive cells of one column share arena nodes and smem banks better.)
+  auto build_cell_list = [&](int buf, int cb) {
+    const int ce0 = min(cb + CHUNK, n_fast);
+    unsigned char *out = S.cells[buf];
+    int base = 0;
 #pragma unroll 1
-      for (int g = l; g < GRP_FAR + 31 - (GRP_FAR + 31) % 32; g += 32) {
-        const bool ne = g < GRP_FAR && max(S.gstart[g], cb) < min(S.gstart[g + 1], ce0);
-        const unsigned m = __ballot_sync(0xffffffffu, ne);
-        if (ne) S.cells[base + __popc(m & lanemask_lt())] = (unsigned char)g;
-        base += __popc(m);
-      }
-      if (l == 0) S.ncells = base;
+    for (int g = l; g < GRP_FAR + 31 - (GRP_FAR + 31) % 32; g += 32) {
+      const bool ne = g < GRP_FAR && max(S.gstart[g], cb) < min(S.gstart[g + 1], ce0);
+      const unsigned m = __ballot_sync(0xffffffffu, ne);
+      if (ne) out[base + __popc(m & lanemask_lt())] = (unsigned char)g;
+      base += __popc(m);
     }
+    if (l == 0) S.ncells[buf] = base;
+  };
+  if (VAR == 4 && w == P2G_NW - 1 && n_fast > 0) build_cell_list(0, 0);
+  for (int cb = 0; cb < n_fast; cb += CHUNK) {
+    const int buf = (cb / CHUNK) & 1;
     {  // records
       const int pos = cb + tid;
       if (pos < n_fast) {
@@ -281,16 +290,21 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     if (VAR == 4) {
       // cell triples are handed out dynamically (one shared counter); each lane group sweeps its own cell, the sums
       // of the lane's three z-nodes go into the arena tiles with shared-memory float atomics
-      const int ncells = S.ncells;
+      const int ncells = S.ncells[buf];
+      const unsigned char *cells = S.cells[buf];
       ColCoef Lc = {L.ax, L.bx, L.cx, L.ay, L.by, L.cy, L.fx, L.fy};
       while (true) {
         int u = 0;
         if (l == 0) u = atomicAdd(&S.next_unit, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
-        if (3 * u >= ncells) break;
+        if (3 * u >= ncells) {
+          // the first warp to run out of work prepares the next chunk's list while the others finish their sweeps
+          if (3 * (u - 1) < ncells && cb + CHUNK < n_fast) build_cell_list(buf ^ 1, cb + CHUNK);
+          break;
+        }
         const int ci = 3 * u + gi;
         const bool have = gi < 3 && ci < ncells;
-        const int g = have ? (int)S.cells[ci] : 0;
+        const int g = have ? (int)cells[ci] : 0;
         const int lo = have ? max(S.gstart[g], cb) - cb : 0, hi = have ? min(S.gstart[g + 1], ce) - cb : 0;
         const int nmax = __reduce_max_sync(0xffffffffu, hi - lo);
         float acc[7][3];
@@ -435,7 +449,13 @@ __device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int 
   for (int d = 0; d < 3; ++d) pos[d] += vel[d] * dt;
 }
 
-constexpr int G2P_NT = 256;
+#ifndef ZPC_G2P_NT
+#define ZPC_G2P_NT 256
+#endif
+#ifndef ZPC_G2P_MINB
+#define ZPC_G2P_MINB 4
+#endif
+constexpr int G2P_NT = ZPC_G2P_NT;
 struct G2PSmem {
   float v[8][3][64];  // 6144 B: channels 1..3 of the eight arena tiles
   unsigned long long bar;
@@ -444,7 +464,7 @@ struct G2PSmem {
   unsigned char grp_of[BIN_MAX];
 };
 
-__global__ void __launch_bounds__(G2P_NT, 4)
+__global__ void __launch_bounds__(G2P_NT, ZPC_G2P_MINB)
 g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder, unsigned short *__restrict__ cellStart,
                   zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx, float dt) {
@@ -455,7 +475,7 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
   const int p0 = binStart[bin], np = min(binStart[bin + 1] - p0, BIN_MAX);
   const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
   if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
-  if (tid < NGRP + 3) S.cnt[tid] = 0;
+  for (int i = tid; i < NGRP + 3; i += G2P_NT) S.cnt[i] = 0;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(&S.bar)), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -475,7 +495,8 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
   }
   // blocks missing from the partition read as zero velocity
   for (int b = 0; b < 8; ++b)
-    if (S.tile_id[b] < 0 && tid < 192) (&S.v[b][0][0])[tid] = 0.f;
+    if (S.tile_id[b] < 0)
+      for (int i = tid; i < 192; i += G2P_NT) (&S.v[b][0][0])[i] = 0.f;
   {  // wait for the TMA bytes (phase 0)
     unsigned done = 0;
     while (!done) {
@@ -573,8 +594,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
-constexpr int G2P_ST = 8;  // particle tiles per stage
-struct G2PStagedSmem {
+template <int NT> struct G2PStagedSmem {
+  static constexpr int G2P_ST = NT / 32;  // particle tiles per stage (one thread per particle)
   float v[8][3][64];               // 6144 B: channels 1..3 of the eight arena tiles
   float xs[2][G2P_ST][3][TS];      // 2 x 3072 B
   float fs[2][G2P_ST][9][TS];      // 2 x 9216 B
@@ -583,14 +604,18 @@ struct G2PStagedSmem {
   int cnt[NGRP + 3];
   unsigned char grp_of[BIN_MAX];
 };
-static_assert(sizeof(G2PStagedSmem) <= 48 * 1024, "static shared memory");
+static_assert(sizeof(G2PStagedSmem<256>) <= 48 * 1024, "static shared memory");
 
-__global__ void __launch_bounds__(G2P_NT, 4)
+// NT threads per CTA: small CTAs interleave their prologue / wait / store phases better — measured at C3:
+// 64 threads (15 CTAs/SM) 2.18 ms, 128 (8/SM) 2.30 ms, 256 (4/SM) 2.98 ms.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)
 g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                          const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder,
                          unsigned short *__restrict__ cellStart, zpc_hashtable_view tb, const float *__restrict__ tiles, int nch,
                          float dx, float dt) {
-  __shared__ __align__(128) G2PStagedSmem S;
+  constexpr int G2P_ST = NT / 32;
+  __shared__ __align__(128) G2PStagedSmem<NT> S;
   const int bin = blockIdx.x;
   if (bin >= *numBins) return;
   const int tid = threadIdx.x;
@@ -604,7 +629,7 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
     mbar_init(&S.bar_stage[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // stage c <- tiles [t0 + 8c, t0 + 8c + 8) ∩ the bin's tiles: x = channels 1..3, F = channels 16..24
+  // stage c <- tiles [t0 + G2P_ST c, t0 + G2P_ST (c + 1)) ∩ the bin's tiles: x = channels 1..3, F = channels 16..24
   auto issue_stage = [&](int c) {
     const int b = c & 1, tb0 = c * G2P_ST, nt = min(G2P_ST, ntiles - tb0);
     mbar_expect_tx(&S.bar_stage[b], (unsigned)nt * (3u + 9u) * TS * 4u);
@@ -620,7 +645,7 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
   }
   const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
   if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
-  if (tid < NGRP + 3) S.cnt[tid] = 0;
+  for (int i = tid; i < NGRP + 3; i += NT) S.cnt[i] = 0;
   __syncthreads();
   if (tid == 0) {
     unsigned bytes = 0;
@@ -630,7 +655,8 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
       if (S.tile_id[b] >= 0) bulk_g2s(&S.v[b][0][0], tiles + ((size_t)S.tile_id[b] * nch + 1) * 64, 768, &S.bar_grid);
   }
   for (int b = 0; b < 8; ++b)  // blocks missing from the partition read as zero velocity
-    if (S.tile_id[b] < 0 && tid < 192) (&S.v[b][0][0])[tid] = 0.f;
+    if (S.tile_id[b] < 0)
+      for (int i = tid; i < 192; i += NT) (&S.v[b][0][0])[i] = 0.f;
   mbar_wait(&S.bar_grid, 0);
   __syncthreads();
   const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
@@ -701,7 +727,7 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
       }
     }
     __syncthreads();
-    for (int i = tid; i < np; i += G2P_NT) cellOrder[p0 + atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
+    for (int i = tid; i < np; i += NT) cellOrder[p0 + atomicAdd(&S.cnt[S.grp_of[i]], 1)] = (unsigned short)i;
   }
 }
 
@@ -856,13 +882,13 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
 // Kernel variants (see zpcb200_set_tuning): defaults from the environment, once.
 struct Tuning {
   int p2g_sweep;   // 4 = three cells x nine node columns per warp; 3 = one cell x 27 nodes
-  int g2p_staged;  // 1 = particle channels staged with TMA bulk copies; 0 = plain loads
+  int g2p_staged;  // 0 = plain loads, 256-thread CTAs; 1 (= 64) | 64 | 128 | 256 = particle channels staged with TMA bulk copies, that many threads per CTA
 };
 Tuning &tuning() {
   static Tuning t = [] {
     Tuning d = {4, 1};
     if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = e[0] == '3' ? 3 : 4;
-    if (const char *e = getenv("ZPCB200_G2P_STAGED")) d.g2p_staged = e[0] == '0' ? 0 : 1;
+    if (const char *e = getenv("ZPCB200_G2P_STAGED")) d.g2p_staged = atoi(e);
     return d;
   }();
   return t;
@@ -873,7 +899,8 @@ Tuning &tuning() {
 extern "C" {
 
 int zpcb200_set_tuning(int p2g_sweep, int g2p_staged) {
-  if ((p2g_sweep != 3 && p2g_sweep != 4 && p2g_sweep != -1) || g2p_staged < -1 || g2p_staged > 1) return ZPCB200_E_BADARG;
+  if ((p2g_sweep != 3 && p2g_sweep != 4 && p2g_sweep != -1) || (g2p_staged != -1 && g2p_staged != 0 && g2p_staged != 1 && g2p_staged != 64 && g2p_staged != 128 && g2p_staged != 256))
+    return ZPCB200_E_BADARG;
   if (p2g_sweep != -1) tuning().p2g_sweep = p2g_sweep;
   if (g2p_staged != -1) tuning().g2p_staged = g2p_staged;
   return ZPCB200_OK;
@@ -931,8 +958,9 @@ int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids
     return ZPCB200_E_BADARG;
   const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
   const int staged = tuning().g2p_staged;
-  auto kern = staged ? g2p_binned_staged_kernel : g2p_binned_kernel;
-  kern<<<bins.binCapacity, G2P_NT, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
+  auto kern = staged == 128 ? g2p_binned_staged_kernel<128> : staged == 256 ? g2p_binned_staged_kernel<256> : staged ? g2p_binned_staged_kernel<64> : g2p_binned_kernel;
+  const int nt = staged == 128 ? 128 : staged == 256 ? 256 : staged ? 64 : G2P_NT;
+  kern<<<bins.binCapacity, nt, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
                                                               cache ? bins.cellOrder : nullptr, bins.cellStart, tb, g.tiles,
                                                               g.numChannels, g.dx, dt);
   ZPC_CHECK_LAUNCH();
