@@ -21,7 +21,7 @@ _i = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 
 
 def build_oracle(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("mpm_oracle.c", "prims_oracle.c", "oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("mpm_oracle.c", "prims_oracle.c", "sparse_oracle.c", "oracle.h")]
     if (not force and os.path.exists(ORACLE_SO)
             and all(os.path.getmtime(ORACLE_SO) >= os.path.getmtime(s) for s in srcs)):
         return ORACLE_SO
@@ -79,6 +79,76 @@ class Oracle:
         k = np.ascontiguousarray(key, np.int32)
         return int(self.lib.zo_table_query(_ptr(k), C.c_int(tab["table_size"]), _ptr(tab["keys"]),
                                            _ptr(tab["indices"])))
+
+    # ---- bht<i32,3,int,16> + SparseGrid<3,f32,8> accessors (sparse_oracle.c) ----
+    def bht_params(self):
+        hf = np.zeros(6, np.uint32)
+        self.lib.zo_bht_params(_ptr(hf))
+        return hf
+
+    def bht_table_size(self, expected):
+        self.lib.zo_bht_table_size.restype = C.c_int
+        return int(self.lib.zo_bht_table_size(C.c_int(expected)))
+
+    def bht_hash(self, hx, hy, key):
+        self.lib.zo_bht_hash.restype = C.c_uint32
+        k = np.ascontiguousarray(key, np.int32)
+        return int(self.lib.zo_bht_hash(C.c_uint32(int(hx)), C.c_uint32(int(hy)), _ptr(k)))
+
+    def bht_new(self, expected):
+        ts = self.bht_table_size(expected)
+        t = dict(table_size=ts, hf=self.bht_params(), keys16=np.empty((ts, 4), np.int32), indices=np.empty(ts, np.int32),
+                 status=np.empty(ts, np.int32), active_keys=np.zeros((max(ts, 1), 3), np.int32), cnt=np.zeros(1, np.int32))
+        self.lib.zo_bht_clear(C.c_int(ts), _ptr(t["keys16"]), _ptr(t["indices"]), _ptr(t["status"]), _ptr(t["cnt"]))
+        return t
+
+    def bht_insert(self, t, keys):
+        self.lib.zo_bht_insert.restype = C.c_int
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        out = np.empty(keys.shape[0], np.int32)
+        for i in range(keys.shape[0]):
+            out[i] = self.lib.zo_bht_insert(_ptr(keys[i]), C.c_int(t["table_size"]), _ptr(t["hf"]), _ptr(t["keys16"]),
+                                            _ptr(t["indices"]), _ptr(t["active_keys"]), _ptr(t["cnt"]))
+        return out
+
+    def bht_query(self, t, keys):
+        self.lib.zo_bht_query.restype = C.c_int
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        out = np.empty(keys.shape[0], np.int32)
+        for i in range(keys.shape[0]):
+            out[i] = self.lib.zo_bht_query(_ptr(keys[i]), C.c_int(t["table_size"]), _ptr(t["hf"]), _ptr(t["keys16"]),
+                                           _ptr(t["indices"]))
+        return out
+
+    def sg_partition_build(self, x, dx, expected):
+        self.lib.zo_sg_partition_build.restype = C.c_int
+        t = self.bht_new(expected)
+        x = np.ascontiguousarray(x, np.float32)
+        nb = self.lib.zo_sg_partition_build(C.c_int(x.shape[0]), _ptr(x), C.c_float(dx), C.c_int(t["table_size"]), _ptr(t["hf"]),
+                                            _ptr(t["keys16"]), _ptr(t["indices"]), _ptr(t["status"]), _ptr(t["active_keys"]),
+                                            _ptr(t["cnt"]))
+        t["nblocks"] = int(nb)
+        return t
+
+    def sg_value_or(self, t, grid, chn, coords, dflt):
+        self.lib.zo_sg_value_or.restype = C.c_float
+        coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
+        grid = np.ascontiguousarray(grid, np.float32)
+        nch = grid.shape[1]
+        out = np.empty(coords.shape[0], np.float32)
+        for i in range(coords.shape[0]):
+            out[i] = self.lib.zo_sg_value_or(C.c_int(chn), _ptr(coords[i]), C.c_float(dflt), C.c_int(t["table_size"]), _ptr(t["hf"]),
+                                             _ptr(t["keys16"]), _ptr(t["indices"]), _ptr(grid), C.c_int(nch))
+        return out
+
+    def sg_coords(self, t, m16, bno, cno):
+        m16 = np.ascontiguousarray(m16, np.float32)
+        ic = np.empty((len(bno), 3), np.int32)
+        wc = np.empty((len(bno), 3), np.float32)
+        for i in range(len(bno)):
+            self.lib.zo_sg_coords(C.c_int(int(bno[i])), C.c_int(int(cno[i])), _ptr(t["active_keys"]), _ptr(m16), _ptr(ic[i]),
+                                  _ptr(wc[i]))
+        return ic, wc
 
     # ---- per particle math ----
     def lame(self, E, nu):
@@ -213,6 +283,101 @@ class Ref:
 
     def max_threads(self):
         return int(self.lib.zpcref_max_threads())
+
+    class Bht:
+        """the reference's bht<int,3,int,16> on the host (container/Bht.hpp)"""
+
+        def __init__(self, ref, expected, handle=None):
+            self.L = ref.lib
+            self.L.zpcref_bht_create.restype = C.c_void_p
+            self.own = handle is None
+            self.h = C.c_void_p(self.L.zpcref_bht_create(C.c_int(expected))) if handle is None else handle
+
+        def close(self):
+            if self.h and self.own:
+                self.L.zpcref_bht_destroy(self.h)
+            self.h = None
+
+        def info(self):
+            info = np.zeros(3, np.int32)
+            hf = np.zeros(6, np.uint32)
+            self.L.zpcref_bht_info(self.h, _ptr(info), _ptr(hf))
+            return dict(table_size=int(info[0]), num_buckets=int(info[1]), cnt=int(info[2]), hf=hf)
+
+        def insert(self, keys):
+            keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+            out = np.empty(keys.shape[0], np.int32)
+            self.L.zpcref_bht_insert(self.h, _ptr(keys), C.c_int(keys.shape[0]), _ptr(out))
+            return out
+
+        def query(self, keys):
+            keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+            out = np.empty(keys.shape[0], np.int32)
+            self.L.zpcref_bht_query(self.h, _ptr(keys), C.c_int(keys.shape[0]), _ptr(out))
+            return out
+
+        def arrays(self):
+            i = self.info()
+            ts = i["table_size"]
+            k16 = np.empty((ts, 4), np.int32); idx = np.empty(ts, np.int32); st = np.empty(ts, np.int32)
+            ak = np.empty((max(i["cnt"], 1), 3), np.int32)
+            self.L.zpcref_bht_get(self.h, _ptr(k16), _ptr(idx), _ptr(st), _ptr(ak))
+            return dict(keys16=k16, indices=idx, status=st, active_keys=ak[: i["cnt"]], cnt=i["cnt"], table_size=ts, hf=i["hf"])
+
+        def load(self, keys16, indices, active_keys, cnt):
+            """overwrite the container's arrays (e.g. with a table built on the GPU); query() then runs the
+            reference's own BHTView::query over them"""
+            k = np.ascontiguousarray(keys16, np.int32); ix = np.ascontiguousarray(indices, np.int32)
+            ak = np.ascontiguousarray(active_keys, np.int32)
+            assert k.shape[0] == self.info()["table_size"]
+            self.L.zpcref_bht_load(self.h, _ptr(k), _ptr(ix), _ptr(ak), C.c_int(int(cnt)))
+
+    class SparseGrid:
+        """the reference's SparseGrid<3,f32,8> on the host (geometry/SparseGrid.hpp)"""
+
+        def __init__(self, ref, nblocks, nch):
+            self.ref, self.L = ref, ref.lib
+            self.L.zpcref_sg_create.restype = C.c_void_p
+            self.L.zpcref_sg_table.restype = C.c_void_p
+            self.h = C.c_void_p(self.L.zpcref_sg_create(C.c_int(nblocks), C.c_int(nch)))
+            self.table = Ref.Bht(ref, 0, handle=C.c_void_p(self.L.zpcref_sg_table(self.h)))
+            self.nch = nch
+
+        def close(self):
+            if self.h:
+                self.L.zpcref_sg_destroy(self.h)
+                self.h = None
+
+        def scale(self, s):
+            self.L.zpcref_sg_scale(self.h, C.c_float(s))
+
+        def translate(self, t):
+            t = np.ascontiguousarray(t, np.float32)
+            self.L.zpcref_sg_translate(self.h, _ptr(t))
+
+        def transform(self):
+            m = np.empty(16, np.float32)
+            self.L.zpcref_sg_get_transform(self.h, _ptr(m))
+            return m
+
+        def set_background(self, b):
+            self.L.zpcref_sg_set_background(self.h, C.c_float(b))
+
+        def load_grid(self, data):
+            data = np.ascontiguousarray(data, np.float32)
+            self.L.zpcref_sg_load_grid(self.h, _ptr(data), C.c_int(data.shape[0]))
+
+        def value_or(self, chn, coords, dflt):
+            coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)
+            out = np.empty(coords.shape[0], np.float32)
+            self.L.zpcref_sg_value_or(self.h, C.c_int(chn), _ptr(coords), C.c_int(coords.shape[0]), C.c_float(dflt), _ptr(out))
+            return out
+
+        def coords(self, bno, cno):
+            bno = np.ascontiguousarray(bno, np.int32); cno = np.ascontiguousarray(cno, np.int32)
+            ic = np.empty((bno.shape[0], 3), np.int32); wc = np.empty((bno.shape[0], 3), np.float32)
+            self.L.zpcref_sg_coords(self.h, _ptr(bno), _ptr(cno), C.c_int(bno.shape[0]), _ptr(ic), _ptr(wc))
+            return ic, wc
 
     class Mpm:
         def __init__(self, ref, n, dx, nthreads, expected_blocks):

@@ -276,3 +276,96 @@ void zpcref_stress_fixedcorotated(float volume, float E, float nu, const float *
 }
 int zpcref_max_threads() { return (int)std::thread::hardware_concurrency(); }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// bht<i32,3,int,16> and SparseGrid<3,f32,8> (container/Bht.hpp, geometry/SparseGrid.hpp) — the reference's own
+// containers and host views, used to pin oracle/sparse_oracle.c and to check tables built by the CUDA path.
+// ---------------------------------------------------------------------------------------------------------
+#include "zensim/container/Bht.hpp"
+#include "zensim/geometry/SparseGrid.hpp"
+
+namespace {
+  using RefBht = bht<int, 3, int, 16>;
+  using RefSg = SparseGrid<3, f32, 8>;
+  using IKey = vec<int, 3>;
+}  // namespace
+
+extern "C" {
+
+void *zpcref_bht_create(int expected) { return new RefBht{(size_t)expected, memsrc_e::host, -1}; }
+void zpcref_bht_destroy(void *h) { delete (RefBht *)h; }
+// info[0] = tableSize, info[1] = numBuckets, info[2] = cnt ; hf = {hf0.x, hf0.y, hf1.x, hf1.y, hf2.x, hf2.y}
+void zpcref_bht_info(void *h, int *info, unsigned *hf) {
+  auto &t = *(RefBht *)h;
+  info[0] = (int)t._tableSize;
+  info[1] = (int)(t._tableSize / RefBht::bucket_size);
+  info[2] = (int)t.size();
+  hf[0] = t._hf0._hashx; hf[1] = t._hf0._hashy; hf[2] = t._hf1._hashx; hf[3] = t._hf1._hashy;
+  hf[4] = t._hf2._hashx; hf[5] = t._hf2._hashy;
+}
+// sequential host insert (BHTView::insert, Bht.hpp:609-664); out[i] = returned index (-1 when already present)
+void zpcref_bht_insert(void *h, const int *keys, int n, int *out) {
+  auto tv = proxy<execspace_e::host>(*(RefBht *)h);
+  for (int i = 0; i < n; ++i) out[i] = tv.insert(IKey{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]});
+}
+void zpcref_bht_query(void *h, const int *keys, int n, int *out) {
+  auto tv = proxy<execspace_e::host>(*(const RefBht *)h);
+  for (int i = 0; i < n; ++i) out[i] = tv.query(IKey{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]});
+}
+// raw table arrays: keys16 = tableSize x 4 ints (storage_key_type, 16-byte slots), indices, status, activeKeys (cnt x 3)
+void zpcref_bht_get(void *h, int *keys16, int *indices, int *status, int *active_keys) {
+  auto &t = *(RefBht *)h;
+  static_assert(sizeof(typename RefBht::storage_key_type) == 16, "padded key slots");
+  std::memcpy(keys16, t._table.keys.data(), (size_t)t._tableSize * 16);
+  std::memcpy(indices, t._table.indices.data(), (size_t)t._tableSize * sizeof(int));
+  std::memcpy(status, t._table.status.data(), (size_t)t._tableSize * sizeof(int));
+  std::memcpy(active_keys, t._activeKeys.data(), (size_t)t.size() * 3 * sizeof(int));
+}
+// overwrite the container's arrays with externally built ones (e.g. downloaded from the GPU build): afterwards the
+// UNMODIFIED BHTView::query runs on them (zpcref_bht_query)
+void zpcref_bht_load(void *h, const int *keys16, const int *indices, const int *active_keys, int cnt) {
+  auto &t = *(RefBht *)h;
+  std::memcpy(t._table.keys.data(), keys16, (size_t)t._tableSize * 16);
+  std::memcpy(t._table.indices.data(), indices, (size_t)t._tableSize * sizeof(int));
+  std::memcpy(t._activeKeys.data(), active_keys, (size_t)cnt * 3 * sizeof(int));
+  t._cnt.setVal(cnt);
+}
+
+void *zpcref_sg_create(int nblocks, int nch) { return new RefSg{(size_t)nch, (size_t)nblocks, memsrc_e::host, -1}; }
+void zpcref_sg_destroy(void *h) { delete (RefSg *)h; }
+void *zpcref_sg_table(void *h) { return &((RefSg *)h)->_table; }
+void zpcref_sg_scale(void *h, float s) { ((RefSg *)h)->scale(s); }
+void zpcref_sg_translate(void *h, const float *t) { ((RefSg *)h)->translate(vec<float, 3>{t[0], t[1], t[2]}); }
+void zpcref_sg_get_transform(void *h, float *m16) {
+  auto m = ((RefSg *)h)->getIndexToWorldTransformation();
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) m16[4 * i + j] = m(i, j);
+}
+void zpcref_sg_set_background(void *h, float b) { ((RefSg *)h)->_background = b; }
+// grid = TileVector<f32,512>: tile b = [nch][512] floats
+void zpcref_sg_load_grid(void *h, const float *data, int nblocks) {
+  auto &g = *(RefSg *)h;
+  std::memcpy(g._grid.data(), data, (size_t)nblocks * g.numChannels() * 512 * sizeof(float));
+}
+// SparseGridView::valueOr(false_c, chn, indexCoord, default) (SparseGrid.hpp:345-351) at n integer coordinates
+void zpcref_sg_value_or(void *h, int chn, const int *coords, int n, float dflt, float *out) {
+  auto sv = proxy<execspace_e::host>(*(const RefSg *)h);
+  for (int i = 0; i < n; ++i) out[i] = sv.valueOr(false_c, chn, IKey{coords[3 * i], coords[3 * i + 1], coords[3 * i + 2]}, dflt);
+}
+// iCoord(bno, cno) / wCoord(bno, cno) (SparseGrid.hpp:407-416) for n (block, cell) pairs
+void zpcref_sg_coords(void *h, const int *bno, const int *cno, int n, int *icoord, float *wcoord) {
+  auto sv = proxy<execspace_e::host>(*(const RefSg *)h);
+  for (int i = 0; i < n; ++i) {
+    auto ic = sv.iCoord((size_t)bno[i], cno[i]);
+    auto wc = sv.wCoord((size_t)bno[i], cno[i]);
+    for (int d = 0; d < 3; ++d) { icoord[3 * i + d] = ic[d]; wcoord[3 * i + d] = wc[d]; }
+  }
+}
+void zpcref_sg_world_to_index(void *h, const float *x, int n, float *X) {
+  auto sv = proxy<execspace_e::host>(*(const RefSg *)h);
+  for (int i = 0; i < n; ++i) {
+    auto r = sv.worldToIndex(vec<float, 3>{x[3 * i], x[3 * i + 1], x[3 * i + 2]});
+    for (int d = 0; d < 3; ++d) X[3 * i + d] = r[d];
+  }
+}
+}
