@@ -97,6 +97,31 @@ typedef struct zpc_hashtable_view {
   int *cnt;
 } zpc_hashtable_view;
 
+/* BHTView<cuda, bht<i32,3,int,16>> — container/Bht.hpp:459-482, 758-763: buckets of 16 slots, three universal hashes
+ * (py_interop/HashUtils.hpp:7-47), keys stored as 16-byte padded vec3i slots (HashUtils.hpp:49-51) whose unused
+ * value is the byte pattern 0x3f (Bht.hpp:108-112,126-131).  hf = {hf0.x, hf0.y, hf1.x, hf1.y, hf2.x, hf2.y}. */
+typedef struct zpc_bht_view {
+  int *keys; /* tableSize x 4 ints */
+  int *indices, *status;
+  int *activeKeys; /* packed vec3i */
+  uint32_t tableSize, numBuckets;
+  int *cnt, *success;
+  uint32_t hf[6];
+} zpc_bht_view;
+
+/* SparseGridView<cuda, SparseGrid<3,f32,8>> — geometry/SparseGrid.hpp:239-243, 912-915: bht keyed by the block ORIGIN
+ * in cell coordinates (:305-309) + TileVector<f32,512> (tile b = [numChannels][512] floats, cell offset
+ * (x*8+y)*8+z, :275-283) + 4x4 index-to-world transform (row vector convention: world = (X,1) * M, :256-258) +
+ * background value. */
+typedef struct zpc_sparsegrid_view {
+  zpc_bht_view table;
+  float *grid;
+  size_t numBlocks; /* capacity in blocks */
+  int numChannels;
+  float transform[16]; /* row-major M[i][j] */
+  float background;
+} zpc_sparsegrid_view;
+
 /* The collocated grid of GridsView<cuda, Grids<f32,3,4>> — geometry/Structure.hpp:876-880: a
  * TileVector<f32,64> whose tile b holds block b as [numChannels][64] floats, channels
  * {m, v(3), rhs(3)} (simulation/mpm/Simulator.cpp:116), cell id (x<<4)|(y<<2)|z (:851-859). */
@@ -185,6 +210,36 @@ int zpcb200_p2g_apic_eos(zpc_particles_view pars, zpc_hashtable_view table, zpc_
                          float dt, zpc_equation_of_state model, zpc_stream_t stream);
 int zpcb200_g2p_apic_eos(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
                          float dt, zpc_stream_t stream);
+
+/* ---- SparseGrid<3,f32,8> variant of the path ----------------------------------------------- */
+/* Host helpers mirroring the bht constructor: the three universal hashes it draws from std::mt19937(2)
+ * (Bht.hpp:165-169, Bcht.hpp:39-43) and evaluateTableSize (Bht.hpp:154-158). */
+void zpcb200_bht_params(uint32_t hf_host[6]);
+size_t zpcb200_bht_table_size(size_t expected_entries);
+/* The MPM functors need an axis-aligned uniform transform without translation (world = X * dx): dx = transform[0].
+ * Otherwise ZPCB200_E_UNSUPPORTED. */
+/* Partition for particles on side-8 blocks: the ComputeSparsity / EnlargeSparsity convention of
+ * simulation/sparsity/SparsityOp.hpp:58-112 with blockLen 8; table keys = block origins.  Writes keys / indices /
+ * activeKeys / *cnt / *success so that the unmodified BHTView::query (Bht.hpp:666-700) resolves every active block;
+ * a key sits in the first of its three candidate buckets that has room (<= 15 keys, threshold 14).  Block numbering
+ * is deterministic: index = rank of the key in lexicographic order. */
+int zpcb200_sg_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, zpc_sparsegrid_view sg,
+                               int enlarge_lo, int enlarge_hi, int *overflow, zpc_stream_t stream);
+/* CleanGridBlocks / P2GTransfer<apic, FixedCorotated> / ComputeGridBlockVelocity / G2PTransfer<apic> on the SparseGrid
+ * (same arithmetic as the Grids<f32,3,4> entries above; channels {m, v(3), rhs(3)}), AoS particles in any order. */
+int zpcb200_sg_clean(zpc_sparsegrid_view sg, zpc_stream_t stream);
+int zpcb200_sg_p2g_apic_fcr(zpc_particles_view pars, zpc_sparsegrid_view sg, float dt, zpc_fixed_corotated model,
+                            zpc_stream_t stream);
+int zpcb200_sg_grid_update(zpc_sparsegrid_view sg, float dt, const float extf_host[3], int mode, float *maxVelSqr,
+                           zpc_stream_t stream);
+int zpcb200_sg_g2p_apic(zpc_particles_view pars, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream);
+/* SparseGridView::valueOr(false_c, chn, indexCoord, default) (SparseGrid.hpp:340-351) at n integer coordinates
+ * (coords = n x 3 ints on the device); absent blocks give dflt. */
+int zpcb200_sg_value_or(zpc_sparsegrid_view sg, int chn, const int *coords, size_t n, float dflt, float *out,
+                        zpc_stream_t stream);
+/* iCoord(bno, cno) and wCoord(bno, cno) (SparseGrid.hpp:407-416) for n (block, cell) pairs; either output may be NULL. */
+int zpcb200_sg_cell_coords(zpc_sparsegrid_view sg, const int *bno, const int *cno, size_t n, int *icoord,
+                           float *wcoord, zpc_stream_t stream);
 
 /* ---- binned (block-sorted AoSoA) fast path ------------------------------------------------- */
 /* Bins: particles sorted by home block (the block ComputeSparsity assigns, SparsityOp.hpp:68-79),

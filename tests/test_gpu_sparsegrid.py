@@ -1,0 +1,176 @@
+"""SparseGrid<3,f32,8> + bht<i32,3,int,16> variant of the path on the GPU (through the C ABI) against the oracle, and
+the GPU-built table against the reference's own BHTView::query."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from zpc_b200 import synth  # noqa: E402
+from tests.parity import GRID_RTOL, check_channels, check_particles  # noqa: E402
+
+E, NU = synth.MODEL["E"], synth.MODEL["nu"]
+
+
+def _build(P, expected=None):
+    from zpc_b200 import api
+    n = P["x"].shape[0]
+    pars = api.Particles(P)
+    sg = api.SparseGrid(7, expected or max(n // 16, 64))
+    sg.scale(P["dx"])
+    api.sg_partition_for_particles(api.vec3_port(pars.x), n, sg)
+    torch.cuda.synchronize()
+    assert sg.table.overflow.item() == 0 and sg.table.success.item() == 1
+    return pars, sg
+
+
+def _host_table(sg):
+    nb = sg.table.size()
+    return dict(keys16=sg.table.keys.cpu().numpy(), indices=sg.table.indices.cpu().numpy(), status=sg.table.status.cpu().numpy(),
+                active_keys=sg.table.active_keys[:nb].cpu().numpy(), nblocks=nb, table_size=sg.table.table_size,
+                hf=np.array(sg.table.hf, np.uint32))
+
+
+def _nodes(keys_cells, grid, side):
+    """flatten a block grid [nb, nch, side^3] into {packed global cell coord: [nch]}; keys_cells = block origins in cells"""
+    nb, nch, cells = grid.shape
+    c = np.arange(cells)
+    loc = np.stack([c // (side * side), (c // side) % side, c % side], 1)                  # [cells, 3]
+    co = (keys_cells[:, None, :] + loc[None, :, :]).reshape(-1, 3).astype(np.int64) + (1 << 20)
+    code = (co[:, 0] << 42) | (co[:, 1] << 21) | co[:, 2]
+    vals = grid.transpose(0, 2, 1).reshape(-1, nch)
+    o = np.argsort(code)
+    return code[o], vals[o]
+
+
+CASES = {
+    "cube8_shuffled": dict(s=8, G=32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=11),
+    "cube7_negative_coords": dict(s=7, G=16, jitter_F=0.05, jitter_C=0.5, shuffle_seed=3, origin_cells=-13),
+    "cube20": dict(s=20, G=32, jitter_F=0.03, jitter_C=0.3),
+}
+
+
+def _make(case):
+    kw = dict(CASES[case])
+    return synth.elastic_cube(kw.pop("s"), kw.pop("G"), **kw)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_bht_partition_matches_oracle_and_reference_query(oracle, case):
+    P = _make(case)
+    pars, sg = _build(P)
+    t = _host_table(sg)
+    nb, ak = t["nblocks"], t["active_keys"]
+    o = oracle.sg_partition_build(P["x"], P["dx"], sg.num_blocks)
+    assert o["table_size"] == t["table_size"] and np.array_equal(o["hf"], t["hf"])
+    ko = o["active_keys"][: o["nblocks"]]
+    order = np.lexsort((ko[:, 2], ko[:, 1], ko[:, 0]))
+    assert nb == o["nblocks"]
+    assert np.array_equal(ak, ko[order])                      # same block set; ours numbered in lexicographic key order
+    assert (ak % 8 == 0).all()
+    # the restated query and (where the reference library travelled) the reference's own BHTView::query resolve it
+    assert np.array_equal(oracle.bht_query(t, ak), np.arange(nb))
+    assert (oracle.bht_query(t, ak + 3) == -1).all()
+    # table invariants of the reference: occupied slots only in positions 0..14 of a bucket, filled contiguously
+    occ = (t["keys16"][:, 0] != 0x3F3F3F3F).reshape(-1, 16)
+    assert not occ[:, 15].any()
+    assert (np.diff(occ.astype(np.int8), axis=1) <= 0).all()
+    assert occ.sum() == nb and (t["status"] == -1).all()
+    from oracle.pyoracle import Ref
+    if Ref.available():
+        r = Ref()
+        rt = Ref.Bht(r, sg.num_blocks)
+        assert rt.info()["table_size"] == t["table_size"]
+        rt.load(t["keys16"], t["indices"], ak, nb)
+        assert np.array_equal(rt.query(ak), np.arange(nb))
+        assert (rt.query(ak + 8 * 1000) == -1).all()
+        rt.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", list(CASES))
+def test_sparsegrid_substep_matches_oracle_node_for_node(oracle, case, mode):
+    """clean -> P2G -> grid update -> G2P on side-8 blocks; the oracle runs the reference's functors on the legacy
+    side-4 grid: results are compared per grid NODE (global cell coordinate) and per particle."""
+    from zpc_b200 import api
+    P = _make(case)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, sg = _build(P)
+    t = _host_table(sg)
+    nb = t["nblocks"]
+    api.sg_clean(sg)
+    model = api.model_fcr(P["volume"], E, NU)
+    api.sg_p2g_transfer(pars, sg, synth.DT, model)
+    g1 = sg.grid[:nb].cpu().numpy()
+    # oracle on the legacy table
+    tab = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    Po = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in P.items()}
+    o1 = oracle.p2g(Po, tab, dx, synth.DT, E, NU, P["volume"])
+    code_o, val_o = _nodes(tab["active_keys"] * 4, o1, 4)
+    code_s, val_s = _nodes(t["active_keys"], g1, 8)
+    pos = np.searchsorted(code_s, code_o)
+    assert (pos < code_s.shape[0]).all() and np.array_equal(code_s[pos], code_o)      # every legacy node exists on side 8
+    check_channels(val_s[pos], val_o, 1, "sg p2g", GRID_RTOL, strict_frac=0.99)
+    rest = np.ones(code_s.shape[0], bool)
+    rest[pos] = False
+    assert not val_s[rest].any()                                                      # nothing outside the stencil cover
+    mx = torch.zeros(1, device="cuda")
+    api.sg_compute_grid_velocity(sg, synth.DT, (0.0, synth.GRAVITY, 0.0), mode, mx)
+    o2 = o1.copy()
+    omx = oracle.grid_update(o2, synth.DT, (0.0, synth.GRAVITY, 0.0), mode)
+    _, val_o2 = _nodes(tab["active_keys"] * 4, o2, 4)
+    _, val_s2 = _nodes(t["active_keys"], sg.grid[:nb].cpu().numpy(), 8)
+    check_channels(val_s2[pos][:, 1:4], val_o2[:, 1:4], 1, "sg grid v")
+    assert abs(mx.item() - omx) <= 1e-5 * max(omx, 1e-30)
+    api.sg_g2p_transfer(pars, sg, synth.DT)
+    oracle.g2p(Po, tab, o2, dx, synth.DT)
+    check_particles(pars.to_host(), Po, dx, "sg g2p")
+
+
+def test_sparsegrid_accessors_match_oracle(oracle):
+    from zpc_b200 import api
+    P = _make("cube8_shuffled")
+    pars, sg = _build(P)
+    sg.translate([0.25, -0.5, 1.0])      # accessors honour the full transform (the MPM functors refuse it)
+    t = _host_table(sg)
+    nb = t["nblocks"]
+    rs = np.random.RandomState(2)
+    sg.grid[:nb] = torch.from_numpy(rs.uniform(-1, 1, (nb, 7, 512)).astype(np.float32)).cuda()
+    grid = sg.grid[:nb].cpu().numpy()
+    ak = t["active_keys"]
+    inside = ak[rs.randint(0, nb, 500)] + rs.randint(0, 8, (500, 3)).astype(np.int32)
+    outside = rs.randint(-300, 300, (500, 3)).astype(np.int32)
+    coords = np.ascontiguousarray(np.concatenate([inside, outside]))
+    for chn in (0, 6):
+        got = api.sg_value_or(sg, chn, torch.from_numpy(coords).cuda(), -3.5).cpu().numpy()
+        assert np.array_equal(got, oracle.sg_value_or(t, grid, chn, coords, -3.5))
+    bno = rs.randint(0, nb, 400).astype(np.int32); cno = rs.randint(0, 512, 400).astype(np.int32)
+    ic, wc = api.sg_cell_coords(sg, torch.from_numpy(bno).cuda(), torch.from_numpy(cno).cuda())
+    ic_o, wc_o = oracle.sg_coords(t, np.array(sg.transform, np.float32), bno, cno)
+    assert np.array_equal(ic.cpu().numpy(), ic_o)
+    assert np.array_equal(wc.cpu().numpy(), wc_o)               # same expression order, no contraction: bit-exact
+    # the MPM functors need the plain world = X * dx transform
+    rc = api.lib().zpcb200_sg_clean(sg.view(), None)
+    assert rc == 0
+    import ctypes as C
+    rc = api.lib().zpcb200_sg_g2p_apic(pars.view(), sg.view(), C.c_float(1e-4), None)
+    assert rc == -3                                             # ZPCB200_E_UNSUPPORTED
+
+
+def test_sparsegrid_empty_and_overflow_flags():
+    from zpc_b200 import api
+    sg = api.SparseGrid(7, 64)
+    sg.scale(1.0 / 32)
+    x = torch.zeros(0, 3, device="cuda")
+    api.sg_partition_for_particles(api.vec3_port(x), 0, sg)
+    assert sg.table.size() == 0 and sg.table.success.item() == 1
+    # far too small a table: flags, no exception, no out-of-bounds write
+    P = synth.elastic_cube(24, 32)
+    pars = api.Particles(P)
+    small = api.SparseGrid(7, 8)
+    small.scale(P["dx"])
+    guard = small.table.keys.clone()
+    api.sg_partition_for_particles(api.vec3_port(pars.x), pars.n, small)
+    torch.cuda.synchronize()
+    assert small.table.overflow.item() == 1 and small.table.success.item() == 0
+    assert guard.shape == small.table.keys.shape

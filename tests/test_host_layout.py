@@ -63,3 +63,27 @@ def test_table_sizing_matches_reference_rule():
     from zpc_b200 import api
     for n, ts in ((1, 16), (2, 32), (3, 64), (1000, 16384), (1024, 16384), (1025, 32768)):
         assert api.next_2pow(n) * 16 == ts      # HashTable.hpp:87-90: next_2pow(entries) * reserve_ratio_v(16)
+
+
+def test_bht_host_helpers_match_oracle(oracle):
+    """zpcb200_bht_params / zpcb200_bht_table_size (host functions of the C ABI) against the pinned restatement"""
+    import ctypes as C
+    from zpc_b200 import api
+    hf = (C.c_uint32 * 6)()
+    api.lib().zpcb200_bht_params(hf)
+    assert [int(v) for v in hf] == [int(v) for v in oracle.bht_params()]
+    for n in (0, 1, 7, 100, 128, 129, 4096, 100000, 1 << 20):
+        assert int(api.lib().zpcb200_bht_table_size(n)) == oracle.bht_table_size(n), n
+
+
+def test_sparsegrid_host_transform_matches_reference(ref):
+    """SparseGrid.scale / translate compose the index-to-world matrix like the reference's Transform"""
+    from oracle.pyoracle import Ref
+    from zpc_b200 import api
+    sg = api.SparseGrid(4, 16, device="cpu")
+    r = Ref.SparseGrid(ref, 16, 4)
+    for obj in (sg, r):
+        obj.scale(0.125)
+        obj.translate([0.5, -1.0, 2.0])
+    assert np.allclose(np.array(sg.transform, np.float32), r.transform(), rtol=0, atol=0)
+    r.close()

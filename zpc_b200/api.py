@@ -63,6 +63,17 @@ class zpc_collider(C.Structure):
     _fields_ = [("geometry", C.c_int), ("type", C.c_int), ("origin", C.c_float * 3), ("normal", C.c_float * 3)]
 
 
+class zpc_bht_view(C.Structure):
+    _fields_ = [("keys", C.c_void_p), ("indices", C.c_void_p), ("status", C.c_void_p), ("activeKeys", C.c_void_p),
+                ("tableSize", C.c_uint32), ("numBuckets", C.c_uint32), ("cnt", C.c_void_p), ("success", C.c_void_p),
+                ("hf", C.c_uint32 * 6)]
+
+
+class zpc_sparsegrid_view(C.Structure):
+    _fields_ = [("table", zpc_bht_view), ("grid", C.c_void_p), ("numBlocks", C.c_size_t), ("numChannels", C.c_int),
+                ("transform", C.c_float * 16), ("background", C.c_float)]
+
+
 class zpc_bins_view(C.Structure):
     _fields_ = [("pars", zpc_tilevector_view), ("binStart", C.c_void_p), ("binKey", C.c_void_p),
                 ("numBins", C.c_void_p), ("binCapacity", C.c_int), ("cellOrder", C.c_void_p),
@@ -82,6 +93,8 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.zpcb200_version.restype = C.c_char_p
         _lib.policy__b200.restype = C.c_void_p
+        _lib.zpcb200_bht_table_size.restype = C.c_size_t
+        _lib.zpcb200_bht_table_size.argtypes = [C.c_size_t]
     return _lib
 
 
@@ -269,6 +282,107 @@ class Grids:
 
     def view(self):
         return zpc_grids_view(self.tiles.data_ptr(), self.num_blocks, self.nch, self.dx)
+
+
+class Bht:
+    """bht<i32,3,int,16> (container/Bht.hpp:16-272): buckets of 16, three universal hashes from std::mt19937(2),
+    tableSize = evaluateTableSize(expected) (:154-158), 16-byte key slots."""
+
+    def __init__(self, expected_entries, device="cuda"):
+        self.table_size = int(lib().zpcb200_bht_table_size(int(expected_entries)))
+        ts = max(self.table_size, 1)
+        hf = (C.c_uint32 * 6)()
+        lib().zpcb200_bht_params(hf)
+        self.hf = [int(v) for v in hf]
+        self.keys = torch.empty(ts, 4, dtype=torch.int32, device=device)
+        self.indices = torch.empty(ts, dtype=torch.int32, device=device)
+        self.status = torch.empty(ts, dtype=torch.int32, device=device)
+        self.active_keys = torch.zeros(ts, 3, dtype=torch.int32, device=device)
+        self.cnt = torch.zeros(1, dtype=torch.int32, device=device)
+        self.success = torch.ones(1, dtype=torch.int32, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def view(self):
+        return zpc_bht_view(self.keys.data_ptr(), self.indices.data_ptr(), self.status.data_ptr(), self.active_keys.data_ptr(),
+                            self.table_size, self.table_size // 16, self.cnt.data_ptr(), self.success.data_ptr(),
+                            (C.c_uint32 * 6)(*self.hf))
+
+    def size(self):
+        return int(self.cnt.item())
+
+
+class SparseGrid:
+    """SparseGrid<3,f32,8> (geometry/SparseGrid.hpp:16-188): bht keyed by block origins + TileVector<f32,512> + 4x4
+    index-to-world transform (row-vector convention) + background value."""
+
+    def __init__(self, num_channels, num_blocks, device="cuda"):
+        self.nch, self.num_blocks = int(num_channels), int(num_blocks)
+        self.table = Bht(num_blocks, device)
+        self.grid = torch.zeros(max(self.num_blocks, 1), self.nch, 512, dtype=torch.float32, device=device)
+        self.transform = [1.0 if i % 5 == 0 else 0.0 for i in range(16)]
+        self.background = 0.0
+
+    def scale(self, s):
+        """SparseGrid::scale -> Transform::preScale (uniform)"""
+        import numpy as np
+        m = np.array(self.transform, np.float32).reshape(4, 4)
+        sm = np.eye(4, dtype=np.float32)
+        sm[0, 0] = sm[1, 1] = sm[2, 2] = np.float32(s)
+        self.transform = [float(v) for v in (sm @ m).reshape(-1)]
+
+    def translate(self, t):
+        """SparseGrid::translate -> Transform::postTranslate"""
+        for d in range(3):
+            self.transform[12 + d] += float(t[d])
+
+    def view(self):
+        return zpc_sparsegrid_view(self.table.view(), self.grid.data_ptr(), self.num_blocks, self.nch,
+                                   (C.c_float * 16)(*self.transform), self.background)
+
+    def num_active_blocks(self):
+        return self.table.size()
+
+
+def sg_partition_for_particles(x_port, n, sg, stream=None, enlarge=(0, 2)):
+    _two_phase(lib().zpcb200_sg_partition_build, (x_port, C.c_size_t(n), sg.view(), C.c_int(enlarge[0]), C.c_int(enlarge[1]),
+                                                  C.c_void_p(sg.table.overflow.data_ptr())), (), stream)
+
+
+def sg_clean(sg, stream=None):
+    _check(lib().zpcb200_sg_clean(sg.view(), _stream_ptr(stream)), "sg_clean")
+
+
+def sg_p2g_transfer(pars, sg, dt, model, stream=None):
+    _check(lib().zpcb200_sg_p2g_apic_fcr(pars.view(), sg.view(), C.c_float(dt), model, _stream_ptr(stream)), "sg_p2g")
+
+
+def sg_compute_grid_velocity(sg, dt, extf, mode, max_vel_sqr, stream=None):
+    e = (C.c_float * 3)(*[float(v) for v in extf])
+    _check(lib().zpcb200_sg_grid_update(sg.view(), C.c_float(dt), e, C.c_int(mode), C.c_void_p(max_vel_sqr.data_ptr()),
+                                        _stream_ptr(stream)), "sg_grid_update")
+
+
+def sg_g2p_transfer(pars, sg, dt, stream=None):
+    _check(lib().zpcb200_sg_g2p_apic(pars.view(), sg.view(), C.c_float(dt), _stream_ptr(stream)), "sg_g2p")
+
+
+def sg_value_or(sg, chn, coords, dflt, stream=None):
+    """SparseGridView::valueOr(false_c, chn, coord, default) at an [n,3] int32 device tensor of index coordinates"""
+    assert coords.is_cuda and coords.dtype == torch.int32 and coords.is_contiguous()
+    out = torch.empty(coords.shape[0], dtype=torch.float32, device=coords.device)
+    _check(lib().zpcb200_sg_value_or(sg.view(), C.c_int(chn), C.c_void_p(coords.data_ptr()), C.c_size_t(coords.shape[0]),
+                                     C.c_float(dflt), C.c_void_p(out.data_ptr()), _stream_ptr(stream)), "sg_value_or")
+    return out
+
+
+def sg_cell_coords(sg, bno, cno, stream=None):
+    """(iCoord, wCoord) of n (block, cell) pairs (int32 device tensors)"""
+    n = bno.shape[0]
+    ic = torch.empty(n, 3, dtype=torch.int32, device=bno.device)
+    wc = torch.empty(n, 3, dtype=torch.float32, device=bno.device)
+    _check(lib().zpcb200_sg_cell_coords(sg.view(), C.c_void_p(bno.data_ptr()), C.c_void_p(cno.data_ptr()), C.c_size_t(n),
+                                        C.c_void_p(ic.data_ptr()), C.c_void_p(wc.data_ptr()), _stream_ptr(stream)), "sg_cell_coords")
+    return ic, wc
 
 
 class Particles:

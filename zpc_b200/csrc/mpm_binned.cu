@@ -379,7 +379,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
 #pragma unroll
     for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
-    zpcp::p2g_scatter_particle(pos, vel, mass, C, F, tb, tiles, 7, dx, dt, volume, mu, lam);
+    zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam);
   }
   if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
 }
@@ -438,7 +438,7 @@ __device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int 
       G[r + 6] = ar.w[0][0] * pz[0][r] + ar.w[0][1] * pz[1][r] + ar.w[0][2] * pz[2][r];
     }
   } else {
-    zpcp::g2p_gather_particle(ar, tb, tiles, nch, vel, G);
+    zpcp::g2p_gather_particle(ar, zpcp::LegacyGrid{tb}, tiles, nch, vel, G);
   }
   // C[r + 3e] = D_inv * sum W v_r (o_e dx - local_e) = D_inv * (dx G_re - local_e v_r)
 #pragma unroll

@@ -9,6 +9,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "../../include/zpcb200.h"
+
 namespace zpcm {
 
 template <int AXIS>
@@ -230,6 +232,32 @@ __device__ __forceinline__ int table_query(int kx, int ky, int kz, int table_siz
     if (k[0] == kx && k[1] == ky && k[2] == kz) return ix;
     slot = (slot + 127) % table_size;
   }
+}
+
+// ---- bht<i32,3,int,16> lookups (container/Bht.hpp) -------------------------------------------------
+// universal_hash over a vec3i key (py_interop/HashUtils.hpp:22-43): sub(k) = ((hashx ^ k) + hashy) % 4294967291 in
+// 32-bit unsigned arithmetic, combined with the 32-bit hash_combine
+__host__ __device__ __forceinline__ unsigned bht_hash(unsigned hx, unsigned hy, int kx, int ky, int kz) {
+  const unsigned P = 4294967291u;
+  unsigned h = ((hx ^ (unsigned)kx) + hy) % P;
+  h ^= (((hx ^ (unsigned)ky) + hy) % P) + 0x9e3779b9u + (h << 6) + (h >> 2);
+  h ^= (((hx ^ (unsigned)kz) + hy) % P) + 0x9e3779b9u + (h << 6) + (h >> 2);
+  return h;
+}
+// BHTView::query (Bht.hpp:666-700): the 16 slots of the hf0 bucket, then hf1's, then hf2's
+__device__ __forceinline__ int bht_query(int kx, int ky, int kz, const zpc_bht_view &tb) {
+  if (tb.numBuckets == 0) return -1;
+#pragma unroll 1
+  for (int it = 0; it < 3; ++it) {
+    const unsigned b = bht_hash(tb.hf[2 * it], tb.hf[2 * it + 1], kx, ky, kz) % tb.numBuckets * 16u;
+    const int4 *k = reinterpret_cast<const int4 *>(tb.keys) + b;
+#pragma unroll 4
+    for (int s = 0; s < 16; ++s) {
+      const int4 c = k[s];
+      if (c.x == kx && c.y == ky && c.z == kz) return tb.indices[b + s];
+    }
+  }
+  return -1;
 }
 
 }  // namespace zpcm

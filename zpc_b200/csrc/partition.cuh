@@ -1,0 +1,149 @@
+// Shared pieces of the hash-grid partition build (simulation/sparsity/SparsityOp.hpp:41-112 restated for the GPU):
+// block codes, the scratch open-addressing set with its append list, the particle marking pass (block side 2^S) and
+// EnlargeSparsity.  Used by the legacy HashTable build (mpm.cu) and the bht / SparseGrid build (sparsegrid.cu); each
+// finishes with its own placement kernel.
+#pragma once
+#include <climits>
+
+#include "common.cuh"
+#include "mpm_math.cuh"
+
+namespace {
+
+// ---- partition build --------------------------------------------------------------------------------
+constexpr unsigned CODE_EMPTY = 0xffffffffu;
+constexpr int CODE_BIAS = 512;  // block coordinates in [-512, 511] per axis (|cell coord| < 2048)
+__device__ __forceinline__ bool code_pack(int bx, int by, int bz, unsigned &code) {
+  const unsigned ux = (unsigned)(bx + CODE_BIAS), uy = (unsigned)(by + CODE_BIAS), uz = (unsigned)(bz + CODE_BIAS);
+  code = (ux << 20) | (uy << 10) | uz;
+  return (ux | uy | uz) < 1024u;
+}
+__device__ __forceinline__ void code_unpack(unsigned code, int &bx, int &by, int &bz) {
+  bx = (int)(code >> 20) - CODE_BIAS;
+  by = (int)((code >> 10) & 1023u) - CODE_BIAS;
+  bz = (int)(code & 1023u) - CODE_BIAS;
+}
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+// insert code into the scratch set; the first inserter appends it to list
+__device__ __forceinline__ void set_insert(unsigned code, unsigned *set, unsigned set_mask, unsigned *list,
+                                           int list_cap, int *list_cnt, int *overflow) {
+  unsigned slot = mix32(code) & set_mask;
+  for (unsigned probes = 0; probes <= set_mask; ++probes) {
+    unsigned cur = set[slot];
+    if (cur == code) return;
+    if (cur == CODE_EMPTY) {
+      cur = atomicCAS(&set[slot], CODE_EMPTY, code);
+      if (cur == CODE_EMPTY) {
+        const int i = atomicAdd(list_cnt, 1);
+        if (i < list_cap) list[i] = code;
+        else if (overflow) *overflow = 1;
+        return;
+      }
+      if (cur == code) return;
+    }
+    slot = (slot + 1) & set_mask;
+  }
+  if (overflow) *overflow = 1;
+}
+
+// scratch of the partition build: the code set, the code list (padded with CODE_EMPTY so that it sorts to the end), counters
+__global__ void part_clear_scratch_kernel(unsigned *set, unsigned set_n, unsigned *list, int list_cap, int *counters) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = t0; i < set_n; i += stride) set[i] = CODE_EMPTY;
+  for (size_t i = t0; i < (size_t)list_cap; i += stride) list[i] = CODE_EMPTY;
+  if (t0 < 4) counters[t0] = 0;
+}
+
+template <int S>  // block side 2^S
+__global__ void part_mark_kernel(PortAcc<const float> x, size_t n, float dxinv, unsigned *set, unsigned set_mask,
+                                 unsigned *list, int list_cap, int *list_cnt, int *overflow) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+  for (size_t i0 = first; i0 < n; i0 += stride) {  // warp-uniform trip count
+    const size_t i = i0 + (threadIdx.x & 31);
+    unsigned code = CODE_EMPTY;
+    if (i < n) {
+      const int bx = zpcm::sparsity_coord(x.at(i, 0), dxinv) >> S;
+      const int by = zpcm::sparsity_coord(x.at(i, 1), dxinv) >> S;
+      const int bz = zpcm::sparsity_coord(x.at(i, 2), dxinv) >> S;
+      if (!code_pack(bx, by, bz, code)) { code = CODE_EMPTY; if (overflow) *overflow = 1; }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, code);
+    if (code != CODE_EMPTY && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+      set_insert(code, set, set_mask, list, list_cap, list_cnt, overflow);
+  }
+}
+// EnlargeSparsity{lo, hi} (SparsityOp.hpp:88-112): every block present after the particle pass adds its
+// neighbours at offsets [lo, hi)^3; the reference's substep uses {0, 2}
+__global__ void part_enlarge_kernel(unsigned *set, unsigned set_mask, unsigned *list, int list_cap,
+                                    const int *cnt_before, int *list_cnt, int lo, int hi, int *overflow) {
+  const int n0 = min(*cnt_before, list_cap);
+  const int w = hi - lo, w3 = w * w * w;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)n0 * w3; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / w3), o = (int)(t % w3);
+    const int ox = lo + o / (w * w), oy = lo + (o / w) % w, oz = lo + o % w;
+    if ((ox | oy | oz) == 0) continue;
+    int bx, by, bz;
+    code_unpack(list[i], bx, by, bz);
+    unsigned code;
+    if (code_pack(bx + ox, by + oy, bz + oz, code))
+      set_insert(code, set, set_mask, list, list_cap, list_cnt, overflow);
+    else if (overflow) *overflow = 1;
+  }
+}
+__global__ void part_snapshot_kernel(const int *src, int *dst) { *dst = *src; }
+
+
+// sizes of the scratch the shared passes need; the sort scratch follows at off_sort
+struct PartScratch {
+  size_t set_n, off_set, off_list, off_sorted, off_sort, sort_bytes, need;
+  int list_cap;
+};
+inline int part_scratch_layout(size_t table_size, PartScratch &L) {
+  L.set_n = 1;
+  while (L.set_n < table_size / 2) L.set_n <<= 1;
+  if (L.set_n < 1024) L.set_n = 1024;
+  L.list_cap = table_size / 8 > 64 ? (int)(table_size / 8) : 64;
+  L.sort_bytes = 0;
+  zpc_port none = {nullptr, 0, 0, 0, 1};
+  const int rc = zpcb200_radix_sort_u32(nullptr, &L.sort_bytes, none, none, (size_t)L.list_cap, 0, 30, nullptr);
+  if (rc) return rc;
+  L.off_set = 256;
+  L.off_list = zpc_align_up(L.off_set + 4 * L.set_n, 256);
+  L.off_sorted = zpc_align_up(L.off_list + 4 * (size_t)L.list_cap, 256);
+  L.off_sort = zpc_align_up(L.off_sorted + 4 * (size_t)L.list_cap, 256);
+  L.need = L.off_sort + L.sort_bytes;
+  return ZPCB200_OK;
+}
+// mark -> enlarge -> sort of the block codes; leaves the sorted codes at temp + off_sorted and their number in
+// counters[0] (= (int*)temp); the caller has already cleared its table and launches its placement kernel afterwards
+template <int S>
+int part_collect_sorted(char *t, const PartScratch &L, zpc_port x, size_t n, float dx, int enlarge_lo, int enlarge_hi, int *overflow,
+                        cudaStream_t s) {
+  int *counters = (int *)t;  // [0] list count, [1] count before enlarge
+  unsigned *set = (unsigned *)(t + L.off_set), *list = (unsigned *)(t + L.off_list), *sorted = (unsigned *)(t + L.off_sorted);
+  const int G = ZPC_SM_COUNT * 8;
+  part_clear_scratch_kernel<<<G, 256, 0, s>>>(set, (unsigned)L.set_n, list, L.list_cap, counters);
+  ZPC_CHECK_LAUNCH();
+  if (n) {
+    part_mark_kernel<S><<<G, 256, 0, s>>>(PortAcc<const float>(x), n, 1.0f / dx, set, (unsigned)(L.set_n - 1), list, L.list_cap,
+                                           counters, overflow);
+    ZPC_CHECK_LAUNCH();
+  }
+  part_snapshot_kernel<<<1, 1, 0, s>>>(counters, counters + 1);
+  ZPC_CHECK_LAUNCH();
+  if (enlarge_hi - enlarge_lo > 0) {
+    part_enlarge_kernel<<<G, 256, 0, s>>>(set, (unsigned)(L.set_n - 1), list, L.list_cap, counters + 1, counters, enlarge_lo,
+                                           enlarge_hi, overflow);
+    ZPC_CHECK_LAUNCH();
+  }
+  zpc_port pl = {list, 0, 0, 0, 1}, ps = {sorted, 0, 0, 0, 1};
+  size_t sb = L.sort_bytes;
+  return zpcb200_radix_sort_u32(t + L.off_sort, &sb, pl, ps, (size_t)L.list_cap, 0, 30, (zpc_stream_t)s);
+}
+
+}  // namespace

@@ -1,0 +1,230 @@
+// SparseGrid<3,f32,8> variant of the MPM path: bht<i32,3,int,16> partition build readable by the
+// reference's unmodified BHTView::query, the transfer / grid functors on side-8 blocks, and the SparseGridView
+// accessors (valueOr, iCoord, wCoord) as bulk operations.
+//
+//   table   : container/Bht.hpp — buckets of 16 slots, three universal hashes drawn from std::mt19937(2) (:165-169),
+//             16-byte padded key slots whose empty value is the byte pattern 0x3f (:108-112), keys = block ORIGINS in
+//             cell coordinates (geometry/SparseGrid.hpp:305-309).
+//   grid    : TileVector<f32,512>, tile b = [nch][512], cell offset (x*8+y)*8+z (SparseGrid.hpp:275-283).
+//   kernels : the same per-particle scatter / gather as the Grids<f32,3,4> drop-in path (mpm_kernels.cuh), instantiated
+//             for zpcp::SparseGrid8.
+#include <climits>
+
+#include "common.cuh"
+#include "mpm_kernels.cuh"
+#include "mpm_math.cuh"
+#include "mpm_particle.cuh"
+#include "partition.cuh"
+
+namespace {
+
+constexpr int KEY_EMPTY = 0x3f3f3f3f;
+
+__global__ void sg_clear_table_kernel(zpc_bht_view tb) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int4 *k = reinterpret_cast<int4 *>(tb.keys);
+  for (size_t i = t0; i < (size_t)tb.tableSize; i += stride) {
+    k[i] = make_int4(KEY_EMPTY, KEY_EMPTY, KEY_EMPTY, KEY_EMPTY);  // Table::reset: every byte of the slot is 0x3f
+    tb.indices[i] = -1;
+    tb.status[i] = -1;
+  }
+}
+
+// key i (rank order) goes to the first of its three candidate buckets with room: slots 0..14 of a bucket are claimed
+// in order with a CAS on the index array (the reference's insert never uses slot 15: threshold = 14, Bht.hpp:41)
+__global__ void sg_place_kernel(const unsigned *sorted, const int *list_cnt, int list_cap, zpc_bht_view tb, int *overflow) {
+  const int n = min(*list_cnt, list_cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int bx, by, bz;
+    code_unpack(sorted[i], bx, by, bz);
+    const int kx = bx * 8, ky = by * 8, kz = bz * 8;
+    bool placed = false;
+    for (int it = 0; it < 3 && !placed; ++it) {
+      const unsigned b = zpcm::bht_hash(tb.hf[2 * it], tb.hf[2 * it + 1], kx, ky, kz) % tb.numBuckets * 16u;
+      for (int s = 0; s < 15; ++s) {
+        if (tb.indices[b + s] != -1) continue;
+        if (atomicCAS(&tb.indices[b + s], -1, i) == -1) {
+          reinterpret_cast<int4 *>(tb.keys)[b + s] = make_int4(kx, ky, kz, KEY_EMPTY);
+          placed = true;
+          break;
+        }
+      }
+    }
+    if (!placed) {
+      if (overflow) *overflow = 1;
+      if (tb.success) *tb.success = 0;
+    }
+    tb.activeKeys[3 * (size_t)i] = kx; tb.activeKeys[3 * (size_t)i + 1] = ky; tb.activeKeys[3 * (size_t)i + 2] = kz;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *tb.cnt = n;
+    if ((unsigned)n + 20u >= tb.tableSize) {  // the reference's "proximity" failure (Bht.hpp:522-527)
+      if (overflow) *overflow = 1;
+      if (tb.success) *tb.success = 0;
+    }
+  }
+}
+
+__global__ void sg_set_success_kernel(int *success) { *success = 1; }
+
+__global__ void sg_value_or_kernel(zpc_sparsegrid_view sg, int chn, const int *__restrict__ coords, size_t n, float dflt,
+                                   float *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
+  const int cx = x & 7, cy = y & 7, cz = z & 7;  // decomposeCoord (SparseGrid.hpp:305-309)
+  const int bno = zpcm::bht_query(x - cx, y - cy, z - cz, sg.table);
+  out[i] = bno == -1 ? dflt : sg.grid[((size_t)bno * sg.numChannels + chn) * 512 + ((cx * 8 + cy) * 8 + cz)];
+}
+
+__global__ void sg_cell_coords_kernel(zpc_sparsegrid_view sg, const int *__restrict__ bno, const int *__restrict__ cno, size_t n,
+                                      int *icoord, float *wcoord) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = bno[i], c = cno[i];
+  const int ic[3] = {sg.table.activeKeys[3 * (size_t)b] + ((c >> 6) & 7), sg.table.activeKeys[3 * (size_t)b + 1] + ((c >> 3) & 7),
+                     sg.table.activeKeys[3 * (size_t)b + 2] + (c & 7)};
+  if (icoord) { icoord[3 * i] = ic[0]; icoord[3 * i + 1] = ic[1]; icoord[3 * i + 2] = ic[2]; }
+  if (wcoord) {
+    const float *M = sg.transform;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {  // (X, 1) * M, accumulated in the reference's order (no contraction)
+      float s = __fmul_rn((float)ic[0], M[j]);
+      s = __fadd_rn(s, __fmul_rn((float)ic[1], M[4 + j]));
+      s = __fadd_rn(s, __fmul_rn((float)ic[2], M[8 + j]));
+      wcoord[3 * i + j] = __fadd_rn(s, M[12 + j]);
+    }
+  }
+}
+
+// dx of an axis-aligned uniform transform without translation; false otherwise
+bool sg_uniform_dx(const zpc_sparsegrid_view &sg, float &dx) {
+  const float *M = sg.transform;
+  dx = M[0];
+  if (!(dx > 0.f) || M[5] != dx || M[10] != dx) return false;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      if (i == j) continue;
+      if (M[4 * i + j] != 0.f) return false;
+    }
+  return M[15] == 1.f;
+}
+bool sg_table_ok(const zpc_bht_view &t) {
+  return t.keys && t.indices && t.status && t.activeKeys && t.cnt && t.numBuckets * 16u == t.tableSize;
+}
+
+}  // namespace
+
+extern "C" {
+
+// std::mt19937(2): MT19937 with the standard constants; universal_hash(rng): hashx = rng() % prime (>= 1), hashy = rng() % prime
+void zpcb200_bht_params(uint32_t hf[6]) {
+  uint32_t mt[624];
+  mt[0] = 2u;
+  for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+  for (int i = 0; i < 624; ++i) {
+    const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+    mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  }
+  for (int k = 0; k < 6; ++k) {
+    uint32_t y = mt[k];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    y %= 4294967291u;
+    if ((k & 1) == 0 && y < 1) y = 1;
+    hf[k] = y;
+  }
+}
+size_t zpcb200_bht_table_size(size_t expected) {
+  if (expected == 0) return 0;
+  size_t p = 1;
+  while (p < expected) p <<= 1;
+  const size_t n = p * 2;
+  return n + (16 - n % 16);
+}
+
+int zpcb200_sg_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, zpc_sparsegrid_view sg, int enlarge_lo,
+                               int enlarge_hi, int *overflow, zpc_stream_t stream) {
+  if (!temp_bytes || sg.table.tableSize < 16 || enlarge_hi < enlarge_lo || enlarge_hi - enlarge_lo > 8) return ZPCB200_E_BADARG;
+  float dx;
+  if (!sg_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  PartScratch L;
+  int rc = part_scratch_layout((size_t)sg.table.tableSize * 4, L);  // the bht holds up to tableSize/2 keys: list of tableSize/2 codes
+  if (rc) return rc;
+  if (!temp) { *temp_bytes = L.need; return ZPCB200_OK; }
+  if (*temp_bytes < L.need) return ZPCB200_E_TEMP_TOO_SMALL;
+  if (!sg_table_ok(sg.table)) return ZPCB200_E_BADARG;
+  char *t = (char *)temp;
+  const int G = ZPC_SM_COUNT * 8;
+  sg_clear_table_kernel<<<G, 256, 0, s>>>(sg.table);
+  ZPC_CHECK_LAUNCH();
+  if (sg.table.success) {
+    sg_set_success_kernel<<<1, 1, 0, s>>>(sg.table.success);
+    ZPC_CHECK_LAUNCH();
+  }
+  rc = part_collect_sorted<3>(t, L, x, n, dx, enlarge_lo, enlarge_hi, overflow, s);
+  if (rc) return rc;
+  sg_place_kernel<<<G, 256, 0, s>>>((const unsigned *)(t + L.off_sorted), (const int *)t, L.list_cap, sg.table, overflow);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_sg_clean(zpc_sparsegrid_view sg, zpc_stream_t stream) {
+  if (!sg.grid || !sg.table.cnt) return ZPCB200_E_BADARG;
+  clean_grid_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>((float4 *)sg.grid, sg.table.cnt, sg.numChannels, sg.numBlocks, 512);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_sg_p2g_apic_fcr(zpc_particles_view P, zpc_sparsegrid_view sg, float dt, zpc_fixed_corotated model, zpc_stream_t stream) {
+  if (sg.numChannels != 7 || !sg.grid || !sg_table_ok(sg.table)) return ZPCB200_E_BADARG;
+  if (P.count && (!P.X || !P.V || !P.M || !P.C || !P.F)) return ZPCB200_E_BADARG;
+  float dx;
+  if (!sg_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  if (!P.count) return ZPCB200_OK;
+  float mu, lam;
+  zpcm::lame_host(model.E, model.nu, mu, lam);
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  p2g_aos_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, zpcp::SparseGrid8{sg.table}, sg.grid, sg.numChannels, dx, dt, model.volume, mu, lam);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_sg_grid_update(zpc_sparsegrid_view sg, float dt, const float extf[3], int mode, float *maxVelSqr, zpc_stream_t stream) {
+  if (!sg.grid || !sg.table.cnt || !extf || !maxVelSqr || (mode != 0 && mode != 1) || sg.numChannels < (mode ? 7 : 4)) return ZPCB200_E_BADARG;
+  grid_update_kernel<512><<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(sg.grid, sg.table.cnt, sg.numChannels, sg.numBlocks, dt, extf[0],
+                                                                              extf[1], extf[2], mode, maxVelSqr);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_sg_g2p_apic(zpc_particles_view P, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream) {
+  if (sg.numChannels < 4 || !sg.grid || !sg_table_ok(sg.table)) return ZPCB200_E_BADARG;
+  if (P.count && (!P.X || !P.V || !P.C || !P.F)) return ZPCB200_E_BADARG;
+  float dx;
+  if (!sg_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  if (!P.count) return ZPCB200_OK;
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  g2p_aos_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(P, zpcp::SparseGrid8{sg.table}, sg.grid, sg.numChannels, dx, dt);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_sg_value_or(zpc_sparsegrid_view sg, int chn, const int *coords, size_t n, float dflt, float *out, zpc_stream_t stream) {
+  if (!sg.grid || !sg_table_ok(sg.table) || chn < 0 || chn >= sg.numChannels || (n && (!coords || !out))) return ZPCB200_E_BADARG;
+  if (!n) return ZPCB200_OK;
+  sg_value_or_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sg, chn, coords, n, dflt, out);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_sg_cell_coords(zpc_sparsegrid_view sg, const int *bno, const int *cno, size_t n, int *icoord, float *wcoord,
+                           zpc_stream_t stream) {
+  if (!sg.table.activeKeys || (n && (!bno || !cno))) return ZPCB200_E_BADARG;
+  if (!n) return ZPCB200_OK;
+  sg_cell_coords_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sg, bno, cno, n, icoord, wcoord);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+}
