@@ -368,7 +368,25 @@ template <typename K> __device__ __forceinline__ unsigned digit_of(K k, int shif
   return (unsigned)((((U)k) ^ KeyBits<K>::flip) >> shift) & mask;
 }
 
-// histogram of every digit position in one pass over the keys
+// histogram of every digit position in one pass over the keys.  Shared-memory integer atomics (native ATOMS.ADD), one
+// per key and digit position; a warp whose 32 keys share the digit (constant high bytes, already sorted ranges) adds
+// once instead of serialising 32 same-address atomics.  Contiguous ranges are read with 128-bit loads.
+template <typename K, int MAXP>
+__device__ __forceinline__ void rs_hist_add(unsigned (*sh)[RS_BINS], K k, bool valid, int sbit, int ebit, int npass) {
+#pragma unroll
+  for (int p = 0; p < MAXP; ++p)
+    if (p < npass) {
+      const int shift = sbit + 8 * p;
+      const int bits = min(8, ebit - shift);
+      const unsigned d = valid ? digit_of(k, shift, (1u << bits) - 1) : RS_BINS;
+      const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+      if (__all_sync(0xffffffffu, d == d0)) {
+        if ((threadIdx.x & 31) == 0 && d0 < RS_BINS) atomicAdd(&sh[p][d0], 32u);
+      } else if (valid) {
+        atomicAdd(&sh[p][d], 1u);
+      }
+    }
+}
 template <typename K, int MAXP>
 __global__ void __launch_bounds__(512) rs_hist_kernel(PortAcc<K> keys, size_t n, int sbit, int ebit, int npass,
                                                       unsigned *ghist /*[npass][256]*/) {
@@ -376,21 +394,28 @@ __global__ void __launch_bounds__(512) rs_hist_kernel(PortAcc<K> keys, size_t n,
   for (int i = threadIdx.x; i < MAXP * RS_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
   __syncthreads();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  // warp-uniform trip count so that __match_any_sync sees whole warps; one atomic per distinct digit
-  const size_t first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
-  for (size_t i0 = first; i0 < n; i0 += stride) {
+  const size_t first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);  // warp-uniform trip counts (votes inside)
+  constexpr int V = 16 / (int)sizeof(K);
+  size_t done = 0;  // keys [0, done) are covered by the vector loop
+  if (keys.contiguous() && ((uintptr_t)(keys.base + keys.idx) & 15) == 0) {
+    using VT = typename VecOf<K>::type;
+    const VT *v = reinterpret_cast<const VT *>(keys.base + keys.idx);
+    const size_t nv = n / V;
+    for (size_t i0 = first; i0 < nv; i0 += stride) {
+      const size_t i = i0 + (threadIdx.x & 31);
+      const bool valid = i < nv;
+      VT q = valid ? v[i] : VT();
+      const K *kk = reinterpret_cast<const K *>(&q);
+#pragma unroll
+      for (int j = 0; j < V; ++j) rs_hist_add<K, MAXP>(sh, kk[j], valid, sbit, ebit, npass);
+    }
+    done = nv * V;
+  }
+  for (size_t i0 = done + first; i0 < n; i0 += stride) {
     const size_t i = i0 + (threadIdx.x & 31);
     const bool valid = i < n;
-    K k = valid ? keys[i] : (K)0;
-#pragma unroll
-    for (int p = 0; p < MAXP; ++p)
-      if (p < npass) {
-        int shift = sbit + 8 * p;
-        int bits = min(8, ebit - shift);
-        unsigned d = valid ? digit_of(k, shift, (1u << bits) - 1) : RS_BINS;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[p][d], (unsigned)__popc(peers));
-      }
+    const K k = valid ? keys[i] : (K)0;
+    rs_hist_add<K, MAXP>(sh, k, valid, sbit, ebit, npass);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < npass * RS_BINS; i += blockDim.x) {
@@ -431,7 +456,13 @@ template <typename T> struct TileAcc<T, false> {
 };
 
 template <typename K, bool PAIRS, int ITEMS, bool FAST>
-__global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? 3 : 2) rs_onesweep_kernel(PortAcc<K> kin, PortAcc<int> vin, PortAcc<K> kout,
+#ifndef ZPC_RS_ITEMS4
+#define ZPC_RS_ITEMS4 16
+#endif
+#ifndef ZPC_RS_MINB4
+#define ZPC_RS_MINB4 3
+#endif
+__global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? ZPC_RS_MINB4 : 2) rs_onesweep_kernel(PortAcc<K> kin, PortAcc<int> vin, PortAcc<K> kout,
                                                             PortAcc<int> vout, size_t n, int shift, unsigned mask, int nbits,
                                                             const unsigned *gbase /*[256] exclusive*/,
                                                             unsigned *lookback /*[tiles][256]*/, unsigned *ticket) {
@@ -460,27 +491,44 @@ __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? 3 : 2) rs_onesweep_ker
   for (int i = 0; i < ITEMS; ++i) key[i] = (wofs + 32 * i) < cnt_tile ? tk[wofs + 32 * i] : (K)0;
   // warp-synchronous stable ranking: lanes holding the same digit are found with one ballot per digit bit
   // (MATCH.ANY has a long, poorly pipelined latency on sm_100), then one shared-memory counter per (warp, digit)
+  const bool full_tile = cnt_tile == TILE;  // CTA-uniform: every lane holds a key, no validity votes
+  // (1) peer masks of all items first: 16 independent vote chains the scheduler can overlap.  Packed into rank[i]:
+  //     bits 0-4 = same-digit lanes before this one, 5-9 = leader lane, 10-15 = group size.
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    const bool valid = (wofs + 32 * i) < cnt_tile;
+    const bool valid = full_tile || (wofs + 32 * i) < cnt_tile;
     const unsigned d = digit_of(key[i], shift, mask);
-    unsigned peers = __ballot_sync(0xffffffffu, valid);
-    if (!valid) peers = ~peers;
-    for (int b = 0; b < nbits; ++b) {
-      const bool bit = (d >> b) & 1u;
-      const unsigned vote = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? vote : ~vote;
+    unsigned peers = 0xffffffffu;
+    if (!full_tile) {
+      peers = __ballot_sync(0xffffffffu, valid);
+      if (!valid) peers = ~peers;
     }
-    const unsigned before = __popc(peers & lanemask_lt());
-    const int leader = __ffs(peers) - 1;
+    if (nbits == 8) {  // the common pass: fully unrolled, one vote + one LOP3 per digit bit
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const unsigned bit = (d >> b) & 1u;
+        const unsigned vote = __ballot_sync(0xffffffffu, bit);
+        peers &= vote ^ (bit - 1u);  // bit ? vote : ~vote
+      }
+    } else {
+      for (int b = 0; b < nbits; ++b) {
+        const unsigned bit = (d >> b) & 1u;
+        const unsigned vote = __ballot_sync(0xffffffffu, bit);
+        peers &= vote ^ (bit - 1u);
+      }
+    }
+    rank[i] = (unsigned)__popc(peers & lanemask_lt()) | ((unsigned)(__ffs(peers) - 1) << 5) | ((unsigned)__popc(peers) << 10);
+  }
+  // (2) one shared atomic per (item, digit group), in item order (stability); the group's base goes to its lanes
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const bool valid = full_tile || (wofs + 32 * i) < cnt_tile;
+    const int leader = (int)((rank[i] >> 5) & 31u);
     unsigned c = 0;
-    if (valid && l == leader) {
-      c = warp_hist[w][d];
-      warp_hist[w][d] = c + __popc(peers);
-    }
+    if (valid && l == leader) c = atomicAdd(&warp_hist[w][digit_of(key[i], shift, mask)], rank[i] >> 10);
     c = __shfl_sync(0xffffffffu, c, leader);
-    rank[i] = c + before;
-    __syncwarp();
+    rank[i] = c + (rank[i] & 31u);
+    __syncwarp();  // item i's counter updates are ordered before item i+1's
   }
   __syncthreads();
   // per digit (thread d): exclusive prefix over warps, tile count
@@ -589,7 +637,7 @@ __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? 3 : 2) rs_onesweep_ker
   }
 }
 
-template <typename K> struct RsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? 16 : 12; };
+template <typename K> struct RsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? ZPC_RS_ITEMS4 : 12; };
 
 template <typename K, bool PAIRS>
 int radix_sort_impl(void *temp, size_t *temp_bytes, zpc_port keys_in, zpc_port vals_in, zpc_port keys_out,
