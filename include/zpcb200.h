@@ -46,7 +46,7 @@ typedef struct zpc_port {
 /* Parallel primitives — replace the CUB calls under CudaExecutionPolicy                        */
 /* (cuda/execution/ExecutionPolicy.cuh: reduce :649-681, inclusive_scan :552-590,               */
 /*  exclusive_scan :601-632, radix_sort_pair :755-826, radix_sort :828-866).                     */
-/* <T> in {i32,u32,i64,f32}; scans/reductions use the identities the reference's C ABI passes     */
+/* <T> in {i32,u32,i64,f32,f64}; scans/reductions use the identities the reference's C ABI passes     */
 /* (py_interop/cuda/ExecutionPolicy.cpp:41-90): 0 for sum, numeric max for min, lowest for max.  */
 /* `out` of a reduce is one element on the device.  Ranges are zpc_ports; n = last - first.      */
 /* ------------------------------------------------------------------------------------------ */
@@ -65,6 +65,7 @@ ZPCB200_DECL_REDUCE_SCAN(i32)
 ZPCB200_DECL_REDUCE_SCAN(u32)
 ZPCB200_DECL_REDUCE_SCAN(i64)
 ZPCB200_DECL_REDUCE_SCAN(f32)
+ZPCB200_DECL_REDUCE_SCAN(f64)
 
 /* Stable LSD radix sort on bits [sbit, ebit) of the key (ExecutionPolicy.hpp:765-781).  Signed
  * keys order as signed.  keys_in/vals_in are not modified; out may not alias in.  n <= 2^30. */
@@ -77,6 +78,18 @@ ZPCB200_DECL_REDUCE_SCAN(f32)
 ZPCB200_DECL_SORT(u32, uint32_t)
 ZPCB200_DECL_SORT(i32, int32_t)
 ZPCB200_DECL_SORT(u64, uint64_t)
+
+/* merge_sort / merge_sort_pair (cuda/execution/ExecutionPolicy.cuh:686-760; host twins execution/ExecutionPolicy.hpp:
+ * 285-455): stable ascending sort under operator<, IN PLACE, <T> in {i32,f32,f64} like the reference's C layer
+ * (py_interop/cuda/ExecutionPolicy.cpp:100-112); values are i32.  -0.0 and +0.0 compare equal (their relative order is
+ * kept); NaN keys sort by bit pattern. */
+#define ZPCB200_DECL_MERGE_SORT(S)                                                                  \
+  int zpcb200_merge_sort_pair_##S(void *temp, size_t *temp_bytes, zpc_port keys, zpc_port vals,     \
+                                  size_t n, zpc_stream_t stream);                                   \
+  int zpcb200_merge_sort_##S(void *temp, size_t *temp_bytes, zpc_port keys, size_t n, zpc_stream_t stream);
+ZPCB200_DECL_MERGE_SORT(i32)
+ZPCB200_DECL_MERGE_SORT(f32)
+ZPCB200_DECL_MERGE_SORT(f64)
 
 /* ------------------------------------------------------------------------------------------ */
 /* View PODs (non-owning)                                                 */
@@ -324,6 +337,13 @@ int policy_last_error__b200(const zpcb200_policy *);
                                         zpc_port out);
 ZPCB200_DECL_POLICY_PRIMS(int, int32_t)
 ZPCB200_DECL_POLICY_PRIMS(float, float)
+ZPCB200_DECL_POLICY_PRIMS(double, double)
+#define ZPCB200_DECL_POLICY_MERGE(T)                                                              \
+  void merge_sort__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last);                 \
+  void merge_sort_pair__b200_##T##_1(zpcb200_policy *, zpc_port keys, zpc_port vals, size_t count);
+ZPCB200_DECL_POLICY_MERGE(int)
+ZPCB200_DECL_POLICY_MERGE(float)
+ZPCB200_DECL_POLICY_MERGE(double)
 void radix_sort__b200_int_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);
 void radix_sort_pair__b200_int_1(zpcb200_policy *, zpc_port keysIn, zpc_port valsIn,
                                  zpc_port keysOut, zpc_port valsOut, size_t count);

@@ -86,3 +86,33 @@ ZO_SCAN_REDUCE_IMPL(i32, int32_t, INT32_MAX, INT32_MIN)
 ZO_SCAN_REDUCE_IMPL(u32, uint32_t, UINT32_MAX, 0u)
 ZO_SCAN_REDUCE_IMPL(i64, int64_t, INT64_MAX, INT64_MIN)
 ZO_SCAN_REDUCE_IMPL(f32, float, FLT_MAX, -FLT_MAX)
+ZO_SCAN_REDUCE_IMPL(f64, double, DBL_MAX, -DBL_MAX)
+
+/* merge_sort_pair (stable, ascending, operator<): execution/ExecutionPolicy.hpp:311-455 — bottom-up merge; the result
+ * of a STABLE sort under a strict weak order is unique, so any stable merge gives the reference's output. */
+#define ZO_MERGE_IMPL(S, T)                                                                       \
+  void zo_merge_sort_pair_##S(T *keys, int32_t *vals, size_t n) {                                 \
+    T *k2 = (T *)malloc(sizeof(T) * (n ? n : 1));                                                 \
+    int32_t *v2 = (int32_t *)malloc(sizeof(int32_t) * (n ? n : 1));                               \
+    T *ka = keys, *kb = k2;                                                                       \
+    int32_t *va = vals, *vb = v2;                                                                 \
+    for (size_t w = 1; w < n; w *= 2) {                                                           \
+      for (size_t lo = 0; lo < n; lo += 2 * w) {                                                  \
+        size_t mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n;               \
+        size_t i = lo, j = mid, o = lo;                                                           \
+        while (i < mid && j < hi) {                                                               \
+          if (ka[j] < ka[i]) { kb[o] = ka[j]; vb[o++] = va[j++]; }                                \
+          else { kb[o] = ka[i]; vb[o++] = va[i++]; }                                              \
+        }                                                                                         \
+        while (i < mid) { kb[o] = ka[i]; vb[o++] = va[i++]; }                                     \
+        while (j < hi) { kb[o] = ka[j]; vb[o++] = va[j++]; }                                      \
+      }                                                                                           \
+      { T *t = ka; ka = kb; kb = t; }                                                             \
+      { int32_t *t = va; va = vb; vb = t; }                                                       \
+    }                                                                                             \
+    if (ka != keys) for (size_t i = 0; i < n; ++i) { keys[i] = ka[i]; vals[i] = va[i]; }          \
+    free(k2); free(v2);                                                                           \
+  }
+ZO_MERGE_IMPL(i32, int32_t)
+ZO_MERGE_IMPL(f32, float)
+ZO_MERGE_IMPL(f64, double)

@@ -41,7 +41,7 @@ def _ptr(a):
 
 
 _KT = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64}
-_ST = {"i32": np.int32, "u32": np.uint32, "i64": np.int64, "f32": np.float32}
+_ST = {"i32": np.int32, "u32": np.uint32, "i64": np.int64, "f32": np.float32, "f64": np.float64}
 
 
 class Oracle:
@@ -260,6 +260,11 @@ class Oracle:
         out = np.zeros(1, _ST[kind])
         getattr(self.lib, "zo_reduce_%s_%s" % (op, kind))(_ptr(a), _ptr(out), C.c_size_t(a.size))
         return out[0]
+
+    def merge_sort_pair(self, kind, keys, vals):
+        k = np.array(keys, _ST[kind]); v = np.array(vals, np.int32)
+        getattr(self.lib, "zo_merge_sort_pair_" + kind)(_ptr(k), _ptr(v), C.c_size_t(k.size))
+        return k, v
 
 
 class Ref:
@@ -495,6 +500,11 @@ class Ref:
         getattr(self.lib, "zpcref_reduce_%s_%s" % (op, kind))(C.c_int(nthreads), _ptr(a), _ptr(out),
                                                               C.c_size_t(a.size))
         return out[0]
+
+    def merge_sort_pair(self, kind, keys, vals, nthreads=0):
+        k = np.array(keys, _ST[kind]); v = np.array(vals, np.int32)
+        getattr(self.lib, "zpcref_merge_sort_pair_" + kind)(C.c_int(nthreads), _ptr(k), _ptr(v), C.c_size_t(k.size))
+        return k, v
 
     def svd3(self, F):
         F = np.ascontiguousarray(F, np.float32)

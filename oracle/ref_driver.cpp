@@ -260,6 +260,15 @@ ZPCREF_SCAN_REDUCE(i32, int32_t)
 ZPCREF_SCAN_REDUCE(f32, float)
 ZPCREF_SCAN_REDUCE(u32, uint32_t)
 ZPCREF_SCAN_REDUCE(i64, int64_t)
+ZPCREF_SCAN_REDUCE(f64, double)
+
+#define ZPCREF_MERGE_SORT_PAIR(SUFFIX, KT)                                                          \
+  void zpcref_merge_sort_pair_##SUFFIX(int nthreads, KT *keys, int *vals, size_t n) {               \
+    with_policy(nthreads, [&](auto &pol, auto) { merge_sort_pair(pol, keys, vals, (std::ptrdiff_t)n); }); \
+  }
+ZPCREF_MERGE_SORT_PAIR(i32, int32_t)
+ZPCREF_MERGE_SORT_PAIR(f32, float)
+ZPCREF_MERGE_SORT_PAIR(f64, double)
 
 /// ---- per-particle math ----
 void zpcref_svd3(const float *F, float *U, float *S, float *V) {  // column-major 9-vectors

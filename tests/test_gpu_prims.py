@@ -204,3 +204,58 @@ def test_policy_object_abi():
     assert np.array_equal(vo.cpu().numpy(), np.argsort(a, kind="stable").astype(np.int32))
     assert L.policy_last_error__b200(p) == 0
     L.del_policy__b200(p)
+
+
+# ---- merge_sort(_pair): stable, in place, {i32, f32, f64} keys (ExecutionPolicy.cuh:686-760) ---------------------------
+MS_DT = {"i32": (np.int32, torch.int32), "f32": (np.float32, torch.float32), "f64": (np.float64, torch.float64)}
+
+
+@pytest.mark.parametrize("kind", list(MS_DT))
+@pytest.mark.parametrize("n", [0, 1, 2, 33, 4097, 300007])
+def test_merge_sort_pair_matches_oracle(pol, oracle, kind, n):
+    npdt, _ = MS_DT[kind]
+    rs = np.random.RandomState(n + 3)
+    k = rs.randint(-200, 200, size=n).astype(npdt)          # many duplicates: the value order proves stability
+    if kind != "i32":
+        k = (k * npdt(0.37)).astype(npdt)
+        if n > 40:
+            k[5] = -0.0; k[9] = 0.0; k[17] = -0.0; k[30] = np.inf; k[31] = -np.inf   # +-0 equal under <
+    v = np.arange(n, dtype=np.int32)
+    dk, dv = dev(k), dev(v)
+    pol.merge_sort_pair(dk, dv)
+    ko, vo = oracle.merge_sort_pair(kind, k, v)
+    assert np.array_equal(dv.cpu().numpy(), vo)
+    assert np.array_equal(dk.cpu().numpy().view(np.uint8), ko.view(np.uint8))
+    dk2 = dev(k)
+    pol.merge_sort(dk2)
+    assert np.array_equal(dk2.cpu().numpy().view(np.uint8), ko.view(np.uint8))
+
+
+def test_merge_sort_pair_on_tilevector_channels(pol, oracle):
+    """keys and values living in channels of an AoSoA TileVector (iterator ports), sorted in place"""
+    from zpc_b200 import api
+    n = 5003
+    rs = np.random.RandomState(1)
+    k = rs.uniform(-10, 10, n).astype(np.float32).round(1)
+    tv = api.TileVector(n, 5, 32)
+    tv.set_channel(2, dev(k))
+    vals = dev(np.arange(n, dtype=np.int32))
+    pol.merge_sort_pair((tv, 2), vals)
+    ko, vo = oracle.merge_sort_pair("f32", k, np.arange(n, dtype=np.int32))
+    assert np.array_equal(tv.channel(2)[:, 0].cpu().numpy(), ko) and np.array_equal(vals.cpu().numpy(), vo)
+
+
+@pytest.mark.parametrize("n", [0, 1, 33, 4097, 1000003])
+def test_f64_scan_and_reduce(pol, oracle, n):
+    """integer-valued doubles: every partial sum is exact, so any association gives the oracle's left fold bit for bit"""
+    a = np.random.RandomState(n).randint(-1000, 1000, size=n).astype(np.float64)
+    d = dev(a)
+    out = torch.empty_like(d)
+    pol.exclusive_scan(d, out)
+    assert np.array_equal(out.cpu().numpy(), oracle.scan("exclusive", "f64", a))
+    pol.inclusive_scan(d, out)
+    assert np.array_equal(out.cpu().numpy(), oracle.scan("inclusive", "f64", a))
+    r = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for op in ("sum", "min", "max"):
+        pol.reduce(d, r, op)
+        assert r.cpu().numpy()[0] == oracle.reduce(op, "f64", a), (op, n)

@@ -56,3 +56,16 @@ def test_float_reduce_is_left_fold(oracle):
         acc = np.float32(acc + x)
     assert oracle.reduce("sum", "f32", a) == acc
     assert oracle.reduce("max", "f32", a) == a.max() and oracle.reduce("min", "f32", a) == a.min()
+
+
+@pytest.mark.parametrize("kind,dt", [("i32", np.int32), ("f32", np.float32), ("f64", np.float64)])
+@pytest.mark.parametrize("n", [0, 1, 2, 33, 4097])
+def test_merge_sort_pair_is_the_stable_sort(oracle, kind, dt, n):
+    rs = np.random.RandomState(n + 7)
+    k = (rs.randint(-20, 20, size=n)).astype(dt)
+    if kind != "i32" and n > 4:
+        k[1] = -0.0; k[3] = 0.0                     # equal under operator<: input order must survive
+    v = np.arange(n, dtype=np.int32)
+    ko, vo = oracle.merge_sort_pair(kind, k, v)
+    order = np.argsort(k, kind="stable")
+    assert np.array_equal(vo, v[order]) and np.array_equal(ko.view(np.uint8), k[order].view(np.uint8))

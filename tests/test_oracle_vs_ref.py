@@ -76,3 +76,27 @@ def test_primitives_vs_reference(oracle, ref, nthreads):
             assert np.array_equal(oracle.scan("inclusive", "i32", x), ref.scan("inclusive", "i32", x, nthreads))
         for op in ("sum", "min", "max"):
             assert oracle.reduce(op, "i32", x) == ref.reduce(op, "i32", x, nthreads)
+
+
+@pytest.mark.parametrize("kind,dt", [("i32", np.int32), ("f32", np.float32), ("f64", np.float64)])
+@pytest.mark.parametrize("nthreads", [0, 4])
+def test_merge_sort_pair_matches_reference(oracle, ref, kind, dt, nthreads):
+    """reference merge_sort_pair (stable) on seq_exec / omp_exec vs the oracle, incl. duplicates and signed zeros"""
+    rs = np.random.RandomState(11)
+    for n in (1, 2, 17, 1000, 50001):
+        k = rs.randint(-50, 50, size=n).astype(dt)
+        if kind != "i32" and n > 4:
+            k[0] = -0.0; k[2] = 0.0
+        v = np.arange(n, dtype=np.int32)
+        kr, vr = ref.merge_sort_pair(kind, k, v, nthreads)
+        ko, vo = oracle.merge_sort_pair(kind, k, v)
+        assert np.array_equal(vr, vo) and np.array_equal(kr.view(np.uint8), ko.view(np.uint8)), (kind, n)
+
+
+def test_f64_scan_reduce_match_reference(oracle, ref):
+    a = np.random.RandomState(3).uniform(-1, 1, 5000).astype(np.float64)
+    for nthreads in (0,):
+        assert np.array_equal(ref.scan("exclusive", "f64", a, nthreads), oracle.scan("exclusive", "f64", a))
+        assert np.array_equal(ref.scan("inclusive", "f64", a, nthreads), oracle.scan("inclusive", "f64", a))
+        for op in ("sum", "min", "max"):
+            assert ref.reduce(op, "f64", a, nthreads) == oracle.reduce(op, "f64", a)

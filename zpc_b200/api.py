@@ -123,7 +123,7 @@ def vec3_port(x):
 
 
 _SUFFIX = {torch.int32: "i32", torch.float32: "f32", torch.int64: "i64", torch.uint32: "u32",
-           torch.uint64: "u64"}
+           torch.uint64: "u64", torch.float64: "f64"}
 
 
 class TileVector:
@@ -239,6 +239,18 @@ class CudaExecutionPolicy:
         ebit = {"u32": 32, "i32": 32, "u64": 64}[kind] if ebit is None else ebit
         self._two_phase(getattr(lib(), "zpcb200_radix_sort_" + kind), pk, pko, C.c_size_t(n), C.c_int(sbit),
                         C.c_int(ebit))
+
+
+    def merge_sort_pair(self, keys, vals, count=None):
+        """stable ascending sort of (keys, vals) IN PLACE (ExecutionPolicy.cuh:701-760); keys i32 | f32 | f64, vals i32"""
+        pk, dt, n = self._as_port(keys)
+        pv, _, _ = self._as_port(vals)
+        n = n if count is None else count
+        self._two_phase(getattr(lib(), "zpcb200_merge_sort_pair_" + _SUFFIX[dt]), pk, pv, C.c_size_t(n))
+
+    def merge_sort(self, keys):
+        pk, dt, n = self._as_port(keys)
+        self._two_phase(getattr(lib(), "zpcb200_merge_sort_" + _SUFFIX[dt]), pk, C.c_size_t(n))
 
 
 def cuda_exec():

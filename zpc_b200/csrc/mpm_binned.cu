@@ -33,7 +33,10 @@ namespace {
 constexpr int TS = 32;                  // particle tile length
 constexpr int NCH = ZPC_PB_NCH;         // 25 channels
 constexpr int BIN_MAX = ZPCB200_BIN_MAX;
-constexpr int P2G_NT = 256, P2G_NW = P2G_NT / 32;
+#ifndef ZPC_P2G_NT
+#define ZPC_P2G_NT 256
+#endif
+constexpr int P2G_NT = ZPC_P2G_NT, P2G_NW = P2G_NT / 32;
 constexpr int CHUNK = P2G_NT;           // particles staged per pass (one record per thread)
 constexpr int NCOL6 = 36;               // (x,y) columns of home cells in [-1,4]^2: 16 nominal + 20 ring
 constexpr int NGRP = NCOL6 * 6 + 1;     // (column, z in [-1,4]) groups + far-stray group
@@ -44,7 +47,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ size_t pslot(size_t i) { return ((i >> 5) * NCH) * TS + (i & 31); }  // channel 0 of particle i
 
 struct P2GSmem {
-  float4 rec4[CHUNK * 7 + CHUNK / 8];  // 29184 B: 7 float4 per record (+1 pad granule per 8 records, used by VAR 4)
+  float4 rec4[CHUNK * 7 + CHUNK / 8];  // 29184 B at CHUNK = 256: 7 float4 per record (+1 pad granule per 8 records, used by VAR 4)
   float out[8 * 448];               // 14336 B: the arena as eight [7][64] grid tiles, accumulated with shared atomics
   unsigned short order[BIN_MAX];    // fallback grouping only (no cell-order cache)
   unsigned char grp_of[BIN_MAX];
@@ -171,7 +174,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   const bool pre = cellOrder != nullptr && *cellOrderValid != 0;
   const unsigned short *gorder = pre ? cellOrder + p0 : S.order;
   if (pre) {
-    if (tid <= NGRP) S.gstart[tid] = cellStart[(size_t)bin * ZPCB200_CELL_GROUPS_PAD + tid];
+    for (int i = tid; i <= NGRP; i += P2G_NT) S.gstart[i] = cellStart[(size_t)bin * ZPCB200_CELL_GROUPS_PAD + i];
     __syncthreads();
   } else {
     for (int i = tid; i < NGRP + 3; i += P2G_NT) S.cnt[i] = 0;

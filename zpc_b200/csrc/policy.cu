@@ -64,6 +64,18 @@ int policy_last_error__b200(const zpcb200_policy *p) { return p ? p->last_error 
   }
 ZPC_DEF_POLICY_PRIMS(int, i32)
 ZPC_DEF_POLICY_PRIMS(float, f32)
+ZPC_DEF_POLICY_PRIMS(double, f64)
+
+#define ZPC_DEF_POLICY_MERGE(T, S)                                                                                   \
+  void merge_sort__b200_##T##_1(zpcb200_policy *p, zpc_port first, zpc_port last) {                                  \
+    run_with_scratch(p, [&](void *t, size_t *b) { return zpcb200_merge_sort_##S(t, b, first, port_distance(first, last), p->stream); }); \
+  }                                                                                                                  \
+  void merge_sort_pair__b200_##T##_1(zpcb200_policy *p, zpc_port keys, zpc_port vals, size_t count) {                \
+    run_with_scratch(p, [&](void *t, size_t *b) { return zpcb200_merge_sort_pair_##S(t, b, keys, vals, count, p->stream); }); \
+  }
+ZPC_DEF_POLICY_MERGE(int, i32)
+ZPC_DEF_POLICY_MERGE(float, f32)
+ZPC_DEF_POLICY_MERGE(double, f64)
 
 void radix_sort__b200_int_1(zpcb200_policy *p, zpc_port first, zpc_port last, zpc_port out) {
   run_with_scratch(p, [&](void *t, size_t *b) { return zpcb200_radix_sort_i32(t, b, first, out, port_distance(first, last), 0, 32, p->stream); });

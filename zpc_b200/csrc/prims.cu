@@ -63,6 +63,7 @@ template <> struct VecOf<uint32_t> { using type = uint4; static constexpr int N 
 template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };
 template <> struct VecOf<int64_t> { using type = longlong2; static constexpr int N = 2; };
 template <> struct VecOf<uint64_t> { using type = ulonglong2; static constexpr int N = 2; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
 
 template <typename T, typename Op, bool CONTIG>
 __global__ void __launch_bounds__(RED_NT) reduce_kernel(PortAcc<T> in, size_t n, T ident, T *partials,
@@ -702,6 +703,90 @@ int radix_sort_impl(void *temp, size_t *temp_bytes, zpc_port keys_in, zpc_port v
   return ZPCB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// merge_sort / merge_sort_pair (execution/ExecutionPolicy.hpp:285-455, cuda/execution/ExecutionPolicy.cuh:686-760):
+// stable ascending sort under operator<, IN PLACE.  A stable sort under a strict weak order has one result, so it is
+// produced with the radix machinery: keys are mapped to an order-preserving unsigned image (-0.0 and +0.0 compare
+// equal and therefore share an image), (image, index) pairs are radix-sorted, then keys and values are gathered
+// through the sorted indices and written back.  NaN keys (unordered under <) sort by their bit pattern.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct OrdKey;
+template <> struct OrdKey<int32_t> {
+  using U = uint32_t;
+  static __device__ __forceinline__ U make(int32_t k) { return (uint32_t)k ^ 0x80000000u; }
+};
+template <> struct OrdKey<float> {
+  using U = uint32_t;
+  static __device__ __forceinline__ U make(float x) {
+    uint32_t b = __float_as_uint(x);
+    if (x == 0.f) b = 0u;
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+  }
+};
+template <> struct OrdKey<double> {
+  using U = uint64_t;
+  static __device__ __forceinline__ U make(double x) {
+    uint64_t b = (uint64_t)__double_as_longlong(x);
+    if (x == 0.0) b = 0ull;
+    return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+  }
+};
+template <typename T>
+__global__ void ms_prepare_kernel(PortAcc<T> keys, size_t n, typename OrdKey<T>::U *img, int *idx) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  img[i] = OrdKey<T>::make(keys[i]);
+  idx[i] = (int)i;
+}
+template <typename T, bool PAIRS>
+__global__ void ms_gather_kernel(PortAcc<T> keys, PortAcc<int> vals, const int *__restrict__ idx, size_t n, T *ktmp, int *vtmp) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t j = (size_t)idx[i];
+  ktmp[i] = keys[j];
+  if (PAIRS) vtmp[i] = vals[j];
+}
+template <typename T, bool PAIRS>
+__global__ void ms_writeback_kernel(const T *__restrict__ ktmp, const int *__restrict__ vtmp, size_t n, PortAcc<T> keys,
+                                    PortAcc<int> vals) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = ktmp[i];
+  if (PAIRS) vals[i] = vtmp[i];
+}
+template <typename T, bool PAIRS>
+int merge_sort_impl(void *temp, size_t *temp_bytes, zpc_port keys, zpc_port vals, size_t n, cudaStream_t s) {
+  using U = typename OrdKey<T>::U;
+  if (!temp_bytes) return ZPCB200_E_BADARG;
+  if (n > ((size_t)1 << 30)) return ZPCB200_E_UNSUPPORTED;
+  size_t sort_bytes = 0;
+  zpc_port none = {nullptr, 0, 0, 0, 1};
+  int rc = radix_sort_impl<U, true>(nullptr, &sort_bytes, none, none, none, none, n, 0, (int)sizeof(U) * 8, s);
+  if (rc) return rc;
+  const size_t o_img = 0, o_idx = zpc_align_up(o_img + sizeof(U) * n, 256), o_img2 = zpc_align_up(o_idx + 4 * n, 256),
+               o_idx2 = zpc_align_up(o_img2 + sizeof(U) * n, 256), o_kt = zpc_align_up(o_idx2 + 4 * n, 256),
+               o_vt = zpc_align_up(o_kt + sizeof(T) * n, 256), o_sort = zpc_align_up(o_vt + 4 * n, 256), need = o_sort + sort_bytes;
+  if (!temp) { *temp_bytes = need; return ZPCB200_OK; }
+  if (*temp_bytes < need) return ZPCB200_E_TEMP_TOO_SMALL;
+  if (!n) return ZPCB200_OK;
+  char *t = (char *)temp;
+  U *img = (U *)(t + o_img), *img2 = (U *)(t + o_img2);
+  int *idx = (int *)(t + o_idx), *idx2 = (int *)(t + o_idx2), *vt = (int *)(t + o_vt);
+  T *kt = (T *)(t + o_kt);
+  const unsigned g = (unsigned)((n + 255) / 256);
+  ms_prepare_kernel<T><<<g, 256, 0, s>>>(PortAcc<T>(keys), n, img, idx);
+  ZPC_CHECK_LAUNCH();
+  zpc_port pi = {img, 0, 0, 0, 1}, px = {idx, 0, 0, 0, 1}, pi2 = {img2, 0, 0, 0, 1}, px2 = {idx2, 0, 0, 0, 1};
+  size_t sb = sort_bytes;
+  rc = radix_sort_impl<U, true>(t + o_sort, &sb, pi, px, pi2, px2, n, 0, (int)sizeof(U) * 8, s);
+  if (rc) return rc;
+  ms_gather_kernel<T, PAIRS><<<g, 256, 0, s>>>(PortAcc<T>(keys), PortAcc<int>(vals), idx2, n, kt, vt);
+  ZPC_CHECK_LAUNCH();
+  ms_writeback_kernel<T, PAIRS><<<g, 256, 0, s>>>(kt, vt, n, PortAcc<T>(keys), PortAcc<int>(vals));
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -736,6 +821,7 @@ ZPC_DEF_REDUCE_SCAN(i32, int32_t, INT32_MAX, INT32_MIN)
 ZPC_DEF_REDUCE_SCAN(u32, uint32_t, UINT32_MAX, 0u)
 ZPC_DEF_REDUCE_SCAN(i64, int64_t, INT64_MAX, INT64_MIN)
 ZPC_DEF_REDUCE_SCAN(f32, float, FLT_MAX, -FLT_MAX)
+ZPC_DEF_REDUCE_SCAN(f64, double, DBL_MAX, -DBL_MAX)
 
 #define ZPC_DEF_SORT(S, K)                                                                                      \
   int zpcb200_radix_sort_pair_##S(void *temp, size_t *tb, zpc_port ki, zpc_port vi, zpc_port ko, zpc_port vo,   \
@@ -752,6 +838,18 @@ ZPC_DEF_REDUCE_SCAN(f32, float, FLT_MAX, -FLT_MAX)
 ZPC_DEF_SORT(u32, uint32_t)
 ZPC_DEF_SORT(i32, int32_t)
 ZPC_DEF_SORT(u64, uint64_t)
+
+#define ZPC_DEF_MERGE_SORT(S, T)                                                                                \
+  int zpcb200_merge_sort_pair_##S(void *temp, size_t *tb, zpc_port keys, zpc_port vals, size_t n, zpc_stream_t st) { \
+    return merge_sort_impl<T, true>(temp, tb, keys, vals, n, (cudaStream_t)st);                                 \
+  }                                                                                                             \
+  int zpcb200_merge_sort_##S(void *temp, size_t *tb, zpc_port keys, size_t n, zpc_stream_t st) {                 \
+    zpc_port none = {nullptr, 0, 0, 0, 1};                                                                      \
+    return merge_sort_impl<T, false>(temp, tb, keys, none, n, (cudaStream_t)st);                                \
+  }
+ZPC_DEF_MERGE_SORT(i32, int32_t)
+ZPC_DEF_MERGE_SORT(f32, float)
+ZPC_DEF_MERGE_SORT(f64, double)
 
 const char *zpcb200_version(void) { return "zpcb200 0.1 (sm_100a)"; }
 int zpcb200_kernel_launch_count(void) { return g_zpc_launches.load(); }
