@@ -311,6 +311,59 @@ void zo_stress_fixedcorotated(float volume, float mu, float lam, const float F[9
       PF[3*c + r] = ((P[r]*F[c] + P[3 + r]*F[3 + c]) + P[6 + r]*F[6 + c]) * volume;
 }
 
+/* math::sqrtNewtonRaphson<float>, math/MathUtils.h:239-251: Newton iteration from 1 until |x_{n+1} - x_n| <= max(n * 1e-6, 128 eps) */
+static float sqrt_newton_raphson(float n) {
+  const float eps = 128.f * 1.1920928955078125e-7f, relTol = 1e-6f;
+  if (n < -eps) return NAN;
+  if (n < eps) return 0.f;
+  float xn = 1.f;
+  float xnp1 = 0.5f * (xn + n / xn);
+  const float tol = n * relTol > eps ? n * relTol : eps;
+  for (; fabsf(xnp1 - xn) > tol; xnp1 = 0.5f * (xn + n / xn)) xn = xnp1;
+  return xnp1;
+}
+
+/* compute_stress_vonmisesfixedcorotated, physics/ConstitutiveModel_Vol_dP.hpp:49-110: fixed-corotated trial stress
+ * in principal space, radial return onto the von Mises cylinder, projected singular values, then the fixed-corotated
+ * P F^T with the projected F (the projection stays local: P2G.hpp:85-91 passes a copy of the particle's F) */
+void zo_stress_vonmises(float volume, float mu, float lam, float yield_stress, const float Fin[9], float PF[9]) {
+  float F[9], U[9], S[3], V[9], Sc[3], tau[3], s_trial[3], P[9], Ph[3];
+  for (int d = 0; d < 9; ++d) F[d] = Fin[d];
+  zo_svd3(F, U, S, V);
+  for (int d = 0; d < 3; ++d) Sc[d] = 1e-4f > S[d] ? 1e-4f : S[d];            /* :60 */
+  float J = Sc[0] * Sc[1] * Sc[2];                                            /* vec::prod: left fold */
+  for (int d = 0; d < 3; ++d) tau[d] = 2 * mu * (Sc[d] - 1) * Sc[d] + lam * (J - 1) * J; /* :63-64 */
+  const float trace_tau = (tau[0] + tau[1]) + tau[2];
+  for (int d = 0; d < 3; ++d) s_trial[d] = tau[d] - (trace_tau / 3.f);
+  const float s_norm = sqrt_newton_raphson((s_trial[0] * s_trial[0] + s_trial[1] * s_trial[1]) + s_trial[2] * s_trial[2]);
+  const float scaled_tauy = sqrt_newton_raphson(2.f / (6.f - 3)) * yield_stress;  /* :68 */
+  if (s_norm - scaled_tauy > 0) {
+    const float alpha = scaled_tauy / s_norm;
+    J = 1.f;
+    for (int d = 0; d < 3; ++d) {
+      const float tau_new = alpha * s_trial[d] + (trace_tau / 3.f);
+      const float b2m4ac = mu * mu - 2 * mu * (lam * (J - 1) * J - tau_new);
+      const float sq = b2m4ac < 0 ? 0 : sqrt_newton_raphson(b2m4ac);
+      S[d] = (mu + sq) / (2 * mu);
+    }
+    /* F = U diag(S) V^T, math/matrix/MatrixUtils.h:26-49 */
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r)
+        F[3 * c + r] = (U[r] * S[0] * V[c] + U[3 + r] * S[1] * V[3 + c]) + U[6 + r] * S[2] * V[6 + c];
+  }
+  J = S[0] * S[1] * S[2];
+  const float smu = 2.f * mu, sl = lam * (J - 1.f);
+  Ph[0] = smu * (S[0] - 1.f) + sl * (S[1] * S[2]);
+  Ph[1] = smu * (S[1] - 1.f) + sl * (S[0] * S[2]);
+  Ph[2] = smu * (S[2] - 1.f) + sl * (S[0] * S[1]);
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r)
+      P[3*c + r] = (Ph[0]*U[r]*V[c] + Ph[1]*U[3 + r]*V[3 + c]) + Ph[2]*U[6 + r]*V[6 + c];
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r)
+      PF[3*c + r] = ((P[r]*F[c] + P[3 + r]*F[3 + c]) + P[6 + r]*F[6 + c]) * volume;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* simulation/Utils.hpp:30-174 LocalArena (collocated, quadratic) + InterpolationKernel.hpp   */
 /* ------------------------------------------------------------------------------------------ */
@@ -339,9 +392,10 @@ void zo_clean_grid(int nblocks, float *grid) { /* GridOp.hpp:54-69 */
   memset(grid, 0, sizeof(float) * 7 * 64 * (size_t)nblocks);
 }
 
-void zo_p2g_fcr(int n, const float *x, const float *v, const float *m, const float *C,
-                const float *F, float dx, float dt, float E, float nu, float volume, int table_size,
-                const int *keys, const int *indices, float *grid) {
+/* P2GTransfer for the F-based elastic models (P2G.hpp:84-91): model 0 = FixedCorotatedConfig, 1 = VonMisesFixedCorotatedConfig */
+static void p2g_elastic(int model, float yield_stress, int n, const float *x, const float *v, const float *m, const float *C,
+                        const float *F, float dx, float dt, float E, float nu, float volume, int table_size,
+                        const int *keys, const int *indices, float *grid) {
   const float dx_inv = (float)1.0 / dx;        /* P2G.hpp:43 */
   const float D_inv = 4.f * dx_inv * dx_inv;   /* :51 */
   float mu, lam;
@@ -350,7 +404,8 @@ void zo_p2g_fcr(int n, const float *x, const float *v, const float *m, const flo
     float contrib[9];
     const float *Cp = C + 9 * p, *vel = v + 3 * p;
     const float mass = m[p];
-    zo_stress_fixedcorotated(volume, mu, lam, F + 9 * p, contrib);            /* :87 */
+    if (model == 0) zo_stress_fixedcorotated(volume, mu, lam, F + 9 * p, contrib);   /* :87 */
+    else zo_stress_vonmises(volume, mu, lam, yield_stress, F + 9 * p, contrib);      /* :89-90 */
     for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;        /* :104 */
     zo_arena ar;
     arena_init(&ar, dx, x + 3 * p);                                           /* :107 */
@@ -372,6 +427,17 @@ void zo_p2g_fcr(int n, const float *x, const float *v, const float *m, const flo
       }
     }
   }
+}
+
+void zo_p2g_fcr(int n, const float *x, const float *v, const float *m, const float *C,
+                const float *F, float dx, float dt, float E, float nu, float volume, int table_size,
+                const int *keys, const int *indices, float *grid) {
+  p2g_elastic(0, 0.f, n, x, v, m, C, F, dx, dt, E, nu, volume, table_size, keys, indices, grid);
+}
+void zo_p2g_vonmises(int n, const float *x, const float *v, const float *m, const float *C, const float *F, float dx,
+                     float dt, float E, float nu, float yield_stress, float volume, int table_size, const int *keys,
+                     const int *indices, float *grid) {
+  p2g_elastic(1, yield_stress, n, x, v, m, C, F, dx, dt, E, nu, volume, table_size, keys, indices, grid);
 }
 
 /* EquationOfStateConfig branch of P2GTransfer, P2G.hpp:66-87 (weakly compressible fluid: J instead of F) */

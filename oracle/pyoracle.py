@@ -182,6 +182,24 @@ class Oracle:
                             _ptr(tab["indices"]), _ptr(grid))
         return grid
 
+    def stress_vonmises(self, volume, E, nu, yield_stress, F):
+        mu, lam = self.lame(E, nu)
+        F = np.ascontiguousarray(F, np.float32)
+        PF = np.empty(9, np.float32)
+        self.lib.zo_stress_vonmises(C.c_float(volume), C.c_float(mu), C.c_float(lam), C.c_float(yield_stress), _ptr(F), _ptr(PF))
+        return PF
+
+    def p2g_vonmises(self, P, tab, dx, dt, E, nu, yield_stress, volume, grid=None):
+        nb = tab["nblocks"]
+        if grid is None:
+            grid = np.zeros((nb, 7, 64), np.float32)
+        n = P["x"].shape[0]
+        self.lib.zo_p2g_vonmises(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["m"]), _ptr(P["C"]), _ptr(P["F"]),
+                                 C.c_float(dx), C.c_float(dt), C.c_float(E), C.c_float(nu), C.c_float(yield_stress),
+                                 C.c_float(volume), C.c_int(tab["table_size"]), _ptr(tab["keys"]), _ptr(tab["indices"]),
+                                 _ptr(grid))
+        return grid
+
     def p2g_eos(self, P, tab, dx, dt, bulk, viscosity, volume, grid=None):
         nb = tab["nblocks"]
         if grid is None:
@@ -432,6 +450,10 @@ class Ref:
             self.L.zpcref_mpm_p2g(self.h, C.c_float(dt), C.c_float(E), C.c_float(nu),
                                   C.c_float(volume))
 
+        def p2g_vonmises(self, dt, E, nu, yield_stress, volume):
+            self.L.zpcref_mpm_p2g_vonmises(self.h, C.c_float(dt), C.c_float(E), C.c_float(nu), C.c_float(yield_stress),
+                                           C.c_float(volume))
+
         def grid_update(self, dt, gravity, mode):
             self.L.zpcref_mpm_grid_update(self.h, C.c_float(dt), C.c_float(gravity), C.c_int(mode))
             return float(self.L.zpcref_mpm_get_maxvel(self.h))
@@ -500,6 +522,12 @@ class Ref:
         getattr(self.lib, "zpcref_reduce_%s_%s" % (op, kind))(C.c_int(nthreads), _ptr(a), _ptr(out),
                                                               C.c_size_t(a.size))
         return out[0]
+
+    def stress_vonmises(self, volume, E, nu, yield_stress, F):
+        F = np.ascontiguousarray(F, np.float32)
+        PF = np.empty(9, np.float32)
+        self.lib.zpcref_stress_vonmises(C.c_float(volume), C.c_float(E), C.c_float(nu), C.c_float(yield_stress), _ptr(F), _ptr(PF))
+        return PF
 
     def merge_sort_pair(self, kind, keys, vals, nthreads=0):
         k = np.array(keys, _ST[kind]); v = np.array(vals, np.int32)

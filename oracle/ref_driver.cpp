@@ -132,6 +132,18 @@ void zpcref_mpm_p2g(void *h, float dt, float E, float nu, float volume) {
         P2GTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.pars, s.table, s.grids});
   });
 }
+void zpcref_mpm_p2g_vonmises(void *h, float dt, float E, float nu, float yieldStress, float volume) {
+  auto &s = *(RefMpm *)h;
+  VonMisesFixedCorotatedConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.yieldStress = yieldStress;
+  model.volume = volume;
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(range(s.n),
+        P2GTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.pars, s.table, s.grids});
+  });
+}
 /// mode 0: ComputeGridBlockVelocity as shipped (v = mv/m + g dt; rhs ignored, GridOp.hpp:71-110).
 /// mode 1: explicit update v = (mv + rhs)/m + g dt, composed as "mv += rhs" then the functor.
 void zpcref_mpm_grid_update(void *h, float dt, float gravity, int mode) {
@@ -281,6 +293,13 @@ void zpcref_stress_fixedcorotated(float volume, float E, float nu, const float *
   vec<float, 9> f{}, pf{};
   for (int d = 0; d != 9; ++d) f[d] = F[d];
   compute_stress_fixedcorotated(volume, mu, lambda, f, pf);
+  for (int d = 0; d != 9; ++d) PF[d] = pf[d];
+}
+void zpcref_stress_vonmises(float volume, float E, float nu, float yieldStress, const float *F, float *PF) {
+  const auto [mu, lambda] = lame_parameters(E, nu);
+  vec<float, 9> f{}, pf{};
+  for (int d = 0; d != 9; ++d) f[d] = F[d];
+  compute_stress_vonmisesfixedcorotated(volume, mu, lambda, yieldStress, f, pf);
   for (int d = 0; d != 9; ++d) PF[d] = pf[d];
 }
 int zpcref_max_threads() { return (int)std::thread::hardware_concurrency(); }
