@@ -162,6 +162,13 @@ typedef struct zpc_fixed_corotated {
   float E, nu;
 } zpc_fixed_corotated;
 
+/* VonMisesFixedCorotatedConfig — physics/ConstitutiveModel.hpp:743-747 */
+typedef struct zpc_vonmises_fixed_corotated {
+  float rho, volume;
+  int dim;
+  float E, nu, yieldStress;
+} zpc_vonmises_fixed_corotated;
+
 /* EquationOfStateConfig — physics/ConstitutiveModel.hpp:730-734 (gamma is forced to 7 by P2G.hpp:72-75) */
 typedef struct zpc_equation_of_state {
   float rho, volume;
@@ -211,6 +218,20 @@ int zpcb200_grid_update(zpc_grids_view grids, const int *cnt, float dt, const fl
 /* ApplyBoundaryConditionOnGridBlocks (GridOp.hpp:112-164): for every cell with mass > 0 of blocks [0, *cnt), project
  * the grid velocity (channels 1-3) against the collider; node position = (blockkey*4 + cell coord) * dx. */
 int zpcb200_apply_boundary(zpc_grids_view grids, zpc_hashtable_view table, zpc_collider collider,
+                           zpc_stream_t stream);
+
+/* P2GTransfer<apic, VonMisesFixedCorotatedConfig> (P2G.hpp:89-90 -> compute_stress_vonmisesfixedcorotated,
+ * physics/ConstitutiveModel_Vol_dP.hpp:49-110): elastoplastic solid with a von Mises yield surface; G2P is
+ * zpcb200_g2p_apic (the projection of F stays local to P2G, like in the reference). */
+int zpcb200_p2g_apic_vonmises(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
+                              float dt, zpc_vonmises_fixed_corotated model, zpc_stream_t stream);
+
+/* ComputeGridBlockVelocity + ApplyBoundaryConditionOnGridBlocks for up to ZPCB200_MAX_COLLIDERS static colliders in one
+ * pass over the grid (same results as zpcb200_grid_update followed by zpcb200_apply_boundary per collider, in order;
+ * *maxVelSqr is taken before the projection, like the reference's sequence).  colliders_host: host array. */
+#define ZPCB200_MAX_COLLIDERS 4
+int zpcb200_grid_update_bc(zpc_grids_view grids, zpc_hashtable_view table, float dt, const float extf_host[3],
+                           int mode, const zpc_collider *colliders_host, int ncolliders, float *maxVelSqr,
                            zpc_stream_t stream);
 
 /* G2PTransfer<apic> (simulation/transfer/G2P.hpp:43-84), AoS layout, any order. */

@@ -62,6 +62,41 @@ def boundary_case(ref, name, s, G, **kw):
     print(name, "n", n, len(BOUNDARY_CASES), "colliders")
 
 
+def vonmises_margin(P, E, nu, ys):
+    """smallest relative distance of any particle's trial deviatoric stress norm from the yield radius"""
+    mu, lam = 0.5 * E / (1 + nu), E * nu / ((1 + nu) * (1 - 2 * nu))
+    F = P["F"].reshape(-1, 3, 3).transpose(0, 2, 1).astype(np.float64)      # column-major 9-vectors
+    sig = np.linalg.svd(F, compute_uv=False)
+    J = sig.prod(1, keepdims=True)
+    tau = 2 * mu * (sig - 1) * sig + lam * (J - 1) * J
+    sn = np.linalg.norm(tau - tau.mean(1, keepdims=True), axis=1)
+    r = np.sqrt(2.0 / 3.0) * ys
+    return float(np.abs(sn - r).min() / r), float((sn > r).mean())
+
+
+def vonmises_case(ref, name, s, G, ys, **kw):
+    """VonMisesFixedCorotatedConfig{E, nu, yieldStress=ys} substep (P2G.hpp:89-90, ConstitutiveModel_Vol_dP.hpp:49-110)"""
+    P = synth.elastic_cube(s, G, **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    margin, frac = vonmises_margin(P, synth.MODEL["E"], synth.MODEL["nu"], ys)
+    assert margin > 1e-3, margin      # no particle sits on the yield surface: host / device rounding cannot flip a branch
+    h = ref.mpm(n, dx, 0)
+    h.set_particles(P)
+    nb = h.partition()
+    tab = h.table()
+    h.clean_grid()
+    h.p2g_vonmises(synth.DT, synth.MODEL["E"], synth.MODEL["nu"], ys, P["volume"])
+    g1 = h.grid()
+    mx = h.grid_update(synth.DT, synth.GRAVITY, 1)
+    h.g2p(synth.DT)
+    out = h.get_particles()
+    h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), s=s, G=G, ys=ys, kw=repr(sorted(kw.items())), nblocks=nb,
+                        active_keys=tab["active_keys"], grid_p2g=g1, max_vel_sqr=mx, yielded_fraction=frac,
+                        x=out["x"], v=out["v"], C=out["C"], F=out["F"])
+    print(name, "n", n, "blocks", nb, "yielded fraction %.2f, margin %.2e" % (frac, margin))
+
+
 def eos_case(ref, name, s, G, **kw):
     """EquationOfStateConfig{bulk=4e4, gamma=7.15, viscosity=0.01} substep (P2G.hpp:66-87, G2P.hpp:69-73)"""
     P = synth.elastic_cube(s, G, **kw)
@@ -139,6 +174,7 @@ if __name__ == "__main__":
     mpm_case(r, "mpm_cube5_neg", 5, 16, 1, jitter_F=0.02, jitter_C=0.2, origin_cells=-9)
     eos_case(r, "mpm_cube6_eos", 6, 32, jitter_C=0.5, shuffle_seed=13)
     boundary_case(r, "mpm_cube7_boundary", 7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
+    vonmises_case(r, "mpm_cube6_vonmises", 6, 32, 2946.0, jitter_F=0.05, jitter_C=0.5, shuffle_seed=17)   # 39 % of the particles yield
     if "--all" in sys.argv:   # the primitive / SVD vectors use unseeded-order-independent inputs: regenerate on demand
         prims_case(r)
         svd_case(r)

@@ -117,3 +117,21 @@ def test_oracle_boundary_conditions_match_reference_golden(oracle):
         oracle.apply_boundary(g, tab["active_keys"], dx, geom, ctype, p0, p1)
         assert np.array_equal(g, z["grid_%d" % i]), (geom, ctype)
         assert (g != g0).any()          # the collider actually bites in every case
+
+
+def test_vonmises_golden_pins_the_oracle(oracle):
+    """reference-generated von Mises vectors (39 % of the particles yield) vs the oracle, by block key"""
+    import ast
+    from zpc_b200 import synth
+    z = np.load(os.path.join(G, "mpm_cube6_vonmises.npz"))
+    kw = dict(ast.literal_eval(str(z["kw"])))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    tab = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    g = oracle.p2g_vonmises(P, tab, dx, synth.DT, synth.MODEL["E"], synth.MODEL["nu"], float(z["ys"]), P["volume"])
+    ko = tab["active_keys"]
+    o = np.lexsort((ko[:, 2], ko[:, 1], ko[:, 0]))
+    kr = z["active_keys"]
+    r = np.lexsort((kr[:, 2], kr[:, 1], kr[:, 0]))
+    assert np.array_equal(ko[o], kr[r])
+    assert np.array_equal(g[o], z["grid_p2g"][r])

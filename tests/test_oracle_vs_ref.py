@@ -100,3 +100,32 @@ def test_f64_scan_reduce_match_reference(oracle, ref):
         assert np.array_equal(ref.scan("inclusive", "f64", a, nthreads), oracle.scan("inclusive", "f64", a))
         for op in ("sum", "min", "max"):
             assert ref.reduce(op, "f64", a, nthreads) == oracle.reduce(op, "f64", a)
+
+
+def test_vonmises_stress_and_p2g_bit_exact_vs_reference(oracle, ref):
+    """compute_stress_vonmisesfixedcorotated (ConstitutiveModel_Vol_dP.hpp:49-110) in the elastic regime (huge yield
+    stress) and deep in the plastic regime (radial return, projected F), then the whole P2G functor"""
+    from zpc_b200 import synth
+    rs = np.random.RandomState(8)
+    E, nu, vol = synth.MODEL["E"], synth.MODEL["nu"], 1e-6
+    yielded = 0
+    for ys in (240e6, 2000.0, 50.0):
+        for _ in range(200):
+            F = (np.eye(3) + rs.uniform(-0.2, 0.2, (3, 3))).astype(np.float32).reshape(9)
+            a, b = ref.stress_vonmises(vol, E, nu, ys, F), oracle.stress_vonmises(vol, E, nu, ys, F)
+            assert np.array_equal(a, b), (ys, F)
+            yielded += int(not np.array_equal(b, oracle.stress_fixedcorotated(vol, E, nu, F)))
+    assert 200 < yielded <= 400                       # the two small yield stresses really project
+    P = synth.elastic_cube(6, 16, jitter_F=0.1, jitter_C=0.5, shuffle_seed=2)
+    n, dx = P["x"].shape[0], P["dx"]
+    h = ref.mpm(n, dx, 0)
+    h.set_particles(P)
+    h.partition()
+    tab = h.table()
+    h.clean_grid()
+    h.p2g_vonmises(synth.DT, E, nu, 300.0, P["volume"])
+    g_ref = h.grid()
+    h.close()
+    g = oracle.p2g_vonmises(P, tab, dx, synth.DT, E, nu, 300.0, P["volume"])
+    assert np.array_equal(g, g_ref)
+    assert not np.array_equal(g, oracle.p2g(P, tab, dx, synth.DT, E, nu, P["volume"]))

@@ -54,6 +54,11 @@ class zpc_fixed_corotated(C.Structure):
     _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("E", C.c_float), ("nu", C.c_float)]
 
 
+class zpc_vonmises_fixed_corotated(C.Structure):
+    _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("E", C.c_float), ("nu", C.c_float),
+                ("yieldStress", C.c_float)]
+
+
 class zpc_equation_of_state(C.Structure):
     _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("bulk", C.c_float), ("gamma", C.c_float),
                 ("viscosity", C.c_float)]
@@ -505,7 +510,15 @@ def model_eos(volume, bulk=4.0e4, gamma=7.15, viscosity=0.0, rho=1000.0):
     return zpc_equation_of_state(rho, volume, 3, bulk, gamma, viscosity)
 
 
+def model_vonmises(volume, E=5.0e4, nu=0.4, yield_stress=240e6, rho=1000.0):
+    return zpc_vonmises_fixed_corotated(rho, volume, 3, E, nu, yield_stress)
+
+
 def p2g_transfer(pars, table, grids, dt, model, stream=None):
+    if isinstance(model, zpc_vonmises_fixed_corotated):
+        _check(lib().zpcb200_p2g_apic_vonmises(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
+                                               _stream_ptr(stream)), "p2g(vonmises)")
+        return
     if isinstance(model, zpc_equation_of_state):
         _check(lib().zpcb200_p2g_apic_eos(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
                                           _stream_ptr(stream)), "p2g(eos)")
@@ -541,6 +554,14 @@ def sphere_collider(center, radius, ctype=COLLIDER_STICKY):
 def apply_boundary_condition(collider, table, grids, stream=None):
     """ApplyBoundaryConditionOnGridBlocks{cuda_c, collider, table, grids} (GridOp.hpp:112-164)."""
     _check(lib().zpcb200_apply_boundary(grids.view(), table.view(), collider, _stream_ptr(stream)), "apply_boundary")
+
+
+def compute_grid_block_velocity_with_boundaries(grids, table, dt, extf, mode, colliders, max_vel_sqr, stream=None):
+    """ComputeGridBlockVelocity + ApplyBoundaryConditionOnGridBlocks for each collider, fused into one grid pass"""
+    e = (C.c_float * 3)(*[float(v) for v in extf])
+    arr = (zpc_collider * max(len(colliders), 1))(*colliders)
+    _check(lib().zpcb200_grid_update_bc(grids.view(), table.view(), C.c_float(dt), e, C.c_int(mode), arr, C.c_int(len(colliders)),
+                                        C.c_void_p(max_vel_sqr.data_ptr()), _stream_ptr(stream)), "grid_update_bc")
 
 
 def g2p_transfer(pars, table, grids, dt, stream=None, model=None):

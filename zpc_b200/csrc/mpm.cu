@@ -49,6 +49,31 @@ __global__ void part_place_kernel(const unsigned *sorted, const int *list_cnt, i
   if (blockIdx.x == 0 && threadIdx.x == 0) *cnt = n;
 }
 
+// Collider::resolveCollision over AnalyticLevelSet<Plane | Sphere> with the default rigid motion (geometry/Collider.h:98-127,
+// geometry/AnalyticLevelSet.h:11-43,130-157): projects the velocity of a node at (px,py,pz) that lies inside the collider
+__device__ __forceinline__ void collide(const zpc_collider &col, float px, float py, float pz, float &vx, float &vy, float &vz) {
+  const float d0 = px - col.origin[0], d1 = py - col.origin[1], d2 = pz - col.origin[2];
+  float n0, n1, n2, dist;
+  if (col.geometry == ZPC_GEOM_PLANE) {
+    n0 = col.normal[0]; n1 = col.normal[1]; n2 = col.normal[2];
+    dist = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));  // no contraction: the sign decides
+  } else {
+    const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+    const float len = sqrtf(l2);
+    dist = len - col.normal[0];
+    const bool tiny = l2 < 1e-7f;
+    n0 = tiny ? 0.f : d0 / len; n1 = tiny ? 0.f : d1 / len; n2 = tiny ? 0.f : d2 / len;
+  }
+  if (dist < 0.f) {
+    if (col.type == ZPC_COLLIDER_STICKY) {
+      vx = vy = vz = 0.f;
+    } else {
+      const float proj = n0 * vx + n1 * vy + n2 * vz;
+      if (col.type == ZPC_COLLIDER_SLIP || proj < 0.f) { vx -= proj * n0; vy -= proj * n1; vz -= proj * n2; }
+    }
+  }
+}
+
 // ApplyBoundaryConditionOnGridBlocks with a static analytic collider: one thread per (block, cell)
 __global__ void __launch_bounds__(256) apply_boundary_kernel(float *tiles, const int *__restrict__ active_keys, const int *cnt,
                                                              int nch, size_t cap_blocks, float dx, zpc_collider col) {
@@ -61,28 +86,53 @@ __global__ void __launch_bounds__(256) apply_boundary_kernel(float *tiles, const
     if (!(t[cell] > 0.f)) continue;
     const float px = ((float)active_keys[3 * b] * 4.f + (float)cx) * dx, py = ((float)active_keys[3 * b + 1] * 4.f + (float)cy) * dx,
                 pz = ((float)active_keys[3 * b + 2] * 4.f + (float)cz) * dx;
-    const float d0 = px - col.origin[0], d1 = py - col.origin[1], d2 = pz - col.origin[2];
-    float n0, n1, n2, dist;
-    if (col.geometry == ZPC_GEOM_PLANE) {
-      n0 = col.normal[0]; n1 = col.normal[1]; n2 = col.normal[2];
-      dist = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));  // no contraction: the sign decides
-    } else {
-      const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
-      const float len = sqrtf(l2);
-      dist = len - col.normal[0];
-      const bool tiny = l2 < 1e-7f;
-      n0 = tiny ? 0.f : d0 / len; n1 = tiny ? 0.f : d1 / len; n2 = tiny ? 0.f : d2 / len;
-    }
-    if (dist < 0.f) {
-      float vx = t[64 + cell], vy = t[128 + cell], vz = t[192 + cell];
-      if (col.type == ZPC_COLLIDER_STICKY) {
-        vx = vy = vz = 0.f;
-      } else {
-        const float proj = n0 * vx + n1 * vy + n2 * vz;
-        if (col.type == ZPC_COLLIDER_SLIP || proj < 0.f) { vx -= proj * n0; vy -= proj * n1; vz -= proj * n2; }
+    float vx = t[64 + cell], vy = t[128 + cell], vz = t[192 + cell];
+    const float ox = vx, oy = vy, oz = vz;
+    collide(col, px, py, pz, vx, vy, vz);
+    if (vx != ox || vy != oy || vz != oz) { t[64 + cell] = vx; t[128 + cell] = vy; t[192 + cell] = vz; }
+  }
+}
+
+// ComputeGridBlockVelocity followed by ApplyBoundaryConditionOnGridBlocks for up to ZPCB200_MAX_COLLIDERS colliders in
+// ONE pass over the grid: the velocity never leaves the registers between the two functors.
+// max |v|^2 is taken before the projection, as the reference's sequence of functors does.
+struct ColliderSet { zpc_collider c[ZPCB200_MAX_COLLIDERS]; int n; };
+__global__ void __launch_bounds__(256) grid_update_bc_kernel(float *tiles, const int *__restrict__ active_keys, const int *cnt, int nch,
+                                                             size_t cap_blocks, float dx, float dt, float ex, float ey, float ez, int mode,
+                                                             ColliderSet cols, float *max_vel_sqr) {
+  size_t nb = (size_t)*cnt;
+  if (nb > cap_blocks) nb = cap_blocks;
+  const int cell = threadIdx.x & 63;
+  const int cx = (cell >> 4) & 3, cy = (cell >> 2) & 3, cz = cell & 3;
+  float mx = 0.f;
+  for (size_t b = (size_t)blockIdx.x * 4 + (threadIdx.x >> 6); b < nb; b += (size_t)gridDim.x * 4) {
+    float *t = tiles + b * (size_t)nch * 64;
+    float mass = t[cell];
+    if (mass != 0.f) {
+      float mvx = t[64 + cell], mvy = t[128 + cell], mvz = t[192 + cell];
+      if (mode == 1) { mvx += t[256 + cell]; mvy += t[320 + cell]; mvz += t[384 + cell]; }
+      const float minv = 1.f / mass;
+      float vx = mvx * minv + ex * dt, vy = mvy * minv + ey * dt, vz = mvz * minv + ez * dt;
+      mx = fmaxf(mx, vx * vx + vy * vy + vz * vz);
+      if (mass > 0.f) {
+        const float px = ((float)active_keys[3 * b] * 4.f + (float)cx) * dx, py = ((float)active_keys[3 * b + 1] * 4.f + (float)cy) * dx,
+                    pz = ((float)active_keys[3 * b + 2] * 4.f + (float)cz) * dx;
+        for (int k = 0; k < cols.n; ++k) collide(cols.c[k], px, py, pz, vx, vy, vz);
       }
       t[64 + cell] = vx; t[128 + cell] = vy; t[192 + cell] = vz;
+    } else if (mode == 1) {
+      t[64 + cell] += t[256 + cell]; t[128 + cell] += t[320 + cell]; t[192 + cell] += t[384 + cell];
     }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  __shared__ float smx[8];
+  if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, smx[i]);
+    if (mx > 0.f) atomicMax((int *)max_vel_sqr, __float_as_int(mx));
   }
 }
 
@@ -150,6 +200,23 @@ int zpcb200_apply_boundary(zpc_grids_view g, zpc_hashtable_view tb, zpc_collider
   return ZPCB200_OK;
 }
 
+int zpcb200_grid_update_bc(zpc_grids_view g, zpc_hashtable_view tb, float dt, const float extf[3], int mode,
+                           const zpc_collider *colliders, int ncolliders, float *maxVelSqr, zpc_stream_t stream) {
+  if (!g.tiles || !tb.activeKeys || !tb.cnt || !extf || !maxVelSqr || (mode != 0 && mode != 1) || g.numChannels < (mode ? 7 : 4) ||
+      ncolliders < 0 || ncolliders > ZPCB200_MAX_COLLIDERS || (ncolliders && !colliders))
+    return ZPCB200_E_BADARG;
+  ColliderSet cs;
+  cs.n = ncolliders;
+  for (int k = 0; k < ncolliders; ++k) {
+    if ((unsigned)colliders[k].geometry > 1u || (unsigned)colliders[k].type > 2u) return ZPCB200_E_BADARG;
+    cs.c[k] = colliders[k];
+  }
+  grid_update_bc_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks, g.dx,
+                                                                           dt, extf[0], extf[1], extf[2], mode, cs, maxVelSqr);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
 int zpcb200_p2g_apic_fcr(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_fixed_corotated model,
                          zpc_stream_t stream) {
   if (P.count == 0) return ZPCB200_OK;  // empty range: nothing to launch (pointers of an empty container may be null)
@@ -158,6 +225,20 @@ int zpcb200_p2g_apic_fcr(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_
   zpcm::lame_host(model.E, model.nu, mu, lam);
   const unsigned grid = (unsigned)((P.count + 127) / 128);
   p2g_aos_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, zpcp::LegacyGrid{tb}, g.tiles, g.numChannels, g.dx, dt, model.volume, mu, lam);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_p2g_apic_vonmises(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt,
+                              zpc_vonmises_fixed_corotated model, zpc_stream_t stream) {
+  if (g.numChannels != 7 || !g.tiles || !tb.keys || !tb.indices) return ZPCB200_E_BADARG;
+  if (P.count && (!P.X || !P.V || !P.M || !P.C || !P.F)) return ZPCB200_E_BADARG;
+  if (!P.count) return ZPCB200_OK;
+  float mu, lam;
+  zpcm::lame_host(model.E, model.nu, mu, lam);
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  p2g_aos_vm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, zpcp::LegacyGrid{tb}, g.tiles, g.numChannels, g.dx, dt, model.volume, mu,
+                                                            lam, model.yieldStress);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }

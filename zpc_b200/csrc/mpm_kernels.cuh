@@ -68,6 +68,19 @@ __global__ void __launch_bounds__(128) p2g_aos_kernel(zpc_particles_view P, GA t
 }
 
 template <class GA>
+__global__ void __launch_bounds__(128) p2g_aos_vm_kernel(zpc_particles_view P, GA tb, float *tiles, int nch, float dx, float dt,
+                                                         float volume, float mu, float lam, float yield_stress) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.count) return;
+  float pos[3], vel[3], C[9], F[9];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { pos[d] = P.X[3 * p + d]; vel[d] = P.V[3 * p + d]; }
+#pragma unroll
+  for (int d = 0; d < 9; ++d) { C[d] = P.C[9 * p + d]; F[d] = P.F[9 * p + d]; }
+  zpcp::p2g_scatter_particle_vm(pos, vel, P.M[p], C, F, tb, tiles, nch, dx, dt, volume, mu, lam, yield_stress);
+}
+
+template <class GA>
 __global__ void __launch_bounds__(128) p2g_aos_eos_kernel(zpc_particles_view P, GA tb, float *tiles, int nch,
                                                           float dx, float dt, float volume, float bulk, float viscosity) {
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -185,6 +185,70 @@ __device__ __forceinline__ void stress_fcr(float volume, float mu, float lam, co
     for (int r = 0; r < 3; ++r) PF[3 * c + r] = (P[r] * F[c] + P[3 + r] * F[3 + c] + P[6 + r] * F[6 + c]) * volume;
 }
 
+// math::sqrtNewtonRaphson<float> (math/MathUtils.h:239-251): Newton iteration from 1 until the step is below
+// max(n * 1e-6, 128 eps).  Restated loop for loop: its result is only ~1e-6 accurate and the yield test depends on it.
+__device__ __forceinline__ float sqrt_newton_raphson(float n) {
+  const float eps = 128.f * 1.1920928955078125e-7f;
+  if (n < -eps) return __int_as_float(0x7fc00000);
+  if (n < eps) return 0.f;
+  float xn = 1.f;
+  float xnp1 = 0.5f * (xn + n / xn);
+  const float tol = fmaxf(n * 1e-6f, eps);
+  for (; fabsf(xnp1 - xn) > tol; xnp1 = 0.5f * (xn + n / xn)) xn = xnp1;
+  return xnp1;
+}
+
+// compute_stress_vonmisesfixedcorotated (physics/ConstitutiveModel_Vol_dP.hpp:49-110): fixed-corotated trial stress in
+// principal space, radial return onto the von Mises cylinder, projected singular values, then the fixed-corotated
+// P F^T with the projected F (the projection is not written back to the particle: P2G.hpp:85-91 works on a copy)
+__device__ __forceinline__ void stress_vonmises(float volume, float mu, float lam, float yield_stress, const float (&Fin)[9],
+                                                float (&PF)[9]) {
+  float F[9], U[9], S[3], V[9];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) F[d] = Fin[d];
+  svd3(F, U, S, V);
+  float Sc[3], tau[3], st[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) Sc[d] = 1e-4f > S[d] ? 1e-4f : S[d];
+  float J = Sc[0] * Sc[1] * Sc[2];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) tau[d] = 2 * mu * (Sc[d] - 1) * Sc[d] + lam * (J - 1) * J;
+  const float trace_tau = (tau[0] + tau[1]) + tau[2];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) st[d] = tau[d] - (trace_tau / 3.f);
+  const float s_norm = sqrt_newton_raphson((st[0] * st[0] + st[1] * st[1]) + st[2] * st[2]);
+  const float scaled_tauy = sqrt_newton_raphson(2.f / (6.f - 3)) * yield_stress;
+  if (s_norm - scaled_tauy > 0) {
+    const float alpha = scaled_tauy / s_norm;
+    J = 1.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float tau_new = alpha * st[d] + (trace_tau / 3.f);
+      const float b2m4ac = mu * mu - 2 * mu * (lam * (J - 1) * J - tau_new);
+      const float sq = b2m4ac < 0 ? 0.f : sqrt_newton_raphson(b2m4ac);
+      S[d] = (mu + sq) / (2 * mu);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) F[3 * c + r] = U[r] * S[0] * V[c] + U[3 + r] * S[1] * V[3 + c] + U[6 + r] * S[2] * V[6 + c];
+  }
+  J = S[0] * S[1] * S[2];
+  const float smu = 2.f * mu, sl = lam * (J - 1.f);
+  const float Ph[3] = {smu * (S[0] - 1.f) + sl * (S[1] * S[2]), smu * (S[1] - 1.f) + sl * (S[0] * S[2]),
+                       smu * (S[2] - 1.f) + sl * (S[0] * S[1])};
+  float P[9];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      P[3 * c + r] = Ph[0] * U[r] * V[c] + Ph[1] * U[3 + r] * V[3 + c] + Ph[2] * U[6 + r] * V[6 + c];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) PF[3 * c + r] = (P[r] * F[c] + P[3 + r] * F[3 + c] + P[6 + r] * F[6 + c]) * volume;
+}
+
 // LocalArena::init (simulation/Utils.hpp:51-70): base node, in-cell offset (scaled by dx), 3x3 weights
 struct Arena {
   int corner[3];

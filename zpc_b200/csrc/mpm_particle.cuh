@@ -90,6 +90,20 @@ static __device__ __forceinline__ void p2g_scatter_particle(const float (&pos)[3
   p2g_scatter_core(pos, vel, mass, C, contrib, tb, tiles, nch, dx);
 }
 
+// VonMisesFixedCorotatedConfig (P2G.hpp:89-90)
+template <class G>
+static __device__ __forceinline__ void p2g_scatter_particle_vm(const float (&pos)[3], const float (&vel)[3], float mass,
+                                                               const float (&C)[9], const float (&F)[9], const G &tb, float *tiles,
+                                                               int nch, float dx, float dt, float volume, float mu, float lam,
+                                                               float yield_stress) {
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  float contrib[9];
+  zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, contrib);
+#pragma unroll
+  for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+  p2g_scatter_core(pos, vel, mass, C, contrib, tb, tiles, nch, dx);
+}
+
 // EquationOfStateConfig (P2G.hpp:66-87): weakly compressible fluid, J instead of F; gamma is fixed to 7 by the reference
 template <class G>
 static __device__ __forceinline__ void p2g_scatter_particle_eos(const float (&pos)[3], const float (&vel)[3], float mass,
