@@ -10,6 +10,8 @@
 //   HashTable (i32,3,int)                   <- container/HashTable.hpp:15-206  (tableSize = next_2pow(n) * 16)
 //   Grids (f32,3,4) {m, v, rhs}             <- geometry/Structure.hpp:140-260
 //   Particles (f32,3) AoS x,v,m,C,F         <- geometry/Structurefree.hpp:22-224
+//   Bht (i32,3,int,16), SparseGrid (3,f32,8) <- container/Bht.hpp, geometry/SparseGrid.hpp  (+ Sg* functors on side-8 blocks)
+//   merge_sort, merge_sort_pair             <- cuda/execution/ExecutionPolicy.cuh:686-760
 //   partition_for_particles, CleanGridBlocks, P2GTransfer, ComputeGridBlockVelocity, G2PTransfer
 //       <- simulation/{sparsity,grid,transfer}/*.hpp; invoked as pol(functor) instead of pol(range, functor).
 // There is no host fallback: every call lands in the sm_100a kernels.
@@ -147,6 +149,22 @@ struct CudaExecutionPolicy {
     else if constexpr (std::is_same_v<K, uint64_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_radix_sort_u64(t, b, ki, ko, n, sbit, ebit, _stream); });
     else static_assert(sizeof(K) == 0, "radix sort keys: u32, i32, u64");
   }
+  // merge_sort_pair / merge_sort: stable, ascending, in place (ExecutionPolicy.cuh:686-760); keys int | float | double
+  template <typename K> void merge_sort_pair(K *keys, int *vals, size_t count) const {
+    const zpc_port k = make_port(keys), v = make_port(vals);
+    if constexpr (std::is_same_v<K, int32_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_merge_sort_pair_i32(t, b, k, v, count, _stream); });
+    else if constexpr (std::is_same_v<K, float>) twoPhase([&](void *t, size_t *b) { return zpcb200_merge_sort_pair_f32(t, b, k, v, count, _stream); });
+    else if constexpr (std::is_same_v<K, double>) twoPhase([&](void *t, size_t *b) { return zpcb200_merge_sort_pair_f64(t, b, k, v, count, _stream); });
+    else static_assert(sizeof(K) == 0, "merge sort keys: int, float, double");
+  }
+  template <typename K> void merge_sort(K *first, K *last) const {
+    const size_t n = (size_t)(last - first);
+    const zpc_port k = make_port(first);
+    if constexpr (std::is_same_v<K, int32_t>) twoPhase([&](void *t, size_t *b) { return zpcb200_merge_sort_i32(t, b, k, n, _stream); });
+    else if constexpr (std::is_same_v<K, float>) twoPhase([&](void *t, size_t *b) { return zpcb200_merge_sort_f32(t, b, k, n, _stream); });
+    else if constexpr (std::is_same_v<K, double>) twoPhase([&](void *t, size_t *b) { return zpcb200_merge_sort_f64(t, b, k, n, _stream); });
+    else static_assert(sizeof(K) == 0, "merge sort keys: int, float, double");
+  }
   // pol(functor): one C call per functor (the reference writes pol(range, functor))
   template <typename F> void operator()(F &&f) const { finish(f.launch(*this)); }
 };
@@ -161,6 +179,9 @@ template <typename K>
 void radix_sort_pair(const CudaExecutionPolicy &p, const K *ki, const int *vi, K *ko, int *vo, size_t count, int sbit = 0, int ebit = sizeof(K) * 8) {
   p.radix_sort_pair(ki, vi, ko, vo, count, sbit, ebit);
 }
+
+template <typename K> void merge_sort_pair(const CudaExecutionPolicy &p, K *keys, int *vals, size_t count) { p.merge_sort_pair(keys, vals, count); }
+template <typename K> void merge_sort(const CudaExecutionPolicy &p, K *first, K *last) { p.merge_sort(first, last); }
 
 // ---- containers of the MPM path -----------------------------------------------------------------------------
 inline size_t next_2pow(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
@@ -189,6 +210,50 @@ struct Particles {  // Particles<f32,3>, AoS attributes
   zpc_particles_view view() { return zpc_particles_view{M.data(), X.data(), V.data(), nullptr, nullptr, F.data(), C.data(), nullptr, _n}; }
 };
 struct FixedCorotatedConfig { float rho{1e3f}, volume{1.f}; int dim{3}; float E{5e4f}, nu{0.4f}; };  // ConstitutiveModel.hpp:739-742
+struct VonMisesFixedCorotatedConfig { float rho{1e3f}, volume{1.f}; int dim{3}; float E{5e4f}, nu{0.4f}, yieldStress{240e6f}; };  // :743-747
+
+// bht<i32,3,int,16> (container/Bht.hpp): buckets of 16, three universal hashes from std::mt19937(2), 16-byte key slots
+struct Bht {
+  size_t _tableSize;
+  uint32_t _hf[6];
+  Vector<int> keys, indices, status, _activeKeys, _cnt, _buildSuccess, _overflow;
+  explicit Bht(size_t numExpectedEntries)
+      : _tableSize{zpcb200_bht_table_size(numExpectedEntries)}, keys((_tableSize ? _tableSize : 1) * 4), indices(_tableSize ? _tableSize : 1),
+        status(_tableSize ? _tableSize : 1), _activeKeys((_tableSize ? _tableSize : 1) * 3), _cnt(1), _buildSuccess(1), _overflow(1) {
+    zpcb200_bht_params(_hf);
+    _cnt.setVal(0); _buildSuccess.setVal(1); _overflow.setVal(0);
+  }
+  int size() const { return _cnt.getVal(); }
+  zpc_bht_view view() {
+    zpc_bht_view v{keys.data(), indices.data(), status.data(), _activeKeys.data(), (uint32_t)_tableSize, (uint32_t)(_tableSize / 16),
+                   _cnt.data(), _buildSuccess.data(), {}};
+    for (int i = 0; i < 6; ++i) v.hf[i] = _hf[i];
+    return v;
+  }
+};
+// SparseGrid<3,f32,8> (geometry/SparseGrid.hpp:16-188): bht keyed by block origins + TileVector<f32,512> + index-to-world transform
+struct SparseGrid {
+  Bht _table;
+  size_t _numBlocks;
+  int _numChannels;
+  Vector<float> _grid;
+  float _transform[16];
+  float _background{0.f};
+  SparseGrid(int numChns, size_t numBlocks) : _table(numBlocks), _numBlocks{numBlocks}, _numChannels{numChns}, _grid((numBlocks ? numBlocks : 1) * numChns * 512) {
+    for (int i = 0; i < 16; ++i) _transform[i] = (i % 5 == 0) ? 1.f : 0.f;
+  }
+  void scale(float s) {  // Transform::preScale (uniform)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 4; ++j) _transform[4 * i + j] *= s;
+  }
+  void translate(const float t[3]) { for (int d = 0; d < 3; ++d) _transform[12 + d] += t[d]; }  // postTranslate
+  size_t numBlocks() const { return (size_t)_table.size(); }
+  zpc_sparsegrid_view view() {
+    zpc_sparsegrid_view v{_table.view(), _grid.data(), _numBlocks, _numChannels, {}, _background};
+    for (int i = 0; i < 16; ++i) v.transform[i] = _transform[i];
+    return v;
+  }
+};
 
 // ---- functors ---------------------------------------------------------------------------------------------------
 struct PartitionForParticles {  // CleanSparsity + ComputeSparsity + EnlargeSparsity{lo,hi}
@@ -204,6 +269,38 @@ struct PartitionForParticles {  // CleanSparsity + ComputeSparsity + EnlargeSpar
              : (int)cudaErrorMemoryAllocation;
   }
 };
+struct SgPartitionForParticles {  // the same convention on side-8 blocks, table = the SparseGrid's bht
+  Particles &pars; SparseGrid &sg; int lo{0}, hi{2};
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_port x{pars.X.data(), 0, 0, 0, 3};
+    size_t bytes = 0;
+    int rc = zpcb200_sg_partition_build(nullptr, &bytes, x, pars.size(), sg.view(), lo, hi, sg._table._overflow.data(), pol._stream);
+    if (rc) return rc;
+    void *t = pol.scratch(bytes);
+    size_t cap = pol._scratchBytes;
+    return t ? zpcb200_sg_partition_build(t, &cap, x, pars.size(), sg.view(), lo, hi, sg._table._overflow.data(), pol._stream)
+             : (int)cudaErrorMemoryAllocation;
+  }
+};
+struct SgCleanGridBlocks { SparseGrid &sg; int launch(const CudaExecutionPolicy &pol) { return zpcb200_sg_clean(sg.view(), pol._stream); } };
+struct SgP2GTransfer {
+  float dt; FixedCorotatedConfig model; Particles &pars; SparseGrid &sg;
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
+    return zpcb200_sg_p2g_apic_fcr(pars.view(), sg.view(), dt, m, pol._stream);
+  }
+};
+struct SgComputeGridBlockVelocity {
+  SparseGrid &sg; float dt; float gravity; float *maxVel; int mode{0};
+  int launch(const CudaExecutionPolicy &pol) {
+    const float extf[3] = {0.f, gravity, 0.f};
+    return zpcb200_sg_grid_update(sg.view(), dt, extf, mode, maxVel, pol._stream);
+  }
+};
+struct SgG2PTransfer {
+  float dt; SparseGrid &sg; Particles &pars;
+  int launch(const CudaExecutionPolicy &pol) { return zpcb200_sg_g2p_apic(pars.view(), sg.view(), dt, pol._stream); }
+};
 struct CleanGridBlocks {
   Grids &grids; HashTable &table;
   int launch(const CudaExecutionPolicy &pol) { return zpcb200_clean_grid(grids.view(), table._cnt.data(), pol._stream); }
@@ -213,6 +310,13 @@ struct P2GTransfer {  // P2GTransfer{cuda_c, wrapv<apic>{}, dt, model, pars, tab
   int launch(const CudaExecutionPolicy &pol) {
     zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
     return zpcb200_p2g_apic_fcr(pars.view(), table.view(), grids.view(), dt, m, pol._stream);
+  }
+};
+struct P2GTransferVonMises {  // P2GTransfer with VonMisesFixedCorotatedConfig (P2G.hpp:89-90)
+  float dt; VonMisesFixedCorotatedConfig model; Particles &pars; HashTable &table; Grids &grids;
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_vonmises_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu, model.yieldStress};
+    return zpcb200_p2g_apic_vonmises(pars.view(), table.view(), grids.view(), dt, m, pol._stream);
   }
 };
 struct ComputeGridBlockVelocity {  // {cuda_c, wrapv<apic>{}, grids, dt, gravity, maxVel}; mode 1 adds rhs (explicit update)

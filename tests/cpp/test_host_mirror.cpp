@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <numeric>
 #include <random>
 #include <stdexcept>
@@ -124,6 +125,61 @@ int main() {
     for (size_t i = 0; i < 9 * n; ++i) eF = std::max(eF, (double)std::fabs(gF[i] - F[i]));
     CHECK(ex <= 1e-5 && ev <= 1.2e-5 && eF <= 1.1e-5, "g2p x/v/F");
     std::printf("substep ok: %d blocks, err x %.2e v %.2e F %.2e\n", nb, ex, ev, eF);
+
+    // the same substep on a SparseGrid<3,f32,8> (bht partition, side-8 blocks): same particles within rounding
+    Particles pars2(n);
+    {
+      // re-create the initial state (x, v, C, F were advanced by the oracle above: rebuild them with the same generator)
+      std::mt19937 rng2(3);
+      std::vector<float> x2(3 * n), v2(3 * n), C2(9 * n), F2(9 * n);
+      size_t q2 = 0;
+      for (int i = 0; i < s; ++i) for (int j = 0; j < s; ++j) for (int k = 0; k < s; ++k) for (int q = 0; q < 8; ++q, ++q2) {
+        const int c3[3] = {i, j, k};
+        for (int d = 0; d < 3; ++d) {
+          x2[3 * q2 + d] = (7 + c3[d] + (((q >> (2 - d)) & 1) + U(rng2)) * 0.5f) * dx;
+          v2[3 * q2 + d] = (d == 1 ? -1.f : 0.f) + 0.2f * (U(rng2) - 0.5f);
+        }
+        for (int d = 0; d < 9; ++d) { C2[d + 9 * q2] = 0.3f * (U(rng2) - 0.5f); F2[d + 9 * q2] = (d % 4 == 0 ? 1.f : 0.f) + 0.04f * (U(rng2) - 0.5f); }
+      }
+      cudaMemcpy(pars2.X.data(), x2.data(), 12 * n, cudaMemcpyHostToDevice);
+      cudaMemcpy(pars2.V.data(), v2.data(), 12 * n, cudaMemcpyHostToDevice);
+      cudaMemcpy(pars2.M.data(), m.data(), 4 * n, cudaMemcpyHostToDevice);
+      cudaMemcpy(pars2.C.data(), C2.data(), 36 * n, cudaMemcpyHostToDevice);
+      cudaMemcpy(pars2.F.data(), F2.data(), 36 * n, cudaMemcpyHostToDevice);
+    }
+    SparseGrid sg(7, n / 16);
+    sg.scale(dx);
+    pol(SgPartitionForParticles{pars2, sg});
+    CHECK(sg._table._buildSuccess.getVal() == 1 && sg.numBlocks() > 0, "bht build");
+    maxVel.setVal(0.f);
+    pol(SgCleanGridBlocks{sg});
+    pol(SgP2GTransfer{dt, model, pars2, sg});
+    pol(SgComputeGridBlockVelocity{sg, dt, gravity, maxVel.data(), 1});
+    pol(SgG2PTransfer{dt, sg, pars2});
+    CHECK(pol.lastError() == 0, "latched error in SparseGrid substep");
+    CHECK(std::fabs(maxVel.getVal() - mx) <= 1e-5f * mx, "SparseGrid maxVel");
+    auto sx = pars2.X.toHost(), sv = pars2.V.toHost(), sF = pars2.F.toHost();
+    double dxm = 0, dvm = 0, dFm = 0;
+    for (size_t i = 0; i < 3 * n; ++i) { dxm = std::max(dxm, (double)std::fabs(sx[i] - x[i])); dvm = std::max(dvm, (double)std::fabs(sv[i] - v[i])); }
+    for (size_t i = 0; i < 9 * n; ++i) dFm = std::max(dFm, (double)std::fabs(sF[i] - F[i]));
+    CHECK(dxm <= 1e-5 && dvm <= 1.2e-5 && dFm <= 1.1e-5, "SparseGrid g2p x/v/F");
+    std::printf("SparseGrid substep ok: %zu blocks of 8^3, err x %.2e v %.2e F %.2e\n", sg.numBlocks(), dxm, dvm, dFm);
+  }
+  {  // merge_sort_pair: stable, in place, float keys with signed zeros
+    const size_t n = 100003;
+    std::mt19937 rng(5);
+    std::vector<float> k(n);
+    std::vector<int> v(n);
+    for (size_t i = 0; i < n; ++i) { k[i] = (float)((int)(rng() % 41) - 20) * 0.5f; v[i] = (int)i; }
+    k[3] = -0.0f; k[7] = 0.0f;
+    Vector<float> dk(k);
+    Vector<int> dv(v);
+    merge_sort_pair(pol, dk.data(), dv.data(), n);
+    std::vector<int> idx(v);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return k[a] < k[b]; });
+    CHECK(dv.toHost() == idx, "merge_sort_pair values");
+    auto ko = dk.toHost();
+    for (size_t i = 0; i < n; ++i) CHECK(std::memcmp(&ko[i], &k[idx[i]], 4) == 0, "merge_sort_pair keys");
   }
   std::printf("all host-mirror tests passed\n");
   return 0;
