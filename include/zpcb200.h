@@ -275,6 +275,22 @@ int zpcb200_sg_value_or(zpc_sparsegrid_view sg, int chn, const int *coords, size
 int zpcb200_sg_cell_coords(zpc_sparsegrid_view sg, const int *bno, const int *cno, size_t n, int *icoord,
                            float *wcoord, zpc_stream_t stream);
 
+/* Renumbering utilities.
+ * TileVector::reorderTiles (container/TileVector.hpp:641-691): scatter != 0: dst tile map[i] <- src tile i; gather:
+ * dst tile i <- src tile map[i].  tileLength = 32 | 64 | 512 ...; src != dst (the reference also builds a new vector). */
+int zpcb200_tilevector_reorder_tiles(const float *src, float *dst, int numChannels, int tileLength,
+                                     const int *map, size_t numTiles, int scatter, zpc_stream_t stream);
+/* bht::reorder (container/Bht.hpp:343-400): writes the reordered key list to orderedKeys (n x vec3i; the caller makes it
+ * the table's activeKeys, as the reference's move-assignment does) and renumbers the index stored with every key. */
+int zpcb200_bht_reorder(zpc_bht_view table, const int *map, int n, int scatter, int *orderedKeys,
+                        zpc_stream_t stream);
+/* Gather map that puts the n active blocks of a SparseGrid in Morton (Z-curve) order of their block coordinates:
+ * map[i] = current index of the block that becomes block i — 30-bit codes, radix_sort_pair of (code, index).  Feed it
+ * to zpcb200_bht_reorder and zpcb200_tilevector_reorder_tiles (gather).  *overflow is set if a block lies outside
+ * [-512, 511] blocks per axis. */
+int zpcb200_sg_morton_order(void *temp, size_t *temp_bytes, zpc_sparsegrid_view sg, int n, int *map,
+                            int *overflow, zpc_stream_t stream);
+
 /* ---- binned (block-sorted AoSoA) fast path ------------------------------------------------- */
 /* Bins: particles sorted by home block (the block ComputeSparsity assigns, SparsityOp.hpp:68-79),
  * stored densely in a 25-channel TileVector<f32,32>; bin b covers particles

@@ -150,6 +150,27 @@ class Oracle:
                                   _ptr(wc[i]))
         return ic, wc
 
+    def tilevector_reorder_tiles(self, tiles, map_, scatter):
+        tiles = np.ascontiguousarray(tiles, np.float32)
+        m = np.ascontiguousarray(map_, np.int32)
+        out = np.zeros_like(tiles)
+        self.lib.zo_tilevector_reorder_tiles(_ptr(tiles), _ptr(out), C.c_int(int(np.prod(tiles.shape[1:]))), _ptr(m),
+                                             C.c_int(m.size), C.c_int(int(scatter)))
+        return out
+
+    def bht_reorder(self, t, map_, scatter):
+        """returns a renumbered copy of table dict t (indices + active_keys)"""
+        m = np.ascontiguousarray(map_, np.int32)
+        n = m.size
+        out = dict(t)
+        out["indices"] = t["indices"].copy()
+        ok = np.zeros_like(np.ascontiguousarray(t["active_keys"][:n], np.int32))
+        ak = np.ascontiguousarray(t["active_keys"][:n], np.int32)
+        self.lib.zo_bht_reorder(C.c_int(t["table_size"]), _ptr(np.ascontiguousarray(t["hf"], np.uint32)), _ptr(t["keys16"]),
+                                _ptr(out["indices"]), _ptr(ak), C.c_int(n), _ptr(m), C.c_int(int(scatter)), _ptr(ok))
+        out["active_keys"] = ok
+        return out
+
     # ---- per particle math ----
     def lame(self, E, nu):
         mu, lam = C.c_float(), C.c_float()
@@ -347,6 +368,10 @@ class Ref:
             self.L.zpcref_bht_get(self.h, _ptr(k16), _ptr(idx), _ptr(st), _ptr(ak))
             return dict(keys16=k16, indices=idx, status=st, active_keys=ak[: i["cnt"]], cnt=i["cnt"], table_size=ts, hf=i["hf"])
 
+        def reorder(self, map_, scatter):
+            m = np.ascontiguousarray(map_, np.int32)
+            self.L.zpcref_bht_reorder(self.h, _ptr(m), C.c_int(int(scatter)))
+
         def load(self, keys16, indices, active_keys, cnt):
             """overwrite the container's arrays (e.g. with a table built on the GPU); query() then runs the
             reference's own BHTView::query over them"""
@@ -389,6 +414,12 @@ class Ref:
         def load_grid(self, data):
             data = np.ascontiguousarray(data, np.float32)
             self.L.zpcref_sg_load_grid(self.h, _ptr(data), C.c_int(data.shape[0]))
+
+        def reorder_tiles(self, map_, scatter):
+            m = np.ascontiguousarray(map_, np.int32)
+            out = np.empty((m.size, self.nch, 512), np.float32)
+            self.L.zpcref_sg_reorder_tiles(self.h, _ptr(m), C.c_int(m.size), C.c_int(int(scatter)), _ptr(out))
+            return out
 
         def value_or(self, chn, coords, dflt):
             coords = np.ascontiguousarray(coords, np.int32).reshape(-1, 3)

@@ -397,3 +397,25 @@ void zpcref_sg_world_to_index(void *h, const float *x, int n, float *X) {
   }
 }
 }
+
+// TileVector::reorderTiles (container/TileVector.hpp:641-691) on the SparseGrid's grid and bht::reorder
+// (container/Bht.hpp:343-400), both with the reference's seq policy; scatter != 0 -> wrapv<true>
+extern "C" {
+void zpcref_sg_reorder_tiles(void *h, const int *map, int ntiles, int scatter, float *grid_out) {
+  auto &g = *(RefSg *)h;
+  Vector<int> m{(size_t)g._grid.numTiles(), memsrc_e::host, -1};
+  for (size_t i = 0; i < m.size(); ++i) m[i] = i < (size_t)ntiles ? map[i] : (int)i;
+  auto pol = seq_exec();
+  if (scatter) g._grid.reorderTiles(pol, m, wrapv<true>{});
+  else g._grid.reorderTiles(pol, m, wrapv<false>{});
+  std::memcpy(grid_out, g._grid.data(), (size_t)ntiles * g.numChannels() * 512 * sizeof(float));
+}
+void zpcref_bht_reorder(void *h, const int *map, int scatter) {
+  auto &t = *(RefBht *)h;
+  Vector<int> m{(size_t)t.size(), memsrc_e::host, -1};
+  for (size_t i = 0; i < m.size(); ++i) m[i] = map[i];
+  auto pol = seq_exec();
+  if (scatter) t.reorder(pol, m, wrapv<true>{});
+  else t.reorder(pol, m, wrapv<false>{});
+}
+}

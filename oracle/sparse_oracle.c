@@ -167,3 +167,37 @@ int zo_sg_partition_build(int n, const float *x, float dx, int table_size, const
         }
   return *cnt;
 }
+
+/* TileVector::reorderTiles, container/TileVector.hpp:641-691 (TileVectorTileReorder): scatter: ordered tile map[i] <- tile i;
+ * gather: ordered tile i <- tile map[i].  tile_floats = numChannels * tile length. */
+void zo_tilevector_reorder_tiles(const float *src, float *dst, int tile_floats, const int *map, int ntiles, int scatter) {
+  for (int i = 0; i < ntiles; ++i) {
+    const int j = map[i];
+    const float *s = src + (size_t)(scatter ? i : j) * tile_floats;
+    float *d = dst + (size_t)(scatter ? j : i) * tile_floats;
+    memcpy(d, s, sizeof(float) * (size_t)tile_floats);
+  }
+}
+
+/* bht::reorder, container/Bht.hpp:343-400 (ReorderBht): the ordered key list and the index stored with every key are
+ * renumbered through map (scatter: old i -> new map[i]; gather: new i <- old map[i]); ordered_keys replaces activeKeys. */
+void zo_bht_reorder(int table_size, const uint32_t hf[6], const int *keys16, int *indices, const int *active_keys, int n,
+                    const int *map, int scatter, int *ordered_keys) {
+  const int nb = table_size / 16;
+  for (int i = 0; i < n; ++i) {
+    const int j = map[i];
+    const int *key = active_keys + 3 * (scatter ? i : j);
+    int *ok = ordered_keys + 3 * (scatter ? j : i);
+    ok[0] = key[0]; ok[1] = key[1]; ok[2] = key[2];
+    /* query(key, false_c): the slot */
+    for (int iter = 0; iter < 3; ++iter) {
+      const int b = (int)(zo_bht_hash(hf[2 * iter], hf[2 * iter + 1], key) % (uint32_t)nb) * 16;
+      int loc = 0;
+      for (; loc != 16; ++loc) {
+        const int *k = keys16 + 4 * (size_t)(b + loc);
+        if (k[0] == key[0] && k[1] == key[1] && k[2] == key[2]) break;
+      }
+      if (loc != 16) { indices[b + loc] = scatter ? j : i; break; }
+    }
+  }
+}

@@ -101,3 +101,31 @@ def test_sparsegrid_accessors_match_reference(oracle, ref):
     assert np.array_equal(ic_r, ic_o)
     np.testing.assert_allclose(wc_r, wc_o, rtol=1e-6, atol=1e-6)
     sg.close()
+
+
+@pytest.mark.parametrize("scatter", [False, True])
+def test_reorder_tiles_and_bht_reorder_match_reference(oracle, ref, scatter):
+    """TileVector::reorderTiles + bht::reorder (the SparseGrid renumbering utilities) vs the reference containers"""
+    rs = np.random.RandomState(12)
+    nb, nch = 37, 3
+    keys = _keys(rs, nb, span=5)
+    perm = rs.permutation(nb).astype(np.int32)
+    grid = rs.uniform(-1, 1, (nb, nch, 512)).astype(np.float32)
+    sg = Ref.SparseGrid(ref, nb, nch)
+    sg.table.insert(keys)
+    sg.load_grid(grid)
+    o = oracle.bht_new(nb)
+    oracle.bht_insert(o, keys)
+    o["active_keys"] = o["active_keys"][:nb].copy()
+    # tiles
+    assert np.array_equal(sg.reorder_tiles(perm, scatter), oracle.tilevector_reorder_tiles(grid, perm, scatter))
+    # table
+    sg.table.reorder(perm, scatter)
+    a = sg.table.arrays()
+    o2 = oracle.bht_reorder(o, perm, scatter)
+    assert np.array_equal(a["active_keys"], o2["active_keys"])
+    occ = a["keys16"][:, 0] != 0x3F3F3F3F
+    assert np.array_equal(a["indices"][occ], o2["indices"][occ])
+    # after renumbering, key k of the new order resolves to its new index
+    assert np.array_equal(oracle.bht_query(o2, o2["active_keys"]), np.arange(nb))
+    sg.close()

@@ -360,6 +360,37 @@ class SparseGrid:
         return self.table.size()
 
 
+def reorder_tiles(src, dst, num_channels, tile_length, map_, scatter=False, stream=None):
+    """TileVector::reorderTiles on raw tile storage (src, dst: float32 device tensors of whole tiles; map_: int32)"""
+    _check(lib().zpcb200_tilevector_reorder_tiles(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_int(num_channels),
+                                                  C.c_int(tile_length), C.c_void_p(map_.data_ptr()), C.c_size_t(map_.numel()),
+                                                  C.c_int(int(scatter)), _stream_ptr(stream)), "reorder_tiles")
+
+
+def bht_reorder(table, map_, scatter=False, stream=None):
+    """bht::reorder: renumber the table through map_ (int32 device tensor of table.size() entries)"""
+    n = map_.numel()
+    ordered = torch.zeros_like(table.active_keys)
+    _check(lib().zpcb200_bht_reorder(table.view(), C.c_void_p(map_.data_ptr()), C.c_int(n), C.c_int(int(scatter)),
+                                     C.c_void_p(ordered.data_ptr()), _stream_ptr(stream)), "bht_reorder")
+    table.active_keys = ordered
+
+
+def sg_reorder_morton(sg, stream=None):
+    """put the active blocks of a SparseGrid in Morton order (table numbering + grid tiles); returns the gather map"""
+    n = sg.table.size()
+    map_ = torch.empty(max(n, 1), dtype=torch.int32, device=sg.grid.device)
+    _two_phase(lib().zpcb200_sg_morton_order, (sg.view(), C.c_int(n), C.c_void_p(map_.data_ptr()),
+                                               C.c_void_p(sg.table.overflow.data_ptr())), (), stream)
+    map_ = map_[:n]
+    if n:
+        bht_reorder(sg.table, map_, False, stream)
+        new_grid = torch.zeros_like(sg.grid)
+        reorder_tiles(sg.grid, new_grid, sg.nch, 512, map_, False, stream)
+        sg.grid = new_grid
+    return map_
+
+
 def sg_partition_for_particles(x_port, n, sg, stream=None, enlarge=(0, 2)):
     _two_phase(lib().zpcb200_sg_partition_build, (x_port, C.c_size_t(n), sg.view(), C.c_int(enlarge[0]), C.c_int(enlarge[1]),
                                                   C.c_void_p(sg.table.overflow.data_ptr())), (), stream)

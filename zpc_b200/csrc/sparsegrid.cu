@@ -98,6 +98,57 @@ __global__ void sg_cell_coords_kernel(zpc_sparsegrid_view sg, const int *__restr
   }
 }
 
+// TileVector::reorderTiles (container/TileVector.hpp:641-691): float4 copies, one tile = tile_f4 float4
+__global__ void reorder_tiles_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t tile_f4, const int *__restrict__ map,
+                                     size_t ntiles, int scatter) {
+  const size_t total = ntiles * tile_f4;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t / tile_f4, r = t % tile_f4;
+    const size_t j = (size_t)map[i];
+    if (scatter) dst[j * tile_f4 + r] = src[t];
+    else dst[t] = src[j * tile_f4 + r];
+  }
+}
+
+// bht::reorder (container/Bht.hpp:343-400, ReorderBht): new key list + renumbered index of every key's slot
+__global__ void bht_reorder_kernel(zpc_bht_view tb, const int *__restrict__ map, int n, int scatter, int *ordered_keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = map[i];
+  const int src = scatter ? i : j, dst = scatter ? j : i;
+  const int kx = tb.activeKeys[3 * (size_t)src], ky = tb.activeKeys[3 * (size_t)src + 1], kz = tb.activeKeys[3 * (size_t)src + 2];
+  ordered_keys[3 * (size_t)dst] = kx; ordered_keys[3 * (size_t)dst + 1] = ky; ordered_keys[3 * (size_t)dst + 2] = kz;
+  bool found = false;
+  for (int it = 0; it < 3 && !found; ++it) {
+    const unsigned b = zpcm::bht_hash(tb.hf[2 * it], tb.hf[2 * it + 1], kx, ky, kz) % tb.numBuckets * 16u;
+    const int4 *k = reinterpret_cast<const int4 *>(tb.keys) + b;
+    for (int s2 = 0; s2 < 16; ++s2) {
+      const int4 c = k[s2];
+      if (c.x == kx && c.y == ky && c.z == kz) { tb.indices[b + s2] = dst; found = true; break; }
+    }
+  }
+  if (!found && tb.success) *tb.success = 0;
+}
+
+// 30-bit Morton code of a block (10 bits per axis of key/8 + 512) and its current index
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+  v &= 1023u;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void sg_morton_kernel(const int *__restrict__ active_keys, int n, unsigned *codes, int *ids, int *overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int bx = (active_keys[3 * (size_t)i] >> 3) + 512, by = (active_keys[3 * (size_t)i + 1] >> 3) + 512,
+            bz = (active_keys[3 * (size_t)i + 2] >> 3) + 512;
+  if (((unsigned)bx | (unsigned)by | (unsigned)bz) >= 1024u && overflow) *overflow = 1;
+  codes[i] = (spread10((unsigned)bx) << 2) | (spread10((unsigned)by) << 1) | spread10((unsigned)bz);
+  ids[i] = i;
+}
+
 // dx of an axis-aligned uniform transform without translation; false otherwise
 bool sg_uniform_dx(const zpc_sparsegrid_view &sg, float &dx) {
   const float *M = sg.transform;
@@ -168,6 +219,46 @@ int zpcb200_sg_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_
   sg_place_kernel<<<G, 256, 0, s>>>((const unsigned *)(t + L.off_sorted), (const int *)t, L.list_cap, sg.table, overflow);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
+}
+
+int zpcb200_tilevector_reorder_tiles(const float *src, float *dst, int numChannels, int tileLength, const int *map, size_t numTiles,
+                                     int scatter, zpc_stream_t stream) {
+  if (numChannels <= 0 || tileLength <= 0 || (tileLength & 3) || (numTiles && (!src || !dst || !map || src == dst))) return ZPCB200_E_BADARG;
+  if (!numTiles) return ZPCB200_OK;
+  reorder_tiles_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>((const float4 *)src, (float4 *)dst,
+                                                                          (size_t)numChannels * tileLength / 4, map, numTiles, scatter);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_bht_reorder(zpc_bht_view table, const int *map, int n, int scatter, int *orderedKeys, zpc_stream_t stream) {
+  if (n < 0 || (n && (!map || !orderedKeys || !sg_table_ok(table) || orderedKeys == table.activeKeys))) return ZPCB200_E_BADARG;
+  if (!n) return ZPCB200_OK;
+  bht_reorder_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(table, map, n, scatter, orderedKeys);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_sg_morton_order(void *temp, size_t *temp_bytes, zpc_sparsegrid_view sg, int n, int *map, int *overflow, zpc_stream_t stream) {
+  if (!temp_bytes || n < 0) return ZPCB200_E_BADARG;
+  size_t sort_bytes = 0;
+  zpc_port none = {nullptr, 0, 0, 0, 1};
+  int rc = zpcb200_radix_sort_pair_u32(nullptr, &sort_bytes, none, none, none, none, (size_t)n, 0, 30, nullptr);
+  if (rc) return rc;
+  const size_t o_codes = 0, o_ids = zpc_align_up(4 * (size_t)n, 256), o_codes2 = o_ids + zpc_align_up(4 * (size_t)n, 256),
+               o_sort = o_codes2 + zpc_align_up(4 * (size_t)n, 256), need = o_sort + sort_bytes;
+  if (!temp) { *temp_bytes = need; return ZPCB200_OK; }
+  if (*temp_bytes < need) return ZPCB200_E_TEMP_TOO_SMALL;
+  if (!n) return ZPCB200_OK;
+  if (!map || !sg.table.activeKeys) return ZPCB200_E_BADARG;
+  char *t = (char *)temp;
+  unsigned *codes = (unsigned *)(t + o_codes), *codes2 = (unsigned *)(t + o_codes2);
+  int *ids = (int *)(t + o_ids);
+  sg_morton_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sg.table.activeKeys, n, codes, ids, overflow);
+  ZPC_CHECK_LAUNCH();
+  zpc_port pc = {codes, 0, 0, 0, 1}, pi = {ids, 0, 0, 0, 1}, pc2 = {codes2, 0, 0, 0, 1}, pm = {map, 0, 0, 0, 1};
+  size_t sb = sort_bytes;
+  return zpcb200_radix_sort_pair_u32(t + o_sort, &sb, pc, pi, pc2, pm, (size_t)n, 0, 30, stream);
 }
 
 int zpcb200_sg_clean(zpc_sparsegrid_view sg, zpc_stream_t stream) {
