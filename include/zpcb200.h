@@ -176,14 +176,21 @@ typedef struct zpc_equation_of_state {
   float bulk, gamma, viscosity;
 } zpc_equation_of_state;
 
-/* A static analytic Collider — geometry/Collider.h:10-127 with its default rigid motion (R = I, s = 1, b = 0, no
- * velocity) over AnalyticLevelSet<Plane> / <Sphere> (geometry/AnalyticLevelSet.h:11-43, 130-157). */
+/* An analytic Collider — geometry/Collider.h:10-143 over AnalyticLevelSet<Plane> / <Sphere>
+ * (geometry/AnalyticLevelSet.h:11-43, 130-157) with its rigid motion x = R s X + b (Collider.h:16-24, 136-143):
+ * translation b and its rate, rotation R (row-major) and angular velocity, uniform scale s and its rate.  The level set
+ * is given in material space; the defaults (b = 0, R = I, s = 1, all rates 0) are a static collider.  Initialise with
+ * zpcb200_collider_static() or set every field. */
 enum { ZPC_GEOM_PLANE = 0, ZPC_GEOM_SPHERE = 1 };
 enum { ZPC_COLLIDER_STICKY = 0, ZPC_COLLIDER_SLIP = 1, ZPC_COLLIDER_SEPARATE = 2 }; /* collider_e, Collider.h:8 */
 typedef struct zpc_collider {
   int geometry, type;
-  float origin[3]; /* plane origin | sphere centre */
+  float origin[3]; /* plane origin | sphere centre (material space) */
   float normal[3]; /* plane unit normal | {radius, -, -} */
+  float b[3], dbdt[3];
+  float R[9];
+  float omega[3];
+  float s, dsdt;
 } zpc_collider;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -214,6 +221,9 @@ int zpcb200_p2g_apic_fcr(zpc_particles_view pars, zpc_hashtable_view table, zpc_
  * mode 0 = as shipped (rhs ignored); mode 1 = explicit update v = (mv + rhs)/m + extf*dt. */
 int zpcb200_grid_update(zpc_grids_view grids, const int *cnt, float dt, const float extf_host[3],
                         int mode, float *maxVelSqr, zpc_stream_t stream);
+
+/* host helper: a collider with the default rigid motion */
+zpc_collider zpcb200_collider_static(int geometry, int type, const float origin[3], const float normal_or_radius[3]);
 
 /* ApplyBoundaryConditionOnGridBlocks (GridOp.hpp:112-164): for every cell with mass > 0 of blocks [0, *cnt), project
  * the grid velocity (channels 1-3) against the collider; node position = (blockkey*4 + cell coord) * dx. */

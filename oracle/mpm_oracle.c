@@ -583,42 +583,74 @@ void zo_g2p_eos(int n, float *x, float *v, float *C, float *Jp, float dx, float 
  * default R = I, s = 1, b = dbdt = omega = 0, so v_object = 0): geom 0 = Plane{origin p0, normal p1}
  * (AnalyticLevelSet.h:11-43), geom 1 = Sphere{centre p0, radius p1[0]} (:130-157); type = collider_e
  * {0 Sticky, 1 Slip, 2 Separate} (Collider.h:8). */
-void zo_apply_boundary(int nblocks, const int *active_keys, float *grid, float dx, int geom, int type,
-                       const float p0[3], const float p1[3]) {
+/* motion (may be NULL = the default rigid motion): b[3], dbdt[3], R[9] row-major, omega[3], s, dsdt — Collider.h:16-24,136-143 */
+void zo_apply_boundary_moving(int nblocks, const int *active_keys, float *grid, float dx, int geom, int type,
+                              const float p0[3], const float p1[3], const float *motion) {
+  float bb[3] = {0, 0, 0}, dbdt[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, om[3] = {0, 0, 0}, sc = 1.f, dsdt = 0.f;
+  if (motion) {
+    for (int k = 0; k < 3; ++k) { bb[k] = motion[k]; dbdt[k] = motion[3 + k]; om[k] = motion[15 + k]; }
+    for (int k = 0; k < 9; ++k) R[k] = motion[6 + k];
+    sc = motion[18]; dsdt = motion[19];
+  }
   for (int b = 0; b < nblocks; ++b) {
     float *tile = grid + (size_t)b * 7 * 64;
     for (int c = 0; c < 64; ++c) {
       if (!(tile[c] > 0)) continue;                                    /* GridOp.hpp:141 */
       const int cc[3] = {(c >> 4) & 3, (c >> 2) & 3, c & 3};           /* cellid_to_coord, Structure.hpp:836-847 */
-      float pos[3], vel[3], n[3], d[3];
+      float pos[3], vel[3], xmb[3], X[3], nm[3], n[3], d[3], vobj[3];
       for (int k = 0; k < 3; ++k) {
         pos[k] = ((float)active_keys[3 * b + k] * 4.f + (float)cc[k]) * dx;   /* :143-144 */
         vel[k] = tile[(1 + k) * 64 + c];
-        d[k] = pos[k] - p0[k];
+        xmb[k] = pos[k] - bb[k];                                        /* Collider.h:106 */
       }
+      const float one_over_s = 1 / sc;
+      for (int i = 0; i < 3; ++i) {                                     /* X = R^T (x - b) * (1/s), :108 */
+        float sum = 0.f;
+        for (int j = 0; j < 3; ++j) sum += R[3 * j + i] * xmb[j];
+        X[i] = sum * one_over_s;
+      }
+      for (int k = 0; k < 3; ++k) d[k] = X[k] - p0[k];
       float dist;
       if (geom == 0) {
         dist = 0.f;
         for (int k = 0; k < 3; ++k) dist += p1[k] * d[k];              /* _normal.dot(x - _origin) */
-        for (int k = 0; k < 3; ++k) n[k] = p1[k];
+        for (int k = 0; k < 3; ++k) nm[k] = p1[k];
       } else {
         float l2 = 0.f;
         for (int k = 0; k < 3; ++k) l2 += d[k] * d[k];
         const float len = sqrtf(l2);
         dist = len - p1[0];
-        for (int k = 0; k < 3; ++k) n[k] = l2 < 1e-7f ? 0.f : d[k] / len;   /* :148-152 */
+        for (int k = 0; k < 3; ++k) nm[k] = l2 < 1e-7f ? 0.f : d[k] / len;   /* AnalyticLevelSet.h:148-152 */
       }
-      if (dist < 0.f) {                                                 /* Collider.h:110 (erosion 0) */
+      if (dist < 0.f) {                                                 /* Collider.h:109 (erosion 0) */
+        /* v_object = omega x (x-b) + (dsdt/s)(x-b) + R s V_material(= 0) + dbdt, :110-111 */
+        const float cr[3] = {om[1] * xmb[2] - om[2] * xmb[1], om[2] * xmb[0] - om[0] * xmb[2], om[0] * xmb[1] - om[1] * xmb[0]};
+        for (int i = 0; i < 3; ++i) {
+          float rs = 0.f;
+          for (int j = 0; j < 3; ++j) rs += (R[3 * i + j] * sc) * 0.f;
+          vobj[i] = ((cr[i] + (dsdt * one_over_s) * xmb[i]) + rs) + dbdt[i];
+        }
         if (type == 0) {
-          vel[0] = vel[1] = vel[2] = 0.f;                               /* Sticky: v = v_object = 0 */
+          for (int k = 0; k < 3; ++k) vel[k] = vobj[k];                 /* Sticky */
         } else {
+          for (int k = 0; k < 3; ++k) vel[k] -= vobj[k];
+          for (int i = 0; i < 3; ++i) {                                 /* n = R * normal(X), :116 */
+            float sum = 0.f;
+            for (int j = 0; j < 3; ++j) sum += R[3 * i + j] * nm[j];
+            n[i] = sum;
+          }
           float proj = 0.f;
           for (int k = 0; k < 3; ++k) proj += n[k] * vel[k];
           if ((type == 2 && proj < 0.f) || type == 1)
             for (int k = 0; k < 3; ++k) vel[k] -= proj * n[k];
+          for (int k = 0; k < 3; ++k) vel[k] += vobj[k];
         }
       }
       for (int k = 0; k < 3; ++k) tile[(1 + k) * 64 + c] = vel[k];      /* block.set(1, cellid, vel) */
     }
   }
+}
+void zo_apply_boundary(int nblocks, const int *active_keys, float *grid, float dx, int geom, int type,
+                       const float p0[3], const float p1[3]) {
+  zo_apply_boundary_moving(nblocks, active_keys, grid, dx, geom, type, p0, p1, 0);
 }

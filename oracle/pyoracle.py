@@ -244,11 +244,18 @@ class Oracle:
                                 C.c_int(mode), _ptr(mx))
         return float(mx[0])
 
-    def apply_boundary(self, grid, active_keys, dx, geom, ctype, p0, p1):
+    def apply_boundary(self, grid, active_keys, dx, geom, ctype, p0, p1, motion=None):
+        """motion: None (static) or 20 floats b[3], dbdt[3], R[9] row-major, omega[3], s, dsdt"""
         k = np.ascontiguousarray(active_keys, np.int32)
         a = np.ascontiguousarray(p0, np.float32); b = np.ascontiguousarray(p1, np.float32)
-        self.lib.zo_apply_boundary(C.c_int(grid.shape[0]), _ptr(k), _ptr(grid), C.c_float(dx), C.c_int(geom),
-                                   C.c_int(ctype), _ptr(a), _ptr(b))
+        if motion is None:
+            self.lib.zo_apply_boundary(C.c_int(grid.shape[0]), _ptr(k), _ptr(grid), C.c_float(dx), C.c_int(geom),
+                                       C.c_int(ctype), _ptr(a), _ptr(b))
+        else:
+            m = np.ascontiguousarray(motion, np.float32)
+            assert m.size == 20
+            self.lib.zo_apply_boundary_moving(C.c_int(grid.shape[0]), _ptr(k), _ptr(grid), C.c_float(dx), C.c_int(geom),
+                                              C.c_int(ctype), _ptr(a), _ptr(b), _ptr(m))
 
     def g2p(self, P, tab, grid, dx, dt):
         n = P["x"].shape[0]
@@ -492,9 +499,13 @@ class Ref:
         def g2p(self, dt):
             self.L.zpcref_mpm_g2p(self.h, C.c_float(dt))
 
-        def apply_boundary(self, geom, ctype, p0, p1):
+        def apply_boundary(self, geom, ctype, p0, p1, motion=None):
             a = np.ascontiguousarray(p0, np.float32); b = np.ascontiguousarray(p1, np.float32)
-            self.L.zpcref_mpm_apply_boundary(self.h, C.c_int(geom), C.c_int(ctype), _ptr(a), _ptr(b))
+            if motion is None:
+                self.L.zpcref_mpm_apply_boundary(self.h, C.c_int(geom), C.c_int(ctype), _ptr(a), _ptr(b))
+            else:
+                m = np.ascontiguousarray(motion, np.float32)
+                self.L.zpcref_mpm_apply_boundary_moving(self.h, C.c_int(geom), C.c_int(ctype), _ptr(a), _ptr(b), _ptr(m))
 
         def set_J(self, J):
             self.L.zpcref_mpm_set_J(self.h, _ptr(np.ascontiguousarray(J, np.float32)))

@@ -215,6 +215,34 @@ void zpcref_mpm_apply_boundary(void *h, int geom, int type, const float *p0, con
     }
   });
 }
+/// the same with a rigid motion: motion = b[3], dbdt[3], R[9] row-major, omega[3], s, dsdt (Collider.h:16-24, 136-143)
+void zpcref_mpm_apply_boundary_moving(void *h, int geom, int type, const float *p0, const float *p1, const float *m) {
+  auto &s = *(RefMpm *)h;
+  const auto ct = type == 0 ? collider_e::Sticky : (type == 1 ? collider_e::Slip : collider_e::Separate);
+  using TV = vec<float, 3>;
+  auto setup = [&](auto &col) {
+    col.setTranslation(TV{m[0], m[1], m[2]}, TV{m[3], m[4], m[5]});
+    vec<float, 3, 3> R{};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R(i, j) = m[6 + 3 * i + j];
+    AngularVelocity<float, 3> om{};
+    om.omega = TV{m[15], m[16], m[17]};
+    col.setRotation(Rotation<float, 3>{R}, om);
+    col.s = m[18];
+    col.dsdt = m[19];
+  };
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    if (geom == 0) {
+      Collider col{AnalyticLevelSet<analytic_geometry_e::Plane, float, 3>{TV{p0[0], p0[1], p0[2]}, TV{p1[0], p1[1], p1[2]}}, ct};
+      setup(col);
+      pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
+    } else {
+      Collider col{AnalyticLevelSet<analytic_geometry_e::Sphere, float, 3>{TV{p0[0], p0[1], p0[2]}, p1[0]}, ct};
+      setup(col);
+      pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
+    }
+  });
+}
 /// grid tiles in table numbering: out[nblocks][7][64]
 void zpcref_mpm_get_grid(void *h, float *out) {
   auto &s = *(RefMpm *)h;

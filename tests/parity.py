@@ -70,3 +70,27 @@ def grid_by_key(keys, grid):
     keys = np.asarray(keys)
     order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
     return keys[order], np.asarray(grid)[order]
+
+
+# ---- moving analytic colliders used by the CPU pin test, the golden generator and the GPU test --------------------
+def _rot(axis, angle):
+    a = np.asarray(axis, np.float64); a /= np.linalg.norm(a)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return (np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * K @ K).astype(np.float32)
+
+
+MOVING_COLLIDERS = [  # (geometry, collider type, p0, p1, motion = b, dbdt, R, omega, s, dsdt)
+    (0, 0, (0.0, 0.10, 0.0), (0.0, 1.0, 0.0), ((0.0, 0.2, 0.0), (0.3, 0.5, -0.2), np.eye(3, dtype=np.float32), (0, 0, 0), 1.0, 0.0)),
+    (0, 2, (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), ((0.3, 0.3, 0.3), (0.0, 1.0, 0.0), _rot((0, 0, 1), 0.4), (0.0, 0.0, 2.0), 1.0, 0.0)),
+    (1, 1, (0.0, 0.0, 0.0), (0.05, 0.0, 0.0), ((0.33, 0.3, 0.33), (0.2, 0.0, 0.1), _rot((1, 2, 3), 1.1), (1.0, -2.0, 0.5), 1.5, 0.7)),
+    (1, 0, (0.01, 0.0, 0.0), (0.06, 0.0, 0.0), ((0.3, 0.32, 0.3), (0.0, -0.4, 0.0), _rot((0, 1, 0), 2.0), (0.0, 3.0, 0.0), 0.9, -0.2)),
+    (1, 2, (0.0, 0.0, 0.0), (0.08, 0.0, 0.0), ((0.33, 0.3, 0.33), (0.0, 0.0, 0.0), np.eye(3, dtype=np.float32), (0, 0, 0), 1.0, 0.0)),
+]
+
+
+def motion_vec(m):
+    b, dbdt, R, om, s, dsdt = m
+    return np.concatenate([np.asarray(b, np.float32), np.asarray(dbdt, np.float32), np.asarray(R, np.float32).reshape(9),
+                           np.asarray(om, np.float32), np.asarray([s, dsdt], np.float32)]).astype(np.float32)
+
+

@@ -584,3 +584,48 @@ def test_fused_grid_update_with_boundaries_equals_the_sequence(mode):
     grids2.tiles.copy_(after_p2g)
     api.compute_grid_block_velocity(grids2, table, synth.DT, ext, mode, mx_a.zero_())
     assert torch.equal(grids.tiles, grids2.tiles)
+
+
+def test_moving_colliders_match_oracle_and_golden(oracle):
+    """Collider with translation / rotation / angular velocity / scaling (geometry/Collider.h:16-24,98-127): the same
+    cells change as in the oracle (the inside test is evaluated without contraction), values within 1e-5; also through
+    the fused update+boundary entry"""
+    from tests.parity import MOVING_COLLIDERS, motion_vec
+    from zpc_b200 import api
+    z = np.load(os.path.join(G, "mpm_cube7_boundary_moving.npz"))
+    kw = dict(ast.literal_eval(str(z["kw"])))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    kr, _ = grid_by_key(z["active_keys"], z["grid_0"])
+    assert np.array_equal(ht["active_keys"], kr)
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(pars, table, grids, synth.DT, api.model_fcr(P["volume"], E, NU))
+    after_p2g = grids.tiles.clone()
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    base = grids.tiles.clone()
+    for i, (geom, ctype, p0, p1, motion) in enumerate(MOVING_COLLIDERS):
+        b, dbdt, R, om, s, dsdt = motion
+        kwm = dict(translation=b, velocity=dbdt, rotation=np.asarray(R).tolist(), omega=om, scale=s, dscale_dt=dsdt)
+        col = api.plane_collider(p0, p1, ctype, **kwm) if geom == 0 else api.sphere_collider(p0, p1[0], ctype, **kwm)
+        grids.tiles.copy_(base)
+        api.apply_boundary_condition(col, table, grids)
+        got = grids.tiles.cpu().numpy()
+        want = base.cpu().numpy()
+        oracle.apply_boundary(want, ht["active_keys"], dx, geom, ctype, p0, p1, motion_vec(motion))
+        assert np.array_equal(got[:, [0, 4, 5, 6]], want[:, [0, 4, 5, 6]])
+        vscale = float(np.abs(want[:, 1:4]).max())
+        check_channels(got[:, 1:4], want[:, 1:4], 1, "moving boundary %d/%d" % (geom, ctype), floor=vscale)
+        changed_got = (got != base.cpu().numpy()).any(axis=1)
+        changed_want = (want != base.cpu().numpy()).any(axis=1)
+        assert (changed_got != changed_want).mean() < 1e-4         # a node within rounding of the surface may flip
+        _, gold = grid_by_key(z["active_keys"], z["grid_%d" % i])
+        check_channels(got[:, 1:4], gold[:, 1:4], 1, "moving boundary golden %d/%d" % (geom, ctype), floor=vscale)
+        # fused with the grid update
+        grids.tiles.copy_(after_p2g)
+        mx2 = torch.zeros(1, device="cuda")
+        api.compute_grid_block_velocity_with_boundaries(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, [col], mx2)
+        assert torch.equal(grids.tiles, torch.from_numpy(got).cuda())

@@ -129,3 +129,29 @@ def test_vonmises_stress_and_p2g_bit_exact_vs_reference(oracle, ref):
     g = oracle.p2g_vonmises(P, tab, dx, synth.DT, E, nu, 300.0, P["volume"])
     assert np.array_equal(g, g_ref)
     assert not np.array_equal(g, oracle.p2g(P, tab, dx, synth.DT, E, nu, P["volume"]))
+
+
+from tests.parity import MOVING_COLLIDERS as MOVING, motion_vec  # noqa: E402
+
+
+def test_moving_colliders_bit_exact_vs_reference(oracle, ref):
+    """Collider::resolveCollision with translation, rotation, angular velocity and scaling (geometry/Collider.h:16-24,98-127)"""
+    from zpc_b200 import synth
+    P = synth.elastic_cube(7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
+    n, dx = P["x"].shape[0], P["dx"]
+    for geom, ctype, p0, p1, motion in MOVING:
+        h = ref.mpm(n, dx, 0)
+        h.set_particles(P)
+        h.partition()
+        tab = h.table()
+        h.clean_grid()
+        h.p2g(synth.DT, synth.MODEL["E"], synth.MODEL["nu"], P["volume"])
+        h.grid_update(synth.DT, synth.GRAVITY, 1)
+        before = h.grid()
+        h.apply_boundary(geom, ctype, p0, p1, motion_vec(motion))
+        after = h.grid()
+        h.close()
+        g = before.copy()
+        oracle.apply_boundary(g, tab["active_keys"], dx, geom, ctype, p0, p1, motion_vec(motion))
+        assert np.array_equal(g, after), (geom, ctype)
+        assert (after != before).any(), "collider %d/%d touches nothing" % (geom, ctype)

@@ -65,7 +65,9 @@ class zpc_equation_of_state(C.Structure):
 
 
 class zpc_collider(C.Structure):
-    _fields_ = [("geometry", C.c_int), ("type", C.c_int), ("origin", C.c_float * 3), ("normal", C.c_float * 3)]
+    _fields_ = [("geometry", C.c_int), ("type", C.c_int), ("origin", C.c_float * 3), ("normal", C.c_float * 3),
+                ("b", C.c_float * 3), ("dbdt", C.c_float * 3), ("R", C.c_float * 9), ("omega", C.c_float * 3),
+                ("s", C.c_float), ("dsdt", C.c_float)]
 
 
 class zpc_bht_view(C.Structure):
@@ -574,12 +576,20 @@ GEOM_PLANE, GEOM_SPHERE = 0, 1
 COLLIDER_STICKY, COLLIDER_SLIP, COLLIDER_SEPARATE = 0, 1, 2
 
 
-def plane_collider(origin, normal, ctype=COLLIDER_STICKY):
-    return zpc_collider(GEOM_PLANE, ctype, (C.c_float * 3)(*origin), (C.c_float * 3)(*normal))
+def _collider(geom, ctype, origin, normal, translation=(0, 0, 0), velocity=(0, 0, 0), rotation=None, omega=(0, 0, 0), scale=1.0,
+              dscale_dt=0.0):
+    """Collider{levelset, type, s, dsdt, R, omega, b, dbdt} (geometry/Collider.h:10-24,136-143); rotation = 3x3 row-major"""
+    R = [1, 0, 0, 0, 1, 0, 0, 0, 1] if rotation is None else [float(v) for row in rotation for v in row]
+    return zpc_collider(geom, ctype, (C.c_float * 3)(*origin), (C.c_float * 3)(*normal), (C.c_float * 3)(*translation),
+                        (C.c_float * 3)(*velocity), (C.c_float * 9)(*R), (C.c_float * 3)(*omega), float(scale), float(dscale_dt))
 
 
-def sphere_collider(center, radius, ctype=COLLIDER_STICKY):
-    return zpc_collider(GEOM_SPHERE, ctype, (C.c_float * 3)(*center), (C.c_float * 3)(radius, 0.0, 0.0))
+def plane_collider(origin, normal, ctype=COLLIDER_STICKY, **motion):
+    return _collider(GEOM_PLANE, ctype, origin, normal, **motion)
+
+
+def sphere_collider(center, radius, ctype=COLLIDER_STICKY, **motion):
+    return _collider(GEOM_SPHERE, ctype, center, (radius, 0.0, 0.0), **motion)
 
 
 def apply_boundary_condition(collider, table, grids, stream=None):

@@ -52,24 +52,40 @@ __global__ void part_place_kernel(const unsigned *sorted, const int *list_cnt, i
 // Collider::resolveCollision over AnalyticLevelSet<Plane | Sphere> with the default rigid motion (geometry/Collider.h:98-127,
 // geometry/AnalyticLevelSet.h:11-43,130-157): projects the velocity of a node at (px,py,pz) that lies inside the collider
 __device__ __forceinline__ void collide(const zpc_collider &col, float px, float py, float pz, float &vx, float &vy, float &vz) {
-  const float d0 = px - col.origin[0], d1 = py - col.origin[1], d2 = pz - col.origin[2];
-  float n0, n1, n2, dist;
+  // material-space position X = R^T (x - b) / s (Collider.h:106-108); products and sums in the reference's order, no contraction
+  // where a sign decides
+  const float xb0 = px - col.b[0], xb1 = py - col.b[1], xb2 = pz - col.b[2];
+  const float inv_s = 1.f / col.s;
+  const float *R = col.R;
+  const float X0 = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], xb0), __fmul_rn(R[3], xb1)), __fmul_rn(R[6], xb2)), inv_s);
+  const float X1 = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[1], xb0), __fmul_rn(R[4], xb1)), __fmul_rn(R[7], xb2)), inv_s);
+  const float X2 = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[2], xb0), __fmul_rn(R[5], xb1)), __fmul_rn(R[8], xb2)), inv_s);
+  const float d0 = X0 - col.origin[0], d1 = X1 - col.origin[1], d2 = X2 - col.origin[2];
+  float m0, m1, m2, dist;  // normal in material space
   if (col.geometry == ZPC_GEOM_PLANE) {
-    n0 = col.normal[0]; n1 = col.normal[1]; n2 = col.normal[2];
-    dist = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));  // no contraction: the sign decides
+    m0 = col.normal[0]; m1 = col.normal[1]; m2 = col.normal[2];
+    dist = __fadd_rn(__fadd_rn(__fmul_rn(m0, d0), __fmul_rn(m1, d1)), __fmul_rn(m2, d2));
   } else {
     const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
     const float len = sqrtf(l2);
     dist = len - col.normal[0];
     const bool tiny = l2 < 1e-7f;
-    n0 = tiny ? 0.f : d0 / len; n1 = tiny ? 0.f : d1 / len; n2 = tiny ? 0.f : d2 / len;
+    m0 = tiny ? 0.f : d0 / len; m1 = tiny ? 0.f : d1 / len; m2 = tiny ? 0.f : d2 / len;
   }
   if (dist < 0.f) {
+    // v_object = omega x (x - b) + (ds/dt / s) (x - b) + db/dt (the analytic level sets have no material velocity), :110-111
+    const float k = col.dsdt * inv_s;
+    const float o0 = (col.omega[1] * xb2 - col.omega[2] * xb1) + k * xb0 + col.dbdt[0];
+    const float o1 = (col.omega[2] * xb0 - col.omega[0] * xb2) + k * xb1 + col.dbdt[1];
+    const float o2 = (col.omega[0] * xb1 - col.omega[1] * xb0) + k * xb2 + col.dbdt[2];
     if (col.type == ZPC_COLLIDER_STICKY) {
-      vx = vy = vz = 0.f;
+      vx = o0; vy = o1; vz = o2;
     } else {
-      const float proj = n0 * vx + n1 * vy + n2 * vz;
+      vx -= o0; vy -= o1; vz -= o2;
+      const float n0 = R[0] * m0 + R[1] * m1 + R[2] * m2, n1 = R[3] * m0 + R[4] * m1 + R[5] * m2, n2 = R[6] * m0 + R[7] * m1 + R[8] * m2;
+      const float proj = __fadd_rn(__fadd_rn(__fmul_rn(n0, vx), __fmul_rn(n1, vy)), __fmul_rn(n2, vz));
       if (col.type == ZPC_COLLIDER_SLIP || proj < 0.f) { vx -= proj * n0; vy -= proj * n1; vz -= proj * n2; }
+      vx += o0; vy += o1; vz += o2;
     }
   }
 }
@@ -192,12 +208,22 @@ int zpcb200_grid_update(zpc_grids_view g, const int *cnt, float dt, const float 
 }
 
 int zpcb200_apply_boundary(zpc_grids_view g, zpc_hashtable_view tb, zpc_collider col, zpc_stream_t stream) {
-  if (!g.tiles || !tb.activeKeys || !tb.cnt || g.numChannels < 4 || (unsigned)col.geometry > 1u || (unsigned)col.type > 2u)
+  if (!g.tiles || !tb.activeKeys || !tb.cnt || g.numChannels < 4 || (unsigned)col.geometry > 1u || (unsigned)col.type > 2u || !(col.s > 0.f))
     return ZPCB200_E_BADARG;
   apply_boundary_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks,
                                                                            g.dx, col);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
+}
+
+zpc_collider zpcb200_collider_static(int geometry, int type, const float origin[3], const float normal_or_radius[3]) {
+  zpc_collider c = {};
+  c.geometry = geometry;
+  c.type = type;
+  for (int d = 0; d < 3; ++d) { c.origin[d] = origin[d]; c.normal[d] = normal_or_radius[d]; }
+  c.R[0] = c.R[4] = c.R[8] = 1.f;
+  c.s = 1.f;
+  return c;
 }
 
 int zpcb200_grid_update_bc(zpc_grids_view g, zpc_hashtable_view tb, float dt, const float extf[3], int mode,
@@ -208,7 +234,7 @@ int zpcb200_grid_update_bc(zpc_grids_view g, zpc_hashtable_view tb, float dt, co
   ColliderSet cs;
   cs.n = ncolliders;
   for (int k = 0; k < ncolliders; ++k) {
-    if ((unsigned)colliders[k].geometry > 1u || (unsigned)colliders[k].type > 2u) return ZPCB200_E_BADARG;
+    if ((unsigned)colliders[k].geometry > 1u || (unsigned)colliders[k].type > 2u || !(colliders[k].s > 0.f)) return ZPCB200_E_BADARG;
     cs.c[k] = colliders[k];
   }
   grid_update_bc_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks, g.dx,
