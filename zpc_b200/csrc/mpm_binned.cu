@@ -6,19 +6,19 @@
 // block arena {b, b+1}^3, and a particle that has since drifted by one cell in any
 // direction still lies inside it.  One CTA per bin:
 //
-//   P2G  (a) counting-sort the bin's particles by (column, z) of their CURRENT home cell in shared
-//            memory (warp match ranking, deterministic);
-//        (b) warp w owns column (x,y) = (w>>2, w&3): lanes first act as 32 particles (coalesced AoSoA
-//            loads, SVD stress, 28-float record -> shared), then as the 27 stencil offsets that sweep
-//            the records with 7 broadcast LDS.128 each, accumulating the 7 grid channels in registers
-//            per cell and folding them into a warp-private column arena — no atomics, no barriers;
-//        (c) the 16 column arenas are summed per node into the eight [7][64] grid tiles in shared
-//            memory and added to HBM with eight 1792-byte TMA bulk reductions
+//   P2G  (a) group the bin's particles by (column, z) of their CURRENT home cell: read the cell-order cache the last
+//            binned G2P left behind, or counting-sort in shared memory (first step after a re-bin);
+//        (b) per chunk of 256 particles: lanes act as particles (coalesced AoSoA loads through the cell order, SVD
+//            stress, 28-float record -> shared), then warps take three non-empty cells at a time from a shared work
+//            counter — lanes = 3 cells x 9 (x,y) node columns, three z-nodes x 7 channels per lane in registers —
+//            and add the sums to the arena (eight [7][64] grid tiles in shared memory) with shared float atomics;
+//        (c) the eight arena tiles are added to HBM with eight 1792-byte TMA bulk reductions
 //            (cp.reduce.async.bulk.global.shared::cta.add.f32) instead of 27*7 REDs per particle;
 //        (d) particles that left the arena's reach since the last re-bin take the per-particle RED path.
-//   G2P  the arena's three velocity channels (8 x 768 contiguous bytes) are staged with TMA bulk
-//        copies on an mbarrier, then one thread per particle gathers with a separable (z, then y,
-//        then x) contraction: 240 FMAs instead of 27*16.
+//   G2P  64-thread CTAs; the arena's three velocity channels (8 x 768 contiguous bytes) AND the particle channels G2P
+//        reads (x, F: contiguous inside a TileVector tile) are staged with TMA bulk copies on mbarriers (two-stage
+//        ring), then one thread per particle gathers with a separable (z, then y, then x) contraction: 240 FMAs
+//        instead of 27*16, and leaves the bin grouped by new home cell for the next P2G.
 //
 // Results equal P2G.hpp / G2P.hpp up to fp32 re-association (tests: <= 1e-5 relative).
 #include <climits>
