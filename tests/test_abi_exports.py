@@ -14,14 +14,17 @@ def declared_symbols():
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = set()
     # expand the declaration macros the header uses
-    for S in ("i32", "u32", "i64", "f32"):
+    for S in ("i32", "u32", "i64", "f32", "f64"):
         for op in ("reduce_sum", "reduce_min", "reduce_max", "exclusive_scan_sum", "inclusive_scan_sum"):
             names.add("zpcb200_%s_%s" % (op, S))
     for S in ("u32", "i32", "u64"):
         names.add("zpcb200_radix_sort_pair_" + S)
         names.add("zpcb200_radix_sort_" + S)
-    for T in ("int", "float"):
-        for op in ("reduce_sum", "reduce_min", "reduce_max", "exclusive_scan_sum", "inclusive_scan_sum"):
+    for S in ("i32", "f32", "f64"):
+        names.add("zpcb200_merge_sort_pair_" + S)
+        names.add("zpcb200_merge_sort_" + S)
+    for T in ("int", "float", "double"):
+        for op in ("reduce_sum", "reduce_min", "reduce_max", "exclusive_scan_sum", "inclusive_scan_sum", "merge_sort", "merge_sort_pair"):
             names.add("%s__b200_%s_1" % (op, T))
     body = "\n".join(l for l in src.splitlines() if not l.rstrip().endswith("\\") and not l.startswith("#"))
     for m in re.finditer(r"\b([a-zA-Z_][a-zA-Z0-9_]*)\s*\(", body):
@@ -53,6 +56,11 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(api.zpc_tilevector_view) == 24
     assert ctypes.sizeof(api.zpc_bins_view) == 80
     assert ctypes.sizeof(api.zpc_fixed_corotated) == 20
+    assert ctypes.sizeof(api.zpc_vonmises_fixed_corotated) == 24
+    assert ctypes.sizeof(api.zpc_equation_of_state) == 24
+    assert ctypes.sizeof(api.zpc_collider) == 32 + 4 * (3 + 3 + 9 + 3 + 2)
+    assert ctypes.sizeof(api.zpc_bht_view) == 4 * 8 + 8 + 2 * 8 + 24
+    assert ctypes.sizeof(api.zpc_sparsegrid_view) == ctypes.sizeof(api.zpc_bht_view) + 8 + 8 + 4 + 64 + 4
 
 
 def test_size_queries_without_gpu():
@@ -66,6 +74,51 @@ def test_size_queries_without_gpu():
     assert L.zpcb200_exclusive_scan_sum_i32(None, ctypes.byref(nb), none, none, ctypes.c_size_t(1 << 20), None) == 0
     assert 0 < nb.value < (1 << 20)
     assert L.zpcb200_radix_sort_u32(None, ctypes.byref(nb), none, none, ctypes.c_size_t(1 << 31), 0, 32, None) == -3
+
+
+def test_new_entries_host_side_behaviour():
+    """size queries and argument checks of the entries added for the SparseGrid variant, merge sort and the kernel tuning
+    hook — none of them launches anything"""
+    from zpc_b200 import api
+    L = api.lib()
+    nb = ctypes.c_size_t(0)
+    none = api.zpc_port(None, 0, 0, 0, 1)
+    for S, ksz in (("i32", 4), ("f32", 4), ("f64", 8)):
+        assert getattr(L, "zpcb200_merge_sort_pair_" + S)(None, ctypes.byref(nb), none, none, ctypes.c_size_t(1 << 20), None) == 0
+        assert nb.value >= (2 * ksz + 2 * 4 + ksz + 4) * (1 << 20)          # image, index (x2), gathered keys and values
+        assert getattr(L, "zpcb200_merge_sort_" + S)(None, ctypes.byref(nb), none, ctypes.c_size_t(0), None) == 0
+    assert L.zpcb200_reduce_sum_f64(None, ctypes.byref(nb), none, none, ctypes.c_size_t(1 << 20), None) == 0
+    # kernel tuning hook: validated values only, -1 keeps
+    a, b = ctypes.c_int(0), ctypes.c_int(0)
+    assert L.zpcb200_get_tuning(ctypes.byref(a), ctypes.byref(b)) == 0 and (a.value, b.value) == (4, 1)
+    assert L.zpcb200_set_tuning(7, -1) == -1 and L.zpcb200_set_tuning(-1, 5) == -1
+    assert L.zpcb200_set_tuning(3, 0) == 0
+    L.zpcb200_get_tuning(ctypes.byref(a), ctypes.byref(b))
+    assert (a.value, b.value) == (3, 0)
+    assert L.zpcb200_set_tuning(-1, 128) == 0 and L.zpcb200_set_tuning(4, -1) == 0
+    L.zpcb200_get_tuning(ctypes.byref(a), ctypes.byref(b))
+    assert (a.value, b.value) == (4, 128)
+    assert L.zpcb200_set_tuning(4, 1) == 0
+    # a SparseGrid with a rotated / translated transform is refused by the MPM functors before anything is launched
+    sg = api.SparseGrid(7, 64, device="cpu")
+    sg.scale(0.1)
+    sg.translate([0.5, 0.0, 0.0])
+    e = (ctypes.c_float * 3)(0.0, -9.8, 0.0)
+    assert L.zpcb200_sg_grid_update(sg.view(), ctypes.c_float(1e-4), e, 2, None, None) == -1      # bad mode / NULL maxVel
+    pv = api.zpc_particles_view(None, None, None, None, None, None, None, None, 0)
+    assert L.zpcb200_sg_g2p_apic(pv, sg.view(), ctypes.c_float(1e-4), None) == -3                   # ZPCB200_E_UNSUPPORTED
+    nbytes = ctypes.c_size_t(0)
+    assert L.zpcb200_sg_partition_build(None, ctypes.byref(nbytes), none, ctypes.c_size_t(0), sg.view(), 0, 2, None, None) == -3
+    sg2 = api.SparseGrid(7, 64, device="cpu")
+    sg2.scale(0.1)
+    assert L.zpcb200_sg_partition_build(None, ctypes.byref(nbytes), none, ctypes.c_size_t(0), sg2.view(), 0, 2, None, None) == 0
+    assert nbytes.value > 0
+    # static collider helper
+    L.zpcb200_collider_static.restype = api.zpc_collider
+    o = (ctypes.c_float * 3)(0.0, 0.3, 0.0)
+    nrm = (ctypes.c_float * 3)(0.0, 1.0, 0.0)
+    c = L.zpcb200_collider_static(0, 2, o, nrm)
+    assert (c.geometry, c.type, c.s, c.dsdt) == (0, 2, 1.0, 0.0) and list(c.R) == [1, 0, 0, 0, 1, 0, 0, 0, 1] and list(c.b) == [0, 0, 0]
 
 
 def test_product_never_imports_oracle():
