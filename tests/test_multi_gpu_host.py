@@ -1,4 +1,4 @@
-"""N>1 host logic on CPU: world_size-2 gloo run of the slab sharding + one-ring grid-block halo exchange
+"""N>1 host logic on CPU: world_size-2 and -4 gloo runs of the slab sharding + one-ring grid-block halo exchange
 (zpc_b200/dist_solver.py::HaloExchange).  The per-rank P2G is computed with the oracle (this is a test of the
 exchange plumbing, not of the kernels); pack / unpack are the torch-indexing stand-ins defined HERE, the product
 uses the C-ABI kernels zpcb200_halo_pack / zpcb200_halo_unpack_add (covered by tests/test_gpu_mpm.py)."""
@@ -54,7 +54,7 @@ def worker(rank, world, port, q):
         from zpc_b200 import synth
         from zpc_b200.dist_solver import HaloExchange, pack_keys
         o = Oracle()
-        s, G = 8, 32
+        s, G = (8, 32) if world == 2 else (16, 32)
         full = synth.elastic_cube(s, G, jitter_F=0.04, jitter_C=0.4)
         c0, c1 = synth.slab_cell_range(s, rank, world)
         mine = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
@@ -66,14 +66,25 @@ def worker(rank, world, port, q):
         tiles = torch.from_numpy(grid.copy())
         halo = HaloExchange(None, 7, "cpu", cpu_pack, cpu_unpack_add)
         peers = halo.build(torch.from_numpy(tab["active_keys"]))
-        assert len(peers) == 1 and peers[0][0] == 1 - rank
-        # both sides list the same shared keys in the same order
-        shared_keys = torch.from_numpy(tab["active_keys"])[peers[0][1].long()]
-        codes = pack_keys(shared_keys)
-        assert bool((codes[1:] > codes[:-1]).all())
-        other = [torch.zeros_like(codes) for _ in range(world)]
-        dist.all_gather(other, codes)
-        assert torch.equal(other[0], other[1])
+        if world == 2:
+            assert len(peers) == 1 and peers[0][0] == 1 - rank
+        else:
+            # 4-cell slabs that do not line up with the 4-cell blocks: a rank shares blocks with its neighbours AND, through
+            # the one-ring of the stencil, with ranks two slabs away
+            assert [p[0] for p in peers] == sorted(p[0] for p in peers) and rank not in [p[0] for p in peers]
+            assert {rank - 1, rank + 1} & set(range(world)) <= {p[0] for p in peers}
+        # every pair of ranks lists the same shared keys in the same (ascending) order
+        mykeys = torch.from_numpy(tab["active_keys"])
+        per_peer = {}
+        for q_, ids, _, _ in peers:
+            codes = pack_keys(mykeys[ids.long()])
+            assert bool((codes[1:] > codes[:-1]).all())
+            per_peer[q_] = codes
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: v.tolist() for k, v in per_peer.items()})
+        for q_, codes in per_peer.items():
+            assert gathered[q_][rank] == codes.tolist()
+        shared_keys = mykeys[torch.cat([ids for _, ids, _, _ in peers]).long().unique()]
         halo.exchange_add(CpuGrids(tiles))
         mx = torch.tensor([float(rank + 1)])
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -99,18 +110,21 @@ def worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_halo_exchange_matches_single_domain():
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_exchange_matches_single_domain(world):
     sk = socket.socket()
     sk.bind(("127.0.0.1", 0))
     port = sk.getsockname()[1]
     sk.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    res = sorted(q.get(timeout=10) for _ in range(2))
-    assert res[0][1] == res[1][1] > 0          # same number of shared blocks on both sides, and some exist
+    res = sorted(q.get(timeout=10) for _ in range(world))
+    assert all(r[1] > 0 for r in res)          # every rank shares blocks with somebody
+    if world == 2:
+        assert res[0][1] == res[1][1]          # the same number on both sides
