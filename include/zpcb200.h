@@ -169,6 +169,26 @@ typedef struct zpc_vonmises_fixed_corotated {
   float E, nu, yieldStress;
 } zpc_vonmises_fixed_corotated;
 
+/* DruckerPragerConfig — physics/ConstitutiveModel.hpp:748-757 (sand; the default yieldSurface is
+ * sqrt(2/3) * 2 sin(30 deg) / (3 - sin(30 deg)), :756).  logJp0 and fa are carried like the reference's struct; the
+ * transfer reads cohesion, beta, yieldSurface and volumeCorrection (P2G.hpp:94-96). */
+typedef struct zpc_drucker_prager {
+  float rho, volume;
+  int dim;
+  float E, nu, logJp0, fa, cohesion, beta;
+  int volumeCorrection;
+  float yieldSurface;
+} zpc_drucker_prager;
+
+/* NACCConfig — physics/ConstitutiveModel.hpp:758-776 (snow).  bulk() and Msqr() are derived from E, nu, fa and dim on
+ * the host exactly as the struct's members do (fa goes to sin as is). */
+typedef struct zpc_nacc {
+  float rho, volume;
+  int dim;
+  float E, nu, logJp0, fa, xi, beta;
+  int hardeningOn;
+} zpc_nacc;
+
 /* EquationOfStateConfig — physics/ConstitutiveModel.hpp:730-734 (gamma is forced to 7 by P2G.hpp:72-75) */
 typedef struct zpc_equation_of_state {
   float rho, volume;
@@ -235,6 +255,15 @@ int zpcb200_apply_boundary(zpc_grids_view grids, zpc_hashtable_view table, zpc_c
  * zpcb200_g2p_apic (the projection of F stays local to P2G, like in the reference). */
 int zpcb200_p2g_apic_vonmises(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
                               float dt, zpc_vonmises_fixed_corotated model, zpc_stream_t stream);
+
+/* P2GTransfer<apic, DruckerPragerConfig> / <apic, NACCConfig> (P2G.hpp:92-102 -> compute_stress_sand /
+ * compute_stress_nacc, physics/ConstitutiveModel_Vol_dP.hpp:116-326): plastic models with a per-particle logJp
+ * (pars.logJp must be set) that the return mapping reads and P2G writes back; F is not modified (the projection stays
+ * local, like in the reference); G2P is zpcb200_g2p_apic. */
+int zpcb200_p2g_apic_drucker_prager(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
+                                    float dt, zpc_drucker_prager model, zpc_stream_t stream);
+int zpcb200_p2g_apic_nacc(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
+                          float dt, zpc_nacc model, zpc_stream_t stream);
 
 /* ComputeGridBlockVelocity + ApplyBoundaryConditionOnGridBlocks for up to ZPCB200_MAX_COLLIDERS static colliders in one
  * pass over the grid (same results as zpcb200_grid_update followed by zpcb200_apply_boundary per collider, in order;

@@ -43,6 +43,10 @@ template <typename T> struct Vector {  // device vector
   Vector(const Vector &) = delete;
   Vector &operator=(const Vector &) = delete;
   Vector(Vector &&o) noexcept : _ptr{o._ptr}, _n{o._n} { o._ptr = nullptr; o._n = 0; }
+  Vector &operator=(Vector &&o) noexcept {
+    if (this != &o) { if (_ptr) cudaFree(_ptr); _ptr = o._ptr; _n = o._n; o._ptr = nullptr; o._n = 0; }
+    return *this;
+  }
   ~Vector() { if (_ptr) cudaFree(_ptr); }
   T *data() { return _ptr; }
   const T *data() const { return _ptr; }
@@ -204,13 +208,23 @@ struct Grids {  // Grids<f32,3,4>, channels {"m",1},{"v",3},{"rhs",3}
 };
 struct Particles {  // Particles<f32,3>, AoS attributes
   size_t _n;
-  Vector<float> X, V, M, C, F;
-  explicit Particles(size_t n) : _n{n}, X(3 * n), V(3 * n), M(n), C(9 * n), F(9 * n) {}
+  Vector<float> X, V, M, C, F, logJp;  // logJp: addAttr("logJp", scalar) of the plastic models, allocated on request
+  explicit Particles(size_t n, bool withLogJp = false) : _n{n}, X(3 * n), V(3 * n), M(n), C(9 * n), F(9 * n) {
+    if (withLogJp) logJp = Vector<float>(n);
+  }
   size_t size() const { return _n; }
-  zpc_particles_view view() { return zpc_particles_view{M.data(), X.data(), V.data(), nullptr, nullptr, F.data(), C.data(), nullptr, _n}; }
+  zpc_particles_view view() { return zpc_particles_view{M.data(), X.data(), V.data(), nullptr, nullptr, F.data(), C.data(), logJp.data(), _n}; }
 };
 struct FixedCorotatedConfig { float rho{1e3f}, volume{1.f}; int dim{3}; float E{5e4f}, nu{0.4f}; };  // ConstitutiveModel.hpp:739-742
 struct VonMisesFixedCorotatedConfig { float rho{1e3f}, volume{1.f}; int dim{3}; float E{5e4f}, nu{0.4f}, yieldStress{240e6f}; };  // :743-747
+
+struct DruckerPragerConfig {  // :748-757
+  float rho{1e3f}, volume{1.f}; int dim{3}; float E{5e4f}, nu{0.4f}, logJp0{0.f}, fa{30.f}, cohesion{0.f}, beta{1.f};
+  bool volumeCorrection{true}; float yieldSurface{0.816496580927726f * 2.f * 0.5f / (3.f - 0.5f)};
+};
+struct NACCConfig {  // :758-776
+  float rho{1e3f}, volume{1.f}; int dim{3}; float E{5e4f}, nu{0.4f}, logJp0{-0.01f}, fa{45.f}, xi{0.8f}, beta{0.5f}; bool hardeningOn{true};
+};
 
 // bht<i32,3,int,16> (container/Bht.hpp): buckets of 16, three universal hashes from std::mt19937(2), 16-byte key slots
 struct Bht {
@@ -317,6 +331,21 @@ struct P2GTransferVonMises {  // P2GTransfer with VonMisesFixedCorotatedConfig (
   int launch(const CudaExecutionPolicy &pol) {
     zpc_vonmises_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu, model.yieldStress};
     return zpcb200_p2g_apic_vonmises(pars.view(), table.view(), grids.view(), dt, m, pol._stream);
+  }
+};
+struct P2GTransferDruckerPrager {  // P2GTransfer with DruckerPragerConfig (P2G.hpp:92-96); pars needs logJp
+  float dt; DruckerPragerConfig model; Particles &pars; HashTable &table; Grids &grids;
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_drucker_prager m{model.rho, model.volume, model.dim, model.E, model.nu, model.logJp0, model.fa, model.cohesion, model.beta,
+                         model.volumeCorrection ? 1 : 0, model.yieldSurface};
+    return zpcb200_p2g_apic_drucker_prager(pars.view(), table.view(), grids.view(), dt, m, pol._stream);
+  }
+};
+struct P2GTransferNACC {  // P2GTransfer with NACCConfig (P2G.hpp:97-100); pars needs logJp
+  float dt; NACCConfig model; Particles &pars; HashTable &table; Grids &grids;
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_nacc m{model.rho, model.volume, model.dim, model.E, model.nu, model.logJp0, model.fa, model.xi, model.beta, model.hardeningOn ? 1 : 0};
+    return zpcb200_p2g_apic_nacc(pars.view(), table.view(), grids.view(), dt, m, pol._stream);
   }
 };
 struct ComputeGridBlockVelocity {  // {cuda_c, wrapv<apic>{}, grids, dt, gravity, maxVel}; mode 1 adds rhs (explicit update)

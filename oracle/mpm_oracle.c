@@ -364,6 +364,180 @@ void zo_stress_vonmises(float volume, float mu, float lam, float yield_stress, c
       PF[3*c + r] = ((P[r]*F[c] + P[3 + r]*F[3 + c]) + P[6 + r]*F[6 + c]) * volume;
 }
 
+/* math::q_rsqrt(float) + math::sqrt(float), math/MathUtils.h:258-269, 288-323: software square root (bit trick, Newton
+ * steps, one correction); restated operation for operation — without FMA contraction it is not always the correctly
+ * rounded root, and the plastic models below go through it */
+static float zo_q_rsqrt(float number) {
+  uint32_t i;
+  float x2 = number * 0.5f, y = number;
+  memcpy(&i, &y, 4);
+  i = 0x5f375a86 - (i >> 1);
+  memcpy(&y, &i, 4);
+  y = y * (1.5f - (x2 * y * y));
+  y = y * (1.5f - (x2 * y * y));
+  return y;
+}
+float zo_math_sqrt(float arg) {
+  const float scale_in = 0x1.0p+26f, scale_out = 0x1.0p-13f;
+  if (arg < 0.0f) { uint32_t u = 0x7fffffffu; float f; memcpy(&f, &u, 4); return f; }
+  if ((arg == 0.0f) || !(fabsf(arg) < INFINITY)) return arg + arg;
+  arg = arg * scale_in;
+  float rsq = zo_q_rsqrt(arg);
+  rsq = ((-0.5f * arg * rsq) * rsq + 0.5f) * rsq + rsq;
+  rsq = ((-0.5f * arg * rsq) * rsq + 0.5f) * rsq + rsq;
+  float sqt = rsq * arg;
+  float err = sqt * -sqt + arg;
+  sqt = (0.5f * rsq * err + sqt);
+  sqt = sqt * scale_out;
+  return sqt;
+}
+
+/* matmul_mat_diag_matT_3D, math/matrix/MatrixUtils.h:26-47 */
+static void mat_diag_matT(float out[9], const float a[9], const float d[3], const float b[9]) {
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r)
+      out[3 * c + r] = (a[r] * d[0] * b[c] + a[3 + r] * d[1] * b[3 + c]) + a[6 + r] * d[2] * b[6 + c];
+}
+/* PF = P F^T * volume, ConstitutiveModel_Vol_dP.hpp:37-45, 317-325 */
+static void p_ft_vol(float PF[9], const float P[9], const float F[9], float volume) {
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r)
+      PF[3 * c + r] = ((P[r] * F[c] + P[3 + r] * F[3 + c]) + P[6 + r] * F[6 + c]) * volume;
+}
+
+/* NACCConfig::bulk(), Msqr() — physics/ConstitutiveModel.hpp:756-776 (fa is passed to sin as is: radians) */
+float zo_nacc_bulk(float E, float nu) { return 2.f / 3.f * (E / (2 * (1 + nu))) + (E * nu / ((1 + nu) * (1 - 2 * nu))); }
+float zo_nacc_msqr(float fa, int dim) {
+  float sin_phi = sinf(fa);
+  float mohr = sqrtf(2.f / 3.f) * 2.f * sin_phi / (3.f - sin_phi);
+  float M = mohr * dim / sqrtf(2.f / (6.f - dim));
+  return M * M;
+}
+
+/* compute_stress_sand, physics/ConstitutiveModel_Vol_dP.hpp:242-326: Drucker-Prager plasticity in log-strain space
+ * (Klar et al. 2016) on top of the St. Venant-Kirchhoff-with-Hencky-strain energy; the projected F stays local
+ * (P2G.hpp:85 passes a copy), logJp is written back (P2G.hpp:101) */
+void zo_stress_sand(float volume, float mu, float lam, float cohesion, float beta, float yieldSurface, int volCorrection,
+                    float *logJp_io, const float Fin[9], float PF[9]) {
+  float F[9], U[9], S[3], V[9];
+  float logJp = *logJp_io;
+  for (int d = 0; d < 9; ++d) F[d] = Fin[d];
+  zo_svd3(F, U, S, V);
+  const float scaled_mu = 2.f * mu;
+  float epsilon[3], New_S[3] = {0.f, 0.f, 0.f}, New_F[9], epsilon_hat[3];
+  for (int i = 0; i < 3; ++i) {
+    float abs_S = S[i] > 0 ? S[i] : -S[i];
+    abs_S = (double)abs_S > 1e-4 ? abs_S : (float)1e-4;      /* :255 — the comparison is in double */
+    epsilon[i] = logf(abs_S) - cohesion;
+  }
+  const float sum_epsilon = epsilon[0] + epsilon[1] + epsilon[2];
+  const float trace_epsilon = sum_epsilon + logJp;
+  for (int i = 0; i < 3; ++i) epsilon_hat[i] = epsilon[i] - (trace_epsilon / 3.f);
+  const float epsilon_hat_norm
+      = zo_math_sqrt(epsilon_hat[0] * epsilon_hat[0] + epsilon_hat[1] * epsilon_hat[1] + epsilon_hat[2] * epsilon_hat[2]);
+  if (trace_epsilon >= 0.f) {                                  /* case II: the cone tip, :270-278 */
+    New_S[0] = New_S[1] = New_S[2] = expf(cohesion);
+    mat_diag_matT(New_F, U, New_S, V);
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+    if (volCorrection) logJp = beta * sum_epsilon + logJp;
+  } else if (mu != 0) {                                        /* :279-297 */
+    logJp = 0;
+    const float delta_gamma = epsilon_hat_norm + (3.f * lam + scaled_mu) / scaled_mu * trace_epsilon * yieldSurface;
+    float H[3];
+    if (delta_gamma <= 0) {                                    /* case I: inside the cone */
+      for (int i = 0; i < 3; ++i) H[i] = epsilon[i] + cohesion;
+    } else {                                                   /* case III: onto the cone surface */
+      for (int i = 0; i < 3; ++i) H[i] = epsilon[i] - (delta_gamma / epsilon_hat_norm) * epsilon_hat[i] + cohesion;
+    }
+    for (int i = 0; i < 3; ++i) New_S[i] = expf(H[i]);
+    mat_diag_matT(New_F, U, New_S, V);
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+  }
+  const float New_S_log[3] = {logf(New_S[0]), logf(New_S[1]), logf(New_S[2])};
+  const float trace_log_S = New_S_log[0] + New_S_log[1] + New_S_log[2];
+  float P_hat[3], P[9];
+  for (int i = 0; i < 3; ++i) P_hat[i] = (scaled_mu * New_S_log[i] + lam * trace_log_S) / New_S[i];
+  mat_diag_matT(P, U, P_hat, V);
+  p_ft_vol(PF, P, F, volume);
+  *logJp_io = logJp;
+}
+
+/* compute_stress_nacc, physics/ConstitutiveModel_Vol_dP.hpp:116-240: non-associated Cam-Clay (Wolper et al. 2019) with
+ * the hardening solve "in 19 Josh Fracture paper" (the #if 1 branch).  p0 uses sin, not sinh, as the reference does. */
+void zo_stress_nacc(float volume, float mu, float lam, float bm, float xi, float beta, float Msqr, int hardeningOn,
+                    float *logJp_io, const float Fin[9], float PF[9]) {
+  (void)lam;
+  float F[9], U[9], S[3], V[9], New_F[9];
+  float logJp = *logJp_io;
+  for (int d = 0; d < 9; ++d) F[d] = Fin[d];
+  zo_svd3(F, U, S, V);
+  const float p0 = (float)((double)(bm * (float)0.00001) + sin((double)(xi * (-logJp > 0 ? -logJp : 0))));  /* :123 */
+  const float p_min = -beta * p0;
+  const float Je_trial = S[0] * S[1] * S[2];
+  const float B_hat_trial[3] = {S[0] * S[0], S[1] * S[1], S[2] * S[2]};
+  const float trace_B_hat_trial_divdim = (B_hat_trial[0] + B_hat_trial[1] + B_hat_trial[2]) / 3.f;
+  const float J_power_neg_2_d_mulmu = mu * powf(Je_trial, -2.f / 3.f);
+  const float s_hat_trial[3] = {J_power_neg_2_d_mulmu * (B_hat_trial[0] - trace_B_hat_trial_divdim),
+                                J_power_neg_2_d_mulmu * (B_hat_trial[1] - trace_B_hat_trial_divdim),
+                                J_power_neg_2_d_mulmu * (B_hat_trial[2] - trace_B_hat_trial_divdim)};
+  const float psi_kappa_partial_J = bm * 0.5f * (Je_trial - 1.f / Je_trial);
+  const float p_trial = -psi_kappa_partial_J * Je_trial;
+  const float y_s_half_coeff = 3.f / 2.f * (1 + 2.f * beta);
+  const float y_p_half = (Msqr * (p_trial - p_min) * (p_trial - p0));
+  const float s_hat_trial_sqrnorm
+      = s_hat_trial[0] * s_hat_trial[0] + s_hat_trial[1] * s_hat_trial[1] + s_hat_trial[2] * s_hat_trial[2];
+  const float y = (y_s_half_coeff * s_hat_trial_sqrnorm) + y_p_half;
+  if (p_trial > p0) {                                          /* case 1: max tip of the yield surface, :148-156 */
+    const float Je_new = zo_math_sqrt(-2.f * p0 / bm + 1.f);
+    S[0] = S[1] = S[2] = powf(Je_new, 1.f / 3.f);
+    mat_diag_matT(New_F, U, S, V);
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+    if (hardeningOn) logJp += logf(Je_trial / Je_new);
+  } else if (p_trial < p_min) {                                /* case 2: min tip, :159-167 */
+    const float Je_new = zo_math_sqrt(-2.f * p_min / bm + 1.f);
+    S[0] = S[1] = S[2] = powf(Je_new, 1.f / 3.f);
+    mat_diag_matT(New_F, U, S, V);
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+    if (hardeningOn) logJp += logf(Je_trial / Je_new);
+  } else if ((double)y >= 1e-4) {                              /* case 3, outside the yield surface, :170-218 */
+    const float B_s_coeff = powf(Je_trial, 2.f / 3.f) / mu * zo_math_sqrt(-y_p_half / y_s_half_coeff)
+                            / zo_math_sqrt(s_hat_trial_sqrnorm);
+    for (int i = 0; i < 3; ++i) S[i] = zo_math_sqrt(s_hat_trial[i] * B_s_coeff + trace_B_hat_trial_divdim);
+    mat_diag_matT(New_F, U, S, V);
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+    if (hardeningOn && (double)p0 > 1e-4 && (double)p_trial < (double)p0 - 1e-4 && (double)p_trial > 1e-4 + (double)p_min) {
+      const float p_center = (1.f - beta) * p0 / 2;
+      const float q_trial = zo_math_sqrt(3.f / 2.f * s_hat_trial_sqrnorm);
+      float direction[2] = {p_center - p_trial, -q_trial};
+      const float direction_norm = zo_math_sqrt(direction[0] * direction[0] + direction[1] * direction[1]);
+      direction[0] /= direction_norm;
+      direction[1] /= direction_norm;
+      const float C = Msqr * (p_center - p_min) * (p_center - p0);
+      const float B = Msqr * direction[0] * (2 * p_center - p0 - p_min);
+      const float A = Msqr * direction[0] * direction[0] + (1 + 2 * beta) * direction[1] * direction[1];
+      const float l1 = (-B + zo_math_sqrt(B * B - 4 * A * C)) / (2 * A);
+      const float l2 = (-B - zo_math_sqrt(B * B - 4 * A * C)) / (2 * A);
+      const float p1 = p_center + l1 * direction[0];
+      const float p2 = p_center + l2 * direction[0];
+      const float p_fake = (p_trial - p_center) * (p1 - p_center) > 0 ? p1 : p2;
+      const float tmp_Je_sqr = (-2 * p_fake / bm + 1);
+      const float Je_new_fake = zo_math_sqrt(tmp_Je_sqr > 0 ? tmp_Je_sqr : -tmp_Je_sqr);
+      if ((double)Je_new_fake > 1e-4) logJp += logf(Je_trial / Je_new_fake);
+    }
+  }
+  /* elasticity, :224-239: J from the (renewed) S, b = F F^T, deviatoric part */
+  const float J = S[0] * S[1] * S[2];
+  float b[9], b_dev[9];
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) b[3 * c + r] = (F[r] * F[c] + F[3 + r] * F[3 + c]) + F[6 + r] * F[6 + c]; /* MatrixUtils.h:244-256 */
+  const float tr3 = ((b[0] + b[4]) + b[8]) / 3.f;                                                          /* :258-271 */
+  for (int i = 0; i < 9; ++i) b_dev[i] = (i % 4 == 0) ? b[i] - tr3 : b[i];
+  const float dev_b_coeff = mu * powf(J, -2.f / 3.f);
+  const float i_coeff = bm * .5f * (J * J - 1.f);
+  for (int i = 0; i < 9; ++i) PF[i] = (i % 4 == 0) ? (dev_b_coeff * b_dev[i] + i_coeff) * volume : (dev_b_coeff * b_dev[i]) * volume;
+  *logJp_io = logJp;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* simulation/Utils.hpp:30-174 LocalArena (collocated, quadratic) + InterpolationKernel.hpp   */
 /* ------------------------------------------------------------------------------------------ */
@@ -392,8 +566,10 @@ void zo_clean_grid(int nblocks, float *grid) { /* GridOp.hpp:54-69 */
   memset(grid, 0, sizeof(float) * 7 * 64 * (size_t)nblocks);
 }
 
-/* P2GTransfer for the F-based elastic models (P2G.hpp:84-91): model 0 = FixedCorotatedConfig, 1 = VonMisesFixedCorotatedConfig */
-static void p2g_elastic(int model, float yield_stress, int n, const float *x, const float *v, const float *m, const float *C,
+/* P2GTransfer for the F-based models (P2G.hpp:84-102): model 0 = FixedCorotatedConfig, 1 = VonMisesFixedCorotatedConfig
+ * (prm = {yieldStress}), 2 = DruckerPragerConfig (prm = {cohesion, beta, yieldSurface, volumeCorrection}),
+ * 3 = NACCConfig (prm = {xi, beta, hardeningOn, fa, dim}); the plastic models read and write logJp (:93, :101) */
+static void p2g_elastic(int model, const float *prm, float *logJp, int n, const float *x, const float *v, const float *m, const float *C,
                         const float *F, float dx, float dt, float E, float nu, float volume, int table_size,
                         const int *keys, const int *indices, float *grid) {
   const float dx_inv = (float)1.0 / dx;        /* P2G.hpp:43 */
@@ -405,7 +581,10 @@ static void p2g_elastic(int model, float yield_stress, int n, const float *x, co
     const float *Cp = C + 9 * p, *vel = v + 3 * p;
     const float mass = m[p];
     if (model == 0) zo_stress_fixedcorotated(volume, mu, lam, F + 9 * p, contrib);   /* :87 */
-    else zo_stress_vonmises(volume, mu, lam, yield_stress, F + 9 * p, contrib);      /* :89-90 */
+    else if (model == 1) zo_stress_vonmises(volume, mu, lam, prm[0], F + 9 * p, contrib); /* :89-90 */
+    else if (model == 2) zo_stress_sand(volume, mu, lam, prm[0], prm[1], prm[2], prm[3] != 0.f, logJp + p, F + 9 * p, contrib); /* :94-96 */
+    else zo_stress_nacc(volume, mu, lam, zo_nacc_bulk(E, nu), prm[0], prm[1], zo_nacc_msqr(prm[3], (int)prm[4]), prm[2] != 0.f,
+                        logJp + p, F + 9 * p, contrib);                                  /* :97-100 */
     for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;        /* :104 */
     zo_arena ar;
     arena_init(&ar, dx, x + 3 * p);                                           /* :107 */
@@ -432,12 +611,24 @@ static void p2g_elastic(int model, float yield_stress, int n, const float *x, co
 void zo_p2g_fcr(int n, const float *x, const float *v, const float *m, const float *C,
                 const float *F, float dx, float dt, float E, float nu, float volume, int table_size,
                 const int *keys, const int *indices, float *grid) {
-  p2g_elastic(0, 0.f, n, x, v, m, C, F, dx, dt, E, nu, volume, table_size, keys, indices, grid);
+  p2g_elastic(0, NULL, NULL, n, x, v, m, C, F, dx, dt, E, nu, volume, table_size, keys, indices, grid);
 }
 void zo_p2g_vonmises(int n, const float *x, const float *v, const float *m, const float *C, const float *F, float dx,
                      float dt, float E, float nu, float yield_stress, float volume, int table_size, const int *keys,
                      const int *indices, float *grid) {
-  p2g_elastic(1, yield_stress, n, x, v, m, C, F, dx, dt, E, nu, volume, table_size, keys, indices, grid);
+  p2g_elastic(1, &yield_stress, NULL, n, x, v, m, C, F, dx, dt, E, nu, volume, table_size, keys, indices, grid);
+}
+void zo_p2g_sand(int n, const float *x, const float *v, const float *m, const float *C, const float *F, float *logJp,
+                 float dx, float dt, float E, float nu, float cohesion, float beta, float yieldSurface, int volCorrection,
+                 float volume, int table_size, const int *keys, const int *indices, float *grid) {
+  const float prm[4] = {cohesion, beta, yieldSurface, volCorrection ? 1.f : 0.f};
+  p2g_elastic(2, prm, logJp, n, x, v, m, C, F, dx, dt, E, nu, volume, table_size, keys, indices, grid);
+}
+void zo_p2g_nacc(int n, const float *x, const float *v, const float *m, const float *C, const float *F, float *logJp,
+                 float dx, float dt, float E, float nu, float fa, float xi, float beta, int hardeningOn, int dim,
+                 float volume, int table_size, const int *keys, const int *indices, float *grid) {
+  const float prm[5] = {xi, beta, hardeningOn ? 1.f : 0.f, fa, (float)dim};
+  p2g_elastic(3, prm, logJp, n, x, v, m, C, F, dx, dt, E, nu, volume, table_size, keys, indices, grid);
 }
 
 /* EquationOfStateConfig branch of P2GTransfer, P2G.hpp:66-87 (weakly compressible fluid: J instead of F) */

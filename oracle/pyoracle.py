@@ -221,6 +221,65 @@ class Oracle:
                                  _ptr(grid))
         return grid
 
+    # DruckerPragerConfig / NACCConfig.  sand = dict(cohesion, beta, yieldSurface, volumeCorrection),
+    # nacc = dict(fa, xi, beta, hardeningOn); both return (PF, logJp_after)
+    def math_sqrt(self, x):
+        self.lib.zo_math_sqrt.restype = C.c_float
+        return float(self.lib.zo_math_sqrt(C.c_float(x)))
+
+    def nacc_consts(self, E, nu, fa, dim=3):
+        self.lib.zo_nacc_bulk.restype = C.c_float
+        self.lib.zo_nacc_msqr.restype = C.c_float
+        return (float(self.lib.zo_nacc_bulk(C.c_float(E), C.c_float(nu))),
+                float(self.lib.zo_nacc_msqr(C.c_float(fa), C.c_int(dim))))
+
+    def stress_sand(self, volume, E, nu, sand, logJp, F):
+        mu, lam = self.lame(E, nu)
+        F = np.ascontiguousarray(F, np.float32)
+        PF = np.empty(9, np.float32)
+        lj = C.c_float(logJp)
+        self.lib.zo_stress_sand(C.c_float(volume), C.c_float(mu), C.c_float(lam), C.c_float(sand["cohesion"]),
+                                C.c_float(sand["beta"]), C.c_float(sand["yieldSurface"]),
+                                C.c_int(int(sand["volumeCorrection"])), C.byref(lj), _ptr(F), _ptr(PF))
+        return PF, lj.value
+
+    def stress_nacc(self, volume, E, nu, nacc, logJp, F):
+        mu, lam = self.lame(E, nu)
+        bm, msqr = self.nacc_consts(E, nu, nacc["fa"])
+        F = np.ascontiguousarray(F, np.float32)
+        PF = np.empty(9, np.float32)
+        lj = C.c_float(logJp)
+        self.lib.zo_stress_nacc(C.c_float(volume), C.c_float(mu), C.c_float(lam), C.c_float(bm), C.c_float(nacc["xi"]),
+                                C.c_float(nacc["beta"]), C.c_float(msqr), C.c_int(int(nacc["hardeningOn"])),
+                                C.byref(lj), _ptr(F), _ptr(PF))
+        return PF, lj.value
+
+    def p2g_sand(self, P, tab, dx, dt, E, nu, sand, volume, grid=None):
+        """P["logJp"] is updated in place (P2G.hpp:101)."""
+        nb = tab["nblocks"]
+        if grid is None:
+            grid = np.zeros((nb, 7, 64), np.float32)
+        n = P["x"].shape[0]
+        self.lib.zo_p2g_sand(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["m"]), _ptr(P["C"]), _ptr(P["F"]),
+                             _ptr(P["logJp"]), C.c_float(dx), C.c_float(dt), C.c_float(E), C.c_float(nu),
+                             C.c_float(sand["cohesion"]), C.c_float(sand["beta"]), C.c_float(sand["yieldSurface"]),
+                             C.c_int(int(sand["volumeCorrection"])), C.c_float(volume), C.c_int(tab["table_size"]),
+                             _ptr(tab["keys"]), _ptr(tab["indices"]), _ptr(grid))
+        return grid
+
+    def p2g_nacc(self, P, tab, dx, dt, E, nu, nacc, volume, grid=None):
+        """P["logJp"] is updated in place (P2G.hpp:101)."""
+        nb = tab["nblocks"]
+        if grid is None:
+            grid = np.zeros((nb, 7, 64), np.float32)
+        n = P["x"].shape[0]
+        self.lib.zo_p2g_nacc(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["m"]), _ptr(P["C"]), _ptr(P["F"]),
+                             _ptr(P["logJp"]), C.c_float(dx), C.c_float(dt), C.c_float(E), C.c_float(nu),
+                             C.c_float(nacc["fa"]), C.c_float(nacc["xi"]), C.c_float(nacc["beta"]),
+                             C.c_int(int(nacc["hardeningOn"])), C.c_int(3), C.c_float(volume), C.c_int(tab["table_size"]),
+                             _ptr(tab["keys"]), _ptr(tab["indices"]), _ptr(grid))
+        return grid
+
     def p2g_eos(self, P, tab, dx, dt, bulk, viscosity, volume, grid=None):
         nb = tab["nblocks"]
         if grid is None:
@@ -515,6 +574,24 @@ class Ref:
             self.L.zpcref_mpm_get_J(self.h, _ptr(J))
             return J
 
+        def set_logJp(self, logJp):
+            self.L.zpcref_mpm_set_logJp(self.h, _ptr(np.ascontiguousarray(logJp, np.float32)))
+
+        def get_logJp(self):
+            a = np.empty(self.n, np.float32)
+            self.L.zpcref_mpm_get_logJp(self.h, _ptr(a))
+            return a
+
+        def p2g_sand(self, dt, E, nu, sand, volume):
+            self.L.zpcref_mpm_p2g_sand(self.h, C.c_float(dt), C.c_float(E), C.c_float(nu), C.c_float(sand["cohesion"]),
+                                       C.c_float(sand["beta"]), C.c_float(sand["yieldSurface"]),
+                                       C.c_int(int(sand["volumeCorrection"])), C.c_float(volume))
+
+        def p2g_nacc(self, dt, E, nu, nacc, volume):
+            self.L.zpcref_mpm_p2g_nacc(self.h, C.c_float(dt), C.c_float(E), C.c_float(nu), C.c_float(nacc["fa"]),
+                                       C.c_float(nacc["xi"]), C.c_float(nacc["beta"]), C.c_int(int(nacc["hardeningOn"])),
+                                       C.c_float(volume))
+
         def p2g_eos(self, dt, bulk, gamma, viscosity, volume):
             self.L.zpcref_mpm_p2g_eos(self.h, C.c_float(dt), C.c_float(bulk), C.c_float(gamma), C.c_float(viscosity),
                                       C.c_float(volume))
@@ -570,6 +647,33 @@ class Ref:
         PF = np.empty(9, np.float32)
         self.lib.zpcref_stress_vonmises(C.c_float(volume), C.c_float(E), C.c_float(nu), C.c_float(yield_stress), _ptr(F), _ptr(PF))
         return PF
+
+    def stress_sand(self, volume, E, nu, sand, logJp, F):
+        F = np.ascontiguousarray(F, np.float32)
+        PF = np.empty(9, np.float32)
+        lj = C.c_float(logJp)
+        self.lib.zpcref_stress_sand(C.c_float(volume), C.c_float(E), C.c_float(nu), C.c_float(sand["cohesion"]),
+                                    C.c_float(sand["beta"]), C.c_float(sand["yieldSurface"]),
+                                    C.c_int(int(sand["volumeCorrection"])), C.byref(lj), _ptr(F), _ptr(PF))
+        return PF, lj.value
+
+    def stress_nacc(self, volume, E, nu, nacc, logJp, F):
+        F = np.ascontiguousarray(F, np.float32)
+        PF = np.empty(9, np.float32)
+        lj = C.c_float(logJp)
+        self.lib.zpcref_stress_nacc(C.c_float(volume), C.c_float(E), C.c_float(nu), C.c_float(nacc["fa"]),
+                                    C.c_float(nacc["xi"]), C.c_float(nacc["beta"]), C.c_int(int(nacc["hardeningOn"])),
+                                    C.byref(lj), _ptr(F), _ptr(PF))
+        return PF, lj.value
+
+    def math_sqrt(self, x):
+        self.lib.zpcref_math_sqrt.restype = C.c_float
+        return float(self.lib.zpcref_math_sqrt(C.c_float(x)))
+
+    def nacc_consts(self, E, nu, fa):
+        b, m = C.c_float(), C.c_float()
+        self.lib.zpcref_nacc_consts(C.c_float(E), C.c_float(nu), C.c_float(fa), C.byref(b), C.byref(m))
+        return b.value, m.value
 
     def merge_sort_pair(self, kind, keys, vals, nthreads=0):
         k = np.array(keys, _ST[kind]); v = np.array(vals, np.int32)

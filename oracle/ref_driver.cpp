@@ -50,6 +50,7 @@ namespace {
       pars.addAttr("F", attrib_e::matrix);
       pars.addAttr("C", attrib_e::matrix);
       pars.addAttr("J", attrib_e::scalar);
+      pars.addAttr("logJp", attrib_e::scalar);
     }
   };
 
@@ -186,6 +187,47 @@ void zpcref_mpm_p2g_eos(void *h, float dt, float bulk, float gamma, float viscos
   model.bulk = bulk;
   model.gamma = gamma;
   model.viscosity = viscosity;
+  model.volume = volume;
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(range(s.n),
+        P2GTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.pars, s.table, s.grids});
+  });
+}
+/// DruckerPragerConfig / NACCConfig (P2G.hpp:92-102): per-particle logJp, read and written back by P2G
+void zpcref_mpm_set_logJp(void *h, const float *logJp) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(s.pars.attrScalar("logJp").data(), logJp, sizeof(float) * s.n);
+}
+void zpcref_mpm_get_logJp(void *h, float *logJp) {
+  auto &s = *(RefMpm *)h;
+  std::memcpy(logJp, s.pars.attrScalar("logJp").data(), sizeof(float) * s.n);
+}
+void zpcref_mpm_p2g_sand(void *h, float dt, float E, float nu, float cohesion, float beta, float yieldSurface,
+                         int volumeCorrection, float volume) {
+  auto &s = *(RefMpm *)h;
+  DruckerPragerConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.cohesion = cohesion;
+  model.beta = beta;
+  model.yieldSurface = yieldSurface;
+  model.volumeCorrection = volumeCorrection != 0;
+  model.volume = volume;
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(range(s.n),
+        P2GTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.pars, s.table, s.grids});
+  });
+}
+void zpcref_mpm_p2g_nacc(void *h, float dt, float E, float nu, float fa, float xi, float beta, int hardeningOn,
+                         float volume) {
+  auto &s = *(RefMpm *)h;
+  NACCConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.fa = fa;
+  model.xi = xi;
+  model.beta = beta;
+  model.hardeningOn = hardeningOn != 0;
   model.volume = volume;
   with_policy(s.nthreads, [&](auto &pol, auto tag) {
     pol(range(s.n),
@@ -329,6 +371,35 @@ void zpcref_stress_vonmises(float volume, float E, float nu, float yieldStress, 
   for (int d = 0; d != 9; ++d) f[d] = F[d];
   compute_stress_vonmisesfixedcorotated(volume, mu, lambda, yieldStress, f, pf);
   for (int d = 0; d != 9; ++d) PF[d] = pf[d];
+}
+void zpcref_stress_sand(float volume, float E, float nu, float cohesion, float beta, float yieldSurface,
+                        int volumeCorrection, float *logJp, const float *F, float *PF) {
+  const auto [mu, lambda] = lame_parameters(E, nu);
+  vec<float, 9> f{}, pf{};
+  for (int d = 0; d != 9; ++d) f[d] = F[d];
+  compute_stress_sand(volume, mu, lambda, cohesion, beta, yieldSurface, volumeCorrection != 0, *logJp, f, pf);
+  for (int d = 0; d != 9; ++d) PF[d] = pf[d];
+}
+void zpcref_stress_nacc(float volume, float E, float nu, float fa, float xi, float beta, int hardeningOn, float *logJp,
+                        const float *F, float *PF) {
+  const auto [mu, lambda] = lame_parameters(E, nu);
+  NACCConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.fa = fa;
+  vec<float, 9> f{}, pf{};
+  for (int d = 0; d != 9; ++d) f[d] = F[d];
+  compute_stress_nacc(volume, mu, lambda, model.bulk(), xi, beta, model.Msqr(), hardeningOn != 0, *logJp, f, pf);
+  for (int d = 0; d != 9; ++d) PF[d] = pf[d];
+}
+float zpcref_math_sqrt(float x) { return math::sqrt(x); }
+void zpcref_nacc_consts(float E, float nu, float fa, float *bulk, float *msqr) {
+  NACCConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.fa = fa;
+  *bulk = model.bulk();
+  *msqr = model.Msqr();
 }
 int zpcref_max_threads() { return (int)std::thread::hardware_concurrency(); }
 }

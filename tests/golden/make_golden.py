@@ -120,6 +120,105 @@ def vonmises_case(ref, name, s, G, ys, **kw):
     print(name, "n", n, "blocks", nb, "yielded fraction %.2f, margin %.2e" % (frac, margin))
 
 
+SAND = dict(cohesion=0.0, beta=1.0, yieldSurface=0.816496580927726 * 2.0 * 0.5 / (3.0 - 0.5), volumeCorrection=True)
+# NACC in a regime where all three branches of the return mapping occur and the stress is well conditioned: with the
+# reference's p0 = bulk*1e-5 + sin(xi*max(-logJp,0)) (ConstitutiveModel_Vol_dP.hpp:123) the yield surface is O(1) Pa
+# wide, so a soft material (E = 10) and logJp in [-1.8, 0.2] put particles inside it, beyond either tip and on it.
+NACC = dict(fa=45.0, xi=0.8, beta=0.5, hardeningOn=True, E=10.0, nu=0.4)
+
+
+def sand_margin(P, E, nu, sand):
+    """branch statistics of compute_stress_sand in float64: fractions of (tip, inside, cone surface) and the smallest
+    distance of any particle from a branch boundary"""
+    mu, lam = 0.5 * E / (1 + nu), E * nu / ((1 + nu) * (1 - 2 * nu))
+    F = P["F"].reshape(-1, 3, 3).transpose(0, 2, 1).astype(np.float64)
+    sig = np.linalg.svd(F, compute_uv=False)
+    eps = np.log(np.maximum(np.abs(sig), 1e-4)) - sand["cohesion"]
+    tr = eps.sum(1) + P["logJp"].astype(np.float64)
+    eh = eps - tr[:, None] / 3
+    dg = np.linalg.norm(eh, axis=1) + (3 * lam + 2 * mu) / (2 * mu) * tr * sand["yieldSurface"]
+    tip, inside = tr >= 0, (tr < 0) & (dg <= 0)
+    margin = min(float(np.abs(tr).min()), float(np.abs(dg[~tip]).min(initial=np.inf)))
+    return margin, (float(tip.mean()), float(inside.mean()), float((~tip & ~inside).mean()))
+
+
+def sand_case(ref, name, s, G, **kw):
+    """DruckerPragerConfig substep (P2G.hpp:92-96, ConstitutiveModel_Vol_dP.hpp:242-326): logJp read and written back"""
+    P = synth.elastic_cube(s, G, **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    P["logJp"] = np.random.RandomState(44).uniform(-0.06, 0.03, n).astype(np.float32)
+    margin, fr = sand_margin(P, synth.MODEL["E"], synth.MODEL["nu"], SAND)
+    assert margin > 2e-5 and min(fr) > 0.05, (margin, fr)   # every branch is taken, nobody sits on a branch boundary
+    h = ref.mpm(n, dx, 0)
+    h.set_particles(P)
+    h.set_logJp(P["logJp"])
+    nb = h.partition()
+    tab = h.table()
+    h.clean_grid()
+    h.p2g_sand(synth.DT, synth.MODEL["E"], synth.MODEL["nu"], SAND, P["volume"])
+    g1 = h.grid()
+    lj = h.get_logJp()
+    mx = h.grid_update(synth.DT, synth.GRAVITY, 1)
+    h.g2p(synth.DT)
+    out = h.get_particles()
+    h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), s=s, G=G, kw=repr(sorted(kw.items())), nblocks=nb,
+                        active_keys=tab["active_keys"], logJp_in=P["logJp"], logJp=lj, grid_p2g=g1, max_vel_sqr=mx,
+                        branch_fractions=np.array(fr), x=out["x"], v=out["v"], C=out["C"], F=out["F"])
+    print(name, "n", n, "blocks", nb, "tip/inside/surface %.2f/%.2f/%.2f, margin %.2e" % (fr + (margin,)))
+
+
+def nacc_margin(P, nacc):
+    """branch statistics of compute_stress_nacc in float64: (max tip, min tip, projected onto the surface, hardening
+    solve taken, inside) and the smallest relative distance from the p_trial branch boundaries"""
+    E, nu = nacc["E"], nacc["nu"]
+    mu = 0.5 * E / (1 + nu)
+    bm = 2.0 / 3.0 * (E / (2 * (1 + nu))) + E * nu / ((1 + nu) * (1 - 2 * nu))
+    sin_phi = np.sin(np.float32(nacc["fa"]))
+    M = np.sqrt(2.0 / 3.0) * 2 * sin_phi / (3 - sin_phi) * 3 / np.sqrt(2.0 / 3.0)
+    F = P["F"].reshape(-1, 3, 3).transpose(0, 2, 1).astype(np.float64)
+    sig = np.linalg.svd(F, compute_uv=False)
+    lj = P["logJp"].astype(np.float64)
+    p0 = bm * 1e-5 + np.sin(nacc["xi"] * np.maximum(-lj, 0))
+    pmin = -nacc["beta"] * p0
+    Je = sig.prod(1)
+    B = sig ** 2
+    s_hat = mu * Je[:, None] ** (-2.0 / 3.0) * (B - B.mean(1, keepdims=True))
+    pt = -bm * 0.5 * (Je - 1 / Je) * Je
+    y = 1.5 * (1 + 2 * nacc["beta"]) * (s_hat ** 2).sum(1) + M * M * (pt - pmin) * (pt - p0)
+    c1, c2 = pt > p0, pt < pmin
+    c3 = ~c1 & ~c2 & (y >= 1e-4)
+    hard = c3 & (p0 > 1e-4) & (pt < p0 - 1e-4) & (pt > 1e-4 + pmin)
+    margin = min(float(np.abs(pt - p0).min()), float(np.abs(pt - pmin).min()), float(np.abs(y - 1e-4)[~c1 & ~c2].min(initial=np.inf)))
+    return margin, tuple(float(m.mean()) for m in (c1, c2, c3, hard, ~c1 & ~c2 & ~c3))
+
+
+def nacc_case(ref, name, s, G, **kw):
+    """NACCConfig substep (P2G.hpp:97-100, ConstitutiveModel_Vol_dP.hpp:116-240): logJp read and written back"""
+    P = synth.elastic_cube(s, G, **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    P["logJp"] = np.random.RandomState(37).uniform(-1.8, 0.2, n).astype(np.float32)
+    margin, fr = nacc_margin(P, NACC)
+    assert margin > 1e-5 and min(fr[:4]) > 0.03, (margin, fr)
+    h = ref.mpm(n, dx, 0)
+    h.set_particles(P)
+    h.set_logJp(P["logJp"])
+    nb = h.partition()
+    tab = h.table()
+    h.clean_grid()
+    h.p2g_nacc(synth.DT, NACC["E"], NACC["nu"], NACC, P["volume"])
+    g1 = h.grid()
+    lj = h.get_logJp()
+    mx = h.grid_update(synth.DT, synth.GRAVITY, 1)
+    h.g2p(synth.DT)
+    out = h.get_particles()
+    h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), s=s, G=G, kw=repr(sorted(kw.items())), nblocks=nb,
+                        active_keys=tab["active_keys"], logJp_in=P["logJp"], logJp=lj, grid_p2g=g1, max_vel_sqr=mx,
+                        branch_fractions=np.array(fr), x=out["x"], v=out["v"], C=out["C"], F=out["F"])
+    print(name, "n", n, "blocks", nb, "maxtip/mintip/surface/hardening/inside %.2f/%.2f/%.2f/%.2f/%.2f, margin %.2e" % (fr + (margin,)))
+
+
 def eos_case(ref, name, s, G, **kw):
     """EquationOfStateConfig{bulk=4e4, gamma=7.15, viscosity=0.01} substep (P2G.hpp:66-87, G2P.hpp:69-73)"""
     P = synth.elastic_cube(s, G, **kw)
@@ -199,6 +298,8 @@ if __name__ == "__main__":
     boundary_case(r, "mpm_cube7_boundary", 7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
     boundary_moving_case(r, "mpm_cube7_boundary_moving", 7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
     vonmises_case(r, "mpm_cube6_vonmises", 6, 32, 2946.0, jitter_F=0.05, jitter_C=0.5, shuffle_seed=17)   # 39 % of the particles yield
+    sand_case(r, "mpm_cube6_sand", 6, 32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=19)
+    nacc_case(r, "mpm_cube6_nacc", 6, 32, jitter_F=0.03, jitter_C=0.5, shuffle_seed=23)
     if "--all" in sys.argv:   # the primitive / SVD vectors use unseeded-order-independent inputs: regenerate on demand
         prims_case(r)
         svd_case(r)

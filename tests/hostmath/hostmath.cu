@@ -1,0 +1,45 @@
+// TEST INFRASTRUCTURE — compiles the product's per-particle device math (zpc_b200/csrc/mpm_math.cuh, __host__ __device__)
+// for the CPU so that tests without a GPU can compare it with the oracle: a transcription error in a stress model or in
+// the stencil shows up here.  Not linked into libzpcb200.so; nothing in zpc_b200/ uses it.
+#include "../../zpc_b200/csrc/mpm_math.cuh"
+
+extern "C" {
+void hm_svd3(const float *F, float *U, float *S, float *V) {
+  float f[9], u[9], s[3], v[9];
+  for (int d = 0; d < 9; ++d) f[d] = F[d];
+  zpcm::svd3(f, u, s, v);
+  for (int d = 0; d < 9; ++d) { U[d] = u[d]; V[d] = v[d]; }
+  for (int d = 0; d < 3; ++d) S[d] = s[d];
+}
+void hm_lame(float E, float nu, float *mu, float *lam) { zpcm::lame_host(E, nu, *mu, *lam); }
+void hm_nacc_consts(float E, float nu, float fa, int dim, float *bulk, float *msqr) {
+  *bulk = zpcm::nacc_bulk_host(E, nu);
+  *msqr = zpcm::nacc_msqr_host(fa, dim);
+}
+// model: 0 fixed-corotated, 1 von Mises {yield}, 2 Drucker-Prager {cohesion, beta, yieldSurface, volumeCorrection},
+// 3 NACC {bulk, xi, beta, Msqr, hardeningOn}; n matrices, logJp in/out for 2 and 3
+void hm_stress(int model, int n, float volume, float mu, float lam, const float *prm, float *logJp, const float *F, float *PF) {
+  for (int p = 0; p < n; ++p) {
+    float f[9], pf[9];
+    for (int d = 0; d < 9; ++d) f[d] = F[9 * p + d];
+    if (model == 0) zpcm::stress_fcr(volume, mu, lam, f, pf);
+    else if (model == 1) zpcm::stress_vonmises(volume, mu, lam, prm[0], f, pf);
+    else if (model == 2) zpcm::stress_sand(volume, mu, lam, prm[0], prm[1], prm[2], prm[3] != 0.f, logJp[p], f, pf);
+    else zpcm::stress_nacc(volume, mu, prm[0], prm[1], prm[2], prm[3], prm[4] != 0.f, logJp[p], f, pf);
+    for (int d = 0; d < 9; ++d) PF[9 * p + d] = pf[d];
+  }
+}
+// LocalArena: corner[3], local[3], w[9] per position
+void hm_arena(int n, float dx, const float *x, int *corner, float *local, float *w) {
+  for (int p = 0; p < n; ++p) {
+    zpcm::Arena a;
+    float pos[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+    zpcm::arena_init(a, dx, pos);
+    for (int d = 0; d < 3; ++d) {
+      corner[3 * p + d] = a.corner[d];
+      local[3 * p + d] = a.local[d];
+      for (int k = 0; k < 3; ++k) w[9 * p + 3 * d + k] = a.w[d][k];
+    }
+  }
+}
+}

@@ -58,6 +58,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(api.zpc_fixed_corotated) == 20
     assert ctypes.sizeof(api.zpc_vonmises_fixed_corotated) == 24
     assert ctypes.sizeof(api.zpc_equation_of_state) == 24
+    assert ctypes.sizeof(api.zpc_drucker_prager) == 44
+    assert ctypes.sizeof(api.zpc_nacc) == 40
     assert ctypes.sizeof(api.zpc_collider) == 32 + 4 * (3 + 3 + 9 + 3 + 2)
     assert ctypes.sizeof(api.zpc_bht_view) == 4 * 8 + 8 + 2 * 8 + 24
     assert ctypes.sizeof(api.zpc_sparsegrid_view) == ctypes.sizeof(api.zpc_bht_view) + 8 + 8 + 4 + 64 + 4
@@ -119,6 +121,26 @@ def test_new_entries_host_side_behaviour():
     nrm = (ctypes.c_float * 3)(0.0, 1.0, 0.0)
     c = L.zpcb200_collider_static(0, 2, o, nrm)
     assert (c.geometry, c.type, c.s, c.dsdt) == (0, 2, 1.0, 0.0) and list(c.R) == [1, 0, 0, 0, 1, 0, 0, 0, 1] and list(c.b) == [0, 0, 0]
+
+
+def test_plastic_model_entries_check_their_arguments():
+    """zpcb200_p2g_apic_drucker_prager / _nacc refuse a particle view without logJp and a non-3D NACC model before
+    anything is launched; an empty range is a no-op"""
+    from zpc_b200 import api
+    L = api.lib()
+    dp, nacc = api.model_drucker_prager(1e-6), api.model_nacc(1e-6)
+    assert abs(dp.yieldSurface - 0.816496580927726 * 2 * 0.5 / 2.5) < 1e-7 and dp.volumeCorrection == 1 and nacc.hardeningOn == 1
+    tv = api.zpc_hashtable_view(1, 1, 1, 1, 16, 1)          # non-null dummies: the checks below fail before any use
+    gv = api.zpc_grids_view(1, 1, 7, 0.1)
+    no_logjp = api.zpc_particles_view(1, 1, 1, None, None, 1, 1, None, 10)
+    empty = api.zpc_particles_view(None, None, None, None, None, None, None, None, 0)
+    for fn, model in ((L.zpcb200_p2g_apic_drucker_prager, dp), (L.zpcb200_p2g_apic_nacc, nacc)):
+        assert fn(no_logjp, tv, gv, ctypes.c_float(1e-4), model, None) == -1
+        assert fn(empty, tv, gv, ctypes.c_float(1e-4), model, None) == 0
+        assert fn(empty, tv, api.zpc_grids_view(1, 1, 4, 0.1), ctypes.c_float(1e-4), model, None) == -1
+    bad = api.model_nacc(1e-6)
+    bad.dim = 2
+    assert L.zpcb200_p2g_apic_nacc(empty, tv, gv, ctypes.c_float(1e-4), bad, None) == -1
 
 
 def test_product_never_imports_oracle():

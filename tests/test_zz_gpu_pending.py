@@ -1,0 +1,77 @@
+"""GPU parity tests of kernels that were written AFTER this round's GPU budget (180 GPU-minutes) was spent: they have
+been compiled for sm_100a and their per-particle math is verified on the host (tests/test_oracle_plastic.py,
+tests/hostmath), but they have not yet executed on a B200.  Until they have, they are non-strict xfail — a pass shows
+up as XPASS, a failure cannot mask the verified suite — and the file sorts last so nothing runs after it in the same
+process.  Remove the marker once a GPU run is green (DESIGN.md §9 lists them).
+"""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="kernel not yet executed on a B200 (round-1 GPU budget spent)")]
+
+from zpc_b200 import synth  # noqa: E402
+from tests.golden.make_golden import NACC, SAND  # noqa: E402
+from tests.parity import RTOL, RTOL_STRESS, check_channels, check_particles, grid_by_key  # noqa: E402
+from tests.test_gpu_mpm import build_partition, host_table  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+E, NU = synth.MODEL["E"], synth.MODEL["nu"]
+# rhs tolerance per model = the reference's own build-to-build distance on this very case (oracle with / without FMA
+# contraction: sand 1.5e-5, NACC 2.4e-4 of channel scale) with the margin tests/parity.py uses for fixed-corotated
+RHS_RTOL = {"sand": RTOL_STRESS, "nacc": 1e-3}
+
+
+@pytest.mark.parametrize("model", ["sand", "nacc"])
+def test_plastic_model_matches_oracle_and_golden(oracle, model):
+    """DruckerPragerConfig / NACCConfig (P2G.hpp:92-102) on the AoS drop-in path: grid after P2G and the logJp written back,
+    vs the oracle on the GPU-built table and vs reference-generated golden vectors by block key; then update + G2P."""
+    from zpc_b200 import api
+    z = np.load(os.path.join(G, "mpm_cube6_%s.npz" % model))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **dict(ast.literal_eval(str(z["kw"]))))
+    P["logJp"] = z["logJp_in"].copy()
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    assert pars.logJp is not None
+    ht = host_table(table)
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    if model == "sand":
+        m = api.model_drucker_prager(P["volume"], E, NU, SAND["cohesion"], SAND["beta"], SAND["volumeCorrection"], SAND["yieldSurface"])
+    else:
+        m = api.model_nacc(P["volume"], NACC["E"], NACC["nu"], NACC["fa"], NACC["xi"], NACC["beta"], NACC["hardeningOn"])
+    api.p2g_transfer(pars, table, grids, synth.DT, m)
+    torch.cuda.synchronize()
+    g1 = grids.tiles.cpu().numpy()
+    lj = pars.logJp.cpu().numpy()
+    Po = dict(P, logJp=P["logJp"].copy())
+    if model == "sand":
+        o1 = oracle.p2g_sand(Po, ht, dx, synth.DT, E, NU, SAND, P["volume"])
+    else:
+        o1 = oracle.p2g_nacc(Po, ht, dx, synth.DT, NACC["E"], NACC["nu"], NACC, P["volume"])
+    rtol = [RTOL] * 4 + [RHS_RTOL[model]] * 3
+    check_channels(g1, o1, 1, model + " p2g", rtol)
+    assert np.abs(lj - Po["logJp"]).max() <= 2e-5            # logf / expf / powf of the device vs glibc: a few ulp
+    assert np.abs(lj - P["logJp"]).max() > 1e-3               # and P2G really wrote it back
+    kr, g1r = grid_by_key(z["active_keys"], z["grid_p2g"])
+    assert np.array_equal(ht["active_keys"], kr)
+    check_channels(g1, g1r, 1, model + " golden p2g", rtol)
+    assert np.abs(lj - z["logJp"]).max() <= 2e-5
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    assert abs(mx.item() - float(z["max_vel_sqr"])) <= RHS_RTOL[model] * float(z["max_vel_sqr"])
+    api.g2p_transfer(pars, table, grids, synth.DT)
+    check_particles(pars.to_host(), {k: z[k] for k in "xvCF"}, dx, model + " golden g2p", rtol=3e-5)
+
+
+def test_plastic_models_need_logjp():
+    from zpc_b200 import api
+    P = synth.elastic_cube(4, 16)
+    pars, table = build_partition(P)
+    grids = api.Grids(P["dx"], table.size())
+    with pytest.raises(ValueError):
+        api.p2g_transfer(pars, table, grids, synth.DT, api.model_nacc(P["volume"]))

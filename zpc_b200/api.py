@@ -59,6 +59,17 @@ class zpc_vonmises_fixed_corotated(C.Structure):
                 ("yieldStress", C.c_float)]
 
 
+class zpc_drucker_prager(C.Structure):
+    _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("E", C.c_float), ("nu", C.c_float),
+                ("logJp0", C.c_float), ("fa", C.c_float), ("cohesion", C.c_float), ("beta", C.c_float),
+                ("volumeCorrection", C.c_int), ("yieldSurface", C.c_float)]
+
+
+class zpc_nacc(C.Structure):
+    _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("E", C.c_float), ("nu", C.c_float),
+                ("logJp0", C.c_float), ("fa", C.c_float), ("xi", C.c_float), ("beta", C.c_float), ("hardeningOn", C.c_int)]
+
+
 class zpc_equation_of_state(C.Structure):
     _fields_ = [("rho", C.c_float), ("volume", C.c_float), ("dim", C.c_int), ("bulk", C.c_float), ("gamma", C.c_float),
                 ("viscosity", C.c_float)]
@@ -446,11 +457,13 @@ class Particles:
         self.C = torch.as_tensor(P["C"]).to(device).contiguous()
         self.F = torch.as_tensor(P["F"]).to(device).contiguous()
         self.J = torch.as_tensor(P["J"]).to(device).contiguous() if "J" in P else None   # EquationOfStateConfig only
+        self.logJp = torch.as_tensor(P["logJp"]).to(device).contiguous() if "logJp" in P else None  # DruckerPrager / NACC
 
     def view(self):
         return zpc_particles_view(self.m.data_ptr(), self.x.data_ptr(), self.v.data_ptr(), None,
                                   self.J.data_ptr() if self.J is not None else None,
-                                  self.F.data_ptr(), self.C.data_ptr(), None, self.n)
+                                  self.F.data_ptr(), self.C.data_ptr(),
+                                  self.logJp.data_ptr() if self.logJp is not None else None, self.n)
 
     def to_host(self):
         return {k: getattr(self, k).cpu().numpy() for k in ("x", "v", "m", "C", "F")}
@@ -547,7 +560,27 @@ def model_vonmises(volume, E=5.0e4, nu=0.4, yield_stress=240e6, rho=1000.0):
     return zpc_vonmises_fixed_corotated(rho, volume, 3, E, nu, yield_stress)
 
 
+DRUCKER_PRAGER_YIELD_SURFACE = 0.816496580927726 * 2.0 * 0.5 / (3.0 - 0.5)   # ConstitutiveModel.hpp:756
+
+
+def model_drucker_prager(volume, E=5.0e4, nu=0.4, cohesion=0.0, beta=1.0, volume_correction=True,
+                         yield_surface=DRUCKER_PRAGER_YIELD_SURFACE, logJp0=0.0, fa=30.0, rho=1000.0):
+    """DruckerPragerConfig (physics/ConstitutiveModel.hpp:748-757)"""
+    return zpc_drucker_prager(rho, volume, 3, E, nu, logJp0, fa, cohesion, beta, int(bool(volume_correction)), yield_surface)
+
+
+def model_nacc(volume, E=5.0e4, nu=0.4, fa=45.0, xi=0.8, beta=0.5, hardening_on=True, logJp0=-0.01, rho=1000.0):
+    """NACCConfig (physics/ConstitutiveModel.hpp:758-776)"""
+    return zpc_nacc(rho, volume, 3, E, nu, logJp0, fa, xi, beta, int(bool(hardening_on)))
+
+
 def p2g_transfer(pars, table, grids, dt, model, stream=None):
+    if isinstance(model, (zpc_drucker_prager, zpc_nacc)):
+        if getattr(pars, "logJp", None) is None:
+            raise ValueError("the plastic models need the per-particle logJp attribute (P2G.hpp:93)")
+        fn = lib().zpcb200_p2g_apic_drucker_prager if isinstance(model, zpc_drucker_prager) else lib().zpcb200_p2g_apic_nacc
+        _check(fn(pars.view(), table.view(), grids.view(), C.c_float(dt), model, _stream_ptr(stream)), "p2g(plastic)")
+        return
     if isinstance(model, zpc_vonmises_fixed_corotated):
         _check(lib().zpcb200_p2g_apic_vonmises(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
                                                _stream_ptr(stream)), "p2g(vonmises)")

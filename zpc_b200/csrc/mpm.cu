@@ -269,6 +269,37 @@ int zpcb200_p2g_apic_vonmises(zpc_particles_view P, zpc_hashtable_view tb, zpc_g
   return ZPCB200_OK;
 }
 
+int zpcb200_p2g_apic_drucker_prager(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt,
+                                    zpc_drucker_prager model, zpc_stream_t stream) {
+  if (g.numChannels != 7 || !g.tiles || !tb.keys || !tb.indices) return ZPCB200_E_BADARG;
+  if (P.count && (!P.X || !P.V || !P.M || !P.C || !P.F || !P.logJp)) return ZPCB200_E_BADARG;
+  if (!P.count) return ZPCB200_OK;
+  float mu, lam;
+  zpcm::lame_host(model.E, model.nu, mu, lam);
+  const PlasticParams prm{model.cohesion, model.beta, model.yieldSurface, 0.f, model.volumeCorrection};
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  p2g_aos_plastic_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(P, zpcp::LegacyGrid{tb}, g.tiles, g.numChannels, g.dx, dt,
+                                                                    model.volume, mu, lam, prm);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_p2g_apic_nacc(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_nacc model,
+                          zpc_stream_t stream) {
+  if (g.numChannels != 7 || !g.tiles || !tb.keys || !tb.indices || model.dim != 3) return ZPCB200_E_BADARG;
+  if (P.count && (!P.X || !P.V || !P.M || !P.C || !P.F || !P.logJp)) return ZPCB200_E_BADARG;
+  if (!P.count) return ZPCB200_OK;
+  float mu, lam;
+  zpcm::lame_host(model.E, model.nu, mu, lam);
+  const PlasticParams prm{zpcm::nacc_bulk_host(model.E, model.nu), model.xi, model.beta, zpcm::nacc_msqr_host(model.fa, model.dim),
+                          model.hardeningOn};
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  p2g_aos_plastic_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(P, zpcp::LegacyGrid{tb}, g.tiles, g.numChannels, g.dx, dt,
+                                                                    model.volume, mu, lam, prm);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
 int zpcb200_g2p_apic(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
   if (P.count == 0) return ZPCB200_OK;
   if (g.numChannels < 4 || !P.X || !P.V || !P.C || !P.F) return ZPCB200_E_BADARG;

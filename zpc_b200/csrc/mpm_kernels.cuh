@@ -93,6 +93,33 @@ __global__ void __launch_bounds__(128) p2g_aos_eos_kernel(zpc_particles_view P, 
   zpcp::p2g_scatter_particle_eos(pos, vel, P.M[p], C, P.J[p], tb, tiles, nch, dx, dt, volume, bulk, viscosity);
 }
 
+// DruckerPragerConfig (MODEL 2) / NACCConfig (MODEL 3): P2G.hpp:92-102 — logJp is read, updated by the return mapping and
+// written back; the projected F stays in registers.  prm: model 2 {cohesion, beta, yieldSurface, -}, flag = volumeCorrection;
+// model 3 {bulk, xi, beta, Msqr}, flag = hardeningOn.
+struct PlasticParams {
+  float a, b, c, d;
+  int flag;
+};
+template <int MODEL, class GA>
+__global__ void __launch_bounds__(128) p2g_aos_plastic_kernel(zpc_particles_view P, GA tb, float *tiles, int nch, float dx, float dt,
+                                                              float volume, float mu, float lam, PlasticParams prm) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.count) return;
+  float pos[3], vel[3], C[9], F[9], contrib[9];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { pos[d] = P.X[3 * p + d]; vel[d] = P.V[3 * p + d]; }
+#pragma unroll
+  for (int d = 0; d < 9; ++d) { C[d] = P.C[9 * p + d]; F[d] = P.F[9 * p + d]; }
+  float logJp = P.logJp[p];
+  if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, prm.a, prm.b, prm.c, prm.flag != 0, logJp, F, contrib);
+  else zpcm::stress_nacc(volume, mu, prm.a, prm.b, prm.c, prm.d, prm.flag != 0, logJp, F, contrib);
+  P.logJp[p] = logJp;
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+#pragma unroll
+  for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+  zpcp::p2g_scatter_core(pos, vel, P.M[p], C, contrib, tb, tiles, nch, dx);
+}
+
 template <bool EOS, class GA>
 __global__ void __launch_bounds__(128) g2p_aos_kernel(zpc_particles_view P, GA tb, const float *tiles,
                                                       int nch, float dx, float dt) {

@@ -8,16 +8,32 @@
 // Matrices are column-major 9-vectors M[3*col+row], exactly the reference's vec9 convention.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
 
 #include "../../include/zpcb200.h"
 
+// The per-particle math is __host__ __device__: tests/hostmath compiles it for the CPU and checks it against the
+// oracle without a GPU (transcription errors show up there; the device build is the one that ships).
+#define ZPC_HD __host__ __device__ __forceinline__
+
 namespace zpcm {
 
+ZPC_HD float bits_to_float(unsigned u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
 template <int AXIS>
-__device__ __forceinline__ void jacobi_step(float &pp, float &qq, float &off, float &rr, float &a, float &b,
+ZPC_HD void jacobi_step(float &pp, float &qq, float &off, float &rr, float &a, float &b,
                                             float (&q)[4]) {
   const float tiny = 1.e-20f, gamma = 5.8284273147583007813f;
-  const float sin_pi8 = __uint_as_float(1053028117u), cos_pi8 = __uint_as_float(1064076127u);
+  const float sin_pi8 = bits_to_float(1053028117u), cos_pi8 = bits_to_float(1064076127u);
   float sh = off * 0.5f;
   float t5 = pp - qq;
   const bool big = sh * sh >= tiny;
@@ -62,13 +78,13 @@ __device__ __forceinline__ void jacobi_step(float &pp, float &qq, float &off, fl
   q[1 + C] -= t[B];
 }
 
-__device__ __forceinline__ float rsqrt_refined(float x) {  // one Newton step, SVD.hpp:386-392
+ZPC_HD float rsqrt_refined(float x) {  // one Newton step, SVD.hpp:386-392
   const float r = rsqrtf(x);
   const float h = r * 0.5f;
   return (r + h) - x * (r * (r * h));
 }
 
-__device__ __forceinline__ void qr_givens(float piv, float low, float &c, float &s) {
+ZPC_HD void qr_givens(float piv, float low, float &c, float &s) {
   const float small = 1.e-12f;
   float sh = (low * low >= small) ? low : 0.0f;
   float ch = fmaxf(fmaxf(-piv, piv), small);
@@ -84,14 +100,14 @@ __device__ __forceinline__ void qr_givens(float piv, float low, float &c, float 
   s = sh * ch;
   s = s + s;
 }
-__device__ __forceinline__ void rot_pair(float &x, float &y, float c, float s) {
+ZPC_HD void rot_pair(float &x, float &y, float c, float s) {
   const float t1 = s * x, t2 = s * y;
   x = c * x + t2;
   y = c * y - t1;
 }
 
 // F, U, V column-major; S the three singular values (signed so that U,V are rotations)
-__device__ __forceinline__ void svd3(const float (&F)[9], float (&U)[9], float (&S)[3], float (&V)[9]) {
+ZPC_HD void svd3(const float (&F)[9], float (&U)[9], float (&S)[3], float (&V)[9]) {
   // row-major local copy a[r][c] = F[3c+r]
   float a00 = F[0], a01 = F[3], a02 = F[6], a10 = F[1], a11 = F[4], a12 = F[7], a20 = F[2], a21 = F[5], a22 = F[8];
   float s11 = a00 * a00 + a10 * a10 + a20 * a20;
@@ -166,7 +182,7 @@ inline void lame_host(float E, float nu, float &mu, float &lam) {
 }
 
 // PF = P(F) F^T * volume for the fixed-corotated model
-__device__ __forceinline__ void stress_fcr(float volume, float mu, float lam, const float (&F)[9], float (&PF)[9]) {
+ZPC_HD void stress_fcr(float volume, float mu, float lam, const float (&F)[9], float (&PF)[9]) {
   float U[9], S[3], V[9];
   svd3(F, U, S, V);
   const float J = S[0] * S[1] * S[2];
@@ -187,9 +203,9 @@ __device__ __forceinline__ void stress_fcr(float volume, float mu, float lam, co
 
 // math::sqrtNewtonRaphson<float> (math/MathUtils.h:239-251): Newton iteration from 1 until the step is below
 // max(n * 1e-6, 128 eps).  Restated loop for loop: its result is only ~1e-6 accurate and the yield test depends on it.
-__device__ __forceinline__ float sqrt_newton_raphson(float n) {
+ZPC_HD float sqrt_newton_raphson(float n) {
   const float eps = 128.f * 1.1920928955078125e-7f;
-  if (n < -eps) return __int_as_float(0x7fc00000);
+  if (n < -eps) return bits_to_float(0x7fc00000u);
   if (n < eps) return 0.f;
   float xn = 1.f;
   float xnp1 = 0.5f * (xn + n / xn);
@@ -201,7 +217,7 @@ __device__ __forceinline__ float sqrt_newton_raphson(float n) {
 // compute_stress_vonmisesfixedcorotated (physics/ConstitutiveModel_Vol_dP.hpp:49-110): fixed-corotated trial stress in
 // principal space, radial return onto the von Mises cylinder, projected singular values, then the fixed-corotated
 // P F^T with the projected F (the projection is not written back to the particle: P2G.hpp:85-91 works on a copy)
-__device__ __forceinline__ void stress_vonmises(float volume, float mu, float lam, float yield_stress, const float (&Fin)[9],
+ZPC_HD void stress_vonmises(float volume, float mu, float lam, float yield_stress, const float (&Fin)[9],
                                                 float (&PF)[9]) {
   float F[9], U[9], S[3], V[9];
 #pragma unroll
@@ -249,13 +265,157 @@ __device__ __forceinline__ void stress_vonmises(float volume, float mu, float la
     for (int r = 0; r < 3; ++r) PF[3 * c + r] = (P[r] * F[c] + P[3 + r] * F[3 + c] + P[6 + r] * F[6 + c]) * volume;
 }
 
+// matmul_mat_diag_matT_3D (math/matrix/MatrixUtils.h:26-47): out = A diag(d) B^T, column-major
+ZPC_HD void mat_diag_matT(float (&out)[9], const float (&a)[9], const float (&d)[3], const float (&b)[9]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) out[3 * c + r] = a[r] * d[0] * b[c] + a[3 + r] * d[1] * b[3 + c] + a[6 + r] * d[2] * b[6 + c];
+}
+
+// NACCConfig::bulk() / Msqr() (physics/ConstitutiveModel.hpp:756-776); fa goes to sin as is (radians), like the reference.
+// Evaluated once on the host and passed to the kernel.
+inline float nacc_bulk_host(float E, float nu) { return 2.f / 3.f * (E / (2 * (1 + nu))) + (E * nu / ((1 + nu) * (1 - 2 * nu))); }
+inline float nacc_msqr_host(float fa, int dim) {
+  const float sin_phi = sinf(fa);
+  const float mohr = sqrtf(2.f / 3.f) * 2.f * sin_phi / (3.f - sin_phi);
+  const float M = mohr * dim / sqrtf(2.f / (6.f - dim));
+  return M * M;
+}
+
+// compute_stress_sand (physics/ConstitutiveModel_Vol_dP.hpp:242-326): Drucker-Prager return mapping in Hencky strain.
+// The projected F stays local (P2G.hpp:85 works on a copy); logJp is read and written back (P2G.hpp:93,101).
+// math::sqrt (math/MathUtils.h:288-323, a software root within 1 ulp) is sqrtf here.
+ZPC_HD void stress_sand(float volume, float mu, float lam, float cohesion, float beta, float yieldSurface, bool volCorrection,
+                        float &logJp, const float (&Fin)[9], float (&PF)[9]) {
+  float F[9], U[9], S[3], V[9];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) F[d] = Fin[d];
+  svd3(F, U, S, V);
+  const float scaled_mu = 2.f * mu;
+  float epsilon[3], New_S[3] = {0.f, 0.f, 0.f}, New_F[9], epsilon_hat[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float abs_S = fabsf(S[i]);
+    abs_S = (double)abs_S > 1e-4 ? abs_S : (float)1e-4;
+    epsilon[i] = logf(abs_S) - cohesion;
+  }
+  const float sum_epsilon = epsilon[0] + epsilon[1] + epsilon[2];
+  const float trace_epsilon = sum_epsilon + logJp;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) epsilon_hat[i] = epsilon[i] - (trace_epsilon / 3.f);
+  const float epsilon_hat_norm = sqrtf(epsilon_hat[0] * epsilon_hat[0] + epsilon_hat[1] * epsilon_hat[1] + epsilon_hat[2] * epsilon_hat[2]);
+  if (trace_epsilon >= 0.f) {  // case II: the cone tip
+    New_S[0] = New_S[1] = New_S[2] = expf(cohesion);
+    mat_diag_matT(New_F, U, New_S, V);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+    if (volCorrection) logJp = beta * sum_epsilon + logJp;
+  } else if (mu != 0.f) {
+    logJp = 0.f;
+    const float delta_gamma = epsilon_hat_norm + (3.f * lam + scaled_mu) / scaled_mu * trace_epsilon * yieldSurface;
+    float H[3];
+    if (delta_gamma <= 0.f) {  // case I: inside the cone
+#pragma unroll
+      for (int i = 0; i < 3; ++i) H[i] = epsilon[i] + cohesion;
+    } else {  // case III: onto the cone surface
+#pragma unroll
+      for (int i = 0; i < 3; ++i) H[i] = epsilon[i] - (delta_gamma / epsilon_hat_norm) * epsilon_hat[i] + cohesion;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) New_S[i] = expf(H[i]);
+    mat_diag_matT(New_F, U, New_S, V);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+  }
+  const float New_S_log[3] = {logf(New_S[0]), logf(New_S[1]), logf(New_S[2])};
+  const float trace_log_S = New_S_log[0] + New_S_log[1] + New_S_log[2];
+  float P_hat[3], P[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) P_hat[i] = (scaled_mu * New_S_log[i] + lam * trace_log_S) / New_S[i];
+  mat_diag_matT(P, U, P_hat, V);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) PF[3 * c + r] = (P[r] * F[c] + P[3 + r] * F[3 + c] + P[6 + r] * F[6 + c]) * volume;
+}
+
+// compute_stress_nacc (physics/ConstitutiveModel_Vol_dP.hpp:116-240): non-associated Cam-Clay with the hardening solve of
+// the "#if 1" branch; p0 = bm*1e-5 + sin(xi*max(-logJp,0)) evaluated in double like the reference (:123, sin — not sinh).
+ZPC_HD void stress_nacc(float volume, float mu, float bm, float xi, float beta, float Msqr, bool hardeningOn, float &logJp,
+                        const float (&Fin)[9], float (&PF)[9]) {
+  float F[9], U[9], S[3], V[9], New_F[9];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) F[d] = Fin[d];
+  svd3(F, U, S, V);
+  const float p0 = (float)((double)(bm * (float)0.00001) + sin((double)(xi * (-logJp > 0 ? -logJp : 0.f))));
+  const float p_min = -beta * p0;
+  const float Je_trial = S[0] * S[1] * S[2];
+  const float B_hat_trial[3] = {S[0] * S[0], S[1] * S[1], S[2] * S[2]};
+  const float trace_B_hat_trial_divdim = (B_hat_trial[0] + B_hat_trial[1] + B_hat_trial[2]) / 3.f;
+  const float J_power_neg_2_d_mulmu = mu * powf(Je_trial, -2.f / 3.f);
+  const float s_hat_trial[3] = {J_power_neg_2_d_mulmu * (B_hat_trial[0] - trace_B_hat_trial_divdim),
+                                J_power_neg_2_d_mulmu * (B_hat_trial[1] - trace_B_hat_trial_divdim),
+                                J_power_neg_2_d_mulmu * (B_hat_trial[2] - trace_B_hat_trial_divdim)};
+  const float psi_kappa_partial_J = bm * 0.5f * (Je_trial - 1.f / Je_trial);
+  const float p_trial = -psi_kappa_partial_J * Je_trial;
+  const float y_s_half_coeff = 3.f / 2.f * (1 + 2.f * beta);
+  const float y_p_half = (Msqr * (p_trial - p_min) * (p_trial - p0));
+  const float s_hat_trial_sqrnorm = s_hat_trial[0] * s_hat_trial[0] + s_hat_trial[1] * s_hat_trial[1] + s_hat_trial[2] * s_hat_trial[2];
+  const float y = (y_s_half_coeff * s_hat_trial_sqrnorm) + y_p_half;
+  if (p_trial > p0 || p_trial < p_min) {  // cases 1 and 2: project to the max / min tip of the yield surface
+    const float Je_new = sqrtf(-2.f * (p_trial > p0 ? p0 : p_min) / bm + 1.f);
+    S[0] = S[1] = S[2] = powf(Je_new, 1.f / 3.f);
+    mat_diag_matT(New_F, U, S, V);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+    if (hardeningOn) logJp += logf(Je_trial / Je_new);
+  } else if ((double)y >= 1e-4) {  // case 3, outside the yield surface: project onto it
+    const float B_s_coeff = powf(Je_trial, 2.f / 3.f) / mu * sqrtf(-y_p_half / y_s_half_coeff) / sqrtf(s_hat_trial_sqrnorm);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S[i] = sqrtf(s_hat_trial[i] * B_s_coeff + trace_B_hat_trial_divdim);
+    mat_diag_matT(New_F, U, S, V);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = New_F[i];
+    if (hardeningOn && (double)p0 > 1e-4 && (double)p_trial < (double)p0 - 1e-4 && (double)p_trial > 1e-4 + (double)p_min) {
+      const float p_center = (1.f - beta) * p0 / 2;
+      const float q_trial = sqrtf(3.f / 2.f * s_hat_trial_sqrnorm);
+      float direction[2] = {p_center - p_trial, -q_trial};
+      const float direction_norm = sqrtf(direction[0] * direction[0] + direction[1] * direction[1]);
+      direction[0] /= direction_norm;
+      direction[1] /= direction_norm;
+      const float C = Msqr * (p_center - p_min) * (p_center - p0);
+      const float B = Msqr * direction[0] * (2 * p_center - p0 - p_min);
+      const float A = Msqr * direction[0] * direction[0] + (1 + 2 * beta) * direction[1] * direction[1];
+      const float disc = sqrtf(B * B - 4 * A * C);
+      const float l1 = (-B + disc) / (2 * A), l2 = (-B - disc) / (2 * A);
+      const float p1 = p_center + l1 * direction[0], p2 = p_center + l2 * direction[0];
+      const float p_fake = (p_trial - p_center) * (p1 - p_center) > 0 ? p1 : p2;
+      const float tmp_Je_sqr = (-2 * p_fake / bm + 1);
+      const float Je_new_fake = sqrtf(fabsf(tmp_Je_sqr));
+      if ((double)Je_new_fake > 1e-4) logJp += logf(Je_trial / Je_new_fake);
+    }
+  }
+  const float J = S[0] * S[1] * S[2];
+  float b[9];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) b[3 * c + r] = F[r] * F[c] + F[3 + r] * F[3 + c] + F[6 + r] * F[6 + c];
+  const float tr3 = (b[0] + b[4] + b[8]) / 3.f;
+  const float dev_b_coeff = mu * powf(J, -2.f / 3.f);
+  const float i_coeff = bm * .5f * (J * J - 1.f);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) PF[i] = (i % 4 == 0) ? (dev_b_coeff * (b[i] - tr3) + i_coeff) * volume : (dev_b_coeff * b[i]) * volume;
+}
+
 // LocalArena::init (simulation/Utils.hpp:51-70): base node, in-cell offset (scaled by dx), 3x3 weights
 struct Arena {
   int corner[3];
   float local[3];   // (X - corner) * dx
   float w[3][3];
 };
-__device__ __forceinline__ void arena_init(Arena &a, float dx, const float (&pos)[3]) {
+ZPC_HD void arena_init(Arena &a, float dx, const float (&pos)[3]) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const float X = pos[d] / dx;  // reference divides (Utils.hpp:56), it does not multiply by 1/dx
