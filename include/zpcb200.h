@@ -196,17 +196,17 @@ typedef struct zpc_equation_of_state {
   float bulk, gamma, viscosity;
 } zpc_equation_of_state;
 
-/* An analytic Collider — geometry/Collider.h:10-143 over AnalyticLevelSet<Plane> / <Sphere>
- * (geometry/AnalyticLevelSet.h:11-43, 130-157) with its rigid motion x = R s X + b (Collider.h:16-24, 136-143):
+/* An analytic Collider — geometry/Collider.h:10-143 over AnalyticLevelSet<Plane> / <Sphere> / <Cuboid>
+ * (geometry/AnalyticLevelSet.h:11-43, 130-157, 55-126) with its rigid motion x = R s X + b (Collider.h:16-24, 136-143):
  * translation b and its rate, rotation R (row-major) and angular velocity, uniform scale s and its rate.  The level set
  * is given in material space; the defaults (b = 0, R = I, s = 1, all rates 0) are a static collider.  Initialise with
  * zpcb200_collider_static() or set every field. */
-enum { ZPC_GEOM_PLANE = 0, ZPC_GEOM_SPHERE = 1 };
+enum { ZPC_GEOM_PLANE = 0, ZPC_GEOM_SPHERE = 1, ZPC_GEOM_CUBOID = 2 };
 enum { ZPC_COLLIDER_STICKY = 0, ZPC_COLLIDER_SLIP = 1, ZPC_COLLIDER_SEPARATE = 2 }; /* collider_e, Collider.h:8 */
 typedef struct zpc_collider {
   int geometry, type;
-  float origin[3]; /* plane origin | sphere centre (material space) */
-  float normal[3]; /* plane unit normal | {radius, -, -} */
+  float origin[3]; /* plane origin | sphere centre | cuboid min corner (material space) */
+  float normal[3]; /* plane unit normal | {radius, -, -} | cuboid max corner */
   float b[3], dbdt[3];
   float R[9];
   float omega[3];

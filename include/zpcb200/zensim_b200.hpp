@@ -355,6 +355,31 @@ struct ComputeGridBlockVelocity {  // {cuda_c, wrapv<apic>{}, grids, dt, gravity
     return zpcb200_grid_update(grids.view(), table._cnt.data(), dt, extf, mode, maxVel, pol._stream);
   }
 };
+// Collider{AnalyticLevelSet<Plane | Sphere | Cuboid>, collider_e} with its rigid motion (geometry/Collider.h:10-143,
+// geometry/AnalyticLevelSet.h) and ApplyBoundaryConditionOnGridBlocks{cuda_c, collider, table, grids} (GridOp.hpp:112-164)
+enum class collider_e : int { Sticky = 0, Slip = 1, Separate = 2 };
+struct Collider {
+  zpc_collider c;
+  static Collider make(int geom, collider_e type, const float (&p0)[3], const float (&p1)[3]) {
+    Collider r{zpcb200_collider_static(geom, (int)type, p0, p1)};
+    return r;
+  }
+  static Collider plane(const float (&origin)[3], const float (&normal)[3], collider_e t = collider_e::Sticky) { return make(ZPC_GEOM_PLANE, t, origin, normal); }
+  static Collider sphere(const float (&center)[3], float radius, collider_e t = collider_e::Sticky) {
+    const float r[3] = {radius, 0.f, 0.f};
+    return make(ZPC_GEOM_SPHERE, t, center, r);
+  }
+  static Collider cuboid(const float (&mn)[3], const float (&mx)[3], collider_e t = collider_e::Sticky) { return make(ZPC_GEOM_CUBOID, t, mn, mx); }
+  void setTranslation(const float (&b)[3], const float (&dbdt)[3]) { for (int d = 0; d < 3; ++d) { c.b[d] = b[d]; c.dbdt[d] = dbdt[d]; } }
+  void setRotation(const float (&R)[9], const float (&omega)[3]) {  // R row-major
+    for (int d = 0; d < 9; ++d) c.R[d] = R[d];
+    for (int d = 0; d < 3; ++d) c.omega[d] = omega[d];
+  }
+};
+struct ApplyBoundaryConditionOnGridBlocks {
+  Collider collider; HashTable &table; Grids &grids;
+  int launch(const CudaExecutionPolicy &pol) { return zpcb200_apply_boundary(grids.view(), table.view(), collider.c, pol._stream); }
+};
 struct G2PTransfer {
   float dt; Grids &grids; HashTable &table; Particles &pars;
   int launch(const CudaExecutionPolicy &pol) { return zpcb200_g2p_apic(pars.view(), table.view(), grids.view(), dt, pol._stream); }

@@ -774,7 +774,46 @@ void zo_g2p_eos(int n, float *x, float *v, float *C, float *Jp, float dx, float 
  * default R = I, s = 1, b = dbdt = omega = 0, so v_object = 0): geom 0 = Plane{origin p0, normal p1}
  * (AnalyticLevelSet.h:11-43), geom 1 = Sphere{centre p0, radius p1[0]} (:130-157); type = collider_e
  * {0 Sticky, 1 Slip, 2 Separate} (Collider.h:8). */
-/* motion (may be NULL = the default rigid motion): b[3], dbdt[3], R[9] row-major, omega[3], s, dsdt — Collider.h:16-24,136-143 */
+/* AnalyticLevelSet<Cuboid>::do_getSignedDistance (AnalyticLevelSet.h:89-96): box [mn, mx] */
+static float cuboid_sdf(const float x[3], const float mn[3], const float mx[3]) {
+  float point[3];
+  for (int i = 0; i < 3; ++i) {
+    const float center = (mn[i] + mx[i]) / 2;
+    const float a = x[i] - center;
+    point[i] = (a > 0 ? a : -a) - (mx[i] - mn[i]) / 2;
+  }
+  float max = point[0];
+  for (int i = 1; i < 3; ++i) if (point[i] > max) max = point[i];
+  for (int i = 0; i < 3; ++i) if (point[i] < 0) point[i] = 0;
+  float l2 = 0.f;
+  for (int i = 0; i < 3; ++i) l2 += point[i] * point[i];
+  return (max < 0 ? max : 0) + sqrtf(l2);
+}
+/* ::do_getNormal (:98-110): central differences of the signed distance with eps = 1e-6 IN FLOAT, then normalized() */
+static void cuboid_normal(const float x[3], const float mn[3], const float mx[3], float nm[3]) {
+  const float eps = (float)1e-6;
+  float diff[3];
+  for (int i = 0; i < 3; ++i) {
+    float v1[3] = {x[0], x[1], x[2]}, v2[3] = {x[0], x[1], x[2]};
+    v1[i] = x[i] + eps;
+    v2[i] = x[i] - eps;
+    diff[i] = (cuboid_sdf(v1, mn, mx) - cuboid_sdf(v2, mn, mx)) / (eps + eps);
+  }
+  float l2 = 0.f;
+  for (int i = 0; i < 3; ++i) l2 += diff[i] * diff[i];
+  const float len = sqrtf(l2);
+  for (int i = 0; i < 3; ++i) nm[i] = diff[i] / len;
+}
+
+void zo_cuboid(int n, const float *x, const float mn[3], const float mx[3], float *sdf, float *normal) {
+  for (int p = 0; p < n; ++p) {
+    sdf[p] = cuboid_sdf(x + 3 * p, mn, mx);
+    cuboid_normal(x + 3 * p, mn, mx, normal + 3 * p);
+  }
+}
+
+/* motion (may be NULL = the default rigid motion): b[3], dbdt[3], R[9] row-major, omega[3], s, dsdt — Collider.h:16-24,136-143;
+ * geom 2 = Cuboid{min p0, max p1} (AnalyticLevelSet.h:55-126) */
 void zo_apply_boundary_moving(int nblocks, const int *active_keys, float *grid, float dx, int geom, int type,
                               const float p0[3], const float p1[3], const float *motion) {
   float bb[3] = {0, 0, 0}, dbdt[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, om[3] = {0, 0, 0}, sc = 1.f, dsdt = 0.f;
@@ -806,6 +845,10 @@ void zo_apply_boundary_moving(int nblocks, const int *active_keys, float *grid, 
         dist = 0.f;
         for (int k = 0; k < 3; ++k) dist += p1[k] * d[k];              /* _normal.dot(x - _origin) */
         for (int k = 0; k < 3; ++k) nm[k] = p1[k];
+      } else if (geom == 2) {
+        dist = cuboid_sdf(X, p0, p1);
+        if (dist < 0.f && type != 0) cuboid_normal(X, p0, p1, nm);     /* only evaluated where it is used (:116) */
+        else nm[0] = nm[1] = nm[2] = 0.f;
       } else {
         float l2 = 0.f;
         for (int k = 0; k < 3; ++k) l2 += d[k] * d[k];

@@ -316,6 +316,13 @@ class Oracle:
             self.lib.zo_apply_boundary_moving(C.c_int(grid.shape[0]), _ptr(k), _ptr(grid), C.c_float(dx), C.c_int(geom),
                                               C.c_int(ctype), _ptr(a), _ptr(b), _ptr(m))
 
+    def cuboid(self, x, mn, mx):
+        x = np.ascontiguousarray(x, np.float32)
+        mn = np.ascontiguousarray(mn, np.float32); mx = np.ascontiguousarray(mx, np.float32)
+        sdf = np.empty(x.shape[0], np.float32); nm = np.empty((x.shape[0], 3), np.float32)
+        self.lib.zo_cuboid(C.c_int(x.shape[0]), _ptr(x), _ptr(mn), _ptr(mx), _ptr(sdf), _ptr(nm))
+        return sdf, nm
+
     def g2p(self, P, tab, grid, dx, dt):
         n = P["x"].shape[0]
         self.lib.zo_g2p(C.c_int(n), _ptr(P["x"]), _ptr(P["v"]), _ptr(P["C"]), _ptr(P["F"]),

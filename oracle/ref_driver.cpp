@@ -251,6 +251,9 @@ void zpcref_mpm_apply_boundary(void *h, int geom, int type, const float *p0, con
     if (geom == 0) {
       Collider col{AnalyticLevelSet<analytic_geometry_e::Plane, float, 3>{TV{p0[0], p0[1], p0[2]}, TV{p1[0], p1[1], p1[2]}}, ct};
       pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
+    } else if (geom == 2) {  // Cuboid{min, max} (AnalyticLevelSet.h:55-126)
+      Collider col{AnalyticLevelSet<analytic_geometry_e::Cuboid, float, 3>{TV{p0[0], p0[1], p0[2]}, TV{p1[0], p1[1], p1[2]}}, ct};
+      pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
     } else {
       Collider col{AnalyticLevelSet<analytic_geometry_e::Sphere, float, 3>{TV{p0[0], p0[1], p0[2]}, p1[0]}, ct};
       pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
@@ -276,6 +279,10 @@ void zpcref_mpm_apply_boundary_moving(void *h, int geom, int type, const float *
   with_policy(s.nthreads, [&](auto &pol, auto tag) {
     if (geom == 0) {
       Collider col{AnalyticLevelSet<analytic_geometry_e::Plane, float, 3>{TV{p0[0], p0[1], p0[2]}, TV{p1[0], p1[1], p1[2]}}, ct};
+      setup(col);
+      pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
+    } else if (geom == 2) {
+      Collider col{AnalyticLevelSet<analytic_geometry_e::Cuboid, float, 3>{TV{p0[0], p0[1], p0[2]}, TV{p1[0], p1[1], p1[2]}}, ct};
       setup(col);
       pol(Collapse{(size_t)s.nblocks, (size_t)64}, ApplyBoundaryConditionOnGridBlocks{tag, col, s.table, s.grids});
     } else {

@@ -85,6 +85,29 @@ def boundary_moving_case(ref, name, s, G, **kw):
     print(name, "n", n, len(MOVING_COLLIDERS), "moving colliders")
 
 
+def boundary_cuboid_case(ref, name, s, G, **kw):
+    """ApplyBoundaryConditionOnGridBlocks over AnalyticLevelSet<Cuboid> colliders, static and moving (tests/parity.py
+    CUBOID_COLLIDERS): signed distance of a box, normal by central differences (AnalyticLevelSet.h:89-110)"""
+    from tests.parity import CUBOID_COLLIDERS, motion_vec
+    P = synth.elastic_cube(s, G, **kw)
+    n, dx = P["x"].shape[0], P["dx"]
+    out = {}
+    for i, (geom, ctype, p0, p1, motion) in enumerate(CUBOID_COLLIDERS):
+        h = ref.mpm(n, dx, 0)
+        h.set_particles(P)
+        h.partition()
+        tab = h.table()
+        h.clean_grid()
+        h.p2g(synth.DT, synth.MODEL["E"], synth.MODEL["nu"], P["volume"])
+        h.grid_update(synth.DT, synth.GRAVITY, 1)
+        h.apply_boundary(geom, ctype, p0, p1, motion_vec(motion))
+        out["grid_%d" % i] = h.grid()
+        out["active_keys"] = tab["active_keys"]
+        h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), s=s, G=G, kw=repr(sorted(kw.items())), **out)
+    print(name, "n", n, len(CUBOID_COLLIDERS), "cuboid colliders")
+
+
 def vonmises_margin(P, E, nu, ys):
     """smallest relative distance of any particle's trial deviatoric stress norm from the yield radius"""
     mu, lam = 0.5 * E / (1 + nu), E * nu / ((1 + nu) * (1 - 2 * nu))
@@ -298,6 +321,7 @@ if __name__ == "__main__":
     boundary_case(r, "mpm_cube7_boundary", 7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
     boundary_moving_case(r, "mpm_cube7_boundary_moving", 7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
     vonmises_case(r, "mpm_cube6_vonmises", 6, 32, 2946.0, jitter_F=0.05, jitter_C=0.5, shuffle_seed=17)   # 39 % of the particles yield
+    boundary_cuboid_case(r, "mpm_cube7_boundary_cuboid", 7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
     sand_case(r, "mpm_cube6_sand", 6, 32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=19)
     nacc_case(r, "mpm_cube6_nacc", 6, 32, jitter_F=0.03, jitter_C=0.5, shuffle_seed=23)
     if "--all" in sys.argv:   # the primitive / SVD vectors use unseeded-order-independent inputs: regenerate on demand

@@ -29,6 +29,13 @@ void hm_stress(int model, int n, float volume, float mu, float lam, const float 
     for (int d = 0; d < 9; ++d) PF[9 * p + d] = pf[d];
   }
 }
+// AnalyticLevelSet<Cuboid>: signed distance and finite-difference normal at n points
+void hm_cuboid(int n, const float *x, const float *mn, const float *mx, float *sdf, float *normal) {
+  for (int p = 0; p < n; ++p) {
+    sdf[p] = zpcm::cuboid_sdf(x[3 * p], x[3 * p + 1], x[3 * p + 2], mn, mx);
+    zpcm::cuboid_normal(x[3 * p], x[3 * p + 1], x[3 * p + 2], mn, mx, normal[3 * p], normal[3 * p + 1], normal[3 * p + 2]);
+  }
+}
 // LocalArena: corner[3], local[3], w[9] per position
 void hm_arena(int n, float dx, const float *x, int *corner, float *local, float *w) {
   for (int p = 0; p < n; ++p) {

@@ -88,7 +88,19 @@ MOVING_COLLIDERS = [  # (geometry, collider type, p0, p1, motion = b, dbdt, R, o
 ]
 
 
+# AnalyticLevelSet<Cuboid>{min, max} colliders (geometry/AnalyticLevelSet.h:55-126): static and moving, all three types
+CUBOID_COLLIDERS = [  # (geometry = 2, collider type, box min, box max, motion or None)
+    (2, 0, (0.2, 0.2, 0.2), (0.3, 0.3, 0.45), None),
+    (2, 1, (0.2, 0.2, 0.2), (0.3, 0.3, 0.45), None),
+    (2, 2, (0.25, 0.1, 0.2), (0.5, 0.3, 0.33), None),
+    (2, 1, (-0.05, -0.04, -0.06), (0.05, 0.04, 0.06), ((0.3, 0.3, 0.3), (0.2, 0.0, 0.1), _rot((1, 2, 3), 0.7), (1.0, -2.0, 0.5), 1.2, 0.3)),
+    (2, 2, (-0.05, -0.04, -0.06), (0.05, 0.04, 0.06), ((0.33, 0.27, 0.3), (0.0, 0.5, 0.0), _rot((0, 0, 1), 0.4), (0.0, 0.0, 2.0), 1.0, 0.0)),
+]
+
+
 def motion_vec(m):
+    if m is None:
+        return None
     b, dbdt, R, om, s, dsdt = m
     return np.concatenate([np.asarray(b, np.float32), np.asarray(dbdt, np.float32), np.asarray(R, np.float32).reshape(9),
                            np.asarray(om, np.float32), np.asarray([s, dsdt], np.float32)]).astype(np.float32)

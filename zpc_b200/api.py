@@ -605,7 +605,7 @@ def compute_grid_block_velocity(grids, table, dt, extf, mode, max_vel_sqr, strea
            "grid_update")
 
 
-GEOM_PLANE, GEOM_SPHERE = 0, 1
+GEOM_PLANE, GEOM_SPHERE, GEOM_CUBOID = 0, 1, 2
 COLLIDER_STICKY, COLLIDER_SLIP, COLLIDER_SEPARATE = 0, 1, 2
 
 
@@ -623,6 +623,11 @@ def plane_collider(origin, normal, ctype=COLLIDER_STICKY, **motion):
 
 def sphere_collider(center, radius, ctype=COLLIDER_STICKY, **motion):
     return _collider(GEOM_SPHERE, ctype, center, (radius, 0.0, 0.0), **motion)
+
+
+def cuboid_collider(box_min, box_max, ctype=COLLIDER_STICKY, **motion):
+    """Collider over AnalyticLevelSet<Cuboid>{min, max} (geometry/AnalyticLevelSet.h:55-126)"""
+    return _collider(GEOM_CUBOID, ctype, box_min, box_max, **motion)
 
 
 def apply_boundary_condition(collider, table, grids, stream=None):

@@ -49,7 +49,7 @@ __global__ void part_place_kernel(const unsigned *sorted, const int *list_cnt, i
   if (blockIdx.x == 0 && threadIdx.x == 0) *cnt = n;
 }
 
-// Collider::resolveCollision over AnalyticLevelSet<Plane | Sphere> with the default rigid motion (geometry/Collider.h:98-127,
+// Collider::resolveCollision over AnalyticLevelSet<Plane | Sphere | Cuboid> with the default rigid motion (geometry/Collider.h:98-127,
 // geometry/AnalyticLevelSet.h:11-43,130-157): projects the velocity of a node at (px,py,pz) that lies inside the collider
 __device__ __forceinline__ void collide(const zpc_collider &col, float px, float py, float pz, float &vx, float &vy, float &vz) {
   // material-space position X = R^T (x - b) / s (Collider.h:106-108); products and sums in the reference's order, no contraction
@@ -65,6 +65,10 @@ __device__ __forceinline__ void collide(const zpc_collider &col, float px, float
   if (col.geometry == ZPC_GEOM_PLANE) {
     m0 = col.normal[0]; m1 = col.normal[1]; m2 = col.normal[2];
     dist = __fadd_rn(__fadd_rn(__fmul_rn(m0, d0), __fmul_rn(m1, d1)), __fmul_rn(m2, d2));
+  } else if (col.geometry == ZPC_GEOM_CUBOID) {  // origin = box min, normal = box max (material space)
+    dist = zpcm::cuboid_sdf(X0, X1, X2, col.origin, col.normal);
+    m0 = m1 = m2 = 0.f;
+    if (dist < 0.f && col.type != ZPC_COLLIDER_STICKY) zpcm::cuboid_normal(X0, X1, X2, col.origin, col.normal, m0, m1, m2);
   } else {
     const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
     const float len = sqrtf(l2);
@@ -208,7 +212,7 @@ int zpcb200_grid_update(zpc_grids_view g, const int *cnt, float dt, const float 
 }
 
 int zpcb200_apply_boundary(zpc_grids_view g, zpc_hashtable_view tb, zpc_collider col, zpc_stream_t stream) {
-  if (!g.tiles || !tb.activeKeys || !tb.cnt || g.numChannels < 4 || (unsigned)col.geometry > 1u || (unsigned)col.type > 2u || !(col.s > 0.f))
+  if (!g.tiles || !tb.activeKeys || !tb.cnt || g.numChannels < 4 || (unsigned)col.geometry > 2u || (unsigned)col.type > 2u || !(col.s > 0.f))
     return ZPCB200_E_BADARG;
   apply_boundary_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks,
                                                                            g.dx, col);
@@ -234,7 +238,7 @@ int zpcb200_grid_update_bc(zpc_grids_view g, zpc_hashtable_view tb, float dt, co
   ColliderSet cs;
   cs.n = ncolliders;
   for (int k = 0; k < ncolliders; ++k) {
-    if ((unsigned)colliders[k].geometry > 1u || (unsigned)colliders[k].type > 2u || !(colliders[k].s > 0.f)) return ZPCB200_E_BADARG;
+    if ((unsigned)colliders[k].geometry > 2u || (unsigned)colliders[k].type > 2u || !(colliders[k].s > 0.f)) return ZPCB200_E_BADARG;
     cs.c[k] = colliders[k];
   }
   grid_update_bc_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks, g.dx,

@@ -409,6 +409,53 @@ ZPC_HD void stress_nacc(float volume, float mu, float bm, float xi, float beta, 
   for (int i = 0; i < 9; ++i) PF[i] = (i % 4 == 0) ? (dev_b_coeff * (b[i] - tr3) + i_coeff) * volume : (dev_b_coeff * b[i]) * volume;
 }
 
+// Individually rounded fp32 operations: the compiler may not contract them into FMAs on the device; the host build
+// (tests/hostmath, -ffp-contract=off) uses the plain operators, which is what the reference's host path executes.
+#ifdef __CUDA_ARCH__
+ZPC_HD float rn_add(float a, float b) { return __fadd_rn(a, b); }
+ZPC_HD float rn_sub(float a, float b) { return __fsub_rn(a, b); }
+ZPC_HD float rn_mul(float a, float b) { return __fmul_rn(a, b); }
+ZPC_HD float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+ZPC_HD float rn_sqrt(float a) { return __fsqrt_rn(a); }
+#else
+ZPC_HD float rn_add(float a, float b) { return a + b; }
+ZPC_HD float rn_sub(float a, float b) { return a - b; }
+ZPC_HD float rn_mul(float a, float b) { return a * b; }
+ZPC_HD float rn_div(float a, float b) { return a / b; }
+ZPC_HD float rn_sqrt(float a) { return sqrtf(a); }
+#endif
+
+// AnalyticLevelSet<Cuboid>::do_getSignedDistance (geometry/AnalyticLevelSet.h:89-96), box [mn, mx].  Every operation is
+// the reference's, individually rounded (no FMA contraction): the normal below is a central difference with eps = 1e-6 in
+// float — it amplifies a one-ulp difference of the distance to 1e-2 of a normal component, so only a bit-identical
+// distance reproduces the reference's normals.
+ZPC_HD float cuboid_sdf(float x0, float x1, float x2, const float *mn, const float *mx) {
+  const float x[3] = {x0, x1, x2};
+  float point[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float center = rn_div(rn_add(mn[i], mx[i]), 2.f);
+    const float a = rn_sub(x[i], center);
+    point[i] = rn_sub(a > 0.f ? a : -a, rn_div(rn_sub(mx[i], mn[i]), 2.f));
+  }
+  float mxp = point[0];
+  if (point[1] > mxp) mxp = point[1];
+  if (point[2] > mxp) mxp = point[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) if (point[i] < 0.f) point[i] = 0.f;
+  const float l2 = rn_add(rn_add(rn_add(0.f, rn_mul(point[0], point[0])), rn_mul(point[1], point[1])), rn_mul(point[2], point[2]));
+  return rn_add(mxp < 0.f ? mxp : 0.f, rn_sqrt(l2));
+}
+// ::do_getNormal (:98-110)
+ZPC_HD void cuboid_normal(float x0, float x1, float x2, const float *mn, const float *mx, float &n0, float &n1, float &n2) {
+  const float eps = (float)1e-6, two_eps = rn_add(eps, eps);
+  const float g0 = rn_div(rn_sub(cuboid_sdf(rn_add(x0, eps), x1, x2, mn, mx), cuboid_sdf(rn_sub(x0, eps), x1, x2, mn, mx)), two_eps);
+  const float g1 = rn_div(rn_sub(cuboid_sdf(x0, rn_add(x1, eps), x2, mn, mx), cuboid_sdf(x0, rn_sub(x1, eps), x2, mn, mx)), two_eps);
+  const float g2 = rn_div(rn_sub(cuboid_sdf(x0, x1, rn_add(x2, eps), mn, mx), cuboid_sdf(x0, x1, rn_sub(x2, eps), mn, mx)), two_eps);
+  const float len = rn_sqrt(rn_add(rn_add(rn_add(0.f, rn_mul(g0, g0)), rn_mul(g1, g1)), rn_mul(g2, g2)));
+  n0 = rn_div(g0, len); n1 = rn_div(g1, len); n2 = rn_div(g2, len);
+}
+
 // LocalArena::init (simulation/Utils.hpp:51-70): base node, in-cell offset (scaled by dx), 3x3 weights
 struct Arena {
   int corner[3];
