@@ -370,6 +370,10 @@ int zpcb200_unbin_particles(zpc_bins_view bins, zpc_particles_view pars, zpc_str
  * shared memory, cell-grouped register accumulation, bulk reduce-add of whole grid tiles. */
 int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,
                                 float dt, zpc_fixed_corotated model, zpc_stream_t stream);
+/* P2GTransfer<apic, VonMisesFixedCorotatedConfig> on the binned layout: the same kernel, the model enters the record
+ * phase only (P2G.hpp:89-90); G2P is zpcb200_g2p_apic_binned. */
+int zpcb200_p2g_apic_vonmises_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,
+                                     float dt, zpc_vonmises_fixed_corotated model, zpc_stream_t stream);
 int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,
                             float dt, zpc_stream_t stream);
 

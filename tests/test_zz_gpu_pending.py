@@ -118,3 +118,40 @@ def test_cuboid_colliders_match_oracle_and_golden(oracle):
         grids.tiles.copy_(after_p2g)      # fused with the grid update
         api.compute_grid_block_velocity_with_boundaries(grids, table, synth.DT, ext, 1, [col], mx.zero_())
         assert torch.equal(grids.tiles, torch.as_tensor(got, device="cuda"))
+
+
+@pytest.mark.parametrize("sweep", [4, 3])
+def test_vonmises_on_the_binned_path_matches_oracle_and_golden(oracle, sweep):
+    """VonMisesFixedCorotatedConfig through the block-binned P2G (zpcb200_p2g_apic_vonmises_binned: the model is a template
+    parameter of the record phase): vs the oracle, the reference-generated golden grid and the AoS kernel"""
+    from zpc_b200 import api
+    from tests.parity import GRID_RTOL
+    z = np.load(os.path.join(G, "mpm_cube6_vonmises.npz"))
+    ys = float(z["ys"])
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **dict(ast.literal_eval(str(z["kw"]))))
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    bins = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    api.bin_particles(pars, table, dx, bins, order)
+    model = api.model_vonmises(P["volume"], E, NU, ys)
+    api.set_tuning(sweep, -1)
+    try:
+        grids = api.Grids(dx, ht["nblocks"])
+        api.clean_grid_blocks(grids, table)
+        api.p2g_transfer(bins, table, grids, synth.DT, model)
+        torch.cuda.synchronize()
+    finally:
+        api.set_tuning(4, -1)
+    g1 = grids.tiles.cpu().numpy()
+    o1 = oracle.p2g_vonmises(P, ht, dx, synth.DT, E, NU, ys, P["volume"])
+    check_channels(g1, o1, 1, "binned vonmises p2g", GRID_RTOL, strict_frac=0.99)
+    fcr = oracle.p2g(P, ht, dx, synth.DT, E, NU, P["volume"])
+    assert np.abs(fcr[:, 4:7] - g1[:, 4:7]).max() > 1e-2 * np.abs(o1[:, 4:7]).max()      # it is not the elastic stress
+    _, gold = grid_by_key(z["active_keys"], z["grid_p2g"])
+    check_channels(g1, gold, 1, "binned vonmises golden p2g", GRID_RTOL)
+    grids2 = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids2, table)
+    api.p2g_transfer(pars, table, grids2, synth.DT, model)
+    check_channels(g1, grids2.tiles.cpu().numpy(), 1, "binned vs AoS vonmises", GRID_RTOL)

@@ -581,6 +581,10 @@ def p2g_transfer(pars, table, grids, dt, model, stream=None):
         fn = lib().zpcb200_p2g_apic_drucker_prager if isinstance(model, zpc_drucker_prager) else lib().zpcb200_p2g_apic_nacc
         _check(fn(pars.view(), table.view(), grids.view(), C.c_float(dt), model, _stream_ptr(stream)), "p2g(plastic)")
         return
+    if isinstance(model, zpc_vonmises_fixed_corotated) and isinstance(pars, ParticleBins):
+        _check(lib().zpcb200_p2g_apic_vonmises_binned(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
+                                                      _stream_ptr(stream)), "p2g(vonmises, binned)")
+        return
     if isinstance(model, zpc_vonmises_fixed_corotated):
         _check(lib().zpcb200_p2g_apic_vonmises(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
                                                _stream_ptr(stream)), "p2g(vonmises)")

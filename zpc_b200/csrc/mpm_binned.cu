@@ -145,12 +145,15 @@ __device__ __forceinline__ void sweep_cells3(const float4 *rec, int lo, int hi, 
 #ifndef ZPC_P2G_MINB
 #define ZPC_P2G_MINB 4
 #endif
-template <int VAR>
+// MODEL 0 = FixedCorotatedConfig, 1 = VonMisesFixedCorotatedConfig (yield_stress; P2G.hpp:89-90) — the model only enters
+// the records phase (and the stray path), the sweep and the write-back are the same
+template <int VAR, int MODEL = 0>
 __global__ void __launch_bounds__(P2G_NT, ZPC_P2G_MINB)
 p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
                   const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
-                  float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, int prefetch) {
+                  float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, int prefetch,
+                  float yield_stress) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GSmem &S = *reinterpret_cast<P2GSmem *>(smem_raw);
   const int bin = blockIdx.x;
@@ -264,7 +267,8 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
         float F[9], K[9];
 #pragma unroll
         for (int d = 0; d < 9; ++d) F[d] = pars[s + (ZPC_PB_F + d) * TS];
-        zpcm::stress_fcr(volume, mu, lam, F, K);
+        if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, K);
+        else zpcm::stress_fcr(volume, mu, lam, F, K);
 #pragma unroll
         for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
         float d0[3], loc[3], vel[3], C[9];
@@ -392,7 +396,8 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
 #pragma unroll
     for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
-    zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam);
+    if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
+    else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam);
   }
   if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
 }
@@ -909,6 +914,30 @@ Tuning &tuning() {
 
 }  // namespace
 
+// shared launch of the binned P2G: MODEL 0 fixed-corotated, 1 von Mises
+template <int MODEL>
+static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, float volume, float E, float nu,
+                             float yield_stress, zpc_stream_t stream) {
+  if (g.numChannels != 7 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
+    return ZPCB200_E_BADARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<3, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    attr_set = true;
+  }
+  const int variant = tuning().p2g_sweep;
+  float mu, lam;
+  zpcm::lame_host(E, nu, mu, lam);
+  const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
+  auto kern = variant == 3 ? p2g_binned_kernel<3, MODEL> : p2g_binned_kernel<4, MODEL>;
+  kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
+      bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
+      bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
 extern "C" {
 
 int zpcb200_set_tuning(int p2g_sweep, int g2p_staged) {
@@ -946,24 +975,11 @@ int zpcb200_unbin_particles(zpc_bins_view bins, zpc_particles_view pars, zpc_str
 
 int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_fixed_corotated model,
                                 zpc_stream_t stream) {
-  if (g.numChannels != 7 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
-    return ZPCB200_E_BADARG;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
-    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
-    attr_set = true;
-  }
-  const int variant = tuning().p2g_sweep;
-  float mu, lam;
-  zpcm::lame_host(model.E, model.nu, mu, lam);
-  const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
-  auto kern = variant == 3 ? p2g_binned_kernel<3> : p2g_binned_kernel<4>;
-  kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
-      bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
-      bins.cellOrderValid, tb, g.tiles, g.dx, dt, model.volume, mu, lam, variant == 3 ? 0 : 1);
-  ZPC_CHECK_LAUNCH();
-  return ZPCB200_OK;
+  return p2g_binned_launch<0>(bins, tb, g, dt, model.volume, model.E, model.nu, 0.f, stream);
+}
+int zpcb200_p2g_apic_vonmises_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt,
+                                     zpc_vonmises_fixed_corotated model, zpc_stream_t stream) {
+  return p2g_binned_launch<1>(bins, tb, g, dt, model.volume, model.E, model.nu, model.yieldStress, stream);
 }
 
 int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
