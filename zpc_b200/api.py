@@ -610,6 +610,7 @@ def compute_grid_block_velocity(grids, table, dt, extf, mode, max_vel_sqr, strea
 
 
 GEOM_PLANE, GEOM_SPHERE, GEOM_CUBOID = 0, 1, 2
+MAX_COLLIDERS = 4   # ZPCB200_MAX_COLLIDERS
 COLLIDER_STICKY, COLLIDER_SLIP, COLLIDER_SEPARATE = 0, 1, 2
 
 

@@ -9,6 +9,12 @@ particles in block-binned AoSoA TileVectors and re-bins every `rebin_every` subs
 (EnlargeSparsity{0,2}).  `partition="with_rebin"` (binned layout only) rebuilds it only together with the re-bin,
 enlarged by one more ring (EnlargeSparsity{-1,3}): a particle that has drifted by less than a block since then
 still finds every block of its stencil, the extra blocks stay empty (mass 0) and results are unchanged.
+
+`model=` selects the constitutive model (api.model_fcr | model_vonmises | model_eos | model_drucker_prager | model_nacc;
+default fixed-corotated from E, nu): the binned layout carries the 25 channels m, x, v, C, F, so it runs the F-only models
+(fixed-corotated, von Mises); the per-particle J / logJp of the other three lives in the AoS layout.  `colliders=` (up to
+four api.plane_collider / sphere_collider / cuboid_collider) are applied inside the grid-update pass
+(ComputeGridBlockVelocity + ApplyBoundaryConditionOnGridBlocks fused, GridOp.hpp:71-164).
 """
 import torch
 
@@ -21,7 +27,8 @@ def default_expected_blocks(n):
 
 class MpmSolver:
     def __init__(self, P, dx, volume, dt, gravity=-9.8, mode=1, layout="binned", expected_blocks=None,
-                 rebin_every=8, E=5.0e4, nu=0.4, device="cuda", shuffle_free=True, partition="every_step"):
+                 rebin_every=8, E=5.0e4, nu=0.4, device="cuda", shuffle_free=True, partition="every_step", model=None,
+                 colliders=()):
         if partition not in ("every_step", "with_rebin") or (partition == "with_rebin" and layout != "binned"):
             raise ValueError(partition)
         self.partition_mode = partition
@@ -29,7 +36,12 @@ class MpmSolver:
         self.device = device
         self.dx, self.dt, self.mode = float(dx), float(dt), int(mode)
         self.extf = (0.0, float(gravity), 0.0)
-        self.model = api.model_fcr(volume, E, nu)
+        self.model = model if model is not None else api.model_fcr(volume, E, nu)
+        if layout == "binned" and not isinstance(self.model, (api.zpc_fixed_corotated, api.zpc_vonmises_fixed_corotated)):
+            raise ValueError("the binned layout has no J / logJp channel: use layout='aos' for %s" % type(self.model).__name__)
+        self.colliders = list(colliders)
+        if len(self.colliders) > api.MAX_COLLIDERS:
+            raise ValueError("at most %d colliders per grid pass" % api.MAX_COLLIDERS)
         self.layout = layout
         self.n = int(P["x"].shape[0])
         eb = expected_blocks or default_expected_blocks(self.n)
@@ -89,10 +101,17 @@ class MpmSolver:
         api.p2g_transfer(self._pars(), self.table, self.grids, self.dt, self.model, stream)
         self._mark("p2g")
         self.max_vel_sqr.zero_()
-        api.compute_grid_block_velocity(self.grids, self.table, self.dt, self.extf, self.mode, self.max_vel_sqr, stream)
+        self._grid_update(stream)
         self._mark("grid_update")
-        api.g2p_transfer(self._pars(), self.table, self.grids, self.dt, stream)
+        api.g2p_transfer(self._pars(), self.table, self.grids, self.dt, stream, model=self.model)
         self._mark("g2p")
+
+    def _grid_update(self, stream=None):
+        if self.colliders:
+            api.compute_grid_block_velocity_with_boundaries(self.grids, self.table, self.dt, self.extf, self.mode, self.colliders,
+                                                            self.max_vel_sqr, stream)
+        else:
+            api.compute_grid_block_velocity(self.grids, self.table, self.dt, self.extf, self.mode, self.max_vel_sqr, stream)
 
     def rebin(self, stream=None):
         self.partition(stream)
@@ -130,8 +149,8 @@ class MpmSolver:
         api.clean_grid_blocks(self.grids, self.table, stream)
         api.p2g_transfer(a, self.table, self.grids, self.dt, self.model, stream)
         self.max_vel_sqr.zero_()
-        api.compute_grid_block_velocity(self.grids, self.table, self.dt, self.extf, self.mode, self.max_vel_sqr, stream)
-        api.g2p_transfer(a, self.table, self.grids, self.dt, stream)
+        self._grid_update(stream)
+        api.g2p_transfer(a, self.table, self.grids, self.dt, stream, model=self.model)
         for k in ("x", "v", "C", "F"):
             hout[k].copy_(getattr(a, k), non_blocking=True)
         return float(self.max_vel_sqr.item())   # D2H read = sync point
