@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--rebin-every", type=int, default=8)
     ap.add_argument("--partition", default="with_rebin", choices=["with_rebin", "every_step"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-pipelined", type=int, default=0, help="chunks of MpmSolver.substep_host_pipelined (0 = the plain call)")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--p2g-sweep", type=int, default=-1, choices=[-1, 3, 4], help="binned P2G sweep variant (zpcb200_set_tuning)")
@@ -262,17 +263,19 @@ def main():
         hout = {k: torch.empty_like(hin[k]).pin_memory() for k in ("x", "v", "C", "F")}
         bi = sum(hin[k].numel() * 4 for k in hin)
         bo = sum(hout[k].numel() * 4 for k in hout) + 4
-        sol2.substep_host(hin, hout)           # warm-up (allocations, first-touch)
+        host_call = (lambda: sol2.substep_host_pipelined(hin, hout, args.e2e_pipelined)) if args.e2e_pipelined > 0 else (lambda: sol2.substep_host(hin, hout))
+        host_call()                            # warm-up (allocations, first-touch)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            sol2.substep_host(hin, hout)
+            host_call()
             torch.cuda.synchronize()
             for k in ("x", "v", "C", "F"):     # feed the result back like a host-side caller would
                 hin[k], hout[k] = hout[k], hin[k]
         dt = (time.perf_counter() - t0) / args.e2e_steps
         e2e = dict(value=n_total / dt, unit=UNIT, h2d_bytes_per_step=bi, d2h_bytes_per_step=bo, ms_per_step=dt * 1e3,
-                   steps=args.e2e_steps, path="MpmSolver.substep_host (AoS drop-in kernels)")
+                   steps=args.e2e_steps, path=("MpmSolver.substep_host_pipelined, %d chunks" % args.e2e_pipelined if args.e2e_pipelined > 0
+                                                 else "MpmSolver.substep_host") + " (AoS drop-in kernels)")
         del sol2
     elif world > 1:
         e2e = dict(value=None, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0, note="host-buffer call measured at N=1 only")

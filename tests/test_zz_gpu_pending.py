@@ -189,3 +189,26 @@ def test_solver_with_model_and_colliders_matches_oracle(oracle, layout):
         return {k: Q[k][o] for k in "xvCF"}
     check_particles(canon(got), canon(Po), dx, "solver %s, von Mises + colliders" % layout, rtol=5e-5)
     assert (Po["x"][:, 1].min() < 0.25 + dx)          # the cloud reaches the floor region
+
+
+@pytest.mark.parametrize("chunks", [1, 5])
+def test_pipelined_host_call_equals_the_plain_one(chunks):
+    """MpmSolver.substep_host_pipelined (PCIe copies overlapped with chunked P2G / G2P) returns what substep_host returns
+    (the AoS scatter uses unordered float atomics: equal up to fp32 re-association), for two consecutive substeps"""
+    from zpc_b200.solver import MpmSolver
+    P = synth.elastic_cube(9, 32, jitter_F=0.04, jitter_C=0.4, shuffle_seed=6)
+    res = []
+    for pipelined in (False, True):
+        sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="aos")
+        hin = {k: torch.from_numpy(P[k].copy()).pin_memory() for k in ("x", "v", "m", "C", "F")}
+        hout = {k: torch.empty_like(hin[k]).pin_memory() for k in ("x", "v", "C", "F")}
+        mx = []
+        for _ in range(2):
+            mx.append(sol.substep_host_pipelined(hin, hout, chunks) if pipelined else sol.substep_host(hin, hout))
+            torch.cuda.synchronize()
+            for k in ("x", "v", "C", "F"):
+                hin[k], hout[k] = hout[k], hin[k]
+        res.append(({k: hin[k].numpy().copy() for k in "xvCF"}, mx))
+    check_particles(res[1][0], res[0][0], P["dx"], "pipelined host call", rtol=3e-5)
+    assert all(abs(a - b) <= 1e-4 * b for a, b in zip(res[1][1], res[0][1]))
+    assert not np.array_equal(res[0][0]["x"], P["x"])

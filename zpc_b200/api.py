@@ -459,14 +459,32 @@ class Particles:
         self.J = torch.as_tensor(P["J"]).to(device).contiguous() if "J" in P else None   # EquationOfStateConfig only
         self.logJp = torch.as_tensor(P["logJp"]).to(device).contiguous() if "logJp" in P else None  # DruckerPrager / NACC
 
-    def view(self):
-        return zpc_particles_view(self.m.data_ptr(), self.x.data_ptr(), self.v.data_ptr(), None,
-                                  self.J.data_ptr() if self.J is not None else None,
-                                  self.F.data_ptr(), self.C.data_ptr(),
-                                  self.logJp.data_ptr() if self.logJp is not None else None, self.n)
+    def view(self, lo=0, hi=None):
+        """ParticlesView over particles [lo, hi) (default: all) — the attribute arrays are AoS, a range is a pointer offset"""
+        hi = self.n if hi is None else hi
+        if not (0 <= lo <= hi <= self.n):
+            raise ValueError("particle range [%d, %d) outside [0, %d)" % (lo, hi, self.n))
+        def p(t, w):
+            return t.data_ptr() + 4 * w * lo if t is not None else None
+        return zpc_particles_view(p(self.m, 1), p(self.x, 3), p(self.v, 3), None, p(self.J, 1), p(self.F, 9), p(self.C, 9),
+                                  p(self.logJp, 1), hi - lo)
+
+    def range(self, lo, hi):
+        """a non-owning sub-range usable wherever Particles is (p2g_transfer / g2p_transfer on a chunk)"""
+        return _ParticleRange(self, lo, hi)
 
     def to_host(self):
         return {k: getattr(self, k).cpu().numpy() for k in ("x", "v", "m", "C", "F")}
+
+
+class _ParticleRange:
+    def __init__(self, pars, lo, hi):
+        self._p, self._lo, self._hi = pars, int(lo), int(hi)
+        self.n = self._hi - self._lo
+        self.J, self.logJp = pars.J, pars.logJp
+
+    def view(self):
+        return self._p.view(self._lo, self._hi)
 
 
 class ParticleBins:

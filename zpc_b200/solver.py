@@ -155,6 +155,54 @@ class MpmSolver:
             hout[k].copy_(getattr(a, k), non_blocking=True)
         return float(self.max_vel_sqr.item())   # D2H read = sync point
 
+    def substep_host_pipelined(self, hin, hout, chunks=8):
+        """substep_host with the PCIe transfers overlapped with the kernels (same results: the AoS kernels are per-particle).
+        Positions go up first (the partition needs all of them); v, m, C, F follow in `chunks` pieces on a copy stream while
+        the compute stream scatters each piece as it lands; after the grid update every piece is gathered and its x, v, C, F
+        start downloading on a second copy stream while the next piece is gathered.  The floor is one PCIe direction at a
+        time (the download depends on the whole upload through the grid)."""
+        a, n = self.aos, self.n
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        s_in, s_out = self._s_in, self._s_out
+        bounds = [n * c // chunks for c in range(chunks + 1)]
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        ev_in = []
+        with torch.cuda.stream(s_in):
+            a.x.copy_(hin["x"], non_blocking=True)
+            ev_x = torch.cuda.Event()
+            ev_x.record(s_in)
+            for c in range(chunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                for k in ("v", "m", "C", "F"):
+                    getattr(a, k)[lo:hi].copy_(hin[k][lo:hi], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ev_in.append(e)
+        cur.wait_event(ev_x)
+        api.partition_for_particles(api.vec3_port(a.x), n, self.dx, self.table)
+        api.clean_grid_blocks(self.grids, self.table)
+        for c in range(chunks):
+            cur.wait_event(ev_in[c])
+            if bounds[c + 1] > bounds[c]:
+                api.p2g_transfer(a.range(bounds[c], bounds[c + 1]), self.table, self.grids, self.dt, self.model)
+        self.max_vel_sqr.zero_()
+        self._grid_update()
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            if hi > lo:
+                api.g2p_transfer(a.range(lo, hi), self.table, self.grids, self.dt, model=self.model)
+            e = torch.cuda.Event()
+            e.record(cur)
+            s_out.wait_event(e)
+            with torch.cuda.stream(s_out):
+                for k in ("x", "v", "C", "F"):
+                    hout[k][lo:hi].copy_(getattr(a, k)[lo:hi], non_blocking=True)
+        cur.wait_stream(s_out)
+        return float(self.max_vel_sqr.item())   # D2H read on the compute stream = sync point (after the downloads)
+
     def particles_host(self):
         """AoS dict on the host, in the solver's CURRENT particle order."""
         if self.layout == "binned":
