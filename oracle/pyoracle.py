@@ -21,7 +21,7 @@ _i = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 
 
 def build_oracle(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("mpm_oracle.c", "prims_oracle.c", "sparse_oracle.c", "oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("mpm_oracle.c", "prims_oracle.c", "sparse_oracle.c", "bvh_oracle.c", "oracle.h")]
     if (not force and os.path.exists(ORACLE_SO)
             and all(os.path.getmtime(ORACLE_SO) >= os.path.getmtime(s) for s in srcs)):
         return ORACLE_SO
@@ -315,6 +315,38 @@ class Oracle:
             assert m.size == 20
             self.lib.zo_apply_boundary_moving(C.c_int(grid.shape[0]), _ptr(k), _ptr(grid), C.c_float(dx), C.c_int(geom),
                                               C.c_int(ctype), _ptr(a), _ptr(b), _ptr(m))
+
+    # ---- LBvh<3,int,f32> ----
+    def lbvh_build(self, bvs, refit=True):
+        bvs = np.ascontiguousarray(bvs, np.float32).reshape(-1, 6)
+        n = bvs.shape[0]
+        nn = 2 * n - 1 if n > 2 else n
+        out = dict(n=n, orderedBvs=np.zeros((nn, 6), np.float32), auxIndices=np.full(nn, -7, np.int32),
+                   parents=np.full(nn, -7, np.int32), levels=np.full(nn, -7, np.int32), leafInds=np.full(n, -7, np.int32))
+        self.lib.zo_lbvh_build(C.c_int(n), _ptr(bvs), _ptr(out["orderedBvs"]), _ptr(out["auxIndices"]), _ptr(out["parents"]),
+                               _ptr(out["levels"]), _ptr(out["leafInds"]), C.c_int(int(refit)))
+        return out
+
+    def lbvh_refit(self, bvh, bvs):
+        bvs = np.ascontiguousarray(bvs, np.float32).reshape(-1, 6)
+        self.lib.zo_lbvh_refit(C.c_int(bvh["n"]), _ptr(bvs), _ptr(bvh["orderedBvs"]), _ptr(bvh["auxIndices"]), _ptr(bvh["parents"]),
+                               _ptr(bvh["levels"]), _ptr(bvh["leafInds"]))
+
+    def lbvh_whole_box_and_codes(self, bvs):
+        bvs = np.ascontiguousarray(bvs, np.float32).reshape(-1, 6)
+        box = np.empty(6, np.float32)
+        self.lib.zo_lbvh_whole_box(C.c_int(bvs.shape[0]), _ptr(bvs), _ptr(box))
+        self.lib.zo_lbvh_morton.restype = C.c_uint32
+        return box, np.array([self.lib.zo_lbvh_morton(_ptr(box), _ptr(b)) for b in bvs], np.uint32)
+
+    def lbvh_iter_neighbors(self, bvh, bv, cap=4096):
+        bv = np.ascontiguousarray(bv, np.float32)
+        out = np.empty(cap, np.int32)
+        self.lib.zo_lbvh_iter_neighbors.restype = C.c_int
+        c = self.lib.zo_lbvh_iter_neighbors(C.c_int(bvh["n"]), _ptr(bvh["orderedBvs"]), _ptr(bvh["auxIndices"]), _ptr(bvh["levels"]),
+                                            _ptr(bv), _ptr(out), C.c_int(cap))
+        assert c <= cap
+        return out[:c].copy()
 
     def cuboid(self, x, mn, mx):
         x = np.ascontiguousarray(x, np.float32)
@@ -672,6 +704,26 @@ class Ref:
                                     C.c_float(nacc["xi"]), C.c_float(nacc["beta"]), C.c_int(int(nacc["hardeningOn"])),
                                     C.byref(lj), _ptr(F), _ptr(PF))
         return PF, lj.value
+
+    def lbvh_build(self, bvs, refit=True, nthreads=0):
+        bvs = np.ascontiguousarray(bvs, np.float32).reshape(-1, 6)
+        n = bvs.shape[0]
+        nn = 2 * n - 1 if n > 2 else n
+        out = dict(n=n, orderedBvs=np.zeros((nn, 6), np.float32), auxIndices=np.full(nn, -7, np.int32),
+                   parents=np.full(nn, -7, np.int32), levels=np.full(nn, -7, np.int32), leafInds=np.full(n, -7, np.int32))
+        self.lib.zpcref_lbvh_build.restype = C.c_int
+        got = self.lib.zpcref_lbvh_build(C.c_int(nthreads), C.c_int(n), _ptr(bvs), _ptr(out["orderedBvs"]), _ptr(out["auxIndices"]),
+                                         _ptr(out["parents"]), _ptr(out["levels"]), _ptr(out["leafInds"]), C.c_int(int(refit)))
+        assert got == nn
+        return out
+
+    def lbvh_build_then_refit(self, bvs0, bvs1, nthreads=0):
+        a = np.ascontiguousarray(bvs0, np.float32).reshape(-1, 6)
+        b = np.ascontiguousarray(bvs1, np.float32).reshape(-1, 6)
+        n = a.shape[0]
+        out = np.zeros((2 * n - 1 if n > 2 else n, 6), np.float32)
+        self.lib.zpcref_lbvh_build_then_refit(C.c_int(nthreads), C.c_int(n), _ptr(a), _ptr(b), _ptr(out))
+        return out
 
     def math_sqrt(self, x):
         self.lib.zpcref_math_sqrt.restype = C.c_float

@@ -525,3 +525,50 @@ void zpcref_bht_reorder(void *h, const int *map, int scatter) {
   else t.reorder(pol, m, wrapv<false>{});
 }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// LBvh<3, int, f32> (container/Bvh.hpp): the reference's own build / refit on its host policies — pins oracle/bvh_oracle.c
+// ---------------------------------------------------------------------------------------------------------
+#include "zensim/container/Bvh.hpp"
+
+extern "C" {
+/// bvs: n boxes {min[3], max[3]}; outputs sized 2n-1 (n if n <= 2) / n as LBvh lays them out.  Returns numNodes.
+int zpcref_lbvh_build(int nthreads, int n, const float *bvs, float *orderedBvs, int *auxIndices, int *parents, int *levels,
+                      int *leafInds, int refit) {
+  using Bvh = LBvh<3, int, float>;
+  using Box = typename Bvh::Box;
+  static_assert(sizeof(Box) == 6 * sizeof(float), "AABBBox<3,f32> is six floats");
+  Vector<Box> prims{(size_t)n};
+  std::memcpy((void *)prims.data(), bvs, sizeof(float) * 6 * n);
+  Bvh bvh{};
+  with_policy(nthreads, [&](auto &pol, auto) {
+    if (refit)
+      bvh.build(pol, prims, true_c);
+    else
+      bvh.build(pol, prims, false_c);
+  });
+  const int nn = (int)bvh.getNumNodes();
+  std::memcpy(orderedBvs, (const void *)bvh.orderedBvs.data(), sizeof(float) * 6 * nn);
+  std::memcpy(auxIndices, bvh.auxIndices.data(), sizeof(int) * bvh.auxIndices.size());
+  if (n > 2) {
+    std::memcpy(parents, bvh.parents.data(), sizeof(int) * nn);
+    std::memcpy(levels, bvh.levels.data(), sizeof(int) * nn);
+  }
+  std::memcpy(leafInds, bvh.leafInds.data(), sizeof(int) * n);
+  return nn;
+}
+/// build on the first set of boxes, refit with the second (same count), read orderedBvs back
+void zpcref_lbvh_build_then_refit(int nthreads, int n, const float *bvs0, const float *bvs1, float *orderedBvs) {
+  using Bvh = LBvh<3, int, float>;
+  using Box = typename Bvh::Box;
+  Vector<Box> a{(size_t)n}, b{(size_t)n};
+  std::memcpy((void *)a.data(), bvs0, sizeof(float) * 6 * n);
+  std::memcpy((void *)b.data(), bvs1, sizeof(float) * 6 * n);
+  Bvh bvh{};
+  with_policy(nthreads, [&](auto &pol, auto) {
+    bvh.build(pol, a, true_c);
+    bvh.refit(pol, b);
+  });
+  std::memcpy(orderedBvs, (const void *)bvh.orderedBvs.data(), sizeof(float) * 6 * bvh.getNumNodes());
+}
+}
