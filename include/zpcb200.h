@@ -284,6 +284,24 @@ int zpcb200_p2g_apic_eos(zpc_particles_view pars, zpc_hashtable_view table, zpc_
 int zpcb200_g2p_apic_eos(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
                          float dt, zpc_stream_t stream);
 
+/* ---- LBvh<3, int, f32> on the primitives -------------------------------------------------- */
+/* LBvhView / LBvh members (container/Bvh.hpp:173-174, 497-510): boxes are AABBBox<3,f32> = {min[3], max[3]} (six floats);
+ * orderedBvs / auxIndices / parents / levels hold 2n-1 nodes in DFS pre-order (n nodes when n <= 2), leafInds n entries.
+ * auxIndices = primitive id at a leaf, escape index at an internal node; levels = 0 at a leaf, else the length of the chain
+ * of left children below the node. */
+typedef struct zpc_lbvh_view {
+  float *orderedBvs;
+  int *auxIndices, *parents, *levels, *leafInds;
+} zpc_lbvh_view;
+/* LBvh::build(policy, primBvs, wrapv<Refit>) (Bvh.hpp:835-1000): whole box (reduce) -> Morton codes -> radix_sort_pair ->
+ * Karras topology -> exclusive_scan -> DFS layout [-> refit].  Two-phase temp.  numLeaves <= 2^30.  Arrays are
+ * bit-identical to the reference's (the topology is a function of the sorted codes). */
+int zpcb200_lbvh_build(void *temp, size_t *temp_bytes, const float *primBvs, size_t numLeaves, zpc_lbvh_view bvh,
+                       int refit, zpc_stream_t stream);
+/* LBvh::refit (Bvh.hpp:1229-1259): new boxes for the same primitives, same topology. */
+int zpcb200_lbvh_refit(void *temp, size_t *temp_bytes, const float *primBvs, size_t numLeaves, zpc_lbvh_view bvh,
+                       zpc_stream_t stream);
+
 /* ---- SparseGrid<3,f32,8> variant of the path ----------------------------------------------- */
 /* Host helpers mirroring the bht constructor: the three universal hashes it draws from std::mt19937(2)
  * (Bht.hpp:165-169, Bcht.hpp:39-43) and evaluateTableSize (Bht.hpp:154-158). */

@@ -355,6 +355,39 @@ struct ComputeGridBlockVelocity {  // {cuda_c, wrapv<apic>{}, grids, dt, gravity
     return zpcb200_grid_update(grids.view(), table._cnt.data(), dt, extf, mode, maxVel, pol._stream);
   }
 };
+// LBvh<3, int, f32> (container/Bvh.hpp:82-174): build(pol, primBvs, refit) / refit(pol, primBvs); boxes = 6 floats {min, max}
+struct LBvh {
+  size_t _numLeaves{0};
+  Vector<float> orderedBvs;
+  Vector<int> auxIndices, parents, levels, leafInds;
+  size_t getNumLeaves() const { return _numLeaves; }
+  size_t getNumNodes() const { return _numLeaves > 2 ? _numLeaves * 2 - 1 : _numLeaves; }
+  zpc_lbvh_view view() { return zpc_lbvh_view{orderedBvs.data(), auxIndices.data(), parents.data(), levels.data(), leafInds.data()}; }
+  int build(const CudaExecutionPolicy &pol, const Vector<float> &primBvs, bool refit = true) {
+    _numLeaves = primBvs.size() / 6;
+    const size_t nn = getNumNodes();
+    orderedBvs = Vector<float>(6 * nn); auxIndices = Vector<int>(nn); parents = Vector<int>(nn); levels = Vector<int>(nn);
+    leafInds = Vector<int>(_numLeaves);
+    size_t bytes = 0;
+    int rc = zpcb200_lbvh_build(nullptr, &bytes, primBvs.data(), _numLeaves, view(), refit, pol._stream);
+    if (rc) return rc;
+    Vector<char> tmp(bytes);
+    rc = zpcb200_lbvh_build(tmp.data(), &bytes, primBvs.data(), _numLeaves, view(), refit, pol._stream);
+    cudaStreamSynchronize(pol._stream);  // tmp is freed on return
+    return rc;
+  }
+  int refit(const CudaExecutionPolicy &pol, const Vector<float> &primBvs) {
+    if (primBvs.size() / 6 != _numLeaves) throw std::runtime_error("bvh topology changes, require rebuild!");  // Bvh.hpp:1239-1240
+    size_t bytes = 0;
+    int rc = zpcb200_lbvh_refit(nullptr, &bytes, primBvs.data(), _numLeaves, view(), pol._stream);
+    if (rc) return rc;
+    Vector<char> tmp(bytes);
+    rc = zpcb200_lbvh_refit(tmp.data(), &bytes, primBvs.data(), _numLeaves, view(), pol._stream);
+    cudaStreamSynchronize(pol._stream);
+    return rc;
+  }
+};
+
 // Collider{AnalyticLevelSet<Plane | Sphere | Cuboid>, collider_e} with its rigid motion (geometry/Collider.h:10-143,
 // geometry/AnalyticLevelSet.h) and ApplyBoundaryConditionOnGridBlocks{cuda_c, collider, table, grids} (GridOp.hpp:112-164)
 enum class collider_e : int { Sticky = 0, Slip = 1, Separate = 2 };

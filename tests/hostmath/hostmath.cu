@@ -2,6 +2,11 @@
 // for the CPU so that tests without a GPU can compare it with the oracle: a transcription error in a stress model or in
 // the stencil shows up here.  Not linked into libzpcb200.so; nothing in zpc_b200/ uses it.
 #include "../../zpc_b200/csrc/mpm_math.cuh"
+#include "../../zpc_b200/csrc/lbvh_core.cuh"
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
 
 extern "C" {
 void hm_svd3(const float *F, float *U, float *S, float *V) {
@@ -48,5 +53,25 @@ void hm_arena(int n, float dx, const float *x, int *corner, float *local, float 
       for (int k = 0; k < 3; ++k) w[9 * p + 3 * d + k] = a.w[d][k];
     }
   }
+}
+// the per-node functions of the LBvh build (what lbvh.cu's kernels call), run index by index with a host stable sort and scan in
+// place of the device primitives; box = the padded whole box (6 floats).  n > 2.
+void hm_lbvh_build(int n, const float *prims, const float *box, int *auxIndices, int *parents, int *levels, int *leafInds) {
+  const int numTrunk = n - 1;
+  std::vector<unsigned> codes(n), smcs(n);
+  std::vector<int> ids(n), pInds(n), tPars(numTrunk), tRs(numTrunk), tDst(numTrunk), lPars(n), lLcas(n), lDepths(n + 1), lOffsets(n + 1);
+  for (int i = 0; i < n; ++i) { codes[i] = zpcb::morton_of(prims, box, i); ids[i] = i; }
+  std::iota(pInds.begin(), pInds.end(), 0);
+  std::stable_sort(pInds.begin(), pInds.end(), [&](int a, int b) { return codes[a] < codes[b]; });
+  for (int i = 0; i < n; ++i) smcs[i] = codes[pInds[i]];
+  for (int i = 0; i < n; ++i) lDepths[i] = 1;
+  lDepths[n] = 0;
+  for (int idx = numTrunk - 1; idx >= 0; --idx) zpcb::topo_node(idx, smcs.data(), numTrunk, tPars.data(), tRs.data(), lPars.data(), lDepths.data());
+  int run = 0;
+  for (int i = 0; i <= n; ++i) { lOffsets[i] = run; run += lDepths[i]; }
+  for (int idx = n - 1; idx >= 0; --idx)
+    zpcb::supp_topo_leaf(idx, n, lOffsets.data(), lPars.data(), tPars.data(), pInds.data(), tDst.data(), lLcas.data(), levels, auxIndices, leafInds);
+  for (int idx = n - 1; idx >= 0; --idx)
+    zpcb::reorder_node(idx, n, lOffsets.data(), lPars.data(), lLcas.data(), tPars.data(), tRs.data(), tDst.data(), auxIndices, parents);
 }
 }

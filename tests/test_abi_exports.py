@@ -143,6 +143,23 @@ def test_plastic_model_entries_check_their_arguments():
     assert L.zpcb200_p2g_apic_nacc(empty, tv, gv, ctypes.c_float(1e-4), bad, None) == -1
 
 
+def test_lbvh_entries_host_side_behaviour():
+    from zpc_b200 import api
+    L = api.lib()
+    assert ctypes.sizeof(api.zpc_lbvh_view) == 40
+    nb = ctypes.c_size_t(0)
+    v = api.zpc_lbvh_view(None, None, None, None, None)
+    assert L.zpcb200_lbvh_build(None, ctypes.byref(nb), None, ctypes.c_size_t(1 << 20), v, 1, None) == 0
+    assert nb.value > 13 * 4 * (1 << 20)               # nine index arrays, codes and ids twice, flags, plus sort scratch
+    assert L.zpcb200_lbvh_build(None, ctypes.byref(nb), None, ctypes.c_size_t(2), v, 1, None) == 0 and nb.value == 256
+    assert L.zpcb200_lbvh_build(None, ctypes.byref(nb), None, ctypes.c_size_t((1 << 30) + 1), v, 1, None) == -3
+    assert L.zpcb200_lbvh_refit(None, ctypes.byref(nb), None, ctypes.c_size_t(1000), v, None) == 0 and nb.value >= 8000
+    assert L.zpcb200_lbvh_build(None, None, None, ctypes.c_size_t(10), v, 1, None) == -1
+    small = ctypes.c_size_t(16)
+    buf = ctypes.create_string_buffer(16)
+    assert L.zpcb200_lbvh_build(buf, ctypes.byref(small), None, ctypes.c_size_t(1000), v, 1, None) == -2
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "zpc_b200")):
         for f in files:

@@ -212,3 +212,28 @@ def test_pipelined_host_call_equals_the_plain_one(chunks):
     check_particles(res[1][0], res[0][0], P["dx"], "pipelined host call", rtol=3e-5)
     assert all(abs(a - b) <= 1e-4 * b for a, b in zip(res[1][1], res[0][1]))
     assert not np.array_equal(res[0][0]["x"], P["x"])
+
+
+@pytest.mark.parametrize("n,dup,scale", [(0, 0, 1.0), (1, 0, 1.0), (2, 0, 1.0), (3, 0, 1.0), (5, 1, 1.0), (1000, 1, 1.0), (4097, 0, 1.0),
+                                         (3000, 0, 100.0), (300000, 0, 1.0), (300000, 1, 1.0)])
+def test_lbvh_build_and_refit_match_oracle(oracle, n, dup, scale):
+    """zpcb200_lbvh_build / _refit (reduce -> Morton -> radix_sort_pair -> Karras topology -> exclusive_scan -> DFS layout ->
+    bottom-up refit) vs the oracle, which is pinned bit-exact against the reference's LBvh: every array identical"""
+    from tests.test_oracle_lbvh import boxes
+    from zpc_b200 import api
+    rs = np.random.RandomState(n + dup)
+    b = boxes(rs, n, dup, scale) if n else np.zeros((0, 6), np.float32)
+    bvh = api.LBvh().build(torch.from_numpy(b).cuda())
+    torch.cuda.synchronize()
+    if n == 0:
+        return
+    A = oracle.lbvh_build(b)
+    for k in ("auxIndices", "leafInds") + (("parents", "levels") if n > 2 else ()):
+        assert np.array_equal(getattr(bvh, k).cpu().numpy()[: len(A[k])], A[k]), k
+    assert np.array_equal(bvh.orderedBvs.cpu().numpy().view(np.uint32), A["orderedBvs"].view(np.uint32))
+    b1 = (b + rs.uniform(-0.01, 0.01, (n, 1)).astype(np.float32)).astype(np.float32)
+    bvh.refit(torch.from_numpy(b1).cuda())
+    oracle.lbvh_refit(A, b1)
+    assert np.array_equal(bvh.orderedBvs.cpu().numpy().view(np.uint32), A["orderedBvs"].view(np.uint32))
+    with pytest.raises(RuntimeError):
+        bvh.refit(torch.zeros(n + 1, 6, device="cuda"))

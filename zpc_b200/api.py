@@ -81,6 +81,11 @@ class zpc_collider(C.Structure):
                 ("s", C.c_float), ("dsdt", C.c_float)]
 
 
+class zpc_lbvh_view(C.Structure):
+    _fields_ = [("orderedBvs", C.c_void_p), ("auxIndices", C.c_void_p), ("parents", C.c_void_p), ("levels", C.c_void_p),
+                ("leafInds", C.c_void_p)]
+
+
 class zpc_bht_view(C.Structure):
     _fields_ = [("keys", C.c_void_p), ("indices", C.c_void_p), ("status", C.c_void_p), ("activeKeys", C.c_void_p),
                 ("tableSize", C.c_uint32), ("numBuckets", C.c_uint32), ("cnt", C.c_void_p), ("success", C.c_void_p),
@@ -555,6 +560,39 @@ def _two_phase(fn, args_before, args_after, stream, device="cuda"):
     tmp = _scratch.get(nbytes.value, device)
     cap = C.c_size_t(tmp.numel())
     _check(fn(C.c_void_p(tmp.data_ptr()), C.byref(cap), *args_before, *args_after, st), fn.__name__)
+
+
+class LBvh:
+    """LBvh<3, int, f32> (container/Bvh.hpp:82-174): orderedBvs / auxIndices / parents / levels in DFS pre-order, leafInds.
+    build(bvs) / refit(bvs) take a float32 [n, 6] device tensor of boxes {min, max}."""
+
+    def __init__(self, device="cuda"):
+        self.device = device
+        self.n = 0
+        self.orderedBvs = self.auxIndices = self.parents = self.levels = self.leafInds = None
+
+    def num_nodes(self):
+        return 2 * self.n - 1 if self.n > 2 else self.n
+
+    def view(self):
+        return zpc_lbvh_view(*[t.data_ptr() if t is not None else None
+                               for t in (self.orderedBvs, self.auxIndices, self.parents, self.levels, self.leafInds)])
+
+    def build(self, bvs, refit=True, stream=None):
+        assert bvs.dtype == torch.float32 and bvs.is_contiguous() and bvs.shape[-1] == 6
+        self.n = int(bvs.shape[0])
+        nn = max(self.num_nodes(), 1)
+        self.orderedBvs = torch.zeros(nn, 6, dtype=torch.float32, device=self.device)
+        self.auxIndices, self.parents, self.levels = (torch.full((nn,), -7, dtype=torch.int32, device=self.device) for _ in range(3))
+        self.leafInds = torch.full((max(self.n, 1),), -7, dtype=torch.int32, device=self.device)
+        _two_phase(lib().zpcb200_lbvh_build, (C.c_void_p(bvs.data_ptr()), C.c_size_t(self.n), self.view(), C.c_int(int(refit))), (),
+                   stream, self.device)
+        return self
+
+    def refit(self, bvs, stream=None):
+        if int(bvs.shape[0]) != self.n:
+            raise RuntimeError("bvh topology changes, require rebuild!")          # Bvh.hpp:1239-1240
+        _two_phase(lib().zpcb200_lbvh_refit, (C.c_void_p(bvs.data_ptr()), C.c_size_t(self.n), self.view()), (), stream, self.device)
 
 
 # ---- functors as free functions (policy = stream holder; all calls asynchronous) -------------------
