@@ -229,6 +229,17 @@ int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n
                             zpc_hashtable_view table, int enlarge_lo, int enlarge_hi, int *overflow,
                             zpc_stream_t stream);
 
+/* index_buckets_for_particles (simulation/particle/Query.tpp:9-58 = CleanSparsity + ComputeSparsity{blockLen 1, offset 0,
+ * displacement} + SpatiallyCount + exclusive_scan + SpatiallyDistribute, SparsityOp.hpp:41-86, 115-195): `table` becomes the
+ * table of occupied CELLS (floor(x/dx + displacement) per axis; the reference sizes it for n entries), counts / offsets get
+ * n + 1 entries each (the reference allocates table.size() + 1; entries past that stay 0 / n), indices[offsets[b] ..
+ * offsets[b+1]) are the particles of bucket b.  Deterministic where the reference is racy: bucket number = rank of the cell
+ * key, ids inside a bucket ascending (what the reference's serial policy produces).  Cell coordinates in [-512, 511]
+ * (flagged through *overflow otherwise).  n <= 2^30. */
+int zpcb200_index_buckets_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, float displacement,
+                                zpc_hashtable_view table, int *counts, int *offsets, int *indices, int *overflow,
+                                zpc_stream_t stream);
+
 /* CleanGridBlocks (simulation/grid/GridOp.hpp:54-69) over blocks [0, *cnt). */
 int zpcb200_clean_grid(zpc_grids_view grids, const int *cnt, zpc_stream_t stream);
 

@@ -10,6 +10,7 @@
 
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 /* ------------------------------------------------------------------------------------------ */
@@ -99,6 +100,41 @@ int zo_partition_build(int n, const float *x, float dx, int table_size, int *key
           zo_table_insert(k, table_size, keys, indices, active_keys, cnt);
         }
   }
+  return *cnt;
+}
+
+/* index_buckets_for_particles (simulation/particle/Query.tpp:9-58) on the serial policy: a table of the occupied CELLS
+ * (ComputeSparsity with blockLen 1, offset 0 and the given displacement, SparsityOp.hpp:58-86), particles counted per cell
+ * (SpatiallyCount, :115-151), exclusive scan, particle ids scattered (SpatiallyDistribute, :154-195).  counts / offsets
+ * have table.size() + 1 entries.  Serially, the ids of a bucket come out in ascending order. */
+static void cell_of_particle(const float x[3], float dxinv, float displacement, int cell[3]) {
+  for (int d = 0; d < 3; ++d) cell[d] = (int)floorf(x[d] * dxinv + displacement) + 0;   /* lower_trunc(pos * dxinv + displacement) + offset */
+}
+int zo_index_buckets(int n, const float *x, float dx, float displacement, int table_size, int *keys, int *indices_tab,
+                     int *status, int *active_keys, int *cnt, int *counts, int *offsets, int *indices) {
+  const float dxinv = (float)1.0 / dx;
+  zo_table_clear(table_size, keys, indices_tab, status, cnt);
+  for (int p = 0; p < n; ++p) {
+    int c[3];
+    cell_of_particle(x + 3 * p, dxinv, displacement, c);
+    zo_table_insert(c, table_size, keys, indices_tab, active_keys, cnt);
+  }
+  const int numCells = *cnt + 1;
+  int *tmp = (int *)calloc((size_t)numCells, sizeof(int));
+  for (int i = 0; i < numCells; ++i) counts[i] = 0;
+  for (int p = 0; p < n; ++p) {
+    int c[3];
+    cell_of_particle(x + 3 * p, dxinv, displacement, c);
+    counts[zo_table_query(c, table_size, keys, indices_tab)] += 1;
+  }
+  { int run = 0; for (int i = 0; i < numCells; ++i) { offsets[i] = run; run += counts[i]; } }
+  for (int p = 0; p < n; ++p) {
+    int c[3];
+    cell_of_particle(x + 3 * p, dxinv, displacement, c);
+    const int cellno = zo_table_query(c, table_size, keys, indices_tab);
+    indices[offsets[cellno] + tmp[cellno]++] = p;
+  }
+  free(tmp);
   return *cnt;
 }
 

@@ -75,6 +75,19 @@ class Oracle:
         return dict(keys=keys, indices=indices, status=status, active_keys=active[:nb].copy(),
                     nblocks=int(nb), table_size=table_size)
 
+    def index_buckets(self, x, dx, displacement, table_size):
+        """-> dict(table arrays, nbuckets, counts[nb+1], offsets[nb+1], indices[n])"""
+        x = np.ascontiguousarray(x, np.float32)
+        n = x.shape[0]
+        keys = np.empty((table_size, 3), np.int32); idx = np.empty(table_size, np.int32); st = np.empty(table_size, np.int32)
+        ak = np.zeros((table_size, 3), np.int32); cnt = np.zeros(1, np.int32)
+        counts = np.zeros(n + 2, np.int32); offsets = np.zeros(n + 2, np.int32); indices = np.full(max(n, 1), -1, np.int32)
+        self.lib.zo_index_buckets.restype = C.c_int
+        nb = self.lib.zo_index_buckets(C.c_int(n), _ptr(x), C.c_float(dx), C.c_float(displacement), C.c_int(table_size), _ptr(keys),
+                                       _ptr(idx), _ptr(st), _ptr(ak), _ptr(cnt), _ptr(counts), _ptr(offsets), _ptr(indices))
+        return dict(keys=keys, indices=idx, table_size=table_size, nblocks=nb, active_keys=ak[:nb].copy(), counts=counts[:nb + 1].copy(),
+                    offsets=offsets[:nb + 1].copy(), ids=indices[:n].copy())
+
     def table_query(self, key, tab):
         k = np.ascontiguousarray(key, np.int32)
         return int(self.lib.zo_table_query(_ptr(k), C.c_int(tab["table_size"]), _ptr(tab["keys"]),
@@ -704,6 +717,16 @@ class Ref:
                                     C.c_float(nacc["xi"]), C.c_float(nacc["beta"]), C.c_int(int(nacc["hardeningOn"])),
                                     C.byref(lj), _ptr(F), _ptr(PF))
         return PF, lj.value
+
+    def index_buckets(self, x, dx, displacement, nthreads=0):
+        x = np.ascontiguousarray(x, np.float32)
+        n = x.shape[0]
+        ak = np.zeros((n, 3), np.int32); counts = np.zeros(n + 2, np.int32); offsets = np.zeros(n + 2, np.int32)
+        indices = np.full(max(n, 1), -1, np.int32)
+        self.lib.zpcref_index_buckets.restype = C.c_int
+        nb = self.lib.zpcref_index_buckets(C.c_int(nthreads), C.c_int(n), _ptr(x), C.c_float(dx), C.c_float(displacement), _ptr(ak),
+                                           _ptr(counts), _ptr(offsets), _ptr(indices))
+        return dict(nblocks=nb, active_keys=ak[:nb].copy(), counts=counts[:nb + 1].copy(), offsets=offsets[:nb + 1].copy(), ids=indices[:n].copy())
 
     def lbvh_build(self, bvs, refit=True, nthreads=0):
         bvs = np.ascontiguousarray(bvs, np.float32).reshape(-1, 6)

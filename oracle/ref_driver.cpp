@@ -572,3 +572,43 @@ void zpcref_lbvh_build_then_refit(int nthreads, int n, const float *bvs0, const 
   std::memcpy(orderedBvs, (const void *)bvh.orderedBvs.data(), sizeof(float) * 6 * bvh.getNumNodes());
 }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// index_buckets_for_particles (simulation/particle/Query.tpp:9-58): the reference's functors in the reference's order on
+// its host policies.  (Query.tpp itself is only instantiated for GeneralParticles inside the un-built simulator library;
+// the body below is that function's sequence, functor for functor.)
+// ---------------------------------------------------------------------------------------------------------
+#include "zensim/container/IndexBuckets.hpp"
+
+extern "C" {
+int zpcref_index_buckets(int nthreads, int n, const float *x, float dx, float displacement, int *activeKeys, int *counts,
+                         int *offsets, int *indices) {
+  using ib_t = IndexBuckets<3, i32, int>;
+  using vector_t = typename ib_t::vector_t;
+  Vector<vec<float, 3>> pos{(size_t)n};
+  std::memcpy((void *)pos.data(), x, sizeof(float) * 3 * n);
+  ib_t ib{};
+  ib._dx = dx;
+  auto &table = ib._table;
+  table = RM_CVREF_T(table){pos.get_allocator(), (size_t)n};
+  int numCells = 0;
+  with_policy(nthreads, [&](auto &pol, auto tag) {
+    pol(range(table._tableSize), CleanSparsity{tag, table});
+    pol(range(n), ComputeSparsity{tag, dx, 1, table, pos, 0, displacement});
+    numCells = table.size() + 1;
+    ib._counts = vector_t{pos.get_allocator(), (size_t)numCells};
+    std::memset(ib._counts.data(), 0, sizeof(int) * numCells);
+    auto tmp = ib._counts;
+    pol(range(n), SpatiallyCount{tag, dx, table, pos, ib._counts, 1, 0, displacement});
+    ib._offsets = vector_t{pos.get_allocator(), (size_t)numCells};
+    exclusive_scan(pol, ib._counts.begin(), ib._counts.end(), ib._offsets.begin());
+    ib._indices = vector_t{pos.get_allocator(), (size_t)n};
+    pol(range(n), SpatiallyDistribute{tag, dx, table, pos, tmp, ib._offsets, ib._indices, 1, 0, displacement});
+  });
+  std::memcpy(activeKeys, table._activeKeys.data(), sizeof(int) * 3 * (numCells - 1));
+  std::memcpy(counts, ib._counts.data(), sizeof(int) * numCells);
+  std::memcpy(offsets, ib._offsets.data(), sizeof(int) * numCells);
+  std::memcpy(indices, ib._indices.data(), sizeof(int) * n);
+  return numCells - 1;
+}
+}

@@ -160,6 +160,22 @@ def test_lbvh_entries_host_side_behaviour():
     assert L.zpcb200_lbvh_build(buf, ctypes.byref(small), None, ctypes.c_size_t(1000), v, 1, None) == -2
 
 
+def test_index_buckets_entry_host_side_behaviour():
+    from zpc_b200 import api
+    L = api.lib()
+    nb = ctypes.c_size_t(0)
+    none = api.zpc_port(None, 0, 0, 0, 3)
+    tv = api.zpc_hashtable_view(None, None, None, None, 16 * 1024, None)
+    args = (none, ctypes.c_size_t(1000), ctypes.c_float(0.1), ctypes.c_float(0.5), tv, None, None, None, None, None)
+    assert L.zpcb200_index_buckets_build(None, ctypes.byref(nb), *args) == 0 and nb.value > 3 * 4 * 1000
+    buf = ctypes.create_string_buffer(nb.value)
+    assert L.zpcb200_index_buckets_build(buf, ctypes.byref(nb), *args) == -1        # null table arrays are refused before any launch
+    assert L.zpcb200_index_buckets_build(None, None, *args) == -1
+    bad = api.zpc_hashtable_view(None, None, None, None, 0, None)
+    assert L.zpcb200_index_buckets_build(None, ctypes.byref(nb), none, ctypes.c_size_t(10), ctypes.c_float(0.1), ctypes.c_float(0.5), bad,
+                                         None, None, None, None, None) == -1
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "zpc_b200")):
         for f in files:

@@ -237,3 +237,36 @@ def test_lbvh_build_and_refit_match_oracle(oracle, n, dup, scale):
     assert np.array_equal(bvh.orderedBvs.cpu().numpy().view(np.uint32), A["orderedBvs"].view(np.uint32))
     with pytest.raises(RuntimeError):
         bvh.refit(torch.zeros(n + 1, 6, device="cuda"))
+
+
+@pytest.mark.parametrize("disp", [0.5, 0.0])
+@pytest.mark.parametrize("case", [dict(s=12, G=32, shuffle_seed=5), dict(s=6, G=16, origin_cells=-9, shuffle_seed=2), dict(s=1, G=8),
+                                  dict(s=40, G=64, shuffle_seed=1)])
+def test_index_buckets_match_oracle(oracle, case, disp):
+    """zpcb200_index_buckets_build vs the oracle (pinned against the reference's functor sequence): same cell set, and — bucket by
+    bucket through the cell key — the same particle ids in the same (ascending) order; the table resolves through the reference's
+    query; offsets are the exclusive scan of counts"""
+    from zpc_b200 import api
+    kw = dict(case)
+    P = synth.elastic_cube(kw.pop("s"), kw.pop("G"), **kw)
+    x, n, dx = P["x"], P["x"].shape[0], P["dx"]
+    xs = torch.from_numpy(x).cuda()
+    ib = api.index_buckets_for_particles(api.vec3_port(xs), n, dx, disp)
+    torch.cuda.synchronize()
+    assert ib.table.overflow.item() == 0
+    nb = ib.num_buckets()
+    A = oracle.index_buckets(x, dx, disp, oracle.table_size_for(n))
+    assert nb == A["nblocks"]
+    keys = ib.table.active_keys[:nb].cpu().numpy()
+    ko = A["active_keys"]
+    order = np.lexsort((ko[:, 2], ko[:, 1], ko[:, 0]))
+    assert np.array_equal(keys, ko[order])                                    # bucket number = rank of the cell key
+    counts, offsets, ids = ib.counts.cpu().numpy(), ib.offsets.cpu().numpy(), ib.indices.cpu().numpy()
+    assert np.array_equal(counts[:nb], A["counts"][order]) and (counts[nb:] == 0).all()
+    assert np.array_equal(offsets[1:], np.cumsum(counts)[:-1]) and offsets[0] == 0 and offsets[nb] == n
+    for j in range(0, nb, max(nb // 200, 1)):
+        b = order[j]
+        assert np.array_equal(ids[offsets[j]: offsets[j] + counts[j]], A["ids"][A["offsets"][b]: A["offsets"][b] + A["counts"][b]])
+    ht = host_table(ib.table)
+    got = np.array([oracle.table_query(k, ht) for k in keys[:: max(nb // 100, 1)]])
+    assert np.array_equal(got, np.arange(nb)[:: max(nb // 100, 1)])

@@ -562,6 +562,31 @@ def _two_phase(fn, args_before, args_after, stream, device="cuda"):
     _check(fn(C.c_void_p(tmp.data_ptr()), C.byref(cap), *args_before, *args_after, st), fn.__name__)
 
 
+class IndexBuckets:
+    """IndexBuckets<3, i32, int> (container/IndexBuckets.hpp:12-59): _table of occupied cells, _counts / _offsets / _indices."""
+
+    def __init__(self, n, dx, device="cuda", expected_cells=None):
+        self.n, self.dx, self.device = int(n), float(dx), device
+        # Query.tpp:24 sizes the table for pars.size() entries (x16 slots each); pass expected_cells when far fewer are occupied
+        self.table = HashTable(max(int(expected_cells) if expected_cells else self.n, 1), device)
+        self.counts = torch.zeros(self.n + 1, dtype=torch.int32, device=device)
+        self.offsets = torch.zeros(self.n + 1, dtype=torch.int32, device=device)
+        self.indices = torch.full((max(self.n, 1),), -1, dtype=torch.int32, device=device)
+
+    def num_buckets(self):
+        return self.table.size()
+
+
+def index_buckets_for_particles(x_port, n, dx, displacement=0.5, stream=None, device="cuda", expected_cells=None):
+    """index_buckets_for_particles(policy, particles, dx, displacement) (simulation/particle/Query.tpp:9-58)"""
+    ib = IndexBuckets(n, dx, device, expected_cells)
+    _two_phase(lib().zpcb200_index_buckets_build, (x_port, C.c_size_t(n), C.c_float(dx), C.c_float(displacement), ib.table.view(),
+                                                   C.c_void_p(ib.counts.data_ptr()), C.c_void_p(ib.offsets.data_ptr()),
+                                                   C.c_void_p(ib.indices.data_ptr()), C.c_void_p(ib.table.overflow.data_ptr())), (),
+               stream, device)
+    return ib
+
+
 class LBvh:
     """LBvh<3, int, f32> (container/Bvh.hpp:82-174): orderedBvs / auxIndices / parents / levels in DFS pre-order, leafInds.
     build(bvs) / refit(bvs) take a float32 [n, 6] device tensor of boxes {min, max}."""

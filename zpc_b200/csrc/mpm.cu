@@ -49,6 +49,39 @@ __global__ void part_place_kernel(const unsigned *sorted, const int *list_cnt, i
   if (blockIdx.x == 0 && threadIdx.x == 0) *cnt = n;
 }
 
+// ---- index_buckets_for_particles (simulation/particle/Query.tpp:9-58) ------------------------------------------------
+// cell of a particle: ComputeSparsity / SpatiallyCount / SpatiallyDistribute with blockLen 1, offset 0 (SparsityOp.hpp:71-76)
+__device__ __forceinline__ int bucket_cell(float x, float dxinv, float displacement) { return (int)floorf(x * dxinv + displacement); }
+__global__ void bucket_mark_kernel(PortAcc<const float> x, size_t n, float dxinv, float displacement, unsigned *set, unsigned set_mask,
+                                   unsigned *list, int list_cap, int *list_cnt, int *overflow) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+  for (size_t i0 = first; i0 < n; i0 += stride) {  // warp-uniform trip count
+    const size_t i = i0 + (threadIdx.x & 31);
+    unsigned code = CODE_EMPTY;
+    if (i < n && !code_pack(bucket_cell(x.at(i, 0), dxinv, displacement), bucket_cell(x.at(i, 1), dxinv, displacement),
+                            bucket_cell(x.at(i, 2), dxinv, displacement), code)) {
+      code = CODE_EMPTY;
+      if (overflow) *overflow = 1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, code);
+    if (code != CODE_EMPTY && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+      set_insert(code, set, set_mask, list, list_cap, list_cnt, overflow);
+  }
+}
+// key = bucket number of the particle's cell, value = particle id; counts the bucket (SpatiallyCount, SparsityOp.hpp:115-151)
+__global__ void bucket_keys_kernel(PortAcc<const float> x, size_t n, float dxinv, float displacement, zpc_hashtable_view tb, unsigned *keys,
+                                   int *vals, int *counts, int *overflow) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int b = zpcm::table_query(bucket_cell(x.at(i, 0), dxinv, displacement), bucket_cell(x.at(i, 1), dxinv, displacement),
+                            bucket_cell(x.at(i, 2), dxinv, displacement), tb.tableSize, tb.keys, tb.indices);
+  if (b < 0) { if (overflow) *overflow = 1; b = 0; }
+  keys[i] = (unsigned)b;
+  vals[i] = (int)i;
+  atomicAdd(&counts[b], 1);
+}
+
 // Collider::resolveCollision over AnalyticLevelSet<Plane | Sphere | Cuboid> with the default rigid motion (geometry/Collider.h:98-127,
 // geometry/AnalyticLevelSet.h:11-43,130-157): projects the velocity of a node at (px,py,pz) that lies inside the collider
 __device__ __forceinline__ void collide(const zpc_collider &col, float px, float py, float pz, float &vx, float &vy, float &vz) {
@@ -192,6 +225,74 @@ int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n
   part_place_kernel<<<G, 256, 0, s>>>((const unsigned *)(t + L.off_sorted), (const int *)t, L.list_cap, tb.tableSize, tb.keys,
                                        tb.indices, tb.activeKeys, tb.cnt, overflow);
   ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+static int bit_length_u(size_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+
+int zpcb200_index_buckets_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, float displacement,
+                                zpc_hashtable_view tb, int *counts, int *offsets, int *indices, int *overflow, zpc_stream_t stream) {
+  if (!temp_bytes || tb.tableSize <= 0) return ZPCB200_E_BADARG;
+  if (n > ((size_t)1 << 30)) return ZPCB200_E_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  PartScratch L;
+  int rc = part_scratch_layout((size_t)tb.tableSize, L);
+  if (rc) return rc;
+  const int ebit = bit_length_u(n ? n - 1 : 0) > 0 ? bit_length_u(n - 1) : 1;   // bucket numbers are < n
+  size_t sort_bytes = 0, scan_bytes = 0;
+  zpc_port none = {nullptr, 0, 0, 0, 1};
+  rc = zpcb200_radix_sort_pair_u32(nullptr, &sort_bytes, none, none, none, none, n, 0, ebit, nullptr);
+  if (rc) return rc;
+  rc = zpcb200_exclusive_scan_sum_i32(nullptr, &scan_bytes, none, none, n + 1, nullptr);
+  if (rc) return rc;
+  const size_t o_keys = zpc_align_up(L.need, 256), o_vals = zpc_align_up(o_keys + 4 * n, 256), o_skeys = zpc_align_up(o_vals + 4 * n, 256),
+               o_scan = zpc_align_up(o_skeys + 4 * n, 256), o_sort = zpc_align_up(o_scan + scan_bytes, 256), need = o_sort + sort_bytes;
+  if (!temp) { *temp_bytes = need; return ZPCB200_OK; }
+  if (*temp_bytes < need) return ZPCB200_E_TEMP_TOO_SMALL;
+  if (!tb.keys || !tb.indices || !tb.status || !tb.activeKeys || !tb.cnt || !counts || !offsets || (n && (!indices || !x.base))) return ZPCB200_E_BADARG;
+  char *t = (char *)temp;
+  const int G = ZPC_SM_COUNT * 8;
+  // table of the occupied cells: clear -> mark -> sort the cell codes -> place (bucket number = rank of the cell key)
+  part_clear_table_kernel<<<G, 256, 0, s>>>(tb.tableSize, tb.keys, tb.indices, tb.status);
+  ZPC_CHECK_LAUNCH();
+  int *counters = (int *)t;
+  unsigned *set = (unsigned *)(t + L.off_set), *list = (unsigned *)(t + L.off_list), *sorted = (unsigned *)(t + L.off_sorted);
+  part_clear_scratch_kernel<<<G, 256, 0, s>>>(set, (unsigned)L.set_n, list, L.list_cap, counters);
+  ZPC_CHECK_LAUNCH();
+  const float dxinv = 1.0f / dx;
+  if (n) {
+    bucket_mark_kernel<<<G, 256, 0, s>>>(PortAcc<const float>(x), n, dxinv, displacement, set, (unsigned)(L.set_n - 1), list, L.list_cap, counters,
+                                          overflow);
+    ZPC_CHECK_LAUNCH();
+  }
+  {
+    zpc_port pl = {list, 0, 0, 0, 1}, ps = {sorted, 0, 0, 0, 1};
+    size_t sb = L.sort_bytes;
+    rc = zpcb200_radix_sort_u32(t + L.off_sort, &sb, pl, ps, (size_t)L.list_cap, 0, 30, stream);
+    if (rc) return rc;
+  }
+  part_place_kernel<<<G, 256, 0, s>>>(sorted, counters, L.list_cap, tb.tableSize, tb.keys, tb.indices, tb.activeKeys, tb.cnt, overflow);
+  ZPC_CHECK_LAUNCH();
+  // counts (n + 1 entries: buckets beyond table.size() stay 0), offsets = exclusive scan, indices = ids sorted by bucket (stable)
+  ZPC_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), s));
+  unsigned *keys = (unsigned *)(t + o_keys), *skeys = (unsigned *)(t + o_skeys);
+  int *vals = (int *)(t + o_vals);
+  if (n) {
+    bucket_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(PortAcc<const float>(x), n, dxinv, displacement, tb, keys, vals, counts, overflow);
+    ZPC_CHECK_LAUNCH();
+  }
+  {
+    zpc_port pi = {counts, 0, 0, 0, 1}, po = {offsets, 0, 0, 0, 1};
+    size_t sb = scan_bytes;
+    rc = zpcb200_exclusive_scan_sum_i32(t + o_scan, &sb, pi, po, n + 1, stream);
+    if (rc) return rc;
+  }
+  if (n) {
+    zpc_port pk = {keys, 0, 0, 0, 1}, pv = {vals, 0, 0, 0, 1}, psk = {skeys, 0, 0, 0, 1}, psv = {indices, 0, 0, 0, 1};
+    size_t sb = sort_bytes;
+    rc = zpcb200_radix_sort_pair_u32(t + o_sort, &sb, pk, pv, psk, psv, n, 0, ebit, stream);
+    if (rc) return rc;
+  }
   return ZPCB200_OK;
 }
 
