@@ -1,0 +1,108 @@
+"""Host-side control flow of MpmSolver without a GPU: the C ABI is replaced by a recorder that returns 0 (and a size for the
+two-phase queries), tensors live on the CPU.  Checks the order of the functor calls of a substep for every layout / model /
+collider combination, the re-bin cadence and the argument checks — a typo in the Python plumbing fails here, not on the box."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from zpc_b200 import api, synth  # noqa: E402
+from zpc_b200.solver import MpmSolver  # noqa: E402
+
+
+class _Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if not name.startswith("zpcb200_"):
+            raise AttributeError(name)
+
+        def fn(*args):
+            self.calls.append(name)
+            # two-phase entries: (temp, &bytes, ...) with temp == NULL -> report a size
+            if len(args) >= 2 and args[0] is None and hasattr(args[1], "_obj"):
+                args[1]._obj.value = 1024
+            return 0
+        fn.__name__ = name
+        return fn
+
+
+@pytest.fixture
+def recorder(monkeypatch):
+    rec = _Recorder()
+    monkeypatch.setattr(api, "lib", lambda: rec)
+    monkeypatch.setattr(api, "_stream_ptr", lambda stream=None: C.c_void_p(None))
+    class _CpuScratch:
+        def get(self, nbytes, device):
+            return torch.empty(max(int(nbytes), 256), dtype=torch.uint8)
+    monkeypatch.setattr(api, "_scratch", _CpuScratch())
+    monkeypatch.setattr(api, "vec3_port", lambda x: api.zpc_port(x.data_ptr(), 0, 0, 0, 3))      # the real one insists on a CUDA tensor
+    return rec
+
+
+def _names(rec):
+    out = [c.replace("zpcb200_", "") for c in rec.calls]
+    rec.calls.clear()
+    return out
+
+
+def test_binned_substep_sequence_and_rebin_cadence(recorder):
+    P = synth.elastic_cube(4, 16)
+    sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="binned", rebin_every=3, device="cpu", partition="with_rebin")
+    assert _names(recorder) == ["partition_build", "partition_build", "bin_particles", "bin_particles"]     # size query + run, each
+    step = ["clean_grid", "p2g_apic_fcr_binned", "grid_update", "g2p_apic_binned"]
+    for i in range(7):
+        sol.substep()
+        got = _names(recorder)
+        if i in (3, 6):                                   # step_no 3 and 6: partition + re-bin first
+            assert got == ["partition_build"] * 2 + ["rebin_particles"] * 2 + step, (i, got)
+        else:
+            assert got == step, (i, got)
+    sol2 = MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="binned", rebin_every=0, device="cpu", partition="every_step")
+    _names(recorder)
+    sol2.substep()
+    assert _names(recorder) == ["partition_build"] * 2 + step
+
+
+def test_models_and_colliders_pick_the_right_entries(recorder):
+    P = synth.elastic_cube(4, 16)
+    n = P["x"].shape[0]
+    cols = [api.plane_collider((0, 0.1, 0), (0, 1, 0), api.COLLIDER_SEPARATE), api.cuboid_collider((0, 0, 0), (0.1, 0.1, 0.1))]
+    vm = api.model_vonmises(P["volume"])
+    sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="binned", device="cpu", model=vm, colliders=cols)
+    _names(recorder)
+    sol.substep()
+    assert _names(recorder) == ["partition_build"] * 2 + ["clean_grid", "p2g_apic_vonmises_binned", "grid_update_bc", "g2p_apic_binned"]
+    for model, p2g, g2p, extra in ((api.model_drucker_prager(P["volume"]), "p2g_apic_drucker_prager", "g2p_apic", "logJp"),
+                                   (api.model_nacc(P["volume"]), "p2g_apic_nacc", "g2p_apic", "logJp"),
+                                   (api.model_eos(P["volume"]), "p2g_apic_eos", "g2p_apic_eos", "J"),
+                                   (vm, "p2g_apic_vonmises", "g2p_apic", None), (None, "p2g_apic_fcr", "g2p_apic", None)):
+        Q = dict(P)
+        if extra:
+            Q[extra] = np.zeros(n, np.float32)
+        s = MpmSolver(Q, P["dx"], P["volume"], synth.DT, layout="aos", device="cpu", model=model)
+        _names(recorder)
+        s.substep()
+        assert _names(recorder) == ["partition_build"] * 2 + ["clean_grid", p2g, "grid_update", g2p]
+    with pytest.raises(ValueError):                       # J / logJp models have no channel in the binned layout
+        MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="binned", device="cpu", model=api.model_nacc(P["volume"]))
+    with pytest.raises(ValueError):                       # plastic model without logJp
+        s = MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="aos", device="cpu", model=api.model_nacc(P["volume"]))
+        s.substep()
+    with pytest.raises(ValueError):
+        MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="aos", device="cpu", colliders=cols * 3)
+
+
+def test_particle_range_views_are_pointer_offsets():
+    P = synth.elastic_cube(3, 16)
+    P["logJp"] = np.zeros(P["x"].shape[0], np.float32)
+    pars = api.Particles(P, device="cpu")
+    full, part = pars.view(), pars.range(10, 50).view()
+    assert part.count == 40 and full.count == pars.n
+    assert part.X - full.X == 4 * 3 * 10 and part.F - full.F == 4 * 9 * 10 and part.M - full.M == 4 * 10 and part.logJp - full.logJp == 40
+    assert not part.J and not full.J
+    with pytest.raises(ValueError):
+        pars.view(5, pars.n + 1)
