@@ -138,6 +138,32 @@ class MpmSolver:
         self.transfer(stream)
         self.step_no += 1
 
+    # ---- CUDA graph of a whole re-bin cycle (launch-bound sizes: C1 / C2) ----
+    def capture_cycle(self):
+        """Captures the next 2 * rebin_every substeps (two re-bins, so that the ping-pong particle buffers end up in their
+        original roles) into one CUDA graph: ~14 launches per substep become one graph launch per cycle.  Runs eagerly up
+        to a cycle boundary first, so every scratch buffer already has its final size.  Binned layout, partition rebuilt
+        with the re-bin (nothing in that sequence reads back to the host)."""
+        if self.layout != "binned" or self.rebin_every <= 0 or self.partition_mode != "with_rebin":
+            raise ValueError("capture_cycle needs layout='binned', rebin_every > 0 and partition='with_rebin'")
+        k = 2 * self.rebin_every
+        while self.step_no == 0 or self.step_no % k != 0:
+            self.substep()
+        torch.cuda.synchronize()
+        step0, bins0 = self.step_no, self.bins
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            for _ in range(k):
+                self.substep()
+        assert self.bins is bins0                      # two swaps: the graph starts and ends on the same buffer
+        self.step_no, self._graph_len = step0, k       # capturing executed nothing
+        return k
+
+    def replay_cycle(self):
+        """one graph launch = 2 * rebin_every substeps"""
+        self._graph.replay()
+        self.step_no += self._graph_len
+
     def substep_host(self, hin, hout, stream=None):
         """Reference-facing call with HOST buffers (pinned torch tensors x,v,m,C,F in; x,v,C,F out), any particle
         order: upload -> partition -> clean -> P2G -> grid update -> G2P on the reference's AoS layout -> download.
