@@ -309,6 +309,11 @@ typedef struct zpc_lbvh_view {
  * bit-identical to the reference's (the topology is a function of the sorted codes). */
 int zpcb200_lbvh_build(void *temp, size_t *temp_bytes, const float *primBvs, size_t numLeaves, zpc_lbvh_view bvh,
                        int refit, zpc_stream_t stream);
+/* Batched LBvhView::iter_neighbors (Bvh.hpp:660-689, stack-free traversal with escape indices): one query box per thread.
+ * out == NULL: counts[q] = number of primitives whose box overlaps query q.  Otherwise their ids are written to
+ * out[offsets[q] ...] in visiting order — the usual count -> zpcb200_exclusive_scan_sum_i32 -> fill sequence. */
+int zpcb200_lbvh_query(zpc_lbvh_view bvh, size_t numLeaves, const float *queryBvs, size_t numQueries, int *counts,
+                       const int *offsets, int *out, zpc_stream_t stream);
 /* LBvh::refit (Bvh.hpp:1229-1259): new boxes for the same primitives, same topology. */
 int zpcb200_lbvh_refit(void *temp, size_t *temp_bytes, const float *primBvs, size_t numLeaves, zpc_lbvh_view bvh,
                        zpc_stream_t stream);

@@ -14,6 +14,6 @@ def build_hostmath(force=False):
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     # -ffp-contract=off: the host pass must not fuse, like the reference's host build (oracle/Makefile)
-    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-Xcompiler",
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler",
                            "-ffp-contract=off", "-shared", "-o", SO, src])
     return SO

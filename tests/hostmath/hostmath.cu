@@ -74,4 +74,10 @@ void hm_lbvh_build(int n, const float *prims, const float *box, int *auxIndices,
   for (int idx = n - 1; idx >= 0; --idx)
     zpcb::reorder_node(idx, n, lOffsets.data(), lPars.data(), lLcas.data(), tPars.data(), tRs.data(), tDst.data(), auxIndices, parents);
 }
+// zpcb::iter_neighbors on the host: ids of the primitives overlapping bv, in visiting order; returns their number
+int hm_lbvh_iter_neighbors(int n, const float *bvs, const int *auxIndices, const int *levels, const float *bv, int *out, int cap) {
+  int c = 0;
+  zpcb::iter_neighbors(n, bvs, auxIndices, levels, bv, [&](int prim) { if (c < cap) out[c] = prim; ++c; });
+  return c;
+}
 }

@@ -77,3 +77,21 @@ def test_device_lbvh_functions_on_the_host_reproduce_the_oracle(oracle, n, dup):
     hm.hm_lbvh_build(C.c_int(n), p(b), p(box), p(out["auxIndices"]), p(out["parents"]), p(out["levels"]), p(out["leafInds"]))
     for k in KEYS:
         assert np.array_equal(out[k], A[k]), k
+
+
+def test_device_traversal_on_the_host_visits_what_the_oracle_visits(oracle):
+    """zpcb::iter_neighbors (the body of the batched query kernel) on the oracle's tree: same primitive ids, same visiting order"""
+    from tests.hostmath import build_hostmath
+    hm = C.CDLL(build_hostmath())
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    for n in (1, 2, 3, 50, 4000):
+        rs = np.random.RandomState(30 + n)
+        bvs = boxes(rs, n, dup=n > 10)
+        t = oracle.lbvh_build(bvs)
+        lev = t["levels"] if n > 2 else np.zeros(max(n, 1), np.int32)
+        for _ in range(60):
+            qc, qh = rs.uniform(0, 1, 3).astype(np.float32), rs.uniform(0.01, 0.15, 3).astype(np.float32)
+            qb = np.concatenate([qc - qh, qc + qh]).astype(np.float32)
+            out = np.empty(n, np.int32)
+            c = hm.hm_lbvh_iter_neighbors(C.c_int(n), p(t["orderedBvs"]), p(t["auxIndices"]), p(lev), p(qb), p(out), C.c_int(n))
+            assert np.array_equal(out[:c], oracle.lbvh_iter_neighbors(t, qb))

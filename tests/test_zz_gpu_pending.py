@@ -297,3 +297,26 @@ def test_graph_replay_equals_eager_substeps():
         o = np.argsort(Q["m"], kind="stable")
         res.append({k: Q[k][o] for k in "xvCF"})
     check_particles(res[1], res[0], P["dx"], "graph replay vs eager", rtol=5e-5)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5000, 200000])
+def test_lbvh_batched_query_matches_oracle(oracle, n):
+    """zpcb200_lbvh_query (count -> exclusive_scan -> fill): per query the oracle's primitive ids in the oracle's visiting
+    order, i.e. LBvhView::iter_neighbors; checked against brute force as well"""
+    from tests.test_oracle_lbvh import boxes
+    from zpc_b200 import api
+    rs = np.random.RandomState(40 + n)
+    b = boxes(rs, n, dup=n > 10)
+    bvh = api.LBvh().build(torch.from_numpy(b).cuda())
+    nq = 300
+    qc, qh = rs.uniform(0, 1, (nq, 3)).astype(np.float32), rs.uniform(0.005, 0.05, (nq, 3)).astype(np.float32)
+    qb = np.concatenate([qc - qh, qc + qh], 1).astype(np.float32)
+    offsets, ids = bvh.query(torch.from_numpy(qb).cuda())
+    torch.cuda.synchronize()
+    offsets, ids = offsets.cpu().numpy(), ids.cpu().numpy()
+    t = oracle.lbvh_build(b)
+    for q in range(nq):
+        want = oracle.lbvh_iter_neighbors(t, qb[q], cap=max(n, 1))
+        assert np.array_equal(ids[offsets[q]: offsets[q + 1]], want), q
+        brute = np.nonzero(~((qb[q][None, :3] > b[:, 3:]).any(1) | (qb[q][None, 3:] < b[:, :3]).any(1)))[0]
+        assert np.array_equal(np.sort(want), brute)

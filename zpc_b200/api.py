@@ -614,6 +614,22 @@ class LBvh:
                    stream, self.device)
         return self
 
+    def query(self, query_bvs, stream=None):
+        """batched iter_neighbors: returns (offsets[nq + 1], ids) — ids[offsets[q]:offsets[q+1]] overlap query box q"""
+        nq = int(query_bvs.shape[0])
+        counts = torch.zeros(nq + 1, dtype=torch.int32, device=self.device)
+        offsets = torch.zeros(nq + 1, dtype=torch.int32, device=self.device)
+        st = _stream_ptr(stream)
+        q = C.c_void_p(query_bvs.data_ptr())
+        _check(lib().zpcb200_lbvh_query(self.view(), C.c_size_t(self.n), q, C.c_size_t(nq), C.c_void_p(counts.data_ptr()), None, None, st),
+               "lbvh_query(count)")
+        _two_phase(lib().zpcb200_exclusive_scan_sum_i32, (port(counts), port(offsets), C.c_size_t(nq + 1)), (), stream, self.device)
+        total = int(offsets[nq].item())
+        ids = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
+        _check(lib().zpcb200_lbvh_query(self.view(), C.c_size_t(self.n), q, C.c_size_t(nq), None, C.c_void_p(offsets.data_ptr()),
+                                        C.c_void_p(ids.data_ptr()), st), "lbvh_query(fill)")
+        return offsets, ids[:total]
+
     def refit(self, bvs, stream=None):
         if int(bvs.shape[0]) != self.n:
             raise RuntimeError("bvh topology changes, require rebuild!")          # Bvh.hpp:1239-1240

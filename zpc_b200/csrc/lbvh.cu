@@ -14,6 +14,7 @@
 // Results are bit-identical to the reference: the topology is a function of the sorted codes, box merging is min / max.
 // The whole box stays on the device (the reference reads it back to the host, :887).
 #include <cfloat>
+#include <climits>
 
 #include "common.cuh"
 #include "lbvh_core.cuh"
@@ -82,6 +83,26 @@ __global__ void lbvh_refit_kernel(int n, const float *__restrict__ prims, float 
 #pragma unroll
     for (int d = 0; d < 6; ++d) bvs[6 * (size_t)node + d] = out[d];
     node = parents[node];
+  }
+}
+
+// Batched LBvhView::iter_neighbors: one thread per query box.  out == nullptr: counts[q] = number of overlapping primitives;
+// otherwise the primitive ids go to out[offsets[q] ...] in visiting order (count -> exclusive_scan -> fill).
+__global__ void lbvh_query_kernel(int numLeaves, const float *__restrict__ bvs, const int *__restrict__ auxIndices,
+                                  const int *__restrict__ levels, const float *__restrict__ queries, int nq, int *counts,
+                                  const int *__restrict__ offsets, int *out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  float bv[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) bv[d] = queries[6 * (size_t)q + d];
+  int c = 0;
+  if (out) {
+    int *dst = out + offsets[q];
+    zpcb::iter_neighbors(numLeaves, bvs, auxIndices, levels, bv, [&](int prim) { dst[c++] = prim; });
+  } else {
+    zpcb::iter_neighbors(numLeaves, bvs, auxIndices, levels, bv, [&](int) { ++c; });
+    counts[q] = c;
   }
 }
 
@@ -206,5 +227,18 @@ int zpcb200_lbvh_refit(void *temp, size_t *temp_bytes, const float *primBvs, siz
   }
   if (!bvh.auxIndices || !bvh.leafInds || !bvh.parents || !bvh.levels) return ZPCB200_E_BADARG;
   return lbvh_refit_launch(primBvs, (int)numLeaves, bvh, (int *)temp, s);
+}
+
+int zpcb200_lbvh_query(zpc_lbvh_view bvh, size_t numLeaves, const float *queryBvs, size_t numQueries, int *counts, const int *offsets,
+                       int *out, zpc_stream_t stream) {
+  if (numLeaves > ((size_t)1 << 30) || numQueries > (size_t)INT_MAX) return ZPCB200_E_UNSUPPORTED;
+  if (numQueries == 0) return ZPCB200_OK;
+  if (!queryBvs || (!out && !counts) || (out && !offsets)) return ZPCB200_E_BADARG;
+  if (numLeaves && (!bvh.orderedBvs || !bvh.auxIndices || (numLeaves > 2 && !bvh.levels))) return ZPCB200_E_BADARG;
+  lbvh_query_kernel<<<(unsigned)((numQueries + 127) / 128), 128, 0, (cudaStream_t)stream>>>((int)numLeaves, bvh.orderedBvs, bvh.auxIndices,
+                                                                                          bvh.levels, queryBvs, (int)numQueries, counts,
+                                                                                          offsets, out);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
 }
 }

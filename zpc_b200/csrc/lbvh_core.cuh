@@ -135,4 +135,32 @@ ZPC_HD void reorder_node(int idx, int n, const int *lOffsets, const int *lPars, 
   }
 }
 
+// LBvhView::iter_neighbors (Bvh.hpp:660-689): stack-free traversal along the DFS order — `level` nodes of a left chain are
+// consecutive, a miss jumps to the node's escape index.  f(primitive id) for every leaf whose box overlaps bv
+// (overlaps(AABB, AABB), geometry/AnalyticLevelSet.h:262-266).
+ZPC_HD bool boxes_overlap(const float *a, const float *b) {
+  return !(b[0] > a[3] || b[3] < a[0] || b[1] > a[4] || b[4] < a[1] || b[2] > a[5] || b[5] < a[2]);
+}
+template <class F>
+ZPC_HD void iter_neighbors(int numLeaves, const float *bvs, const int *auxIndices, const int *levels, const float *bv, F &&f) {
+  if (numLeaves <= 2) {
+    for (int i = 0; i < numLeaves; ++i)
+      if (boxes_overlap(bvs + 6 * i, bv)) f(i);
+    return;
+  }
+  const int numNodes = 2 * numLeaves - 1;
+  int node = 0;
+  while (node != -1 && node != numNodes) {
+    int level = levels[node];
+    for (; level; --level, ++node)
+      if (!boxes_overlap(bvs + 6 * (size_t)node, bv)) break;
+    if (level == 0) {
+      if (boxes_overlap(bvs + 6 * (size_t)node, bv)) f(auxIndices[node]);
+      node++;
+    } else {
+      node = auxIndices[node];
+    }
+  }
+}
+
 }  // namespace zpcb
