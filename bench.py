@@ -152,6 +152,17 @@ def main():
     workload = "%s: %d particles (%d^3 cells x 8 ppc), %d^3 sparse grid (dx=1/%d), fixed-corotated APIC fp32" % (
         args.config, n_total, s, G, G)
 
+    if args.impl == "reference-cuda":
+        # informational: the reference's own CUDA functors on the same GPU (oracle/_ref/libzpcref_cuda.so, `make -C oracle refcuda`),
+        # in a process of its own.  Not the contract's reference arm (that is the CPU path below).
+        if rank != 0:
+            return 0
+        r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "bench", str(G), str(s), str(max(args.steps, 1)), str(max(args.warmup, 0))],
+                           cwd=ROOT, capture_output=True, text=True)
+        line = r.stdout.strip().splitlines()[-1] if r.returncode == 0 and r.stdout.strip() else json.dumps(
+            dict(impl="reference-cuda", unavailable=(r.stderr.strip().splitlines() or ["failed"])[-1][:200]))
+        print(line)
+        return 0
     if args.impl == "reference":
         if rank != 0:
             return 0

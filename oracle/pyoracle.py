@@ -36,6 +36,17 @@ def build_ref():
     return REF_SO if os.path.exists(REF_SO) else None
 
 
+def build_ref_cuda():
+    """(Re)build oracle/_ref/libzpcref_cuda.so — the reference's own CUDA path, compiled for sm_100 — when /root/reference is
+    mounted and the library is older than its driver; no-op otherwise (it can only RUN on a GPU box)."""
+    so = os.path.join(HERE, "_ref", "libzpcref_cuda.so")
+    srcs = [os.path.join(HERE, f) for f in ("ref_driver_cuda.cu", "Makefile")]
+    if os.path.isdir("/root/reference/include/zensim") and not (
+            os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(f) for f in srcs)):
+        subprocess.check_call(["make", "-s", "-C", HERE, "-j8", "refcuda"])
+    return so if os.path.exists(so) else None
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -1,0 +1,149 @@
+// TEST / BASELINE INFRASTRUCTURE — not product code.
+//
+// The reference's OWN CUDA path of the MPM substep ("pick the CUDA reference as primary for GPU parity"):
+// the unmodified reference headers and its CUDA backend sources, compiled in place from /root/reference by oracle/Makefile
+// (target `refcuda`) for sm_100 into oracle/_ref/libzpcref_cuda.so.  Containers live on memsrc_e::device, functors run on
+// cuda_exec() — CleanSparsity / ComputeSparsity / EnlargeSparsity{0,2}, CleanGridBlocks, P2GTransfer<apic, FixedCorotated>,
+// ComputeGridBlockVelocity (preceded by the "mv += rhs" lambda for the explicit update, like oracle/ref_driver.cpp),
+// G2PTransfer — exactly the composed step of SURVEY §3.1.  Used by tests (parity of libzpcb200.so against the reference's
+// device arithmetic) and by bench.py --impl reference-cuda (informational GPU-vs-GPU baseline).  Needs a GPU to run: the
+// build container can only compile it.
+#include <cstring>
+
+#include "zensim/container/HashTable.hpp"
+#include "zensim/container/Vector.hpp"
+#include "zensim/cuda/execution/ExecutionPolicy.cuh"
+#include "zensim/execution/ExecutionPolicy.hpp"
+#include "zensim/geometry/AnalyticLevelSet.h"
+#include "zensim/geometry/Collider.h"
+#include "zensim/geometry/SparseLevelSet.hpp"
+#include "zensim/geometry/Structure.hpp"
+#include "zensim/geometry/Structurefree.hpp"
+#include "zensim/physics/ConstitutiveModel_Vol_dP.hpp"
+#include "zensim/simulation/grid/GridOp.hpp"
+#include "zensim/simulation/sparsity/SparsityOp.hpp"
+#include "zensim/simulation/transfer/G2P.hpp"
+#include "zensim/simulation/transfer/P2G.hpp"
+
+using namespace zs;
+
+namespace {
+  struct RefMpmCuda {
+    int n;
+    float dx;
+    Particles<f32, 3> pars;
+    HashTable<i32, 3, int> table;
+    Grids<f32, 3, 4> grids;
+    Vector<float> maxVel;
+    int nblocks{0};
+    RefMpmCuda(int n_, float dx_, int expectedBlocks)
+        : n{n_},
+          dx{dx_},
+          pars{(size_t)n_, memsrc_e::device, 0},
+          table{(size_t)expectedBlocks, memsrc_e::device, 0},
+          grids{{{"m", 1}, {"v", 3}, {"rhs", 3}}, dx_, (size_t)expectedBlocks, memsrc_e::device, 0},
+          maxVel{1, memsrc_e::device, 0} {
+      pars.addAttr("m", attrib_e::scalar);
+      pars.addAttr("v", attrib_e::vector);
+      pars.addAttr("F", attrib_e::matrix);
+      pars.addAttr("C", attrib_e::matrix);
+    }
+  };
+  void h2d(void *dst, const void *src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); }
+  void d2h(void *dst, const void *src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); }
+}  // namespace
+
+extern "C" {
+void *zpcrefcuda_mpm_create(int n, float dx, int expectedBlocks) { return new RefMpmCuda{n, dx, expectedBlocks}; }
+void zpcrefcuda_mpm_destroy(void *h) { delete (RefMpmCuda *)h; }
+void zpcrefcuda_mpm_set_particles(void *h, const float *x, const float *v, const float *m, const float *C, const float *F) {
+  auto &s = *(RefMpmCuda *)h;
+  h2d(s.pars.attrVector("x").data(), x, sizeof(float) * 3 * s.n);
+  h2d(s.pars.attrVector("v").data(), v, sizeof(float) * 3 * s.n);
+  h2d(s.pars.attrScalar("m").data(), m, sizeof(float) * s.n);
+  h2d(s.pars.attrMatrix("C").data(), C, sizeof(float) * 9 * s.n);
+  h2d(s.pars.attrMatrix("F").data(), F, sizeof(float) * 9 * s.n);
+}
+void zpcrefcuda_mpm_get_particles(void *h, float *x, float *v, float *C, float *F) {
+  auto &s = *(RefMpmCuda *)h;
+  d2h(x, s.pars.attrVector("x").data(), sizeof(float) * 3 * s.n);
+  d2h(v, s.pars.attrVector("v").data(), sizeof(float) * 3 * s.n);
+  d2h(C, s.pars.attrMatrix("C").data(), sizeof(float) * 9 * s.n);
+  d2h(F, s.pars.attrMatrix("F").data(), sizeof(float) * 9 * s.n);
+}
+/// CleanSparsity, ComputeSparsity, EnlargeSparsity{0,2}; returns table.size() (a device-to-host read, like the reference's app)
+int zpcrefcuda_mpm_partition(void *h) {
+  auto &s = *(RefMpmCuda *)h;
+  auto pol = cuda_exec().device(0);
+  constexpr auto tag = exec_cuda;
+  pol(range(s.table._tableSize), CleanSparsity{tag, s.table});
+  pol(range(s.n), ComputeSparsity{tag, s.dx, 4, s.table, s.pars.attrVector("x")});
+  const int cnt = s.table.size();
+  pol(range(cnt), EnlargeSparsity{tag, s.table, vec<int, 3>{0, 0, 0}, vec<int, 3>{2, 2, 2}});
+  s.nblocks = s.table.size();
+  return s.nblocks;
+}
+void zpcrefcuda_mpm_get_keys(void *h, int *keys) {
+  auto &s = *(RefMpmCuda *)h;
+  d2h(keys, s.table._activeKeys.data(), sizeof(int) * 3 * s.nblocks);
+}
+void zpcrefcuda_mpm_clean_grid(void *h) {
+  auto &s = *(RefMpmCuda *)h;
+  auto pol = cuda_exec().device(0);
+  pol(Collapse{(size_t)s.nblocks, (size_t)64}, CleanGridBlocks{exec_cuda, s.grids});
+}
+void zpcrefcuda_mpm_p2g(void *h, float dt, float E, float nu, float volume) {
+  auto &s = *(RefMpmCuda *)h;
+  FixedCorotatedConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.volume = volume;
+  auto pol = cuda_exec().device(0);
+  pol(range(s.n), P2GTransfer{exec_cuda, wrapv<transfer_scheme_e::apic>{}, dt, model, s.pars, s.table, s.grids});
+}
+/// mode 0: ComputeGridBlockVelocity as shipped; mode 1: "mv += rhs" first (explicit update).  Returns max |v|^2.
+float zpcrefcuda_mpm_grid_update(void *h, float dt, float gravity, int mode) {
+  auto &s = *(RefMpmCuda *)h;
+  s.maxVel.setVal(0.f);
+  auto pol = cuda_exec().device(0);
+  if (mode == 1) {
+    auto gv = proxy<execspace_e::cuda>(s.grids);
+    pol(Collapse{(size_t)s.nblocks, (size_t)64}, [gv] __device__(int b, int c) mutable {
+      auto block = gv[b];
+      for (int d = 0; d != 3; ++d) block(1 + d, c) += block(4 + d, c);
+    });
+  }
+  pol(Collapse{(size_t)s.nblocks, (size_t)64},
+      ComputeGridBlockVelocity{exec_cuda, wrapv<transfer_scheme_e::apic>{}, s.grids, dt, gravity, s.maxVel.data()});
+  return s.maxVel.getVal();
+}
+void zpcrefcuda_mpm_g2p(void *h, float dt) {
+  auto &s = *(RefMpmCuda *)h;
+  FixedCorotatedConfig model{};
+  auto pol = cuda_exec().device(0);
+  pol(range(s.n), G2PTransfer{exec_cuda, wrapv<transfer_scheme_e::apic>{}, dt, model, s.grids, s.table, s.pars});
+}
+void zpcrefcuda_mpm_get_grid(void *h, float *out) {
+  auto &s = *(RefMpmCuda *)h;
+  d2h(out, s.grids.grid(collocated_c).blocks.data(), sizeof(float) * 7 * 64 * s.nblocks);
+}
+void zpcrefcuda_sync() { cudaDeviceSynchronize(); }
+
+/// ---- primitives through the reference's CudaExecutionPolicy (CUB underneath, ExecutionPolicy.cuh:552-866), device pointers ----
+void zpcrefcuda_radix_sort_pair_u32(const unsigned *kin, const int *vin, unsigned *kout, int *vout, size_t n) {
+  auto pol = cuda_exec().device(0);
+  unsigned *ki = const_cast<unsigned *>(kin);
+  int *vi = const_cast<int *>(vin);
+  radix_sort_pair(pol, ki, vi, kout, vout, (std::ptrdiff_t)n, 0, 32);   // all lvalues: KeyIter is deduced from both key arguments
+}
+void zpcrefcuda_exclusive_scan_i32(const int *in, int *out, size_t n) {
+  auto pol = cuda_exec().device(0);
+  int *first = const_cast<int *>(in), *last = first + n;
+  exclusive_scan(pol, first, last, out);
+}
+void zpcrefcuda_reduce_sum_i32(const int *in, int *out, size_t n) {
+  auto pol = cuda_exec().device(0);
+  int *first = const_cast<int *>(in), *last = first + n;
+  reduce(pol, first, last, out, 0);
+}
+}

@@ -1,0 +1,99 @@
+"""TEST / BASELINE INFRASTRUCTURE — NOT PRODUCT CODE.
+
+Runs the reference's OWN CUDA path (oracle/_ref/libzpcref_cuda.so: the unmodified reference headers + CUDA backend compiled by
+`make -C oracle refcuda`) in a process of its own — no torch, no libzpcb200 — so that a fault inside the reference cannot take a
+test session or a bench run down with it.
+
+  python -m oracle.refcuda_runner substep IN.npz OUT.npz   # x v m C F dx dt E nu volume gravity mode -> grids + particles
+  python -m oracle.refcuda_runner bench G S STEPS WARMUP    # elastic cube of S^3 cells in a G^3 domain; prints one JSON line
+  python -m oracle.refcuda_runner prims N                   # radix_sort_pair / exclusive_scan / reduce through CudaExecutionPolicy
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_ref", "libzpcref_cuda.so")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefCuda:
+    def __init__(self):
+        self.L = C.CDLL(SO)
+        self.L.zpcrefcuda_mpm_create.restype = C.c_void_p
+        self.L.zpcrefcuda_mpm_partition.restype = C.c_int
+        self.L.zpcrefcuda_mpm_grid_update.restype = C.c_float
+
+    @staticmethod
+    def available():
+        return os.path.exists(SO)
+
+    def substep(self, P, dt, E, nu, gravity, mode, steps=1, collect=True, expected_blocks=None):
+        n, dx = P["x"].shape[0], float(P["dx"])
+        L = self.L
+        h = C.c_void_p(L.zpcrefcuda_mpm_create(C.c_int(n), C.c_float(dx), C.c_int(expected_blocks or max(n // 8, 64))))
+        L.zpcrefcuda_mpm_set_particles(h, _p(P["x"]), _p(P["v"]), _p(P["m"]), _p(P["C"]), _p(P["F"]))
+        out = {}
+        times = []
+        for _ in range(steps):
+            L.zpcrefcuda_sync()
+            t0 = time.perf_counter()
+            nb = L.zpcrefcuda_mpm_partition(h)
+            L.zpcrefcuda_mpm_clean_grid(h)
+            L.zpcrefcuda_mpm_p2g(h, C.c_float(dt), C.c_float(E), C.c_float(nu), C.c_float(P["volume"]))
+            if collect and steps == 1:
+                keys = np.empty((nb, 3), np.int32); g1 = np.empty((nb, 7, 64), np.float32)
+                L.zpcrefcuda_mpm_get_keys(h, _p(keys)); L.zpcrefcuda_mpm_get_grid(h, _p(g1))
+                out.update(active_keys=keys, grid_p2g=g1)
+            mx = L.zpcrefcuda_mpm_grid_update(h, C.c_float(dt), C.c_float(gravity), C.c_int(mode))
+            if collect and steps == 1:
+                g2 = np.empty((nb, 7, 64), np.float32)
+                L.zpcrefcuda_mpm_get_grid(h, _p(g2))
+                out.update(grid_upd=g2, max_vel_sqr=np.float32(mx), nblocks=nb)
+            L.zpcrefcuda_mpm_g2p(h, C.c_float(dt))
+            L.zpcrefcuda_sync()
+            times.append(time.perf_counter() - t0)
+        if collect:
+            x = np.empty((n, 3), np.float32); v = np.empty((n, 3), np.float32)
+            Cm = np.empty((n, 9), np.float32); F = np.empty((n, 9), np.float32)
+            L.zpcrefcuda_mpm_get_particles(h, _p(x), _p(v), _p(Cm), _p(F))
+            out.update(x=x, v=v, C=Cm, F=F)
+        L.zpcrefcuda_mpm_destroy(h)
+        out["times"] = np.array(times)
+        return out
+
+
+def main(argv):
+    sys.path.insert(0, os.path.dirname(HERE))
+    r = RefCuda()
+    if argv[0] == "substep":
+        z = np.load(argv[1])
+        P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}
+        P["dx"], P["volume"] = float(z["dx"]), float(z["volume"])
+        out = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), int(z["mode"]))
+        np.savez(argv[2], **out)
+    elif argv[0] == "bench":
+        from zpc_b200 import synth
+        G, s, steps, warmup = (int(a) for a in argv[1:5])
+        P = synth.elastic_cube(s, G)
+        n = P["x"].shape[0]
+        out = r.substep(P, synth.DT, synth.MODEL["E"], synth.MODEL["nu"], synth.GRAVITY, 1, steps=steps + warmup, collect=False,
+                        expected_blocks=max(n // 64, 1024))
+        t = out["times"][warmup:]
+        print(json.dumps(dict(impl="reference-cuda", n=n, ms_per_step=float(t.mean() * 1e3), ms_min=float(t.min() * 1e3),
+                              value=n / float(t.mean()), unit="particle-substeps/s", steps=steps, warmup=warmup,
+                              note="the reference's own CUDA functors on cuda_exec(), wall clock around a synchronised substep "
+                                   "(partition + clean + P2G + mv+=rhs + update + G2P), particles resident in HBM")))
+    else:
+        raise SystemExit(__doc__)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

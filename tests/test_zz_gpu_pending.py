@@ -320,3 +320,45 @@ def test_lbvh_batched_query_matches_oracle(oracle, n):
         assert np.array_equal(ids[offsets[q]: offsets[q + 1]], want), q
         brute = np.nonzero(~((qb[q][None, :3] > b[:, 3:]).any(1) | (qb[q][None, 3:] < b[:, :3]).any(1)))[0]
         assert np.array_equal(np.sort(want), brute)
+
+
+def test_against_the_references_own_cuda_path(oracle, tmp_path):
+    """"pick the CUDA reference as primary for GPU parity".  oracle/_ref/libzpcref_cuda.so is the unmodified reference
+    (headers + CUDA backend) compiled for sm_100; it runs one substep in a process of its own (oracle/refcuda_runner.py).  Its
+    grid after P2G / update and its particles after G2P are compared with this library's AoS path on the same input, by block
+    key, and with the host oracle (the reference's device build differs from its host build by ::rsqrtf and FMA contraction:
+    the measured basis of RTOL_STRESS)."""
+    import subprocess
+    import sys
+    from oracle.refcuda_runner import RefCuda
+    from tests.parity import GRID_RTOL
+    from zpc_b200 import api
+    if not RefCuda.available():
+        pytest.skip("oracle/_ref/libzpcref_cuda.so not built (make -C oracle refcuda, where /root/reference is mounted)")
+    P = synth.elastic_cube(8, 32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=11)
+    n, dx = P["x"].shape[0], P["dx"]
+    fin, fout = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(fin, dt=synth.DT, E=E, nu=NU, gravity=synth.GRAVITY, mode=1, **P)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "substep", fin, fout], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    z = np.load(fout)
+    # ours, same input
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(pars, table, grids, synth.DT, api.model_fcr(P["volume"], E, NU))
+    g1 = grids.tiles.cpu().numpy()
+    kr, g1r = grid_by_key(z["active_keys"], z["grid_p2g"])
+    assert int(z["nblocks"]) == ht["nblocks"] and np.array_equal(ht["active_keys"], kr)       # same block set (ours is key-ordered)
+    check_channels(g1, g1r, 1, "P2G vs reference CUDA", GRID_RTOL)
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    _, g2r = grid_by_key(z["active_keys"], z["grid_upd"])
+    check_channels(grids.tiles.cpu().numpy()[:, 1:4], g2r[:, 1:4], 1, "grid update vs reference CUDA", RTOL_STRESS)
+    api.g2p_transfer(pars, table, grids, synth.DT)
+    check_particles(pars.to_host(), {k: z[k] for k in "xvCF"}, dx, "G2P vs reference CUDA", rtol=3e-5)
+    # and the host oracle against the reference's device build: the distance the parity rule allows for
+    o1 = oracle.p2g(P, ht, dx, synth.DT, E, NU, P["volume"])
+    check_channels(o1, g1r, 1, "host oracle vs reference CUDA", GRID_RTOL)
