@@ -272,33 +272,6 @@ def test_index_buckets_match_oracle(oracle, case, disp):
     assert np.array_equal(got, np.arange(nb)[:: max(nb // 100, 1)])
 
 
-def test_graph_replay_equals_eager_substeps():
-    """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same
-    number of eager substeps give (binned P2G adds with unordered shared-memory atomics: equal up to fp32 re-association)"""
-    from zpc_b200.solver import MpmSolver
-    P = synth.elastic_cube(10, 32, jitter_F=0.03, jitter_C=0.3, seed=5)
-    P["v"][:] = P["v"] * 6.0
-    n0 = P["m"].shape[0]
-    P["m"] = (P["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)
-    res = []
-    for graph in (False, True):
-        sol = MpmSolver(P, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, layout="binned", rebin_every=2, partition="with_rebin")
-        if graph:
-            k = sol.capture_cycle()
-            assert k == 4 and sol.step_no == 4
-            sol.replay_cycle()
-            sol.replay_cycle()
-        else:
-            for _ in range(12):
-                sol.substep()
-        torch.cuda.synchronize()
-        assert sol.step_no == 12 and sol.table.overflow.item() == 0
-        Q = sol.particles_host()
-        o = np.argsort(Q["m"], kind="stable")
-        res.append({k: Q[k][o] for k in "xvCF"})
-    check_particles(res[1], res[0], P["dx"], "graph replay vs eager", rtol=5e-5)
-
-
 @pytest.mark.parametrize("n", [1, 2, 3, 5000, 200000])
 def test_lbvh_batched_query_matches_oracle(oracle, n):
     """zpcb200_lbvh_query (count -> exclusive_scan -> fill): per query the oracle's primitive ids in the oracle's visiting
@@ -362,3 +335,31 @@ def test_against_the_references_own_cuda_path(oracle, tmp_path):
     # and the host oracle against the reference's device build: the distance the parity rule allows for
     o1 = oracle.p2g(P, ht, dx, synth.DT, E, NU, P["volume"])
     check_channels(o1, g1r, 1, "host oracle vs reference CUDA", GRID_RTOL)
+
+
+# last: a failed stream capture could leave the process unable to launch — nothing runs after it
+def test_graph_replay_equals_eager_substeps():
+    """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same
+    number of eager substeps give (binned P2G adds with unordered shared-memory atomics: equal up to fp32 re-association)"""
+    from zpc_b200.solver import MpmSolver
+    P = synth.elastic_cube(10, 32, jitter_F=0.03, jitter_C=0.3, seed=5)
+    P["v"][:] = P["v"] * 6.0
+    n0 = P["m"].shape[0]
+    P["m"] = (P["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)
+    res = []
+    for graph in (False, True):
+        sol = MpmSolver(P, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, layout="binned", rebin_every=2, partition="with_rebin")
+        if graph:
+            k = sol.capture_cycle()
+            assert k == 4 and sol.step_no == 4
+            sol.replay_cycle()
+            sol.replay_cycle()
+        else:
+            for _ in range(12):
+                sol.substep()
+        torch.cuda.synchronize()
+        assert sol.step_no == 12 and sol.table.overflow.item() == 0
+        Q = sol.particles_host()
+        o = np.argsort(Q["m"], kind="stable")
+        res.append({k: Q[k][o] for k in "xvCF"})
+    check_particles(res[1], res[0], P["dx"], "graph replay vs eager", rtol=5e-5)
