@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of the next round (run from the repo root through gpurun, one GPU):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash benchmarks/round2_first_call.sh'
+# 1. everything written after round 1's GPU budget was spent: XPASS = green, then drop the xfail marker;
+# 2. the verified suite, unchanged paths;
+# 3. bench line + the opt-in variants that only need a measurement to become defaults;
+# 4. the reference's own CUDA path on the same GPU (informational baseline).
+set -u
+mkdir -p gpurun_out
+python -m pytest tests/test_zz_gpu_pending.py -m gpu -q -rxX --timeout 900 > gpurun_out/r2_pending.log 2>&1
+python -m pytest tests -m gpu -x -q --deselect tests/test_zz_gpu_pending.py > gpurun_out/r2_tests.log 2>&1
+python bench.py --steps 16 --warmup 4 > gpurun_out/r2_bench.log 2>&1
+python bench.py --steps 8 --warmup 4 --no-cpu-baseline --e2e-pipelined 8 > gpurun_out/r2_bench_e2e_pipelined.log 2>&1
+python bench.py --impl reference-cuda --config C2 --steps 5 --warmup 2 > gpurun_out/r2_refcuda_c2.log 2>&1
+python bench.py --impl reference-cuda --config C3 --steps 3 --warmup 1 > gpurun_out/r2_refcuda_c3.log 2>&1
+python bench.py --config C2 --steps 16 --warmup 4 --no-cpu-baseline --e2e-steps 0 > gpurun_out/r2_bench_c2.log 2>&1
+tail -3 gpurun_out/r2_pending.log gpurun_out/r2_tests.log
+cut -c1-400 gpurun_out/r2_bench.log gpurun_out/r2_refcuda_c2.log gpurun_out/r2_refcuda_c3.log

@@ -87,3 +87,35 @@ def test_sparsegrid_host_transform_matches_reference(ref):
         obj.translate([0.5, -1.0, 2.0])
     assert np.allclose(np.array(sg.transform, np.float32), r.transform(), rtol=0, atol=0)
     r.close()
+
+
+def test_shard_by_blocks_cuts_equal_particle_counts_without_splitting_blocks():
+    """sorted block keys, prefix sum of particles per block, contiguous ranges of equal particle counts"""
+    import numpy as np
+    from zpc_b200 import synth
+    from zpc_b200.dist_solver import shard_by_blocks
+    P = synth.elastic_cube(20, 64, shuffle_seed=3)
+    x, dx, n = P["x"], P["dx"], P["x"].shape[0]
+    blk = (np.floor(x / np.float32(dx) + np.float32(0.5)).astype(np.int64) - 2) >> 2
+    for order in ("xmajor", "morton"):
+        for world in (1, 2, 3, 8):
+            owner, cuts, keys = shard_by_blocks(x, dx, world, order)
+            assert owner.shape == (n,) and owner.min() == 0 and owner.max() == world - 1
+            assert cuts[0] == 0 and cuts[-1] == len(keys) and (np.diff(cuts) > 0).all()
+            # no block is split, and the sorted block list is cut into contiguous ranges
+            code = (blk[:, 0] * 1000 + blk[:, 1]) * 1000 + blk[:, 2]
+            for c in np.unique(code)[::7]:
+                assert np.unique(owner[code == c]).size == 1
+            kcode = (keys[:, 0].astype(np.int64) * 1000 + keys[:, 1]) * 1000 + keys[:, 2]
+            assert np.unique(kcode).size == len(keys) == np.unique(code).size
+            for r in range(world):
+                mine = np.unique(code[owner == r])
+                assert set(mine.tolist()) == set(kcode[cuts[r]:cuts[r + 1]].tolist())
+            # balance: within one block's worth of particles (<= 512 at 8 ppc) of n / world
+            per = np.bincount(owner, minlength=world)
+            assert np.abs(per - n / world).max() <= 512, (order, world, per)
+            if order == "xmajor" and world > 1:                   # x-major cuts are slabs: ranks are ordered along x
+                xm = [x[owner == r, 0].mean() for r in range(world)]
+                assert (np.diff(xm) > 0).all()
+    owner, cuts, keys = shard_by_blocks(np.zeros((0, 3), np.float32), dx, 4)
+    assert owner.shape == (0,) and len(keys) == 0

@@ -26,6 +26,45 @@ def pack_keys(keys):
     return (k[:, 0] << 42) | (k[:, 1] << 21) | k[:, 2]
 
 
+def shard_by_blocks(x, dx, world, order="xmajor"):
+    """SURVEY §8(e) partitioning of an arbitrary particle cloud (host side, numpy): home block of every particle (the block
+    ComputeSparsity assigns: floor_div(floor(x/dx + 0.5) - 2, 4), SparsityOp.hpp:68-79), active blocks sorted x-major (or along
+    the Morton curve), exclusive prefix sum of the particles per block, cut into `world` contiguous ranges of (nearly) equal
+    PARTICLE counts.  Returns (owner[n] int32 rank of every particle, cuts[world + 1] block-range boundaries, keys[nb, 3] the
+    sorted block keys).  A block is never split: every particle of a block has the same owner, so the halo of a rank is the
+    one-block ring its stencils reach into."""
+    import numpy as np
+    x = np.asarray(x, np.float32)
+    cell = np.floor(x / np.float32(dx) + np.float32(0.5)).astype(np.int64) - 2
+    blk = cell >> 2                                               # arithmetic shift = floor division by 4
+    lo = blk.min(0) if len(blk) else np.zeros(3, np.int64)
+    rel = blk - lo
+    if order == "morton":
+        def spread(v):                                            # 21 bits -> every third bit
+            v = v.astype(np.uint64) & np.uint64(0x1fffff)
+            v = (v | (v << np.uint64(32))) & np.uint64(0x1f00000000ffff)
+            v = (v | (v << np.uint64(16))) & np.uint64(0x1f0000ff0000ff)
+            v = (v | (v << np.uint64(8))) & np.uint64(0x100f00f00f00f00f)
+            v = (v | (v << np.uint64(4))) & np.uint64(0x10c30c30c30c30c3)
+            v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+            return v
+        code = (spread(rel[:, 0]) << np.uint64(2)) | (spread(rel[:, 1]) << np.uint64(1)) | spread(rel[:, 2])
+    else:
+        ext = rel.max(0) + 1 if len(rel) else np.ones(3, np.int64)
+        code = ((rel[:, 0] * ext[1] + rel[:, 1]) * ext[2] + rel[:, 2]).astype(np.uint64)
+    ucodes, inverse, counts = np.unique(code, return_inverse=True, return_counts=True)
+    first = np.zeros(len(ucodes), np.int64)
+    first[inverse[::-1]] = np.arange(len(code))[::-1]             # any representative particle of each block
+    keys = blk[first].astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(counts)])            # exclusive prefix sum (+ total)
+    n = len(code)
+    # block b goes to the rank whose target range [r n / world, (r + 1) n / world) contains the midpoint of its particles
+    mid = offsets[:-1] + counts / 2.0
+    block_owner = np.minimum((mid * world / max(n, 1)).astype(np.int64), world - 1)
+    cuts = np.searchsorted(block_owner, np.arange(world + 1), side="left")
+    return block_owner[inverse].astype(np.int32), cuts.astype(np.int64), keys
+
+
 class HaloExchange:
     """Host-side plumbing of the one-ring grid-block exchange.  `pack(ids, buf)` / `unpack_add(ids, buf)` move
     the tiles listed in ids between the grid and a contiguous buffer; the CUDA versions call the C ABI
