@@ -1,5 +1,7 @@
 """torchrun --nproc-per-node N tests/dist_check.py : N-GPU sharded substeps against the single-GPU solver on
-the same cloud (rank 0 holds both).  Exit code 0 = parity within the multi-step tolerance."""
+the same cloud (rank 0 holds both).  Exit code 0 = parity within the multi-step tolerance.
+ZPC_MIGRATE=1: after half of the substeps every particle is handed to the rank that owns its current home block
+(DistMpmSolver.migrate; ownership = BlockOwnership over shard_by_blocks of the initial cloud) — results must not change."""
 import os
 import sys
 
@@ -30,7 +32,15 @@ def main():
     P = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
     sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, rebin_every=3,
                         transport=os.environ.get("ZPC_HALO", "auto"))
-    for _ in range(steps):
+    ownership = None
+    if os.environ.get("ZPC_MIGRATE") == "1":
+        from zpc_b200.dist_solver import BlockOwnership, shard_by_blocks
+        _, cuts, keys = shard_by_blocks(full["x"], full["dx"], world)
+        ownership = BlockOwnership(keys, cuts)
+    for i in range(steps):
+        if ownership is not None and i == steps // 2:       # a re-bin boundary (rebin_every = 3, steps = 6)
+            moved = sol.migrate(ownership)
+            print("rank %d: migrated %d particles away, now holds %d" % (rank, moved, sol.n))
         sol.substep()
     torch.cuda.synchronize()
     mine = sol.local.particles_host()

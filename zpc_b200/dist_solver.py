@@ -65,6 +65,65 @@ def shard_by_blocks(x, dx, world, order="xmajor"):
     return block_owner[inverse].astype(np.int32), cuts.astype(np.int64), keys
 
 
+class BlockOwnership:
+    """Which rank owns which block, as a function of the block key alone (so that blocks that become active later have an
+    owner too): the x-major code of the key against the boundary codes of the cuts shard_by_blocks made."""
+
+    def __init__(self, keys, cuts, lo=None, ext=None):
+        import numpy as np
+        keys = np.asarray(keys, np.int64)
+        self.lo = keys.min(0) - 64 if lo is None else np.asarray(lo, np.int64)           # room for the cloud to move
+        self.ext = (keys.max(0) - self.lo + 65) if ext is None else np.asarray(ext, np.int64)
+        codes = self.code(keys)
+        assert (np.diff(codes) > 0).all(), "keys must be the x-major sorted block list of shard_by_blocks"
+        world = len(cuts) - 1
+        # rank r owns the codes in [bounds[r], bounds[r + 1]); first / last rank are open-ended
+        self.bounds = np.array([codes[cuts[r]] if 0 < cuts[r] < len(codes) else (0 if r == 0 else np.iinfo(np.int64).max)
+                                for r in range(1, world)], np.int64)
+        self.world = world
+
+    def code(self, blk):
+        rel = blk - self.lo
+        return (rel[..., 0] * self.ext[1] + rel[..., 1]) * self.ext[2] + rel[..., 2]
+
+    def owner_of_positions(self, x, dx):
+        """x: float32 [n, 3] torch tensor (any device) -> int64 [n] owning rank of every particle's home block"""
+        cell = torch.floor(x / dx + 0.5).to(torch.int64) - 2
+        blk = cell >> 2
+        lo = torch.as_tensor(self.lo, device=x.device)
+        ext = torch.as_tensor(self.ext, device=x.device)
+        rel = blk - lo
+        code = (rel[:, 0] * ext[1] + rel[:, 1]) * ext[2] + rel[:, 2]
+        bounds = torch.as_tensor(self.bounds, device=x.device)
+        return torch.searchsorted(bounds, code, right=True)
+
+
+def migrate_particles(attrs, dest, group=None):
+    """Moves every particle to the rank dest[i] names.  attrs: dict name -> [n, w] (or [n]) float32 tensors on one device;
+    dest: int64 [n].  One all_to_all of the counts, one of the packed records (100 B per particle for x, v, m, C, F: the
+    exchange of SURVEY §8(e)); particles that stay are part of the same exchange (rank -> itself), so the result is simply
+    what arrives, ordered by source rank and, within a source, in the source's order.  Returns the new attrs dict."""
+    world = dist.get_world_size(group)
+    names = list(attrs)
+    widths = [attrs[k].shape[1] if attrs[k].dim() == 2 else 1 for k in names]
+    n = dest.numel()
+    packed = torch.cat([attrs[k].reshape(n, -1) for k in names], dim=1) if n else torch.zeros(0, sum(widths), dtype=torch.float32, device=dest.device)
+    order = torch.argsort(dest, stable=True)
+    send_counts = torch.bincount(dest, minlength=world).to(torch.int64)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    send = packed[order].contiguous()
+    recv = torch.empty(sum(rc), packed.shape[1], dtype=packed.dtype, device=packed.device)
+    dist.all_to_all_single(recv, send, rc, sc, group=group)
+    out, col = {}, 0
+    for k, w in zip(names, widths):
+        t = recv[:, col:col + w].contiguous()
+        out[k] = t if attrs[k].dim() == 2 else t[:, 0].contiguous()
+        col += w
+    return out
+
+
 class HaloExchange:
     """Host-side plumbing of the one-ring grid-block exchange.  `pack(ids, buf)` / `unpack_add(ids, buf)` move
     the tiles listed in ids between the grid and a contiguous buffer; the CUDA versions call the C ABI
@@ -244,6 +303,29 @@ class DistMpmSolver:
     def _rebuild_topology(self):
         nb = self.local.table.size()
         self.halo.build(self.local.table.active_keys[:nb])
+
+    def migrate(self, ownership):
+        """Hands every particle to the rank that owns its current home block (BlockOwnership), then rebuilds the local solver
+        on what arrived: unbin -> all_to_all of 100-byte records -> partition + bin.  Collective; call it at a re-bin
+        boundary, every few hundred substeps — ownership only matters for load balance, never for correctness."""
+        L = self.local
+        if self._cfl_work is not None:
+            self._cfl_work.wait()
+            self._cfl_work = None
+        dev = L.device
+        aos = {k: L.bins.attr(k).clone() for k in ("x", "v", "m", "C", "F")}
+        dest = ownership.owner_of_positions(aos["x"], L.dx)
+        new = migrate_particles(aos, dest, self.group)
+        moved = int((dest != dist.get_rank(self.group)).sum().item())
+        P = {k: v for k, v in new.items()}
+        kw = dict(gravity=L.extf[1], mode=L.mode, layout="binned", rebin_every=L.rebin_every, device=dev, partition="with_rebin",
+                  model=L.model, colliders=L.colliders)
+        step_no = L.step_no
+        self.local = MpmSolver(P, L.dx, L.model.volume, L.dt, **kw)
+        self.local.step_no = step_no
+        self.n, self.table = self.local.n, self.local.table
+        self._rebuild_topology()
+        return moved
 
     def max_vel_sqr(self):
         """global max |v|^2 of the last substep (CFL input); waits for the in-flight all_reduce"""
