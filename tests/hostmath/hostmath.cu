@@ -41,6 +41,10 @@ void hm_cuboid(int n, const float *x, const float *mn, const float *mx, float *s
     zpcm::cuboid_normal(x[3 * p], x[3 * p + 1], x[3 * p + 2], mn, mx, normal[3 * p], normal[3 * p + 1], normal[3 * p + 2]);
   }
 }
+// zpcm::collide at n nodes: positions p[n][3], velocities v[n][3] in/out
+void hm_collide(int n, zpc_collider col, const float *p, float *v) {
+  for (int i = 0; i < n; ++i) zpcm::collide(col, p[3 * i], p[3 * i + 1], p[3 * i + 2], v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+}
 // LocalArena: corner[3], local[3], w[9] per position
 void hm_arena(int n, float dx, const float *x, int *corner, float *local, float *w) {
   for (int p = 0; p < n; ++p) {

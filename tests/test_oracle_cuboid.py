@@ -73,3 +73,41 @@ def test_device_cuboid_functions_on_the_host_are_bit_exact(oracle):
     assert np.array_equal(sdf.view(np.uint32), so.view(np.uint32))
     assert np.array_equal(nm.view(np.uint32), no.view(np.uint32))
     assert (so < 0).sum() > 100 and (so > 0).sum() > 1000
+
+
+def test_device_collide_on_the_host_equals_the_oracle_for_every_collider():
+    """zpcm::collide (the function both boundary kernels call) compiled for the host vs the oracle's
+    ApplyBoundaryConditionOnGridBlocks on a synthetic grid whose every cell is occupied: plane / sphere / cuboid, sticky /
+    slip / separate, static and moving — value for value (the host build does not contract, like the oracle)."""
+    from oracle.pyoracle import Oracle
+    from tests.golden.make_golden import BOUNDARY_CASES
+    from tests.hostmath import build_hostmath
+    from tests.parity import MOVING_COLLIDERS
+    from zpc_b200 import api
+    oracle = Oracle()
+    hm = C.CDLL(build_hostmath())
+    rs = np.random.RandomState(9)
+    dx = np.float32(1.0 / 32)
+    keys = np.array([[bx, by, bz] for bx in range(1, 4) for by in range(1, 4) for bz in range(1, 4)], np.int32)
+    nb = keys.shape[0]
+    grid = np.zeros((nb, 7, 64), np.float32)
+    grid[:, 0] = 1.0                                                    # mass > 0 everywhere
+    grid[:, 1:4] = rs.uniform(-1, 1, (nb, 3, 64)).astype(np.float32)
+    cc = np.array([[(c >> 4) & 3, (c >> 2) & 3, c & 3] for c in range(64)], np.float32)
+    pos = ((keys[:, None, :].astype(np.float32) * np.float32(4.0) + cc[None]) * dx).astype(np.float32).reshape(-1, 3)
+    vel0 = np.ascontiguousarray(grid[:, 1:4].transpose(0, 2, 1).reshape(-1, 3))
+    cases = [(g, t, p0, p1, None) for g, t, p0, p1 in BOUNDARY_CASES] + list(MOVING_COLLIDERS) + list(CUBOID_COLLIDERS)
+    # colliders placed inside this grid's extent (0.125 .. 0.5)
+    for geom, ctype, p0, p1, motion in cases:
+        kw = {}
+        if motion is not None:
+            b, dbdt, R, om, s, dsdt = motion
+            kw = dict(translation=b, velocity=dbdt, rotation=np.asarray(R).tolist(), omega=om, scale=s, dscale_dt=dsdt)
+        col = api._collider(geom, ctype, p0, p1, **kw)
+        want = grid.copy()
+        oracle.apply_boundary(want, keys, float(dx), geom, ctype, p0, p1, motion_vec(motion))
+        v = vel0.copy()
+        hm.hm_collide(C.c_int(v.shape[0]), col, pos.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+        got = v.reshape(nb, 64, 3).transpose(0, 2, 1)
+        assert np.array_equal(got, want[:, 1:4]), (geom, ctype, motion is not None)
+        assert (want[:, 1:4] != grid[:, 1:4]).any(), "collider (%d, %d) touches nothing on this grid" % (geom, ctype)

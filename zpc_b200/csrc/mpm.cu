@@ -82,50 +82,7 @@ __global__ void bucket_keys_kernel(PortAcc<const float> x, size_t n, float dxinv
   atomicAdd(&counts[b], 1);
 }
 
-// Collider::resolveCollision over AnalyticLevelSet<Plane | Sphere | Cuboid> with the default rigid motion (geometry/Collider.h:98-127,
-// geometry/AnalyticLevelSet.h:11-43,130-157): projects the velocity of a node at (px,py,pz) that lies inside the collider
-__device__ __forceinline__ void collide(const zpc_collider &col, float px, float py, float pz, float &vx, float &vy, float &vz) {
-  // material-space position X = R^T (x - b) / s (Collider.h:106-108); products and sums in the reference's order, no contraction
-  // where a sign decides
-  const float xb0 = px - col.b[0], xb1 = py - col.b[1], xb2 = pz - col.b[2];
-  const float inv_s = 1.f / col.s;
-  const float *R = col.R;
-  const float X0 = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], xb0), __fmul_rn(R[3], xb1)), __fmul_rn(R[6], xb2)), inv_s);
-  const float X1 = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[1], xb0), __fmul_rn(R[4], xb1)), __fmul_rn(R[7], xb2)), inv_s);
-  const float X2 = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[2], xb0), __fmul_rn(R[5], xb1)), __fmul_rn(R[8], xb2)), inv_s);
-  const float d0 = X0 - col.origin[0], d1 = X1 - col.origin[1], d2 = X2 - col.origin[2];
-  float m0, m1, m2, dist;  // normal in material space
-  if (col.geometry == ZPC_GEOM_PLANE) {
-    m0 = col.normal[0]; m1 = col.normal[1]; m2 = col.normal[2];
-    dist = __fadd_rn(__fadd_rn(__fmul_rn(m0, d0), __fmul_rn(m1, d1)), __fmul_rn(m2, d2));
-  } else if (col.geometry == ZPC_GEOM_CUBOID) {  // origin = box min, normal = box max (material space)
-    dist = zpcm::cuboid_sdf(X0, X1, X2, col.origin, col.normal);
-    m0 = m1 = m2 = 0.f;
-    if (dist < 0.f && col.type != ZPC_COLLIDER_STICKY) zpcm::cuboid_normal(X0, X1, X2, col.origin, col.normal, m0, m1, m2);
-  } else {
-    const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
-    const float len = sqrtf(l2);
-    dist = len - col.normal[0];
-    const bool tiny = l2 < 1e-7f;
-    m0 = tiny ? 0.f : d0 / len; m1 = tiny ? 0.f : d1 / len; m2 = tiny ? 0.f : d2 / len;
-  }
-  if (dist < 0.f) {
-    // v_object = omega x (x - b) + (ds/dt / s) (x - b) + db/dt (the analytic level sets have no material velocity), :110-111
-    const float k = col.dsdt * inv_s;
-    const float o0 = (col.omega[1] * xb2 - col.omega[2] * xb1) + k * xb0 + col.dbdt[0];
-    const float o1 = (col.omega[2] * xb0 - col.omega[0] * xb2) + k * xb1 + col.dbdt[1];
-    const float o2 = (col.omega[0] * xb1 - col.omega[1] * xb0) + k * xb2 + col.dbdt[2];
-    if (col.type == ZPC_COLLIDER_STICKY) {
-      vx = o0; vy = o1; vz = o2;
-    } else {
-      vx -= o0; vy -= o1; vz -= o2;
-      const float n0 = R[0] * m0 + R[1] * m1 + R[2] * m2, n1 = R[3] * m0 + R[4] * m1 + R[5] * m2, n2 = R[6] * m0 + R[7] * m1 + R[8] * m2;
-      const float proj = __fadd_rn(__fadd_rn(__fmul_rn(n0, vx), __fmul_rn(n1, vy)), __fmul_rn(n2, vz));
-      if (col.type == ZPC_COLLIDER_SLIP || proj < 0.f) { vx -= proj * n0; vy -= proj * n1; vz -= proj * n2; }
-      vx += o0; vy += o1; vz += o2;
-    }
-  }
-}
+using zpcm::collide;  // Collider::resolveCollision over the analytic level sets: mpm_math.cuh (host + device)
 
 // ApplyBoundaryConditionOnGridBlocks with a static analytic collider: one thread per (block, cell)
 __global__ void __launch_bounds__(256) apply_boundary_kernel(float *tiles, const int *__restrict__ active_keys, const int *cnt,

@@ -456,6 +456,51 @@ ZPC_HD void cuboid_normal(float x0, float x1, float x2, const float *mn, const f
   n0 = rn_div(g0, len); n1 = rn_div(g1, len); n2 = rn_div(g2, len);
 }
 
+// Collider::resolveCollision over AnalyticLevelSet<Plane | Sphere | Cuboid> with its rigid motion (geometry/Collider.h:16-24, 98-127,
+// geometry/AnalyticLevelSet.h:11-43,130-157): projects the velocity of a node at (px,py,pz) that lies inside the collider
+ZPC_HD void collide(const zpc_collider &col, float px, float py, float pz, float &vx, float &vy, float &vz) {
+  // material-space position X = R^T (x - b) / s (Collider.h:106-108); products and sums in the reference's order, no contraction
+  // where a sign decides
+  const float xb0 = px - col.b[0], xb1 = py - col.b[1], xb2 = pz - col.b[2];
+  const float inv_s = 1.f / col.s;
+  const float *R = col.R;
+  const float X0 = rn_mul(rn_add(rn_add(rn_mul(R[0], xb0), rn_mul(R[3], xb1)), rn_mul(R[6], xb2)), inv_s);
+  const float X1 = rn_mul(rn_add(rn_add(rn_mul(R[1], xb0), rn_mul(R[4], xb1)), rn_mul(R[7], xb2)), inv_s);
+  const float X2 = rn_mul(rn_add(rn_add(rn_mul(R[2], xb0), rn_mul(R[5], xb1)), rn_mul(R[8], xb2)), inv_s);
+  const float d0 = X0 - col.origin[0], d1 = X1 - col.origin[1], d2 = X2 - col.origin[2];
+  float m0, m1, m2, dist;  // normal in material space
+  if (col.geometry == ZPC_GEOM_PLANE) {
+    m0 = col.normal[0]; m1 = col.normal[1]; m2 = col.normal[2];
+    dist = rn_add(rn_add(rn_mul(m0, d0), rn_mul(m1, d1)), rn_mul(m2, d2));
+  } else if (col.geometry == ZPC_GEOM_CUBOID) {  // origin = box min, normal = box max (material space)
+    dist = cuboid_sdf(X0, X1, X2, col.origin, col.normal);
+    m0 = m1 = m2 = 0.f;
+    if (dist < 0.f && col.type != ZPC_COLLIDER_STICKY) cuboid_normal(X0, X1, X2, col.origin, col.normal, m0, m1, m2);
+  } else {
+    const float l2 = rn_add(rn_add(rn_mul(d0, d0), rn_mul(d1, d1)), rn_mul(d2, d2));
+    const float len = sqrtf(l2);
+    dist = len - col.normal[0];
+    const bool tiny = l2 < 1e-7f;
+    m0 = tiny ? 0.f : d0 / len; m1 = tiny ? 0.f : d1 / len; m2 = tiny ? 0.f : d2 / len;
+  }
+  if (dist < 0.f) {
+    // v_object = omega x (x - b) + (ds/dt / s) (x - b) + db/dt (the analytic level sets have no material velocity), :110-111
+    const float k = col.dsdt * inv_s;
+    const float o0 = (col.omega[1] * xb2 - col.omega[2] * xb1) + k * xb0 + col.dbdt[0];
+    const float o1 = (col.omega[2] * xb0 - col.omega[0] * xb2) + k * xb1 + col.dbdt[1];
+    const float o2 = (col.omega[0] * xb1 - col.omega[1] * xb0) + k * xb2 + col.dbdt[2];
+    if (col.type == ZPC_COLLIDER_STICKY) {
+      vx = o0; vy = o1; vz = o2;
+    } else {
+      vx -= o0; vy -= o1; vz -= o2;
+      const float n0 = R[0] * m0 + R[1] * m1 + R[2] * m2, n1 = R[3] * m0 + R[4] * m1 + R[5] * m2, n2 = R[6] * m0 + R[7] * m1 + R[8] * m2;
+      const float proj = rn_add(rn_add(rn_mul(n0, vx), rn_mul(n1, vy)), rn_mul(n2, vz));
+      if (col.type == ZPC_COLLIDER_SLIP || proj < 0.f) { vx -= proj * n0; vy -= proj * n1; vz -= proj * n2; }
+      vx += o0; vy += o1; vz += o2;
+    }
+  }
+}
+
 // LocalArena::init (simulation/Utils.hpp:51-70): base node, in-cell offset (scaled by dx), 3x3 weights
 struct Arena {
   int corner[3];
