@@ -3,6 +3,7 @@
 // the stencil shows up here.  Not linked into libzpcb200.so; nothing in zpc_b200/ uses it.
 #include "../../zpc_b200/csrc/mpm_math.cuh"
 #include "../../zpc_b200/csrc/lbvh_core.cuh"
+#include "../../zpc_b200/csrc/mpm_kernels.cuh"
 
 #include <algorithm>
 #include <numeric>
@@ -83,5 +84,37 @@ int hm_lbvh_iter_neighbors(int n, const float *bvs, const int *auxIndices, const
   int c = 0;
   zpcb::iter_neighbors(n, bvs, auxIndices, levels, bv, [&](int prim) { if (c < cap) out[c] = prim; ++c; });
   return c;
+}
+// The AoS P2G / G2P of the product, particle by particle on the host: the same zpcp::p2g_scatter_* / g2p_aos_particle the kernels
+// call (mpm_particle.cuh, mpm_kernels.cuh), against the legacy hash table.  model: 0 fixed-corotated, 1 von Mises {yield},
+// 2 Drucker-Prager {cohesion, beta, yieldSurface, volumeCorrection}, 3 NACC {bulk, xi, beta, Msqr, hardeningOn},
+// 4 equation of state {bulk, viscosity}.
+void hm_p2g_aos(int model, zpc_particles_view P, zpc_hashtable_view tb, float *tiles, float dx, float dt, float volume, float mu,
+                float lam, const float *prm) {
+  const zpcp::LegacyGrid g{tb};
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  for (size_t p = 0; p < P.count; ++p) {
+    float pos[3], vel[3], C[9], F[9], contrib[9];
+    for (int d = 0; d < 3; ++d) { pos[d] = P.X[3 * p + d]; vel[d] = P.V[3 * p + d]; }
+    for (int d = 0; d < 9; ++d) { C[d] = P.C[9 * p + d]; F[d] = P.F ? P.F[9 * p + d] : 0.f; }
+    if (model == 0) zpcp::p2g_scatter_particle(pos, vel, P.M[p], C, F, g, tiles, 7, dx, dt, volume, mu, lam);
+    else if (model == 1) zpcp::p2g_scatter_particle_vm(pos, vel, P.M[p], C, F, g, tiles, 7, dx, dt, volume, mu, lam, prm[0]);
+    else if (model == 4) zpcp::p2g_scatter_particle_eos(pos, vel, P.M[p], C, P.J[p], g, tiles, 7, dx, dt, volume, prm[0], prm[1]);
+    else {  // the body of p2g_aos_plastic_kernel
+      float logJp = P.logJp[p];
+      if (model == 2) zpcm::stress_sand(volume, mu, lam, prm[0], prm[1], prm[2], prm[3] != 0.f, logJp, F, contrib);
+      else zpcm::stress_nacc(volume, mu, prm[0], prm[1], prm[2], prm[3], prm[4] != 0.f, logJp, F, contrib);
+      P.logJp[p] = logJp;
+      for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+      zpcp::p2g_scatter_core(pos, vel, P.M[p], C, contrib, g, tiles, 7, dx);
+    }
+  }
+}
+void hm_g2p_aos(int eos, zpc_particles_view P, zpc_hashtable_view tb, const float *tiles, float dx, float dt) {
+  const zpcp::LegacyGrid g{tb};
+  for (size_t p = 0; p < P.count; ++p) {
+    if (eos) g2p_aos_particle<true>(P, p, g, tiles, 7, dx, dt);
+    else g2p_aos_particle<false>(P, p, g, tiles, 7, dx, dt);
+  }
 }
 }

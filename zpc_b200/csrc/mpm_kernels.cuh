@@ -120,11 +120,9 @@ __global__ void __launch_bounds__(128) p2g_aos_plastic_kernel(zpc_particles_view
   zpcp::p2g_scatter_core(pos, vel, P.M[p], C, contrib, tb, tiles, nch, dx);
 }
 
+// G2PTransfer<apic> for particle p (G2P.hpp:43-84), F or J variant — one function for the kernel and for tests/hostmath
 template <bool EOS, class GA>
-__global__ void __launch_bounds__(128) g2p_aos_kernel(zpc_particles_view P, GA tb, const float *tiles,
-                                                      int nch, float dx, float dt) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P.count) return;
+ZPC_HD void g2p_aos_particle(const zpc_particles_view &P, size_t p, GA tb, const float *tiles, int nch, float dx, float dt) {
   const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
   float pos[3], vel[3] = {0.f, 0.f, 0.f}, C[9];
 #pragma unroll
@@ -149,7 +147,7 @@ __global__ void __launch_bounds__(128) g2p_aos_kernel(zpc_particles_view P, GA t
         const float *t = tiles + off + zpcp::cell_offset<GA>(lx, ly, lz);
         const float xixp[3] = {(float)i * dx - ar.local[0], (float)j * dx - ar.local[1], (float)k * dx - ar.local[2]};
         const float W = ar.w[0][i] * ar.w[1][j] * ar.w[2][k];
-        const float vi[3] = {__ldg(t + CS), __ldg(t + 2 * CS), __ldg(t + 3 * CS)};
+        const float vi[3] = {zpcm::grid_load(t + CS), zpcm::grid_load(t + 2 * CS), zpcm::grid_load(t + 3 * CS)};
 #pragma unroll
         for (int d = 0; d < 3; ++d) vel[d] += vi[d] * W;
 #pragma unroll
@@ -172,6 +170,14 @@ __global__ void __launch_bounds__(128) g2p_aos_kernel(zpc_particles_view P, GA t
   for (int d = 0; d < 3; ++d) { P.X[3 * p + d] = pos[d]; P.V[3 * p + d] = vel[d]; }
 #pragma unroll
   for (int d = 0; d < 9; ++d) P.C[9 * p + d] = C[d];
+}
+
+template <bool EOS, class GA>
+__global__ void __launch_bounds__(128) g2p_aos_kernel(zpc_particles_view P, GA tb, const float *tiles,
+                                                      int nch, float dx, float dt) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.count) return;
+  g2p_aos_particle<EOS>(P, p, tb, tiles, nch, dx, dt);
 }
 
 }  // namespace

@@ -29,6 +29,22 @@ ZPC_HD float bits_to_float(unsigned u) {
 #endif
 }
 
+// float add to the grid: a RED on the device; the host build (tests/hostmath) runs one particle at a time
+ZPC_HD void grid_add(float *p, float v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+ZPC_HD float grid_load(const float *p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 template <int AXIS>
 ZPC_HD void jacobi_step(float &pp, float &qq, float &off, float &rr, float &a, float &b,
                                             float (&q)[4]) {
@@ -525,12 +541,12 @@ ZPC_HD void arena_init(Arena &a, float dx, const float (&pos)[3]) {
 }
 
 // home block of a particle as ComputeSparsity assigns it (SparsityOp.hpp:68-79): floor_div(floor(x/dx+.5)-2, 4)
-__device__ __forceinline__ int sparsity_coord(float x, float dxinv) { return (int)floorf(x * dxinv + 0.5f) - 2; }
-__device__ __forceinline__ int floor_div4(int c) { return c >> 2; }  // arithmetic shift == floor division by 4
+ZPC_HD int sparsity_coord(float x, float dxinv) { return (int)floorf(x * dxinv + 0.5f) - 2; }
+ZPC_HD int floor_div4(int c) { return c >> 2; }  // arithmetic shift == floor division by 4
 
 // ---- legacy hash table lookups (container/HashTable.hpp) -----------------------------------------
 // do_hash (:496-500) + 64-bit hash_combine (math/Hash.hpp:17-27), then "(h % size + size) % size" (:358)
-__device__ __forceinline__ int hash_slot0(int kx, int ky, int kz, int table_size) {
+ZPC_HD int hash_slot0(int kx, int ky, int kz, int table_size) {
   unsigned long long seed = (unsigned long long)(long long)kx;
   seed ^= ((unsigned long long)(long long)ky + 0x9e3779b97f4a7c15ULL + (seed << 12) + (seed >> 4));
   seed ^= ((unsigned long long)(long long)kz + 0x9e3779b97f4a7c15ULL + (seed << 12) + (seed >> 4));
@@ -538,7 +554,7 @@ __device__ __forceinline__ int hash_slot0(int kx, int ky, int kz, int table_size
   return (e % table_size + table_size) % table_size;
 }
 // HashTableView::query (:447-456) along insert's probe sequence (:386)
-__device__ __forceinline__ int table_query(int kx, int ky, int kz, int table_size, const int *__restrict__ keys,
+ZPC_HD int table_query(int kx, int ky, int kz, int table_size, const int *__restrict__ keys,
                                            const int *__restrict__ indices) {
   int slot = hash_slot0(kx, ky, kz, table_size);
   while (true) {
@@ -553,7 +569,7 @@ __device__ __forceinline__ int table_query(int kx, int ky, int kz, int table_siz
 // ---- bht<i32,3,int,16> lookups (container/Bht.hpp) -------------------------------------------------
 // universal_hash over a vec3i key (py_interop/HashUtils.hpp:22-43): sub(k) = ((hashx ^ k) + hashy) % 4294967291 in
 // 32-bit unsigned arithmetic, combined with the 32-bit hash_combine
-__host__ __device__ __forceinline__ unsigned bht_hash(unsigned hx, unsigned hy, int kx, int ky, int kz) {
+ZPC_HD unsigned bht_hash(unsigned hx, unsigned hy, int kx, int ky, int kz) {
   const unsigned P = 4294967291u;
   unsigned h = ((hx ^ (unsigned)kx) + hy) % P;
   h ^= (((hx ^ (unsigned)ky) + hy) % P) + 0x9e3779b9u + (h << 6) + (h >> 2);
@@ -561,7 +577,7 @@ __host__ __device__ __forceinline__ unsigned bht_hash(unsigned hx, unsigned hy, 
   return h;
 }
 // BHTView::query (Bht.hpp:666-700): the 16 slots of the hf0 bucket, then hf1's, then hf2's
-__device__ __forceinline__ int bht_query(int kx, int ky, int kz, const zpc_bht_view &tb) {
+ZPC_HD int bht_query(int kx, int ky, int kz, const zpc_bht_view &tb) {
   if (tb.numBuckets == 0) return -1;
 #pragma unroll 1
   for (int it = 0; it < 3; ++it) {

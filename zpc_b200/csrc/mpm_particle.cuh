@@ -14,23 +14,23 @@ namespace zpcp {
 struct LegacyGrid {
   static constexpr int S = 2;
   zpc_hashtable_view tb;
-  __device__ __forceinline__ int query(int bx, int by, int bz) const {
+  ZPC_HD int query(int bx, int by, int bz) const {
     return zpcm::table_query(bx, by, bz, tb.tableSize, tb.keys, tb.indices);
   }
 };
 struct SparseGrid8 {
   static constexpr int S = 3;
   zpc_bht_view tb;
-  __device__ __forceinline__ int query(int bx, int by, int bz) const { return zpcm::bht_query(bx << 3, by << 3, bz << 3, tb); }
+  ZPC_HD int query(int bx, int by, int bz) const { return zpcm::bht_query(bx << 3, by << 3, bz << 3, tb); }
 };
-template <class G> __device__ __forceinline__ int cell_offset(int lx, int ly, int lz) {
+template <class G> ZPC_HD int cell_offset(int lx, int ly, int lz) {
   constexpr int M = (1 << G::S) - 1;
   return ((lx & M) << (2 * G::S)) | ((ly & M) << G::S) | (lz & M);
 }
 
 // tile offsets (in floats) of the 2x2x2 blocks around the stencil; -1 where not needed / absent
 template <class G>
-__device__ __forceinline__ void resolve_blocks(const int (&corner)[3], const G &g, int nch, long long (&off)[8]) {
+ZPC_HD void resolve_blocks(const int (&corner)[3], const G &g, int nch, long long (&off)[8]) {
   constexpr int S = G::S, M = (1 << S) - 1;
   const int b0x = corner[0] >> S, b0y = corner[1] >> S, b0z = corner[2] >> S;
   const bool nx = (corner[0] & M) >= M - 1, ny = (corner[1] & M) >= M - 1, nz = (corner[2] & M) >= M - 1;  // stencil spills over
@@ -46,7 +46,7 @@ __device__ __forceinline__ void resolve_blocks(const int (&corner)[3], const G &
 
 // scatter of one particle given its (already scaled: * -dt * D_inv) stress contribution — P2G.hpp:104-125
 template <class G>
-static __device__ __noinline__ void p2g_scatter_core(const float (&pos)[3], const float (&vel)[3], float mass, const float (&C)[9],
+static __host__ __device__ __noinline__ void p2g_scatter_core(const float (&pos)[3], const float (&vel)[3], float mass, const float (&C)[9],
                                                      const float (&contrib)[9], const G &tb, float *tiles, int nch,
                                                      float dx) {
   constexpr int S = G::S, M = (1 << S) - 1, CS = 1 << (3 * S);  // CS = cells per block = channel stride
@@ -67,19 +67,19 @@ static __device__ __noinline__ void p2g_scatter_core(const float (&pos)[3], cons
         float *t = tiles + o + cell_offset<G>(lx, ly, lz);
         const float x0 = (float)i * dx - ar.local[0], x1 = (float)j * dx - ar.local[1], x2 = (float)k * dx - ar.local[2];
         const float W = ar.w[0][i] * ar.w[1][j] * ar.w[2][k];
-        atomicAdd(t, mass * W);
+        zpcm::grid_add(t, mass * W);
         const float Wm = W * mass;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          atomicAdd(t + (1 + d) * CS, Wm * (vel[d] + (C[d] * x0 + C[3 + d] * x1 + C[6 + d] * x2)));
-          atomicAdd(t + (4 + d) * CS, (contrib[d] * x0 + contrib[3 + d] * x1 + contrib[6 + d] * x2) * W);
+          zpcm::grid_add(t + (1 + d) * CS, Wm * (vel[d] + (C[d] * x0 + C[3 + d] * x1 + C[6 + d] * x2)));
+          zpcm::grid_add(t + (4 + d) * CS, (contrib[d] * x0 + contrib[3 + d] * x1 + contrib[6 + d] * x2) * W);
         }
       }
 }
 
 // FixedCorotatedConfig (P2G.hpp:88-91)
 template <class G>
-static __device__ __forceinline__ void p2g_scatter_particle(const float (&pos)[3], const float (&vel)[3], float mass, const float (&C)[9],
+static ZPC_HD void p2g_scatter_particle(const float (&pos)[3], const float (&vel)[3], float mass, const float (&C)[9],
                                                   const float (&F)[9], const G &tb, float *tiles, int nch,
                                                   float dx, float dt, float volume, float mu, float lam) {
   const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
@@ -92,7 +92,7 @@ static __device__ __forceinline__ void p2g_scatter_particle(const float (&pos)[3
 
 // VonMisesFixedCorotatedConfig (P2G.hpp:89-90)
 template <class G>
-static __device__ __forceinline__ void p2g_scatter_particle_vm(const float (&pos)[3], const float (&vel)[3], float mass,
+static ZPC_HD void p2g_scatter_particle_vm(const float (&pos)[3], const float (&vel)[3], float mass,
                                                                const float (&C)[9], const float (&F)[9], const G &tb, float *tiles,
                                                                int nch, float dx, float dt, float volume, float mu, float lam,
                                                                float yield_stress) {
@@ -106,7 +106,7 @@ static __device__ __forceinline__ void p2g_scatter_particle_vm(const float (&pos
 
 // EquationOfStateConfig (P2G.hpp:66-87): weakly compressible fluid, J instead of F; gamma is fixed to 7 by the reference
 template <class G>
-static __device__ __forceinline__ void p2g_scatter_particle_eos(const float (&pos)[3], const float (&vel)[3], float mass,
+static ZPC_HD void p2g_scatter_particle_eos(const float (&pos)[3], const float (&vel)[3], float mass,
                                                                 const float (&C)[9], float J, const G &tb,
                                                                 float *tiles, int nch, float dx, float dt, float volume, float bulk,
                                                                 float viscosity) {
@@ -132,7 +132,7 @@ static __device__ __forceinline__ void p2g_scatter_particle_eos(const float (&po
 // vel = sum W v_i ; G[r + 3e] = sum W v_i[r] * o_e   (o = stencil offset 0..2), so that
 // C[r + 3e] = D_inv * (dx * G[r+3e] - local_e * vel[r])  ==  sum W v_i[r] * xixp[e] * D_inv  (G2P.hpp:65)
 template <class GA>
-static __device__ __noinline__ void g2p_gather_particle(const zpcm::Arena &ar, const GA &tb, const float *tiles, int nch,
+static __host__ __device__ __noinline__ void g2p_gather_particle(const zpcm::Arena &ar, const GA &tb, const float *tiles, int nch,
                                                  float (&vel)[3], float (&G)[9]) {
   constexpr int S = GA::S, M = (1 << S) - 1, CS = 1 << (3 * S);
   long long off[8];
@@ -156,7 +156,7 @@ static __device__ __noinline__ void g2p_gather_particle(const zpcm::Arena &ar, c
         const float oe[3] = {(float)i, (float)j, (float)k};
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const float wv = W * __ldg(t + (1 + r) * CS);
+          const float wv = W * zpcm::grid_load(t + (1 + r) * CS);
           vel[r] += wv;
 #pragma unroll
           for (int e = 0; e < 3; ++e) G[r + 3 * e] = fmaf(wv, oe[e], G[r + 3 * e]);
