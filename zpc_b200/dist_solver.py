@@ -269,13 +269,15 @@ def _cuda_unpack_add(grids, ids, buf):
 
 class DistMpmSolver:
     def __init__(self, P_local, dx, volume, dt, gravity=-9.8, mode=1, rebin_every=8, group=None, device="cuda",
-                 transport="auto", **kw):
-        self.local = MpmSolver(P_local, dx, volume, dt, gravity, mode, layout="binned", rebin_every=rebin_every,
-                               device=device, partition="with_rebin", **kw)
+                 transport="auto", layout="binned", halo=None, **kw):
+        """layout="binned": the fast path (substep).  layout="aos": the reference's particle layout and order, partition rebuilt
+        every step — what substep_host (host buffers in / out) runs on.  halo: a ready HaloExchange (tests)."""
+        self.local = MpmSolver(P_local, dx, volume, dt, gravity, mode, layout=layout, rebin_every=rebin_every,
+                               device=device, partition="with_rebin" if layout == "binned" else "every_step", **kw)
         self.n = self.local.n
         self.table = self.local.table
-        self.halo = None
-        if transport in ("auto", "p2p"):
+        self.halo = halo
+        if halo is None and transport in ("auto", "p2p"):
             try:
                 self.halo = HaloExchangeP2P(group, 7, device, _cuda_pack_ptr, _cuda_unpack_add)
             except Exception as ex:  # no symmetric memory on this system: same exchange over NCCL send/recv
@@ -303,6 +305,30 @@ class DistMpmSolver:
     def _rebuild_topology(self):
         nb = self.local.table.size()
         self.halo.build(self.local.table.active_keys[:nb])
+
+    def substep_host(self, hin, hout):
+        """Reference-facing call with HOST buffers on every rank (pinned torch tensors x, v, m, C, F of this rank's particles
+        in; x, v, C, F out), layout="aos": upload -> partition -> exchange topology -> clean -> P2G -> halo exchange ->
+        grid update -> G2P -> download.  Collective.  Returns the global max |v|^2."""
+        L = self.local
+        a = L.aos
+        if self._cfl_work is not None:
+            self._cfl_work.wait()
+            self._cfl_work = None
+        for k in ("x", "v", "m", "C", "F"):
+            getattr(a, k).copy_(hin[k], non_blocking=True)
+        api.partition_for_particles(api.vec3_port(a.x), L.n, L.dx, L.table)
+        self._rebuild_topology()                       # the partition is new every step on this path
+        api.clean_grid_blocks(L.grids, L.table)
+        api.p2g_transfer(a, L.table, L.grids, L.dt, L.model)
+        self.halo.exchange_add(L.grids)
+        L.max_vel_sqr.zero_()
+        L._grid_update()
+        dist.all_reduce(L.max_vel_sqr, op=dist.ReduceOp.MAX, group=self.group)
+        api.g2p_transfer(a, L.table, L.grids, L.dt, model=L.model)
+        for k in ("x", "v", "C", "F"):
+            hout[k].copy_(getattr(a, k), non_blocking=True)
+        return float(L.max_vel_sqr.item())             # D2H read = sync point
 
     def migrate(self, ownership):
         """Hands every particle to the rank that owns its current home block (BlockOwnership), then rebuilds the local solver
