@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--rebin-every", type=int, default=8)
     ap.add_argument("--partition", default="with_rebin", choices=["with_rebin", "every_step"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-timeout", type=int, default=240, help="seconds after which the N>1 e2e leg is abandoned (the line is still printed)")
     ap.add_argument("--e2e-pipelined", type=int, default=0, help="chunks of MpmSolver.substep_host_pipelined (0 = the plain call)")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,6 +265,38 @@ def main():
                  kernels=kern, partition_ms=per_step.get("partition"), halo_ms=per_step.get("halo"), rebin_ms_each=(stage.get("rebin", 0.0) / n_rebins) if n_rebins else None,
                  rebins_in_timed_region=n_rebins)
 
+    tuning_now = api.get_tuning()
+
+    def make_line(e2e, cpu):
+        return dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
+                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=workload, layout="block-binned AoSoA TileVector<f32,32>, re-bin every %d substeps" % args.rebin_every,
+                                partition=("hash-grid partition rebuilt every substep (EnlargeSparsity{0,2})" if (args.partition == "every_step" and world == 1)
+                                           else "hash-grid partition rebuilt with each re-bin, one extra ring (EnlargeSparsity{-1,3})"),
+                                kernel_variants=tuning_now, active_blocks=nblocks, l2="inputs (%.1f GB particle state) exceed the 126 MB L2; no explicit flush" % (n_local * 100 / 1e9),
+                                parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, halo exchange of shared grid blocks via %s" % (
+                                    world, "peer stores into symmetric memory over NVLink + device barrier" if transport == "p2p" else "NCCL send/recv")),
+                    substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,
+                    clocks=clocks)
+
+    # the e2e leg at N > 1 is collective: if it has not finished after --e2e-timeout seconds (a rank stuck in a collective), rank 0
+    # still prints the line — the device-resident numbers above are complete — and every rank leaves
+    import threading
+    finished = threading.Event()
+
+    def _bail():
+        if finished.is_set():
+            return
+        if rank == 0:
+            print(json.dumps(make_line(dict(value=None, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0,
+                                            note="e2e at N>1 did not finish within %d s" % args.e2e_timeout), None)), flush=True)
+        os._exit(0)
+    watchdog = None
+    if world > 1 and args.e2e_steps > 0:
+        watchdog = threading.Timer(args.e2e_timeout, _bail)
+        watchdog.daemon = True
+        watchdog.start()
+
     # ---- e2e: host buffers in, host buffers out, through the reference-facing call (N = 1) -----------------------
     e2e = None
     if world == 1 and args.e2e_steps > 0:
@@ -326,6 +359,8 @@ def main():
     elif world > 1:
         e2e = dict(value=None, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0, note="--e2e-steps 0")
 
+    if watchdog is not None:
+        watchdog.cancel()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -334,18 +369,9 @@ def main():
         except Exception as ex:  # the checker is optional; never let it break the GPU number
             cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(ex))
 
+    finished.set()
     if rank == 0:
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
-                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=workload, layout="block-binned AoSoA TileVector<f32,32>, re-bin every %d substeps" % args.rebin_every,
-                                partition=("hash-grid partition rebuilt every substep (EnlargeSparsity{0,2})" if (args.partition == "every_step" and world == 1)
-                                           else "hash-grid partition rebuilt with each re-bin, one extra ring (EnlargeSparsity{-1,3})"),
-                                kernel_variants=api.get_tuning(), active_blocks=nblocks, l2="inputs (%.1f GB particle state) exceed the 126 MB L2; no explicit flush" % (n_local * 100 / 1e9),
-                                parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, halo exchange of shared grid blocks via %s" % (
-                                    world, "peer stores into symmetric memory over NVLink + device barrier" if transport == "p2p" else "NCCL send/recv")),
-                    substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,
-                    clocks=clocks)
-        print(json.dumps(line))
+        print(json.dumps(make_line(e2e, cpu)), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
