@@ -284,6 +284,16 @@ int zpcb200_grid_update_bc(zpc_grids_view grids, zpc_hashtable_view table, float
                            int mode, const zpc_collider *colliders_host, int ncolliders, float *maxVelSqr,
                            zpc_stream_t stream);
 
+/* G2P2GTransfer<apic, Model> (simulation/transfer/G2P2G.hpp:49-141) — the matrix-free force evaluation of the implicit solver
+ * (simulation/mpm/ImplicitMPM.hpp:32-59): gridv / gridr are the DOF vectors of dof_view<space, 3>(Vector<float>), three floats
+ * per node, node = blockno * 64 + cellid.  C is gathered from gridv, the trial F = (I + dt C) F stays in registers (particles are
+ * not modified, logJp is read only), W * (P F^T vol * D_inv) * (x_i - x_p) is ADDED to gridr (clear it first, like DofFill).
+ * model_kind selects the struct `model` points to (host memory).  The reference's dof_view types do not compile under gcc 13, so
+ * this entry is checked against a restatement of the source only (oracle zo_g2p2g: parity unpinned). */
+enum { ZPC_MODEL_FIXED_COROTATED = 0, ZPC_MODEL_VONMISES = 1, ZPC_MODEL_DRUCKER_PRAGER = 2, ZPC_MODEL_NACC = 3, ZPC_MODEL_EOS = 4 };
+int zpcb200_g2p2g_apic(zpc_particles_view pars, zpc_hashtable_view table, float dx, float dt, int model_kind, const void *model,
+                       const float *gridv, float *gridr, zpc_stream_t stream);
+
 /* G2PTransfer<apic> (simulation/transfer/G2P.hpp:43-84), AoS layout, any order. */
 int zpcb200_g2p_apic(zpc_particles_view pars, zpc_hashtable_view table, zpc_grids_view grids,
                      float dt, zpc_stream_t stream);

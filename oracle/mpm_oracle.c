@@ -775,6 +775,83 @@ void zo_g2p(int n, float *x, float *v, float *C, float *F, float dx, float dt, i
   }
 }
 
+/* G2P2GTransfer::operator() (simulation/transfer/G2P2G.hpp:49-141): the matrix-free force evaluation of the implicit solver —
+ * gather C from a grid DOF vector gridv (3 floats per node, node = blockno * 64 + cellid, :62-76), F_trial = (I + dt C) F
+ * (:100-103, not stored), stress of the trial state (:104-121), scatter W * (contrib * D_inv) * xixp into the DOF vector gridr
+ * (:123-138).  PARITY UNPINNED: the reference's dof_view types (types/View.h) do not compile under gcc 13 here, so no
+ * reference output exists for this functor; this is a restatement of the source, checked against nothing but itself.
+ * model 0 fixed-corotated, 1 von Mises {yield}, 2 Drucker-Prager {cohesion, beta, yieldSurface, volumeCorrection},
+ * 3 NACC {xi, beta, hardeningOn, fa, dim}, 4 equation of state {bulk, viscosity} (Jp instead of F). */
+void zo_g2p2g(int model, const float *prm, int n, const float *x, const float *F, const float *Jp, const float *logJp,
+              float dx, float dt, float E, float nu, float volume, int table_size, const int *keys, const int *indices,
+              const float *gridv, float *gridr) {
+  const float dx_inv = (float)1 / dx;
+  const float D_inv = 4.f * dx_inv * dx_inv;
+  float mu, lam;
+  zo_lame(E, nu, &mu, &lam);
+  for (int p = 0; p < n; ++p) {
+    float pos[3] = {x[3*p], x[3*p+1], x[3*p+2]}, Cn[9] = {0}, contrib[9];
+    zo_arena ar;
+    arena_init(&ar, dx, pos);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) {
+      int o[3] = {i, j, k}, loc[3], blk[3];
+      float xixp[3];
+      for (int d = 0; d < 3; ++d) {
+        blk[d] = floor_div4(ar.corner[d] + o[d], &loc[d]);
+        xixp[d] = (float)o[d] * ar.dx - ar.local[d];
+      }
+      float W = 1.f; W *= ar.w[0][i]; W *= ar.w[1][j]; W *= ar.w[2][k];
+      const int bno = zo_table_query(blk, table_size, keys, indices);
+      const int cell = (loc[0] << 4) | (loc[1] << 2) | loc[2];
+      const float *vi = gridv + ((size_t)bno * 64 + cell) * 3;
+      for (int d = 0; d < 9; ++d) Cn[d] += W * vi[d % 3] * xixp[d / 3] * D_inv;               /* :75-76 */
+    }
+    if (model == 4) {                                                                          /* :80-98 */
+      float J = Jp[p];
+      J = (1 + (Cn[0] + Cn[4] + Cn[8]) * dt) * J;
+      const float vol = volume * J;
+      float pressure = prm[0];
+      { float J2 = J * J; float J4 = J2 * J2; pressure = pressure * (1 / (J * J2 * J4) - 1); }
+      const float visc = prm[1];
+      contrib[0] = ((Cn[0] + Cn[0]) * visc - pressure) * vol;
+      contrib[1] = (Cn[1] + Cn[3]) * visc * vol;
+      contrib[2] = (Cn[2] + Cn[6]) * visc * vol;
+      contrib[3] = (Cn[3] + Cn[1]) * visc * vol;
+      contrib[4] = ((Cn[4] + Cn[4]) * visc - pressure) * vol;
+      contrib[5] = (Cn[5] + Cn[7]) * visc * vol;
+      contrib[6] = (Cn[6] + Cn[2]) * visc * vol;
+      contrib[7] = (Cn[7] + Cn[5]) * visc * vol;
+      contrib[8] = ((Cn[8] + Cn[8]) * visc - pressure) * vol;
+    } else {
+      float tmp[9], Fn[9];
+      const float *Fo = F + 9 * p;
+      for (int d = 0; d < 9; ++d) tmp[d] = Cn[d] * dt + ((d & 0x3) ? 0.f : 1.f);
+      for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r)
+        Fn[3*c + r] = (tmp[r] * Fo[3*c] + tmp[3 + r] * Fo[3*c + 1]) + tmp[6 + r] * Fo[3*c + 2];
+      float lj = logJp ? logJp[p] : 0.f;                                                       /* a local copy: never written back */
+      if (model == 0) zo_stress_fixedcorotated(volume, mu, lam, Fn, contrib);
+      else if (model == 1) zo_stress_vonmises(volume, mu, lam, prm[0], Fn, contrib);
+      else if (model == 2) zo_stress_sand(volume, mu, lam, prm[0], prm[1], prm[2], prm[3] != 0.f, &lj, Fn, contrib);
+      else zo_stress_nacc(volume, mu, lam, zo_nacc_bulk(E, nu), prm[0], prm[1], zo_nacc_msqr(prm[3], (int)prm[4]), prm[2] != 0.f, &lj, Fn, contrib);
+    }
+    for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * D_inv;                               /* :122 */
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) {
+      int o[3] = {i, j, k}, loc[3], blk[3];
+      float xixp[3];
+      for (int d = 0; d < 3; ++d) {
+        blk[d] = floor_div4(ar.corner[d] + o[d], &loc[d]);
+        xixp[d] = (float)o[d] * ar.dx - ar.local[d];
+      }
+      float W = 1.f; W *= ar.w[0][i]; W *= ar.w[1][j]; W *= ar.w[2][k];
+      const int bno = zo_table_query(blk, table_size, keys, indices);
+      const int cell = (loc[0] << 4) | (loc[1] << 2) | loc[2];
+      float *r = gridr + ((size_t)bno * 64 + cell) * 3;
+      for (int d = 0; d < 3; ++d)
+        r[d] += W * (contrib[d] * xixp[0] + contrib[3 + d] * xixp[1] + contrib[6 + d] * xixp[2]);   /* :134-137 */
+    }
+  }
+}
+
 /* EquationOfStateConfig branch of G2PTransfer, G2P.hpp:69-73: J <- (1 + tr(C) dt) J, F untouched */
 void zo_g2p_eos(int n, float *x, float *v, float *C, float *Jp, float dx, float dt, int table_size,
                 const int *keys, const int *indices, const float *grid) {

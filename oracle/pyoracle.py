@@ -372,6 +372,19 @@ class Oracle:
         assert c <= cap
         return out[:c].copy()
 
+    def g2p2g(self, model, prm, P, tab, dx, dt, E, nu, volume, gridv):
+        """G2P2GTransfer (parity unpinned): gridv [nb*64, 3] -> gridr [nb*64, 3]"""
+        n = P["x"].shape[0]
+        prm = np.ascontiguousarray(prm, np.float32)
+        gridv = np.ascontiguousarray(gridv, np.float32)
+        gridr = np.zeros_like(gridv)
+        nul = C.c_void_p(None)
+        self.lib.zo_g2p2g(C.c_int(model), _ptr(prm), C.c_int(n), _ptr(P["x"]), _ptr(P["F"]) if "F" in P else nul,
+                          _ptr(P["J"]) if "J" in P else nul, _ptr(P["logJp"]) if "logJp" in P else nul, C.c_float(dx), C.c_float(dt),
+                          C.c_float(E), C.c_float(nu), C.c_float(volume), C.c_int(tab["table_size"]), _ptr(tab["keys"]),
+                          _ptr(tab["indices"]), _ptr(gridv), _ptr(gridr))
+        return gridr
+
     def cuboid(self, x, mn, mx):
         x = np.ascontiguousarray(x, np.float32)
         mn = np.ascontiguousarray(mn, np.float32); mx = np.ascontiguousarray(mx, np.float32)

@@ -117,4 +117,18 @@ void hm_g2p_aos(int eos, zpc_particles_view P, zpc_hashtable_view tb, const floa
     else g2p_aos_particle<false>(P, p, g, tiles, 7, dx, dt);
   }
 }
+// g2p2g_particle (the body of g2p2g_aos_kernel) particle by particle; model / prm as hm_p2g_aos
+void hm_g2p2g(int model, zpc_particles_view P, zpc_hashtable_view tb, const float *gridv, float *gridr, float dx, float dt, float volume,
+              float mu, float lam, const float *prm) {
+  const zpcp::LegacyGrid g{tb};
+  PlasticParams pp{prm[0], prm[1], prm[2], prm[3], prm[4] != 0.f};
+  if (model == 2) pp.flag = prm[3] != 0.f;
+  for (size_t p = 0; p < P.count; ++p) {
+    if (model == 0) g2p2g_particle<0>(P, p, g, gridv, gridr, dx, dt, volume, mu, lam, pp);
+    else if (model == 1) g2p2g_particle<1>(P, p, g, gridv, gridr, dx, dt, volume, mu, lam, pp);
+    else if (model == 2) g2p2g_particle<2>(P, p, g, gridv, gridr, dx, dt, volume, mu, lam, pp);
+    else if (model == 3) g2p2g_particle<3>(P, p, g, gridv, gridr, dx, dt, volume, mu, lam, pp);
+    else g2p2g_particle<4>(P, p, g, gridv, gridr, dx, dt, volume, mu, lam, pp);
+  }
+}
 }

@@ -176,6 +176,22 @@ def test_index_buckets_entry_host_side_behaviour():
                                          None, None, None, None, None) == -1
 
 
+def test_g2p2g_entry_checks_its_arguments():
+    from zpc_b200 import api
+    L = api.lib()
+    tv = api.zpc_hashtable_view(1, 1, 1, 1, 16, 1)
+    m = api.model_fcr(1e-6)
+    empty = api.zpc_particles_view(None, None, None, None, None, None, None, None, 0)
+    some = api.zpc_particles_view(1, 1, 1, None, None, 1, 1, None, 10)
+    f = ctypes.c_float
+    assert L.zpcb200_g2p2g_apic(empty, tv, f(0.1), f(1e-4), 0, ctypes.byref(m), None, None, None) == 0          # empty range: no-op
+    assert L.zpcb200_g2p2g_apic(some, tv, f(0.1), f(1e-4), 0, ctypes.byref(m), None, None, None) == -1         # null DOF vectors
+    assert L.zpcb200_g2p2g_apic(some, tv, f(0.1), f(1e-4), 7, ctypes.byref(m), None, None, None) == -1         # unknown model kind
+    assert L.zpcb200_g2p2g_apic(some, tv, f(0.1), f(1e-4), 0, None, None, None, None) == -1
+    nacc = api.model_nacc(1e-6)
+    assert L.zpcb200_g2p2g_apic(some, tv, f(0.1), f(1e-4), 3, ctypes.byref(nacc), ctypes.c_void_p(8), ctypes.c_void_p(8), None) == -1   # no logJp
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "zpc_b200")):
         for f in files:

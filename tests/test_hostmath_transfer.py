@@ -105,3 +105,48 @@ def test_plastic_models_on_the_host(hm, oracle, model):
     check_channels(grid[o], z["grid_p2g"][r], 1, "host-compiled %s P2G vs golden" % model, [RTOL] * 4 + [rhs] * 3)
     assert np.abs(keep["logJp"] - z["logJp"]).max() <= 2e-5
     assert np.abs(keep["logJp"] - z["logJp_in"]).max() > 1e-3
+
+
+@pytest.mark.parametrize("model", [0, 1, 2, 3, 4])
+def test_g2p2g_on_the_host_matches_the_restated_functor(hm, oracle, model):
+    """g2p2g_particle (the body of zpcb200_g2p2g_apic's kernel) vs oracle.zo_g2p2g for all five models.  PARITY UNPINNED: the
+    reference's G2P2G cannot be compiled here (types/View.h), the oracle is a restatement of simulation/transfer/G2P2G.hpp:49-141;
+    this test checks that the product code and that restatement agree, and that the functor does what its algebra says (a rigid
+    translation field gives C = 0, hence the stress of F itself)."""
+    P = synth.elastic_cube(6, 32, jitter_F=0.04, jitter_C=0.3, shuffle_seed=21)
+    n, dx = P["x"].shape[0], P["dx"]
+    rs = np.random.RandomState(5)
+    En, nun = (NACC["E"], NACC["nu"]) if model == 3 else (E, NU)
+    if model in (2, 3):
+        P["logJp"] = rs.uniform(-1.8, 0.2, n).astype(np.float32) if model == 3 else rs.uniform(-0.06, 0.03, n).astype(np.float32)
+    if model == 4:
+        P["J"] = (1.0 + rs.uniform(-0.05, 0.05, n)).astype(np.float32)
+    tab = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    nb = tab["nblocks"]
+    gridv = rs.uniform(-1, 1, (nb * 64, 3)).astype(np.float32)
+    bm, msqr = oracle.nacc_consts(NACC["E"], NACC["nu"], NACC["fa"])
+    prm_o = {0: [0], 1: [2946.0], 2: [SAND["cohesion"], SAND["beta"], SAND["yieldSurface"], 1.0],
+             3: [NACC["xi"], NACC["beta"], 1.0, NACC["fa"], 3.0], 4: [4.0e4, 0.01]}[model]
+    prm_d = {0: [0, 0, 0, 0, 0], 1: [2946.0, 0, 0, 0, 0], 2: [SAND["cohesion"], SAND["beta"], SAND["yieldSurface"], 1.0, 0],
+             3: [bm, NACC["xi"], NACC["beta"], msqr, 1.0], 4: [4.0e4, 0.01, 0, 0, 0]}[model]
+    want = oracle.g2p2g(model, prm_o, P, tab, dx, synth.DT, En, nun, P["volume"], gridv)
+    pv, tv, keep, tk = _views(P, tab)
+    mu, lam = oracle.lame(En, nun)
+    got = np.zeros_like(gridv)
+    prm = np.array(prm_d, np.float32)
+    hm.hm_g2p2g(C.c_int(model), pv, tv, gridv.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), C.c_float(dx), C.c_float(synth.DT),
+                C.c_float(P["volume"]), C.c_float(mu), C.c_float(lam), prm.ctypes.data_as(C.c_void_p))
+    scale = float(np.abs(want).max())
+    assert scale > 0
+    tol = 1e-3 if model == 3 else RTOL_STRESS
+    assert np.abs(got - want).max() <= tol * scale, (model, np.abs(got - want).max() / scale)
+    for k in ("F", "logJp", "J"):                       # particles are read only
+        if k in P:
+            assert np.array_equal(keep[k], P[k])
+    if model == 0:
+        # rigid translation: v_i = const  =>  C = 0 (partition of unity)  =>  r = sum W (P(F) F^T vol D_inv) xixp, the rhs of P2G / (-dt)
+        gv = np.tile(np.float32([0.3, -0.2, 0.1]), (nb * 64, 1))
+        r = oracle.g2p2g(0, [0], P, tab, dx, synth.DT, E, NU, P["volume"], gv)
+        g = oracle.p2g(P, tab, dx, synth.DT, E, NU, P["volume"])
+        rhs = g[:, 4:7].transpose(0, 2, 1).reshape(-1, 3) / np.float32(-synth.DT)
+        assert np.abs(r - rhs).max() <= 2e-5 * np.abs(rhs).max()

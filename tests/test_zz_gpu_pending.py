@@ -337,6 +337,37 @@ def test_against_the_references_own_cuda_path(oracle, tmp_path):
     check_channels(o1, g1r, 1, "host oracle vs reference CUDA", GRID_RTOL)
 
 
+@pytest.mark.parametrize("model", ["fcr", "vonmises", "nacc", "eos"])
+def test_g2p2g_matches_the_restated_functor(oracle, model):
+    """zpcb200_g2p2g_apic vs oracle.zo_g2p2g (a restatement of G2P2G.hpp:49-141 — parity unpinned, the reference's functor does not
+    compile here): force terms added to gridr, particles untouched"""
+    from zpc_b200 import api
+    P = synth.elastic_cube(8, 32, jitter_F=0.04, jitter_C=0.3, shuffle_seed=21)
+    n, dx = P["x"].shape[0], P["dx"]
+    rs = np.random.RandomState(5)
+    En, nun = (NACC["E"], NACC["nu"]) if model == "nacc" else (E, NU)
+    if model == "nacc":
+        P["logJp"] = rs.uniform(-1.8, 0.2, n).astype(np.float32)
+    if model == "eos":
+        P["J"] = (1.0 + rs.uniform(-0.05, 0.05, n)).astype(np.float32)
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    nb = ht["nblocks"]
+    gridv = rs.uniform(-1, 1, (nb * 64, 3)).astype(np.float32)
+    m, kind, prm = {"fcr": (api.model_fcr(P["volume"], E, NU), 0, [0]),
+                    "vonmises": (api.model_vonmises(P["volume"], E, NU, 2946.0), 1, [2946.0]),
+                    "nacc": (api.model_nacc(P["volume"], NACC["E"], NACC["nu"], NACC["fa"], NACC["xi"], NACC["beta"], True), 3,
+                             [NACC["xi"], NACC["beta"], 1.0, NACC["fa"], 3.0]),
+                    "eos": (api.model_eos(P["volume"], 4.0e4, 7.15, 0.01), 4, [4.0e4, 0.01])}[model]
+    gv, gr = torch.from_numpy(gridv).cuda(), torch.zeros(nb * 64, 3, device="cuda")
+    api.g2p2g_transfer(pars, table, dx, synth.DT, m, gv, gr)
+    torch.cuda.synchronize()
+    want = oracle.g2p2g(kind, prm, P, ht, dx, synth.DT, En, nun, P["volume"], gridv)
+    scale = float(np.abs(want).max())
+    assert np.abs(gr.cpu().numpy() - want).max() <= (1e-3 if model == "nacc" else RTOL_STRESS) * scale
+    assert np.array_equal(pars.x.cpu().numpy(), P["x"])
+
+
 # last: a failed stream capture could leave the process unable to launch — nothing runs after it
 def test_graph_replay_equals_eager_substeps():
     """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same

@@ -699,6 +699,17 @@ def p2g_transfer(pars, table, grids, dt, model, stream=None):
     _check(rc, "p2g")
 
 
+_MODEL_KIND = {zpc_fixed_corotated: 0, zpc_vonmises_fixed_corotated: 1, zpc_drucker_prager: 2, zpc_nacc: 3, zpc_equation_of_state: 4}
+
+
+def g2p2g_transfer(pars, table, dx, dt, model, gridv, gridr, stream=None):
+    """G2P2GTransfer{cuda_c, wrapv<apic>{}, dt, model, grid, x, r, table, particles} (simulation/transfer/G2P2G.hpp:49-141): gridv, gridr =
+    float32 [numBlocks * 64, 3] DOF vectors; the force terms are ADDED to gridr"""
+    assert gridv.dtype == torch.float32 and gridr.dtype == torch.float32 and gridv.is_contiguous() and gridr.is_contiguous()
+    _check(lib().zpcb200_g2p2g_apic(pars.view(), table.view(), C.c_float(dx), C.c_float(dt), C.c_int(_MODEL_KIND[type(model)]), C.byref(model),
+                                    C.c_void_p(gridv.data_ptr()), C.c_void_p(gridr.data_ptr()), _stream_ptr(stream)), "g2p2g")
+
+
 def compute_grid_block_velocity(grids, table, dt, extf, mode, max_vel_sqr, stream=None):
     e = (C.c_float * 3)(*[float(v) for v in extf])
     _check(lib().zpcb200_grid_update(grids.view(), C.c_void_p(table.cnt.data_ptr()), C.c_float(dt), e,

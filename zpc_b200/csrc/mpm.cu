@@ -362,6 +362,54 @@ int zpcb200_p2g_apic_nacc(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids
   return ZPCB200_OK;
 }
 
+int zpcb200_g2p2g_apic(zpc_particles_view P, zpc_hashtable_view tb, float dx, float dt, int model_kind, const void *model,
+                       const float *gridv, float *gridr, zpc_stream_t stream) {
+  if (!model || (unsigned)model_kind > 4u || !tb.keys || !tb.indices) return ZPCB200_E_BADARG;
+  if (!P.count) return ZPCB200_OK;
+  if (!P.X || !gridv || !gridr || (model_kind == ZPC_MODEL_EOS ? !P.J : !P.F) ||
+      ((model_kind == ZPC_MODEL_DRUCKER_PRAGER || model_kind == ZPC_MODEL_NACC) && !P.logJp))
+    return ZPCB200_E_BADARG;
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  const zpcp::LegacyGrid ga{tb};
+  float mu = 0.f, lam = 0.f;
+  PlasticParams prm{0.f, 0.f, 0.f, 0.f, 0};
+  switch (model_kind) {
+    case ZPC_MODEL_FIXED_COROTATED: {
+      const auto &m = *(const zpc_fixed_corotated *)model;
+      zpcm::lame_host(m.E, m.nu, mu, lam);
+      g2p2g_aos_kernel<0><<<grid, 128, 0, s>>>(P, ga, gridv, gridr, dx, dt, m.volume, mu, lam, prm);
+    } break;
+    case ZPC_MODEL_VONMISES: {
+      const auto &m = *(const zpc_vonmises_fixed_corotated *)model;
+      zpcm::lame_host(m.E, m.nu, mu, lam);
+      prm.a = m.yieldStress;
+      g2p2g_aos_kernel<1><<<grid, 128, 0, s>>>(P, ga, gridv, gridr, dx, dt, m.volume, mu, lam, prm);
+    } break;
+    case ZPC_MODEL_DRUCKER_PRAGER: {
+      const auto &m = *(const zpc_drucker_prager *)model;
+      zpcm::lame_host(m.E, m.nu, mu, lam);
+      prm = PlasticParams{m.cohesion, m.beta, m.yieldSurface, 0.f, m.volumeCorrection};
+      g2p2g_aos_kernel<2><<<grid, 128, 0, s>>>(P, ga, gridv, gridr, dx, dt, m.volume, mu, lam, prm);
+    } break;
+    case ZPC_MODEL_NACC: {
+      const auto &m = *(const zpc_nacc *)model;
+      if (m.dim != 3) return ZPCB200_E_BADARG;
+      zpcm::lame_host(m.E, m.nu, mu, lam);
+      prm = PlasticParams{zpcm::nacc_bulk_host(m.E, m.nu), m.xi, m.beta, zpcm::nacc_msqr_host(m.fa, m.dim), m.hardeningOn};
+      g2p2g_aos_kernel<3><<<grid, 128, 0, s>>>(P, ga, gridv, gridr, dx, dt, m.volume, mu, lam, prm);
+    } break;
+    default: {
+      const auto &m = *(const zpc_equation_of_state *)model;
+      prm.a = m.bulk;
+      prm.b = m.viscosity;
+      g2p2g_aos_kernel<4><<<grid, 128, 0, s>>>(P, ga, gridv, gridr, dx, dt, m.volume, mu, lam, prm);
+    } break;
+  }
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
 int zpcb200_g2p_apic(zpc_particles_view P, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
   if (P.count == 0) return ZPCB200_OK;
   if (g.numChannels < 4 || !P.X || !P.V || !P.C || !P.F) return ZPCB200_E_BADARG;

@@ -180,4 +180,94 @@ __global__ void __launch_bounds__(128) g2p_aos_kernel(zpc_particles_view P, GA t
   g2p_aos_particle<EOS>(P, p, tb, tiles, nch, dx, dt);
 }
 
+// G2P2GTransfer (simulation/transfer/G2P2G.hpp:49-141) for particle p: C gathered from the DOF vector gridv (3 floats per node,
+// node = block * cells + cell), trial F = (I + dt C) F (kept in registers), stress of the trial state, W * (contrib * D_inv) * xixp
+// scattered into the DOF vector gridr.  MODEL 0 fixed-corotated, 1 von Mises, 2 Drucker-Prager, 3 NACC (logJp read, not written
+// back), 4 equation of state (J).  prm as in PlasticParams; model 1: a = yield stress; model 4: a = bulk, b = viscosity.
+template <int MODEL, class GA>
+ZPC_HD void g2p2g_particle(const zpc_particles_view &P, size_t p, GA tb, const float *gridv, float *gridr, float dx, float dt,
+                           float volume, float mu, float lam, const PlasticParams &prm) {
+  constexpr int S = GA::S, M = (1 << S) - 1, CS = 1 << (3 * S);
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  float pos[3], C[9], contrib[9];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) pos[d] = P.X[3 * p + d];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) C[d] = 0.f;
+  zpcm::Arena ar;
+  zpcm::arena_init(ar, dx, pos);
+  long long boff[8];
+  zpcp::resolve_blocks(ar.corner, tb, 1, boff);                 // nch = 1: offsets in nodes (block * cells)
+  const int lx0 = ar.corner[0] & M, ly0 = ar.corner[1] & M, lz0 = ar.corner[2] & M;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int lx = lx0 + i, ly = ly0 + j, lz = lz0 + k;
+        const long long off = boff[((lx >> S) << 2) | ((ly >> S) << 1) | (lz >> S)];
+        if (off < 0) continue;
+        const float *t = gridv + 3 * (off + zpcp::cell_offset<GA>(lx, ly, lz));
+        const float xixp[3] = {(float)i * dx - ar.local[0], (float)j * dx - ar.local[1], (float)k * dx - ar.local[2]};
+        const float W = ar.w[0][i] * ar.w[1][j] * ar.w[2][k];
+        const float vi[3] = {zpcm::grid_load(t), zpcm::grid_load(t + 1), zpcm::grid_load(t + 2)};
+#pragma unroll
+        for (int d = 0; d < 9; ++d) C[d] += W * vi[d % 3] * xixp[d / 3] * D_inv;
+      }
+  if constexpr (MODEL == 4) {
+    float J = P.J[p];
+    J = (1 + (C[0] + C[4] + C[8]) * dt) * J;
+    const float vol = volume * J, J2 = J * J, J4 = J2 * J2;
+    const float pressure = prm.a * (1.f / (J * J2 * J4) - 1.f), visc = prm.b;
+    contrib[0] = ((C[0] + C[0]) * visc - pressure) * vol;
+    contrib[1] = (C[1] + C[3]) * visc * vol;
+    contrib[2] = (C[2] + C[6]) * visc * vol;
+    contrib[3] = (C[3] + C[1]) * visc * vol;
+    contrib[4] = ((C[4] + C[4]) * visc - pressure) * vol;
+    contrib[5] = (C[5] + C[7]) * visc * vol;
+    contrib[6] = (C[6] + C[2]) * visc * vol;
+    contrib[7] = (C[7] + C[5]) * visc * vol;
+    contrib[8] = ((C[8] + C[8]) * visc - pressure) * vol;
+  } else {
+    float Fo[9], tmp[9], F[9];
+#pragma unroll
+    for (int d = 0; d < 9; ++d) { Fo[d] = P.F[9 * p + d]; tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f); }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) F[3 * c + r] = tmp[r] * Fo[3 * c] + tmp[3 + r] * Fo[3 * c + 1] + tmp[6 + r] * Fo[3 * c + 2];
+    if constexpr (MODEL == 0) zpcm::stress_fcr(volume, mu, lam, F, contrib);
+    else if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, prm.a, F, contrib);
+    else {
+      float logJp = P.logJp[p];
+      if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, prm.a, prm.b, prm.c, prm.flag != 0, logJp, F, contrib);
+      else zpcm::stress_nacc(volume, mu, prm.a, prm.b, prm.c, prm.d, prm.flag != 0, logJp, F, contrib);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * D_inv;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int lx = lx0 + i, ly = ly0 + j, lz = lz0 + k;
+        const long long off = boff[((lx >> S) << 2) | ((ly >> S) << 1) | (lz >> S)];
+        if (off < 0) continue;
+        float *r = gridr + 3 * (off + zpcp::cell_offset<GA>(lx, ly, lz));
+        const float x0 = (float)i * dx - ar.local[0], x1 = (float)j * dx - ar.local[1], x2 = (float)k * dx - ar.local[2];
+        const float W = ar.w[0][i] * ar.w[1][j] * ar.w[2][k];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) zpcm::grid_add(r + d, W * (contrib[d] * x0 + contrib[3 + d] * x1 + contrib[6 + d] * x2));
+      }
+}
+template <int MODEL, class GA>
+__global__ void __launch_bounds__(128) g2p2g_aos_kernel(zpc_particles_view P, GA tb, const float *gridv, float *gridr, float dx, float dt,
+                                                        float volume, float mu, float lam, PlasticParams prm) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P.count) g2p2g_particle<MODEL>(P, p, tb, gridv, gridr, dx, dt, volume, mu, lam, prm);
+}
+
 }  // namespace
