@@ -1,0 +1,213 @@
+// zs_overlay.cuh — the binding INTEGRATION.md describes, as code that compiles against the UNMODIFIED reference headers
+// (include it after the zensim headers of the path; link libzpcb200.so).
+//
+//   zs::B200ExecutionPolicy / zs::b200_exec()   a CudaExecutionPolicy whose reduce / exclusive_scan / inclusive_scan /
+//       radix_sort / radix_sort_pair members go to libzpcb200 when the iterators are raw pointers or zs::Vector iterators and
+//       the operator is plus (reduce: plus / getmin / getmax) on {i32, u32, i64, f32, f64} — every other call, and every
+//       policy(range, functor) launch, stays the reference's (members are hidden, not removed).  Generic code that is templated
+//       on the policy (zs::radix_sort_pair(pol, ...), LBvh::build(pol, ...), ...) needs no change: pass b200_exec().
+//   zs::b200::partition_for_particles / clean_grid_blocks / p2g / compute_grid_block_velocity / g2p
+//       the MPM functor launches of SURVEY §3.1 on the reference's own containers (Particles, HashTable, Grids):
+//       pol(range(n), P2GTransfer{cuda_c, wrapv<apic>{}, dt, model, pars, table, grids})  becomes  b200::p2g(pol, dt, model, pars, table, grids).
+//
+// Temporary storage comes from the policy's stream-ordered pool (streamMemAlloc / streamMemFree, like
+// cuda/execution/ExecutionPolicy.cuh:806-815); errors surface like the reference's (checkCuApiError is private to Cuda, so a
+// std::runtime_error carries the code); the policy's sync(true) default is honoured.
+#pragma once
+#include <stdexcept>
+#include <string>
+
+#include "zensim/container/HashTable.hpp"
+#include "zensim/container/Vector.hpp"
+#include "zensim/cuda/execution/ExecutionPolicy.cuh"
+#include "zensim/geometry/Structure.hpp"
+#include "zensim/geometry/Structurefree.hpp"
+#include "zensim/physics/ConstitutiveModel.hpp"
+#include "zpcb200.h"
+
+namespace zs {
+
+  namespace b200_detail {
+    template <class It> struct raw_iter {  // raw pointer or zs::Vector iterator -> element pointer; anything else: no fast path
+      using I = remove_cvref_t<It>;
+      template <class T> static constexpr bool is_vector_iter
+          = is_same_v<I, decltype(zs::begin(declval<Vector<T> &>()))> || is_same_v<I, decltype(zs::begin(declval<const Vector<T> &>()))>;
+      using value_type = typename std::iterator_traits<I>::value_type;
+      static constexpr bool ok = std::is_pointer_v<I> || is_vector_iter<remove_cv_t<value_type>>;
+      static auto get(I it) {
+        if constexpr (std::is_pointer_v<I>) return it;
+        else return it.operator->();
+      }
+    };
+    template <class T> constexpr int kind_of() {  // index into the per-type entry tables below, -1 = unsupported
+      if constexpr (is_same_v<T, int>) return 0;
+      else if constexpr (is_same_v<T, unsigned>) return 1;
+      else if constexpr (is_same_v<T, long long> || is_same_v<T, long>) return sizeof(T) == 8 ? 2 : -1;
+      else if constexpr (is_same_v<T, float>) return 3;
+      else if constexpr (is_same_v<T, double>) return 4;
+      else return -1;
+    }
+    using prim2_t = int (*)(void *, size_t *, zpc_port, zpc_port, size_t, zpc_stream_t);
+    inline prim2_t reduce_entry(int op, int kind) {
+      static const prim2_t t[3][5] = {
+          {zpcb200_reduce_sum_i32, zpcb200_reduce_sum_u32, zpcb200_reduce_sum_i64, zpcb200_reduce_sum_f32, zpcb200_reduce_sum_f64},
+          {zpcb200_reduce_min_i32, zpcb200_reduce_min_u32, zpcb200_reduce_min_i64, zpcb200_reduce_min_f32, zpcb200_reduce_min_f64},
+          {zpcb200_reduce_max_i32, zpcb200_reduce_max_u32, zpcb200_reduce_max_i64, zpcb200_reduce_max_f32, zpcb200_reduce_max_f64}};
+      return t[op][kind];
+    }
+    inline prim2_t scan_entry(bool inclusive, int kind) {
+      static const prim2_t t[2][5] = {{zpcb200_exclusive_scan_sum_i32, zpcb200_exclusive_scan_sum_u32, zpcb200_exclusive_scan_sum_i64,
+                                       zpcb200_exclusive_scan_sum_f32, zpcb200_exclusive_scan_sum_f64},
+                                      {zpcb200_inclusive_scan_sum_i32, zpcb200_inclusive_scan_sum_u32, zpcb200_inclusive_scan_sum_i64,
+                                       zpcb200_inclusive_scan_sum_f32, zpcb200_inclusive_scan_sum_f64}};
+      return t[inclusive ? 1 : 0][kind];
+    }
+    template <class Op, class T> constexpr int reduce_op() {  // 0 plus, 1 min, 2 max, -1 other
+      using O = remove_cvref_t<Op>;
+      if constexpr (is_same_v<O, plus<T>> || is_same_v<O, plus<void>>) return 0;
+      else if constexpr (is_same_v<O, getmin<T>> || is_same_v<O, getmin<void>>) return 1;
+      else if constexpr (is_same_v<O, getmax<T>> || is_same_v<O, getmax<void>>) return 2;
+      else return -1;
+    }
+    inline zpc_port port_of(const void *p) { return zpc_port{const_cast<void *>(p), 0, 0, 0, 1}; }
+  }  // namespace b200_detail
+
+  struct B200ExecutionPolicy : CudaExecutionPolicy {
+    using Base = CudaExecutionPolicy;
+    using Base::operator();
+    B200ExecutionPolicy() = default;
+    B200ExecutionPolicy(const CudaExecutionPolicy &p) : CudaExecutionPolicy{p} {}
+
+    void *b200Stream() const {
+      auto &ctx = Cuda::context(getProcid());
+      ctx.setContext();
+      return ctx.streamSpare(getStreamid());
+    }
+    void b200Done(int rc, const char *what, const source_location &loc) const {
+      if (rc) throw std::runtime_error(std::string("[") + what + "] failed with code " + std::to_string(rc));
+      if (this->shouldSync()) Cuda::context(getProcid()).syncStreamSpare(getStreamid(), loc);
+    }
+    /// temp == nullptr size query, allocation from the stream-ordered pool, the call, release on the same stream
+    template <class Fn, class... Args> void b200TwoPhase(const char *what, const source_location &loc, Fn fn, Args... args) const {
+      auto &ctx = Cuda::context(getProcid());
+      void *stream = b200Stream();
+      size_t bytes = 0;
+      int rc = fn(nullptr, &bytes, args..., nullptr);
+      if (rc) b200Done(rc, what, loc);
+      void *tmp = ctx.streamMemAlloc(bytes ? bytes : 256, stream, loc);
+      rc = fn(tmp, &bytes, args..., stream);
+      ctx.streamMemFree(tmp, stream, loc);
+      b200Done(rc, what, loc);
+    }
+
+    template <class InputIt, class OutputIt, class BinaryOp = plus<typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type>>
+    void reduce(InputIt &&first, InputIt &&last, OutputIt &&d_first,
+                typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type init
+                = deduce_identity<BinaryOp, typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type>(),
+                BinaryOp &&binary_op = {}, const source_location &loc = source_location::current()) const {
+      using T = remove_cv_t<typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type>;
+      constexpr int kind = b200_detail::kind_of<T>(), op = b200_detail::reduce_op<BinaryOp, T>();
+      if constexpr (kind >= 0 && op >= 0 && b200_detail::raw_iter<InputIt>::ok && b200_detail::raw_iter<OutputIt>::ok) {
+        // the library reduces from the operator's identity, which is what every in-tree caller passes (deduce_identity)
+        if (init == deduce_identity<remove_cvref_t<BinaryOp>, T>()) {
+          const auto n = (size_t)(last - first);
+          b200TwoPhase("zpcb200_reduce", loc, b200_detail::reduce_entry(op, kind), b200_detail::port_of(b200_detail::raw_iter<InputIt>::get(first)),
+                       b200_detail::port_of(b200_detail::raw_iter<OutputIt>::get(d_first)), n);
+          return;
+        }
+      }
+      Base::reduce(FWD(first), FWD(last), FWD(d_first), init, FWD(binary_op), loc);
+    }
+    template <class InputIt, class OutputIt, class BinaryOperation = plus<typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type>>
+    void exclusive_scan(InputIt &&first, InputIt &&last, OutputIt &&d_first,
+                        typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type init
+                        = deduce_identity<BinaryOperation, typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type>(),
+                        BinaryOperation &&binary_op = {}, const source_location &loc = source_location::current()) const {
+      using T = remove_cv_t<typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type>;
+      constexpr int kind = b200_detail::kind_of<T>();
+      if constexpr (kind >= 0 && b200_detail::reduce_op<BinaryOperation, T>() == 0 && b200_detail::raw_iter<InputIt>::ok
+                    && b200_detail::raw_iter<OutputIt>::ok) {
+        if (init == T{}) {
+          b200TwoPhase("zpcb200_exclusive_scan_sum", loc, b200_detail::scan_entry(false, kind),
+                       b200_detail::port_of(b200_detail::raw_iter<InputIt>::get(first)),
+                       b200_detail::port_of(b200_detail::raw_iter<OutputIt>::get(d_first)), (size_t)(last - first));
+          return;
+        }
+      }
+      Base::exclusive_scan(FWD(first), FWD(last), FWD(d_first), init, FWD(binary_op), loc);
+    }
+    template <class InputIt, class OutputIt, class BinaryOperation = plus<typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type>>
+    void inclusive_scan(InputIt &&first, InputIt &&last, OutputIt &&d_first, BinaryOperation &&binary_op = {},
+                        const source_location &loc = source_location::current()) const {
+      using T = remove_cv_t<typename std::iterator_traits<remove_cvref_t<InputIt>>::value_type>;
+      constexpr int kind = b200_detail::kind_of<T>();
+      if constexpr (kind >= 0 && b200_detail::reduce_op<BinaryOperation, T>() == 0 && b200_detail::raw_iter<InputIt>::ok
+                    && b200_detail::raw_iter<OutputIt>::ok) {
+        b200TwoPhase("zpcb200_inclusive_scan_sum", loc, b200_detail::scan_entry(true, kind),
+                     b200_detail::port_of(b200_detail::raw_iter<InputIt>::get(first)),
+                     b200_detail::port_of(b200_detail::raw_iter<OutputIt>::get(d_first)), (size_t)(last - first));
+      } else
+        Base::inclusive_scan(FWD(first), FWD(last), FWD(d_first), FWD(binary_op), loc);
+    }
+    template <class KeyIter, class ValueIter,
+              typename Tn = typename std::iterator_traits<remove_reference_t<KeyIter>>::difference_type>
+    enable_if_type<is_ra_iter_v<remove_reference_t<KeyIter>> && is_ra_iter_v<remove_reference_t<ValueIter>>> radix_sort_pair(
+        KeyIter &&keysIn, ValueIter &&valsIn, KeyIter &&keysOut, ValueIter &&valsOut, Tn count = 0, int sbit = 0,
+        int ebit = sizeof(typename std::iterator_traits<remove_reference_t<KeyIter>>::value_type) * 8,
+        const source_location &loc = source_location::current()) const {
+      using K = remove_cv_t<typename std::iterator_traits<remove_cvref_t<KeyIter>>::value_type>;
+      using V = remove_cv_t<typename std::iterator_traits<remove_cvref_t<ValueIter>>::value_type>;
+      constexpr bool keyOk = is_same_v<K, unsigned> || is_same_v<K, int> || (std::is_unsigned_v<K> && sizeof(K) == 8);
+      if constexpr (keyOk && is_same_v<V, int> && b200_detail::raw_iter<KeyIter>::ok && b200_detail::raw_iter<ValueIter>::ok) {
+        auto fn = is_same_v<K, unsigned> ? zpcb200_radix_sort_pair_u32 : (is_same_v<K, int> ? zpcb200_radix_sort_pair_i32 : zpcb200_radix_sort_pair_u64);
+        b200TwoPhase("zpcb200_radix_sort_pair", loc, fn, b200_detail::port_of(b200_detail::raw_iter<KeyIter>::get(keysIn)),
+                     b200_detail::port_of(b200_detail::raw_iter<ValueIter>::get(valsIn)),
+                     b200_detail::port_of(b200_detail::raw_iter<KeyIter>::get(keysOut)),
+                     b200_detail::port_of(b200_detail::raw_iter<ValueIter>::get(valsOut)), (size_t)count, sbit, ebit);
+      } else
+        Base::radix_sort_pair(FWD(keysIn), FWD(valsIn), FWD(keysOut), FWD(valsOut), count, sbit, ebit, loc);
+    }
+  };
+  inline B200ExecutionPolicy b200_exec() noexcept { return B200ExecutionPolicy{}; }
+
+  /// the MPM functor launches on the reference's own containers (device memory)
+  namespace b200 {
+    inline zpc_particles_view view(Particles<f32, 3> &pars) {
+      auto addr = [&](const char *name) { return pars.hasAttr(name) ? (float *)pars.getAttrAddress(name) : (float *)nullptr; };
+      return zpc_particles_view{addr("m"), addr("x"), addr("v"), nullptr, addr("J"), addr("F"), addr("C"), addr("logJp"), pars.size()};
+    }
+    inline zpc_hashtable_view view(HashTable<i32, 3, int> &t) {
+      return zpc_hashtable_view{(int *)t._table.keys.data(), t._table.indices.data(), t._table.status.data(), (int *)t._activeKeys.data(),
+                                (int)t._tableSize, t._cnt.data()};
+    }
+    inline zpc_grids_view view(Grids<f32, 3, 4> &g) {
+      auto &blocks = g.grid(collocated_c).blocks;
+      return zpc_grids_view{(float *)blocks.data(), blocks.size() / 64, 7, g._dx};
+    }
+    /// partition_for_particles: CleanSparsity + ComputeSparsity + EnlargeSparsity{0, 2} (simulation/sparsity/SparsityOp.hpp:41-112)
+    inline void partition_for_particles(const B200ExecutionPolicy &pol, HashTable<i32, 3, int> &table, Particles<f32, 3> &pars, float dx,
+                                        const source_location &loc = source_location::current()) {
+      zpc_port x{(void *)pars.getAttrAddress("x"), 0, 0, 0, 3};
+      pol.b200TwoPhase("zpcb200_partition_build", loc, zpcb200_partition_build, x, (size_t)pars.size(), dx, view(table), 0, 2, (int *)nullptr);
+    }
+    inline void clean_grid_blocks(const B200ExecutionPolicy &pol, HashTable<i32, 3, int> &table, Grids<f32, 3, 4> &grids,
+                                  const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_clean_grid(view(grids), table._cnt.data(), pol.b200Stream()), "zpcb200_clean_grid", loc);
+    }
+    inline void p2g(const B200ExecutionPolicy &pol, float dt, const FixedCorotatedConfig &model, Particles<f32, 3> &pars,
+                    HashTable<i32, 3, int> &table, Grids<f32, 3, 4> &grids, const source_location &loc = source_location::current()) {
+      zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
+      pol.b200Done(zpcb200_p2g_apic_fcr(view(pars), view(table), view(grids), dt, m, pol.b200Stream()), "zpcb200_p2g_apic_fcr", loc);
+    }
+    /// ComputeGridBlockVelocity{cuda_c, wrapv<apic>{}, grids, dt, gravity, maxVel}; mode 1 adds rhs first (explicit update)
+    inline void compute_grid_block_velocity(const B200ExecutionPolicy &pol, Grids<f32, 3, 4> &grids, HashTable<i32, 3, int> &table, float dt,
+                                            float gravity, float *maxVel, int mode = 0, const source_location &loc = source_location::current()) {
+      const float extf[3] = {0.f, gravity, 0.f};
+      pol.b200Done(zpcb200_grid_update(view(grids), table._cnt.data(), dt, extf, mode, maxVel, pol.b200Stream()), "zpcb200_grid_update", loc);
+    }
+    inline void g2p(const B200ExecutionPolicy &pol, float dt, Grids<f32, 3, 4> &grids, HashTable<i32, 3, int> &table, Particles<f32, 3> &pars,
+                    const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_g2p_apic(view(pars), view(table), view(grids), dt, pol.b200Stream()), "zpcb200_g2p_apic", loc);
+    }
+  }  // namespace b200
+}  // namespace zs

@@ -40,7 +40,7 @@ def build_ref_cuda():
     """(Re)build oracle/_ref/libzpcref_cuda.so — the reference's own CUDA path, compiled for sm_100 — when /root/reference is
     mounted and the library is older than its driver; no-op otherwise (it can only RUN on a GPU box)."""
     so = os.path.join(HERE, "_ref", "libzpcref_cuda.so")
-    srcs = [os.path.join(HERE, f) for f in ("ref_driver_cuda.cu", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("ref_driver_cuda.cu", "Makefile", "../include/zpcb200/zs_overlay.cuh", "../include/zpcb200.h")]
     if os.path.isdir("/root/reference/include/zensim") and not (
             os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(f) for f in srcs)):
         subprocess.check_call(["make", "-s", "-C", HERE, "-j8", "refcuda"])

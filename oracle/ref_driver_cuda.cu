@@ -25,6 +25,8 @@
 #include "zensim/simulation/transfer/G2P.hpp"
 #include "zensim/simulation/transfer/P2G.hpp"
 
+#include "zpcb200/zs_overlay.cuh"  // the binding of INTEGRATION.md, compiled against the headers above
+
 using namespace zs;
 
 namespace {
@@ -145,5 +147,56 @@ void zpcrefcuda_reduce_sum_i32(const int *in, int *out, size_t n) {
   auto pol = cuda_exec().device(0);
   int *first = const_cast<int *>(in), *last = first + n;
   reduce(pol, first, last, out, 0);
+}
+
+/// ---- the same composed substep and primitives through the overlay (include/zpcb200/zs_overlay.cuh): the reference's containers,
+/// this repository's kernels.  What a zpc application runs after replacing cuda_exec() by b200_exec() and the five functor launches.
+int zpcrefcuda_overlay_partition(void *h) {
+  auto &s = *(RefMpmCuda *)h;
+  auto pol = b200_exec();
+  b200::partition_for_particles(pol, s.table, s.pars, s.dx);
+  s.nblocks = s.table.size();
+  return s.nblocks;
+}
+void zpcrefcuda_overlay_clean_grid(void *h) {
+  auto &s = *(RefMpmCuda *)h;
+  b200::clean_grid_blocks(b200_exec(), s.table, s.grids);
+}
+void zpcrefcuda_overlay_p2g(void *h, float dt, float E, float nu, float volume) {
+  auto &s = *(RefMpmCuda *)h;
+  FixedCorotatedConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.volume = volume;
+  b200::p2g(b200_exec(), dt, model, s.pars, s.table, s.grids);
+}
+float zpcrefcuda_overlay_grid_update(void *h, float dt, float gravity, int mode) {
+  auto &s = *(RefMpmCuda *)h;
+  s.maxVel.setVal(0.f);
+  b200::compute_grid_block_velocity(b200_exec(), s.grids, s.table, dt, gravity, s.maxVel.data(), mode);
+  return s.maxVel.getVal();
+}
+void zpcrefcuda_overlay_g2p(void *h, float dt) {
+  auto &s = *(RefMpmCuda *)h;
+  b200::g2p(b200_exec(), dt, s.grids, s.table, s.pars);
+}
+/// generic code templated on the policy, unchanged: zs::radix_sort_pair / exclusive_scan / reduce with b200_exec() — host arrays
+/// in, host arrays out (zs::Vector on the device in between, so the Vector-iterator path of the overlay is the one exercised)
+void zpcrefcuda_overlay_prims(const unsigned *keys, const int *vals, unsigned *keysOut, int *valsOut, int *scanOut, int *sumOut, int *maxOut,
+                              size_t n) {
+  auto pol = b200_exec();
+  Vector<unsigned> k{n, memsrc_e::device, 0}, ko{n, memsrc_e::device, 0};
+  Vector<int> v{n, memsrc_e::device, 0}, vo{n, memsrc_e::device, 0}, sc{n, memsrc_e::device, 0}, red{2, memsrc_e::device, 0};
+  h2d(k.data(), keys, sizeof(unsigned) * n);
+  h2d(v.data(), vals, sizeof(int) * n);
+  radix_sort_pair(pol, k.begin(), v.begin(), ko.begin(), vo.begin(), (std::ptrdiff_t)n);
+  exclusive_scan(pol, v.begin(), v.end(), sc.begin());
+  reduce(pol, v.begin(), v.end(), red.begin(), 0);
+  reduce(pol, v.begin(), v.end(), red.begin() + 1, detail::deduce_numeric_lowest<int>(), getmax<int>{});
+  d2h(keysOut, ko.data(), sizeof(unsigned) * n);
+  d2h(valsOut, vo.data(), sizeof(int) * n);
+  d2h(scanOut, sc.data(), sizeof(int) * n);
+  d2h(sumOut, red.data(), sizeof(int));
+  d2h(maxOut, red.data() + 1, sizeof(int));
 }
 }

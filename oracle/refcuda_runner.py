@@ -6,7 +6,9 @@ test session or a bench run down with it.
 
   python -m oracle.refcuda_runner substep IN.npz OUT.npz   # x v m C F dx dt E nu volume gravity mode -> grids + particles
   python -m oracle.refcuda_runner bench G S STEPS WARMUP    # elastic cube of S^3 cells in a G^3 domain; prints one JSON line
-  python -m oracle.refcuda_runner prims N                   # radix_sort_pair / exclusive_scan / reduce through CudaExecutionPolicy
+  python -m oracle.refcuda_runner overlay IN.npz OUT.npz   # the same substep on the reference's containers through
+                                                            # include/zpcb200/zs_overlay.cuh (b200_exec() + zs::b200::* launches)
+  python -m oracle.refcuda_runner prims N OUT.npz           # zs::radix_sort_pair / exclusive_scan / reduce with b200_exec()
 """
 import ctypes as C
 import json
@@ -35,9 +37,21 @@ class RefCuda:
     def available():
         return os.path.exists(SO)
 
-    def substep(self, P, dt, E, nu, gravity, mode, steps=1, collect=True, expected_blocks=None):
+    def substep(self, P, dt, E, nu, gravity, mode, steps=1, collect=True, expected_blocks=None, overlay=False):
         n, dx = P["x"].shape[0], float(P["dx"])
         L = self.L
+        if overlay:   # same containers, this repository's kernels behind the reference-side binding
+            class _O:
+                pass
+            O = _O()
+            for name in ("partition", "clean_grid", "p2g", "grid_update", "g2p"):
+                setattr(O, "zpcrefcuda_mpm_" + name, getattr(L, "zpcrefcuda_overlay_" + name))
+            O.zpcrefcuda_mpm_partition.restype = C.c_int
+            O.zpcrefcuda_mpm_grid_update.restype = C.c_float
+            for name in ("create", "set_particles", "get_keys", "get_grid", "get_particles", "destroy"):
+                setattr(O, "zpcrefcuda_mpm_" + name, getattr(L, "zpcrefcuda_mpm_" + name))
+            O.zpcrefcuda_sync = L.zpcrefcuda_sync
+            L = O
         h = C.c_void_p(L.zpcrefcuda_mpm_create(C.c_int(n), C.c_float(dx), C.c_int(expected_blocks or max(n // 8, 64))))
         L.zpcrefcuda_mpm_set_particles(h, _p(P["x"]), _p(P["v"]), _p(P["m"]), _p(P["C"]), _p(P["F"]))
         out = {}
@@ -79,6 +93,21 @@ def main(argv):
         P["dx"], P["volume"] = float(z["dx"]), float(z["volume"])
         out = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), int(z["mode"]))
         np.savez(argv[2], **out)
+    elif argv[0] == "overlay":
+        z = np.load(argv[1])
+        P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}
+        P["dx"], P["volume"] = float(z["dx"]), float(z["volume"])
+        out = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), int(z["mode"]), overlay=True)
+        np.savez(argv[2], **out)
+    elif argv[0] == "prims":
+        n = int(argv[1])
+        rs = np.random.RandomState(12345)
+        keys = rs.randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+        vals = rs.randint(-1000, 1000, size=n).astype(np.int32)
+        ko, vo, sc = np.empty_like(keys), np.empty_like(vals), np.empty_like(vals)
+        sm, mx = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        r.L.zpcrefcuda_overlay_prims(_p(keys), _p(vals), _p(ko), _p(vo), _p(sc), _p(sm), _p(mx), C.c_size_t(n))
+        np.savez(argv[2], keys=keys, vals=vals, keys_out=ko, vals_out=vo, scan=sc, sum=sm, max=mx)
     elif argv[0] == "bench":
         from zpc_b200 import synth
         G, s, steps, warmup = (int(a) for a in argv[1:5])

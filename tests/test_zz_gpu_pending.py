@@ -368,6 +368,47 @@ def test_g2p2g_matches_the_restated_functor(oracle, model):
     assert np.array_equal(pars.x.cpu().numpy(), P["x"])
 
 
+def test_overlay_on_the_references_containers(oracle, tmp_path):
+    """include/zpcb200/zs_overlay.cuh compiled against the unmodified reference headers (oracle/_ref/libzpcref_cuda.so): the
+    reference's own Particles / HashTable / Grids on the device, the composed substep once through the reference's functors on
+    cuda_exec() and once through b200_exec() + zs::b200::* — same block set, grids and particles within the parity rule; and
+    zs::radix_sort_pair / exclusive_scan / reduce (generic code templated on the policy) with b200_exec(), index-exact."""
+    import subprocess
+    import sys
+    from oracle.refcuda_runner import RefCuda
+    from tests.parity import GRID_RTOL
+    if not RefCuda.available():
+        pytest.skip("oracle/_ref/libzpcref_cuda.so not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    P = synth.elastic_cube(8, 32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=11)
+    fin = str(tmp_path / "in.npz")
+    np.savez(fin, dt=synth.DT, E=E, nu=NU, gravity=synth.GRAVITY, mode=1, **P)
+    outs = {}
+    for mode in ("substep", "overlay"):
+        fout = str(tmp_path / (mode + ".npz"))
+        r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", mode, fin, fout], cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, mode + ": " + r.stdout + r.stderr
+        outs[mode] = np.load(fout)
+    a, b = outs["substep"], outs["overlay"]
+    ka, ga = grid_by_key(a["active_keys"], a["grid_p2g"])
+    kb, gb = grid_by_key(b["active_keys"], b["grid_p2g"])
+    assert np.array_equal(ka, kb) and np.array_equal(b["active_keys"], kb)          # the overlay's numbering is key-ordered
+    check_channels(gb, ga, 1, "overlay P2G vs reference functors", GRID_RTOL)
+    _, ua = grid_by_key(a["active_keys"], a["grid_upd"])
+    _, ub = grid_by_key(b["active_keys"], b["grid_upd"])
+    check_channels(ub[:, 1:4], ua[:, 1:4], 1, "overlay grid update", RTOL_STRESS)
+    assert abs(float(a["max_vel_sqr"]) - float(b["max_vel_sqr"])) <= RTOL_STRESS * float(a["max_vel_sqr"])
+    check_particles({k: b[k] for k in "xvCF"}, {k: a[k] for k in "xvCF"}, P["dx"], "overlay G2P vs reference functors", rtol=3e-5)
+    fout = str(tmp_path / "prims.npz")
+    r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "prims", "100003", fout], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    z = np.load(fout)
+    ek, ev = oracle.radix_sort_pair("u32", z["keys"], z["vals"])
+    assert np.array_equal(z["keys_out"], ek) and np.array_equal(z["vals_out"], ev)
+    assert np.array_equal(z["scan"], oracle.scan("exclusive", "i32", z["vals"]))
+    assert int(z["sum"][0]) == int(z["vals"].sum()) and int(z["max"][0]) == int(z["vals"].max())
+
+
 # last: a failed stream capture could leave the process unable to launch — nothing runs after it
 def test_graph_replay_equals_eager_substeps():
     """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same
