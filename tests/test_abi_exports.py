@@ -192,6 +192,26 @@ def test_g2p2g_entry_checks_its_arguments():
     assert L.zpcb200_g2p2g_apic(some, tv, f(0.1), f(1e-4), 3, ctypes.byref(nacc), ctypes.c_void_p(8), ctypes.c_void_p(8), None) == -1   # no logJp
 
 
+def test_overlay_binds_the_reference_headers_to_the_library():
+    """oracle/_ref/libzpcref_cuda.so = the unmodified reference (CUDA backend) + include/zpcb200/zs_overlay.cuh.  It cannot be loaded
+    without a driver, but its dynamic symbol table shows what the overlay resolved to: generic zs::radix_sort_pair / exclusive_scan /
+    reduce calls with b200_exec() and the five functor launches must reference zpcb200_* entries that libzpcb200.so exports."""
+    import subprocess
+    so = os.path.join(ROOT, "oracle", "_ref", "libzpcref_cuda.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libzpcref_cuda.so not built (make -C oracle refcuda where /root/reference is mounted)")
+    from zpc_b200 import build
+    lib = ctypes.CDLL(build.build())
+    out = subprocess.check_output(["nm", "-D", so], text=True)
+    undefined = {l.split()[-1] for l in out.splitlines() if " U zpcb200_" in l}
+    want = {"zpcb200_partition_build", "zpcb200_clean_grid", "zpcb200_p2g_apic_fcr", "zpcb200_grid_update", "zpcb200_g2p_apic",
+            "zpcb200_radix_sort_pair_u32", "zpcb200_exclusive_scan_sum_i32", "zpcb200_reduce_sum_i32", "zpcb200_reduce_max_i32"}
+    assert want <= undefined, want - undefined
+    assert all(hasattr(lib, n) for n in undefined)
+    defined = {l.split()[-1] for l in out.splitlines() if " T zpcrefcuda_" in l}
+    assert {"zpcrefcuda_mpm_p2g", "zpcrefcuda_overlay_p2g", "zpcrefcuda_overlay_prims"} <= defined
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "zpc_b200")):
         for f in files:
