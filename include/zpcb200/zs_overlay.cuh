@@ -20,6 +20,8 @@
 #include "zensim/container/HashTable.hpp"
 #include "zensim/container/Vector.hpp"
 #include "zensim/cuda/execution/ExecutionPolicy.cuh"
+#include "zensim/geometry/AnalyticLevelSet.h"
+#include "zensim/geometry/Collider.h"
 #include "zensim/geometry/Structure.hpp"
 #include "zensim/geometry/Structurefree.hpp"
 #include "zensim/physics/ConstitutiveModel.hpp"
@@ -198,6 +200,58 @@ namespace zs {
                     HashTable<i32, 3, int> &table, Grids<f32, 3, 4> &grids, const source_location &loc = source_location::current()) {
       zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
       pol.b200Done(zpcb200_p2g_apic_fcr(view(pars), view(table), view(grids), dt, m, pol.b200Stream()), "zpcb200_p2g_apic_fcr", loc);
+    }
+    /// the other constitutive models of P2GTransfer (P2G.hpp:66-102): same call, the model type selects the entry
+    inline void p2g(const B200ExecutionPolicy &pol, float dt, const VonMisesFixedCorotatedConfig &model, Particles<f32, 3> &pars,
+                    HashTable<i32, 3, int> &table, Grids<f32, 3, 4> &grids, const source_location &loc = source_location::current()) {
+      zpc_vonmises_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu, model.yieldStress};
+      pol.b200Done(zpcb200_p2g_apic_vonmises(view(pars), view(table), view(grids), dt, m, pol.b200Stream()), "zpcb200_p2g_apic_vonmises", loc);
+    }
+    inline void p2g(const B200ExecutionPolicy &pol, float dt, const EquationOfStateConfig &model, Particles<f32, 3> &pars,
+                    HashTable<i32, 3, int> &table, Grids<f32, 3, 4> &grids, const source_location &loc = source_location::current()) {
+      zpc_equation_of_state m{model.rho, model.volume, model.dim, model.bulk, model.gamma, model.viscosity};
+      pol.b200Done(zpcb200_p2g_apic_eos(view(pars), view(table), view(grids), dt, m, pol.b200Stream()), "zpcb200_p2g_apic_eos", loc);
+    }
+    inline void p2g(const B200ExecutionPolicy &pol, float dt, const DruckerPragerConfig &model, Particles<f32, 3> &pars,
+                    HashTable<i32, 3, int> &table, Grids<f32, 3, 4> &grids, const source_location &loc = source_location::current()) {
+      zpc_drucker_prager m{model.rho, model.volume, model.dim, model.E, model.nu, model.logJp0, model.fa, model.cohesion, model.beta,
+                           model.volumeCorrection ? 1 : 0, model.yieldSurface};
+      pol.b200Done(zpcb200_p2g_apic_drucker_prager(view(pars), view(table), view(grids), dt, m, pol.b200Stream()), "zpcb200_p2g_apic_drucker_prager", loc);
+    }
+    inline void p2g(const B200ExecutionPolicy &pol, float dt, const NACCConfig &model, Particles<f32, 3> &pars, HashTable<i32, 3, int> &table,
+                    Grids<f32, 3, 4> &grids, const source_location &loc = source_location::current()) {
+      zpc_nacc m{model.rho, model.volume, model.dim, model.E, model.nu, model.logJp0, model.fa, model.xi, model.beta, model.hardeningOn ? 1 : 0};
+      pol.b200Done(zpcb200_p2g_apic_nacc(view(pars), view(table), view(grids), dt, m, pol.b200Stream()), "zpcb200_p2g_apic_nacc", loc);
+    }
+    /// G2PTransfer with EquationOfStateConfig (G2P.hpp:69-73): J instead of F
+    inline void g2p(const B200ExecutionPolicy &pol, float dt, const EquationOfStateConfig &, Grids<f32, 3, 4> &grids, HashTable<i32, 3, int> &table,
+                    Particles<f32, 3> &pars, const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_g2p_apic_eos(view(pars), view(table), view(grids), dt, pol.b200Stream()), "zpcb200_g2p_apic_eos", loc);
+    }
+    /// Collider<AnalyticLevelSet<Plane | Sphere | Cuboid>> with its rigid motion -> zpc_collider (geometry/Collider.h:10-24, 136-143)
+    template <analytic_geometry_e geom> zpc_collider view(const Collider<AnalyticLevelSet<geom, f32, 3>> &col) {
+      static_assert(geom == analytic_geometry_e::Plane || geom == analytic_geometry_e::Sphere || geom == analytic_geometry_e::Cuboid,
+                    "plane, sphere and cuboid colliders are built");
+      zpc_collider c{};
+      c.type = col.type == collider_e::Sticky ? ZPC_COLLIDER_STICKY : (col.type == collider_e::Slip ? ZPC_COLLIDER_SLIP : ZPC_COLLIDER_SEPARATE);
+      for (int d = 0; d < 3; ++d) {
+        if constexpr (geom == analytic_geometry_e::Plane) { c.geometry = ZPC_GEOM_PLANE; c.origin[d] = col.levelset._origin[d]; c.normal[d] = col.levelset._normal[d]; }
+        else if constexpr (geom == analytic_geometry_e::Sphere) { c.geometry = ZPC_GEOM_SPHERE; c.origin[d] = col.levelset._center[d]; c.normal[d] = d == 0 ? col.levelset._radius : 0.f; }
+        else { c.geometry = ZPC_GEOM_CUBOID; c.origin[d] = col.levelset._min[d]; c.normal[d] = col.levelset._max[d]; }
+        c.b[d] = col.b[d];
+        c.dbdt[d] = col.dbdt[d];
+        c.omega[d] = col.omega.omega[d];
+        for (int e = 0; e < 3; ++e) c.R[3 * d + e] = col.R(d, e);
+      }
+      c.s = col.s;
+      c.dsdt = col.dsdt;
+      return c;
+    }
+    /// pol(Collapse{nb, 64}, ApplyBoundaryConditionOnGridBlocks{cuda_c, collider, table, grids}) (GridOp.hpp:112-164)
+    template <analytic_geometry_e geom>
+    void apply_boundary_condition(const B200ExecutionPolicy &pol, const Collider<AnalyticLevelSet<geom, f32, 3>> &col, HashTable<i32, 3, int> &table,
+                                  Grids<f32, 3, 4> &grids, const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_apply_boundary(view(grids), view(table), view(col), pol.b200Stream()), "zpcb200_apply_boundary", loc);
     }
     /// ComputeGridBlockVelocity{cuda_c, wrapv<apic>{}, grids, dt, gravity, maxVel}; mode 1 adds rhs first (explicit update)
     inline void compute_grid_block_velocity(const B200ExecutionPolicy &pol, Grids<f32, 3, 4> &grids, HashTable<i32, 3, int> &table, float dt,

@@ -180,6 +180,23 @@ void zpcrefcuda_overlay_g2p(void *h, float dt) {
   auto &s = *(RefMpmCuda *)h;
   b200::g2p(b200_exec(), dt, s.grids, s.table, s.pars);
 }
+/// compile-time coverage of the remaining overlay launches (other constitutive models, analytic colliders); run by no test yet
+void zpcrefcuda_overlay_models_and_colliders(void *h, float dt) {
+  auto &s = *(RefMpmCuda *)h;
+  auto pol = b200_exec();
+  using TV = vec<float, 3>;
+  b200::p2g(pol, dt, VonMisesFixedCorotatedConfig{}, s.pars, s.table, s.grids);
+  b200::p2g(pol, dt, EquationOfStateConfig{}, s.pars, s.table, s.grids);
+  b200::p2g(pol, dt, DruckerPragerConfig{}, s.pars, s.table, s.grids);
+  b200::p2g(pol, dt, NACCConfig{}, s.pars, s.table, s.grids);
+  b200::g2p(pol, dt, EquationOfStateConfig{}, s.grids, s.table, s.pars);
+  Collider plane{AnalyticLevelSet<analytic_geometry_e::Plane, float, 3>{TV{0.f, 0.1f, 0.f}, TV{0.f, 1.f, 0.f}}, collider_e::Separate};
+  Collider sphere{AnalyticLevelSet<analytic_geometry_e::Sphere, float, 3>{TV{0.3f, 0.3f, 0.3f}, 0.1f}, collider_e::Slip};
+  Collider box{AnalyticLevelSet<analytic_geometry_e::Cuboid, float, 3>{TV{0.2f, 0.2f, 0.2f}, TV{0.3f, 0.3f, 0.4f}}, collider_e::Sticky};
+  b200::apply_boundary_condition(pol, plane, s.table, s.grids);
+  b200::apply_boundary_condition(pol, sphere, s.table, s.grids);
+  b200::apply_boundary_condition(pol, box, s.table, s.grids);
+}
 /// generic code templated on the policy, unchanged: zs::radix_sort_pair / exclusive_scan / reduce with b200_exec() — host arrays
 /// in, host arrays out (zs::Vector on the device in between, so the Vector-iterator path of the overlay is the one exercised)
 void zpcrefcuda_overlay_prims(const unsigned *keys, const int *vals, unsigned *keysOut, int *valsOut, int *scanOut, int *sumOut, int *maxOut,
