@@ -25,6 +25,8 @@
 #include "zensim/simulation/transfer/G2P.hpp"
 #include "zensim/simulation/transfer/P2G.hpp"
 
+#include "zensim/container/Bvh.hpp"
+
 #include "zpcb200/zs_overlay.cuh"  // the binding of INTEGRATION.md, compiled against the headers above
 
 using namespace zs;
@@ -215,5 +217,32 @@ void zpcrefcuda_overlay_prims(const unsigned *keys, const int *vals, unsigned *k
   d2h(scanOut, sc.data(), sizeof(int) * n);
   d2h(sumOut, red.data(), sizeof(int));
   d2h(maxOut, red.data() + 1, sizeof(int));
+}
+
+/// The reference's own LBvh<3,int,f32>::build (container/Bvh.hpp:835-1000), unchanged, on the device — with cuda_exec() (use_b200 = 0)
+/// or with b200_exec() (use_b200 = 1): the template is generic in the policy, so its radix_sort_pair and exclusive_scan then run in
+/// libzpcb200 while its own functors keep launching through the inherited operator().  Host arrays in / out; returns numNodes.
+int zpcrefcuda_lbvh_build(int use_b200, int n, const float *bvs, float *orderedBvs, int *auxIndices, int *parents, int *levels, int *leafInds) {
+  using Bvh = LBvh<3, int, float>;
+  using Box = typename Bvh::Box;
+  Vector<Box> prims{(size_t)n, memsrc_e::device, 0};
+  h2d((void *)prims.data(), bvs, sizeof(float) * 6 * n);
+  Bvh bvh{};
+  if (use_b200) {
+    auto pol = b200_exec();
+    bvh.build(pol, prims, true_c);
+  } else {
+    auto pol = cuda_exec().device(0);
+    bvh.build(pol, prims, true_c);
+  }
+  const int nn = (int)bvh.getNumNodes();
+  d2h(orderedBvs, (const void *)bvh.orderedBvs.data(), sizeof(float) * 6 * nn);
+  d2h(auxIndices, bvh.auxIndices.data(), sizeof(int) * bvh.auxIndices.size());
+  if (n > 2) {
+    d2h(parents, bvh.parents.data(), sizeof(int) * nn);
+    d2h(levels, bvh.levels.data(), sizeof(int) * nn);
+  }
+  d2h(leafInds, bvh.leafInds.data(), sizeof(int) * n);
+  return nn;
 }
 }

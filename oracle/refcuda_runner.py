@@ -8,6 +8,7 @@ test session or a bench run down with it.
   python -m oracle.refcuda_runner bench G S STEPS WARMUP    # elastic cube of S^3 cells in a G^3 domain; prints one JSON line
   python -m oracle.refcuda_runner overlay IN.npz OUT.npz   # the same substep on the reference's containers through
                                                             # include/zpcb200/zs_overlay.cuh (b200_exec() + zs::b200::* launches)
+  python -m oracle.refcuda_runner lbvh N OUT.npz            # the reference's own LBvh::build on cuda_exec() and on b200_exec()
   python -m oracle.refcuda_runner prims N OUT.npz           # zs::radix_sort_pair / exclusive_scan / reduce with b200_exec()
 """
 import ctypes as C
@@ -98,6 +99,22 @@ def main(argv):
         P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}
         P["dx"], P["volume"] = float(z["dx"]), float(z["volume"])
         out = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), int(z["mode"]), overlay=True)
+        np.savez(argv[2], **out)
+    elif argv[0] == "lbvh":
+        n = int(argv[1])
+        rs = np.random.RandomState(77)
+        c = rs.uniform(0, 1, (n, 3)).astype(np.float32); hw = rs.uniform(0.001, 0.03, (n, 3)).astype(np.float32)
+        c[n // 3: 2 * n // 3] = c[n // 3]
+        bvs = np.ascontiguousarray(np.concatenate([c - hw, c + hw], 1), np.float32)
+        out = dict(bvs=bvs)
+        r.L.zpcrefcuda_lbvh_build.restype = C.c_int
+        for tag, use in (("cuda", 0), ("b200", 1)):
+            nn = 2 * n - 1
+            ob = np.zeros((nn, 6), np.float32); aux = np.full(nn, -7, np.int32); par = np.full(nn, -7, np.int32)
+            lev = np.full(nn, -7, np.int32); li = np.full(n, -7, np.int32)
+            got = r.L.zpcrefcuda_lbvh_build(C.c_int(use), C.c_int(n), _p(bvs), _p(ob), _p(aux), _p(par), _p(lev), _p(li))
+            assert got == nn
+            out.update({tag + "_orderedBvs": ob, tag + "_auxIndices": aux, tag + "_parents": par, tag + "_levels": lev, tag + "_leafInds": li})
         np.savez(argv[2], **out)
     elif argv[0] == "prims":
         n = int(argv[1])

@@ -409,6 +409,32 @@ def test_overlay_on_the_references_containers(oracle, tmp_path):
     assert int(z["sum"][0]) == int(z["vals"].sum()) and int(z["max"][0]) == int(z["vals"].max())
 
 
+def test_references_own_lbvh_build_runs_on_b200_exec(oracle, tmp_path):
+    """LBvh<3,int,f32>::build of the reference, UNCHANGED (it is a template in the policy), once with cuda_exec() and once with
+    b200_exec(): its radix_sort_pair / exclusive_scan then run in libzpcb200, its own functors through the inherited launcher.  Both
+    trees and this repository's native zpcb200_lbvh_build equal the oracle's, array for array."""
+    import subprocess
+    import sys
+    from oracle.refcuda_runner import RefCuda
+    from zpc_b200 import api
+    if not RefCuda.available():
+        pytest.skip("oracle/_ref/libzpcref_cuda.so not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fout = str(tmp_path / "lbvh.npz")
+    r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "lbvh", "20000", fout], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    z = np.load(fout)
+    A = oracle.lbvh_build(z["bvs"])
+    native = api.LBvh().build(torch.from_numpy(z["bvs"]).cuda())
+    for k in ("auxIndices", "parents", "levels", "leafInds", "orderedBvs"):
+        want = A[k].view(np.uint32) if A[k].dtype == np.float32 else A[k]
+        for tag in ("cuda", "b200"):
+            got = z[tag + "_" + k]
+            assert np.array_equal(got.view(np.uint32) if got.dtype == np.float32 else got, want), (tag, k)
+        got = getattr(native, k).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32) if got.dtype == np.float32 else got, want), ("native", k)
+
+
 # last: a failed stream capture could leave the process unable to launch — nothing runs after it
 def test_graph_replay_equals_eager_substeps():
     """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same
