@@ -25,20 +25,25 @@
 #include "zensim/geometry/Structure.hpp"
 #include "zensim/geometry/Structurefree.hpp"
 #include "zensim/physics/ConstitutiveModel.hpp"
+#include "zensim/py_interop/GenericIterator.hpp"
 #include "zpcb200.h"
 
 namespace zs {
 
   namespace b200_detail {
-    template <class It> struct raw_iter {  // raw pointer or zs::Vector iterator -> element pointer; anything else: no fast path
+    /// iterator -> zpc_port: raw pointers, zs::Vector iterators (contiguous) and the reference's aosoa_iterator<T, 1> — TileVector
+    /// channels as its own C layer passes them (py_interop/GenericIterator.hpp:16-98; the port struct is the same five fields)
+    template <class It> struct raw_iter {
       using I = remove_cvref_t<It>;
-      template <class T> static constexpr bool is_vector_iter
-          = is_same_v<I, decltype(zs::begin(declval<Vector<T> &>()))> || is_same_v<I, decltype(zs::begin(declval<const Vector<T> &>()))>;
-      using value_type = typename std::iterator_traits<I>::value_type;
-      static constexpr bool ok = std::is_pointer_v<I> || is_vector_iter<remove_cv_t<value_type>>;
-      static auto get(I it) {
-        if constexpr (std::is_pointer_v<I>) return it;
-        else return it.operator->();
+      using value_type = remove_cv_t<typename std::iterator_traits<I>::value_type>;
+      static constexpr bool is_vector_iter
+          = is_same_v<I, decltype(zs::begin(declval<Vector<value_type> &>()))> || is_same_v<I, decltype(zs::begin(declval<const Vector<value_type> &>()))>;
+      static constexpr bool is_aosoa = std::is_base_of_v<aosoa_iterator<value_type, 1>, I> || std::is_base_of_v<aosoa_iterator<const value_type, 1>, I>;
+      static constexpr bool ok = std::is_pointer_v<I> || is_vector_iter || is_aosoa;
+      static zpc_port get(I it) {
+        if constexpr (std::is_pointer_v<I>) return zpc_port{(void *)it, 0, 0, 0, 1};
+        else if constexpr (is_aosoa) return zpc_port{(void *)it.base, it.idx, it.numTileBits, it.tileMask, it.numChns};
+        else return zpc_port{(void *)it.operator->(), 0, 0, 0, 1};
       }
     };
     template <class T> constexpr int kind_of() {  // index into the per-type entry tables below, -1 = unsupported
@@ -71,7 +76,7 @@ namespace zs {
       else if constexpr (is_same_v<O, getmax<T>> || is_same_v<O, getmax<void>>) return 2;
       else return -1;
     }
-    inline zpc_port port_of(const void *p) { return zpc_port{const_cast<void *>(p), 0, 0, 0, 1}; }
+    inline zpc_port port_of(zpc_port p) { return p; }
   }  // namespace b200_detail
 
   struct B200ExecutionPolicy : CudaExecutionPolicy {

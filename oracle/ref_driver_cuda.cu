@@ -245,4 +245,26 @@ int zpcrefcuda_lbvh_build(int use_b200, int n, const float *bvs, float *orderedB
   d2h(leafInds, bvh.leafInds.data(), sizeof(int) * n);
   return nn;
 }
+
+/// TileVector channels through the overlay, passed the way the reference's own C layer passes them (LegacyIterator<aosoa_iterator<T, 1>>,
+/// py_interop/GenericIterator.hpp): data = an AoSoA buffer of `ntiles` tiles x nch channels x 32 lanes (host, int); channel chn of the first
+/// n elements is scanned into channel chn of `out` (same layout) and reduced (sum) into *sum.
+void zpcrefcuda_overlay_aosoa(const int *data, int ntiles, int nch, int chn, size_t n, int *out, int *sum) {
+  const size_t total = (size_t)ntiles * nch * 32;
+  Vector<int> buf{total, memsrc_e::device, 0}, obuf{total, memsrc_e::device, 0}, red{1, memsrc_e::device, 0};
+  h2d(buf.data(), data, sizeof(int) * total);
+  cudaMemset(obuf.data(), 0, sizeof(int) * total);
+  using It = LegacyIterator<aosoa_iterator<int, 1>>;
+  static_assert(b200_detail::raw_iter<It>::is_aosoa && b200_detail::raw_iter<It>::ok, "the overlay takes the reference's aosoa iterators to the library");
+  static_assert(b200_detail::raw_iter<decltype(zs::begin(declval<Vector<int> &>()))>::is_vector_iter && !b200_detail::raw_iter<int *>::is_aosoa, "iterator classification");
+  It first{aosoa_iterator<int, 1>{wrapv<layout_e::aosoa>{}, buf.data(), 0u, 32u, (u32)chn, (u32)nch}};
+  It last{aosoa_iterator<int, 1>{wrapv<layout_e::aosoa>{}, buf.data(), (u32)n, 32u, (u32)chn, (u32)nch}};
+  It ofirst{aosoa_iterator<int, 1>{wrapv<layout_e::aosoa>{}, obuf.data(), 0u, 32u, (u32)chn, (u32)nch}};
+  It rfirst{aosoa_iterator<int, 1>{wrapv<layout_e::aos>{}, red.data(), 0u}};
+  auto pol = b200_exec();
+  exclusive_scan(pol, first, last, ofirst);
+  reduce(pol, first, last, rfirst, 0);
+  d2h(out, obuf.data(), sizeof(int) * total);
+  d2h(sum, red.data(), sizeof(int));
+}
 }

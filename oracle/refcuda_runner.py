@@ -124,7 +124,13 @@ def main(argv):
         ko, vo, sc = np.empty_like(keys), np.empty_like(vals), np.empty_like(vals)
         sm, mx = np.zeros(1, np.int32), np.zeros(1, np.int32)
         r.L.zpcrefcuda_overlay_prims(_p(keys), _p(vals), _p(ko), _p(vo), _p(sc), _p(sm), _p(mx), C.c_size_t(n))
-        np.savez(argv[2], keys=keys, vals=vals, keys_out=ko, vals_out=vo, scan=sc, sum=sm, max=mx)
+        # a TileVector<int, 32> channel through the reference's aosoa iterators
+        ntiles, nch, chn, na = 41, 3, 1, 41 * 32 - 5
+        tv = rs.randint(-50, 50, size=ntiles * nch * 32).astype(np.int32)
+        tvo, tsum = np.zeros_like(tv), np.zeros(1, np.int32)
+        r.L.zpcrefcuda_overlay_aosoa(_p(tv), C.c_int(ntiles), C.c_int(nch), C.c_int(chn), C.c_size_t(na), _p(tvo), _p(tsum))
+        np.savez(argv[2], keys=keys, vals=vals, keys_out=ko, vals_out=vo, scan=sc, sum=sm, max=mx, tv=tv, tv_scan=tvo, tv_sum=tsum,
+                 tv_shape=np.array([ntiles, nch, chn, na]))
     elif argv[0] == "bench":
         from zpc_b200 import synth
         G, s, steps, warmup = (int(a) for a in argv[1:5])

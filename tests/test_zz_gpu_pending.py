@@ -407,6 +407,13 @@ def test_overlay_on_the_references_containers(oracle, tmp_path):
     assert np.array_equal(z["keys_out"], ek) and np.array_equal(z["vals_out"], ev)
     assert np.array_equal(z["scan"], oracle.scan("exclusive", "i32", z["vals"]))
     assert int(z["sum"][0]) == int(z["vals"].sum()) and int(z["max"][0]) == int(z["vals"].max())
+    # a TileVector channel through the reference's aosoa iterators (the way its own C layer passes them)
+    ntiles, nch, chn, na = (int(v) for v in z["tv_shape"])
+    src = z["tv"].reshape(ntiles, nch, 32)[:, chn, :].reshape(-1)[:na]
+    got = z["tv_scan"].reshape(ntiles, nch, 32)
+    assert np.array_equal(got[:, chn, :].reshape(-1)[:na], np.cumsum(src) - src) and int(z["tv_sum"][0]) == int(src.sum())
+    other = np.delete(got, chn, axis=1)
+    assert not other.any() and not got[:, chn, :].reshape(-1)[na:].any()           # nothing outside the channel range was written
 
 
 def test_references_own_lbvh_build_runs_on_b200_exec(oracle, tmp_path):
