@@ -67,7 +67,7 @@ __global__ void lbvh_refit_kernel(int n, const float *__restrict__ prims, float 
 #pragma unroll
   for (int d = 0; d < 6; ++d) bvs[6 * (size_t)node + d] = prims[6 * (size_t)prim + d];
   node = parents[node];
-  while (node != -1) {
+  for (int guard = 0; node >= 0 && guard < 2 * n; ++guard) {  // a parent chain is at most n - 1 long; the bound keeps garbage finite
     __threadfence();
     if (atomicCAS(&flags[node], 0, 1) == 0) break;
     __threadfence();

@@ -105,6 +105,7 @@ ZPC_HD void supp_topo_leaf(int idx, int n, const int *lOffsets, const int *lPars
                            int *lLcas, int *levels, int *auxIndices, int *leafInds) {
   const int numTrunk = n - 1;
   int depth = lOffsets[idx + 1] - lOffsets[idx];
+  if (depth < 1 || depth > n) return;  // cannot happen on a consistent scan; never walk on garbage
   int dst = lOffsets[idx + 1] - 2;
   int node = lPars[idx], ch = idx + numTrunk, level = 0;
   for (; --depth; node = tPars[node], --dst) {
@@ -150,7 +151,9 @@ ZPC_HD void iter_neighbors(int numLeaves, const float *bvs, const int *auxIndice
   }
   const int numNodes = 2 * numLeaves - 1;
   int node = 0;
-  while (node != -1 && node != numNodes) {
+  // node only moves forward in a well-formed tree (escape indices point past the subtree): the bound turns a corrupted array
+  // into an early exit instead of an endless loop
+  for (int guard = 0; node >= 0 && node < numNodes && guard < numNodes; ++guard) {
     int level = levels[node];
     for (; level; --level, ++node)
       if (!boxes_overlap(bvs + 6 * (size_t)node, bv)) break;
