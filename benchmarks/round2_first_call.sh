@@ -19,3 +19,6 @@ cut -c1-400 gpurun_out/r2_bench.log gpurun_out/r2_refcuda_c2.log gpurun_out/r2_r
 # 5. C5 up to 2^30 keys (BASELINE "1M-1B keys"; round 1 measured up to 2^28)
 python benchmarks/prims_sweep.py --min-log2 20 --max-log2 30 > gpurun_out/r2_prims_sweep.jsonl 2> gpurun_out/r2_prims_sweep.err
 tail -2 gpurun_out/r2_prims_sweep.jsonl | cut -c1-300
+# 6. C5 "vs reference CudaExecutionPolicy": the reference's own policy (CUB underneath, sync(true)) and the same generic calls on b200_exec()
+for lg in 20 22 24 26 28; do python -m oracle.refcuda_runner prims-bench $lg 5; done > gpurun_out/r2_prims_vs_refcuda.jsonl 2> gpurun_out/r2_prims_vs_refcuda.err
+tail -1 gpurun_out/r2_prims_vs_refcuda.jsonl | cut -c1-400

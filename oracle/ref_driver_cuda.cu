@@ -8,7 +8,9 @@
 // G2PTransfer — exactly the composed step of SURVEY §3.1.  Used by tests (parity of libzpcb200.so against the reference's
 // device arithmetic) and by bench.py --impl reference-cuda (informational GPU-vs-GPU baseline).  Needs a GPU to run: the
 // build container can only compile it.
+#include <chrono>
 #include <cstring>
+#include <vector>
 
 #include "zensim/container/HashTable.hpp"
 #include "zensim/container/Vector.hpp"
@@ -266,5 +268,42 @@ void zpcrefcuda_overlay_aosoa(const int *data, int ntiles, int nch, int chn, siz
   reduce(pol, first, last, rfirst, 0);
   d2h(out, obuf.data(), sizeof(int) * total);
   d2h(sum, red.data(), sizeof(int));
+}
+
+/// BASELINE config C5 "GB/s vs reference CudaExecutionPolicy": the reference's radix_sort_pair (u32 keys, i32 values, 32 bits) /
+/// exclusive_scan (i32) / reduce (i32 sum) through cuda_exec() with its defaults (sync(true): every call ends with a stream
+/// synchronisation, ExecutionPolicy.cuh:824), on device-resident zs::Vectors of n elements; wall clock per call, mean of `iters`
+/// after one warm-up each.  use_b200 = 1 times the same generic calls with b200_exec() instead.  ms[0..2] = sort, scan, reduce.
+void zpcrefcuda_prims_bench(int use_b200, size_t n, int iters, double *ms) {
+  Vector<unsigned> k{n, memsrc_e::device, 0}, ko{n, memsrc_e::device, 0};
+  Vector<int> v{n, memsrc_e::device, 0}, vo{n, memsrc_e::device, 0}, red{1, memsrc_e::device, 0};
+  {
+    std::vector<unsigned> hk(n);
+    std::vector<int> hv(n);
+    unsigned x = 12345u;
+    for (size_t i = 0; i < n; ++i) { x = x * 1664525u + 1013904223u; hk[i] = x; hv[i] = (int)(i & 1); }
+    h2d(k.data(), hk.data(), sizeof(unsigned) * n);
+    h2d(v.data(), hv.data(), sizeof(int) * n);
+  }
+  auto run = [&](auto &pol) {
+    auto timeit = [&](auto &&f) {
+      f();
+      cudaDeviceSynchronize();
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int i = 0; i < iters; ++i) f();
+      cudaDeviceSynchronize();
+      return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+    };
+    ms[0] = timeit([&] { radix_sort_pair(pol, k.begin(), v.begin(), ko.begin(), vo.begin(), (std::ptrdiff_t)n); });
+    ms[1] = timeit([&] { exclusive_scan(pol, v.begin(), v.end(), vo.begin()); });
+    ms[2] = timeit([&] { reduce(pol, v.begin(), v.end(), red.begin(), 0); });
+  };
+  if (use_b200) {
+    auto pol = b200_exec();
+    run(pol);
+  } else {
+    auto pol = cuda_exec().device(0);
+    run(pol);
+  }
 }
 }

@@ -9,6 +9,8 @@ test session or a bench run down with it.
   python -m oracle.refcuda_runner overlay IN.npz OUT.npz   # the same substep on the reference's containers through
                                                             # include/zpcb200/zs_overlay.cuh (b200_exec() + zs::b200::* launches)
   python -m oracle.refcuda_runner lbvh N OUT.npz            # the reference's own LBvh::build on cuda_exec() and on b200_exec()
+  python -m oracle.refcuda_runner prims-bench LOG2N ITERS   # C5: the reference's CudaExecutionPolicy primitives (and the same generic
+                                                            # calls on b200_exec()) timed on the GPU; one JSON line
   python -m oracle.refcuda_runner prims N OUT.npz           # zs::radix_sort_pair / exclusive_scan / reduce with b200_exec()
 """
 import ctypes as C
@@ -116,6 +118,16 @@ def main(argv):
             assert got == nn
             out.update({tag + "_orderedBvs": ob, tag + "_auxIndices": aux, tag + "_parents": par, tag + "_levels": lev, tag + "_leafInds": li})
         np.savez(argv[2], **out)
+    elif argv[0] == "prims-bench":
+        lg, iters = int(argv[1]), int(argv[2])
+        n = 1 << lg
+        row = dict(log2n=lg, impl="reference CudaExecutionPolicy (cuda_exec(), CUB underneath) vs the same calls on b200_exec()")
+        for tag, use in (("ref_cuda", 0), ("overlay", 1)):
+            ms = (C.c_double * 3)()
+            r.L.zpcrefcuda_prims_bench(C.c_int(use), C.c_size_t(n), C.c_int(iters), ms)
+            row.update({tag + "_sort_pair_ms": ms[0], tag + "_scan_ms": ms[1], tag + "_reduce_ms": ms[2],
+                        tag + "_sort_pair_gbps": 68 * n / ms[0] / 1e6, tag + "_scan_gbps": 8 * n / ms[1] / 1e6, tag + "_reduce_gbps": 4 * n / ms[2] / 1e6})
+        print(json.dumps(row))
     elif argv[0] == "prims":
         n = int(argv[1])
         rs = np.random.RandomState(12345)
