@@ -1,7 +1,8 @@
 """torchrun --nproc-per-node N tests/dist_check.py : N-GPU sharded substeps against the single-GPU solver on
 the same cloud (rank 0 holds both).  Exit code 0 = parity within the multi-step tolerance.
 ZPC_MIGRATE=1: after half of the substeps every particle is handed to the rank that owns its current home block
-(DistMpmSolver.migrate; ownership = BlockOwnership over shard_by_blocks of the initial cloud) — results must not change."""
+(DistMpmSolver.migrate; ownership = BlockOwnership over shard_by_blocks of the initial cloud) — results must not change.
+ZPC_E2E=1: the substeps go through DistMpmSolver.substep_host (host buffers per rank, AoS kernels) instead."""
 import os
 import sys
 
@@ -30,8 +31,12 @@ def main():
     full["m"] = (full["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)   # identity tag
     c0, c1 = synth.slab_cell_range(s, rank, world)
     P = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
+    e2e = os.environ.get("ZPC_E2E") == "1"
     sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, rebin_every=3,
-                        transport=os.environ.get("ZPC_HALO", "auto"))
+                        transport=os.environ.get("ZPC_HALO", "auto"), layout="aos" if e2e else "binned")
+    if e2e:
+        hin = {k: torch.from_numpy(P[k].copy()).pin_memory() for k in ("x", "v", "m", "C", "F")}
+        hout = {k: torch.empty_like(hin[k]).pin_memory() for k in ("x", "v", "C", "F")}
     ownership = None
     if os.environ.get("ZPC_MIGRATE") == "1":
         from zpc_b200.dist_solver import BlockOwnership, shard_by_blocks
@@ -41,9 +46,15 @@ def main():
         if ownership is not None and i == steps // 2:       # a re-bin boundary (rebin_every = 3, steps = 6)
             moved = sol.migrate(ownership)
             print("rank %d: migrated %d particles away, now holds %d" % (rank, moved, sol.n))
-        sol.substep()
+        if e2e:
+            sol.substep_host(hin, hout)
+            torch.cuda.synchronize()
+            for k in ("x", "v", "C", "F"):
+                hin[k], hout[k] = hout[k], hin[k]
+        else:
+            sol.substep()
     torch.cuda.synchronize()
-    mine = sol.local.particles_host()
+    mine = {k: hin[k].numpy() for k in ("x", "v", "m", "C", "F")} if e2e else sol.local.particles_host()
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     mx = float(sol.max_vel_sqr().item())
