@@ -22,6 +22,7 @@
 #include "zensim/cuda/execution/ExecutionPolicy.cuh"
 #include "zensim/geometry/AnalyticLevelSet.h"
 #include "zensim/geometry/Collider.h"
+#include "zensim/geometry/SparseGrid.hpp"
 #include "zensim/geometry/Structure.hpp"
 #include "zensim/geometry/Structurefree.hpp"
 #include "zensim/physics/ConstitutiveModel.hpp"
@@ -267,6 +268,45 @@ namespace zs {
     inline void g2p(const B200ExecutionPolicy &pol, float dt, Grids<f32, 3, 4> &grids, HashTable<i32, 3, int> &table, Particles<f32, 3> &pars,
                     const source_location &loc = source_location::current()) {
       pol.b200Done(zpcb200_g2p_apic(view(pars), view(table), view(grids), dt, pol.b200Stream()), "zpcb200_g2p_apic", loc);
+    }
+
+    /// ---- the SparseGrid<3, f32, 8> seam (geometry/SparseGrid.hpp:16-188): bht keyed by block origins + TileVector<f32, 512> ----
+    inline zpc_sparsegrid_view view(SparseGrid<3, f32, 8> &sg) {
+      auto &t = sg._table;
+      zpc_sparsegrid_view v{};
+      v.table = zpc_bht_view{(int *)t._table.keys.data(), t._table.indices.data(), t._table.status.data(), (int *)t._activeKeys.data(),
+                             (uint32_t)t._tableSize, (uint32_t)(t._tableSize / 16), t._cnt.data(), t._buildSuccess.data(),
+                             {t._hf0._hashx, t._hf0._hashy, t._hf1._hashx, t._hf1._hashy, t._hf2._hashx, t._hf2._hashy}};
+      v.grid = (float *)sg._grid.data();
+      v.numBlocks = sg._grid.numTiles();
+      v.numChannels = (int)sg.numChannels();
+      const auto m = sg.getIndexToWorldTransformation();
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) v.transform[4 * i + j] = m(i, j);
+      v.background = sg._background;
+      return v;
+    }
+    inline void sg_partition_for_particles(const B200ExecutionPolicy &pol, SparseGrid<3, f32, 8> &sg, Particles<f32, 3> &pars,
+                                           const source_location &loc = source_location::current()) {
+      zpc_port x{(void *)pars.getAttrAddress("x"), 0, 0, 0, 3};
+      pol.b200TwoPhase("zpcb200_sg_partition_build", loc, zpcb200_sg_partition_build, x, (size_t)pars.size(), view(sg), 0, 2, (int *)nullptr);
+    }
+    inline void sg_clean(const B200ExecutionPolicy &pol, SparseGrid<3, f32, 8> &sg, const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_sg_clean(view(sg), pol.b200Stream()), "zpcb200_sg_clean", loc);
+    }
+    inline void sg_p2g(const B200ExecutionPolicy &pol, float dt, const FixedCorotatedConfig &model, Particles<f32, 3> &pars, SparseGrid<3, f32, 8> &sg,
+                       const source_location &loc = source_location::current()) {
+      zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
+      pol.b200Done(zpcb200_sg_p2g_apic_fcr(view(pars), view(sg), dt, m, pol.b200Stream()), "zpcb200_sg_p2g_apic_fcr", loc);
+    }
+    inline void sg_grid_update(const B200ExecutionPolicy &pol, SparseGrid<3, f32, 8> &sg, float dt, float gravity, float *maxVel, int mode = 0,
+                               const source_location &loc = source_location::current()) {
+      const float extf[3] = {0.f, gravity, 0.f};
+      pol.b200Done(zpcb200_sg_grid_update(view(sg), dt, extf, mode, maxVel, pol.b200Stream()), "zpcb200_sg_grid_update", loc);
+    }
+    inline void sg_g2p(const B200ExecutionPolicy &pol, float dt, SparseGrid<3, f32, 8> &sg, Particles<f32, 3> &pars,
+                       const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_sg_g2p_apic(view(pars), view(sg), dt, pol.b200Stream()), "zpcb200_sg_g2p_apic", loc);
     }
   }  // namespace b200
 }  // namespace zs

@@ -306,4 +306,23 @@ void zpcrefcuda_prims_bench(int use_b200, size_t n, int iters, double *ms) {
     run(pol);
   }
 }
+
+/// compile-time coverage of the SparseGrid seam of the overlay: the reference's SparseGrid<3, f32, 8> on the device, one substep through
+/// zs::b200::sg_*; x, v, C, F come back to the host.  (Run by no test yet.)
+void zpcrefcuda_overlay_sparsegrid_substep(void *h, int nblocks, float dt, float E, float nu, float volume, float gravity) {
+  auto &s = *(RefMpmCuda *)h;
+  SparseGrid<3, f32, 8> sg{7, (size_t)nblocks, memsrc_e::device, 0};
+  sg.scale(s.dx);
+  auto pol = b200_exec();
+  FixedCorotatedConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.volume = volume;
+  b200::sg_partition_for_particles(pol, sg, s.pars);
+  b200::sg_clean(pol, sg);
+  b200::sg_p2g(pol, dt, model, s.pars, sg);
+  s.maxVel.setVal(0.f);
+  b200::sg_grid_update(pol, sg, dt, gravity, s.maxVel.data(), 1);
+  b200::sg_g2p(pol, dt, sg, s.pars);
+}
 }
