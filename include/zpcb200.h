@@ -418,6 +418,16 @@ int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view table, zp
  * phase only (P2G.hpp:89-90); G2P is zpcb200_g2p_apic_binned. */
 int zpcb200_p2g_apic_vonmises_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,
                                      float dt, zpc_vonmises_fixed_corotated model, zpc_stream_t stream);
+/* DruckerPragerConfig / NACCConfig on the binned layout: logJp = one float per particle in BIN order (slot i of the bins), read
+ * and written back by the record phase (P2G.hpp:93,101).  The caller permutes it together with the particles:
+ * zpcb200_bin_particles(order_out) / zpcb200_rebin_particles_ordered(order_out) return the permutation (dst slot i <- src
+ * order_out[i]). */
+int zpcb200_p2g_apic_drucker_prager_binned(zpc_bins_view bins, float *logJp, zpc_hashtable_view table, zpc_grids_view grids,
+                                           float dt, zpc_drucker_prager model, zpc_stream_t stream);
+int zpcb200_p2g_apic_nacc_binned(zpc_bins_view bins, float *logJp, zpc_hashtable_view table, zpc_grids_view grids, float dt,
+                                 zpc_nacc model, zpc_stream_t stream);
+int zpcb200_rebin_particles_ordered(void *temp, size_t *temp_bytes, zpc_bins_view src, zpc_hashtable_view table, float dx,
+                                    zpc_bins_view dst, int *order_out, zpc_stream_t stream);
 int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,
                             float dt, zpc_stream_t stream);
 

@@ -443,6 +443,54 @@ def test_references_own_lbvh_build_runs_on_b200_exec(oracle, tmp_path):
         assert np.array_equal(got.view(np.uint32) if got.dtype == np.float32 else got, want), ("native", k)
 
 
+@pytest.mark.parametrize("model", ["sand", "nacc"])
+def test_plastic_models_on_the_binned_path(oracle, model):
+    """Drucker-Prager / NACC through the block-binned P2G (logJp as a side array in bin order): grid and logJp vs the
+    reference-generated golden vectors; then four substeps with a re-bin in between (logJp follows the permutation) against the
+    any-order AoS solver on the same particles."""
+    from zpc_b200 import api
+    from zpc_b200.solver import MpmSolver
+    z = np.load(os.path.join(G, "mpm_cube6_%s.npz" % model))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **dict(ast.literal_eval(str(z["kw"]))))
+    P["logJp"] = z["logJp_in"].copy()
+    n, dx = P["x"].shape[0], P["dx"]
+    if model == "sand":
+        m = api.model_drucker_prager(P["volume"], E, NU, SAND["cohesion"], SAND["beta"], SAND["volumeCorrection"], SAND["yieldSurface"])
+    else:
+        m = api.model_nacc(P["volume"], NACC["E"], NACC["nu"], NACC["fa"], NACC["xi"], NACC["beta"], NACC["hardeningOn"])
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    bins = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    api.bin_particles(pars, table, dx, bins, order)
+    bins.logJp = pars.logJp[order.long()].contiguous()
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(bins, table, grids, synth.DT, m)
+    torch.cuda.synchronize()
+    rtol = [RTOL] * 4 + [RHS_RTOL[model]] * 3
+    _, gold = grid_by_key(z["active_keys"], z["grid_p2g"])
+    check_channels(grids.tiles.cpu().numpy(), gold, 1, "binned %s golden p2g" % model, rtol)
+    perm = order.cpu().numpy()
+    assert np.abs(bins.logJp.cpu().numpy() - z["logJp"][perm]).max() <= 2e-5
+    # multi-step with a re-bin: binned vs AoS solver
+    Q = dict(P)
+    Q["v"] = (P["v"] * 6.0).astype(np.float32)
+    Q["m"] = (P["m"] * (1.0 + 0.1 * np.arange(n) / n)).astype(np.float32)
+    res = []
+    for layout in ("aos", "binned"):
+        sol = MpmSolver(Q, dx, P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, layout=layout, rebin_every=2, model=m,
+                        **({"partition": "with_rebin"} if layout == "binned" else {}))
+        for _ in range(4):
+            sol.substep()
+        torch.cuda.synchronize()
+        H = sol.particles_host() if layout == "binned" else dict(sol.aos.to_host(), logJp=sol.aos.logJp.cpu().numpy())
+        o = np.argsort(H["m"], kind="stable")
+        res.append({k: H[k][o] for k in ("x", "v", "C", "F", "logJp")})
+    check_particles(res[1], res[0], dx, "binned vs AoS, %s, 4 substeps" % model, rtol=1e-4)
+    assert np.abs(res[1]["logJp"] - res[0]["logJp"]).max() <= 1e-4
+
+
 # last: a failed stream capture could leave the process unable to launch — nothing runs after it
 def test_graph_replay_equals_eager_substeps():
     """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same

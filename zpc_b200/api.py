@@ -502,6 +502,7 @@ class ParticleBins:
         self.bin_start = torch.zeros(self.cap + 1, dtype=torch.int32, device=device)
         self.bin_key = torch.zeros(self.cap, 3, dtype=torch.int32, device=device)
         self.num_bins = torch.zeros(1, dtype=torch.int32, device=device)
+        self.logJp = None        # plastic models: one float per particle in bin order (set by the owner, permuted with every re-bin)
         self.cell_order = self.cell_start = self.cell_order_valid = None
         if cell_order_cache:
             self.cell_order = torch.zeros(max(self.n, 1), dtype=torch.int16, device=device)
@@ -675,7 +676,13 @@ def p2g_transfer(pars, table, grids, dt, model, stream=None):
     if isinstance(model, (zpc_drucker_prager, zpc_nacc)):
         if getattr(pars, "logJp", None) is None:
             raise ValueError("the plastic models need the per-particle logJp attribute (P2G.hpp:93)")
-        fn = lib().zpcb200_p2g_apic_drucker_prager if isinstance(model, zpc_drucker_prager) else lib().zpcb200_p2g_apic_nacc
+        dp = isinstance(model, zpc_drucker_prager)
+        if isinstance(pars, ParticleBins):          # logJp: one float per particle in bin order, kept next to the bins
+            fn = lib().zpcb200_p2g_apic_drucker_prager_binned if dp else lib().zpcb200_p2g_apic_nacc_binned
+            _check(fn(pars.view(), C.c_void_p(pars.logJp.data_ptr()), table.view(), grids.view(), C.c_float(dt), model, _stream_ptr(stream)),
+                   "p2g(plastic, binned)")
+            return
+        fn = lib().zpcb200_p2g_apic_drucker_prager if dp else lib().zpcb200_p2g_apic_nacc
         _check(fn(pars.view(), table.view(), grids.view(), C.c_float(dt), model, _stream_ptr(stream)), "p2g(plastic)")
         return
     if isinstance(model, zpc_vonmises_fixed_corotated) and isinstance(pars, ParticleBins):
@@ -775,8 +782,13 @@ def bin_particles(pars, table, dx, bins, order_out=None, stream=None):
                (), stream)
 
 
-def rebin_particles(src, table, dx, dst, stream=None):
-    _two_phase(lib().zpcb200_rebin_particles, (src.view(), table.view(), C.c_float(dx), dst.view()), (), stream)
+def rebin_particles(src, table, dx, dst, stream=None, order_out=None):
+    """order_out (int32 [n], optional): the permutation applied, dst slot i <- src slot order_out[i] (side arrays follow it)"""
+    if order_out is None:
+        _two_phase(lib().zpcb200_rebin_particles, (src.view(), table.view(), C.c_float(dx), dst.view()), (), stream)
+    else:
+        _two_phase(lib().zpcb200_rebin_particles_ordered, (src.view(), table.view(), C.c_float(dx), dst.view(),
+                                                           C.c_void_p(order_out.data_ptr())), (), stream)
 
 
 def unbin_particles(bins, pars, stream=None):

@@ -145,7 +145,9 @@ __device__ __forceinline__ void sweep_cells3(const float4 *rec, int lo, int hi, 
 #ifndef ZPC_P2G_MINB
 #define ZPC_P2G_MINB 4
 #endif
-// MODEL 0 = FixedCorotatedConfig, 1 = VonMisesFixedCorotatedConfig (yield_stress; P2G.hpp:89-90) — the model only enters
+// MODEL 0 = FixedCorotatedConfig, 1 = VonMisesFixedCorotatedConfig (yield_stress; P2G.hpp:89-90), 2 = DruckerPragerConfig,
+// 3 = NACCConfig (pp; the per-particle logJp lives in `scalar`, one float per particle in BIN order, read and written back by the
+// record phase like P2G.hpp:93,101) — the model only enters
 // the records phase (and the stray path), the sweep and the write-back are the same
 template <int VAR, int MODEL = 0>
 __global__ void __launch_bounds__(P2G_NT, ZPC_P2G_MINB)
@@ -153,7 +155,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
                   const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
                   const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
                   float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, int prefetch,
-                  float yield_stress) {
+                  float yield_stress, float *__restrict__ scalar, zpcm::PlasticPrm pp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GSmem &S = *reinterpret_cast<P2GSmem *>(smem_raw);
   const int bin = blockIdx.x;
@@ -268,7 +270,13 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 #pragma unroll
         for (int d = 0; d < 9; ++d) F[d] = pars[s + (ZPC_PB_F + d) * TS];
         if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, K);
-        else zpcm::stress_fcr(volume, mu, lam, F, K);
+        else if constexpr (MODEL >= 2) {
+          float *lj = scalar + (size_t)p0 + gorder[pos];
+          float logJp = *lj;
+          if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, K);
+          else zpcm::stress_nacc(volume, mu, pp.a, pp.b, pp.c, pp.d, pp.flag != 0, logJp, F, K);
+          *lj = logJp;
+        } else zpcm::stress_fcr(volume, mu, lam, F, K);
 #pragma unroll
         for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
         float d0[3], loc[3], vel[3], C[9];
@@ -397,7 +405,16 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 #pragma unroll
     for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
     if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
-    else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam);
+    else if constexpr (MODEL >= 2) {
+      float *lj = scalar + (size_t)p0 + gorder[t];
+      float logJp = *lj, contrib[9];
+      if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, contrib);
+      else zpcm::stress_nacc(volume, mu, pp.a, pp.b, pp.c, pp.d, pp.flag != 0, logJp, F, contrib);
+      *lj = logJp;
+#pragma unroll
+      for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+      zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb}, tiles, 7, dx);
+    } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam);
   }
   if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
 }
@@ -917,7 +934,7 @@ Tuning &tuning() {
 // shared launch of the binned P2G: MODEL 0 fixed-corotated, 1 von Mises
 template <int MODEL>
 static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, float volume, float E, float nu,
-                             float yield_stress, zpc_stream_t stream) {
+                             float yield_stress, zpc_stream_t stream, float *scalar = nullptr, zpcm::PlasticPrm pp = {}) {
   if (g.numChannels != 7 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
     return ZPCB200_E_BADARG;
   static bool attr_set = false;
@@ -933,7 +950,7 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
   auto kern = variant == 3 ? p2g_binned_kernel<3, MODEL> : p2g_binned_kernel<4, MODEL>;
   kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
-      bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress);
+      bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }
@@ -976,6 +993,27 @@ int zpcb200_unbin_particles(zpc_bins_view bins, zpc_particles_view pars, zpc_str
 int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_fixed_corotated model,
                                 zpc_stream_t stream) {
   return p2g_binned_launch<0>(bins, tb, g, dt, model.volume, model.E, model.nu, 0.f, stream);
+}
+int zpcb200_p2g_apic_drucker_prager_binned(zpc_bins_view bins, float *logJp, zpc_hashtable_view tb, zpc_grids_view g, float dt,
+                                           zpc_drucker_prager model, zpc_stream_t stream) {
+  if (!logJp) return ZPCB200_E_BADARG;
+  return p2g_binned_launch<2>(bins, tb, g, dt, model.volume, model.E, model.nu, 0.f, stream, logJp,
+                              zpcm::PlasticPrm{model.cohesion, model.beta, model.yieldSurface, 0.f, model.volumeCorrection});
+}
+int zpcb200_p2g_apic_nacc_binned(zpc_bins_view bins, float *logJp, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_nacc model,
+                                 zpc_stream_t stream) {
+  if (!logJp || model.dim != 3) return ZPCB200_E_BADARG;
+  return p2g_binned_launch<3>(bins, tb, g, dt, model.volume, model.E, model.nu, 0.f, stream, logJp,
+                              zpcm::PlasticPrm{zpcm::nacc_bulk_host(model.E, model.nu), model.xi, model.beta,
+                                               zpcm::nacc_msqr_host(model.fa, model.dim), model.hardeningOn});
+}
+/* zpcb200_rebin_particles that also returns the permutation it applied: dst slot i <- src slot order_out[i] (for per-particle
+ * side arrays such as logJp, which the caller permutes with it) */
+int zpcb200_rebin_particles_ordered(void *temp, size_t *temp_bytes, zpc_bins_view src, zpc_hashtable_view table, float dx,
+                                    zpc_bins_view dst, int *order_out, zpc_stream_t stream) {
+  zpc_particles_view none = {};
+  if (temp && (src.pars.base == dst.pars.base || dst.pars.size < src.pars.size)) return ZPCB200_E_BADARG;
+  return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, table, dx, dst, order_out, (cudaStream_t)stream);
 }
 int zpcb200_p2g_apic_vonmises_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt,
                                      zpc_vonmises_fixed_corotated model, zpc_stream_t stream) {

@@ -96,10 +96,7 @@ __global__ void __launch_bounds__(128) p2g_aos_eos_kernel(zpc_particles_view P, 
 // DruckerPragerConfig (MODEL 2) / NACCConfig (MODEL 3): P2G.hpp:92-102 — logJp is read, updated by the return mapping and
 // written back; the projected F stays in registers.  prm: model 2 {cohesion, beta, yieldSurface, -}, flag = volumeCorrection;
 // model 3 {bulk, xi, beta, Msqr}, flag = hardeningOn.
-struct PlasticParams {
-  float a, b, c, d;
-  int flag;
-};
+using PlasticParams = zpcm::PlasticPrm;
 template <int MODEL, class GA>
 __global__ void __launch_bounds__(128) p2g_aos_plastic_kernel(zpc_particles_view P, GA tb, float *tiles, int nch, float dx, float dt,
                                                               float volume, float mu, float lam, PlasticParams prm) {

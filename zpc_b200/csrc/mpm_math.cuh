@@ -281,6 +281,13 @@ ZPC_HD void stress_vonmises(float volume, float mu, float lam, float yield_stres
     for (int r = 0; r < 3; ++r) PF[3 * c + r] = (P[r] * F[c] + P[3 + r] * F[3 + c] + P[6 + r] * F[6 + c]) * volume;
 }
 
+// parameters of the plastic models as the kernels take them: Drucker-Prager {cohesion, beta, yieldSurface, -}, flag = volumeCorrection;
+// NACC {bulk, xi, beta, Msqr}, flag = hardeningOn
+struct PlasticPrm {
+  float a, b, c, d;
+  int flag;
+};
+
 // matmul_mat_diag_matT_3D (math/matrix/MatrixUtils.h:26-47): out = A diag(d) B^T, column-major
 ZPC_HD void mat_diag_matT(float (&out)[9], const float (&a)[9], const float (&d)[3], const float (&b)[9]) {
 #pragma unroll
