@@ -426,6 +426,12 @@ int zpcb200_p2g_apic_drucker_prager_binned(zpc_bins_view bins, float *logJp, zpc
                                            float dt, zpc_drucker_prager model, zpc_stream_t stream);
 int zpcb200_p2g_apic_nacc_binned(zpc_bins_view bins, float *logJp, zpc_hashtable_view table, zpc_grids_view grids, float dt,
                                  zpc_nacc model, zpc_stream_t stream);
+/* EquationOfStateConfig on the binned layout (P2G.hpp:66-87, G2P.hpp:69-73): J = one float per particle in bin order; the F
+ * channels of the bins are neither read nor written. */
+int zpcb200_p2g_apic_eos_binned(zpc_bins_view bins, const float *J, zpc_hashtable_view table, zpc_grids_view grids, float dt,
+                                zpc_equation_of_state model, zpc_stream_t stream);
+int zpcb200_g2p_apic_eos_binned(zpc_bins_view bins, float *J, zpc_hashtable_view table, zpc_grids_view grids, float dt,
+                                zpc_stream_t stream);
 int zpcb200_rebin_particles_ordered(void *temp, size_t *temp_bytes, zpc_bins_view src, zpc_hashtable_view table, float dx,
                                     zpc_bins_view dst, int *order_out, zpc_stream_t stream);
 int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids,

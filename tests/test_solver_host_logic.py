@@ -87,8 +87,18 @@ def test_models_and_colliders_pick_the_right_entries(recorder):
         _names(recorder)
         s.substep()
         assert _names(recorder) == ["partition_build"] * 2 + ["clean_grid", p2g, "grid_update", g2p]
-    with pytest.raises(ValueError):                       # the equation of state has no J channel in the binned layout
+    with pytest.raises(ValueError):                       # the equation of state needs J
         MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="binned", device="cpu", model=api.model_eos(P["volume"]))
+    Qj = {k: v for k, v in P.items() if k != "F"}
+    Qj["J"] = np.ones(n, np.float32)
+    s = MpmSolver(Qj, P["dx"], P["volume"], synth.DT, layout="binned", device="cpu", model=api.model_eos(P["volume"]), rebin_every=2,
+                  partition="with_rebin")
+    _names(recorder)
+    for _ in range(3):
+        s.substep()
+    step = ["clean_grid", "p2g_apic_eos_binned", "grid_update", "g2p_apic_eos_binned"]
+    assert _names(recorder) == step * 2 + ["partition_build"] * 2 + ["rebin_particles_ordered"] * 2 + step
+    assert s.bins.J is not None and "J" in s.particles_host()
     # plastic models on the binned layout: logJp rides next to the bins and follows every re-bin
     Q = dict(P, logJp=np.linspace(-1, 0, n).astype(np.float32))
     s = MpmSolver(Q, P["dx"], P["volume"], synth.DT, layout="binned", device="cpu", model=api.model_nacc(P["volume"]), rebin_every=2,

@@ -491,6 +491,58 @@ def test_plastic_models_on_the_binned_path(oracle, model):
     assert np.abs(res[1]["logJp"] - res[0]["logJp"]).max() <= 1e-4
 
 
+@pytest.mark.parametrize("staged", [1, 0])
+def test_equation_of_state_on_the_binned_path(oracle, staged):
+    """EquationOfStateConfig through the binned kernels (J as a side array in bin order; P2G record from C and J, G2P updates J and
+    leaves F alone): vs the reference-generated golden vectors, then four substeps with a re-bin against the AoS solver"""
+    from zpc_b200 import api
+    from zpc_b200.solver import MpmSolver
+    z = np.load(os.path.join(G, "mpm_cube6_eos.npz"))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **dict(ast.literal_eval(str(z["kw"]))))
+    P["J"] = z["J_in"].copy()
+    n, dx = P["x"].shape[0], P["dx"]
+    m = api.model_eos(P["volume"], 4.0e4, 7.15, 0.01)
+    api.set_tuning(-1, staged)
+    try:
+        pars, table = build_partition(P)
+        ht = host_table(table)
+        bins = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
+        order = torch.empty(n, dtype=torch.int32, device="cuda")
+        api.bin_particles(pars, table, dx, bins, order)
+        bins.J = pars.J[order.long()].contiguous()
+        grids = api.Grids(dx, ht["nblocks"])
+        api.clean_grid_blocks(grids, table)
+        api.p2g_transfer(bins, table, grids, synth.DT, m)
+        _, gold = grid_by_key(z["active_keys"], z["grid_p2g"])
+        check_channels(grids.tiles.cpu().numpy(), gold, 1, "binned EOS golden p2g", RTOL)
+        mx = torch.zeros(1, device="cuda")
+        api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+        api.g2p_transfer(bins, table, grids, synth.DT, model=m)
+        torch.cuda.synchronize()
+        perm = order.cpu().numpy()
+        for k in "xv":
+            check_channels(bins.attr(k).cpu().numpy(), z[k][perm], 1, "binned EOS golden g2p " + k, 3e-5, floor=float(np.abs(z[k]).max()))
+        check_channels(bins.J.cpu().numpy()[:, None], z["J"][perm][:, None], 1, "binned EOS golden J", 3e-5)
+        Q = {k: v for k, v in P.items() if k != "F"}
+        Q["v"] = (P["v"] * 6.0).astype(np.float32)
+        Q["m"] = (P["m"] * (1.0 + 0.1 * np.arange(n) / n)).astype(np.float32)
+        res = []
+        for layout in ("aos", "binned"):
+            sol = MpmSolver(Q, dx, P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, layout=layout, rebin_every=2, model=m,
+                            **({"partition": "with_rebin"} if layout == "binned" else {}))
+            for _ in range(4):
+                sol.substep()
+            torch.cuda.synchronize()
+            H = sol.particles_host() if layout == "binned" else dict(sol.aos.to_host(), J=sol.aos.J.cpu().numpy())
+            o = np.argsort(H["m"], kind="stable")
+            res.append({k: H[k][o] for k in ("x", "v", "C", "J")})
+        for k in "xv":
+            check_channels(res[1][k], res[0][k], 1, "binned vs AoS EOS " + k, 1e-4, floor=float(np.abs(res[0][k]).max()))
+        assert np.abs(res[1]["J"] - res[0]["J"]).max() <= 1e-4
+    finally:
+        api.set_tuning(-1, 1)
+
+
 # last: a failed stream capture could leave the process unable to launch — nothing runs after it
 def test_graph_replay_equals_eager_substeps():
     """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same

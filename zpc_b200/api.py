@@ -460,7 +460,8 @@ class Particles:
         self.v = torch.as_tensor(P["v"]).to(device).contiguous()
         self.m = torch.as_tensor(P["m"]).to(device).contiguous()
         self.C = torch.as_tensor(P["C"]).to(device).contiguous()
-        self.F = torch.as_tensor(P["F"]).to(device).contiguous()
+        self.F = (torch.as_tensor(P["F"]).to(device).contiguous() if "F" in P          # the equation of state carries J instead
+                  else torch.eye(3, dtype=torch.float32, device=device).reshape(1, 9).repeat(self.n, 1))
         self.J = torch.as_tensor(P["J"]).to(device).contiguous() if "J" in P else None   # EquationOfStateConfig only
         self.logJp = torch.as_tensor(P["logJp"]).to(device).contiguous() if "logJp" in P else None  # DruckerPrager / NACC
 
@@ -503,6 +504,7 @@ class ParticleBins:
         self.bin_key = torch.zeros(self.cap, 3, dtype=torch.int32, device=device)
         self.num_bins = torch.zeros(1, dtype=torch.int32, device=device)
         self.logJp = None        # plastic models: one float per particle in bin order (set by the owner, permuted with every re-bin)
+        self.J = None            # equation of state: likewise
         self.cell_order = self.cell_start = self.cell_order_valid = None
         if cell_order_cache:
             self.cell_order = torch.zeros(max(self.n, 1), dtype=torch.int16, device=device)
@@ -693,6 +695,12 @@ def p2g_transfer(pars, table, grids, dt, model, stream=None):
         _check(lib().zpcb200_p2g_apic_vonmises(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
                                                _stream_ptr(stream)), "p2g(vonmises)")
         return
+    if isinstance(model, zpc_equation_of_state) and isinstance(pars, ParticleBins):
+        if pars.J is None:
+            raise ValueError("the equation of state needs the per-particle J attribute (P2G.hpp:67)")
+        _check(lib().zpcb200_p2g_apic_eos_binned(pars.view(), C.c_void_p(pars.J.data_ptr()), table.view(), grids.view(), C.c_float(dt), model,
+                                                 _stream_ptr(stream)), "p2g(eos, binned)")
+        return
     if isinstance(model, zpc_equation_of_state):
         _check(lib().zpcb200_p2g_apic_eos(pars.view(), table.view(), grids.view(), C.c_float(dt), model,
                                           _stream_ptr(stream)), "p2g(eos)")
@@ -764,6 +772,10 @@ def compute_grid_block_velocity_with_boundaries(grids, table, dt, extf, mode, co
 
 
 def g2p_transfer(pars, table, grids, dt, stream=None, model=None):
+    if isinstance(model, zpc_equation_of_state) and isinstance(pars, ParticleBins):
+        _check(lib().zpcb200_g2p_apic_eos_binned(pars.view(), C.c_void_p(pars.J.data_ptr()), table.view(), grids.view(), C.c_float(dt),
+                                                 _stream_ptr(stream)), "g2p(eos, binned)")
+        return
     if isinstance(model, zpc_equation_of_state):
         _check(lib().zpcb200_g2p_apic_eos(pars.view(), table.view(), grids.view(), C.c_float(dt), _stream_ptr(stream)),
                "g2p(eos)")

@@ -147,7 +147,8 @@ __device__ __forceinline__ void sweep_cells3(const float4 *rec, int lo, int hi, 
 #endif
 // MODEL 0 = FixedCorotatedConfig, 1 = VonMisesFixedCorotatedConfig (yield_stress; P2G.hpp:89-90), 2 = DruckerPragerConfig,
 // 3 = NACCConfig (pp; the per-particle logJp lives in `scalar`, one float per particle in BIN order, read and written back by the
-// record phase like P2G.hpp:93,101) — the model only enters
+// record phase like P2G.hpp:93,101), 4 = EquationOfStateConfig (pp.a = bulk, pp.b = viscosity; `scalar` = J, read only; the F
+// channels of the bins are not touched, P2G.hpp:66-87) — the model only enters
 // the records phase (and the stray path), the sweep and the write-back are the same
 template <int VAR, int MODEL = 0>
 __global__ void __launch_bounds__(P2G_NT, ZPC_P2G_MINB)
@@ -267,10 +268,29 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
       if (pos < n_fast) {
         const size_t s = pslot((size_t)p0 + gorder[pos]);
         float F[9], K[9];
+        if constexpr (MODEL != 4) {
 #pragma unroll
-        for (int d = 0; d < 9; ++d) F[d] = pars[s + (ZPC_PB_F + d) * TS];
-        if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, K);
-        else if constexpr (MODEL >= 2) {
+          for (int d = 0; d < 9; ++d) F[d] = pars[s + (ZPC_PB_F + d) * TS];
+        }
+        if constexpr (MODEL == 4) {
+          // stress from C and J (P2G.hpp:66-83); C is loaded again below for the affine part — the compiler merges the loads
+          const float J = scalar[(size_t)p0 + gorder[pos]];
+          float Cc[9];
+#pragma unroll
+          for (int d = 0; d < 9; ++d) Cc[d] = pars[s + (ZPC_PB_C + d) * TS];
+          const float vol = volume * J, J2 = J * J, J4 = J2 * J2;
+          const float pressure = pp.a * (1.f / (J * J2 * J4) - 1.f), visc = pp.b;
+          K[0] = ((Cc[0] + Cc[0]) * visc - pressure) * vol;
+          K[1] = (Cc[1] + Cc[3]) * visc * vol;
+          K[2] = (Cc[2] + Cc[6]) * visc * vol;
+          K[3] = (Cc[3] + Cc[1]) * visc * vol;
+          K[4] = ((Cc[4] + Cc[4]) * visc - pressure) * vol;
+          K[5] = (Cc[5] + Cc[7]) * visc * vol;
+          K[6] = (Cc[6] + Cc[2]) * visc * vol;
+          K[7] = (Cc[7] + Cc[5]) * visc * vol;
+          K[8] = ((Cc[8] + Cc[8]) * visc - pressure) * vol;
+        } else if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, K);
+        else if constexpr (MODEL == 2 || MODEL == 3) {
           float *lj = scalar + (size_t)p0 + gorder[pos];
           float logJp = *lj;
           if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, K);
@@ -405,7 +425,9 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 #pragma unroll
     for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
     if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
-    else if constexpr (MODEL >= 2) {
+    else if constexpr (MODEL == 4) {
+      zpcp::p2g_scatter_particle_eos(pos, vel, mass, C, scalar[(size_t)p0 + gorder[t]], zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, pp.a, pp.b);
+    } else if constexpr (MODEL >= 2) {
       float *lj = scalar + (size_t)p0 + gorder[t];
       float logJp = *lj, contrib[9];
       if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, contrib);
@@ -499,10 +521,13 @@ struct G2PSmem {
   unsigned char grp_of[BIN_MAX];
 };
 
+// EOS = true: G2PTransfer with EquationOfStateConfig (G2P.hpp:69-73) — J (side array `scalar`, bin order) <- (1 + tr(C) dt) J, the F
+// channels are neither read nor written
+template <bool EOS = false>
 __global__ void __launch_bounds__(G2P_NT, ZPC_G2P_MINB)
 g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder, unsigned short *__restrict__ cellStart,
-                  zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx, float dt) {
+                  zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx, float dt, float *__restrict__ scalar) {
   __shared__ __align__(128) G2PSmem S;
   const int bin = blockIdx.x;
   if (bin >= *numBins) return;
@@ -549,8 +574,10 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
     float pos[3], Fo[9];
 #pragma unroll
     for (int d = 0; d < 3; ++d) pos[d] = pars[s + (ZPC_PB_X + d) * TS];
+    if constexpr (!EOS) {
 #pragma unroll
-    for (int d = 0; d < 9; ++d) Fo[d] = pars[s + (ZPC_PB_F + d) * TS];  // issued early: consumed after the contraction
+      for (int d = 0; d < 9; ++d) Fo[d] = pars[s + (ZPC_PB_F + d) * TS];  // issued early: consumed after the contraction
+    }
     float vel[3], C[9], tmp[9];
     g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C);
     if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
@@ -562,13 +589,17 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
       S.grp_of[i] = (unsigned char)g;
       atomicAdd(&S.cnt[g], 1);
     }
+    if constexpr (EOS) {
+      scalar[(size_t)p0 + i] = (1 + (C[0] + C[4] + C[8]) * dt) * scalar[(size_t)p0 + i];
+    } else {
 #pragma unroll
-    for (int d = 0; d < 9; ++d) tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f);
+      for (int d = 0; d < 9; ++d) tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f);
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+      for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
-        pars[s + (ZPC_PB_F + 3 * c + r) * TS] = tmp[r] * Fo[3 * c] + tmp[3 + r] * Fo[3 * c + 1] + tmp[6 + r] * Fo[3 * c + 2];
+        for (int r = 0; r < 3; ++r)
+          pars[s + (ZPC_PB_F + 3 * c + r) * TS] = tmp[r] * Fo[3 * c] + tmp[3 + r] * Fo[3 * c + 1] + tmp[6 + r] * Fo[3 * c + 2];
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d) { pars[s + (ZPC_PB_X + d) * TS] = pos[d]; pars[s + (ZPC_PB_V + d) * TS] = vel[d]; }
 #pragma unroll
@@ -643,12 +674,12 @@ static_assert(sizeof(G2PStagedSmem<256>) <= 48 * 1024, "static shared memory");
 
 // NT threads per CTA: small CTAs interleave their prologue / wait / store phases better — measured at C3:
 // 64 threads (15 CTAs/SM) 2.18 ms, 128 (8/SM) 2.30 ms, 256 (4/SM) 2.98 ms.
-template <int NT>
+template <int NT, bool EOS = false>
 __global__ void __launch_bounds__(NT, 1024 / NT)
 g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                          const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder,
                          unsigned short *__restrict__ cellStart, zpc_hashtable_view tb, const float *__restrict__ tiles, int nch,
-                         float dx, float dt) {
+                         float dx, float dt, float *__restrict__ scalar) {
   constexpr int G2P_ST = NT / 32;
   __shared__ __align__(128) G2PStagedSmem<NT> S;
   const int bin = blockIdx.x;
@@ -667,11 +698,11 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
   // stage c <- tiles [t0 + G2P_ST c, t0 + G2P_ST (c + 1)) ∩ the bin's tiles: x = channels 1..3, F = channels 16..24
   auto issue_stage = [&](int c) {
     const int b = c & 1, tb0 = c * G2P_ST, nt = min(G2P_ST, ntiles - tb0);
-    mbar_expect_tx(&S.bar_stage[b], (unsigned)nt * (3u + 9u) * TS * 4u);
+    mbar_expect_tx(&S.bar_stage[b], (unsigned)nt * (EOS ? 3u : 3u + 9u) * TS * 4u);
     for (int t = 0; t < nt; ++t) {
       const float *src = pars + (size_t)(t0 + tb0 + t) * NCH * TS;
       bulk_g2s(&S.xs[b][t][0][0], src + ZPC_PB_X * TS, 3 * TS * 4, &S.bar_stage[b]);
-      bulk_g2s(&S.fs[b][t][0][0], src + ZPC_PB_F * TS, 9 * TS * 4, &S.bar_stage[b]);
+      if constexpr (!EOS) bulk_g2s(&S.fs[b][t][0][0], src + ZPC_PB_F * TS, 9 * TS * 4, &S.bar_stage[b]);
     }
   };
   if (tid == 0) {  // the same thread initialised the barriers: program order suffices
@@ -707,8 +738,10 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
     if (mine) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) pos[d] = S.xs[b][tl][d][ln];
+      if constexpr (!EOS) {
 #pragma unroll
-      for (int d = 0; d < 9; ++d) Fo[d] = S.fs[b][tl][d][ln];
+        for (int d = 0; d < 9; ++d) Fo[d] = S.fs[b][tl][d][ln];
+      }
     }
     if (c + 2 < nstages) {  // bins with more than 512 particles: refill this stage once everybody has read it
       __syncthreads();
@@ -727,13 +760,17 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
         S.grp_of[i] = (unsigned char)g;
         atomicAdd(&S.cnt[g], 1);
       }
+      if constexpr (EOS) {
+        scalar[gp] = (1 + (C[0] + C[4] + C[8]) * dt) * scalar[gp];
+      } else {
 #pragma unroll
-      for (int d = 0; d < 9; ++d) tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f);
+        for (int d = 0; d < 9; ++d) tmp[d] = C[d] * dt + ((d & 3) ? 0.f : 1.f);
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc)
+        for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-          pars[s + (ZPC_PB_F + 3 * cc + r) * TS] = tmp[r] * Fo[3 * cc] + tmp[3 + r] * Fo[3 * cc + 1] + tmp[6 + r] * Fo[3 * cc + 2];
+          for (int r = 0; r < 3; ++r)
+            pars[s + (ZPC_PB_F + 3 * cc + r) * TS] = tmp[r] * Fo[3 * cc] + tmp[3 + r] * Fo[3 * cc + 1] + tmp[6 + r] * Fo[3 * cc + 2];
+      }
 #pragma unroll
       for (int d = 0; d < 3; ++d) { pars[s + (ZPC_PB_X + d) * TS] = pos[d]; pars[s + (ZPC_PB_V + d) * TS] = vel[d]; }
 #pragma unroll
@@ -955,6 +992,22 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
   return ZPCB200_OK;
 }
 
+template <bool EOS>
+static int g2p_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, float *scalar, zpc_stream_t stream) {
+  if (g.numChannels < 4 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
+    return ZPCB200_E_BADARG;
+  const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
+  const int staged = tuning().g2p_staged;
+  auto kern = staged == 128 ? g2p_binned_staged_kernel<128, EOS> : staged == 256 ? g2p_binned_staged_kernel<256, EOS> : staged ? g2p_binned_staged_kernel<64, EOS> : g2p_binned_kernel<EOS>;
+  const int nt = staged == 128 ? 128 : staged == 256 ? 256 : staged ? 64 : G2P_NT;
+  kern<<<bins.binCapacity, nt, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
+                                                              cache ? bins.cellOrder : nullptr, bins.cellStart, tb, g.tiles,
+                                                              g.numChannels, g.dx, dt, scalar);
+  ZPC_CHECK_LAUNCH();
+  if (cache) ZPC_CUDA(cudaMemsetAsync(bins.cellOrderValid, 1, sizeof(int), (cudaStream_t)stream));  // non-zero = valid
+  return ZPCB200_OK;
+}
+
 extern "C" {
 
 int zpcb200_set_tuning(int p2g_sweep, int g2p_staged) {
@@ -1021,17 +1074,17 @@ int zpcb200_p2g_apic_vonmises_binned(zpc_bins_view bins, zpc_hashtable_view tb, 
 }
 
 int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
-  if (g.numChannels < 4 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
-    return ZPCB200_E_BADARG;
-  const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
-  const int staged = tuning().g2p_staged;
-  auto kern = staged == 128 ? g2p_binned_staged_kernel<128> : staged == 256 ? g2p_binned_staged_kernel<256> : staged ? g2p_binned_staged_kernel<64> : g2p_binned_kernel;
-  const int nt = staged == 128 ? 128 : staged == 256 ? 256 : staged ? 64 : G2P_NT;
-  kern<<<bins.binCapacity, nt, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
-                                                              cache ? bins.cellOrder : nullptr, bins.cellStart, tb, g.tiles,
-                                                              g.numChannels, g.dx, dt);
-  ZPC_CHECK_LAUNCH();
-  if (cache) ZPC_CUDA(cudaMemsetAsync(bins.cellOrderValid, 1, sizeof(int), (cudaStream_t)stream));  // non-zero = valid
-  return ZPCB200_OK;
+  return g2p_binned_launch<false>(bins, tb, g, dt, nullptr, stream);
+}
+/* EquationOfStateConfig on the binned layout: J = one float per particle in bin order (like logJp above) */
+int zpcb200_p2g_apic_eos_binned(zpc_bins_view bins, const float *J, zpc_hashtable_view tb, zpc_grids_view g, float dt,
+                                zpc_equation_of_state model, zpc_stream_t stream) {
+  if (!J) return ZPCB200_E_BADARG;
+  return p2g_binned_launch<4>(bins, tb, g, dt, model.volume, 0.f, 0.f, 0.f, stream, const_cast<float *>(J),
+                              zpcm::PlasticPrm{model.bulk, model.viscosity, 0.f, 0.f, 0});
+}
+int zpcb200_g2p_apic_eos_binned(zpc_bins_view bins, float *J, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_stream_t stream) {
+  if (!J) return ZPCB200_E_BADARG;
+  return g2p_binned_launch<true>(bins, tb, g, dt, J, stream);
 }
 }

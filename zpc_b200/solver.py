@@ -11,9 +11,8 @@ enlarged by one more ring (EnlargeSparsity{-1,3}): a particle that has drifted b
 still finds every block of its stencil, the extra blocks stay empty (mass 0) and results are unchanged.
 
 `model=` selects the constitutive model (api.model_fcr | model_vonmises | model_eos | model_drucker_prager | model_nacc;
-default fixed-corotated from E, nu): the binned layout carries the 25 channels m, x, v, C, F and, for Drucker-Prager / NACC, a
-logJp side array in bin order that is permuted with every re-bin; the per-particle J of the equation of state lives in the
-AoS layout only.  `colliders=` (up to
+default fixed-corotated from E, nu): the binned layout carries the 25 channels m, x, v, C, F and, for Drucker-Prager / NACC
+(logJp) and the equation of state (J), a side array in bin order that is permuted with every re-bin.  `colliders=` (up to
 four api.plane_collider / sphere_collider / cuboid_collider) are applied inside the grid-update pass
 (ComputeGridBlockVelocity + ApplyBoundaryConditionOnGridBlocks fused, GridOp.hpp:71-164).
 """
@@ -38,9 +37,9 @@ class MpmSolver:
         self.dx, self.dt, self.mode = float(dx), float(dt), int(mode)
         self.extf = (0.0, float(gravity), 0.0)
         self.model = model if model is not None else api.model_fcr(volume, E, nu)
-        if layout == "binned" and isinstance(self.model, api.zpc_equation_of_state):
-            raise ValueError("the binned layout has no J channel: use layout='aos' for the equation of state")
-        self._plastic = isinstance(self.model, (api.zpc_drucker_prager, api.zpc_nacc))
+        # per-particle scalar the model carries besides F: logJp (plastic models), J (equation of state)
+        self._side = ("logJp" if isinstance(self.model, (api.zpc_drucker_prager, api.zpc_nacc))
+                      else "J" if isinstance(self.model, api.zpc_equation_of_state) else None)
         self.colliders = list(colliders)
         if len(self.colliders) > api.MAX_COLLIDERS:
             raise ValueError("at most %d colliders per grid pass" % api.MAX_COLLIDERS)
@@ -61,10 +60,11 @@ class MpmSolver:
             self.order = torch.arange(self.n, dtype=torch.int32, device=device)      # overwritten by bin_particles
             api.partition_for_particles(api.vec3_port(self.aos.x), self.n, self.dx, self.table, enlarge=self.enlarge)
             api.bin_particles(self.aos, self.table, self.dx, self.bins, self.order)
-            if self._plastic:
-                if self.aos.logJp is None:
-                    raise ValueError("the plastic models need the per-particle logJp attribute (P2G.hpp:93)")
-                self.bins.logJp = self.aos.logJp[self.order.long()].contiguous()
+            if self._side:
+                src = getattr(self.aos, self._side)
+                if src is None:
+                    raise ValueError("this model needs the per-particle %s attribute (P2G.hpp:67,93)" % self._side)
+                setattr(self.bins, self._side, src[self.order.long()].contiguous())
                 self._rebin_order = torch.arange(self.n, dtype=torch.int32, device=device)
             self.aos = None if shuffle_free else self.aos
         elif layout != "aos":
@@ -123,9 +123,9 @@ class MpmSolver:
     def rebin(self, stream=None):
         self.partition(stream)
         self._mark("begin")
-        if self._plastic:   # the logJp side array follows the permutation of the re-bin
+        if self._side:   # the side array (logJp / J) follows the permutation of the re-bin
             api.rebin_particles(self.bins, self.table, self.dx, self.bins_alt, stream, order_out=self._rebin_order)
-            self.bins_alt.logJp = self.bins.logJp[self._rebin_order.long()].contiguous()
+            setattr(self.bins_alt, self._side, getattr(self.bins, self._side)[self._rebin_order.long()].contiguous())
         else:
             api.rebin_particles(self.bins, self.table, self.dx, self.bins_alt, stream)
         self.bins, self.bins_alt = self.bins_alt, self.bins
@@ -244,7 +244,7 @@ class MpmSolver:
         """AoS dict on the host, in the solver's CURRENT particle order."""
         if self.layout == "binned":
             out = {k: self.bins.attr(k).cpu().numpy() for k in ("x", "v", "m", "C", "F")}
-            if self.bins.logJp is not None:
-                out["logJp"] = self.bins.logJp.cpu().numpy()
+            if self._side:
+                out[self._side] = getattr(self.bins, self._side).cpu().numpy()
             return out
         return self.aos.to_host()
