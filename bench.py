@@ -26,6 +26,8 @@ sys.path.insert(0, ROOT)
 METRIC = "mpm_particle_substeps_per_sec"
 UNIT = "particle-substeps/s"
 BYTES_PER_PARTICLE = dict(clean=28 / 8, p2g=100 + 28 / 8, grid_update=(28 + 12) / 8, g2p=48 + 96 + 12 / 8)  # sum 257.5
+# EquationOfStateConfig (SURVEY §8(d) "cheap variant"): P2G reads x v m C J = 68 B, G2P reads x J = 16 B and writes x v C J = 64 B -> 161.5
+BYTES_PER_PARTICLE_EOS = dict(clean=28 / 8, p2g=68 + 28 / 8, grid_update=(28 + 12) / 8, g2p=16 + 64 + 12 / 8)
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -137,6 +139,8 @@ def main():
     ap.add_argument("--rebin-every", type=int, default=8)
     ap.add_argument("--partition", default="with_rebin", choices=["with_rebin", "every_step"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--model", default="fcr", choices=["fcr", "eos"], help="fcr = the headline workload (fixed-corotated); eos = the weakly "
+                    "compressible fluid of SURVEY §8(d) on the same cloud (single GPU, no e2e leg)")
     ap.add_argument("--e2e-timeout", type=int, default=240, help="seconds after which the N>1 e2e leg is abandoned (the line is still printed)")
     ap.add_argument("--e2e-pipelined", type=int, default=0, help="chunks of MpmSolver.substep_host_pipelined (0 = the plain call)")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
@@ -150,8 +154,11 @@ def main():
     from zpc_b200 import synth
     G, s = synth.CONFIGS[args.config]
     n_total = 8 * s ** 3
-    workload = "%s: %d particles (%d^3 cells x 8 ppc), %d^3 sparse grid (dx=1/%d), fixed-corotated APIC fp32" % (
-        args.config, n_total, s, G, G)
+    workload = "%s: %d particles (%d^3 cells x 8 ppc), %d^3 sparse grid (dx=1/%d), %s APIC fp32" % (
+        args.config, n_total, s, G, G, "fixed-corotated" if args.model == "fcr" else "equation-of-state (bulk 4e4, viscosity 0.01)")
+    bytes_pp = BYTES_PER_PARTICLE if args.model == "fcr" else BYTES_PER_PARTICLE_EOS
+    if args.model == "eos" and (int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.impl != "ours"):
+        raise SystemExit("--model eos is a single-GPU line of this implementation")
 
     if args.impl == "reference-cuda":
         # informational: the reference's own CUDA functors on the same GPU (oracle/_ref/libzpcref_cuda.so, `make -C oracle refcuda`),
@@ -194,8 +201,14 @@ def main():
     if world == 1:
         from zpc_b200.solver import MpmSolver
         P = synth.elastic_cube(s, G)
+        kw_model = {}
+        if args.model == "eos":
+            P = {k: v for k, v in P.items() if k != "F"}
+            P["J"] = np.ones(n_total, np.float32)
+            kw_model = dict(model=api.model_eos(P["volume"], 4.0e4, 7.15, 0.01))
+            args.e2e_steps = 0
         sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="binned", rebin_every=args.rebin_every,
-                        partition=args.partition)
+                        partition=args.partition, **kw_model)
         n_local = sol.n
     else:
         from zpc_b200.dist_solver import DistMpmSolver
@@ -244,7 +257,7 @@ def main():
     n_rebins = sum(1 for i in range(args.warmup, args.warmup + args.steps) if i > 0 and args.rebin_every > 0 and i % args.rebin_every == 0)
     fused_ms = sum(per_step.get(k, 0.0) for k in ("clean", "p2g", "grid_update", "g2p"))
     kern = {}
-    for k, bpp in BYTES_PER_PARTICLE.items():
+    for k, bpp in bytes_pp.items():
         if per_step.get(k):
             gbs = bpp * n_local / (per_step[k] * 1e-3) / 1e9
             kern[k] = dict(ms=per_step[k], algorithmic_gbps=gbs, frac=gbs / hbm_peak)
@@ -252,16 +265,17 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tr.get("config") == args.config and world == 1:
+        if tr.get("config") == args.config and world == 1 and args.model == "fcr":
             traffic = tr["kernels"]["p2g_binned_kernel"]["dram_bytes"]
     except Exception:
         pass
     dom = "p2g"
     roof = dict(bound="hbm", kernel="p2g_binned_kernel", achieved=kern.get(dom, {}).get("algorithmic_gbps"), peak=hbm_peak, unit="GB/s",
                 frac=kern.get(dom, {}).get("frac"), traffic=traffic, peak_source=peak_src,
-                algorithmic_bytes_per_launch=BYTES_PER_PARTICLE[dom] * n_local)
-    fused_gbps = 257.5 * n_local / (fused_ms * 1e-3) / 1e9 if fused_ms else None
-    fused = dict(ms=fused_ms, bytes_per_particle=257.5, achieved=fused_gbps, frac=(fused_gbps / hbm_peak) if fused_gbps else None,
+                algorithmic_bytes_per_launch=bytes_pp[dom] * n_local)
+    fused_bpp = sum(bytes_pp.values())
+    fused_gbps = fused_bpp * n_local / (fused_ms * 1e-3) / 1e9 if fused_ms else None
+    fused = dict(ms=fused_ms, bytes_per_particle=fused_bpp, achieved=fused_gbps, frac=(fused_gbps / hbm_peak) if fused_gbps else None,
                  kernels=kern, partition_ms=per_step.get("partition"), halo_ms=per_step.get("halo"), rebin_ms_each=(stage.get("rebin", 0.0) / n_rebins) if n_rebins else None,
                  rebins_in_timed_region=n_rebins)
 

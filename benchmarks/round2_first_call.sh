@@ -22,3 +22,6 @@ tail -2 gpurun_out/r2_prims_sweep.jsonl | cut -c1-300
 # 6. C5 "vs reference CudaExecutionPolicy": the reference's own policy (CUB underneath, sync(true)) and the same generic calls on b200_exec()
 for lg in 20 22 24 26 28; do python -m oracle.refcuda_runner prims-bench $lg 5; done > gpurun_out/r2_prims_vs_refcuda.jsonl 2> gpurun_out/r2_prims_vs_refcuda.err
 tail -1 gpurun_out/r2_prims_vs_refcuda.jsonl | cut -c1-400
+# 7. the weakly compressible fluid (EquationOfStateConfig, SURVEY §8(d) "cheap variant") on the binned path: 161.5 B / particle-substep
+python bench.py --model eos --steps 16 --warmup 4 --no-cpu-baseline > gpurun_out/r2_bench_eos.log 2>&1
+cut -c1-300 gpurun_out/r2_bench_eos.log | tail -1
