@@ -278,17 +278,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
           float Cc[9];
 #pragma unroll
           for (int d = 0; d < 9; ++d) Cc[d] = pars[s + (ZPC_PB_C + d) * TS];
-          const float vol = volume * J, J2 = J * J, J4 = J2 * J2;
-          const float pressure = pp.a * (1.f / (J * J2 * J4) - 1.f), visc = pp.b;
-          K[0] = ((Cc[0] + Cc[0]) * visc - pressure) * vol;
-          K[1] = (Cc[1] + Cc[3]) * visc * vol;
-          K[2] = (Cc[2] + Cc[6]) * visc * vol;
-          K[3] = (Cc[3] + Cc[1]) * visc * vol;
-          K[4] = ((Cc[4] + Cc[4]) * visc - pressure) * vol;
-          K[5] = (Cc[5] + Cc[7]) * visc * vol;
-          K[6] = (Cc[6] + Cc[2]) * visc * vol;
-          K[7] = (Cc[7] + Cc[5]) * visc * vol;
-          K[8] = ((Cc[8] + Cc[8]) * visc - pressure) * vol;
+          zpcm::eos_contrib(Cc, J, volume, pp.a, pp.b, K);
         } else if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, K);
         else if constexpr (MODEL == 2 || MODEL == 3) {
           float *lj = scalar + (size_t)p0 + gorder[pos];

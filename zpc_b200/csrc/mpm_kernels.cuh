@@ -215,17 +215,7 @@ ZPC_HD void g2p2g_particle(const zpc_particles_view &P, size_t p, GA tb, const f
   if constexpr (MODEL == 4) {
     float J = P.J[p];
     J = (1 + (C[0] + C[4] + C[8]) * dt) * J;
-    const float vol = volume * J, J2 = J * J, J4 = J2 * J2;
-    const float pressure = prm.a * (1.f / (J * J2 * J4) - 1.f), visc = prm.b;
-    contrib[0] = ((C[0] + C[0]) * visc - pressure) * vol;
-    contrib[1] = (C[1] + C[3]) * visc * vol;
-    contrib[2] = (C[2] + C[6]) * visc * vol;
-    contrib[3] = (C[3] + C[1]) * visc * vol;
-    contrib[4] = ((C[4] + C[4]) * visc - pressure) * vol;
-    contrib[5] = (C[5] + C[7]) * visc * vol;
-    contrib[6] = (C[6] + C[2]) * visc * vol;
-    contrib[7] = (C[7] + C[5]) * visc * vol;
-    contrib[8] = ((C[8] + C[8]) * visc - pressure) * vol;
+    zpcm::eos_contrib(C, J, volume, prm.a, prm.b, contrib);
   } else {
     float Fo[9], tmp[9], F[9];
 #pragma unroll

@@ -281,6 +281,23 @@ ZPC_HD void stress_vonmises(float volume, float mu, float lam, float yield_stres
     for (int r = 0; r < 3; ++r) PF[3 * c + r] = (P[r] * F[c] + P[3 + r] * F[3 + c] + P[6 + r] * F[6 + c]) * volume;
 }
 
+// EquationOfStateConfig branch of P2GTransfer / G2P2GTransfer (P2G.hpp:66-83): weakly compressible fluid, pressure from J with the
+// exponent fixed to 7 ("from Bow"), viscous part from the symmetrised C; contrib before the -dt * D_inv scaling
+ZPC_HD void eos_contrib(const float (&C)[9], float J, float volume, float bulk, float viscosity, float (&contrib)[9]) {
+  const float vol = volume * J;
+  const float J2 = J * J, J4 = J2 * J2;
+  const float pressure = bulk * (1.f / (J * J2 * J4) - 1.f);
+  contrib[0] = ((C[0] + C[0]) * viscosity - pressure) * vol;
+  contrib[1] = (C[1] + C[3]) * viscosity * vol;
+  contrib[2] = (C[2] + C[6]) * viscosity * vol;
+  contrib[3] = (C[3] + C[1]) * viscosity * vol;
+  contrib[4] = ((C[4] + C[4]) * viscosity - pressure) * vol;
+  contrib[5] = (C[5] + C[7]) * viscosity * vol;
+  contrib[6] = (C[6] + C[2]) * viscosity * vol;
+  contrib[7] = (C[7] + C[5]) * viscosity * vol;
+  contrib[8] = ((C[8] + C[8]) * viscosity - pressure) * vol;
+}
+
 // parameters of the plastic models as the kernels take them: Drucker-Prager {cohesion, beta, yieldSurface, -}, flag = volumeCorrection;
 // NACC {bulk, xi, beta, Msqr}, flag = hardeningOn
 struct PlasticPrm {

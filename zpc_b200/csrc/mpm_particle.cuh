@@ -111,19 +111,8 @@ static ZPC_HD void p2g_scatter_particle_eos(const float (&pos)[3], const float (
                                                                 float *tiles, int nch, float dx, float dt, float volume, float bulk,
                                                                 float viscosity) {
   const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
-  const float vol = volume * J;
-  const float J2 = J * J, J4 = J2 * J2;
-  const float pressure = bulk * (1.f / (J * J2 * J4) - 1.f);
   float contrib[9];
-  contrib[0] = ((C[0] + C[0]) * viscosity - pressure) * vol;
-  contrib[1] = (C[1] + C[3]) * viscosity * vol;
-  contrib[2] = (C[2] + C[6]) * viscosity * vol;
-  contrib[3] = (C[3] + C[1]) * viscosity * vol;
-  contrib[4] = ((C[4] + C[4]) * viscosity - pressure) * vol;
-  contrib[5] = (C[5] + C[7]) * viscosity * vol;
-  contrib[6] = (C[6] + C[2]) * viscosity * vol;
-  contrib[7] = (C[7] + C[5]) * viscosity * vol;
-  contrib[8] = ((C[8] + C[8]) * viscosity - pressure) * vol;
+  zpcm::eos_contrib(C, J, volume, bulk, viscosity, contrib);
 #pragma unroll
   for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
   p2g_scatter_core(pos, vel, mass, C, contrib, tb, tiles, nch, dx);
