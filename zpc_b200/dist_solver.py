@@ -340,6 +340,8 @@ class DistMpmSolver:
             self._cfl_work = None
         dev = L.device
         aos = {k: L.bins.attr(k).clone() for k in ("x", "v", "m", "C", "F")}
+        if L._side:                                    # logJp / J travel with their particle (one more float per record)
+            aos[L._side] = getattr(L.bins, L._side).clone()
         dest = ownership.owner_of_positions(aos["x"], L.dx)
         new = migrate_particles(aos, dest, self.group)
         moved = int((dest != dist.get_rank(self.group)).sum().item())
