@@ -5,8 +5,10 @@ Each rank runs the single-GPU solver on its own particles.  A grid block that mo
 ("shared") holds only PARTIAL sums after the local P2G, so after P2G every pair of ranks exchanges the 7 channels of
 the blocks they share and adds what it receives; every rank then runs the grid update redundantly on its (now
 complete) copies — one message per neighbour per substep instead of two — and G2P stays local.  The CFL scalar
-max|v|^2 is an all_reduce(max).  Ownership of particles never changes, so a particle that wanders into another
-rank's slab is still correct (its blocks simply become shared); migrating it for load balance is future work.
+max|v|^2 is an all_reduce(max).  Ownership of particles need not change for correctness: a particle that wanders into
+another rank's slab is still right (its blocks simply become shared).  For load balance, migrate() hands every particle
+to the rank that owns its current home block (BlockOwnership over the cuts of shard_by_blocks; one all_to_all of counts,
+one of the particle records).
 
 The exchange topology (which blocks are shared with which rank) is rebuilt only when the partition is, i.e.
 with the re-bin every `rebin_every` substeps (partition="with_rebin").
