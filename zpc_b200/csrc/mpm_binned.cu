@@ -964,11 +964,11 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
                              float yield_stress, zpc_stream_t stream, float *scalar = nullptr, zpcm::PlasticPrm pp = {}) {
   if (g.numChannels != 7 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
     return ZPCB200_E_BADARG;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set{false};  // idempotent: two threads racing here both set the same attribute
+  if (!attr_set.load(std::memory_order_acquire)) {
     ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<3, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
     ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   const int variant = tuning().p2g_sweep;
   float mu, lam;
