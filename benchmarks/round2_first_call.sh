@@ -29,3 +29,6 @@ cut -c1-300 gpurun_out/r2_bench_eos.log | tail -1
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_pending.py -m gpu -q -x \
   -k "plastic_model_matches or cuboid or index_buckets or g2p2g or vonmises_on_the_binned or equation_of_state_on or plastic_models_on" \
   > gpurun_out/r2_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/r2_memcheck.log
+# 9. racecheck on the shared-memory-staged binned kernels, one small case
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_mpm.py -m gpu -q -x \
+  -k "binned_path_matches_oracle and cube8" > gpurun_out/r2_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -3 gpurun_out/r2_racecheck.log
