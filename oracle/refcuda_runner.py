@@ -59,24 +59,32 @@ class RefCuda:
         L.zpcrefcuda_mpm_set_particles(h, _p(P["x"]), _p(P["v"]), _p(P["m"]), _p(P["C"]), _p(P["F"]))
         out = {}
         times = []
+        stages = {k: [] for k in ("partition", "clean", "p2g", "grid_update", "g2p")}
+
+        def timed(name, fn, *a):
+            t = time.perf_counter()
+            r_ = fn(*a)
+            L.zpcrefcuda_sync()
+            stages[name].append(time.perf_counter() - t)
+            return r_
         for _ in range(steps):
             L.zpcrefcuda_sync()
             t0 = time.perf_counter()
-            nb = L.zpcrefcuda_mpm_partition(h)
-            L.zpcrefcuda_mpm_clean_grid(h)
-            L.zpcrefcuda_mpm_p2g(h, C.c_float(dt), C.c_float(E), C.c_float(nu), C.c_float(P["volume"]))
+            nb = timed("partition", L.zpcrefcuda_mpm_partition, h)
+            timed("clean", L.zpcrefcuda_mpm_clean_grid, h)
+            timed("p2g", L.zpcrefcuda_mpm_p2g, h, C.c_float(dt), C.c_float(E), C.c_float(nu), C.c_float(P["volume"]))
             if collect and steps == 1:
                 keys = np.empty((nb, 3), np.int32); g1 = np.empty((nb, 7, 64), np.float32)
                 L.zpcrefcuda_mpm_get_keys(h, _p(keys)); L.zpcrefcuda_mpm_get_grid(h, _p(g1))
                 out.update(active_keys=keys, grid_p2g=g1)
-            mx = L.zpcrefcuda_mpm_grid_update(h, C.c_float(dt), C.c_float(gravity), C.c_int(mode))
+            mx = timed("grid_update", L.zpcrefcuda_mpm_grid_update, h, C.c_float(dt), C.c_float(gravity), C.c_int(mode))
             if collect and steps == 1:
                 g2 = np.empty((nb, 7, 64), np.float32)
                 L.zpcrefcuda_mpm_get_grid(h, _p(g2))
                 out.update(grid_upd=g2, max_vel_sqr=np.float32(mx), nblocks=nb)
-            L.zpcrefcuda_mpm_g2p(h, C.c_float(dt))
-            L.zpcrefcuda_sync()
+            timed("g2p", L.zpcrefcuda_mpm_g2p, h, C.c_float(dt))
             times.append(time.perf_counter() - t0)
+        out["stage_ms"] = {k: [1e3 * t for t in v] for k, v in stages.items()}
         if collect:
             x = np.empty((n, 3), np.float32); v = np.empty((n, 3), np.float32)
             Cm = np.empty((n, 9), np.float32); F = np.empty((n, 9), np.float32)
@@ -95,12 +103,14 @@ def main(argv):
         P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}
         P["dx"], P["volume"] = float(z["dx"]), float(z["volume"])
         out = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), int(z["mode"]))
+        out.pop("stage_ms", None)
         np.savez(argv[2], **out)
     elif argv[0] == "overlay":
         z = np.load(argv[1])
         P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}
         P["dx"], P["volume"] = float(z["dx"]), float(z["volume"])
         out = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), int(z["mode"]), overlay=True)
+        out.pop("stage_ms", None)
         np.savez(argv[2], **out)
     elif argv[0] == "lbvh":
         n = int(argv[1])
@@ -151,7 +161,8 @@ def main(argv):
         out = r.substep(P, synth.DT, synth.MODEL["E"], synth.MODEL["nu"], synth.GRAVITY, 1, steps=steps + warmup, collect=False,
                         expected_blocks=max(n // 64, 1024))
         t = out["times"][warmup:]
-        print(json.dumps(dict(impl="reference-cuda", n=n, ms_per_step=float(t.mean() * 1e3), ms_min=float(t.min() * 1e3),
+        stage = {k: float(np.mean(v[warmup:])) for k, v in out["stage_ms"].items()}
+        print(json.dumps(dict(impl="reference-cuda", n=n, ms_per_step=float(t.mean() * 1e3), ms_min=float(t.min() * 1e3), stage_ms=stage,
                               value=n / float(t.mean()), unit="particle-substeps/s", steps=steps, warmup=warmup,
                               note="the reference's own CUDA functors on cuda_exec(), wall clock around a synchronised substep "
                                    "(partition + clean + P2G + mv+=rhs + update + G2P), particles resident in HBM")))
