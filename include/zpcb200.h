@@ -196,6 +196,9 @@ typedef struct zpc_equation_of_state {
   float bulk, gamma, viscosity;
 } zpc_equation_of_state;
 
+/* model_kind of the entries that take any model through a pointer (zpcb200_g2p2g_apic, zpcb200_sg_p2g_apic_model) */
+enum { ZPC_MODEL_FIXED_COROTATED = 0, ZPC_MODEL_VONMISES = 1, ZPC_MODEL_DRUCKER_PRAGER = 2, ZPC_MODEL_NACC = 3, ZPC_MODEL_EOS = 4 };
+
 /* An analytic Collider — geometry/Collider.h:10-143 over AnalyticLevelSet<Plane> / <Sphere> / <Cuboid>
  * (geometry/AnalyticLevelSet.h:11-43, 130-157, 55-126) with its rigid motion x = R s X + b (Collider.h:16-24, 136-143):
  * translation b and its rate, rotation R (row-major) and angular velocity, uniform scale s and its rate.  The level set
@@ -290,7 +293,6 @@ int zpcb200_grid_update_bc(zpc_grids_view grids, zpc_hashtable_view table, float
  * not modified, logJp is read only), W * (P F^T vol * D_inv) * (x_i - x_p) is ADDED to gridr (clear it first, like DofFill).
  * model_kind selects the struct `model` points to (host memory).  The reference's dof_view types do not compile under gcc 13, so
  * this entry is checked against a restatement of the source only (oracle zo_g2p2g: parity unpinned). */
-enum { ZPC_MODEL_FIXED_COROTATED = 0, ZPC_MODEL_VONMISES = 1, ZPC_MODEL_DRUCKER_PRAGER = 2, ZPC_MODEL_NACC = 3, ZPC_MODEL_EOS = 4 };
 int zpcb200_g2p2g_apic(zpc_particles_view pars, zpc_hashtable_view table, float dx, float dt, int model_kind, const void *model,
                        const float *gridv, float *gridr, zpc_stream_t stream);
 
@@ -347,6 +349,11 @@ int zpcb200_sg_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_
 int zpcb200_sg_clean(zpc_sparsegrid_view sg, zpc_stream_t stream);
 int zpcb200_sg_p2g_apic_fcr(zpc_particles_view pars, zpc_sparsegrid_view sg, float dt, zpc_fixed_corotated model,
                             zpc_stream_t stream);
+/* P2GTransfer with any of the five constitutive models on the SparseGrid (model_kind = ZPC_MODEL_*, model -> the matching struct,
+ * host memory; J / logJp in the particle view where the model needs them) and the J-variant of G2PTransfer. */
+int zpcb200_sg_p2g_apic_model(zpc_particles_view pars, zpc_sparsegrid_view sg, float dt, int model_kind, const void *model,
+                              zpc_stream_t stream);
+int zpcb200_sg_g2p_apic_eos(zpc_particles_view pars, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream);
 int zpcb200_sg_grid_update(zpc_sparsegrid_view sg, float dt, const float extf_host[3], int mode, float *maxVelSqr,
                            zpc_stream_t stream);
 int zpcb200_sg_g2p_apic(zpc_particles_view pars, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream);

@@ -543,6 +543,46 @@ def test_equation_of_state_on_the_binned_path(oracle, staged):
         api.set_tuning(-1, 1)
 
 
+@pytest.mark.parametrize("model", ["vonmises", "sand", "nacc", "eos"])
+def test_sparsegrid_runs_every_model(oracle, model):
+    """zpcb200_sg_p2g_apic_model / zpcb200_sg_g2p_apic_eos: the any-order kernels instantiated for SparseGrid<3,f32,8>; grid after P2G
+    compared per NODE (global cell coordinate) with the oracle's functor on the legacy side-4 grid, like the fixed-corotated test"""
+    from tests.test_gpu_sparsegrid import _build, _host_table, _nodes
+    from zpc_b200 import api
+    name = {"vonmises": "mpm_cube6_vonmises", "sand": "mpm_cube6_sand", "nacc": "mpm_cube6_nacc", "eos": "mpm_cube6_eos"}[model]
+    z = np.load(os.path.join(G, name + ".npz"))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **dict(ast.literal_eval(str(z["kw"]))))
+    n, dx = P["x"].shape[0], P["dx"]
+    if model in ("sand", "nacc"):
+        P["logJp"] = z["logJp_in"].copy()
+    if model == "eos":
+        P["J"] = z["J_in"].copy()
+    m = {"vonmises": lambda: api.model_vonmises(P["volume"], E, NU, float(z["ys"])),
+         "sand": lambda: api.model_drucker_prager(P["volume"], E, NU, SAND["cohesion"], SAND["beta"], SAND["volumeCorrection"], SAND["yieldSurface"]),
+         "nacc": lambda: api.model_nacc(P["volume"], NACC["E"], NACC["nu"], NACC["fa"], NACC["xi"], NACC["beta"], NACC["hardeningOn"]),
+         "eos": lambda: api.model_eos(P["volume"], 4.0e4, 7.15, 0.01)}[model]()
+    pars, sg = _build(P)
+    t = _host_table(sg)
+    nb = t["nblocks"]
+    api.sg_clean(sg)
+    api.sg_p2g_transfer(pars, sg, synth.DT, m)
+    torch.cuda.synchronize()
+    g1 = sg.grid[:nb].cpu().numpy()
+    code_o, val_o = _nodes(z["active_keys"] * 4, z["grid_p2g"], 4)           # the reference-generated grid, per node
+    code_s, val_s = _nodes(t["active_keys"], g1, 8)
+    pos = np.searchsorted(code_s, code_o)
+    assert (pos < code_s.shape[0]).all() and np.array_equal(code_s[pos], code_o)
+    rhs = {"vonmises": RTOL_STRESS, "sand": RTOL_STRESS, "nacc": 1e-3, "eos": RTOL}[model]
+    check_channels(val_s[pos], val_o, 1, "sg p2g " + model, [RTOL] * 4 + [rhs] * 3)
+    if model in ("sand", "nacc"):
+        assert np.abs(pars.logJp.cpu().numpy() - z["logJp"]).max() <= 2e-5
+    if model == "eos":
+        mx = torch.zeros(1, device="cuda")
+        api.sg_compute_grid_velocity(sg, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+        api.sg_g2p_transfer(pars, sg, synth.DT, model=m)
+        check_channels(pars.J.cpu().numpy()[:, None], z["J"][:, None], 1, "sg eos J", 3e-5)
+
+
 # last: a failed stream capture could leave the process unable to launch — nothing runs after it
 def test_graph_replay_equals_eager_substeps():
     """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same

@@ -419,7 +419,12 @@ def sg_clean(sg, stream=None):
 
 
 def sg_p2g_transfer(pars, sg, dt, model, stream=None):
-    _check(lib().zpcb200_sg_p2g_apic_fcr(pars.view(), sg.view(), C.c_float(dt), model, _stream_ptr(stream)), "sg_p2g")
+    if isinstance(model, zpc_fixed_corotated):
+        _check(lib().zpcb200_sg_p2g_apic_fcr(pars.view(), sg.view(), C.c_float(dt), model, _stream_ptr(stream)), "sg_p2g")
+        return
+    kind = {zpc_vonmises_fixed_corotated: 1, zpc_drucker_prager: 2, zpc_nacc: 3, zpc_equation_of_state: 4}[type(model)]
+    _check(lib().zpcb200_sg_p2g_apic_model(pars.view(), sg.view(), C.c_float(dt), C.c_int(kind), C.byref(model), _stream_ptr(stream)),
+           "sg_p2g(model)")
 
 
 def sg_compute_grid_velocity(sg, dt, extf, mode, max_vel_sqr, stream=None):
@@ -428,7 +433,10 @@ def sg_compute_grid_velocity(sg, dt, extf, mode, max_vel_sqr, stream=None):
                                         _stream_ptr(stream)), "sg_grid_update")
 
 
-def sg_g2p_transfer(pars, sg, dt, stream=None):
+def sg_g2p_transfer(pars, sg, dt, stream=None, model=None):
+    if isinstance(model, zpc_equation_of_state):
+        _check(lib().zpcb200_sg_g2p_apic_eos(pars.view(), sg.view(), C.c_float(dt), _stream_ptr(stream)), "sg_g2p(eos)")
+        return
     _check(lib().zpcb200_sg_g2p_apic(pars.view(), sg.view(), C.c_float(dt), _stream_ptr(stream)), "sg_g2p")
 
 

@@ -282,6 +282,62 @@ int zpcb200_sg_p2g_apic_fcr(zpc_particles_view P, zpc_sparsegrid_view sg, float 
   return ZPCB200_OK;
 }
 
+// the other constitutive models of P2GTransfer on the SparseGrid: the any-order kernels of mpm_kernels.cuh instantiated for SparseGrid8
+int zpcb200_sg_p2g_apic_model(zpc_particles_view P, zpc_sparsegrid_view sg, float dt, int model_kind, const void *model, zpc_stream_t stream) {
+  if (!model || (unsigned)model_kind > 4u || sg.numChannels != 7 || !sg.grid || !sg_table_ok(sg.table)) return ZPCB200_E_BADARG;
+  if (P.count && (!P.X || !P.V || !P.M || !P.C || (model_kind == ZPC_MODEL_EOS ? !P.J : !P.F) ||
+                  ((model_kind == ZPC_MODEL_DRUCKER_PRAGER || model_kind == ZPC_MODEL_NACC) && !P.logJp)))
+    return ZPCB200_E_BADARG;
+  float dx;
+  if (!sg_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  if (!P.count) return ZPCB200_OK;
+  const unsigned grid = (unsigned)((P.count + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  const zpcp::SparseGrid8 ga{sg.table};
+  float mu = 0.f, lam = 0.f;
+  switch (model_kind) {
+    case ZPC_MODEL_FIXED_COROTATED: {
+      const auto &m = *(const zpc_fixed_corotated *)model;
+      zpcm::lame_host(m.E, m.nu, mu, lam);
+      p2g_aos_kernel<<<grid, 128, 0, s>>>(P, ga, sg.grid, sg.numChannels, dx, dt, m.volume, mu, lam);
+    } break;
+    case ZPC_MODEL_VONMISES: {
+      const auto &m = *(const zpc_vonmises_fixed_corotated *)model;
+      zpcm::lame_host(m.E, m.nu, mu, lam);
+      p2g_aos_vm_kernel<<<grid, 128, 0, s>>>(P, ga, sg.grid, sg.numChannels, dx, dt, m.volume, mu, lam, m.yieldStress);
+    } break;
+    case ZPC_MODEL_DRUCKER_PRAGER: {
+      const auto &m = *(const zpc_drucker_prager *)model;
+      zpcm::lame_host(m.E, m.nu, mu, lam);
+      p2g_aos_plastic_kernel<2><<<grid, 128, 0, s>>>(P, ga, sg.grid, sg.numChannels, dx, dt, m.volume, mu, lam,
+                                                     PlasticParams{m.cohesion, m.beta, m.yieldSurface, 0.f, m.volumeCorrection});
+    } break;
+    case ZPC_MODEL_NACC: {
+      const auto &m = *(const zpc_nacc *)model;
+      if (m.dim != 3) return ZPCB200_E_BADARG;
+      zpcm::lame_host(m.E, m.nu, mu, lam);
+      p2g_aos_plastic_kernel<3><<<grid, 128, 0, s>>>(P, ga, sg.grid, sg.numChannels, dx, dt, m.volume, mu, lam,
+                                                     PlasticParams{zpcm::nacc_bulk_host(m.E, m.nu), m.xi, m.beta, zpcm::nacc_msqr_host(m.fa, m.dim), m.hardeningOn});
+    } break;
+    default: {
+      const auto &m = *(const zpc_equation_of_state *)model;
+      p2g_aos_eos_kernel<<<grid, 128, 0, s>>>(P, ga, sg.grid, sg.numChannels, dx, dt, m.volume, m.bulk, m.viscosity);
+    } break;
+  }
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+int zpcb200_sg_g2p_apic_eos(zpc_particles_view P, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream) {
+  if (sg.numChannels < 4 || !sg.grid || !sg_table_ok(sg.table)) return ZPCB200_E_BADARG;
+  if (P.count && (!P.X || !P.V || !P.C || !P.J)) return ZPCB200_E_BADARG;
+  float dx;
+  if (!sg_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  if (!P.count) return ZPCB200_OK;
+  g2p_aos_kernel<true><<<(unsigned)((P.count + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, zpcp::SparseGrid8{sg.table}, sg.grid, sg.numChannels, dx, dt);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
 int zpcb200_sg_grid_update(zpc_sparsegrid_view sg, float dt, const float extf[3], int mode, float *maxVelSqr, zpc_stream_t stream) {
   if (!sg.grid || !sg.table.cnt || !extf || !maxVelSqr || (mode != 0 && mode != 1) || sg.numChannels < (mode ? 7 : 4)) return ZPCB200_E_BADARG;
   grid_update_kernel<512><<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(sg.grid, sg.table.cnt, sg.numChannels, sg.numBlocks, dt, extf[0],
