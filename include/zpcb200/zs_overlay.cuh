@@ -9,6 +9,8 @@
 //   zs::b200::partition_for_particles / clean_grid_blocks / p2g / compute_grid_block_velocity / g2p
 //       the MPM functor launches of SURVEY §3.1 on the reference's own containers (Particles, HashTable, Grids):
 //       pol(range(n), P2GTransfer{cuda_c, wrapv<apic>{}, dt, model, pars, table, grids})  becomes  b200::p2g(pol, dt, model, pars, table, grids).
+//   zs::b200::BinnedParticles + bin_particles / rebin_particles / p2g / g2p   the block-binned fast path on TileVector<f32, 32> (the type of
+//       Particles::particleBins) with zs::Vector metadata.
 //
 // Temporary storage comes from the policy's stream-ordered pool (streamMemAlloc / streamMemFree, like
 // cuda/execution/ExecutionPolicy.cuh:806-815); errors surface like the reference's (checkCuApiError is private to Cuda, so a
@@ -18,6 +20,7 @@
 #include <string>
 
 #include "zensim/container/HashTable.hpp"
+#include "zensim/container/TileVector.hpp"
 #include "zensim/container/Vector.hpp"
 #include "zensim/cuda/execution/ExecutionPolicy.cuh"
 #include "zensim/geometry/AnalyticLevelSet.h"
@@ -307,6 +310,70 @@ namespace zs {
     inline void sg_g2p(const B200ExecutionPolicy &pol, float dt, SparseGrid<3, f32, 8> &sg, Particles<f32, 3> &pars,
                        const source_location &loc = source_location::current()) {
       pol.b200Done(zpcb200_sg_g2p_apic(view(pars), view(sg), dt, pol.b200Stream()), "zpcb200_sg_g2p_apic", loc);
+    }
+
+    /// ---- the block-binned fast path on the reference's containers ------------------------------------------------------------
+    /// Particles binned by home block live in TileVector<f32, 32> — the type of Particles::particleBins (geometry/Structurefree.hpp:220) —
+    /// with the 25 channels {m, x, v, C, F}; bin metadata and the cell-order cache are zs::Vectors.  Two particle buffers: re-binning
+    /// ping-pongs between them.  Usage (one substep): partition_for_particles(pol, table, bins) [every rebinEvery substeps, followed by
+    /// rebin], clean_grid_blocks, p2g, compute_grid_block_velocity, g2p.
+    struct BinnedParticles {
+      using TV = TileVector<f32, 32>;
+      TV cur, alt;
+      Vector<int> binStart, binKey, numBins, cellOrderValid, order;
+      Vector<unsigned short> cellOrder, cellStart;
+      size_t n;
+      int binCapacity;
+      BinnedParticles(size_t n_, int binCapacity_, ProcID dev = 0)
+          : cur{{{"m", 1}, {"x", 3}, {"v", 3}, {"C", 9}, {"F", 9}}, n_, memsrc_e::device, dev},
+            alt{{{"m", 1}, {"x", 3}, {"v", 3}, {"C", 9}, {"F", 9}}, n_, memsrc_e::device, dev},
+            binStart{(size_t)binCapacity_ + 1, memsrc_e::device, dev},
+            binKey{(size_t)binCapacity_ * 3, memsrc_e::device, dev},
+            numBins{1, memsrc_e::device, dev},
+            cellOrderValid{1, memsrc_e::device, dev},
+            order{n_ ? n_ : 1, memsrc_e::device, dev},
+            cellOrder{n_ ? n_ : 1, memsrc_e::device, dev},
+            cellStart{(size_t)binCapacity_ * ZPCB200_CELL_GROUPS_PAD, memsrc_e::device, dev},
+            n{n_},
+            binCapacity{binCapacity_} {
+        static_assert(ZPC_PB_M == 0 && ZPC_PB_X == 1 && ZPC_PB_V == 4 && ZPC_PB_C == 7 && ZPC_PB_F == 16 && ZPC_PB_NCH == 25, "channel order");
+        cellOrderValid.setVal(0);
+      }
+      zpc_bins_view view(TV &tv) {
+        return zpc_bins_view{zpc_tilevector_view{(float *)tv.data(), n, (int)tv.numChannels()}, binStart.data(), binKey.data(), numBins.data(),
+                             binCapacity, cellOrder.data(), cellStart.data(), cellOrderValid.data()};
+      }
+      zpc_bins_view view() { return view(cur); }
+      /// positions as an iterator port over channel "x" of the current buffer (for the partition build)
+      zpc_port xPort() { return zpc_port{(void *)((float *)cur.data() + ZPC_PB_X * 32), 0, 5, 31, ZPC_PB_NCH}; }
+    };
+    /// AoS Particles -> bins (stable sort by home block and cell, AoSoA gather); order[i] = source particle of slot i
+    inline void bin_particles(const B200ExecutionPolicy &pol, Particles<f32, 3> &pars, HashTable<i32, 3, int> &table, float dx, BinnedParticles &bins,
+                              const source_location &loc = source_location::current()) {
+      pol.b200TwoPhase("zpcb200_bin_particles", loc, zpcb200_bin_particles, view(pars), view(table), dx, bins.view(), bins.order.data());
+    }
+    /// re-bin after the particles have moved (and the partition has been rebuilt): cur -> alt, swap
+    inline void rebin_particles(const B200ExecutionPolicy &pol, HashTable<i32, 3, int> &table, float dx, BinnedParticles &bins,
+                                const source_location &loc = source_location::current()) {
+      pol.b200TwoPhase("zpcb200_rebin_particles", loc, zpcb200_rebin_particles, bins.view(bins.cur), view(table), dx, bins.view(bins.alt));
+      std::swap(bins.cur, bins.alt);
+    }
+    inline void unbin_particles(const B200ExecutionPolicy &pol, BinnedParticles &bins, Particles<f32, 3> &pars,
+                                const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_unbin_particles(bins.view(), view(pars), pol.b200Stream()), "zpcb200_unbin_particles", loc);
+    }
+    inline void partition_for_particles(const B200ExecutionPolicy &pol, HashTable<i32, 3, int> &table, BinnedParticles &bins, float dx,
+                                        int enlargeLo = 0, int enlargeHi = 2, const source_location &loc = source_location::current()) {
+      pol.b200TwoPhase("zpcb200_partition_build", loc, zpcb200_partition_build, bins.xPort(), bins.n, dx, view(table), enlargeLo, enlargeHi, (int *)nullptr);
+    }
+    inline void p2g(const B200ExecutionPolicy &pol, float dt, const FixedCorotatedConfig &model, BinnedParticles &bins, HashTable<i32, 3, int> &table,
+                    Grids<f32, 3, 4> &grids, const source_location &loc = source_location::current()) {
+      zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
+      pol.b200Done(zpcb200_p2g_apic_fcr_binned(bins.view(), view(table), view(grids), dt, m, pol.b200Stream()), "zpcb200_p2g_apic_fcr_binned", loc);
+    }
+    inline void g2p(const B200ExecutionPolicy &pol, float dt, Grids<f32, 3, 4> &grids, HashTable<i32, 3, int> &table, BinnedParticles &bins,
+                    const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_g2p_apic_binned(bins.view(), view(table), view(grids), dt, pol.b200Stream()), "zpcb200_g2p_apic_binned", loc);
     }
   }  // namespace b200
 }  // namespace zs

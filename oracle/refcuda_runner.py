@@ -8,6 +8,8 @@ test session or a bench run down with it.
   python -m oracle.refcuda_runner bench G S STEPS WARMUP    # elastic cube of S^3 cells in a G^3 domain; prints one JSON line
   python -m oracle.refcuda_runner overlay IN.npz OUT.npz   # the same substep on the reference's containers through
                                                             # include/zpcb200/zs_overlay.cuh (b200_exec() + zs::b200::* launches)
+  python -m oracle.refcuda_runner binned IN.npz OUT.npz     # IN also carries steps, rebin_every: the reference's functors for `steps`
+                                                            # substeps vs the overlay's block-binned fast path (zs::b200::BinnedParticles)
   python -m oracle.refcuda_runner lbvh N OUT.npz            # the reference's own LBvh::build on cuda_exec() and on b200_exec()
   python -m oracle.refcuda_runner prims-bench LOG2N ITERS   # C5: the reference's CudaExecutionPolicy primitives (and the same generic
                                                             # calls on b200_exec()) timed on the GPU; one JSON line
@@ -112,6 +114,25 @@ def main(argv):
         out = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), int(z["mode"]), overlay=True)
         out.pop("stage_ms", None)
         np.savez(argv[2], **out)
+    elif argv[0] == "binned":
+        z = np.load(argv[1])
+        P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}
+        P["dx"], P["volume"] = float(z["dx"]), float(z["volume"])
+        steps, every = int(z["steps"]), int(z["rebin_every"])
+        ref = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), 1, steps=steps, collect=True)
+        n = P["x"].shape[0]
+        L = r.L
+        h = C.c_void_p(L.zpcrefcuda_mpm_create(C.c_int(n), C.c_float(P["dx"]), C.c_int(max(n // 8, 64))))
+        L.zpcrefcuda_mpm_set_particles(h, _p(P["x"]), _p(P["v"]), _p(P["m"]), _p(P["C"]), _p(P["F"]))
+        order = np.empty(n, np.int32)
+        L.zpcrefcuda_overlay_binned_substeps(h, C.c_int(steps), C.c_int(every), C.c_float(float(z["dt"])), C.c_float(float(z["E"])),
+                                             C.c_float(float(z["nu"])), C.c_float(P["volume"]), C.c_float(float(z["gravity"])), _p(order))
+        x = np.empty((n, 3), np.float32); v = np.empty((n, 3), np.float32); Cm = np.empty((n, 9), np.float32); F = np.empty((n, 9), np.float32)
+        m = np.empty(n, np.float32)
+        L.zpcrefcuda_mpm_get_particles(h, _p(x), _p(v), _p(Cm), _p(F))
+        L.zpcrefcuda_mpm_get_mass(h, _p(m))
+        L.zpcrefcuda_mpm_destroy(h)
+        np.savez(argv[2], ref_x=ref["x"], ref_v=ref["v"], ref_C=ref["C"], ref_F=ref["F"], ref_m=P["m"], x=x, v=v, C=Cm, F=F, m=m)
     elif argv[0] == "lbvh":
         n = int(argv[1])
         rs = np.random.RandomState(77)

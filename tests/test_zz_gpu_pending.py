@@ -583,6 +583,30 @@ def test_sparsegrid_runs_every_model(oracle, model):
         check_channels(pars.J.cpu().numpy()[:, None], z["J"][:, None], 1, "sg eos J", 3e-5)
 
 
+def test_overlay_fast_path_on_the_references_containers(tmp_path):
+    """zs::b200::BinnedParticles (TileVector<f32,32> = the type of Particles::particleBins, zs::Vector metadata): four substeps with a re-bin
+    through the overlay's block-binned fast path vs the same four substeps through the reference's own functors on cuda_exec(), both on
+    the reference's containers, in one process of their own; particles are matched by their (unique) mass."""
+    import subprocess
+    import sys
+    from oracle.refcuda_runner import RefCuda
+    if not RefCuda.available():
+        pytest.skip("oracle/_ref/libzpcref_cuda.so not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    P = synth.elastic_cube(10, 32, jitter_F=0.03, jitter_C=0.3, seed=5)
+    P["v"][:] = P["v"] * 6.0
+    n = P["m"].shape[0]
+    P["m"] = (P["m"] * (1.0 + 0.1 * np.arange(n) / n)).astype(np.float32)
+    fin, fout = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(fin, dt=synth.DT * 10, E=E, nu=NU, gravity=synth.GRAVITY, mode=1, steps=4, rebin_every=2, **P)
+    r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "binned", fin, fout], cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    z = np.load(fout)
+    assert np.unique(z["m"]).size == n and np.array_equal(np.sort(z["m"]), np.sort(z["ref_m"]))
+    o, ro = np.argsort(z["m"], kind="stable"), np.argsort(z["ref_m"], kind="stable")
+    check_particles({k: z[k][o] for k in "xvCF"}, {k: z["ref_" + k][ro] for k in "xvCF"}, P["dx"], "overlay fast path vs reference functors", rtol=5e-5)
+
+
 # last: a failed stream capture could leave the process unable to launch — nothing runs after it
 def test_graph_replay_equals_eager_substeps():
     """MpmSolver.capture_cycle / replay_cycle: two replays of the captured 2 x rebin_every substeps give the particles the same
