@@ -131,4 +131,11 @@ void hm_g2p2g(int model, zpc_particles_view P, zpc_hashtable_view tb, const floa
     else g2p2g_particle<4>(P, p, g, gridv, gridr, dx, dt, volume, mu, lam, pp);
   }
 }
+// the table lookups the kernels use (mpm_math.cuh), on host copies of the tables
+void hm_table_query(int n, const int *keys3, int table_size, const int *tkeys, const int *tindices, int *out) {
+  for (int i = 0; i < n; ++i) out[i] = zpcm::table_query(keys3[3 * i], keys3[3 * i + 1], keys3[3 * i + 2], table_size, tkeys, tindices);
+}
+void hm_bht_query(int n, const int *keys3, zpc_bht_view tb, int *out) {
+  for (int i = 0; i < n; ++i) out[i] = zpcm::bht_query(keys3[3 * i], keys3[3 * i + 1], keys3[3 * i + 2], tb);
+}
 }

@@ -150,3 +150,33 @@ def test_g2p2g_on_the_host_matches_the_restated_functor(hm, oracle, model):
         g = oracle.p2g(P, tab, dx, synth.DT, E, NU, P["volume"])
         rhs = g[:, 4:7].transpose(0, 2, 1).reshape(-1, 3) / np.float32(-synth.DT)
         assert np.abs(r - rhs).max() <= 2e-5 * np.abs(rhs).max()
+
+
+def test_table_lookups_on_the_host_resolve_the_oracles_tables(hm, oracle):
+    """zpcm::table_query (legacy HashTable: 64-bit hash_combine, stride-127 probing) and zpcm::bht_query (three universal hashes,
+    buckets of 16) — the lookups every transfer kernel performs — on tables the ORACLE built (i.e. the reference's insert order):
+    every active key resolves to its index, absent keys to -1"""
+    rs = np.random.RandomState(3)
+    P = synth.elastic_cube(9, 32, origin_cells=-11, shuffle_seed=2)
+    n, dx = P["x"].shape[0], P["dx"]
+    tab = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    nb = tab["nblocks"]
+    absent = (tab["active_keys"][:50] + np.int32([1000, 0, 0])).astype(np.int32)
+    keys = np.ascontiguousarray(np.concatenate([tab["active_keys"], absent]), np.int32)
+    out = np.empty(keys.shape[0], np.int32)
+    tk, ti = np.ascontiguousarray(tab["keys"]), np.ascontiguousarray(tab["indices"])
+    hm.hm_table_query(C.c_int(keys.shape[0]), keys.ctypes.data_as(C.c_void_p), C.c_int(tab["table_size"]), tk.ctypes.data_as(C.c_void_p),
+                      ti.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out[:nb], np.arange(nb)) and (out[nb:] == -1).all()
+    # bht: block ORIGINS in cell coordinates as keys
+    t = oracle.bht_new(4 * nb)
+    bkeys = np.ascontiguousarray(tab["active_keys"] * 8, np.int32)
+    idx = oracle.bht_insert(t, bkeys)
+    assert np.array_equal(np.sort(idx), np.arange(nb))
+    hf = oracle.bht_params()
+    view = api.zpc_bht_view(t["keys16"].ctypes.data, t["indices"].ctypes.data, None, None, int(t["table_size"]), int(t["table_size"]) // 16,
+                            None, None, (C.c_uint32 * 6)(*[int(v) for v in hf]))
+    q = np.ascontiguousarray(np.concatenate([bkeys, bkeys[:50] + np.int32([8000, 0, 0])]), np.int32)
+    out2 = np.empty(q.shape[0], np.int32)
+    hm.hm_bht_query(C.c_int(q.shape[0]), q.ctypes.data_as(C.c_void_p), view, out2.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out2[:nb], idx) and (out2[nb:] == -1).all()
