@@ -256,6 +256,19 @@ int zpcb200_p2g_apic_fcr(zpc_particles_view pars, zpc_hashtable_view table, zpc_
 int zpcb200_grid_update(zpc_grids_view grids, const int *cnt, float dt, const float extf_host[3],
                         int mode, float *maxVelSqr, zpc_stream_t stream);
 
+/* GridMomentumToVelocity (simulation/grid/GridOp.hpp:184-214): for every cell of blocks [0, *cnt) whose mass (channel mChn) is not
+ * zero, momentum channels mvChn..mvChn+2 become velocities (mv * (1/m)); *maxVelSqr = max(*maxVelSqr, |v|^2).  No gravity and no
+ * rhs — that is zpcb200_grid_update (ComputeGridBlockVelocity). */
+int zpcb200_grid_momentum_to_velocity(zpc_grids_view grids, const int *cnt, int mChn, int mvChn, float *maxVelSqr,
+                                      zpc_stream_t stream);
+
+/* GridAngularMomentum (GridOp.hpp:216-262): sum6[0..2] += sum over cells with mass of x cross mv, sum6[3..5] += sum of mv,
+ * x = (blockkey*4 + cell coord) * dx; products in float, sums in double (device memory, six doubles, ADDED to: zero them first).
+ * The reference adds six double atomics per cell in launch order; the sums here differ from it only by the order of the double
+ * additions. */
+int zpcb200_grid_angular_momentum(zpc_grids_view grids, zpc_hashtable_view table, int mChn, int mvChn, double *sum6,
+                                  zpc_stream_t stream);
+
 /* host helper: a collider with the default rigid motion */
 zpc_collider zpcb200_collider_static(int geometry, int type, const float origin[3], const float normal_or_radius[3]);
 

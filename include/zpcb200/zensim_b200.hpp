@@ -355,6 +355,18 @@ struct ComputeGridBlockVelocity {  // {cuda_c, wrapv<apic>{}, grids, dt, gravity
     return zpcb200_grid_update(grids.view(), table._cnt.data(), dt, extf, mode, maxVel, pol._stream);
   }
 };
+struct GridMomentumToVelocity {  // {cuda_c, grid, mChn, mvChn, maxVel} (GridOp.hpp:184-214): v = mv / m, no gravity
+  Grids &grids; HashTable &table; int mChn; int mvChn; float *maxVel;
+  int launch(const CudaExecutionPolicy &pol) {
+    return zpcb200_grid_momentum_to_velocity(grids.view(), table._cnt.data(), mChn, mvChn, maxVel, pol._stream);
+  }
+};
+struct GridAngularMomentum {  // {cuda_c, table, grid, mChn, mvChn, sum} (GridOp.hpp:216-262): six doubles on the device, added to
+  HashTable &table; Grids &grids; int mChn; int mvChn; double *sumAngularMomentum;
+  int launch(const CudaExecutionPolicy &pol) {
+    return zpcb200_grid_angular_momentum(grids.view(), table.view(), mChn, mvChn, sumAngularMomentum, pol._stream);
+  }
+};
 // LBvh<3, int, f32> (container/Bvh.hpp:82-174): build(pol, primBvs, refit) / refit(pol, primBvs); boxes = 6 floats {min, max}
 struct LBvh {
   size_t _numLeaves{0};

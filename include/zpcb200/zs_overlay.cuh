@@ -268,6 +268,18 @@ namespace zs {
       const float extf[3] = {0.f, gravity, 0.f};
       pol.b200Done(zpcb200_grid_update(view(grids), table._cnt.data(), dt, extf, mode, maxVel, pol.b200Stream()), "zpcb200_grid_update", loc);
     }
+    /// GridMomentumToVelocity{cuda_c, grids.grid(collocated_c), mChn, mvChn, maxVel} (GridOp.hpp:184-214)
+    inline void grid_momentum_to_velocity(const B200ExecutionPolicy &pol, Grids<f32, 3, 4> &grids, HashTable<i32, 3, int> &table, float *maxVel,
+                                          int mChn = 0, int mvChn = 1, const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_grid_momentum_to_velocity(view(grids), table._cnt.data(), mChn, mvChn, maxVel, pol.b200Stream()),
+                   "zpcb200_grid_momentum_to_velocity", loc);
+    }
+    /// GridAngularMomentum{cuda_c, table, grids.grid(collocated_c), mChn, mvChn, sum} (GridOp.hpp:216-262); sum: six doubles, added to
+    inline void grid_angular_momentum(const B200ExecutionPolicy &pol, HashTable<i32, 3, int> &table, Grids<f32, 3, 4> &grids, double *sum,
+                                      int mChn = 0, int mvChn = 1, const source_location &loc = source_location::current()) {
+      pol.b200Done(zpcb200_grid_angular_momentum(view(grids), view(table), mChn, mvChn, sum, pol.b200Stream()),
+                   "zpcb200_grid_angular_momentum", loc);
+    }
     inline void g2p(const B200ExecutionPolicy &pol, float dt, Grids<f32, 3, 4> &grids, HashTable<i32, 3, int> &table, Particles<f32, 3> &pars,
                     const source_location &loc = source_location::current()) {
       pol.b200Done(zpcb200_g2p_apic(view(pars), view(table), view(grids), dt, pol.b200Stream()), "zpcb200_g2p_apic", loc);

@@ -740,6 +740,51 @@ void zo_grid_update(int nblocks, float *grid, float dt, const float extf[3], int
   *max_vel_sqr = mx;
 }
 
+/* GridMomentumToVelocity (GridOp.hpp:184-214): v = mv * (1/m) on cells with m != 0; max |v|^2.  nch channels per block,
+ * mass in channel mChn, momentum in mvChn..mvChn+2. */
+void zo_grid_momentum_to_velocity(int nblocks, int nch, float *grid, int mChn, int mvChn, float *max_vel_sqr) {
+  float mx = *max_vel_sqr;
+  for (int b = 0; b < nblocks; ++b) {
+    float *tile = grid + (size_t)b * nch * 64;
+    for (int c = 0; c < 64; ++c) {
+      float mass = tile[mChn * 64 + c];             /* :200 */
+      if (mass != 0.f) {
+        mass = 1.f / mass;                          /* :202 */
+        float nrm = 0.f;
+        for (int d = 0; d < 3; ++d) {
+          float vd = tile[(mvChn + d) * 64 + c] * mass;   /* :203 */
+          tile[(mvChn + d) * 64 + c] = vd;
+          nrm += vd * vd;
+        }
+        if (nrm > mx) mx = nrm;                     /* :208-209 */
+      }
+    }
+  }
+  *max_vel_sqr = mx;
+}
+
+/* GridAngularMomentum (GridOp.hpp:216-262): out6[0..2] += x cross mv, out6[3..5] += mv, per cell with m != 0;
+ * x = (blockkey*4 + cell coord)*dx and the cross product in float (Vec cross, VecInterface.hpp:945-956), the sums in double.
+ * The reference adds with atomics in launch order; this loop adds in (block, cell) order. */
+void zo_grid_angular_momentum(int nblocks, int nch, const int *active_keys, const float *grid, float dx, int mChn, int mvChn,
+                              double *out6) {
+  for (int b = 0; b < nblocks; ++b) {
+    const float *tile = grid + (size_t)b * nch * 64;
+    for (int c = 0; c < 64; ++c) {
+      if (tile[mChn * 64 + c] == 0.f) continue;     /* :235 */
+      const int cc[3] = {(c >> 4) & 3, (c >> 2) & 3, c & 3};
+      float x[3], mv[3];
+      for (int d = 0; d < 3; ++d) {
+        x[d] = ((float)active_keys[3 * b + d] * 4.f + (float)cc[d]) * dx;   /* :237-239 */
+        mv[d] = tile[(mvChn + d) * 64 + c];
+      }
+      const float r0 = x[1] * mv[2] - x[2] * mv[1], r1 = x[2] * mv[0] - x[0] * mv[2], r2 = x[0] * mv[1] - x[1] * mv[0];
+      out6[0] += (double)r0; out6[1] += (double)r1; out6[2] += (double)r2;
+      for (int d = 0; d < 3; ++d) out6[3 + d] += (double)mv[d];
+    }
+  }
+}
+
 void zo_g2p(int n, float *x, float *v, float *C, float *F, float dx, float dt, int table_size,
             const int *keys, const int *indices, const float *grid) {
   const float dx_inv = (float)1 / dx;            /* G2P.hpp:45 */

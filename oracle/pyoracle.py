@@ -327,6 +327,19 @@ class Oracle:
                                 C.c_int(mode), _ptr(mx))
         return float(mx[0])
 
+    def grid_momentum_to_velocity(self, grid, m_chn=0, mv_chn=1):
+        mx = np.zeros(1, np.float32)
+        self.lib.zo_grid_momentum_to_velocity(C.c_int(grid.shape[0]), C.c_int(grid.shape[1]), _ptr(grid), C.c_int(m_chn),
+                                              C.c_int(mv_chn), _ptr(mx))
+        return float(mx[0])
+
+    def grid_angular_momentum(self, grid, active_keys, dx, m_chn=0, mv_chn=1):
+        k = np.ascontiguousarray(active_keys, np.int32)
+        out = np.zeros(6, np.float64)
+        self.lib.zo_grid_angular_momentum(C.c_int(grid.shape[0]), C.c_int(grid.shape[1]), _ptr(k), _ptr(grid), C.c_float(dx),
+                                          C.c_int(m_chn), C.c_int(mv_chn), _ptr(out))
+        return out
+
     def apply_boundary(self, grid, active_keys, dx, geom, ctype, p0, p1, motion=None):
         """motion: None (static) or 20 floats b[3], dbdt[3], R[9] row-major, omega[3], s, dsdt"""
         k = np.ascontiguousarray(active_keys, np.int32)
@@ -633,6 +646,15 @@ class Ref:
 
         def g2p(self, dt):
             self.L.zpcref_mpm_g2p(self.h, C.c_float(dt))
+
+        def momentum_to_velocity(self):
+            self.L.zpcref_mpm_momentum_to_velocity(self.h)
+            return float(self.L.zpcref_mpm_get_maxvel(self.h))
+
+        def angular_momentum(self):
+            out = np.zeros(6, np.float64)
+            self.L.zpcref_mpm_angular_momentum(self.h, _ptr(out))
+            return out
 
         def apply_boundary(self, geom, ctype, p0, p1, motion=None):
             a = np.ascontiguousarray(p0, np.float32); b = np.ascontiguousarray(p1, np.float32)

@@ -242,6 +242,26 @@ void zpcref_mpm_g2p_eos(void *h, float dt) {
         G2PTransfer{tag, wrapv<transfer_scheme_e::apic>{}, dt, model, s.grids, s.table, s.pars});
   });
 }
+/// GridMomentumToVelocity (GridOp.hpp:184-214) on the collocated grid: v = mv / m, max |v|^2; no gravity, rhs untouched
+void zpcref_mpm_momentum_to_velocity(void *h) {
+  auto &s = *(RefMpm *)h;
+  s.maxVel.setVal(0.f);
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(Collapse{(size_t)s.nblocks, (size_t)64},
+        GridMomentumToVelocity{tag, s.grids.grid(collocated_c), 0, 1, s.maxVel.data()});
+  });
+}
+/// GridAngularMomentum (GridOp.hpp:216-262): out6 = sum x cross mv (3), sum mv (3), accumulated in double
+void zpcref_mpm_angular_momentum(void *h, double *out6) {
+  auto &s = *(RefMpm *)h;
+  Vector<double> sum{6};
+  for (int i = 0; i != 6; ++i) sum.setVal(0., i);
+  with_policy(s.nthreads, [&](auto &pol, auto tag) {
+    pol(Collapse{(size_t)s.nblocks, (size_t)64},
+        GridAngularMomentum{tag, s.table, s.grids.grid(collocated_c), 0, 1, sum.data()});
+  });
+  for (int i = 0; i != 6; ++i) out6[i] = sum.getVal(i);
+}
 /// ApplyBoundaryConditionOnGridBlocks with a static analytic collider (GridOp.hpp:112-164)
 void zpcref_mpm_apply_boundary(void *h, int geom, int type, const float *p0, const float *p1) {
   auto &s = *(RefMpm *)h;

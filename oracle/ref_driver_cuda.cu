@@ -123,6 +123,30 @@ float zpcrefcuda_mpm_grid_update(void *h, float dt, float gravity, int mode) {
       ComputeGridBlockVelocity{exec_cuda, wrapv<transfer_scheme_e::apic>{}, s.grids, dt, gravity, s.maxVel.data()});
   return s.maxVel.getVal();
 }
+/// the reference's GridAngularMomentum / GridMomentumToVelocity (GridOp.hpp:184-262) on cuda_exec(): out6 first, then the velocities
+float zpcrefcuda_mpm_grid_momentum(void *h, double *out6) {
+  auto &s = *(RefMpmCuda *)h;
+  auto pol = cuda_exec().device(0);
+  Vector<double> sum{6, memsrc_e::device, 0};
+  cudaMemset(sum.data(), 0, sizeof(double) * 6);
+  pol(Collapse{(size_t)s.nblocks, (size_t)64}, GridAngularMomentum{exec_cuda, s.table, s.grids.grid(collocated_c), 0, 1, sum.data()});
+  d2h(out6, sum.data(), sizeof(double) * 6);
+  s.maxVel.setVal(0.f);
+  pol(Collapse{(size_t)s.nblocks, (size_t)64}, GridMomentumToVelocity{exec_cuda, s.grids.grid(collocated_c), 0, 1, s.maxVel.data()});
+  return s.maxVel.getVal();
+}
+/// the same two through the overlay (libzpcb200's kernels on the reference's containers)
+float zpcrefcuda_overlay_grid_momentum(void *h, double *out6) {
+  auto &s = *(RefMpmCuda *)h;
+  auto pol = b200_exec();
+  Vector<double> sum{6, memsrc_e::device, 0};
+  cudaMemset(sum.data(), 0, sizeof(double) * 6);
+  b200::grid_angular_momentum(pol, s.table, s.grids, sum.data());
+  d2h(out6, sum.data(), sizeof(double) * 6);
+  s.maxVel.setVal(0.f);
+  b200::grid_momentum_to_velocity(pol, s.grids, s.table, s.maxVel.data());
+  return s.maxVel.getVal();
+}
 void zpcrefcuda_mpm_g2p(void *h, float dt) {
   auto &s = *(RefMpmCuda *)h;
   FixedCorotatedConfig model{};

@@ -133,6 +133,29 @@ def main(argv):
         L.zpcrefcuda_mpm_get_mass(h, _p(m))
         L.zpcrefcuda_mpm_destroy(h)
         np.savez(argv[2], ref_x=ref["x"], ref_v=ref["v"], ref_C=ref["C"], ref_F=ref["F"], ref_m=P["m"], x=x, v=v, C=Cm, F=F, m=m)
+    elif argv[0] == "gridmom":   # GridAngularMomentum + GridMomentumToVelocity: the reference's functors on cuda_exec() vs the overlay
+        z = np.load(argv[1])
+        P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}
+        P["dx"], P["volume"] = float(z["dx"]), float(z["volume"])
+        n = P["x"].shape[0]
+        L = r.L
+        out = {}
+        for tag, fn in (("ref", L.zpcrefcuda_mpm_grid_momentum), ("b200", L.zpcrefcuda_overlay_grid_momentum)):
+            fn.restype = C.c_float
+            h = C.c_void_p(L.zpcrefcuda_mpm_create(C.c_int(n), C.c_float(P["dx"]), C.c_int(max(n // 8, 64))))
+            L.zpcrefcuda_mpm_set_particles(h, _p(P["x"]), _p(P["v"]), _p(P["m"]), _p(P["C"]), _p(P["F"]))
+            nb = L.zpcrefcuda_mpm_partition(h)            # the reference's own partition and P2G for both: identical tables,
+            L.zpcrefcuda_mpm_clean_grid(h)                # grids equal up to the order of the P2G atomics
+            L.zpcrefcuda_mpm_p2g(h, C.c_float(float(z["dt"])), C.c_float(float(z["E"])), C.c_float(float(z["nu"])), C.c_float(P["volume"]))
+            g0 = np.empty((nb, 7, 64), np.float32); keys = np.empty((nb, 3), np.int32)
+            L.zpcrefcuda_mpm_get_grid(h, _p(g0)); L.zpcrefcuda_mpm_get_keys(h, _p(keys))
+            sum6 = np.zeros(6, np.float64)
+            mx = fn(h, _p(sum6))
+            g1 = np.empty((nb, 7, 64), np.float32)
+            L.zpcrefcuda_mpm_get_grid(h, _p(g1))
+            L.zpcrefcuda_mpm_destroy(h)
+            out.update({tag + "_grid": g0, tag + "_keys": keys, tag + "_sum6": sum6, tag + "_max": np.float32(mx), tag + "_vel": g1})
+        np.savez(argv[2], **out)
     elif argv[0] == "lbvh":
         n = int(argv[1])
         rs = np.random.RandomState(77)

@@ -108,6 +108,27 @@ def boundary_cuboid_case(ref, name, s, G, **kw):
     print(name, "n", n, len(CUBOID_COLLIDERS), "cuboid colliders")
 
 
+def grid_momentum_case(ref, name, s, G, **kw):
+    """GridMomentumToVelocity and GridAngularMomentum (GridOp.hpp:184-262) under the sequential policy on the grid P2G leaves"""
+    P = synth.elastic_cube(s, G, **kw)
+    P["v"] = (P["v"] + np.float32([0.3, -0.2, 0.1])).astype(np.float32)
+    n, dx = P["x"].shape[0], P["dx"]
+    h = ref.mpm(n, dx, 0)
+    h.set_particles(P)
+    h.partition()
+    tab = h.table()
+    h.clean_grid()
+    h.p2g(synth.DT, synth.MODEL["E"], synth.MODEL["nu"], P["volume"])
+    grid = h.grid()
+    sum6 = h.angular_momentum()
+    mx = h.momentum_to_velocity()
+    vel = h.grid()
+    h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), s=s, G=G, kw=repr(sorted(kw.items())), v_shift=np.float32([0.3, -0.2, 0.1]),
+                        active_keys=tab["active_keys"], grid=grid, sum6=sum6, max_vel_sqr=np.float32(mx), vel=vel)
+    print(name, "n", n, "blocks", grid.shape[0], "sum6", sum6)
+
+
 def vonmises_margin(P, E, nu, ys):
     """smallest relative distance of any particle's trial deviatoric stress norm from the yield radius"""
     mu, lam = 0.5 * E / (1 + nu), E * nu / ((1 + nu) * (1 - 2 * nu))
@@ -324,6 +345,7 @@ if __name__ == "__main__":
     boundary_cuboid_case(r, "mpm_cube7_boundary_cuboid", 7, 32, jitter_C=0.6, jitter_F=0.03, shuffle_seed=4)
     sand_case(r, "mpm_cube6_sand", 6, 32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=19)
     nacc_case(r, "mpm_cube6_nacc", 6, 32, jitter_F=0.03, jitter_C=0.5, shuffle_seed=23)
+    grid_momentum_case(r, "mpm_cube6_grid_momentum", 6, 32, jitter_F=0.05, jitter_C=0.5, shuffle_seed=29)
     if "--all" in sys.argv:   # the primitive / SVD vectors use unseeded-order-independent inputs: regenerate on demand
         prims_case(r)
         svd_case(r)

@@ -192,6 +192,21 @@ def test_g2p2g_entry_checks_its_arguments():
     assert L.zpcb200_g2p2g_apic(some, tv, f(0.1), f(1e-4), 3, ctypes.byref(nacc), ctypes.c_void_p(8), ctypes.c_void_p(8), None) == -1   # no logJp
 
 
+def test_grid_momentum_entries_check_their_arguments():
+    from zpc_b200 import api
+    L = api.lib()
+    g = api.zpc_grids_view(1, 100, 7, 0.1)
+    tv = api.zpc_hashtable_view(1, 1, 1, 1, 16, 1)
+    one = ctypes.c_void_p(8)
+    for m_chn, mv_chn in ((-1, 1), (0, 5), (7, 1), (2, 1), (0, -1)):     # outside the 7 channels, or mass inside the momentum range
+        assert L.zpcb200_grid_momentum_to_velocity(g, one, m_chn, mv_chn, one, None) == -1, (m_chn, mv_chn)
+    assert L.zpcb200_grid_momentum_to_velocity(g, None, 0, 1, one, None) == -1
+    assert L.zpcb200_grid_momentum_to_velocity(g, one, 0, 1, None, None) == -1
+    assert L.zpcb200_grid_angular_momentum(g, tv, 0, 1, None, None) == -1
+    assert L.zpcb200_grid_angular_momentum(g, tv, 0, 5, one, None) == -1
+    assert L.zpcb200_grid_angular_momentum(api.zpc_grids_view(None, 100, 7, 0.1), tv, 0, 1, one, None) == -1
+
+
 def test_overlay_binds_the_reference_headers_to_the_library():
     """oracle/_ref/libzpcref_cuda.so = the unmodified reference (CUDA backend) + include/zpcb200/zs_overlay.cuh.  It cannot be loaded
     without a driver, but its dynamic symbol table shows what the overlay resolved to: generic zs::radix_sort_pair / exclusive_scan /

@@ -583,6 +583,79 @@ def test_sparsegrid_runs_every_model(oracle, model):
         check_channels(pars.J.cpu().numpy()[:, None], z["J"][:, None], 1, "sg eos J", 3e-5)
 
 
+def test_grid_momentum_functors(oracle):
+    """zpcb200_grid_momentum_to_velocity / zpcb200_grid_angular_momentum (GridOp.hpp:184-262) on the grid our own P2G leaves, against
+    the oracle on that same grid: velocities bit for bit (one IEEE division and three products per cell), max |v|^2 to an ulp of the
+    contracted sum, the six double sums to the rounding of another addition order; then the reference-generated golden file"""
+    from zpc_b200 import api
+    z = np.load(os.path.join(G, "mpm_cube6_grid_momentum.npz"))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **dict(ast.literal_eval(str(z["kw"]))))
+    P["v"] = (P["v"] + z["v_shift"]).astype(np.float32)
+    dx = P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    grids = api.Grids(dx, ht["nblocks"] + 2)                       # spare blocks beyond *cnt stay untouched
+    api.p2g_transfer(pars, table, grids, synth.DT, api.model_fcr(P["volume"], E, NU))
+    grids.tiles[ht["nblocks"]:] = 3.0
+    torch.cuda.synchronize()
+    g0 = grids.tiles.cpu().numpy()
+    sum6 = torch.zeros(6, dtype=torch.float64, device="cuda")
+    api.grid_angular_momentum(grids, table, sum6)
+    api.grid_angular_momentum(grids, table, sum6)                  # adds: twice the sum
+    want = oracle.grid_angular_momentum(g0[:ht["nblocks"]], ht["active_keys"], dx)
+    got = sum6.cpu().numpy() / 2
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (got, want)
+    ko, go = grid_by_key(z["active_keys"], z["grid"])
+    ks, gs = grid_by_key(ht["active_keys"], g0[:ht["nblocks"]])
+    assert np.array_equal(ko, ks)
+    assert np.abs(got - z["sum6"]).max() <= 1e-5 * np.abs(z["sum6"]).max()      # the reference's own P2G grid differs by float rounding
+    mx = torch.zeros(1, device="cuda")
+    api.grid_momentum_to_velocity(grids, table, mx)
+    torch.cuda.synchronize()
+    g1 = grids.tiles.cpu().numpy()
+    ref = g0[:ht["nblocks"]].copy()
+    mo = oracle.grid_momentum_to_velocity(ref)
+    assert np.array_equal(g1[:ht["nblocks"]].view(np.uint32), ref.view(np.uint32))
+    assert (g1[ht["nblocks"]:] == 3.0).all()
+    assert abs(float(mx.item()) - mo) <= 1e-6 * mo
+    check_channels(gs[:, :4], go[:, :4], 1, "mass and momentum vs the reference-generated grid", RTOL)
+    # channel arguments: the rhs channels against the mass channel; bad channel ranges are refused
+    alt = torch.zeros(6, dtype=torch.float64, device="cuda")
+    api.grid_angular_momentum(grids, table, alt, 0, 4)
+    want_alt = oracle.grid_angular_momentum(g1[:ht["nblocks"]], ht["active_keys"], dx, 0, 4)
+    assert np.abs(alt.cpu().numpy() - want_alt).max() <= 1e-12 * max(np.abs(want_alt).max(), 1e-30)
+    with pytest.raises(RuntimeError):
+        api.grid_momentum_to_velocity(grids, table, mx, 0, 5)
+    with pytest.raises(RuntimeError):
+        api.grid_momentum_to_velocity(grids, table, mx, 2, 1)
+
+
+def test_grid_momentum_functors_vs_the_references_cuda_functors(oracle, tmp_path):
+    """GridAngularMomentum / GridMomentumToVelocity: the reference's functors on cuda_exec() and zs::b200::grid_* on the same reference
+    containers (own process); each arm against the oracle on the grid that arm started from"""
+    import subprocess
+    import sys
+    from oracle.refcuda_runner import RefCuda
+    if not RefCuda.available():
+        pytest.skip("oracle/_ref/libzpcref_cuda.so not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    P = synth.elastic_cube(9, 32, jitter_F=0.03, jitter_C=0.3, seed=6)
+    P["v"] = (P["v"] + np.float32([0.3, -0.2, 0.1])).astype(np.float32)
+    fin, fout = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(fin, dt=synth.DT, E=E, nu=NU, **P)
+    r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "gridmom", fin, fout], cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    z = np.load(fout)
+    for tag in ("ref", "b200"):
+        want = oracle.grid_angular_momentum(z[tag + "_grid"], z[tag + "_keys"], P["dx"])
+        assert np.abs(z[tag + "_sum6"] - want).max() <= (2e-7 if tag == "ref" else 1e-12) * np.abs(want).max(), tag   # nvcc contracts the reference's cross product
+        g = z[tag + "_grid"].copy()
+        mo = oracle.grid_momentum_to_velocity(g)
+        assert np.array_equal(g.view(np.uint32), z[tag + "_vel"].view(np.uint32)), tag
+        assert abs(float(z[tag + "_max"]) - mo) <= 1e-6 * mo
+    assert np.abs(z["b200_sum6"] - z["ref_sum6"]).max() <= 1e-5 * np.abs(z["ref_sum6"]).max()
+
+
 def test_overlay_fast_path_on_the_references_containers(tmp_path):
     """zs::b200::BinnedParticles (TileVector<f32,32> = the type of Particles::particleBins, zs::Vector metadata): four substeps with a re-bin
     through the overlay's block-binned fast path vs the same four substeps through the reference's own functors on cuda_exec(), both on

@@ -740,6 +740,19 @@ def compute_grid_block_velocity(grids, table, dt, extf, mode, max_vel_sqr, strea
            "grid_update")
 
 
+def grid_momentum_to_velocity(grids, table, max_vel_sqr, m_chn=0, mv_chn=1, stream=None):
+    """GridMomentumToVelocity{cuda_c, grid, mChn, mvChn, maxVel} (GridOp.hpp:184-214): v = mv / m, no gravity"""
+    _check(lib().zpcb200_grid_momentum_to_velocity(grids.view(), C.c_void_p(table.cnt.data_ptr()), C.c_int(m_chn), C.c_int(mv_chn),
+                                                   C.c_void_p(max_vel_sqr.data_ptr()), _stream_ptr(stream)), "grid_momentum_to_velocity")
+
+
+def grid_angular_momentum(grids, table, sum6, m_chn=0, mv_chn=1, stream=None):
+    """GridAngularMomentum{cuda_c, table, grid, mChn, mvChn, sum} (GridOp.hpp:216-262); sum6: six float64 on the device, added to"""
+    assert sum6.dtype == torch.float64 and sum6.numel() >= 6 and sum6.is_cuda
+    _check(lib().zpcb200_grid_angular_momentum(grids.view(), table.view(), C.c_int(m_chn), C.c_int(mv_chn),
+                                               C.c_void_p(sum6.data_ptr()), _stream_ptr(stream)), "grid_angular_momentum")
+
+
 GEOM_PLANE, GEOM_SPHERE, GEOM_CUBOID = 0, 1, 2
 MAX_COLLIDERS = 4   # ZPCB200_MAX_COLLIDERS
 COLLIDER_STICKY, COLLIDER_SLIP, COLLIDER_SEPARATE = 0, 1, 2

@@ -103,6 +103,74 @@ __global__ void __launch_bounds__(256) apply_boundary_kernel(float *tiles, const
   }
 }
 
+// GridMomentumToVelocity (GridOp.hpp:184-214): v = mv * (1/m) where m != 0, max |v|^2; one thread per (block, cell)
+__global__ void __launch_bounds__(256) grid_momentum_to_velocity_kernel(float *tiles, const int *cnt, int nch, size_t cap_blocks, int m_chn,
+                                                                        int mv_chn, float *max_vel_sqr) {
+  size_t nb = (size_t)*cnt;
+  if (nb > cap_blocks) nb = cap_blocks;
+  float mx = 0.f;
+  for (size_t gc = (size_t)blockIdx.x * 256 + threadIdx.x; gc < nb * 64; gc += (size_t)gridDim.x * 256) {
+    float *t = tiles + (gc >> 6) * (size_t)nch * 64 + (gc & 63);
+    float mass = t[m_chn * 64];
+    if (mass != 0.f) {
+      mass = 1.f / mass;
+      const float vx = t[mv_chn * 64] * mass, vy = t[(mv_chn + 1) * 64] * mass, vz = t[(mv_chn + 2) * 64] * mass;
+      t[mv_chn * 64] = vx; t[(mv_chn + 1) * 64] = vy; t[(mv_chn + 2) * 64] = vz;
+      mx = fmaxf(mx, vx * vx + vy * vy + vz * vz);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  __shared__ float smx[8];
+  if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, smx[i]);
+    if (mx > 0.f) atomicMax((int *)max_vel_sqr, __float_as_int(mx));
+  }
+}
+
+// GridAngularMomentum (GridOp.hpp:216-262): sum6 += {x cross mv, mv} over the cells with mass; the per-cell products in float
+// without contraction (the host build of the functor), the sums in double: warp shuffle -> shared -> one atomicAdd(double) per
+// CTA and component instead of the reference's six atomics per cell.
+__global__ void __launch_bounds__(256) grid_angular_momentum_kernel(const float *__restrict__ tiles, const int *__restrict__ active_keys,
+                                                                    const int *cnt, int nch, size_t cap_blocks, float dx, int m_chn,
+                                                                    int mv_chn, double *sum6) {
+  size_t nb = (size_t)*cnt;
+  if (nb > cap_blocks) nb = cap_blocks;
+  const int cell = threadIdx.x & 63;
+  const int cx = (cell >> 4) & 3, cy = (cell >> 2) & 3, cz = cell & 3;
+  double acc[6] = {0., 0., 0., 0., 0., 0.};
+  for (size_t b = (size_t)blockIdx.x * 4 + (threadIdx.x >> 6); b < nb; b += (size_t)gridDim.x * 4) {
+    const float *t = tiles + b * (size_t)nch * 64 + cell;
+    if (t[m_chn * 64] == 0.f) continue;
+    const float px = zpcm::rn_mul(zpcm::rn_add(zpcm::rn_mul((float)active_keys[3 * b], 4.f), (float)cx), dx),
+                py = zpcm::rn_mul(zpcm::rn_add(zpcm::rn_mul((float)active_keys[3 * b + 1], 4.f), (float)cy), dx),
+                pz = zpcm::rn_mul(zpcm::rn_add(zpcm::rn_mul((float)active_keys[3 * b + 2], 4.f), (float)cz), dx);
+    const float mx = t[mv_chn * 64], my = t[(mv_chn + 1) * 64], mz = t[(mv_chn + 2) * 64];
+    acc[0] += (double)zpcm::rn_sub(zpcm::rn_mul(py, mz), zpcm::rn_mul(pz, my));
+    acc[1] += (double)zpcm::rn_sub(zpcm::rn_mul(pz, mx), zpcm::rn_mul(px, mz));
+    acc[2] += (double)zpcm::rn_sub(zpcm::rn_mul(px, my), zpcm::rn_mul(py, mx));
+    acc[3] += (double)mx; acc[4] += (double)my; acc[5] += (double)mz;
+  }
+  __shared__ double ssum[8][6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) ssum[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = 0.;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += ssum[w][threadIdx.x];
+    if (v != 0.) atomicAdd(sum6 + threadIdx.x, v);
+  }
+}
+
 // ComputeGridBlockVelocity followed by ApplyBoundaryConditionOnGridBlocks for up to ZPCB200_MAX_COLLIDERS colliders in
 // ONE pass over the grid: the velocity never leaves the registers between the two functors.
 // max |v|^2 is taken before the projection, as the reference's sequence of functors does.
@@ -274,6 +342,25 @@ int zpcb200_apply_boundary(zpc_grids_view g, zpc_hashtable_view tb, zpc_collider
     return ZPCB200_E_BADARG;
   apply_boundary_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks,
                                                                            g.dx, col);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_grid_momentum_to_velocity(zpc_grids_view g, const int *cnt, int mChn, int mvChn, float *maxVelSqr, zpc_stream_t stream) {
+  if (!g.tiles || !cnt || !maxVelSqr || mChn < 0 || mvChn < 0 || mChn >= g.numChannels || mvChn + 3 > g.numChannels ||
+      (mChn >= mvChn && mChn < mvChn + 3))
+    return ZPCB200_E_BADARG;
+  grid_momentum_to_velocity_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, cnt, g.numChannels, g.numBlocks, mChn, mvChn,
+                                                                                      maxVelSqr);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_grid_angular_momentum(zpc_grids_view g, zpc_hashtable_view tb, int mChn, int mvChn, double *sum6, zpc_stream_t stream) {
+  if (!g.tiles || !tb.activeKeys || !tb.cnt || !sum6 || mChn < 0 || mvChn < 0 || mChn >= g.numChannels || mvChn + 3 > g.numChannels)
+    return ZPCB200_E_BADARG;
+  grid_angular_momentum_kernel<<<ZPC_SM_COUNT * 4, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks,
+                                                                                  g.dx, mChn, mvChn, sum6);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }
