@@ -243,7 +243,8 @@ int zpcb200_index_buckets_build(void *temp, size_t *temp_bytes, zpc_port x, size
                                 zpc_hashtable_view table, int *counts, int *offsets, int *indices, int *overflow,
                                 zpc_stream_t stream);
 
-/* CleanGridBlocks (simulation/grid/GridOp.hpp:54-69) over blocks [0, *cnt). */
+/* CleanGridBlocks (simulation/grid/GridOp.hpp:54-69) over blocks [0, *cnt): every channel of every cell becomes 0.
+ * ResetGrid (GridOp.hpp:166-182) is the same operation on one Grid of the Grids: this entry serves both. */
 int zpcb200_clean_grid(zpc_grids_view grids, const int *cnt, zpc_stream_t stream);
 
 /* P2GTransfer<apic, FixedCorotatedConfig> (simulation/transfer/P2G.hpp:45-127) on the reference's
