@@ -388,7 +388,10 @@ def main():
     if rank == 0:
         print(json.dumps(make_line(e2e, cpu)), flush=True)
     if dist is not None:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:   # the line is out; a failed e2e leg must not turn the teardown into a non-zero exit
+            pass
     return 0
 
 
