@@ -27,7 +27,7 @@ python bench.py --model eos --steps 16 --warmup 4 --no-cpu-baseline > gpurun_out
 cut -c1-300 gpurun_out/r2_bench_eos.log | tail -1
 # 8. memcheck over the kernels that ran for the first time today (small cases only; slow under the tool, hence the timeout)
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_pending.py -m gpu -q -x \
-  -k "plastic_model_matches or cuboid or index_buckets or g2p2g or vonmises_on_the_binned or equation_of_state_on or plastic_models_on" \
+  -k "plastic_model_matches or cuboid or index_buckets or g2p2g or grid_momentum_functors or vonmises_on_the_binned or equation_of_state_on or plastic_models_on" \
   > gpurun_out/r2_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/r2_memcheck.log
 # 9. racecheck on the shared-memory-staged binned kernels, one small case
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_mpm.py -m gpu -q -x \
