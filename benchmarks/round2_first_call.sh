@@ -11,10 +11,12 @@ python -m pytest tests/test_zz_gpu_pending.py -m gpu -q -rxX --timeout 900 > gpu
 python -m pytest tests -m gpu -x -q --deselect tests/test_zz_gpu_pending.py > gpurun_out/r2_tests.log 2>&1
 python bench.py --steps 16 --warmup 4 > gpurun_out/r2_bench.log 2>&1
 python bench.py --steps 8 --warmup 4 --no-cpu-baseline --e2e-pipelined 8 > gpurun_out/r2_bench_e2e_pipelined.log 2>&1
+python bench.py --steps 16 --warmup 4 --no-cpu-baseline --e2e-steps 0 --p2g-sweep 5 > gpurun_out/r2_bench_sweep5.log 2>&1   # packed fp32 (FFMA2) sweep vs the default line above
 python bench.py --impl reference-cuda --config C2 --steps 5 --warmup 2 > gpurun_out/r2_refcuda_c2.log 2>&1
 python bench.py --impl reference-cuda --config C3 --steps 3 --warmup 1 > gpurun_out/r2_refcuda_c3.log 2>&1
 python bench.py --config C2 --steps 16 --warmup 4 --no-cpu-baseline --e2e-steps 0 > gpurun_out/r2_bench_c2.log 2>&1
 tail -3 gpurun_out/r2_pending.log gpurun_out/r2_tests.log
+cut -c1-400 gpurun_out/r2_bench_sweep5.log | tail -1
 cut -c1-400 gpurun_out/r2_bench.log gpurun_out/r2_refcuda_c2.log gpurun_out/r2_refcuda_c3.log
 # 5. C5 up to 2^30 keys (BASELINE "1M-1B keys"; round 1 measured up to 2^28)
 python benchmarks/prims_sweep.py --min-log2 20 --max-log2 30 > gpurun_out/r2_prims_sweep.jsonl 2> gpurun_out/r2_prims_sweep.err

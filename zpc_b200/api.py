@@ -534,7 +534,7 @@ class ParticleBins:
 
 
 def set_tuning(p2g_sweep=-1, g2p_staged=-1):
-    """zpcb200_set_tuning: pick the kernel variant of the binned P2G sweep (4 | 3) and of the binned G2P (1 = TMA-staged
+    """zpcb200_set_tuning: pick the kernel variant of the binned P2G sweep (4 | 3 | 5 = 4 on packed fp32, FFMA2) and of the binned G2P (1 = TMA-staged
     particles | 0 = plain loads); -1 keeps a setting."""
     rc = lib().zpcb200_set_tuning(int(p2g_sweep), int(g2p_staged))
     if rc:

@@ -66,7 +66,7 @@ __constant__ unsigned char c_unit_c6[NCOL6] = {7,  8,  9,  10, 13, 14, 15, 16, 1
 
 // record i of the chunk starts at float4 index rec_at<VAR>(i).  VAR 4 reads three records per LDS.128 (one per lane
 // group), typically 8 apart (8 particles per cell): a pad granule every 8 records puts them in different banks.
-template <int VAR> __device__ __forceinline__ int rec_at(int i) { return VAR == 4 ? 7 * i + (i >> 3) : 7 * i; }
+template <int VAR> __device__ __forceinline__ int rec_at(int i) { return VAR >= 4 ? 7 * i + (i >> 3) : 7 * i; }
 
 // lanes = the 27 stencil offsets.  Sweeps the records of sorted positions [lo,hi) (all in one cell) and returns the
 // 7 channel sums of this lane's node.
@@ -138,6 +138,49 @@ __device__ __forceinline__ void sweep_cells3(const float4 *rec, int lo, int hi, 
       ZPC_COL3(5, r4.y, r5.z, r5.w, r6.x)
       ZPC_COL3(6, r4.z, r6.y, r6.z, r6.w)
 #undef ZPC_COL3
+    }
+  }
+}
+
+// ---- v5 sweep: the v4 sweep on packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2, sm_100: two IEEE-rounded fp32 operations per
+// issue slot) -------------------------------------------------------------------------------------------------------------------
+// The six vector channels go through the same 7 operations per z-column with the same weights, so channels are paired:
+// (1,2), (3,4), (5,6).  The record keeps the v4 size (7 float4) but stores the operands of a pair next to each other —
+//   rec[1 + 2q] = (A0_c, A0_c', BX_c, BX_c'),  rec[2 + 2q] = (BY_c, BY_c', BZ_c, BZ_c')   for pair q = (c, c') —
+// so that every LDS.128 delivers two aligned register pairs.  Each half of a packed operation is the scalar operation of the v4
+// sweep (fma.rn / add.rn per half): the per-lane sums are bit-identical to v4's; 38 issue slots per (particle, column) against 59.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ void sweep_cells3_packed(const float4 *rec, int lo, int hi, int nmax, const ColCoef &L, float (&accm)[3],
+                                                    float2 (&acc)[3][3]) {
+  // the lane's eight coefficients are made opaque so that ptxas keeps them in registers instead of rebuilding them from (ox, oy)
+  // inside the loop (14 extra instructions per iteration at the 64-register cap)
+  float ax = L.ax, bx = L.bx, cx = L.cx, ay = L.ay, by = L.by, cy = L.cy, fx = L.fx, fy = L.fy;
+  asm volatile("" : "+f"(ax), "+f"(bx), "+f"(cx), "+f"(ay), "+f"(by), "+f"(cy), "+f"(fx), "+f"(fy));
+  const float2 fx2 = f2(fx, fx), fy2 = f2(fy, fy), two2 = f2(2.0f, 2.0f);
+#pragma unroll 1
+  for (int it = 0; it < nmax; ++it) {
+    const int p = lo + it;
+    if (p < hi) {
+      const float4 *rp = rec + rec_at<5>(p);
+      const float4 r0 = rp[0];
+      const float wx = fmaf(fmaf(ax, r0.x, bx), r0.x, cx), wy = fmaf(fmaf(ay, r0.y, by), r0.y, cy);
+      const float wxy = wx * wy;   // scalar like v4: packing (wx, wy) made ptxas rebuild the six coefficients inside the loop
+      const float W0 = wxy * fmaf(fmaf(0.5f, r0.z, -1.5f), r0.z, 1.125f);
+      const float W1 = wxy * fmaf(fmaf(-1.0f, r0.z, 2.0f), r0.z, -0.25f);
+      const float W2 = wxy * fmaf(fmaf(0.5f, r0.z, -0.5f), r0.z, 0.125f);
+      accm[0] = fmaf(W0, r0.w, accm[0]);
+      accm[1] = fmaf(W1, r0.w, accm[1]);
+      accm[2] = fmaf(W2, r0.w, accm[2]);
+      const float2 W0p = f2(W0, W0), W1p = f2(W1, W1), W2p = f2(W2, W2);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 q0 = rp[1 + 2 * q], q1 = rp[2 + 2 * q];
+        const float2 BZ = f2(q1.z, q1.w);
+        const float2 b0 = __ffma2_rn(f2(q1.x, q1.y), fy2, __ffma2_rn(f2(q0.z, q0.w), fx2, f2(q0.x, q0.y)));
+        acc[q][0] = __ffma2_rn(W0p, b0, acc[q][0]);
+        acc[q][1] = __ffma2_rn(W1p, __fadd2_rn(b0, BZ), acc[q][1]);
+        acc[q][2] = __ffma2_rn(W2p, __ffma2_rn(two2, BZ, b0), acc[q][2]);
+      }
     }
   }
 }
@@ -233,7 +276,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   // VAR 3: lanes = the 27 stencil offsets of one cell.  VAR 4: lanes = 3 cells x 9 (ox,oy) node columns.
   const bool lane_on = l < 27;
   const int lc = lane_on ? l : 0;  // VAR 3: lanes 27..31 shadow lane 0 and never write
-  const int ox = VAR == 4 ? (lc % 9) / 3 : lc / 9, oy = VAR == 4 ? lc % 3 : (lc / 3) % 3, oz = lc % 3;
+  const int ox = VAR >= 4 ? (lc % 9) / 3 : lc / 9, oy = VAR >= 4 ? lc % 3 : (lc / 3) % 3, oz = lc % 3;
   const int gi = l / 9;            // VAR 4: cell slot of this lane (3 = idle lanes 27..31)
   LaneCoef L;
   {
@@ -260,7 +303,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     }
     if (l == 0) S.ncells[buf] = base;
   };
-  if (VAR == 4 && w == P2G_NW - 1 && n_fast > 0) build_cell_list(0, 0);
+  if (VAR >= 4 && w == P2G_NW - 1 && n_fast > 0) build_cell_list(0, 0);
   for (int cb = 0; cb < n_fast; cb += CHUNK) {
     const int buf = (cb / CHUNK) & 1;
     {  // records
@@ -312,17 +355,26 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
           for (int e = 0; e < 3; ++e) { B[3 * d + e] = mass * C[d + 3 * e] * dx; Kd[3 * d + e] = K[d + 3 * e] * dx; }
         }
         dst[0] = make_float4(d0[0], d0[1], d0[2], mass);
-        dst[1] = make_float4(A[0], A[1], A[2], B[0]);
-        dst[2] = make_float4(B[1], B[2], B[3], B[4]);
-        dst[3] = make_float4(B[5], B[6], B[7], B[8]);
-        dst[4] = make_float4(a[0], a[1], a[2], Kd[0]);
-        dst[5] = make_float4(Kd[1], Kd[2], Kd[3], Kd[4]);
-        dst[6] = make_float4(Kd[5], Kd[6], Kd[7], Kd[8]);
+        if constexpr (VAR == 5) {  // channel pairs (1,2) (3,4) (5,6): (A0, A0', BX, BX'), (BY, BY', BZ, BZ') — see sweep_cells3_packed
+          dst[1] = make_float4(A[0], A[1], B[0], B[3]);
+          dst[2] = make_float4(B[1], B[4], B[2], B[5]);
+          dst[3] = make_float4(A[2], a[0], B[6], Kd[0]);
+          dst[4] = make_float4(B[7], Kd[1], B[8], Kd[2]);
+          dst[5] = make_float4(a[1], a[2], Kd[3], Kd[6]);
+          dst[6] = make_float4(Kd[4], Kd[7], Kd[5], Kd[8]);
+        } else {
+          dst[1] = make_float4(A[0], A[1], A[2], B[0]);
+          dst[2] = make_float4(B[1], B[2], B[3], B[4]);
+          dst[3] = make_float4(B[5], B[6], B[7], B[8]);
+          dst[4] = make_float4(a[0], a[1], a[2], Kd[0]);
+          dst[5] = make_float4(Kd[1], Kd[2], Kd[3], Kd[4]);
+          dst[6] = make_float4(Kd[5], Kd[6], Kd[7], Kd[8]);
+        }
       }
     }
     __syncthreads();
     const int ce = min(cb + CHUNK, n_fast);
-    if (VAR == 4) {
+    if (VAR >= 4) {
       // cell triples are handed out dynamically (one shared counter); each lane group sweeps its own cell, the sums
       // of the lane's three z-nodes go into the arena tiles with shared-memory float atomics
       const int ncells = S.ncells[buf];
@@ -343,9 +395,23 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
         const int lo = have ? max(S.gstart[g], cb) - cb : 0, hi = have ? min(S.gstart[g + 1], ce) - cb : 0;
         const int nmax = __reduce_max_sync(0xffffffffu, hi - lo);
         float acc[7][3];
+        if constexpr (VAR == 5) {
+          float accm[3] = {0.f, 0.f, 0.f};
+          float2 accp[3][3];
 #pragma unroll
-        for (int ch = 0; ch < 7; ++ch) { acc[ch][0] = 0.f; acc[ch][1] = 0.f; acc[ch][2] = 0.f; }
-        sweep_cells3(S.rec4, lo, hi, nmax, Lc, acc);
+          for (int q = 0; q < 3; ++q) { accp[q][0] = f2(0.f, 0.f); accp[q][1] = f2(0.f, 0.f); accp[q][2] = f2(0.f, 0.f); }
+          sweep_cells3_packed(S.rec4, lo, hi, nmax, Lc, accm, accp);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            acc[0][k] = accm[k];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { acc[1 + 2 * q][k] = accp[q][k].x; acc[2 + 2 * q][k] = accp[q][k].y; }
+          }
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 7; ++ch) { acc[ch][0] = 0.f; acc[ch][1] = 0.f; acc[ch][2] = 0.f; }
+          sweep_cells3(S.rec4, lo, hi, nmax, Lc, acc);
+        }
         if (have) {
           const int c6 = g / 6, zc = g - 6 * c6;                     // g = (cx+1)*36 + (cy+1)*6 + (cz+1)
           const int axn = c6 / 6 + ox, ayn = c6 % 6 + oy;            // arena node (cx+1+ox, cy+1+oy, cz+1+k)
@@ -943,13 +1009,13 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
 
 // Kernel variants (see zpcb200_set_tuning): defaults from the environment, once.
 struct Tuning {
-  int p2g_sweep;   // 4 = three cells x nine node columns per warp; 3 = one cell x 27 nodes
+  int p2g_sweep;   // 4 = three cells x nine node columns per warp; 5 = the same on packed fp32 (FFMA2); 3 = one cell x 27 nodes
   int g2p_staged;  // 0 = plain loads, 256-thread CTAs; 1 (= 64) | 64 | 128 | 256 = particle channels staged with TMA bulk copies, that many threads per CTA
 };
 Tuning &tuning() {
   static Tuning t = [] {
     Tuning d = {4, 1};
-    if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = e[0] == '3' ? 3 : 4;
+    if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = e[0] == '3' ? 3 : (e[0] == '5' ? 5 : 4);
     if (const char *e = getenv("ZPCB200_G2P_STAGED")) d.g2p_staged = atoi(e);
     return d;
   }();
@@ -968,13 +1034,14 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
   if (!attr_set.load(std::memory_order_acquire)) {
     ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<3, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
     ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<5, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
     attr_set.store(true, std::memory_order_release);
   }
   const int variant = tuning().p2g_sweep;
   float mu, lam;
   zpcm::lame_host(E, nu, mu, lam);
   const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
-  auto kern = variant == 3 ? p2g_binned_kernel<3, MODEL> : p2g_binned_kernel<4, MODEL>;
+  auto kern = variant == 3 ? p2g_binned_kernel<3, MODEL> : variant == 5 ? p2g_binned_kernel<5, MODEL> : p2g_binned_kernel<4, MODEL>;
   kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
       bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp);
@@ -1001,7 +1068,7 @@ static int g2p_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
 extern "C" {
 
 int zpcb200_set_tuning(int p2g_sweep, int g2p_staged) {
-  if ((p2g_sweep != 3 && p2g_sweep != 4 && p2g_sweep != -1) || (g2p_staged != -1 && g2p_staged != 0 && g2p_staged != 1 && g2p_staged != 64 && g2p_staged != 128 && g2p_staged != 256))
+  if ((p2g_sweep != 3 && p2g_sweep != 4 && p2g_sweep != 5 && p2g_sweep != -1) || (g2p_staged != -1 && g2p_staged != 0 && g2p_staged != 1 && g2p_staged != 64 && g2p_staged != 128 && g2p_staged != 256))
     return ZPCB200_E_BADARG;
   if (p2g_sweep != -1) tuning().p2g_sweep = p2g_sweep;
   if (g2p_staged != -1) tuning().g2p_staged = g2p_staged;
