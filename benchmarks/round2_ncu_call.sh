@@ -11,4 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
   python bench.py --steps 10 --warmup 2 --no-cpu-baseline --e2e-steps 0 > gpurun_out/r02_launch_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'p2g_binned_kernel|g2p_binned_staged_kernel' -s 6 -c 2 \
   -o gpurun_out/r02_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/r02_ncu.log 2>&1
+# 3. the packed-fp32 sweep: same capture with sweep 5, to compare issue-slot and shared-pipe utilisation with sweep 4
+ncu --set full --clock-control none --import-source on -k regex:'p2g_binned_kernel' -s 3 -c 1 \
+  -o gpurun_out/r02_full_sweep5 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 --p2g-sweep 5 > gpurun_out/r02_ncu_sweep5.log 2>&1
 ls -la gpurun_out/r02_*
