@@ -9,7 +9,7 @@ SO = os.path.join(HERE, "_hostmath.so")
 
 def build_hostmath(force=False):
     src = os.path.join(HERE, "hostmath.cu")
-    deps = [src] + [os.path.join(HERE, "..", "..", "zpc_b200", "csrc", f) for f in ("mpm_math.cuh", "lbvh_core.cuh", "mpm_particle.cuh", "mpm_kernels.cuh", "common.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "..", "zpc_b200", "csrc", f) for f in ("mpm_math.cuh", "lbvh_core.cuh", "mpm_particle.cuh", "mpm_kernels.cuh", "common.cuh", "p2g_sweep.cuh")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

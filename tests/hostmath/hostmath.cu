@@ -4,6 +4,7 @@
 #include "../../zpc_b200/csrc/mpm_math.cuh"
 #include "../../zpc_b200/csrc/lbvh_core.cuh"
 #include "../../zpc_b200/csrc/mpm_kernels.cuh"
+#include "../../zpc_b200/csrc/p2g_sweep.cuh"
 
 #include <algorithm>
 #include <numeric>
@@ -137,5 +138,49 @@ void hm_table_query(int n, const int *keys3, int table_size, const int *tkeys, c
 }
 void hm_bht_query(int n, const int *keys3, zpc_bht_view tb, int *out) {
   for (int i = 0; i < n; ++i) out[i] = zpcm::bht_query(keys3[3 * i], keys3[3 * i + 1], keys3[3 * i + 2], tb);
+}
+// The three sweep variants of the binned P2G (p2g_sweep.cuh) over n particles of ONE cell: records written by write_record<VAR> from
+// (d0, mass, A, a, B, Kd), then swept by every lane role.  out3[27][7]: sweep_cell, lane = node (ox*9 + oy*3 + oz);
+// out4 / out5 [9][7][3]: sweep_cells3 / sweep_cells3_packed, lane = column (ox*3 + oy), last index = oz.
+static void hm_coef(int o, float &a, float &b, float &c) {   // the polynomial table of p2g_binned_kernel
+  a = o == 1 ? -1.0f : 0.5f; b = o == 0 ? -1.5f : (o == 1 ? 2.0f : -0.5f); c = o == 0 ? 1.125f : (o == 1 ? -0.25f : 0.125f);
+}
+void hm_p2g_sweeps(int n, const float *d0, const float *mass, const float *A, const float *a, const float *B, const float *Kd, float *out3,
+                   float *out4, float *out5) {
+  std::vector<float4> r3((size_t)7 * n + 8), r4((size_t)zpcs::rec_at<4>(n) + 8), r5((size_t)zpcs::rec_at<5>(n) + 8);
+  for (int i = 0; i < n; ++i) {
+    float d[3], Av[3], av[3], Bv[9], Kv[9];
+    for (int k = 0; k < 3; ++k) { d[k] = d0[3 * i + k]; Av[k] = A[3 * i + k]; av[k] = a[3 * i + k]; }
+    for (int k = 0; k < 9; ++k) { Bv[k] = B[9 * i + k]; Kv[k] = Kd[9 * i + k]; }
+    zpcs::write_record<3>(r3.data() + zpcs::rec_at<3>(i), d, mass[i], Av, av, Bv, Kv);
+    zpcs::write_record<4>(r4.data() + zpcs::rec_at<4>(i), d, mass[i], Av, av, Bv, Kv);
+    zpcs::write_record<5>(r5.data() + zpcs::rec_at<5>(i), d, mass[i], Av, av, Bv, Kv);
+  }
+  for (int lane = 0; lane < 27; ++lane) {
+    const int ox = lane / 9, oy = (lane / 3) % 3, oz = lane % 3;
+    zpcs::LaneCoef L;
+    hm_coef(ox, L.ax, L.bx, L.cx); hm_coef(oy, L.ay, L.by, L.cy); hm_coef(oz, L.az, L.bz, L.cz);
+    L.fx = (float)ox; L.fy = (float)oy; L.fz = (float)oz;
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    zpcs::sweep_cell(r3.data(), 0, n, L, acc);
+    for (int ch = 0; ch < 7; ++ch) out3[lane * 7 + ch] = acc[ch];
+  }
+  for (int col = 0; col < 9; ++col) {
+    const int ox = col / 3, oy = col % 3;
+    zpcs::ColCoef L;
+    hm_coef(ox, L.ax, L.bx, L.cx); hm_coef(oy, L.ay, L.by, L.cy);
+    L.fx = (float)ox; L.fy = (float)oy;
+    float acc[7][3] = {};
+    zpcs::sweep_cells3(r4.data(), 0, n, n, L, acc);
+    float accm[3] = {0.f, 0.f, 0.f};
+    float2 accp[3][3];
+    for (int q = 0; q < 3; ++q) for (int k = 0; k < 3; ++k) accp[q][k] = make_float2(0.f, 0.f);
+    zpcs::sweep_cells3_packed(r5.data(), 0, n, n, L, accm, accp);
+    for (int k = 0; k < 3; ++k) {
+      for (int ch = 0; ch < 7; ++ch) out4[(col * 7 + ch) * 3 + k] = acc[ch][k];
+      out5[(col * 7 + 0) * 3 + k] = accm[k];
+      for (int q = 0; q < 3; ++q) { out5[(col * 7 + 1 + 2 * q) * 3 + k] = accp[q][k].x; out5[(col * 7 + 2 + 2 * q) * 3 + k] = accp[q][k].y; }
+    }
+  }
 }
 }

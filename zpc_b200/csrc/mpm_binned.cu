@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "mpm_math.cuh"
 #include "mpm_particle.cuh"
+#include "p2g_sweep.cuh"
 
 namespace {
 
@@ -63,127 +64,6 @@ static_assert(sizeof(P2GSmem) <= 56 * 1024, "four CTAs per SM");
 // sweep units in scheduling order: the 16 nominal columns first, then the 20 ring columns; c6 = (x+1)*6 + (y+1)
 __constant__ unsigned char c_unit_c6[NCOL6] = {7,  8,  9,  10, 13, 14, 15, 16, 19, 20, 21, 22, 25, 26, 27, 28,
                                               0,  1,  2,  3,  4,  5,  6,  11, 12, 17, 18, 23, 24, 29, 30, 31, 32, 33, 34, 35};
-
-// record i of the chunk starts at float4 index rec_at<VAR>(i).  VAR 4 reads three records per LDS.128 (one per lane
-// group), typically 8 apart (8 particles per cell): a pad granule every 8 records puts them in different banks.
-template <int VAR> __device__ __forceinline__ int rec_at(int i) { return VAR >= 4 ? 7 * i + (i >> 3) : 7 * i; }
-
-// lanes = the 27 stencil offsets.  Sweeps the records of sorted positions [lo,hi) (all in one cell) and returns the
-// 7 channel sums of this lane's node.
-struct LaneCoef {
-  float ax, bx, cx, ay, by, cy, az, bz, cz, fx, fy, fz;
-};
-__device__ __forceinline__ void sweep_cell(const float4 *rec, int lo, int hi, const LaneCoef &L, float (&acc)[7]) {
-#pragma unroll 1
-  for (int p = lo; p < hi; ++p) {
-    const float4 *rp = rec + 7 * p;
-    const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3], r4 = rp[4], r5 = rp[5], r6 = rp[6];
-    const float wx = fmaf(fmaf(L.ax, r0.x, L.bx), r0.x, L.cx), wy = fmaf(fmaf(L.ay, r0.y, L.by), r0.y, L.cy),
-                wz = fmaf(fmaf(L.az, r0.z, L.bz), r0.z, L.cz);
-    const float W = wx * wy * wz;
-    acc[0] = fmaf(W, r0.w, acc[0]);
-    // A = r1.xyz ; B row d = (r1.w r2.x r2.y), (r2.z r2.w r3.x), (r3.y r3.z r3.w)
-    acc[1] = fmaf(W, fmaf(r2.y, L.fz, fmaf(r2.x, L.fy, fmaf(r1.w, L.fx, r1.x))), acc[1]);
-    acc[2] = fmaf(W, fmaf(r3.x, L.fz, fmaf(r2.w, L.fy, fmaf(r2.z, L.fx, r1.y))), acc[2]);
-    acc[3] = fmaf(W, fmaf(r3.w, L.fz, fmaf(r3.z, L.fy, fmaf(r3.y, L.fx, r1.z))), acc[3]);
-    // a = r4.xyz ; K row d = (r4.w r5.x r5.y), (r5.z r5.w r6.x), (r6.y r6.z r6.w)
-    acc[4] = fmaf(W, fmaf(r5.y, L.fz, fmaf(r5.x, L.fy, fmaf(r4.w, L.fx, r4.x))), acc[4]);
-    acc[5] = fmaf(W, fmaf(r6.x, L.fz, fmaf(r5.w, L.fy, fmaf(r5.z, L.fx, r4.y))), acc[5]);
-    acc[6] = fmaf(W, fmaf(r6.w, L.fz, fmaf(r6.z, L.fy, fmaf(r6.y, L.fx, r4.z))), acc[6]);
-  }
-}
-
-
-// ---- v4 sweep: lanes = 3 cells x 9 (ox,oy) node columns -------------------------------------------------------
-// A warp takes three non-empty cells at a time.  Lane group gi = lane/9 owns one cell, lane j = lane%9 owns the node
-// column (ox,oy) = (j/3, j%3) of that cell's stencil and keeps the sums of its three z-nodes x 7 channels in
-// registers: the affine part A + B.o is evaluated once per column (12 FMA) and extended along z with 12 more, the
-// x/y weights are shared by the three nodes — 59 FP instructions per (particle, column) for 3 nodes instead of
-// 33 per node, and every LDS.128 of a record now serves three different particles.
-struct ColCoef {
-  float ax, bx, cx, ay, by, cy, fx, fy;
-};
-__device__ __forceinline__ void sweep_cells3(const float4 *rec, int lo, int hi, int nmax, const ColCoef &L,
-                                             float (&acc)[7][3]) {
-  // lo, hi: record indices relative to the chunk
-#pragma unroll 1
-  for (int it = 0; it < nmax; ++it) {
-    const int p = lo + it;
-    if (p < hi) {
-      const float4 *rp = rec + rec_at<4>(p);
-      const float4 r0 = rp[0];
-      const float wx = fmaf(fmaf(L.ax, r0.x, L.bx), r0.x, L.cx), wy = fmaf(fmaf(L.ay, r0.y, L.by), r0.y, L.cy);
-      const float wxy = wx * wy;
-      const float W0 = wxy * fmaf(fmaf(0.5f, r0.z, -1.5f), r0.z, 1.125f);
-      const float W1 = wxy * fmaf(fmaf(-1.0f, r0.z, 2.0f), r0.z, -0.25f);
-      const float W2 = wxy * fmaf(fmaf(0.5f, r0.z, -0.5f), r0.z, 0.125f);
-      acc[0][0] = fmaf(W0, r0.w, acc[0][0]);
-      acc[0][1] = fmaf(W1, r0.w, acc[0][1]);
-      acc[0][2] = fmaf(W2, r0.w, acc[0][2]);
-#define ZPC_COL3(CH, A0, BX, BY, BZ)                                    \
-  {                                                                     \
-    const float b0 = fmaf(BY, L.fy, fmaf(BX, L.fx, A0));                \
-    acc[CH][0] = fmaf(W0, b0, acc[CH][0]);                              \
-    acc[CH][1] = fmaf(W1, b0 + BZ, acc[CH][1]);                         \
-    acc[CH][2] = fmaf(W2, fmaf(2.0f, BZ, b0), acc[CH][2]);              \
-  }
-      // A = r1.xyz ; B row d = (r1.w r2.x r2.y), (r2.z r2.w r3.x), (r3.y r3.z r3.w)
-      const float4 r1 = rp[1], r2 = rp[2], r3 = rp[3];
-      ZPC_COL3(1, r1.x, r1.w, r2.x, r2.y)
-      ZPC_COL3(2, r1.y, r2.z, r2.w, r3.x)
-      ZPC_COL3(3, r1.z, r3.y, r3.z, r3.w)
-      // a = r4.xyz ; K row d = (r4.w r5.x r5.y), (r5.z r5.w r6.x), (r6.y r6.z r6.w)
-      const float4 r4 = rp[4], r5 = rp[5], r6 = rp[6];
-      ZPC_COL3(4, r4.x, r4.w, r5.x, r5.y)
-      ZPC_COL3(5, r4.y, r5.z, r5.w, r6.x)
-      ZPC_COL3(6, r4.z, r6.y, r6.z, r6.w)
-#undef ZPC_COL3
-    }
-  }
-}
-
-// ---- v5 sweep: the v4 sweep on packed fp32 arithmetic (FFMA2 / FADD2 / FMUL2, sm_100: two IEEE-rounded fp32 operations per
-// issue slot) -------------------------------------------------------------------------------------------------------------------
-// The six vector channels go through the same 7 operations per z-column with the same weights, so channels are paired:
-// (1,2), (3,4), (5,6).  The record keeps the v4 size (7 float4) but stores the operands of a pair next to each other —
-//   rec[1 + 2q] = (A0_c, A0_c', BX_c, BX_c'),  rec[2 + 2q] = (BY_c, BY_c', BZ_c, BZ_c')   for pair q = (c, c') —
-// so that every LDS.128 delivers two aligned register pairs.  Each half of a packed operation is the scalar operation of the v4
-// sweep (fma.rn / add.rn per half): the per-lane sums are bit-identical to v4's; 38 issue slots per (particle, column) against 59.
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ void sweep_cells3_packed(const float4 *rec, int lo, int hi, int nmax, const ColCoef &L, float (&accm)[3],
-                                                    float2 (&acc)[3][3]) {
-  // the lane's eight coefficients are made opaque so that ptxas keeps them in registers instead of rebuilding them from (ox, oy)
-  // inside the loop (14 extra instructions per iteration at the 64-register cap)
-  float ax = L.ax, bx = L.bx, cx = L.cx, ay = L.ay, by = L.by, cy = L.cy, fx = L.fx, fy = L.fy;
-  asm volatile("" : "+f"(ax), "+f"(bx), "+f"(cx), "+f"(ay), "+f"(by), "+f"(cy), "+f"(fx), "+f"(fy));
-  const float2 fx2 = f2(fx, fx), fy2 = f2(fy, fy), two2 = f2(2.0f, 2.0f);
-#pragma unroll 1
-  for (int it = 0; it < nmax; ++it) {
-    const int p = lo + it;
-    if (p < hi) {
-      const float4 *rp = rec + rec_at<5>(p);
-      const float4 r0 = rp[0];
-      const float wx = fmaf(fmaf(ax, r0.x, bx), r0.x, cx), wy = fmaf(fmaf(ay, r0.y, by), r0.y, cy);
-      const float wxy = wx * wy;   // scalar like v4: packing (wx, wy) made ptxas rebuild the six coefficients inside the loop
-      const float W0 = wxy * fmaf(fmaf(0.5f, r0.z, -1.5f), r0.z, 1.125f);
-      const float W1 = wxy * fmaf(fmaf(-1.0f, r0.z, 2.0f), r0.z, -0.25f);
-      const float W2 = wxy * fmaf(fmaf(0.5f, r0.z, -0.5f), r0.z, 0.125f);
-      accm[0] = fmaf(W0, r0.w, accm[0]);
-      accm[1] = fmaf(W1, r0.w, accm[1]);
-      accm[2] = fmaf(W2, r0.w, accm[2]);
-      const float2 W0p = f2(W0, W0), W1p = f2(W1, W1), W2p = f2(W2, W2);
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float4 q0 = rp[1 + 2 * q], q1 = rp[2 + 2 * q];
-        const float2 BZ = f2(q1.z, q1.w);
-        const float2 b0 = __ffma2_rn(f2(q1.x, q1.y), fy2, __ffma2_rn(f2(q0.z, q0.w), fx2, f2(q0.x, q0.y)));
-        acc[q][0] = __ffma2_rn(W0p, b0, acc[q][0]);
-        acc[q][1] = __ffma2_rn(W1p, __fadd2_rn(b0, BZ), acc[q][1]);
-        acc[q][2] = __ffma2_rn(W2p, __ffma2_rn(two2, BZ, b0), acc[q][2]);
-      }
-    }
-  }
-}
 
 #ifndef ZPC_P2G_MINB
 #define ZPC_P2G_MINB 4
@@ -278,7 +158,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   const int lc = lane_on ? l : 0;  // VAR 3: lanes 27..31 shadow lane 0 and never write
   const int ox = VAR >= 4 ? (lc % 9) / 3 : lc / 9, oy = VAR >= 4 ? lc % 3 : (lc / 3) % 3, oz = lc % 3;
   const int gi = l / 9;            // VAR 4: cell slot of this lane (3 = idle lanes 27..31)
-  LaneCoef L;
+  zpcs::LaneCoef L;
   {
     // quadratic B-spline as a polynomial in d0 (InterpolationKernel.hpp:105-113):
     //   o=0: .5 d^2 - 1.5 d + 1.125 ; o=1: -d^2 + 2 d - .25 ; o=2: .5 d^2 - .5 d + .125
@@ -345,7 +225,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 #pragma unroll
         for (int d = 0; d < 9; ++d) C[d] = pars[s + (ZPC_PB_C + d) * TS];
         // mv_d = W (A_d + sum_e B_de o_e), rhs_d = W (a_d + sum_e K_de o_e), o = stencil offset (0,1,2)^3
-        float4 *dst = S.rec4 + rec_at<VAR>(tid);
+        float4 *dst = S.rec4 + zpcs::rec_at<VAR>(tid);
         float A[3], a[3], B[9], Kd[9];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -354,22 +234,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 #pragma unroll
           for (int e = 0; e < 3; ++e) { B[3 * d + e] = mass * C[d + 3 * e] * dx; Kd[3 * d + e] = K[d + 3 * e] * dx; }
         }
-        dst[0] = make_float4(d0[0], d0[1], d0[2], mass);
-        if constexpr (VAR == 5) {  // channel pairs (1,2) (3,4) (5,6): (A0, A0', BX, BX'), (BY, BY', BZ, BZ') — see sweep_cells3_packed
-          dst[1] = make_float4(A[0], A[1], B[0], B[3]);
-          dst[2] = make_float4(B[1], B[4], B[2], B[5]);
-          dst[3] = make_float4(A[2], a[0], B[6], Kd[0]);
-          dst[4] = make_float4(B[7], Kd[1], B[8], Kd[2]);
-          dst[5] = make_float4(a[1], a[2], Kd[3], Kd[6]);
-          dst[6] = make_float4(Kd[4], Kd[7], Kd[5], Kd[8]);
-        } else {
-          dst[1] = make_float4(A[0], A[1], A[2], B[0]);
-          dst[2] = make_float4(B[1], B[2], B[3], B[4]);
-          dst[3] = make_float4(B[5], B[6], B[7], B[8]);
-          dst[4] = make_float4(a[0], a[1], a[2], Kd[0]);
-          dst[5] = make_float4(Kd[1], Kd[2], Kd[3], Kd[4]);
-          dst[6] = make_float4(Kd[5], Kd[6], Kd[7], Kd[8]);
-        }
+        zpcs::write_record<VAR>(dst, d0, mass, A, a, B, Kd);
       }
     }
     __syncthreads();
@@ -379,7 +244,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
       // of the lane's three z-nodes go into the arena tiles with shared-memory float atomics
       const int ncells = S.ncells[buf];
       const unsigned char *cells = S.cells[buf];
-      ColCoef Lc = {L.ax, L.bx, L.cx, L.ay, L.by, L.cy, L.fx, L.fy};
+      zpcs::ColCoef Lc = {L.ax, L.bx, L.cx, L.ay, L.by, L.cy, L.fx, L.fy};
       while (true) {
         int u = 0;
         if (l == 0) u = atomicAdd(&S.next_unit, 1);
@@ -399,8 +264,8 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
           float accm[3] = {0.f, 0.f, 0.f};
           float2 accp[3][3];
 #pragma unroll
-          for (int q = 0; q < 3; ++q) { accp[q][0] = f2(0.f, 0.f); accp[q][1] = f2(0.f, 0.f); accp[q][2] = f2(0.f, 0.f); }
-          sweep_cells3_packed(S.rec4, lo, hi, nmax, Lc, accm, accp);
+          for (int q = 0; q < 3; ++q) { accp[q][0] = make_float2(0.f, 0.f); accp[q][1] = make_float2(0.f, 0.f); accp[q][2] = make_float2(0.f, 0.f); }
+          zpcs::sweep_cells3_packed(S.rec4, lo, hi, nmax, Lc, accm, accp);
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             acc[0][k] = accm[k];
@@ -410,7 +275,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
         } else {
 #pragma unroll
           for (int ch = 0; ch < 7; ++ch) { acc[ch][0] = 0.f; acc[ch][1] = 0.f; acc[ch][2] = 0.f; }
-          sweep_cells3(S.rec4, lo, hi, nmax, Lc, acc);
+          zpcs::sweep_cells3(S.rec4, lo, hi, nmax, Lc, acc);
         }
         if (have) {
           const int c6 = g / 6, zc = g - 6 * c6;                     // g = (cx+1)*36 + (cy+1)*6 + (cz+1)
@@ -443,7 +308,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
           const int lo = max(S.gstart[g0 + zc], cb), hi = min(S.gstart[g0 + zc + 1], ce);
           if (lo >= hi) continue;
           float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          sweep_cell(S.rec4 - 7 * cb, lo, hi, L, acc);
+          zpcs::sweep_cell(S.rec4 - 7 * cb, lo, hi, L, acc);
           if (lane_on) {
             const int azn = zc + oz;
             float *dstn = S.out + xy_off + (azn >> 2) * 448 + (azn & 3);
