@@ -125,8 +125,9 @@ ZPC_HD void sweep_cells3_packed(const float4 *rec, int lo, int hi, int nmax, con
     if (p < hi) {
       const float4 *rp = rec + rec_at<5>(p);
       const float4 r0 = rp[0];
-      const float wx = fmaf(fmaf(ax, r0.x, bx), r0.x, cx), wy = fmaf(fmaf(ay, r0.y, by), r0.y, cy);
-      const float wxy = wx * wy;   // scalar like v4: packing (wx, wy) made ptxas rebuild the six coefficients inside the loop
+      const float2 xy = f2(r0.x, r0.y);
+      const float2 w2 = fma2(fma2(f2(ax, ay), xy, f2(bx, by)), xy, f2(cx, cy));
+      const float wxy = w2.x * w2.y;   // scalar like v4: packing (wx, wy) made ptxas rebuild the six coefficients inside the loop
       const float W0 = wxy * fmaf(fmaf(0.5f, r0.z, -1.5f), r0.z, 1.125f);
       const float W1 = wxy * fmaf(fmaf(-1.0f, r0.z, 2.0f), r0.z, -0.25f);
       const float W2 = wxy * fmaf(fmaf(0.5f, r0.z, -0.5f), r0.z, 0.125f);
