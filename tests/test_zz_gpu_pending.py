@@ -121,7 +121,7 @@ def test_cuboid_colliders_match_oracle_and_golden(oracle):
         assert torch.equal(grids.tiles, torch.as_tensor(got, device="cuda"))
 
 
-@pytest.mark.parametrize("sweep", [4, 3, 5])
+@pytest.mark.parametrize("sweep", [4, 3])
 def test_vonmises_on_the_binned_path_matches_oracle_and_golden(oracle, sweep):
     """VonMisesFixedCorotatedConfig through the block-binned P2G (zpcb200_p2g_apic_vonmises_binned: the model is a template
     parameter of the record phase): vs the oracle, the reference-generated golden grid and the AoS kernel"""
@@ -583,47 +583,6 @@ def test_sparsegrid_runs_every_model(oracle, model):
         check_channels(pars.J.cpu().numpy()[:, None], z["J"][:, None], 1, "sg eos J", 3e-5)
 
 
-@pytest.mark.parametrize("case", ["cube8", "cube12_sorted", "cube7_negative_coords", "cube16_rest"])
-def test_packed_fp32_sweep_matches_oracle_and_the_scalar_sweep(oracle, case):
-    """zpcb200_set_tuning(5, .): the binned P2G sweep on FFMA2 / FADD2 (channel pairs per issue slot).  Against the oracle under the
-    grid parity rule, and against sweep 4 on the same bins: every lane's sums are bit-identical, only the order of the shared-memory
-    atomics between warps differs, so the two grids agree to a few ulp of each channel's scale.  Then a whole substep each (the G2P
-    leaves the cell-order cache the next P2G's sweep consumes) and a second P2G on the cached order."""
-    from tests.parity import GRID_RTOL
-    from tests.test_gpu_mpm import make, run_oracle_on_table
-    from zpc_b200 import api
-    P = make(case)
-    n, dx = P["x"].shape[0], P["dx"]
-    pars, table = build_partition(P)
-    ht = host_table(table)
-    model = api.model_fcr(P["volume"], E, NU)
-    o1, _, _, _ = run_oracle_on_table(oracle, P, ht, 1)
-    out = {}
-    try:
-        for sweep in (5, 4):
-            api.set_tuning(sweep, -1)
-            bins = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
-            order = torch.empty(n, dtype=torch.int32, device="cuda")
-            api.bin_particles(pars, table, dx, bins, order)
-            grids = api.Grids(dx, ht["nblocks"])
-            api.clean_grid_blocks(grids, table)
-            api.p2g_transfer(bins, table, grids, synth.DT, model)
-            torch.cuda.synchronize()
-            g1 = grids.tiles.cpu().numpy()
-            check_channels(g1, o1, 1, "binned p2g, sweep %d" % sweep, GRID_RTOL, strict_frac=0.99)
-            mx = torch.zeros(1, device="cuda")
-            api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
-            api.g2p_transfer(bins, table, grids, synth.DT)          # writes the cell-order cache
-            api.clean_grid_blocks(grids, table)
-            api.p2g_transfer(bins, table, grids, synth.DT, model)   # second P2G: cached order, moved particles
-            torch.cuda.synchronize()
-            out[sweep] = (g1, grids.tiles.cpu().numpy())
-    finally:
-        api.set_tuning(4, -1)
-    for i, what in enumerate(("first P2G", "P2G on the cached cell order")):
-        check_channels(out[5][i], out[4][i], 1, "sweep 5 vs sweep 4, " + what, 2e-6)
-
-
 def test_grid_momentum_functors(oracle):
     """zpcb200_grid_momentum_to_velocity / zpcb200_grid_angular_momentum (GridOp.hpp:184-262) on the grid our own P2G leaves, against
     the oracle on that same grid: velocities bit for bit (one IEEE division and three products per cell), max |v|^2 to an ulp of the
@@ -719,6 +678,53 @@ def test_overlay_fast_path_on_the_references_containers(tmp_path):
     assert np.unique(z["m"]).size == n and np.array_equal(np.sort(z["m"]), np.sort(z["ref_m"]))
     o, ro = np.argsort(z["m"], kind="stable"), np.argsort(z["ref_m"], kind="stable")
     check_particles({k: z[k][o] for k in "xvCF"}, {k: z["ref_" + k][ro] for k in "xvCF"}, P["dx"], "overlay fast path vs reference functors", rtol=5e-5)
+
+
+@pytest.mark.parametrize("case", ["cube8", "cube12_sorted", "cube7_negative_coords", "cube16_rest"])
+def test_packed_fp32_sweep_matches_oracle_and_the_scalar_sweep(oracle, case):
+    """zpcb200_set_tuning(5, .): the binned P2G sweep on FFMA2 / FADD2 (channel pairs per issue slot).  Against the oracle under the
+    grid parity rule, and against sweep 4 on the same bins: every lane's sums are bit-identical, only the order of the shared-memory
+    atomics between warps differs, so the two grids agree to a few ulp of each channel's scale.  Then a whole substep each (the G2P
+    leaves the cell-order cache the next P2G's sweep consumes) and a second P2G on the cached order."""
+    from tests.parity import GRID_RTOL
+    from tests.test_gpu_mpm import make, run_oracle_on_table
+    from zpc_b200 import api
+    P = make(case)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    model = api.model_fcr(P["volume"], E, NU)
+    o1, _, _, _ = run_oracle_on_table(oracle, P, ht, 1)
+    out = {}
+    try:
+        for sweep in (5, 4):
+            api.set_tuning(sweep, -1)
+            bins = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
+            order = torch.empty(n, dtype=torch.int32, device="cuda")
+            api.bin_particles(pars, table, dx, bins, order)
+            grids = api.Grids(dx, ht["nblocks"])
+            api.clean_grid_blocks(grids, table)
+            api.p2g_transfer(bins, table, grids, synth.DT, model)
+            torch.cuda.synchronize()
+            g1 = grids.tiles.cpu().numpy()
+            check_channels(g1, o1, 1, "binned p2g, sweep %d" % sweep, GRID_RTOL, strict_frac=0.99)
+            mx = torch.zeros(1, device="cuda")
+            api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+            api.g2p_transfer(bins, table, grids, synth.DT)          # writes the cell-order cache
+            api.clean_grid_blocks(grids, table)
+            api.p2g_transfer(bins, table, grids, synth.DT, model)   # second P2G: cached order, moved particles
+            torch.cuda.synchronize()
+            out[sweep] = (g1, grids.tiles.cpu().numpy())
+    finally:
+        api.set_tuning(4, -1)
+    for i, what in enumerate(("first P2G", "P2G on the cached cell order")):
+        check_channels(out[5][i], out[4][i], 1, "sweep 5 vs sweep 4, " + what, 2e-6)
+
+
+def test_packed_fp32_sweep_with_another_model(oracle):
+    """the von Mises record phase in front of the packed sweep (kept late in the file: a fault in a kernel that has never run would
+    poison the tests after it)"""
+    test_vonmises_on_the_binned_path_matches_oracle_and_golden(oracle, 5)
 
 
 # last: a failed stream capture could leave the process unable to launch — nothing runs after it
