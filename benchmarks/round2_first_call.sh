@@ -18,6 +18,8 @@ python bench.py --config C2 --steps 16 --warmup 4 --no-cpu-baseline --e2e-steps 
 tail -3 gpurun_out/r2_pending.log gpurun_out/r2_tests.log
 cut -c1-400 gpurun_out/r2_bench_sweep5.log | tail -1
 cut -c1-400 gpurun_out/r2_bench.log gpurun_out/r2_refcuda_c2.log gpurun_out/r2_refcuda_c3.log
+python benchmarks/variants.py --combos 4:1,5:1,4:1,5:1 --tag r2_sweep5 > gpurun_out/r2_variants_sweep5.jsonl 2> gpurun_out/r2_variants_sweep5.err   # A/B on one resident workload, interleaved
+tail -4 gpurun_out/r2_variants_sweep5.jsonl | cut -c1-300
 # 5. C5 up to 2^30 keys (BASELINE "1M-1B keys"; round 1 measured up to 2^28)
 python benchmarks/prims_sweep.py --min-log2 20 --max-log2 30 > gpurun_out/r2_prims_sweep.jsonl 2> gpurun_out/r2_prims_sweep.err
 tail -2 gpurun_out/r2_prims_sweep.jsonl | cut -c1-300

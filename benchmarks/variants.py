@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--config", default="C3")
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--combos", default="3:0,4:0,4:1,4:64,4:256", help="comma list of p2g_sweep:g2p_staged")
+    ap.add_argument("--combos", default="3:0,4:0,4:1,5:1,4:64,4:256", help="comma list of p2g_sweep:g2p_staged")
     ap.add_argument("--tag", default=os.environ.get("ZPCB200_LIB", ""))
     args = ap.parse_args()
     import torch
