@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--e2e-pipelined", type=int, default=0, help="chunks of MpmSolver.substep_host_pipelined (0 = the plain call)")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--p2g-sweep", type=int, default=-1, choices=[-1, 3, 4, 5], help="binned P2G sweep variant (zpcb200_set_tuning; 5 = packed fp32)")
+    ap.add_argument("--p2g-sweep", type=int, default=-1, choices=[-1, 3, 4, 5, 6], help="binned P2G sweep variant (zpcb200_set_tuning; 5 = packed fp32)")
     ap.add_argument("--g2p-staged", type=int, default=-1, choices=[-1, 0, 1], help="binned G2P particle staging variant")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

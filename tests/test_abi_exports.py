@@ -100,9 +100,9 @@ def test_new_entries_host_side_behaviour():
     assert L.zpcb200_set_tuning(-1, 128) == 0 and L.zpcb200_set_tuning(4, -1) == 0
     L.zpcb200_get_tuning(ctypes.byref(a), ctypes.byref(b))
     assert (a.value, b.value) == (4, 128)
-    assert L.zpcb200_set_tuning(5, -1) == 0 and L.zpcb200_set_tuning(6, -1) == -1   # 5 = the packed-fp32 sweep
+    assert L.zpcb200_set_tuning(6, -1) == 0 and L.zpcb200_set_tuning(8, -1) == -1   # 6 = the plane sweep
     L.zpcb200_get_tuning(ctypes.byref(a), ctypes.byref(b))
-    assert (a.value, b.value) == (5, 128)
+    assert (a.value, b.value) == (6, 128)
     assert L.zpcb200_set_tuning(4, 1) == 0
     # a SparseGrid with a rotated / translated transform is refused by the MPM functors before anything is launched
     sg = api.SparseGrid(7, 64, device="cpu")

@@ -36,7 +36,7 @@ def build_partition(P, expected=None):
     return pars, table
 
 
-@pytest.fixture(params=[(4, 1), (3, 0)], ids=["sweep4-staged", "sweep3-plain"])
+@pytest.fixture(params=[(6, 1), (4, 1), (3, 0)], ids=["plane-staged", "sweep4-staged", "sweep3-plain"])
 def binned_variant(request):
     """every binned-path test runs on both kernel variants of the binned P2G / G2P (zpcb200_set_tuning)"""
     from zpc_b200 import api

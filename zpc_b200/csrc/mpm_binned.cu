@@ -209,14 +209,16 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
           if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, K);
           else zpcm::stress_nacc(volume, mu, pp.a, pp.b, pp.c, pp.d, pp.flag != 0, logJp, F, K);
           *lj = logJp;
-        } else zpcm::stress_fcr(volume, mu, lam, F, K);
+        } else zpcm::stress_fcr_lean(volume * (-dt * D_inv), mu, lam, F, K);
+        if constexpr (MODEL != 0) {
 #pragma unroll
-        for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
+          for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
+        }
         float d0[3], loc[3], vel[3], C[9];
         const float mass = pars[s + ZPC_PB_M * TS];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const float X = pars[s + (ZPC_PB_X + d) * TS] / dx;
+          const float X = zpcm::div_exact(pars[s + (ZPC_PB_X + d) * TS], dx, dx_inv);
           const float lp = X - floorf(X - 0.5f);
           d0[d] = lp;
           loc[d] = lp * dx;
@@ -338,6 +340,304 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
 
   // ---- (d) far strays (moved more than one cell since the re-bin): per-particle scatter with REDs --------------
   for (int t = n_fast + tid; t < np; t += P2G_NT) {
+    const size_t s = pslot((size_t)p0 + gorder[t]);
+    float pos[3], vel[3], C[9], F[9];
+    const float mass = pars[s + ZPC_PB_M * TS];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
+#pragma unroll
+    for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
+    if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
+    else if constexpr (MODEL == 4) {
+      zpcp::p2g_scatter_particle_eos(pos, vel, mass, C, scalar[(size_t)p0 + gorder[t]], zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, pp.a, pp.b);
+    } else if constexpr (MODEL >= 2) {
+      float *lj = scalar + (size_t)p0 + gorder[t];
+      float logJp = *lj, contrib[9];
+      if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, contrib);
+      else zpcm::stress_nacc(volume, mu, pp.a, pp.b, pp.c, pp.d, pp.flag != 0, logJp, F, contrib);
+      *lj = logJp;
+#pragma unroll
+      for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
+      zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb}, tiles, 7, dx);
+    } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam);
+  }
+  if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Binned P2G, plane sweep (round 2; zpcs::sweep_plane): same bins, same TMA write-back as p2g_binned_kernel, but
+//   * a lane of the sweep owns one x-plane of a cell's stencil (9 nodes x 7 channels in registers), ten cells per warp round:
+//     a record is pulled out of shared memory by three lanes instead of nine — the data path, not issue, bounded the column sweep;
+//   * ATOMIC-FREE accumulation: the bin's 6 x 6 cell columns are split into eight fixed regions (four x-slabs x two y-halves), one
+//     per warp; a warp adds its sums with plain read-modify-writes to a PRIVATE copy of the part of the arena its region can reach
+//     (4 x 5 x 8 nodes x 7 channels = 4 480 B) — lanes of one flush instruction hold different cells or different planes, so their
+//     addresses differ, and nobody else writes there.  (Shared-memory float atomics are CAS loops on sm_100a: measured 5.9 clk per
+//     warp-op on an idle SM against 2.4 for a plain RMW, benchmarks/micro/ffma2.cu; in the kernel, 7.7 wavefronts + 1.8 rounds each.)
+//     After the last chunk the eight private copies are summed node by node — fixed order — straight into the eight [7][64] grid
+//     tiles the TMA write-back reads;
+//   * chunks of 512 particles (a whole nominal bin), two records per thread, the fixed-corotated stress in its lean form
+//     (zpcm::stress_fcr_lean); two CTAs per SM at <= 128 registers.
+constexpr int PL_NT = 256, PL_NW = PL_NT / 32, PL_CHUNK = 512, PL_RPT = PL_CHUNK / PL_NT, PL_UNIT = 10;
+static_assert(PL_NW == 8, "eight warp regions");
+// warp w = 2 a + h owns the cell columns cx' = cx + 1 in xlo(a) .. xlo(a) + ncx(a) - 1, cy' = cy + 1 in 3 h .. 3 h + 2 (all cz):
+// x-slabs {0,1} {2} {3} {4,5} — the ring columns ride with the outer nominal slabs — and the arena nodes X0 .. X0 + nX - 1, 3 h .. 3 h + 4
+__host__ __device__ constexpr int pl_xlo(int a) { return a == 0 ? 0 : a + 1; }
+__host__ __device__ constexpr int pl_ncx(int a) { return (a == 0 || a == 3) ? 2 : 1; }
+constexpr int PL_PRIV = 7 * 160;   // floats per private region: [channel][lx 0..3][ly 0..4][8 z], z rotated by 4 ly (bank spreading)
+__device__ __forceinline__ int priv_idx(int lx, int ly, int z) { return lx * 40 + ly * 8 + ((z + 4 * ly) & 7); }
+struct P2GPlaneSmem {
+  float4 rec4[PL_CHUNK * 7 + PL_CHUNK / 8];  // 58368 B; reused as the eight [7][64] grid tiles of the write-back
+  float priv[PL_NW * PL_PRIV];               // 35840 B
+  unsigned short order[BIN_MAX];             // fallback grouping only (no cell-order cache)
+  unsigned short rank[BIN_MAX];              // slot of the bin -> position in the (column, z) order (inverse of the cell order)
+  unsigned char grp_of[BIN_MAX];
+  int cnt[NGRP + 3];
+  int gstart[NGRP + 3];
+  int tile_id[8];
+  unsigned char wcells[PL_NW][40];           // per warp: the non-empty cells of its region in the current chunk
+};
+static_assert(sizeof(P2GPlaneSmem) <= 112 * 1024, "two CTAs per SM");
+
+// the 28 numbers of one particle's record from its 25 channels pd (ZPC_PB_* order): stress of MODEL, then
+// mv_d = W (A_d + B_d. o), rhs_d = W (a_d + Kd_d. o)
+template <int MODEL>
+__device__ __forceinline__ void particle_record(const float (&pd)[NCH], float *__restrict__ sc, bool live, float dx, float dx_inv, float dt,
+                                                float D_inv, float volume, float mu, float lam, float yield_stress,
+                                                const zpcm::PlasticPrm &pp, float (&d0)[3], float &mass, float (&A)[3], float (&a)[3],
+                                                float (&B)[9], float (&Kd)[9]) {
+  float F[9], K[9], C[9];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) { C[d] = pd[ZPC_PB_C + d]; F[d] = pd[ZPC_PB_F + d]; }
+  if constexpr (MODEL == 4) zpcm::eos_contrib(C, *sc, volume, pp.a, pp.b, K);
+  else if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, K);
+  else if constexpr (MODEL == 2 || MODEL == 3) {
+    float logJp = *sc;
+    if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, K);
+    else zpcm::stress_nacc(volume, mu, pp.a, pp.b, pp.c, pp.d, pp.flag != 0, logJp, F, K);
+    if (live) *sc = logJp;
+  } else zpcm::stress_fcr_lean(volume * (-dt * D_inv), mu, lam, F, K);
+  if constexpr (MODEL != 0) {
+#pragma unroll
+    for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
+  }
+  float loc[3], vel[3];
+  mass = pd[ZPC_PB_M];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float X = zpcm::div_exact(pd[ZPC_PB_X + d], dx, dx_inv);
+    const float lp = X - floorf(X - 0.5f);
+    d0[d] = lp;
+    loc[d] = lp * dx;
+    vel[d] = pd[ZPC_PB_V + d];
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    A[d] = mass * (vel[d] - (C[d] * loc[0] + C[3 + d] * loc[1] + C[6 + d] * loc[2]));
+    a[d] = -(K[d] * loc[0] + K[3 + d] * loc[1] + K[6 + d] * loc[2]);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { B[3 * d + e] = mass * C[d + 3 * e] * dx; Kd[3 * d + e] = K[d + 3 * e] * dx; }
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(PL_NT, 2)
+p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
+                 const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
+                 const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
+                 float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, float yield_stress,
+                 float *__restrict__ scalar, zpcm::PlasticPrm pp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  P2GPlaneSmem &S = *reinterpret_cast<P2GPlaneSmem *>(smem_raw);
+  const int bin = blockIdx.x;
+  if (bin >= *numBins) return;
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const int p0 = binStart[bin], np = min(binStart[bin + 1] - p0, BIN_MAX);
+  const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
+  const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
+  // the records are computed in STORAGE order — thread t owns slots t and t + 256 of every block of 512 — and written to the shared
+  // record buffer at the particle's position in the cell order: every global load is a full 128-byte line, nothing is gathered, and
+  // the loads of the first block are issued before anything else so that the lookups and the barriers below hide their latency
+  float pd[PL_RPT][NCH];
+#pragma unroll
+  for (int r = 0; r < PL_RPT; ++r) {
+    const int i = tid + r * PL_NT;
+    const size_t s = pslot((size_t)p0 + i);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) pd[r][c] = i < np ? pars[s + c * TS] : 0.f;
+  }
+  if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
+  {
+    float4 *z = reinterpret_cast<float4 *>(S.priv);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < PL_NW * PL_PRIV / 4; i += PL_NT) z[i] = zero;
+  }
+
+  // ---- (a) grouping by (column, z) of the current home cell: the cache the last binned G2P left, or a counting sort here -------
+  const bool pre = cellOrder != nullptr && *cellOrderValid != 0;
+  const unsigned short *gorder = pre ? cellOrder + p0 : S.order;
+  if (pre) {
+    for (int i = tid; i <= NGRP; i += PL_NT) S.gstart[i] = cellStart[(size_t)bin * ZPCB200_CELL_GROUPS_PAD + i];
+    for (int i = tid; i < np; i += PL_NT) S.rank[gorder[i]] = (unsigned short)i;
+    __syncthreads();
+  } else {
+    for (int i = tid; i < NGRP + 3; i += PL_NT) S.cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < np; i += PL_NT) {
+      const size_t s = pslot((size_t)p0 + i);
+      const int cx = (int)floorf(pars[s + (ZPC_PB_X + 0) * TS] / dx - 0.5f) - 1 - 4 * kx;
+      const int cy = (int)floorf(pars[s + (ZPC_PB_X + 1) * TS] / dx - 0.5f) - 1 - 4 * ky;
+      const int cz = (int)floorf(pars[s + (ZPC_PB_X + 2) * TS] / dx - 0.5f) - 1 - 4 * kz;
+      const int g = ((unsigned)(cx + 1) < 6u && (unsigned)(cy + 1) < 6u && (unsigned)(cz + 1) < 6u)
+                        ? ((cx + 1) * 6 + (cy + 1)) * 6 + (cz + 1)
+                        : GRP_FAR;
+      S.grp_of[i] = (unsigned char)g;
+      atomicAdd(&S.cnt[g], 1);
+    }
+    __syncthreads();
+    if (w == 0) {
+      int c[7], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { const int g = l * 7 + k; c[k] = g < NGRP ? S.cnt[g] : 0; sum += c[k]; }
+      int inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (l >= d) inc += t; }
+      int run = inc - sum;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int g = l * 7 + k;
+        if (g <= NGRP) { S.gstart[g] = run; S.cnt[g] = run; }
+        run += c[k];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < np; i += PL_NT) {
+      const int r = atomicAdd(&S.cnt[S.grp_of[i]], 1);
+      S.order[r] = (unsigned short)i;
+      S.rank[i] = (unsigned short)r;
+    }
+    __syncthreads();
+  }
+
+  // ---- (b) per chunk: records (two per thread), then plane sweeps ------------------------------------------------------------
+  const int n_fast = S.gstart[GRP_FAR];
+  const int gi = l / 3, pi = l - 3 * gi;     // cell slot of the round (10 = idle lanes 30, 31) and x-plane of this lane
+  const zpcs::PlaneCoef Lp = {pi == 1 ? -1.0f : 0.5f, pi == 0 ? -1.5f : (pi == 1 ? 2.0f : -0.5f), pi == 0 ? 1.125f : (pi == 1 ? -0.25f : 0.125f),
+                              (float)pi};
+  const int ra = w >> 1, rh = w & 1, rxlo = pl_xlo(ra), rncx = pl_ncx(ra);   // this warp's region: rncx x-slabs of 3 columns x 6 cells
+  float *Pw = S.priv + w * PL_PRIV;
+  for (int cb = 0; cb < n_fast; cb += PL_CHUNK) {
+    const int ce = min(cb + PL_CHUNK, n_fast);
+#pragma unroll 1
+    for (int sb = 0; sb < np; sb += PL_CHUNK) {   // blocks of 512 slots; a bin of at most 512 particles has one block and one chunk
+      if (sb + cb > 0) {                          // (the first block of the first chunk was loaded at kernel entry)
+#pragma unroll
+        for (int r = 0; r < PL_RPT; ++r) {
+          const int i = sb + tid + r * PL_NT;
+          const size_t s = pslot((size_t)p0 + i);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) pd[r][c] = i < np ? pars[s + c * TS] : 0.f;
+        }
+      }
+      float d0[PL_RPT][3], mass[PL_RPT], A[PL_RPT][3], a[PL_RPT][3], B[PL_RPT][9], Kd[PL_RPT][9];
+      int slot[PL_RPT];
+#pragma unroll
+      for (int r = 0; r < PL_RPT; ++r) {
+        const int i = sb + tid + r * PL_NT;
+        const int pos = i < np ? (int)S.rank[i] : INT_MAX;
+        slot[r] = (pos >= cb && pos < ce) ? pos - cb : -1;   // strays (pos >= n_fast) and other chunks' particles: not this pass
+        particle_record<MODEL>(pd[r], scalar ? scalar + (size_t)p0 + min(i, np - 1) : nullptr, slot[r] >= 0, dx, dx_inv, dt, D_inv, volume,
+                               mu, lam, yield_stress, pp, d0[r], mass[r], A[r], a[r], B[r], Kd[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < PL_RPT; ++r)
+        if (slot[r] >= 0) zpcs::write_plane_record(S.rec4 + zpcs::prec_at(slot[r]), d0[r], mass[r], A[r], a[r], B[r], Kd[r]);
+    }
+    __syncthreads();   // records of the chunk complete
+    // x-slab by x-slab (the outer regions hold a ring slab next to the nominal one): lanes of one flush instruction must differ in
+    // (cy', cz') or in the plane while sharing cx' — two slabs in one round would meet at cx' + i
+#pragma unroll 1
+    for (int sl = 0; sl < rncx; ++sl) {
+      // the slab's cells that have particles in this chunk, in (column, z) order — gstart is stable since the prologue
+      const int col = l / 6, zc0 = l - 6 * col;
+      const int g0 = ((rxlo + sl) * 6 + 3 * rh + col) * 6 + zc0;
+      const bool ne = l < 18 && max(S.gstart[g0], cb) < min(S.gstart[g0 + 1], ce);
+      const unsigned m = __ballot_sync(0xffffffffu, ne);
+      if (ne) S.wcells[w][__popc(m & lanemask_lt())] = (unsigned char)g0;
+      const int n_w = __popc(m);
+      __syncwarp();
+      // cells per round: spread evenly over the rounds, at most ten (30 lanes)
+      const int rounds = (n_w + PL_UNIT - 1) / PL_UNIT;
+      const int U = rounds > 0 ? (n_w + rounds - 1) / rounds : 0;
+#pragma unroll 1
+      for (int r = 0; r < rounds; ++r) {
+        const int ci = r * U + gi;
+        const bool have = gi < U && ci < n_w;
+        const int g = have ? (int)S.wcells[w][ci] : 0;
+        const int lo = have ? max(S.gstart[g], cb) - cb : 0, hi = have ? min(S.gstart[g + 1], ce) - cb : 0;
+        const int nmax = __reduce_max_sync(0xffffffffu, hi - lo);
+        float acc[7][3][3];
+#pragma unroll
+        for (int ch = 0; ch < 7; ++ch)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { acc[ch][j][0] = 0.f; acc[ch][j][1] = 0.f; acc[ch][j][2] = 0.f; }
+        zpcs::sweep_plane(S.rec4, lo, hi, nmax, Lp, acc);
+        if (have) {
+          const int c6 = g / 6, zc = g - 6 * c6, cyp = c6 % 6;                    // g = (cx' * 6 + cy') * 6 + cz'
+          const int lx = sl + pi, ly0 = cyp - 3 * rh;                             // arena node (cx' + i, cy' + j, cz' + k), region-local
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              float *dstn = Pw + priv_idx(lx, ly0 + j, zc + k);
+#pragma unroll
+              for (int ch = 0; ch < 7; ++ch) dstn[ch * 160] += acc[ch][j][k];
+            }
+        }
+        __syncwarp();   // the next round's lanes may touch the nodes this round's lanes wrote (and the list is rebuilt per slab)
+      }
+    }
+    __syncthreads();  // records are overwritten by the next chunk / the private copies are read by the merge
+  }
+
+  // ---- (c) sum the private copies into eight [7][64] grid tiles (over the dead records), then add them to the grid: TMA bulk
+  // reductions.  One float4 = four z-neighbours of one channel; a node is covered by up to three x-slabs and two y-halves.
+  float4 *T4 = S.rec4;
+  const float4 *P4 = reinterpret_cast<const float4 *>(S.priv);
+  for (int o = tid; o < 8 * 112; o += PL_NT) {
+    const int b = o / 112, r = o - 112 * b, ch = r >> 4, c4 = r & 15;
+    const int X = ((b >> 2) << 2) | (c4 >> 2), Y = (((b >> 1) & 1) << 2) | (c4 & 3), zh = b & 1;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int lx = X - pl_xlo(a);
+      if ((unsigned)lx < (unsigned)(pl_ncx(a) + 2)) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ly = Y - 3 * h;
+          if ((unsigned)ly < 5u) {
+            const float4 v = P4[(2 * a + h) * (PL_PRIV / 4) + ch * 40 + lx * 10 + ly * 2 + ((zh + ly) & 1)];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+          }
+        }
+      }
+    }
+    T4[o] = sum;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+  __syncthreads();
+  if (tid < 8) {
+    const int id = S.tile_id[tid];
+    if (id >= 0) {
+      float *g = tiles + (size_t)id * 448;
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
+                   "r"(smem_u32(reinterpret_cast<float *>(T4) + tid * 448)), "r"(1792)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+
+  // ---- (d) far strays (moved more than one cell since the re-bin): per-particle scatter with REDs -----------------------------
+  for (int t = n_fast + tid; t < np; t += PL_NT) {
     const size_t s = pslot((size_t)p0 + gorder[t]);
     float pos[3], vel[3], C[9], F[9];
     const float mass = pars[s + ZPC_PB_M * TS];
@@ -880,7 +1180,7 @@ struct Tuning {
 Tuning &tuning() {
   static Tuning t = [] {
     Tuning d = {4, 1};
-    if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = e[0] == '3' ? 3 : (e[0] == '5' ? 5 : 4);
+    if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = e[0] == '3' ? 3 : (e[0] == '5' ? 5 : (e[0] == '6' ? 6 : 4));
     if (const char *e = getenv("ZPCB200_G2P_STAGED")) d.g2p_staged = atoi(e);
     return d;
   }();
@@ -900,12 +1200,20 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
     ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<3, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
     ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
     ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<5, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_plane_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GPlaneSmem)));
     attr_set.store(true, std::memory_order_release);
   }
   const int variant = tuning().p2g_sweep;
   float mu, lam;
   zpcm::lame_host(E, nu, mu, lam);
   const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
+  if (variant == 6) {
+    p2g_plane_kernel<MODEL><<<bins.binCapacity, PL_NT, sizeof(P2GPlaneSmem), (cudaStream_t)stream>>>(
+        bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart, bins.cellOrderValid, tb,
+        g.tiles, g.dx, dt, volume, mu, lam, yield_stress, scalar, pp);
+    ZPC_CHECK_LAUNCH();
+    return ZPCB200_OK;
+  }
   auto kern = variant == 3 ? p2g_binned_kernel<3, MODEL> : variant == 5 ? p2g_binned_kernel<5, MODEL> : p2g_binned_kernel<4, MODEL>;
   kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
@@ -933,7 +1241,7 @@ static int g2p_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
 extern "C" {
 
 int zpcb200_set_tuning(int p2g_sweep, int g2p_staged) {
-  if ((p2g_sweep != 3 && p2g_sweep != 4 && p2g_sweep != 5 && p2g_sweep != -1) || (g2p_staged != -1 && g2p_staged != 0 && g2p_staged != 1 && g2p_staged != 64 && g2p_staged != 128 && g2p_staged != 256))
+  if ((p2g_sweep != 3 && p2g_sweep != 4 && p2g_sweep != 5 && p2g_sweep != 6 && p2g_sweep != -1) || (g2p_staged != -1 && g2p_staged != 0 && g2p_staged != 1 && g2p_staged != 64 && g2p_staged != 128 && g2p_staged != 256))
     return ZPCB200_E_BADARG;
   if (p2g_sweep != -1) tuning().p2g_sweep = p2g_sweep;
   if (g2p_staged != -1) tuning().g2p_staged = g2p_staged;

@@ -217,6 +217,160 @@ ZPC_HD void stress_fcr(float volume, float mu, float lam, const float (&F)[9], f
     for (int r = 0; r < 3; ++r) PF[3 * c + r] = (P[r] * F[c] + P[3 + r] * F[3 + c] + P[6 + r] * F[6 + c]) * volume;
 }
 
+// x / d in three dependent operations and no branch, given inv = 1.0f / d (IEEE, once per kernel): q = RN(x inv), r = x - q d (exact
+// in one fma), RN(q + r inv) — the correction step of a Newton division (Markstein).  Bit-identical to the IEEE quotient for operands
+// in the normal range: 5.2e8 random positions x 13 cell sizes without a mismatch on the host, and tests/test_hostmath_transfer.py
+// replays that against `/`; nvcc's own x / d is the same arithmetic plus a range check behind a branch, which splits the record
+// code into basic blocks the scheduler cannot interleave.
+ZPC_HD float div_exact(float x, float d, float inv) {
+  const float q = x * inv;
+  return fmaf(fmaf(-q, d, x), inv, q);
+}
+
+// ---- the same stress with the arithmetic of the binned fast path (round 2) -----------------------------------------------------
+// stress_fcr above follows the reference operation by operation (~1 050 instructions per particle, 36 of the 87 warp-instructions
+// the binned P2G spent per particle).  The fixed-corotated model only needs  P F^T = U Phat V^T F^T = sum_k Phat_k u_k (F v_k)^T,
+// so everything after the Jacobi sweeps is restated in its cheapest algebraically equal form:
+//   * the twelve Jacobi rotations keep the reference's rule for the angle (approximate Givens, the pi/8 fallback, the 1e-20 guard:
+//     SVD.hpp:27-32, 63-160 — the eigenvector basis the reference stops at after four sweeps is part of its result), but the
+//     rotation is applied in normalised form: the (sh^2 + ch^2) factors that keep an UNnormalised pair consistent are 1 +- 2 ulp
+//     here, and the third diagonal entry is not touched at all;
+//   * B = F V, columns ordered by norm with the reference's sign rule (SVD.hpp:516-676);
+//   * QR of B by Gram-Schmidt instead of three Givens rotations applied to B and to an identity matrix: the factorisation is unique
+//     (diagonal of R >= 0 for the first two columns, U a rotation), so U and the singular values agree to rounding;
+//   * P F^T as three outer products u_k (Phat_k b_k)^T instead of P = U Phat V^T followed by P F^T.
+// Every difference to stress_fcr is a rounding-level perturbation of an intermediate (no step is skipped), i.e. of the same kind as
+// the difference between the reference's own host and device builds; tests/test_oracle_plastic.py holds it to that distance.
+ZPC_HD float rsqrt_fast(float x) {  // x is never subnormal where this is used (>= 1e-20 or a sum with 1)
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+template <int AXIS>
+ZPC_HD void jacobi_lean(float &pp, float &qq, float &off, float &a, float &b, float (&q)[4]) {
+  const float tiny = 1.e-20f, gamma = 5.8284273147583007813f;
+  const float sin_pi8 = bits_to_float(1053028117u), cos_pi8 = bits_to_float(1064076127u);
+  float sh = off * 0.5f;
+  const float t5 = pp - qq;
+  const bool big = sh * sh >= tiny;
+  sh = big ? sh : 0.0f;
+  float ch = big ? t5 : 1.0f;
+  float t1 = sh * sh, t2 = ch * ch;
+  const float r = rsqrt_fast(t1 + t2);
+  sh = r * sh;
+  ch = r * ch;
+  if (t2 <= gamma * t1) { sh = sin_pi8; ch = cos_pi8; }
+  t1 = sh * sh;
+  t2 = ch * ch;
+  const float c = t2 - t1;
+  float s = ch * sh;
+  s = s + s;
+  const float sa = s * a, sb = s * b;
+  a = fmaf(c, a, sb);
+  b = fmaf(c, b, -sa);
+  const float s2 = s * s, c2 = c * c, cs = c * s;
+  const float twice = (off + off) * cs;
+  const float npp = fmaf(pp, c2, fmaf(qq, s2, twice)), nqq = fmaf(qq, c2, fmaf(pp, s2, -twice));
+  off = fmaf(off, c2 - s2, -(t5 * cs));
+  pp = npp;
+  qq = nqq;
+  const float tx = sh * q[1], ty = sh * q[2], tz = sh * q[3];
+  const float t[3] = {tx, ty, tz};
+  sh = sh * q[0];
+  q[0] = ch * q[0];
+  q[1] = ch * q[1];
+  q[2] = ch * q[2];
+  q[3] = ch * q[3];
+  constexpr int B = (AXIS + 1) % 3, C = (AXIS + 2) % 3;
+  q[1 + AXIS] += sh;
+  q[0] -= t[AXIS];
+  q[1 + B] += t[C];
+  q[1 + C] -= t[B];
+}
+// scale = the factor the caller wants on P F^T (volume, or volume * -dt * D_inv for the P2G record): folded into Phat
+ZPC_HD void stress_fcr_lean(float scale, float mu, float lam, const float (&F)[9], float (&PF)[9]) {
+  const float a00 = F[0], a01 = F[3], a02 = F[6], a10 = F[1], a11 = F[4], a12 = F[7], a20 = F[2], a21 = F[5], a22 = F[8];
+  float s11 = a00 * a00 + a10 * a10 + a20 * a20;
+  float s21 = a01 * a00 + a11 * a10 + a21 * a20;
+  float s31 = a02 * a00 + a12 * a10 + a22 * a20;
+  float s22 = a01 * a01 + a11 * a11 + a21 * a21;
+  float s32 = a02 * a01 + a12 * a11 + a22 * a21;
+  float s33 = a02 * a02 + a12 * a12 + a22 * a22;
+  float q[4] = {1.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int sweep = 0; sweep < 4; ++sweep) {
+    jacobi_lean<2>(s11, s22, s21, s31, s32, q);
+    jacobi_lean<0>(s22, s33, s32, s21, s31, q);
+    jacobi_lean<1>(s33, s11, s31, s32, s21, q);
+  }
+  {
+    const float r = rsqrt_refined(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] *= r; q[1] *= r; q[2] *= r; q[3] *= r;
+  }
+  float v00, v01, v02, v10, v11, v12, v20, v21, v22;
+  {
+    const float xx = q[1] * q[1], yy = q[2] * q[2], zz = q[3] * q[3], ww = q[0] * q[0];
+    v00 = ww + xx - yy - zz;
+    v11 = ww - xx + yy - zz;
+    v22 = ww - xx - yy + zz;
+    const float x2 = q[1] + q[1], y2 = q[2] + q[2], z2 = q[3] + q[3];
+    const float wx = q[0] * x2, wy = q[0] * y2, wz = q[0] * z2;
+    const float xy = q[2] * x2, yz = q[3] * y2, zx = q[1] * z2;
+    v01 = xy - wz; v12 = yz - wx; v20 = zx - wy;
+    v10 = xy + wz; v21 = yz + wx; v02 = zx + wy;
+  }
+  // B = F V: column k = F v_k
+  float b0[3] = {a00 * v00 + a01 * v10 + a02 * v20, a10 * v00 + a11 * v10 + a12 * v20, a20 * v00 + a21 * v10 + a22 * v20};
+  float b1[3] = {a00 * v01 + a01 * v11 + a02 * v21, a10 * v01 + a11 * v11 + a12 * v21, a20 * v01 + a21 * v11 + a22 * v21};
+  float b2[3] = {a00 * v02 + a01 * v12 + a02 * v22, a10 * v02 + a11 * v12 + a12 * v22, a20 * v02 + a21 * v12 + a22 * v22};
+  float r0 = b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2], r1 = b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2],
+        r2 = b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2];
+  // swap (1,2) negate col 2; swap (1,3) negate col 1; swap (2,3) negate col 3  (SVD.hpp:516-676): only B is needed afterwards
+#define ZPC_SWAPB(cond, ba, bb, ra, rb, NEG_FIRST)                                                     \
+  {                                                                                                     \
+    const bool sw = (cond);                                                                             \
+    _Pragma("unroll") for (int d = 0; d < 3; ++d) {                                                     \
+      const float xa = ba[d], xb = bb[d];                                                               \
+      ba[d] = sw ? (NEG_FIRST ? -xb : xb) : xa;                                                         \
+      bb[d] = sw ? (NEG_FIRST ? xa : -xa) : xb;                                                         \
+    }                                                                                                   \
+    const float ta = ra;                                                                                \
+    ra = sw ? rb : ra;                                                                                  \
+    rb = sw ? ta : rb;                                                                                  \
+  }
+  ZPC_SWAPB(r0 < r1, b0, b1, r0, r1, false)
+  ZPC_SWAPB(r0 < r2, b0, b2, r0, r2, true)
+  ZPC_SWAPB(r1 < r2, b1, b2, r1, r2, false)
+#undef ZPC_SWAPB
+  // Gram-Schmidt QR: u0 = b0 / |b0| ; u1 = (b1 - (u0.b1) u0) / |.| ; u2 = u0 x u1 ; sigma = (|b0|, |b1'|, u2.b2)
+  const float tiny2 = 1.e-30f;
+  const float i0 = rsqrt_refined(fmaxf(r0, tiny2));
+  const float u0[3] = {b0[0] * i0, b0[1] * i0, b0[2] * i0};
+  const float sg0 = r0 * i0;
+  const float d01 = u0[0] * b1[0] + u0[1] * b1[1] + u0[2] * b1[2];
+  const float c1[3] = {fmaf(-d01, u0[0], b1[0]), fmaf(-d01, u0[1], b1[1]), fmaf(-d01, u0[2], b1[2])};
+  const float n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2];
+  const float i1 = rsqrt_refined(fmaxf(n1, tiny2));
+  const float u1[3] = {c1[0] * i1, c1[1] * i1, c1[2] * i1};
+  const float sg1 = n1 * i1;
+  const float u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+  const float sg2 = u2[0] * b2[0] + u2[1] * b2[1] + u2[2] * b2[2];
+  const float J = sg0 * sg1 * sg2;
+  const float smu = 2.f * mu, sl = lam * (J - 1.f);
+  const float P0 = (smu * (sg0 - 1.f) + sl * (sg1 * sg2)) * scale, P1 = (smu * (sg1 - 1.f) + sl * (sg0 * sg2)) * scale,
+              P2 = (smu * (sg2 - 1.f) + sl * (sg0 * sg1)) * scale;
+  const float w0[3] = {P0 * u0[0], P0 * u0[1], P0 * u0[2]}, w1[3] = {P1 * u1[0], P1 * u1[1], P1 * u1[2]},
+              w2[3] = {P2 * u2[0], P2 * u2[1], P2 * u2[2]};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) PF[3 * c + r] = fmaf(w0[r], b0[c], fmaf(w1[r], b1[c], w2[r] * b2[c]));
+}
+
 // math::sqrtNewtonRaphson<float> (math/MathUtils.h:239-251): Newton iteration from 1 until the step is below
 // max(n * 1e-6, 128 eps).  Restated loop for loop: its result is only ~1e-6 accurate and the yield test depends on it.
 ZPC_HD float sqrt_newton_raphson(float n) {

@@ -173,4 +173,65 @@ ZPC_HD void write_record(float4 *dst, const float (&d0)[3], float mass, const fl
   }
 }
 
+
+// ---- plane sweep (round 2): lanes = 10 cells x 3 x-planes ----------------------------------------------------------------------
+// The column sweep above is bound by the shared-memory -> register path, not by issue slots: every one of the nine lanes that serve a
+// particle pulls the whole 112-byte record (7 LDS.128 = 28 data-pipe cycles per three particles; ncu: 13.3 wavefronts per particle,
+// data pipe 69 % busy).  Here a lane owns one x-plane of a cell's stencil — nine nodes x 7 channels = 63 sums in registers — so a
+// record is pulled by three lanes instead of nine (28 cycles per TEN particles), the y/z weights and the affine part are shared by
+// nine nodes (143 FP instructions per (particle, plane) = 429 per particle against 9 x 59 = 531), and a warp takes ten cells per unit.
+// Record layout: rec[0] = (d0x, d0y, d0z, m); rec[1 + c] = (A0, BX, BY, BZ) of vector channel c (0..2 momentum, 3..5 rhs):
+// value_c(i, j, k) = A0 + BX i + BY j + BZ k.
+struct PlaneCoef {
+  float ax, bx, cx, fi;   // x weight of this lane's plane i as a polynomial in d0x, and (float)i
+};
+ZPC_HD int prec_at(int i) { return 7 * i + (i >> 3); }   // same pad granule as rec_at<4>: records of neighbouring cells (8 apart) land in different banks
+ZPC_HD void write_plane_record(float4 *dst, const float (&d0)[3], float mass, const float (&A)[3], const float (&a)[3], const float (&B)[9],
+                               const float (&Kd)[9]) {
+  dst[0] = make_float4(d0[0], d0[1], d0[2], mass);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    dst[1 + c] = make_float4(A[c], B[3 * c], B[3 * c + 1], B[3 * c + 2]);
+    dst[4 + c] = make_float4(a[c], Kd[3 * c], Kd[3 * c + 1], Kd[3 * c + 2]);
+  }
+}
+// acc[ch][j][k]: channel ch of node (i, j, k) of the lane's plane
+ZPC_HD void sweep_plane(const float4 *rec, int lo, int hi, int nmax, const PlaneCoef &L, float (&acc)[7][3][3]) {
+#pragma unroll 1
+  for (int it = 0; it < nmax; ++it) {
+    const int p = lo + it;
+    if (p < hi) {
+      const float4 *rp = rec + prec_at(p);
+      const float4 r0 = rp[0];
+      const float wx = fmaf(fmaf(L.ax, r0.x, L.bx), r0.x, L.cx);
+      float wxy[3], wz[3], W[3][3];
+      wxy[0] = wx * fmaf(fmaf(0.5f, r0.y, -1.5f), r0.y, 1.125f);
+      wxy[1] = wx * fmaf(fmaf(-1.0f, r0.y, 2.0f), r0.y, -0.25f);
+      wxy[2] = wx * fmaf(fmaf(0.5f, r0.y, -0.5f), r0.y, 0.125f);
+      wz[0] = fmaf(fmaf(0.5f, r0.z, -1.5f), r0.z, 1.125f);
+      wz[1] = fmaf(fmaf(-1.0f, r0.z, 2.0f), r0.z, -0.25f);
+      wz[2] = fmaf(fmaf(0.5f, r0.z, -0.5f), r0.z, 0.125f);
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          W[j][k] = wxy[j] * wz[k];
+          acc[0][j][k] = fmaf(W[j][k], r0.w, acc[0][j][k]);
+        }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const float4 q = rp[1 + c];
+        const float base = fmaf(q.y, L.fi, q.x);
+        const float bj[3] = {base, base + q.z, fmaf(2.0f, q.z, base)};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          acc[1 + c][j][0] = fmaf(W[j][0], bj[j], acc[1 + c][j][0]);
+          acc[1 + c][j][1] = fmaf(W[j][1], bj[j] + q.w, acc[1 + c][j][1]);
+          acc[1 + c][j][2] = fmaf(W[j][2], fmaf(2.0f, q.w, bj[j]), acc[1 + c][j][2]);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace zpcs
