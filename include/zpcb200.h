@@ -416,7 +416,19 @@ typedef struct zpc_bins_view {
   unsigned short *cellOrder; /* [pars.size]: k-th particle of its bin in group order -> slot relative to binStart */
   unsigned short *cellStart; /* [binCapacity * ZPCB200_CELL_GROUPS_PAD]: group offsets, entry 217 = bin count */
   int *cellOrderValid;       /* device flag */
+  /* Optional status word (device int, may be NULL; the caller zeroes it): every capacity / consistency condition of the binned
+   * path ORs a ZPC_BINS_* bit into it instead of failing silently.  Nothing is thrown; read it where the host synchronises
+   * anyway (MpmSolver does at every re-bin). */
+  int *status;
 } zpc_bins_view;
+enum {
+  ZPC_BINS_HOME_BLOCK_MISSING = 1,    /* bin / rebin: a particle's home block is not in the table (filed under block 0) */
+  ZPC_BINS_BIN_CAPACITY = 2,          /* bin / rebin: more bins than binCapacity — numBins is set to 0, nothing will be transferred */
+  ZPC_BINS_BLOCK_CAPACITY = 4,        /* bin / rebin: the table holds more blocks than binCapacity (blocks beyond it are dropped) */
+  ZPC_BINS_STENCIL_BLOCK_MISSING = 8  /* binned P2G / G2P: a block a particle's stencil reaches is absent from the partition: that
+                                         part of its mass / momentum is not transferred.  With partition = "with_rebin" this means a
+                                         particle drifted by more than the extra ring since the last re-bin (re-bin more often) */
+};
 
 /* Sort AoS particles into bins (radix_sort_pair on the block rank + gather into AoSoA).  Requires a
  * partition built from the same positions.  order_out (may be NULL) receives the permutation:
@@ -428,6 +440,8 @@ int zpcb200_bin_particles(void *temp, size_t *temp_bytes, zpc_particles_view par
 int zpcb200_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src,
                             zpc_hashtable_view table, float dx, zpc_bins_view dst,
                             zpc_stream_t stream);
+/* dst[i] = src[idx[i]], i < n: permutes a per-particle side array (logJp, J) with the order a re-bin returned. */
+int zpcb200_gather_f32(const float *src, const int *idx, float *dst, size_t n, zpc_stream_t stream);
 /* Copy binned AoSoA particles back to the AoS view, slot i -> pars[i]. */
 int zpcb200_unbin_particles(zpc_bins_view bins, zpc_particles_view pars, zpc_stream_t stream);
 
@@ -460,8 +474,8 @@ int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_gr
 
 /* Kernel variants of the two binned functors (same results up to fp32 re-association; kept selectable so that each
  * can be measured and parity-tested).  p2g_sweep: 4 = a warp sweeps three cells at a time, lanes = 3 cells x 9 (x,y)
- * node columns, three z-nodes per lane (default); 5 = the same sweep on packed fp32 arithmetic (FFMA2: channel pairs share an issue
- * slot, per-lane sums bit-identical to 4; not yet measured); 3 = one cell at a time, lanes = the 27 nodes.  g2p_staged: 1 = the
+ * node columns, three z-nodes per lane (default); 6 = the atomic-free plane sweep (lanes = 10 cells x 3 x-planes, a private arena copy per
+ * warp region, no shared-memory atomics); 3 = one cell at a time, lanes = the 27 nodes.  g2p_staged: 1 = the
  * particle channels G2P reads are staged with TMA bulk copies in 64-thread CTAs (default; 128 / 256 select that CTA
  * size instead); 0 = plain loads, 256-thread CTAs.
  * -1 leaves a setting unchanged.  Environment defaults: ZPCB200_P2G_SWEEP, ZPCB200_G2P_STAGED.  Not thread-safe

@@ -11,8 +11,12 @@ rtol = 1e-5 (BASELINE.json north_star) everywhere except the three rhs grid chan
 the reference's 4-sweep approximate SVD (math/matrix/SVD.hpp): that computation is not reproducible to 1e-5 even
 between two builds of the SAME source — enabling FMA contraction in the host oracle moves rhs by 1.3e-5..1.8e-5
 of channel scale (tests/test_oracle_sensitivity.py measures it), and the reference's device build differs from its
-host build in exactly that way (::rsqrtf vs 1/sqrtf, nvcc FMA contraction; SURVEY §8(a2)).  rhs is therefore
-held to RTOL_STRESS = 1e-4 against the host oracle / host-generated golden vectors.
+host build in exactly that way (::rsqrtf vs 1/sqrtf, nvcc FMA contraction; SURVEY §8(a2)).  Measured on a B200 at
+8 M particles (profiles/r02_parity_vs_reference_c2.md): the reference's OWN CUDA and OpenMP paths differ by 2.8e-5 of
+channel scale on rhs (1.4e-6 on m / mv); this library sits at 1.6e-5 (AoS) .. 2.1e-5 (binned) from the reference CUDA
+path and 2.6e-5 from the OpenMP path — closer to each than they are to each other — and at <= 1.2e-6 on every other
+channel of the grid and of the particles.  rhs is therefore held to RTOL_STRESS = 5e-5 (round 1: 1e-4), everything else
+to 1e-5.
 
 The stricter floor of 1e-3 * channel max-abs from the survey is applied where asked (strict_frac) as the
 fraction of entries that must meet rtol under it.
@@ -20,7 +24,7 @@ fraction of entries that must meet rtol under it.
 import numpy as np
 
 RTOL = 1e-5
-RTOL_STRESS = 1e-4
+RTOL_STRESS = 5e-5
 GRID_RTOL = [RTOL] * 4 + [RTOL_STRESS] * 3          # channels m, mv(3), rhs(3)
 
 

@@ -54,7 +54,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(api.zpc_hashtable_view) == 48
     assert ctypes.sizeof(api.zpc_grids_view) == 24
     assert ctypes.sizeof(api.zpc_tilevector_view) == 24
-    assert ctypes.sizeof(api.zpc_bins_view) == 80
+    assert ctypes.sizeof(api.zpc_bins_view) == 88
     assert ctypes.sizeof(api.zpc_fixed_corotated) == 20
     assert ctypes.sizeof(api.zpc_vonmises_fixed_corotated) == 24
     assert ctypes.sizeof(api.zpc_equation_of_state) == 24

@@ -64,7 +64,7 @@ def test_plastic_model_matches_oracle_and_golden(oracle, model):
     api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
     assert abs(mx.item() - float(z["max_vel_sqr"])) <= RHS_RTOL[model] * float(z["max_vel_sqr"])
     api.g2p_transfer(pars, table, grids, synth.DT)
-    check_particles(pars.to_host(), {k: z[k] for k in "xvCF"}, dx, model + " golden g2p", rtol=3e-5)
+    check_particles(pars.to_host(), {k: z[k] for k in "xvCF"}, dx, model + " golden g2p", rtol=1e-5)
 
 
 def test_plastic_models_need_logjp():
@@ -208,7 +208,7 @@ def test_pipelined_host_call_equals_the_plain_one(chunks):
             for k in ("x", "v", "C", "F"):
                 hin[k], hout[k] = hout[k], hin[k]
         res.append(({k: hin[k].numpy().copy() for k in "xvCF"}, mx))
-    check_particles(res[1][0], res[0][0], P["dx"], "pipelined host call", rtol=3e-5)
+    check_particles(res[1][0], res[0][0], P["dx"], "pipelined host call", rtol=1e-5)
     assert all(abs(a - b) <= 1e-4 * b for a, b in zip(res[1][1], res[0][1]))
     assert not np.array_equal(res[0][0]["x"], P["x"])
 
@@ -330,7 +330,7 @@ def test_against_the_references_own_cuda_path(oracle, tmp_path):
     _, g2r = grid_by_key(z["active_keys"], z["grid_upd"])
     check_channels(grids.tiles.cpu().numpy()[:, 1:4], g2r[:, 1:4], 1, "grid update vs reference CUDA", RTOL_STRESS)
     api.g2p_transfer(pars, table, grids, synth.DT)
-    check_particles(pars.to_host(), {k: z[k] for k in "xvCF"}, dx, "G2P vs reference CUDA", rtol=3e-5)
+    check_particles(pars.to_host(), {k: z[k] for k in "xvCF"}, dx, "G2P vs reference CUDA", rtol=1e-5)
     # and the host oracle against the reference's device build: the distance the parity rule allows for
     o1 = oracle.p2g(P, ht, dx, synth.DT, E, NU, P["volume"])
     check_channels(o1, g1r, 1, "host oracle vs reference CUDA", GRID_RTOL)
@@ -397,7 +397,7 @@ def test_overlay_on_the_references_containers(oracle, tmp_path):
     _, ub = grid_by_key(b["active_keys"], b["grid_upd"])
     check_channels(ub[:, 1:4], ua[:, 1:4], 1, "overlay grid update", RTOL_STRESS)
     assert abs(float(a["max_vel_sqr"]) - float(b["max_vel_sqr"])) <= RTOL_STRESS * float(a["max_vel_sqr"])
-    check_particles({k: b[k] for k in "xvCF"}, {k: a[k] for k in "xvCF"}, P["dx"], "overlay G2P vs reference functors", rtol=3e-5)
+    check_particles({k: b[k] for k in "xvCF"}, {k: a[k] for k in "xvCF"}, P["dx"], "overlay G2P vs reference functors", rtol=1e-5)
     fout = str(tmp_path / "prims.npz")
     r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "prims", "100003", fout], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -704,3 +704,104 @@ def test_graph_replay_equals_eager_substeps():
         o = np.argsort(Q["m"], kind="stable")
         res.append({k: Q[k][o] for k in "xvCF"})
     check_particles(res[1], res[0], P["dx"], "graph replay vs eager", rtol=5e-5)
+
+
+def test_bins_status_word_reports_what_used_to_be_silent(oracle):
+    """zpc_bins_view.status (ADVICE r1 / VERDICT r1 weak #8): a particle that out-runs the partition's extra ring between re-bins, a bin
+    buffer that is too small and a table with more blocks than bins each OR their ZPC_BINS_* bit into the device status word; nothing
+    is thrown by the library, MpmSolver raises at the next re-bin."""
+    from zpc_b200 import api
+    from zpc_b200.solver import MpmSolver
+    P = synth.elastic_cube(6, 32)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    # (a) binCapacity smaller than the number of blocks / bins
+    small = api.ParticleBins(n, max(ht["nblocks"] // 4, 1))
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    api.bin_particles(pars, table, dx, small, order)
+    torch.cuda.synchronize()
+    st = int(small.status.item())
+    assert st & api.BINS_BLOCK_CAPACITY, st
+    with pytest.raises(RuntimeError):
+        small.check_status()
+    assert int(small.status.item()) == 0                                   # check_status cleared it
+    # (b) a clean run leaves it at zero
+    bins = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
+    api.bin_particles(pars, table, dx, bins, order)
+    grids = api.Grids(dx, ht["nblocks"])
+    model = api.model_fcr(P["volume"], E, NU)
+    for sweep in (4, 6):
+        api.set_tuning(sweep, -1)
+        try:
+            api.clean_grid_blocks(grids, table)
+            api.p2g_transfer(bins, table, grids, synth.DT, model)
+            mx = torch.zeros(1, device="cuda")
+            api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+            torch.cuda.synchronize()
+            assert int(bins.status.item()) == 0
+        finally:
+            api.set_tuning(4, -1)
+    # (c) particles teleported three blocks away without a new partition: their stencil blocks do not exist
+    x = bins.pars.channel(api.PB_X, 3)
+    far = torch.arange(0, n, 97, device="cuda")
+    x[far] += torch.tensor([12.5 * dx, 0.0, 0.0], device="cuda")
+    bins.pars.set_channel(api.PB_X, x)
+    bins.cell_order_valid.zero_()
+    for sweep in (4, 6):
+        api.set_tuning(sweep, -1)
+        try:
+            bins.status.zero_()
+            api.clean_grid_blocks(grids, table)
+            api.p2g_transfer(bins, table, grids, synth.DT, model)
+            torch.cuda.synchronize()
+            assert int(bins.status.item()) & api.BINS_STENCIL_BLOCK_MISSING, sweep
+        finally:
+            api.set_tuning(4, -1)
+    bins.status.zero_()
+    api.g2p_transfer(bins, table, grids, synth.DT)
+    torch.cuda.synchronize()
+    assert int(bins.status.item()) & api.BINS_STENCIL_BLOCK_MISSING
+    # (d) the solver surfaces it at the re-bin: a velocity that crosses more than the extra ring within one cadence
+    Pf = synth.elastic_cube(6, 32)
+    Pf["v"][:] = (0.0, -400.0, 0.0)                                        # 400 * 1e-4 * 32 = 1.3 cells per substep
+    sol = MpmSolver(Pf, dx, Pf["volume"], synth.DT, synth.GRAVITY, mode=1, layout="binned", rebin_every=8, partition="with_rebin")
+    with pytest.raises(RuntimeError, match="stencil block"):
+        for _ in range(9):
+            sol.substep()
+
+
+def test_graph_replay_with_a_side_array_equals_eager_substeps():
+    """capture_cycle with a model that carries a per-particle scalar: J ping-pongs between two persistent buffers through the
+    library's own gather, so the captured graph ends on the buffer it started from"""
+    from zpc_b200 import api
+    from zpc_b200.solver import MpmSolver
+    P = synth.elastic_cube(10, 32, jitter_C=0.3, seed=5)
+    n0 = P["m"].shape[0]
+    P["v"][:] = P["v"] * 6.0
+    P["m"] = (P["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)
+    Q = {k: v for k, v in P.items() if k != "F"}
+    Q["J"] = (1.0 + 0.02 * np.sin(np.arange(n0))).astype(np.float32)
+    model = api.model_eos(P["volume"])
+    res = []
+    for graph in (False, True):
+        sol = MpmSolver(Q, P["dx"], P["volume"], synth.DT * 10, synth.GRAVITY, mode=1, layout="binned", rebin_every=2, partition="with_rebin",
+                        model=model)
+        if graph:
+            k = sol.capture_cycle()
+            assert k == 4
+            sol.replay_cycle()
+            sol.replay_cycle()
+        else:
+            for _ in range(12):
+                sol.substep()
+        torch.cuda.synchronize()
+        assert sol.step_no == 12
+        R = sol.particles_host()
+        o = np.argsort(R["m"], kind="stable")
+        res.append({k: R[k][o] for k in ("x", "v", "C", "J")})
+    vmax = float(np.abs(res[0]["v"]).max())
+    check_channels(res[1]["x"], res[0]["x"], 1, "graph x", 5e-5, floor=float(np.abs(res[0]["x"]).max()))
+    check_channels(res[1]["v"], res[0]["v"], 1, "graph v", 5e-5, floor=vmax)
+    check_channels(res[1]["J"][:, None], res[0]["J"][:, None], 1, "graph J", 5e-5)
+    assert np.abs(res[0]["J"] - Q["J"][np.argsort(Q["m"], kind="stable")]).max() > 1e-6   # J really evolved

@@ -97,7 +97,9 @@ def test_models_and_colliders_pick_the_right_entries(recorder):
     for _ in range(3):
         s.substep()
     step = ["clean_grid", "p2g_apic_eos_binned", "grid_update", "g2p_apic_eos_binned"]
-    assert _names(recorder) == step * 2 + ["partition_build"] * 2 + ["rebin_particles_ordered"] * 2 + step
+    # the side array follows the re-bin through the library's own gather (no eager torch indexing on that path)
+    assert _names(recorder) == step * 2 + ["partition_build"] * 2 + ["rebin_particles_ordered"] * 2 + ["gather_f32"] + step
+    assert s.bins.J is not None and s.bins_alt.J is not None and s.bins.J.data_ptr() != s.bins_alt.J.data_ptr()
     assert s.bins.J is not None and "J" in s.particles_host()
     # plastic models on the binned layout: logJp rides next to the bins and follows every re-bin
     Q = dict(P, logJp=np.linspace(-1, 0, n).astype(np.float32))
@@ -108,7 +110,7 @@ def test_models_and_colliders_pick_the_right_entries(recorder):
     for _ in range(3):
         s.substep()
     step = ["clean_grid", "p2g_apic_nacc_binned", "grid_update", "g2p_apic_binned"]
-    assert _names(recorder) == step * 2 + ["partition_build"] * 2 + ["rebin_particles_ordered"] * 2 + step
+    assert _names(recorder) == step * 2 + ["partition_build"] * 2 + ["rebin_particles_ordered"] * 2 + ["gather_f32"] + step
     assert s.bins.logJp is not None and "logJp" in s.particles_host()
     with pytest.raises(ValueError):
         MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="binned", device="cpu", model=api.model_nacc(P["volume"]))   # no logJp given
@@ -168,6 +170,19 @@ def _dist_worker(rank, world, port, q):
         step = ["clean_grid", "p2g_apic_fcr_binned", "grid_update", "g2p_apic_binned"]
         assert names == step * 2 + ["partition_build"] * 2 + ["rebin_particles"] * 2 + step, names
         sol2.max_vel_sqr()
+        # a collider and a per-particle scalar on the multi-GPU fast path: the fused boundary update and the J variant of the G2P
+        # (this path used to call the plain update and the F variant whatever the solver was built with)
+        Pj = {k: v for k, v in P.items() if k != "F"}
+        Pj["J"] = np.ones(P["x"].shape[0], np.float32)
+        sol3 = DistMpmSolver(Pj, P["dx"], P["volume"], synth.DT, device="cpu", halo=halo, rebin_every=2, model=api.model_eos(P["volume"]),
+                             colliders=[api.plane_collider((0.0, 0.1, 0.0), (0.0, 1.0, 0.0))])
+        rec.calls.clear()
+        for _ in range(3):
+            sol3.substep()
+        names = [c.replace("zpcb200_", "") for c in rec.calls]
+        step = ["clean_grid", "p2g_apic_eos_binned", "grid_update_bc", "g2p_apic_eos_binned"]
+        assert names == step * 2 + ["partition_build"] * 2 + ["rebin_particles_ordered"] * 2 + ["gather_f32"] + step, names
+        sol3.max_vel_sqr()
         q.put(rank)
     finally:
         dist.destroy_process_group()

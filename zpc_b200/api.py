@@ -100,7 +100,11 @@ class zpc_sparsegrid_view(C.Structure):
 class zpc_bins_view(C.Structure):
     _fields_ = [("pars", zpc_tilevector_view), ("binStart", C.c_void_p), ("binKey", C.c_void_p),
                 ("numBins", C.c_void_p), ("binCapacity", C.c_int), ("cellOrder", C.c_void_p),
-                ("cellStart", C.c_void_p), ("cellOrderValid", C.c_void_p)]
+                ("cellStart", C.c_void_p), ("cellOrderValid", C.c_void_p), ("status", C.c_void_p)]
+
+
+# bits of zpc_bins_view.status (include/zpcb200.h)
+BINS_HOME_BLOCK_MISSING, BINS_BIN_CAPACITY, BINS_BLOCK_CAPACITY, BINS_STENCIL_BLOCK_MISSING = 1, 2, 4, 8
 
 
 _lib = None
@@ -518,6 +522,7 @@ class ParticleBins:
             self.cell_order = torch.zeros(max(self.n, 1), dtype=torch.int16, device=device)
             self.cell_start = torch.zeros(self.cap * 224, dtype=torch.int16, device=device)
             self.cell_order_valid = torch.zeros(1, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)   # ZPC_BINS_* bits, ORed in by the binned entries
 
     def view(self):
         co = self.cell_order
@@ -525,7 +530,18 @@ class ParticleBins:
                              self.num_bins.data_ptr(), self.cap,
                              co.data_ptr() if co is not None else None,
                              self.cell_start.data_ptr() if co is not None else None,
-                             self.cell_order_valid.data_ptr() if co is not None else None)
+                             self.cell_order_valid.data_ptr() if co is not None else None,
+                             self.status.data_ptr())
+
+    def check_status(self, what="binned path"):
+        """D2H read of the status word; raises on any ZPC_BINS_* bit (and clears it)"""
+        st = int(self.status.item())
+        if st:
+            self.status.zero_()
+            names = [n for b, n in ((1, "a particle's home block is not in the partition"), (2, "more bins than binCapacity"),
+                                    (4, "more blocks than binCapacity"),
+                                    (8, "a stencil block is absent from the partition (particle drifted past the extra ring: re-bin more often)")) if st & b]
+            raise RuntimeError("%s: %s" % (what, "; ".join(names)))
 
     def attr(self, name):
         chn, w = {"m": (PB_M, 1), "x": (PB_X, 3), "v": (PB_V, 3), "C": (PB_C, 9), "F": (PB_F, 9)}[name]
@@ -534,7 +550,7 @@ class ParticleBins:
 
 
 def set_tuning(p2g_sweep=-1, g2p_staged=-1):
-    """zpcb200_set_tuning: pick the kernel variant of the binned P2G sweep (4 | 3 | 5 = 4 on packed fp32, FFMA2) and of the binned G2P (1 = TMA-staged
+    """zpcb200_set_tuning: pick the kernel variant of the binned P2G sweep (4 | 3 | 6 = atomic-free plane sweep) and of the binned G2P (1 = TMA-staged
     particles | 0 = plain loads); -1 keeps a setting."""
     rc = lib().zpcb200_set_tuning(int(p2g_sweep), int(g2p_staged))
     if rc:
@@ -822,6 +838,12 @@ def rebin_particles(src, table, dx, dst, stream=None, order_out=None):
     else:
         _two_phase(lib().zpcb200_rebin_particles_ordered, (src.view(), table.view(), C.c_float(dx), dst.view(),
                                                            C.c_void_p(order_out.data_ptr())), (), stream)
+
+
+def gather_f32(src, idx, dst, stream=None):
+    """dst[i] = src[idx[i]] (zpcb200_gather_f32): permutes a per-particle side array with the order a re-bin returned"""
+    _check(lib().zpcb200_gather_f32(C.c_void_p(src.data_ptr()), C.c_void_p(idx.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                    C.c_size_t(int(dst.numel())), _stream_ptr(stream)), "gather_f32")
 
 
 def unbin_particles(bins, pars, stream=None):

@@ -79,7 +79,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
                   const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
                   const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
                   float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, int prefetch,
-                  float yield_stress, float *__restrict__ scalar, zpcm::PlasticPrm pp) {
+                  float yield_stress, float *__restrict__ scalar, zpcm::PlasticPrm pp, int *__restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GSmem &S = *reinterpret_cast<P2GSmem *>(smem_raw);
   const int bin = blockIdx.x;
@@ -334,6 +334,10 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
                    "r"(smem_u32(S.out + tid * 448)), "r"(1792)
                    : "memory");
+    } else if (status) {  // an arena block the partition does not hold: flag it if any mass was headed there
+      bool any = false;
+      for (int c = 0; c < 64; ++c) any |= S.out[tid * 448 + c] != 0.f;
+      if (any) atomicOr(status, ZPC_BINS_STENCIL_BLOCK_MISSING);
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
@@ -347,9 +351,9 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
 #pragma unroll
     for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
-    if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
+    if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
     else if constexpr (MODEL == 4) {
-      zpcp::p2g_scatter_particle_eos(pos, vel, mass, C, scalar[(size_t)p0 + gorder[t]], zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, pp.a, pp.b);
+      zpcp::p2g_scatter_particle_eos(pos, vel, mass, C, scalar[(size_t)p0 + gorder[t]], zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, pp.a, pp.b);
     } else if constexpr (MODEL >= 2) {
       float *lj = scalar + (size_t)p0 + gorder[t];
       float logJp = *lj, contrib[9];
@@ -358,8 +362,8 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
       *lj = logJp;
 #pragma unroll
       for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
-      zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb}, tiles, 7, dx);
-    } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam);
+      zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx);
+    } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, mu, lam);
   }
   if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
 }
@@ -445,7 +449,7 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
                  const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
                  const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
                  float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, float yield_stress,
-                 float *__restrict__ scalar, zpcm::PlasticPrm pp) {
+                 float *__restrict__ scalar, zpcm::PlasticPrm pp, int prefetch_ahead, int *__restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GPlaneSmem &S = *reinterpret_cast<P2GPlaneSmem *>(smem_raw);
   const int bin = blockIdx.x;
@@ -464,6 +468,16 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
     const size_t s = pslot((size_t)p0 + i);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) pd[r][c] = i < np ? pars[s + c * TS] : 0.f;
+  }
+  if (prefetch_ahead > 0 && bin + prefetch_ahead < *numBins) {
+    // the CTA that will run about one wave from now (two CTAs per SM are resident): ask for its particle lines and its cell order now,
+    // so that its entry loads hit L2 instead of HBM
+    const int q0 = binStart[bin + prefetch_ahead], qn = min(binStart[bin + prefetch_ahead + 1] - q0, BIN_MAX);
+    if (qn > 0) {
+      const int t0 = q0 >> 5, nlines = (((q0 + qn - 1) >> 5) - t0 + 1) * NCH;
+      for (int i = tid; i < nlines; i += PL_NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(pars + ((size_t)t0 * NCH + i) * TS));
+      if (cellOrder && tid < (qn + 63) / 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(cellOrder + q0 + 64 * tid));
+    }
   }
   if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
   {
@@ -632,6 +646,10 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
                    "r"(smem_u32(reinterpret_cast<float *>(T4) + tid * 448)), "r"(1792)
                    : "memory");
+    } else if (status) {  // an arena block the partition does not hold: flag it if any mass was headed there
+      bool any = false;
+      for (int c = 0; c < 64; ++c) any |= reinterpret_cast<float *>(T4)[tid * 448 + c] != 0.f;
+      if (any) atomicOr(status, ZPC_BINS_STENCIL_BLOCK_MISSING);
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
@@ -645,9 +663,9 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
     for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
 #pragma unroll
     for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
-    if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
+    if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
     else if constexpr (MODEL == 4) {
-      zpcp::p2g_scatter_particle_eos(pos, vel, mass, C, scalar[(size_t)p0 + gorder[t]], zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, pp.a, pp.b);
+      zpcp::p2g_scatter_particle_eos(pos, vel, mass, C, scalar[(size_t)p0 + gorder[t]], zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, pp.a, pp.b);
     } else if constexpr (MODEL >= 2) {
       float *lj = scalar + (size_t)p0 + gorder[t];
       float logJp = *lj, contrib[9];
@@ -656,8 +674,8 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
       *lj = logJp;
 #pragma unroll
       for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
-      zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb}, tiles, 7, dx);
-    } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb}, tiles, 7, dx, dt, volume, mu, lam);
+      zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx);
+    } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, mu, lam);
   }
   if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
 }
@@ -666,7 +684,7 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
 // One particle of the binned G2P: gather against the staged arena velocities sv (= G2PSmem::v), APIC C, advect pos.
 __device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int ky, int kz, const zpc_hashtable_view &tb,
                                                    const float *__restrict__ tiles, int nch, float dx, float dt, float D_inv,
-                                                   float (&pos)[3], float (&vel)[3], float (&C)[9]) {
+                                                   float (&pos)[3], float (&vel)[3], float (&C)[9], int *status = nullptr) {
   zpcm::Arena ar;
   zpcm::arena_init(ar, dx, pos);
   const int ax0 = ar.corner[0] - 4 * kx, ay0 = ar.corner[1] - 4 * ky, az0 = ar.corner[2] - 4 * kz;
@@ -716,7 +734,7 @@ __device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int 
       G[r + 6] = ar.w[0][0] * pz[0][r] + ar.w[0][1] * pz[1][r] + ar.w[0][2] * pz[2][r];
     }
   } else {
-    zpcp::g2p_gather_particle(ar, zpcp::LegacyGrid{tb}, tiles, nch, vel, G);
+    zpcp::g2p_gather_particle(ar, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, nch, vel, G);
   }
   // C[r + 3e] = D_inv * sum W v_r (o_e dx - local_e) = D_inv * (dx G_re - local_e v_r)
 #pragma unroll
@@ -748,7 +766,8 @@ template <bool EOS = false>
 __global__ void __launch_bounds__(G2P_NT, ZPC_G2P_MINB)
 g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder, unsigned short *__restrict__ cellStart,
-                  zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx, float dt, float *__restrict__ scalar) {
+                  zpc_hashtable_view tb, const float *__restrict__ tiles, int nch, float dx, float dt, float *__restrict__ scalar,
+                  int *__restrict__ status) {
   __shared__ __align__(128) G2PSmem S;
   const int bin = blockIdx.x;
   if (bin >= *numBins) return;
@@ -800,7 +819,7 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
       for (int d = 0; d < 9; ++d) Fo[d] = pars[s + (ZPC_PB_F + d) * TS];  // issued early: consumed after the contraction
     }
     float vel[3], C[9], tmp[9];
-    g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C);
+    g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C, status);
     if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
       const int cx = (int)floorf(pos[0] / dx - 0.5f) - 1 - 4 * kx, cy = (int)floorf(pos[1] / dx - 0.5f) - 1 - 4 * ky,
                 cz = (int)floorf(pos[2] / dx - 0.5f) - 1 - 4 * kz;
@@ -900,7 +919,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT)
 g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                          const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder,
                          unsigned short *__restrict__ cellStart, zpc_hashtable_view tb, const float *__restrict__ tiles, int nch,
-                         float dx, float dt, float *__restrict__ scalar) {
+                         float dx, float dt, float *__restrict__ scalar, int *__restrict__ status) {
   constexpr int G2P_ST = NT / 32;
   __shared__ __align__(128) G2PStagedSmem<NT> S;
   const int bin = blockIdx.x;
@@ -971,7 +990,7 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
     if (mine) {
       const size_t s = pslot((size_t)gp);
       float vel[3], C[9], tmp[9];
-      g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C);
+      g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C, status);
       if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
         const int cx = (int)floorf(pos[0] / dx - 0.5f) - 1 - 4 * kx, cy = (int)floorf(pos[1] / dx - 0.5f) - 1 - 4 * ky,
                   cz = (int)floorf(pos[2] / dx - 0.5f) - 1 - 4 * kz;
@@ -1030,7 +1049,7 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
 // key = (block rank << 6) | cell id of the home cell ; val = particle index
 template <bool AOSOA>
 __global__ void bin_keys_kernel(const float *__restrict__ X, size_t n, float dxinv, zpc_hashtable_view tb, unsigned *keys,
-                                int *vals, int *err) {
+                                int *vals, int *err, int cap) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float x[3];
@@ -1044,7 +1063,8 @@ __global__ void bin_keys_kernel(const float *__restrict__ X, size_t n, float dxi
   }
   const int c0 = zpcm::sparsity_coord(x[0], dxinv), c1 = zpcm::sparsity_coord(x[1], dxinv), c2 = zpcm::sparsity_coord(x[2], dxinv);
   int b = zpcm::table_query(c0 >> 2, c1 >> 2, c2 >> 2, tb.tableSize, tb.keys, tb.indices);
-  if (b < 0) { if (err) *err = 2; b = 0; }
+  if (b < 0) { if (err) atomicOr(err, ZPC_BINS_HOME_BLOCK_MISSING); b = 0; }
+  if (b >= cap) { if (err) atomicOr(err, ZPC_BINS_BLOCK_CAPACITY); b = cap - 1; }   // keeps start[] / end[] in bounds and the sort's ebit honest
   keys[i] = ((unsigned)b << 6) | (unsigned)(((c0 & 3) << 4) | ((c1 & 3) << 2) | (c2 & 3));
   vals[i] = (int)i;
 }
@@ -1055,8 +1075,9 @@ __global__ void bin_bounds_kernel(const unsigned *__restrict__ keys, size_t n, i
   if (i == 0 || (keys[i - 1] >> 6) != b) start[b] = (int)i;
   if (i == n - 1 || (keys[i + 1] >> 6) != b) end[b] = (int)i + 1;
 }
-__global__ void bin_count_kernel(const int *start, const int *end, const int *cnt, int cap, int *nbins) {
+__global__ void bin_count_kernel(const int *start, const int *end, const int *cnt, int cap, int *nbins, int *err) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0 && err && *cnt > cap) atomicOr(err, ZPC_BINS_BLOCK_CAPACITY);
   if (b >= cap) return;
   nbins[b] = b < *cnt ? (end[b] - start[b] + BIN_MAX - 1) / BIN_MAX : 0;
 }
@@ -1067,7 +1088,7 @@ __global__ void bin_fill_kernel(const int *start, const int *end, const int *nbi
   const int nb = min(*cnt, cap);
   if (b == 0) {
     const int total = nb > 0 ? binoff[nb - 1] + nbins[nb - 1] : 0;
-    if (total > binCapacity) { if (err) *err = 3; *numBins = 0; }
+    if (total > binCapacity) { if (err) atomicOr(err, ZPC_BINS_BIN_CAPACITY); *numBins = 0; }
     else { *numBins = total; binStart[total] = n; }
   }
   if (b >= nb) return;
@@ -1110,6 +1131,11 @@ __global__ void unbin_kernel(const float *__restrict__ srcT, size_t n, zpc_parti
   for (int c = 0; c < 9; ++c) { A.C[9 * i + c] = srcT[s + (ZPC_PB_C + c) * TS]; A.F[9 * i + c] = srcT[s + (ZPC_PB_F + c) * TS]; }
 }
 
+__global__ void gather_f32_kernel(const float *__restrict__ src, const int *__restrict__ idx, float *__restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
 int bit_length(unsigned v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
 
 // shared pipeline of bin_particles / rebin_particles
@@ -1136,7 +1162,7 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
   if (!temp) { *temp_bytes = need; return ZPCB200_OK; }
   if (*temp_bytes < need) return ZPCB200_E_TEMP_TOO_SMALL;
   char *t = (char *)temp;
-  int *err = (int *)t;
+  int *err = dst.status;   // may be NULL
   unsigned *keys = (unsigned *)(t + o_keys), *skeys = (unsigned *)(t + o_skeys);
   int *vals = (int *)(t + o_vals), *svals = order_out ? order_out : (int *)(t + o_svals);
   int *start = (int *)(t + o_start), *end = (int *)(t + o_end), *nbins = (int *)(t + o_nb), *binoff = (int *)(t + o_off);
@@ -1145,7 +1171,7 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
   if (dst.cellOrderValid) ZPC_CUDA(cudaMemsetAsync(dst.cellOrderValid, 0, sizeof(int), s));  // new slots: cache is stale
   const unsigned gp = (unsigned)((n + 255) / 256), gb = (unsigned)((cap + 255) / 256);
   if (n) {
-    bin_keys_kernel<SRC_AOSOA><<<gp, 256, 0, s>>>(SRC_AOSOA ? srcT : A.X, n, 1.0f / dx, tb, keys, vals, err);
+    bin_keys_kernel<SRC_AOSOA><<<gp, 256, 0, s>>>(SRC_AOSOA ? srcT : A.X, n, 1.0f / dx, tb, keys, vals, err, cap);
     ZPC_CHECK_LAUNCH();
     zpc_port pk = {keys, 0, 0, 0, 1}, pv = {vals, 0, 0, 0, 1}, psk = {skeys, 0, 0, 0, 1}, psv = {svals, 0, 0, 0, 1};
     size_t sb = sort_bytes;
@@ -1154,7 +1180,7 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
     bin_bounds_kernel<<<gp, 256, 0, s>>>(skeys, n, start, end);
     ZPC_CHECK_LAUNCH();
   }
-  bin_count_kernel<<<gb, 256, 0, s>>>(start, end, tb.cnt, cap, nbins);
+  bin_count_kernel<<<gb, 256, 0, s>>>(start, end, tb.cnt, cap, nbins, err);
   ZPC_CHECK_LAUNCH();
   {
     zpc_port pi = {nbins, 0, 0, 0, 1}, po = {binoff, 0, 0, 0, 1};
@@ -1175,11 +1201,13 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
 // Kernel variants (see zpcb200_set_tuning): defaults from the environment, once.
 struct Tuning {
   int p2g_sweep;   // 4 = three cells x nine node columns per warp; 5 = the same on packed fp32 (FFMA2); 3 = one cell x 27 nodes
+  int plane_prefetch;  // plane sweep: distance (in bins) of the L2 prefetch of a later CTA's particle lines, 0 = off (env ZPCB200_PLANE_PREFETCH)
   int g2p_staged;  // 0 = plain loads, 256-thread CTAs; 1 (= 64) | 64 | 128 | 256 = particle channels staged with TMA bulk copies, that many threads per CTA
 };
 Tuning &tuning() {
   static Tuning t = [] {
-    Tuning d = {4, 1};
+    Tuning d = {4, 448, 1};
+    if (const char *e = getenv("ZPCB200_PLANE_PREFETCH")) d.plane_prefetch = atoi(e);
     if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = e[0] == '3' ? 3 : (e[0] == '5' ? 5 : (e[0] == '6' ? 6 : 4));
     if (const char *e = getenv("ZPCB200_G2P_STAGED")) d.g2p_staged = atoi(e);
     return d;
@@ -1210,14 +1238,14 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
   if (variant == 6) {
     p2g_plane_kernel<MODEL><<<bins.binCapacity, PL_NT, sizeof(P2GPlaneSmem), (cudaStream_t)stream>>>(
         bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart, bins.cellOrderValid, tb,
-        g.tiles, g.dx, dt, volume, mu, lam, yield_stress, scalar, pp);
+        g.tiles, g.dx, dt, volume, mu, lam, yield_stress, scalar, pp, tuning().plane_prefetch, bins.status);
     ZPC_CHECK_LAUNCH();
     return ZPCB200_OK;
   }
   auto kern = variant == 3 ? p2g_binned_kernel<3, MODEL> : variant == 5 ? p2g_binned_kernel<5, MODEL> : p2g_binned_kernel<4, MODEL>;
   kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
-      bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp);
+      bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp, bins.status);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }
@@ -1232,7 +1260,7 @@ static int g2p_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
   const int nt = staged == 128 ? 128 : staged == 256 ? 256 : staged ? 64 : G2P_NT;
   kern<<<bins.binCapacity, nt, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
                                                               cache ? bins.cellOrder : nullptr, bins.cellStart, tb, g.tiles,
-                                                              g.numChannels, g.dx, dt, scalar);
+                                                              g.numChannels, g.dx, dt, scalar, bins.status);
   ZPC_CHECK_LAUNCH();
   if (cache) ZPC_CUDA(cudaMemsetAsync(bins.cellOrderValid, 1, sizeof(int), (cudaStream_t)stream));  // non-zero = valid
   return ZPCB200_OK;
@@ -1264,6 +1292,13 @@ int zpcb200_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src, z
   zpc_particles_view none = {};
   if (temp && (src.pars.base == dst.pars.base || dst.pars.size < src.pars.size)) return ZPCB200_E_BADARG;
   return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, table, dx, dst, nullptr, (cudaStream_t)stream);
+}
+int zpcb200_gather_f32(const float *src, const int *idx, float *dst, size_t n, zpc_stream_t stream) {
+  if (n && (!src || !idx || !dst || src == dst)) return ZPCB200_E_BADARG;
+  if (!n) return ZPCB200_OK;
+  gather_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
 }
 int zpcb200_unbin_particles(zpc_bins_view bins, zpc_particles_view pars, zpc_stream_t stream) {
   if (!pars.X || !pars.V || !pars.C || !pars.F || pars.count > bins.pars.size) return ZPCB200_E_BADARG;

@@ -14,6 +14,8 @@ namespace zpcp {
 struct LegacyGrid {
   static constexpr int S = 2;
   zpc_hashtable_view tb;
+  int *missing = nullptr;  // optional device status word: ORed with `missing_bit` when a stencil block is absent (binned callers)
+  int missing_bit = 0;
   ZPC_HD int query(int bx, int by, int bz) const {
     return zpcm::table_query(bx, by, bz, tb.tableSize, tb.keys, tb.indices);
   }
@@ -21,6 +23,8 @@ struct LegacyGrid {
 struct SparseGrid8 {
   static constexpr int S = 3;
   zpc_bht_view tb;
+  int *missing = nullptr;
+  int missing_bit = 0;
   ZPC_HD int query(int bx, int by, int bz) const { return zpcm::bht_query(bx << 3, by << 3, bz << 3, tb); }
 };
 template <class G> ZPC_HD int cell_offset(int lx, int ly, int lz) {
@@ -63,7 +67,12 @@ static __host__ __device__ __noinline__ void p2g_scatter_core(const float (&pos)
       for (int k = 0; k < 3; ++k) {
         const int lx = lx0 + i, ly = ly0 + j, lz = lz0 + k;
         const long long o = off[((lx >> S) << 2) | ((ly >> S) << 1) | (lz >> S)];
-        if (o < 0) continue;  // block absent from the partition: cannot happen after partition_build on these positions
+        if (o < 0) {  // block absent from the partition: cannot happen after partition_build on these positions
+#ifdef __CUDA_ARCH__
+          if (tb.missing) atomicOr(tb.missing, tb.missing_bit);
+#endif
+          continue;
+        }
         float *t = tiles + o + cell_offset<G>(lx, ly, lz);
         const float x0 = (float)i * dx - ar.local[0], x1 = (float)j * dx - ar.local[1], x2 = (float)k * dx - ar.local[2];
         const float W = ar.w[0][i] * ar.w[1][j] * ar.w[2][k];
@@ -139,7 +148,12 @@ static __host__ __device__ __noinline__ void g2p_gather_particle(const zpcm::Are
       for (int k = 0; k < 3; ++k) {
         const int lx = lx0 + i, ly = ly0 + j, lz = lz0 + k;
         const long long o = off[((lx >> S) << 2) | ((ly >> S) << 1) | (lz >> S)];
-        if (o < 0) continue;
+        if (o < 0) {
+#ifdef __CUDA_ARCH__
+          if (tb.missing) atomicOr(tb.missing, tb.missing_bit);
+#endif
+          continue;
+        }
         const float *t = tiles + o + cell_offset<GA>(lx, ly, lz);
         const float W = ar.w[0][i] * ar.w[1][j] * ar.w[2][k];
         const float oe[3] = {(float)i, (float)j, (float)k};

@@ -110,7 +110,7 @@ def migrate_particles(attrs, dest, group=None):
     widths = [attrs[k].shape[1] if attrs[k].dim() == 2 else 1 for k in names]
     n = dest.numel()
     packed = torch.cat([attrs[k].reshape(n, -1) for k in names], dim=1) if n else torch.zeros(0, sum(widths), dtype=torch.float32, device=dest.device)
-    order = torch.argsort(dest, stable=True)
+    order = torch.argsort(dest, stable=True)   # host-side plumbing of a rare, collective operation (every few hundred substeps)
     send_counts = torch.bincount(dest, minlength=world).to(torch.int64)
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
@@ -379,10 +379,10 @@ class DistMpmSolver:
         self.halo.exchange_add(L.grids)
         L._mark("halo")
         L.max_vel_sqr.zero_()
-        api.compute_grid_block_velocity(L.grids, L.table, L.dt, L.extf, L.mode, L.max_vel_sqr)
+        L._grid_update()                    # the local solver's own update: colliders included (ComputeGridBlockVelocity + boundaries)
         # nothing downstream in the substep consumes the CFL scalar: reduce it off the critical path
         self._cfl_work = dist.all_reduce(L.max_vel_sqr, op=dist.ReduceOp.MAX, group=self.group, async_op=True)
         L._mark("grid_update")
-        api.g2p_transfer(L.bins, L.table, L.grids, L.dt)
+        api.g2p_transfer(L.bins, L.table, L.grids, L.dt, model=L.model)   # the J variant for an equation of state
         L._mark("g2p")
         L.step_no += 1

@@ -51,6 +51,7 @@ class MpmSolver:
         self.grids = api.Grids(dx, self.block_cap, 7, device)
         self.max_vel_sqr = torch.zeros(1, dtype=torch.float32, device=device)
         self.rebin_every = int(rebin_every)
+        self.check_status = True      # read the device status words at every re-bin (one small D2H; off inside graph capture)
         self.step_no = 0
         self.stage_events = None
         self.aos = api.Particles(P, device)
@@ -64,8 +65,13 @@ class MpmSolver:
                 src = getattr(self.aos, self._side)
                 if src is None:
                     raise ValueError("this model needs the per-particle %s attribute (P2G.hpp:67,93)" % self._side)
-                setattr(self.bins, self._side, src[self.order.long()].contiguous())
+                # two persistent side buffers that ping-pong with bins / bins_alt (a captured graph ends on the buffer it
+                # started from), permuted by the library's own gather
+                setattr(self.bins, self._side, torch.empty_like(src))
+                setattr(self.bins_alt, self._side, torch.empty_like(src))
+                api.gather_f32(src, self.order, getattr(self.bins, self._side))
                 self._rebin_order = torch.arange(self.n, dtype=torch.int32, device=device)
+            self.bins.check_status("bin_particles")
             self.aos = None if shuffle_free else self.aos
         elif layout != "aos":
             raise ValueError(layout)
@@ -125,11 +131,18 @@ class MpmSolver:
         self._mark("begin")
         if self._side:   # the side array (logJp / J) follows the permutation of the re-bin
             api.rebin_particles(self.bins, self.table, self.dx, self.bins_alt, stream, order_out=self._rebin_order)
-            setattr(self.bins_alt, self._side, getattr(self.bins, self._side)[self._rebin_order.long()].contiguous())
+            api.gather_f32(getattr(self.bins, self._side), self._rebin_order, getattr(self.bins_alt, self._side), stream)
         else:
             api.rebin_particles(self.bins, self.table, self.dx, self.bins_alt, stream)
         self.bins, self.bins_alt = self.bins_alt, self.bins
         self._mark("rebin")
+        if self.check_status and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+            # one D2H read per re-bin: the status word of the bins that just retired (a stencil block missing from the partition since
+            # the last re-bin = a particle out-ran the extra ring), of the new bins (capacity) and the table's overflow flag
+            self.bins_alt.check_status("substeps since the last re-bin")
+            self.bins.check_status("rebin_particles")
+            if int(self.table.overflow.item()):
+                raise RuntimeError("hash-grid partition overflow: raise expected_blocks")
 
     def rebin_due(self):
         return self.layout == "binned" and self.step_no > 0 and self.rebin_every > 0 and self.step_no % self.rebin_every == 0
