@@ -6,8 +6,10 @@
 One "step" = one explicit APIC substep over the whole synthetic particle cloud:
   partition build -> clear grid -> P2G -> grid update -> G2P   (+ the re-bin every `--rebin-every` substeps).
 value   = particle-substeps / s, inputs resident in HBM (whole job, all ranks; max-over-ranks time).
-e2e     = the same metric through the reference-facing host-buffer call (MpmSolver.substep_host): pinned host
-          arrays -> H2D -> substep on the reference's AoS layout -> D2H of the particle state, every step.
+e2e     = the same metric through the reference-facing host-buffer call (MpmSolver.substep_host_pipelined): pinned host
+          arrays -> H2D -> substep on the reference's AoS layout -> D2H of the particle state, every step, the copies
+          overlapped with the chunked P2G / G2P.  PCIe-bound at N = 1: 6.4 GB up + 6.1 GB down per step, and the download
+          cannot start before the last upload has been scattered (the grid couples all particles).
 roofline= the dominant kernel (binned P2G): algorithmic bytes (100 B/particle read + 28 B per
           active cell written at 8 ppc = 103.5 B/particle) / its CUDA-event time, against MEASURED_PEAKS.json.
 cpu_baseline = the reference's own OpenMP path (oracle/_ref, built from /root/reference) on a bounded sample.
@@ -143,9 +145,16 @@ def main():
     ap.add_argument("--model", default="fcr", choices=["fcr", "eos"], help="fcr = the headline workload (fixed-corotated); eos = the weakly "
                     "compressible fluid of SURVEY §8(d) on the same cloud (single GPU, no e2e leg)")
     ap.add_argument("--e2e-timeout", type=int, default=240, help="seconds after which the N>1 e2e leg is abandoned (the line is still printed)")
-    ap.add_argument("--e2e-pipelined", type=int, default=0, help="chunks of MpmSolver.substep_host_pipelined (0 = the plain call)")
+    ap.add_argument("--e2e-pipelined", type=int, default=8, help="chunks of MpmSolver.substep_host_pipelined: PCIe copies overlapped with the chunked "
+                    "P2G / G2P (default; measured 232 ms against 256 ms for the plain call at C3 — both PCIe-bound: 12.5 GB per step over one link); "
+                    "0 = the plain MpmSolver.substep_host")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the N-GPU vs 1-GPU self-check (zpc_b200/selfcheck.py) that precedes the timing")
+    ap.add_argument("--refcuda-steps", type=int, default=2, help="N = 1: timed substeps of the reference's own CUDA path on the same GPU "
+                    "(oracle/_ref/libzpcref_cuda.so, a process of its own; informational `vs_reference_cuda` block; 0 = skip)")
+    ap.add_argument("--prims-log2", type=int, default=26, help="N = 1: size of the C5 primitive line (reduce / exclusive_scan / radix_sort_pair, "
+                    "i32 / u32 keys) added as `prims`; 0 = skip")
     ap.add_argument("--p2g-sweep", type=int, default=-1, choices=[-1, 3, 4, 5, 6], help="binned P2G sweep variant (zpcb200_set_tuning; 5 = packed fp32)")
     ap.add_argument("--g2p-staged", type=int, default=-1, choices=[-1, 0, 1], help="binned G2P particle staging variant")
     args = ap.parse_args()
@@ -197,6 +206,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = peaks()
     api.set_tuning(args.p2g_sweep, args.g2p_staged)
+    # ---- N > 1: the sharded path is checked against the single-GPU solver before anything is timed ----------------
+    mg_parity = None
+    if world > 1 and not args.no_parity_check:
+        from zpc_b200.selfcheck import multi_gpu_parity
+        try:
+            plain = multi_gpu_parity(transport=args.halo)
+            moved = multi_gpu_parity(transport=args.halo, migrate=True)
+            mg_parity = dict(ok=bool(plain["ok"] and moved["ok"]), substeps=plain, substeps_with_migration=moved,
+                             what="N-GPU sharded substeps vs the single-GPU solver on the same 110 592-particle cloud (particles cross the "
+                                  "slab cuts), all particle attributes within 5e-5 after 6 substeps; zpc_b200/selfcheck.py")
+        except Exception as ex:   # collective: raised on every rank alike
+            mg_parity = dict(ok=False, error=repr(ex))
 
     # ---- build the (rank's shard of the) workload ----------------------------------------------------------
     if world == 1:
@@ -265,7 +286,7 @@ def main():
     # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this config (per launch)
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if tr.get("config") == args.config and world == 1 and args.model == "fcr":
             traffic = tr["kernels"]["p2g_binned_kernel"]["dram_bytes"]
     except Exception:
@@ -281,6 +302,7 @@ def main():
                  rebins_in_timed_region=n_rebins)
 
     tuning_now = api.get_tuning()
+    vs_refcuda, prims = None, None
 
     def make_line(e2e, cpu):
         return dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
@@ -292,7 +314,7 @@ def main():
                                 parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, halo exchange of shared grid blocks via %s" % (
                                     world, "peer stores into symmetric memory over NVLink + device barrier" if transport == "p2p" else "NCCL send/recv")),
                     substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,
-                    clocks=clocks)
+                    clocks=clocks, multi_gpu_parity=mg_parity, vs_reference_cuda=vs_refcuda, prims=prims)
 
     # the e2e leg at N > 1 is collective: if it has not finished after --e2e-timeout seconds (a rank stuck in a collective), rank 0
     # still prints the line — the device-resident numbers above are complete — and every rank leaves
@@ -383,6 +405,35 @@ def main():
             cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"], ms_per_step=r["ms_per_step"])
         except Exception as ex:  # the checker is optional; never let it break the GPU number
             cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(ex))
+
+    # ---- informational: the reference's own CUDA path on the same GPU (SURVEY §8(d) secondary baseline), per stage -------------
+    if rank == 0 and world == 1 and args.refcuda_steps > 0 and args.model == "fcr":
+        try:
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "bench", str(G), str(s), str(args.refcuda_steps), "1"],
+                               cwd=ROOT, capture_output=True, text=True, timeout=600)
+            if r.returncode == 0 and r.stdout.strip():
+                ref = json.loads(r.stdout.strip().splitlines()[-1][r.stdout.strip().splitlines()[-1].index("{"):])
+                ours_stage = dict(partition=(per_step.get("partition") or 0.0), clean=per_step.get("clean"), p2g=per_step.get("p2g"),
+                                  grid_update=per_step.get("grid_update"), g2p=per_step.get("g2p"))
+                vs_refcuda = dict(reference_ms_per_step=ref["ms_per_step"], reference_stage_ms=ref["stage_ms"], ours_ms_per_step=ms_per_step,
+                                  ours_stage_ms=ours_stage,
+                                  speedup=dict(step=ref["ms_per_step"] / ms_per_step,
+                                               **{k: ref["stage_ms"][k] / ours_stage[k] for k in ("clean", "p2g", "grid_update", "g2p") if ours_stage.get(k)}),
+                                  note="the reference's generic functors on cuda_exec() (range_launch + CUB + HashTable lock-CAS insert), unmodified, "
+                                       "compiled for sm_100 (oracle/_ref/libzpcref_cuda.so), same cloud, particles resident; it rebuilds its partition "
+                                       "every substep (ours: with the re-bin, amortised in ours_ms_per_step)")
+            else:
+                vs_refcuda = dict(unavailable=(r.stderr.strip().splitlines() or ["failed"])[-1][:200])
+        except Exception as ex:
+            vs_refcuda = dict(unavailable=repr(ex)[:200])
+    # ---- C5 in one line: the primitives at 2^k keys, algorithmic GB/s against the same peak ------------------------------------
+    if rank == 0 and world == 1 and args.prims_log2 > 0:
+        try:
+            from benchmarks.prims_sweep import time_prims
+            prims = time_prims(args.prims_log2, hbm_peak)
+        except Exception as ex:
+            prims = dict(unavailable=repr(ex)[:200])
 
     finished.set()
     if rank == 0:

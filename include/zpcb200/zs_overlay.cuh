@@ -16,6 +16,7 @@
 // cuda/execution/ExecutionPolicy.cuh:806-815); errors surface like the reference's (checkCuApiError is private to Cuda, so a
 // std::runtime_error carries the code); the policy's sync(true) default is honoured.
 #pragma once
+#include <atomic>
 #include <stdexcept>
 #include <string>
 
@@ -99,8 +100,23 @@ namespace zs {
       if (this->shouldSync()) Cuda::context(getProcid()).syncStreamSpare(getStreamid(), loc);
     }
     /// temp == nullptr size query, allocation from the stream-ordered pool, the call, release on the same stream
+    /// The reference releases the stream-ordered pool at every synchronisation (release threshold 0): each primitive call then pays a
+    /// fresh cuMemCreate / map for its scratch — measured 2.5 ms per call on a B200 whatever the size (r02_prims_vs_refcuda).  The
+    /// overlay keeps the device's default pool warm instead (once per device; memory stays reserved for later scratch requests).
+    static void b200KeepPoolWarm(int dev) {
+      static std::atomic<unsigned long long> done{0};
+      const unsigned long long bit = 1ull << (dev & 63);
+      if (done.load(std::memory_order_acquire) & bit) return;
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      done.fetch_or(bit, std::memory_order_release);
+    }
     template <class Fn, class... Args> void b200TwoPhase(const char *what, const source_location &loc, Fn fn, Args... args) const {
       auto &ctx = Cuda::context(getProcid());
+      b200KeepPoolWarm(getProcid());
       void *stream = b200Stream();
       size_t bytes = 0;
       int rc = fn(nullptr, &bytes, args..., nullptr);

@@ -259,3 +259,63 @@ def test_f64_scan_and_reduce(pol, oracle, n):
     for op in ("sum", "min", "max"):
         pol.reduce(d, r, op)
         assert r.cpu().numpy()[0] == oracle.reduce(op, "f64", a), (op, n)
+
+
+def _chunks(n, step=1 << 27):
+    for a in range(0, n, step):
+        yield a, min(a + step, n)
+
+
+def test_one_billion_keys_sort_scan_reduce_properties(pol):
+    """C5 upper end (BASELINE configs[4] "1M-1B keys"): n = 2^30 — the API limit, where an all-one-digit pass drives a look-back
+    prefix to exactly 2^30 (csrc/prims.cu: RS_VAL_MASK) — pairs sorted with every key sharing its top byte, then sortedness, stability,
+    keys-follow-values and the permutation checksum, verified in slices; exclusive scan of ones and reduce at the same size."""
+    n = 1 << 30
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    k = torch.randint(0, 1 << 24, (n,), device="cuda", dtype=torch.int32, generator=g)
+    k |= 0x35000000                                                # one digit value in the fourth pass: its prefix reaches n
+    v = torch.arange(n, device="cuda", dtype=torch.int32)
+    ko = torch.empty_like(k); vo = torch.empty_like(v)
+    pol.radix_sort_pair(k, v, ko, vo, kind="i32")
+    total = 0
+    for a, b in _chunks(n):
+        e = min(b + 1, n)
+        kk, vv = ko[a:e], vo[a:e]
+        assert bool((kk[1:] >= kk[:-1]).all())
+        eq = kk[1:] == kk[:-1]
+        assert bool((vv[1:][eq] > vv[:-1][eq]).all())              # stability
+        assert bool((k[vo[a:b].long()] == ko[a:b]).all())           # values follow their keys
+        total += int(vo[a:b].long().sum().item())
+    assert total == n * (n - 1) // 2                               # a permutation
+    del ko, vo, v
+    ones = k; ones.fill_(1)
+    out = torch.empty_like(ones)
+    pol.exclusive_scan(ones, out)
+    for a, b in _chunks(n):
+        assert bool((out[a:b] == torch.arange(a, b, device="cuda", dtype=torch.int32)).all())
+    r = torch.zeros(1, dtype=torch.int32, device="cuda")
+    pol.reduce(ones, r, "sum")
+    assert r.item() == n
+
+
+@pytest.mark.parametrize("kind,ebit", [("u32", 12), ("u32", 20), ("u32", 24), ("u64", 64), ("u64", 40)])
+def test_block_key_style_sorts_at_2_26(pol, kind, ebit):
+    """12- / 20- / 24-bit restricted u32 keys through `ebit` (what block-key and binning sorts use) and u64 keys, 2^26
+    pairs: result equals torch's stable sort of the masked keys, index for index"""
+    n = 1 << 26
+    g = torch.Generator(device="cuda"); g.manual_seed(ebit)
+    if kind == "u32":
+        k = torch.randint(0, 2 ** 31 - 1, (n,), device="cuda", dtype=torch.int32, generator=g)
+        masked = (k & ((1 << ebit) - 1)).to(torch.int64)
+        keys = k.view(torch.uint32)
+    else:
+        k = torch.randint(0, 2 ** 62, (n,), device="cuda", dtype=torch.int64, generator=g)
+        masked = k if ebit == 64 else (k & ((1 << ebit) - 1))
+        keys = k.view(torch.uint64)
+    v = torch.arange(n, device="cuda", dtype=torch.int32)
+    ko = torch.empty_like(keys); vo = torch.empty_like(v)
+    pol.radix_sort_pair(keys, v, ko, vo, kind=kind, sbit=0, ebit=ebit)
+    want_k, want_i = torch.sort(masked, stable=True)
+    assert bool((vo.long() == want_i).all())                       # index-exact (stable)
+    got = ko.view(torch.int32 if kind == "u32" else torch.int64)
+    assert bool((got == k[want_i]).all())                          # whole keys travel, only the window orders them

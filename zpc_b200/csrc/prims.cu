@@ -357,6 +357,9 @@ int scan_impl(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_t 
 constexpr int RS_NT = 256;
 constexpr int RS_NW = RS_NT / 32;
 constexpr int RS_BINS = 256;
+// look-back descriptor = 2 flag bits + a 30-bit count.  n <= 2^30 is safe: an aggregate is at most one tile, an inclusive prefix of
+// tile t is at most n minus the keys of the later tiles, i.e. < 2^30 for every tile that HAS a successor; the one value that can
+// reach 2^30 exactly (last tile, every key in one digit) wraps to 0 and is never read — nobody looks back at the last tile.
 constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_INCL = 2u << 30, RS_VAL_MASK = (1u << 30) - 1;
 
 template <typename K> struct KeyBits;
