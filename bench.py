@@ -148,7 +148,10 @@ def main():
     ap.add_argument("--e2e-pipelined", type=int, default=8, help="chunks of MpmSolver.substep_host_pipelined: PCIe copies overlapped with the chunked "
                     "P2G / G2P (default; measured 232 ms against 256 ms for the plain call at C3 — both PCIe-bound: 12.5 GB per step over one link); "
                     "0 = the plain MpmSolver.substep_host")
-    ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--halo", default="auto", choices=["auto", "fused", "p2p", "nccl"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "off"], help="N > 1: replay the substeps as CUDA graphs of 2 x rebin_every substeps "
+                    "(DistMpmSolver.capture_cycle: kernels, re-bins, topology all_gathers and device barriers in one launch); the per-stage "
+                    "times then come from a separate eager pass.  auto = fall back to eager launches if the capture is refused")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the N-GPU vs 1-GPU self-check (zpc_b200/selfcheck.py) that precedes the timing")
     ap.add_argument("--refcuda-steps", type=int, default=2, help="N = 1: timed substeps of the reference's own CUDA path on the same GPU "
@@ -248,18 +251,45 @@ def main():
     for _ in range(args.warmup):
         sol.substep()
     barrier()
+    graph_len, graph_note = 0, None
+    if world > 1 and args.graph == "auto" and getattr(sol, "transport", None) == "fused":
+        try:
+            graph_len = sol.capture_cycle()
+            sol.replay_cycle()                 # one untimed replay: graph upload
+        except Exception as ex:                # collective code path: refused on every rank alike
+            graph_len, graph_note = 0, "capture refused: %r" % (ex,)
+        barrier()
     launches0 = api.kernel_launch_count()
-    sol.stage_events = []
+    if not graph_len:
+        sol.stage_events = []
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        sol.substep()
+    if graph_len:
+        for _ in range(args.steps // graph_len):
+            sol.replay_cycle()
+        for _ in range(args.steps % graph_len):
+            sol.substep()
+    else:
+        for _ in range(args.steps):
+            sol.substep()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = api.kernel_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    stage_steps = args.steps
+    if graph_len:
+        # kernels inside a graph replay are not counted by the library's launch counter and carry no stage events: one eager cycle
+        # (same kernels, same order) supplies both — its wall time is not the headline, `ms` above is
+        barrier()                              # rank 0 just spent 0.15 s closing the clock sampler: start the pass together
+        launches0 = api.kernel_launch_count()
+        sol.stage_events = []
+        for _ in range(graph_len):
+            sol.substep()
+        barrier()
+        launches = launches + (api.kernel_launch_count() - launches0) * (args.steps // graph_len)
+        stage_steps = graph_len
     stage = sol.stage_times_ms()
     sol.stage_events = None
     if dist is not None:
@@ -269,14 +299,23 @@ def main():
         cnt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(cnt)
         launches = int(cnt.item())
+    per_rank = None
+    if dist is not None:
+        # every rank's own stage times: the step is as slow as the slowest rank, the others wait at the barrier / the CFL reduction
+        names = ("clean", "p2g", "halo", "grid_update", "g2p", "partition", "rebin", "gap")
+        mine = torch.tensor([stage.get(k, 0.0) / stage_steps for k in names], device="cuda", dtype=torch.float64)
+        allr = torch.zeros(world * len(names), device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {k: [round(v, 4) for v in allr.view(world, len(names))[:, i].tolist()] for i, k in enumerate(names)}
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
     nblocks = sol.table.size()
     transport = getattr(sol, "transport", None)
 
     # ---- per-kernel roofline from the live CUDA-event stage times ---------------------------------------------
-    per_step = {k: v / args.steps for k, v in stage.items()}
-    n_rebins = sum(1 for i in range(args.warmup, args.warmup + args.steps) if i > 0 and args.rebin_every > 0 and i % args.rebin_every == 0)
+    per_step = {k: v / stage_steps for k, v in stage.items()}
+    n_rebins = (sum(1 for i in range(args.warmup, args.warmup + args.steps) if i > 0 and args.rebin_every > 0 and i % args.rebin_every == 0)
+                if not graph_len else graph_len // max(args.rebin_every, 1))
     fused_ms = sum(per_step.get(k, 0.0) for k in ("clean", "p2g", "grid_update", "g2p"))
     kern = {}
     for k, bpp in bytes_pp.items():
@@ -298,7 +337,7 @@ def main():
     fused_bpp = sum(bytes_pp.values())
     fused_gbps = fused_bpp * n_local / (fused_ms * 1e-3) / 1e9 if fused_ms else None
     fused = dict(ms=fused_ms, bytes_per_particle=fused_bpp, achieved=fused_gbps, frac=(fused_gbps / hbm_peak) if fused_gbps else None,
-                 kernels=kern, partition_ms=per_step.get("partition"), halo_ms=per_step.get("halo"), rebin_ms_each=(stage.get("rebin", 0.0) / n_rebins) if n_rebins else None,
+                 kernels=kern, partition_ms=per_step.get("partition"), halo_ms=per_step.get("halo"), gap_ms=per_step.get("gap"), rebin_ms_each=(stage.get("rebin", 0.0) / n_rebins) if n_rebins else None,
                  rebins_in_timed_region=n_rebins)
 
     tuning_now = api.get_tuning()
@@ -312,9 +351,12 @@ def main():
                                            else "hash-grid partition rebuilt with each re-bin, one extra ring (EnlargeSparsity{-1,3})"),
                                 kernel_variants=tuning_now, active_blocks=nblocks, l2="inputs (%.1f GB particle state) exceed the 126 MB L2; no explicit flush" % (n_local * 100 / 1e9),
                                 parallelism="1 GPU" if world == 1 else "x-slab shards over %d GPUs, halo exchange of shared grid blocks via %s" % (
-                                    world, "peer stores into symmetric memory over NVLink + device barrier" if transport == "p2p" else "NCCL send/recv")),
+                                    world, {"fused": "TMA bulk reduce-adds from the P2G write-back straight into the peers' symmetric-memory buffers over NVLink, "
+                                                     "one device barrier, receive fused into the grid update",
+                                            "p2p": "peer stores into symmetric memory over NVLink + device barrier"}.get(transport, "NCCL send/recv"))),
                     substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,
-                    clocks=clocks, multi_gpu_parity=mg_parity, vs_reference_cuda=vs_refcuda, prims=prims)
+                    clocks=clocks, cuda_graph=dict(substeps_per_graph=graph_len, note=graph_note, stage_times="from one eager cycle after the timed region") if world > 1 else None,
+                    per_rank_stage_ms=per_rank, multi_gpu_parity=mg_parity, vs_reference_cuda=vs_refcuda, prims=prims)
 
     # the e2e leg at N > 1 is collective: if it has not finished after --e2e-timeout seconds (a rank stuck in a collective), rank 0
     # still prints the line — the device-resident numbers above are complete — and every rank leaves
@@ -439,10 +481,17 @@ def main():
     if rank == 0:
         print(json.dumps(make_line(e2e, cpu)), flush=True)
     if dist is not None:
+        # the line is out.  Leave without tearing NCCL / symmetric memory / captured graphs down object by object: a process group
+        # destroyed while a CUDA graph still references its communicator has been seen to hang (round 2, N = 2), and nothing is
+        # left to flush — every rank waits for the others, then exits
         try:
-            dist.destroy_process_group()
-        except Exception:   # the line is out; a failed e2e leg must not turn the teardown into a non-zero exit
+            torch.cuda.synchronize()
+            dist.barrier()
+        except Exception:
             pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -483,7 +483,46 @@ int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_gr
 int zpcb200_set_tuning(int p2g_sweep, int g2p_staged);
 int zpcb200_get_tuning(int *p2g_sweep_host, int *g2p_staged_host);
 
-/* ---- multi-GPU one-ring halo; no reference counterpart ----------------------- */
+/* ---- multi-GPU one-ring halo, fused (SURVEY §8(e), §2.1 last paragraph; no reference counterpart) --------------------------
+ * Every rank owns a receive buffer that its peers can address (peer-mapped over NVLink: torch symmetric memory, cudaIpc or
+ * cuMem exports — the library only sees addresses): [2 halves][world senders][seg tiles][7 x 64 floats], all zero outside the
+ * window between a send and its receive.
+ *   send    = inside the binned P2G's write-back: a CTA that adds an arena tile to a grid block which another rank also holds
+ *             issues one more TMA bulk reduce-add (cp.reduce.async.bulk ... add.f32, 1 792 B) for it — into the slot of that
+ *             block in the PEER's buffer.  No pack kernel, no staging copy; the transfer overlaps the rest of the P2G.
+ *   barrier = the caller's (one device-side barrier between the P2G and the grid update: symmetric-memory barrier, NCCL, ...).
+ *   receive = inside the grid update: a shared block adds its slots (ascending peer rank: a fixed summation order), writes the
+ *             complete m / rhs back like a single-GPU grid would hold them, zeroes the slots, then computes v.
+ * half alternates every substep, so one barrier per substep suffices.
+ * The maps come from zpcb200_halo_codes (this rank's block keys as sortable codes, padded) -> the caller's all_gather ->
+ * zpcb200_halo_build: both ranks of a pair enumerate their common blocks in ascending key order, so the slot of a block is its
+ * rank in that intersection — the same number on both sides, no negotiation, nothing read back to the host. */
+#define ZPCB200_HALO_MAX_PEERS 16
+#define ZPCB200_HALO_K 4 /* a block is shared with at most this many other ranks (slab or block-range shards: 1..3) */
+typedef struct zpc_halo_view {
+  const int *peer; /* [numBlocks * ZPCB200_HALO_K]: ranks that also hold block b, ascending, -1 terminated; NULL = no halo */
+  const int *pos;  /* [numBlocks * ZPCB200_HALO_K]: slot of block b in the segment this rank and that peer share */
+  int world, rank;
+  int seg;  /* tiles per (half, sender) segment */
+  int half; /* 0 | 1 */
+  float *recv;                          /* this rank's receive buffer */
+  float *peers[ZPCB200_HALO_MAX_PEERS]; /* every rank's receive buffer as addressable from this rank (peers[rank] == recv) */
+  int *status;                          /* device int, ORed with ZPC_HALO_* (may be NULL) */
+} zpc_halo_view;
+enum { ZPC_HALO_TOO_MANY_PEERS = 1 /* a block is shared with more than ZPCB200_HALO_K ranks */, ZPC_HALO_SEGMENT_FULL = 2 /* > seg common blocks */ };
+/* codes[i] = sortable 63-bit code of active block i (i < *cnt), INT64_MAX beyond: what the caller all_gathers ([capacity] each) */
+int zpcb200_halo_codes(zpc_hashtable_view table, int capacity, long long *codes, zpc_stream_t stream);
+/* all_codes: [world][capacity] gathered codes (each row ascending).  Writes peer / pos ([capacity * ZPCB200_HALO_K] ints each). */
+int zpcb200_halo_build(void *temp, size_t *temp_bytes, const long long *all_codes, int world, int rank, int capacity, int seg,
+                       int *peer_out, int *pos_out, int *status, zpc_stream_t stream);
+/* P2GTransfer on the binned layout with the halo send fused into the write-back (fixed-corotated) */
+int zpcb200_p2g_apic_fcr_binned_halo(zpc_bins_view bins, zpc_hashtable_view table, zpc_grids_view grids, float dt,
+                                     zpc_fixed_corotated model, zpc_halo_view halo, zpc_stream_t stream);
+/* ComputeGridBlockVelocity (+ up to ZPCB200_MAX_COLLIDERS colliders) with the halo receive fused in */
+int zpcb200_grid_update_halo(zpc_grids_view grids, zpc_hashtable_view table, float dt, const float extf[3], int mode,
+                             const zpc_collider *colliders, int ncolliders, float *maxVelSqr, zpc_halo_view halo, zpc_stream_t stream);
+
+/* ---- multi-GPU one-ring halo, unfused building blocks (pack / exchange / unpack; the NCCL transport uses them) ------------- */
 /* pack: copy tiles listed in blockIds[0..n) into a contiguous buffer (nch channels from chn0);
  * unpack_add / unpack_set: add / overwrite them back.  The exchange itself is NCCL send/recv (host). */
 int zpcb200_halo_pack(zpc_grids_view grids, const int *blockIds, int n, int chn0, int nch,

@@ -103,6 +103,14 @@ class zpc_bins_view(C.Structure):
                 ("cellStart", C.c_void_p), ("cellOrderValid", C.c_void_p), ("status", C.c_void_p)]
 
 
+HALO_K, HALO_MAX_PEERS = 4, 16
+
+
+class zpc_halo_view(C.Structure):
+    _fields_ = [("peer", C.c_void_p), ("pos", C.c_void_p), ("world", C.c_int), ("rank", C.c_int), ("seg", C.c_int), ("half", C.c_int),
+                ("recv", C.c_void_p), ("peers", C.c_void_p * HALO_MAX_PEERS), ("status", C.c_void_p)]
+
+
 # bits of zpc_bins_view.status (include/zpcb200.h)
 BINS_HOME_BLOCK_MISSING, BINS_BIN_CAPACITY, BINS_BLOCK_CAPACITY, BINS_STENCIL_BLOCK_MISSING = 1, 2, 4, 8
 
@@ -806,6 +814,29 @@ def compute_grid_block_velocity_with_boundaries(grids, table, dt, extf, mode, co
     arr = (zpc_collider * max(len(colliders), 1))(*colliders)
     _check(lib().zpcb200_grid_update_bc(grids.view(), table.view(), C.c_float(dt), e, C.c_int(mode), arr, C.c_int(len(colliders)),
                                         C.c_void_p(max_vel_sqr.data_ptr()), _stream_ptr(stream)), "grid_update_bc")
+
+
+def p2g_transfer_halo(bins, table, grids, dt, model, halo, stream=None):
+    """binned P2G (fixed-corotated) with the halo send fused into the write-back (zpcb200_p2g_apic_fcr_binned_halo)"""
+    _check(lib().zpcb200_p2g_apic_fcr_binned_halo(bins.view(), table.view(), grids.view(), C.c_float(dt), model, halo, _stream_ptr(stream)),
+           "p2g(binned, halo)")
+
+
+def grid_update_halo(grids, table, dt, extf, mode, colliders, max_vel_sqr, halo, stream=None):
+    """ComputeGridBlockVelocity (+ colliders) with the halo receive fused in (zpcb200_grid_update_halo)"""
+    e = (C.c_float * 3)(*[float(v) for v in extf])
+    arr = (zpc_collider * max(len(colliders), 1))(*colliders)
+    _check(lib().zpcb200_grid_update_halo(grids.view(), table.view(), C.c_float(dt), e, C.c_int(mode), arr, C.c_int(len(colliders)),
+                                          C.c_void_p(max_vel_sqr.data_ptr()), halo, _stream_ptr(stream)), "grid_update_halo")
+
+
+def halo_codes(table, capacity, codes, stream=None):
+    _check(lib().zpcb200_halo_codes(table.view(), C.c_int(capacity), C.c_void_p(codes.data_ptr()), _stream_ptr(stream)), "halo_codes")
+
+
+def halo_build(all_codes, world, rank, capacity, seg, peer_out, pos_out, status, stream=None):
+    _two_phase(lib().zpcb200_halo_build, (C.c_void_p(all_codes.data_ptr()), C.c_int(world), C.c_int(rank), C.c_int(capacity), C.c_int(seg),
+                                          C.c_void_p(peer_out.data_ptr()), C.c_void_p(pos_out.data_ptr()), C.c_void_p(status.data_ptr())), (), stream)
 
 
 def g2p_transfer(pars, table, grids, dt, stream=None, model=None):

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzpcb200.so")
-SOURCES = ["prims.cu", "mpm.cu", "mpm_binned.cu", "sparsegrid.cu", "policy.cu", "lbvh.cu"]
+SOURCES = ["prims.cu", "mpm.cu", "mpm_binned.cu", "sparsegrid.cu", "policy.cu", "lbvh.cu", "halo.cu"]
 HEADERS = ["common.cuh", "mpm_math.cuh", "mpm_particle.cuh", "mpm_kernels.cuh", "partition.cuh", "lbvh_core.cuh", "p2g_sweep.cuh", "../../include/zpcb200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

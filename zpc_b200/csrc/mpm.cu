@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) grid_angular_momentum_kernel(const float 
 struct ColliderSet { zpc_collider c[ZPCB200_MAX_COLLIDERS]; int n; };
 __global__ void __launch_bounds__(256) grid_update_bc_kernel(float *tiles, const int *__restrict__ active_keys, const int *cnt, int nch,
                                                              size_t cap_blocks, float dx, float dt, float ex, float ey, float ez, int mode,
-                                                             ColliderSet cols, float *max_vel_sqr) {
+                                                             ColliderSet cols, float *max_vel_sqr, zpc_halo_view halo) {
   size_t nb = (size_t)*cnt;
   if (nb > cap_blocks) nb = cap_blocks;
   const int cell = threadIdx.x & 63;
@@ -185,6 +185,35 @@ __global__ void __launch_bounds__(256) grid_update_bc_kernel(float *tiles, const
   float mx = 0.f;
   for (size_t b = (size_t)blockIdx.x * 4 + (threadIdx.x >> 6); b < nb; b += (size_t)gridDim.x * 4) {
     float *t = tiles + b * (size_t)nch * 64;
+    if (halo.peer) {
+      // fused halo receive: add what the ranks sharing this block sent (ascending rank: fixed order), leave the complete sums in the
+      // grid like a single-GPU run would, hand the slots back zeroed.  Every load is issued before the first store (one vector load
+      // for the four peer ranks, one for their slots, then up to 4 x 7 + 7 independent loads): the kernel is latency-bound otherwise
+      // (ncu: 3 dependent round trips per peer, 15 % of the DRAM bandwidth).
+      const int4 pr = *reinterpret_cast<const int4 *>(halo.peer + b * ZPCB200_HALO_K);
+      if (pr.x >= 0) {
+        const int4 ps = *reinterpret_cast<const int4 *>(halo.pos + b * ZPCB200_HALO_K);
+        const int rk[4] = {pr.x, pr.y, pr.z, pr.w}, pk[4] = {ps.x, ps.y, ps.z, ps.w};
+        float *src[4];
+        float v[4][7], own[7];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          src[k] = halo.recv + (((size_t)halo.half * halo.world + (rk[k] >= 0 ? rk[k] : 0)) * halo.seg + pk[k]) * 448 + cell;
+#pragma unroll
+          for (int c = 0; c < 7; ++c) v[k][c] = rk[k] >= 0 ? __ldcg(src[k] + c * 64) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) own[c] = t[c * 64 + cell];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (rk[k] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) { own[c] += v[k][c]; src[k][c * 64] = 0.f; }
+          }
+#pragma unroll
+        for (int c = 0; c < 7; ++c) t[c * 64 + cell] = own[c];
+      }
+    }
     float mass = t[cell];
     if (mass != 0.f) {
       float mvx = t[64 + cell], mvy = t[128 + cell], mvz = t[192 + cell];
@@ -387,7 +416,27 @@ int zpcb200_grid_update_bc(zpc_grids_view g, zpc_hashtable_view tb, float dt, co
     cs.c[k] = colliders[k];
   }
   grid_update_bc_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks, g.dx,
-                                                                           dt, extf[0], extf[1], extf[2], mode, cs, maxVelSqr);
+                                                                           dt, extf[0], extf[1], extf[2], mode, cs, maxVelSqr, zpc_halo_view{});
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+
+int zpcb200_grid_update_halo(zpc_grids_view g, zpc_hashtable_view tb, float dt, const float extf[3], int mode,
+                             const zpc_collider *colliders, int ncolliders, float *maxVelSqr, zpc_halo_view halo, zpc_stream_t stream) {
+  if (!g.tiles || !tb.activeKeys || !tb.cnt || !extf || !maxVelSqr || (mode != 0 && mode != 1) || g.numChannels != 7 ||
+      ncolliders < 0 || ncolliders > ZPCB200_MAX_COLLIDERS || (ncolliders && !colliders))
+    return ZPCB200_E_BADARG;
+  if (halo.peer && (!halo.pos || !halo.recv || halo.world < 1 || halo.world > ZPCB200_HALO_MAX_PEERS || (unsigned)halo.rank >= (unsigned)halo.world ||
+                    halo.seg <= 0 || (halo.half != 0 && halo.half != 1)))
+    return ZPCB200_E_BADARG;
+  ColliderSet cs;
+  cs.n = ncolliders;
+  for (int k = 0; k < ncolliders; ++k) {
+    if ((unsigned)colliders[k].geometry > 2u || (unsigned)colliders[k].type > 2u || !(colliders[k].s > 0.f)) return ZPCB200_E_BADARG;
+    cs.c[k] = colliders[k];
+  }
+  grid_update_bc_kernel<<<ZPC_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(g.tiles, tb.activeKeys, tb.cnt, g.numChannels, g.numBlocks, g.dx,
+                                                                           dt, extf[0], extf[1], extf[2], mode, cs, maxVelSqr, halo);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }

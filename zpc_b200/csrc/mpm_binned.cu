@@ -47,6 +47,25 @@ constexpr int REC_F = 28;               // floats per particle record
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ size_t pslot(size_t i) { return ((i >> 5) * NCH) * TS + (i & 31); }  // channel 0 of particle i
 
+
+// fused halo send (include/zpcb200.h: zpc_halo_view): the arena tile in shared memory at `tile_smem` was just added to grid block `id`;
+// if other ranks hold that block too, the same 1 792 bytes are reduce-added into its slot of their receive buffers (peer-mapped)
+__device__ __forceinline__ bool halo_send_tile(const zpc_halo_view &halo, int id, const float *tile_smem) {
+  bool sent = false;
+  if (halo.peer) {
+#pragma unroll
+    for (int k = 0; k < ZPCB200_HALO_K; ++k) {
+      const int r = halo.peer[(size_t)id * ZPCB200_HALO_K + k];
+      if (r < 0) break;
+      float *dst = halo.peers[r] + (((size_t)halo.half * halo.world + halo.rank) * halo.seg + halo.pos[(size_t)id * ZPCB200_HALO_K + k]) * 448;
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(tile_smem)), "r"(1792)
+                   : "memory");
+      sent = true;
+    }
+  }
+  return sent;
+}
+
 struct P2GSmem {
   float4 rec4[CHUNK * 7 + CHUNK / 8];  // 29184 B at CHUNK = 256: 7 float4 per record (+1 pad granule per 8 records, used by VAR 4)
   float out[8 * 448];               // 14336 B: the arena as eight [7][64] grid tiles, accumulated with shared atomics
@@ -79,7 +98,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
                   const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
                   const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
                   float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, int prefetch,
-                  float yield_stress, float *__restrict__ scalar, zpcm::PlasticPrm pp, int *__restrict__ status) {
+                  float yield_stress, float *__restrict__ scalar, zpcm::PlasticPrm pp, int *__restrict__ status, zpc_halo_view halo) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GSmem &S = *reinterpret_cast<P2GSmem *>(smem_raw);
   const int bin = blockIdx.x;
@@ -327,6 +346,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   // ---- (c) add the eight arena tiles to the grid: TMA bulk reductions --------------------------------------------
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
   __syncthreads();
+  bool remote = false;
   if (tid < 8) {
     const int id = S.tile_id[tid];
     if (id >= 0) {
@@ -334,6 +354,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
                    "r"(smem_u32(S.out + tid * 448)), "r"(1792)
                    : "memory");
+      remote = halo_send_tile(halo, id, S.out + tid * 448);
     } else if (status) {  // an arena block the partition does not hold: flag it if any mass was headed there
       bool any = false;
       for (int c = 0; c < 64; ++c) any |= S.out[tid * 448 + c] != 0.f;
@@ -365,7 +386,12 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
       zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx);
     } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, mu, lam);
   }
-  if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
+  if (tid < 8) {
+    // smem must outlive the bulk reads; a tile that also went to a peer waits for the writes themselves, so that the kernel's
+    // completion (and the barrier the caller puts after it) orders them before the peer's grid update
+    if (remote) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -449,7 +475,7 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
                  const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
                  const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
                  float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, float yield_stress,
-                 float *__restrict__ scalar, zpcm::PlasticPrm pp, int prefetch_ahead, int *__restrict__ status) {
+                 float *__restrict__ scalar, zpcm::PlasticPrm pp, int prefetch_ahead, int *__restrict__ status, zpc_halo_view halo) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GPlaneSmem &S = *reinterpret_cast<P2GPlaneSmem *>(smem_raw);
   const int bin = blockIdx.x;
@@ -639,6 +665,7 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
   __syncthreads();
+  bool remote = false;
   if (tid < 8) {
     const int id = S.tile_id[tid];
     if (id >= 0) {
@@ -646,6 +673,7 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
                    "r"(smem_u32(reinterpret_cast<float *>(T4) + tid * 448)), "r"(1792)
                    : "memory");
+      remote = halo_send_tile(halo, id, reinterpret_cast<float *>(T4) + tid * 448);
     } else if (status) {  // an arena block the partition does not hold: flag it if any mass was headed there
       bool any = false;
       for (int c = 0; c < 64; ++c) any |= reinterpret_cast<float *>(T4)[tid * 448 + c] != 0.f;
@@ -677,7 +705,12 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
       zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx);
     } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, mu, lam);
   }
-  if (tid < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the bulk reads
+  if (tid < 8) {
+    // smem must outlive the bulk reads; a tile that also went to a peer waits for the writes themselves, so that the kernel's
+    // completion (and the barrier the caller puts after it) orders them before the peer's grid update
+    if (remote) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1220,7 +1253,8 @@ Tuning &tuning() {
 // shared launch of the binned P2G: MODEL 0 fixed-corotated, 1 von Mises
 template <int MODEL>
 static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, float volume, float E, float nu,
-                             float yield_stress, zpc_stream_t stream, float *scalar = nullptr, zpcm::PlasticPrm pp = {}) {
+                             float yield_stress, zpc_stream_t stream, float *scalar = nullptr, zpcm::PlasticPrm pp = {},
+                             zpc_halo_view halo = {}) {
   if (g.numChannels != 7 || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
     return ZPCB200_E_BADARG;
   static std::atomic<bool> attr_set{false};  // idempotent: two threads racing here both set the same attribute
@@ -1238,14 +1272,14 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
   if (variant == 6) {
     p2g_plane_kernel<MODEL><<<bins.binCapacity, PL_NT, sizeof(P2GPlaneSmem), (cudaStream_t)stream>>>(
         bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart, bins.cellOrderValid, tb,
-        g.tiles, g.dx, dt, volume, mu, lam, yield_stress, scalar, pp, tuning().plane_prefetch, bins.status);
+        g.tiles, g.dx, dt, volume, mu, lam, yield_stress, scalar, pp, tuning().plane_prefetch, bins.status, halo);
     ZPC_CHECK_LAUNCH();
     return ZPCB200_OK;
   }
   auto kern = variant == 3 ? p2g_binned_kernel<3, MODEL> : variant == 5 ? p2g_binned_kernel<5, MODEL> : p2g_binned_kernel<4, MODEL>;
   kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
-      bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp, bins.status);
+      bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp, bins.status, halo);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }
@@ -1311,6 +1345,13 @@ int zpcb200_unbin_particles(zpc_bins_view bins, zpc_particles_view pars, zpc_str
 int zpcb200_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_fixed_corotated model,
                                 zpc_stream_t stream) {
   return p2g_binned_launch<0>(bins, tb, g, dt, model.volume, model.E, model.nu, 0.f, stream);
+}
+int zpcb200_p2g_apic_fcr_binned_halo(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt, zpc_fixed_corotated model,
+                                     zpc_halo_view halo, zpc_stream_t stream) {
+  if (halo.peer && (!halo.pos || !halo.recv || halo.world < 1 || halo.world > ZPCB200_HALO_MAX_PEERS || (unsigned)halo.rank >= (unsigned)halo.world ||
+                    halo.seg <= 0 || (halo.half != 0 && halo.half != 1)))
+    return ZPCB200_E_BADARG;
+  return p2g_binned_launch<0>(bins, tb, g, dt, model.volume, model.E, model.nu, 0.f, stream, nullptr, zpcm::PlasticPrm{}, halo);
 }
 int zpcb200_p2g_apic_drucker_prager_binned(zpc_bins_view bins, float *logJp, zpc_hashtable_view tb, zpc_grids_view g, float dt,
                                            zpc_drucker_prager model, zpc_stream_t stream) {

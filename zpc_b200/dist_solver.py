@@ -250,6 +250,52 @@ class HaloExchangeP2P(HaloExchange):
             self._unpack_add(grids, ids, self.buf[(half + off_mine) * self.tile:(half + off_mine + n) * self.tile])
 
 
+class HaloFused:
+    """The exchange with nothing of its own on the stream but one barrier: the binned P2G's write-back reduce-adds every shared tile
+    straight into the peers' receive buffers (TMA bulk reduce over NVLink, zpcb200_p2g_apic_fcr_binned_halo), the grid update adds
+    what arrived and zeroes the slots (zpcb200_grid_update_halo).  The maps are built on the device from one fixed-size all_gather of
+    block codes (zpcb200_halo_codes / zpcb200_halo_build): no host read anywhere on the re-bin path.  include/zpcb200.h: zpc_halo_view."""
+
+    def __init__(self, group, device, capacity_blocks, seg=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > api.HALO_MAX_PEERS:
+            raise ValueError("HaloFused handles up to %d ranks" % api.HALO_MAX_PEERS)
+        self.cap = int(capacity_blocks)
+        self.seg = int(seg) if seg else max(8192, self.cap // 2)   # a neighbour slab can share almost half of the active set (thin slabs + rings)
+        self.tile = 7 * 64
+        self.buf = symm_mem.empty(2 * self.world * self.seg * self.tile, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        self.buf.zero_()
+        self.peer = torch.full((self.cap * api.HALO_K,), -1, dtype=torch.int32, device=device)
+        self.pos = torch.zeros(self.cap * api.HALO_K, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.codes = torch.empty(self.cap, dtype=torch.int64, device=device)
+        self.all_codes = torch.empty(self.world * self.cap, dtype=torch.int64, device=device)
+        self.step = 0
+        self._ptrs = (C.c_void_p * api.HALO_MAX_PEERS)(*([int(p) for p in self.hdl.buffer_ptrs] + [None] * (api.HALO_MAX_PEERS - self.world)))
+        self.hdl.barrier(channel=0)      # every buffer is zero before anybody sends
+
+    def build_from_table(self, table):
+        """collective, device-only: codes -> all_gather -> maps"""
+        api.halo_codes(table, self.cap, self.codes)
+        dist.all_gather_into_tensor(self.all_codes, self.codes, group=self.group)
+        api.halo_build(self.all_codes, self.world, self.rank, self.cap, self.seg, self.peer, self.pos, self.status)
+
+    def view(self):
+        import ctypes as C
+        return api.zpc_halo_view(self.peer.data_ptr(), self.pos.data_ptr(), self.world, self.rank, self.seg, self.step & 1,
+                                 self.buf.data_ptr(), self._ptrs, self.status.data_ptr())
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)      # device-side, on the current stream
+
+    def shared_blocks(self):
+        return int((self.peer.view(-1, api.HALO_K)[:, 0] >= 0).sum().item())
+
+
 def _cuda_pack_ptr(grids, ids, dst_ptr):
     import ctypes as C
     api._check(api.lib().zpcb200_halo_pack(grids.view(), C.c_void_p(ids.data_ptr()), C.c_int(ids.numel()), C.c_int(0),
@@ -279,7 +325,15 @@ class DistMpmSolver:
         self.n = self.local.n
         self.table = self.local.table
         self.halo = halo
-        if halo is None and transport in ("auto", "p2p"):
+        fused_ok = layout == "binned" and isinstance(self.local.model, api.zpc_fixed_corotated)
+        if halo is None and transport in ("auto", "fused") and fused_ok:
+            try:   # send inside the P2G write-back, receive inside the grid update, maps built on the device
+                self.halo = HaloFused(group, device, self.local.block_cap)
+            except Exception as ex:
+                if transport == "fused":
+                    raise
+                self.halo_fallback_reason = repr(ex)
+        if self.halo is None and transport in ("auto", "p2p", "fused"):
             try:
                 self.halo = HaloExchangeP2P(group, 7, device, _cuda_pack_ptr, _cuda_unpack_add)
             except Exception as ex:  # no symmetric memory on this system: same exchange over NCCL send/recv
@@ -288,9 +342,13 @@ class DistMpmSolver:
                 self.halo_fallback_reason = repr(ex)
         if self.halo is None:
             self.halo = HaloExchange(group, 7, device, _cuda_pack, _cuda_unpack_add)
-        self.transport = "p2p" if isinstance(self.halo, HaloExchangeP2P) else "nccl"
+        self.transport = "fused" if isinstance(self.halo, HaloFused) else "p2p" if isinstance(self.halo, HaloExchangeP2P) else "nccl"
+        if isinstance(self.halo, HaloFused):
+            self.local.extra_status.append((self.halo.status, "halo maps: a block shared with more than %d ranks, or a segment of the receive "
+                                                              "buffer too small" % api.HALO_K))
         self.group = group
         self._cfl_work = None
+        self._cfl_reduced = False
         self._rebuild_topology()
 
     @property
@@ -305,6 +363,9 @@ class DistMpmSolver:
         return self.local.stage_times_ms()
 
     def _rebuild_topology(self):
+        if isinstance(self.halo, HaloFused):
+            self.halo.build_from_table(self.local.table)      # nothing read back to the host
+            return
         nb = self.local.table.size()
         self.halo.build(self.local.table.active_keys[:nb])
 
@@ -327,6 +388,7 @@ class DistMpmSolver:
         L.max_vel_sqr.zero_()
         L._grid_update()
         dist.all_reduce(L.max_vel_sqr, op=dist.ReduceOp.MAX, group=self.group)
+        self._cfl_reduced = True
         api.g2p_transfer(a, L.table, L.grids, L.dt, model=L.model)
         for k in ("x", "v", "C", "F"):
             hout[k].copy_(getattr(a, k), non_blocking=True)
@@ -358,31 +420,68 @@ class DistMpmSolver:
         return moved
 
     def max_vel_sqr(self):
-        """global max |v|^2 of the last substep (CFL input); waits for the in-flight all_reduce"""
-        if self._cfl_work is not None:
-            self._cfl_work.wait()
-            self._cfl_work = None
+        """global max |v|^2 of the last substep (CFL input).  Collective: the all_reduce(max) of the per-rank scalar happens HERE, when
+        somebody asks — one NCCL enqueue per substep that nobody reads cost more host time than the whole 8-GPU step could hide
+        (the substep is ~1.5 ms at C4; round 2 measured a 0.3 ms gap per step on every rank from host-side enqueue work alone)."""
+        if not self._cfl_reduced:
+            dist.all_reduce(self.local.max_vel_sqr, op=dist.ReduceOp.MAX, group=self.group)
+            self._cfl_reduced = True
         return self.local.max_vel_sqr
+
+    # ---- CUDA graph of a whole re-bin cycle: at 8 GPUs a substep is ~1.5 ms of kernels and ~14 launches + collectives, i.e. the
+    # host cannot enqueue it faster than the GPU runs it; one graph launch per 2 * rebin_every substeps removes the host from the loop
+    def capture_cycle(self):
+        """Captures the next 2 * rebin_every substeps — two re-bins (the ping-pong particle buffers return to their roles), two
+        topology rebuilds (one fixed-size all_gather each), 2 * rebin_every device barriers — into one CUDA graph.  Needs the fused
+        halo (its maps are built on the device: nothing in the cycle reads back to the host).  Collective."""
+        L = self.local
+        if not isinstance(self.halo, HaloFused) or L.rebin_every <= 0:
+            raise ValueError("capture_cycle needs the fused halo transport and rebin_every > 0")
+        k = 2 * L.rebin_every
+        while L.step_no == 0 or L.step_no % k != 0 or (self.halo.step & 1):
+            self.substep()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        step0, bins0, hstep0 = L.step_no, L.bins, self.halo.step
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            for _ in range(k):
+                self.substep()
+        assert L.bins is bins0 and (self.halo.step - hstep0) % 2 == 0
+        L.step_no, self.halo.step, self._graph_len = step0, hstep0, k      # capturing executed nothing
+        return k
+
+    def replay_cycle(self):
+        """one graph launch = 2 * rebin_every substeps; the status words are read once per replay (outside the graph)"""
+        self._graph.replay()
+        self.local.step_no += self._graph_len
+        self._cfl_reduced = False
 
     def substep(self):
         L = self.local
-        if self._cfl_work is not None:      # the previous step's CFL reduction must be done before the scalar is reused
-            self._cfl_work.wait()
-            self._cfl_work = None
+        self._cfl_reduced = False
         if L.prepare():
             self._rebuild_topology()
         L._mark("begin")
         api.clean_grid_blocks(L.grids, L.table)
         L._mark("clean")
-        api.p2g_transfer(L.bins, L.table, L.grids, L.dt, L.model)
-        L._mark("p2g")
-        self.halo.exchange_add(L.grids)
-        L._mark("halo")
-        L.max_vel_sqr.zero_()
-        L._grid_update()                    # the local solver's own update: colliders included (ComputeGridBlockVelocity + boundaries)
-        # nothing downstream in the substep consumes the CFL scalar: reduce it off the critical path
-        self._cfl_work = dist.all_reduce(L.max_vel_sqr, op=dist.ReduceOp.MAX, group=self.group, async_op=True)
-        L._mark("grid_update")
+        if isinstance(self.halo, HaloFused):
+            hv = self.halo.view()
+            api.p2g_transfer_halo(L.bins, L.table, L.grids, L.dt, L.model, hv)      # shared tiles go to the peers from the write-back
+            L._mark("p2g")
+            self.halo.barrier()
+            L._mark("halo")
+            L.max_vel_sqr.zero_()
+            api.grid_update_halo(L.grids, L.table, L.dt, L.extf, L.mode, L.colliders, L.max_vel_sqr, hv)   # ... and are added here
+            self.halo.step += 1
+        else:
+            api.p2g_transfer(L.bins, L.table, L.grids, L.dt, L.model)
+            L._mark("p2g")
+            self.halo.exchange_add(L.grids)
+            L._mark("halo")
+            L.max_vel_sqr.zero_()
+            L._grid_update()                # the local solver's own update: colliders included (ComputeGridBlockVelocity + boundaries)
+        L._mark("grid_update")             # the CFL scalar stays per-rank until max_vel_sqr() asks for it
         api.g2p_transfer(L.bins, L.table, L.grids, L.dt, model=L.model)   # the J variant for an equation of state
         L._mark("g2p")
         L.step_no += 1

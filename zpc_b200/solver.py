@@ -52,6 +52,7 @@ class MpmSolver:
         self.max_vel_sqr = torch.zeros(1, dtype=torch.float32, device=device)
         self.rebin_every = int(rebin_every)
         self.check_status = True      # read the device status words at every re-bin (one small D2H; off inside graph capture)
+        self.extra_status = []        # [(device int tensor, message)] read together with them
         self.step_no = 0
         self.stage_events = None
         self.aos = api.Particles(P, device)
@@ -97,8 +98,10 @@ class MpmSolver:
         out = {}
         ev = self.stage_events or []
         for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
-            if n1 != "begin":
-                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+            # "begin" closes a gap nobody claimed (between two marked sections: host-side work the GPU waited for, collectives on
+            # other streams, the topology rebuild of the multi-GPU solver): reported as "gap"
+            k = n1 if n1 != "begin" else "gap"
+            out[k] = out.get(k, 0.0) + e0.elapsed_time(e1)
         return out
 
     def partition(self, stream=None):
@@ -137,12 +140,22 @@ class MpmSolver:
         self.bins, self.bins_alt = self.bins_alt, self.bins
         self._mark("rebin")
         if self.check_status and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
-            # one D2H read per re-bin: the status word of the bins that just retired (a stencil block missing from the partition since
-            # the last re-bin = a particle out-ran the extra ring), of the new bins (capacity) and the table's overflow flag
-            self.bins_alt.check_status("substeps since the last re-bin")
-            self.bins.check_status("rebin_particles")
-            if int(self.table.overflow.item()):
-                raise RuntimeError("hash-grid partition overflow: raise expected_blocks")
+            # ONE D2H read per re-bin: the status word of the bins that just retired (a stencil block missing from the partition since
+            # the last re-bin = a particle out-ran the extra ring), of the new bins (capacity), the table's overflow flag and whatever
+            # the owner registered (multi-GPU: the halo maps)
+            words = [self.bins_alt.status, self.bins.status, self.table.overflow] + [t for t, _ in self.extra_status]
+            vals = torch.cat([w.reshape(1).to(torch.int32) for w in words]).tolist()
+            if any(vals):
+                if vals[0]:
+                    self.bins_alt.check_status("substeps since the last re-bin")
+                if vals[1]:
+                    self.bins.check_status("rebin_particles")
+                if vals[2]:
+                    raise RuntimeError("hash-grid partition overflow: raise expected_blocks")
+                for v, (t, what) in zip(vals[3:], self.extra_status):
+                    if v:
+                        t.zero_()
+                        raise RuntimeError("%s (status %d)" % (what, v))
 
     def rebin_due(self):
         return self.layout == "binned" and self.step_no > 0 and self.rebin_every > 0 and self.step_no % self.rebin_every == 0
