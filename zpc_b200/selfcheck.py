@@ -18,7 +18,7 @@ def _rel(a, b, floor):
     return float((np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)).max())
 
 
-def multi_gpu_parity(s=24, G=64, steps=6, rebin_every=3, migrate=False, e2e=False, transport="auto", rtol=5e-5):
+def multi_gpu_parity(s=24, G=64, steps=6, rebin_every=3, migrate=False, e2e=False, transport="auto", rtol=5e-5, graph=False):
     """-> dict(ok, world, steps, max_err per attribute, max_vel_err, transport, shared_blocks_rank0, migrated)"""
     rank, world = dist.get_rank(), dist.get_world_size()
     full = synth.elastic_cube(s, G, jitter_F=0.03, jitter_C=0.3)
@@ -38,7 +38,12 @@ def multi_gpu_parity(s=24, G=64, steps=6, rebin_every=3, migrate=False, e2e=Fals
         from .dist_solver import BlockOwnership, shard_by_blocks
         _, cuts, keys = shard_by_blocks(full["x"], full["dx"], world)
         ownership = BlockOwnership(keys, cuts)
-    for i in range(steps):
+    if graph:   # the same substeps as CUDA graph replays (DistMpmSolver.capture_cycle): eager up to a cycle boundary, then one replay
+        k = sol.capture_cycle()
+        sol.replay_cycle()
+        torch.cuda.synchronize()
+        steps = sol.local.step_no
+    for i in range(0 if graph else steps):
         if ownership is not None and i == (steps // 2 // rebin_every) * rebin_every and i > 0:     # at a re-bin boundary
             moved = sol.migrate(ownership)
         if e2e:
@@ -56,7 +61,7 @@ def multi_gpu_parity(s=24, G=64, steps=6, rebin_every=3, migrate=False, e2e=Fals
     moved_all = torch.tensor([moved], device="cuda", dtype=torch.int64)
     dist.all_reduce(moved_all)
     out = dict(ok=True, world=world, steps=steps, transport=sol.transport, migrated=int(moved_all.item()) if migrate else None,
-               path="substep_host (AoS)" if e2e else "substep (binned)")
+               path="substep_host (AoS)" if e2e else "substep (binned)" + (", CUDA graph replay" if graph else ""))
     if rank == 0:
         got = {k: np.concatenate([g[k] for g in gathered]) for k in ("x", "v", "m", "C", "F")}
         one = MpmSolver(full, full["dx"], full["volume"], dt, synth.GRAVITY, mode=1, layout="binned", rebin_every=rebin_every,
