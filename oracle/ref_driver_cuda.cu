@@ -25,6 +25,7 @@
 #include "zensim/simulation/grid/GridOp.hpp"
 #include "zensim/simulation/sparsity/SparsityOp.hpp"
 #include "zensim/simulation/transfer/G2P.hpp"
+#include "zensim/simulation/transfer/G2P2G.hpp"
 #include "zensim/simulation/transfer/P2G.hpp"
 
 #include "zensim/container/Bvh.hpp"
@@ -57,6 +58,24 @@ namespace {
   };
   void h2d(void *dst, const void *src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); }
   void d2h(void *dst, const void *src, size_t bytes) { cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); }
+}  // namespace
+
+/// ---- G2P2GTransfer (simulation/transfer/G2P2G.hpp:49-141): the reference's own functor, instantiated with a minimal grid-dof view ----
+/// The functor is generic in GridDofView and only asks it for scalar_value_type, get(node, vector_c) and ref(i); the reference's
+/// own DofView (types/View.h) does not compile under gcc 13, so this driver hands it three floats per node in a plain device
+/// array — the arithmetic that runs is the reference's, line for line (round 1 could only check a restatement).
+namespace {
+  struct PlainDofView {
+    using scalar_value_type = float;
+    float *p;
+    template <class Tag> __device__ vec<float, 3> get(size_t node, Tag) const { return vec<float, 3>{p[3 * node], p[3 * node + 1], p[3 * node + 2]}; }
+    __device__ float &ref(size_t i) { return p[i]; }
+  };
+  template <class Model> void run_g2p2g(RefMpmCuda &s, float dt, const Model &model, float *gridv_dev, float *gridr_dev) {
+    auto pol = cuda_exec().device(0);
+    pol(range(s.n), G2P2GTransfer{exec_cuda, wrapv<transfer_scheme_e::apic>{}, dt, model, proxy<execspace_e::cuda>(s.grids.grid(collocated_c)),
+                                  PlainDofView{gridv_dev}, PlainDofView{gridr_dev}, s.table, s.pars});
+  }
 }  // namespace
 
 extern "C" {
@@ -152,6 +171,28 @@ void zpcrefcuda_mpm_g2p(void *h, float dt) {
   FixedCorotatedConfig model{};
   auto pol = cuda_exec().device(0);
   pol(range(s.n), G2PTransfer{exec_cuda, wrapv<transfer_scheme_e::apic>{}, dt, model, s.grids, s.table, s.pars});
+}
+/// model_kind 0 fixed-corotated {E, nu}, 1 von Mises {E, nu, yieldStress}; gridv / gridr: host arrays [nblocks * 64 * 3] in the
+/// partition's block numbering (zpcrefcuda_mpm_get_keys); gridr is zeroed first and returned.
+int zpcrefcuda_mpm_g2p2g(void *h, int model_kind, const float *prm, float volume, float dt, const float *gridv, float *gridr) {
+  auto &s = *(RefMpmCuda *)h;
+  const size_t ndof = (size_t)s.nblocks * 64 * 3;
+  Vector<float> gv{ndof, memsrc_e::device, 0}, gr{ndof, memsrc_e::device, 0};
+  h2d(gv.data(), gridv, sizeof(float) * ndof);
+  cudaMemset(gr.data(), 0, sizeof(float) * ndof);
+  if (model_kind == 0) {
+    FixedCorotatedConfig m{};
+    m.E = prm[0]; m.nu = prm[1]; m.volume = volume;
+    run_g2p2g(s, dt, m, gv.data(), gr.data());
+  } else if (model_kind == 1) {
+    VonMisesFixedCorotatedConfig m{};
+    m.E = prm[0]; m.nu = prm[1]; m.yieldStress = prm[2]; m.volume = volume;
+    run_g2p2g(s, dt, m, gv.data(), gr.data());
+  } else
+    return -1;
+  cudaDeviceSynchronize();
+  d2h(gridr, gr.data(), sizeof(float) * ndof);
+  return 0;
 }
 void zpcrefcuda_mpm_get_grid(void *h, float *out) {
   auto &s = *(RefMpmCuda *)h;

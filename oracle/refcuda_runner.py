@@ -14,6 +14,9 @@ test session or a bench run down with it.
   python -m oracle.refcuda_runner prims-bench LOG2N ITERS   # C5: the reference's CudaExecutionPolicy primitives (and the same generic
                                                             # calls on b200_exec()) timed on the GPU; one JSON line
   python -m oracle.refcuda_runner prims N OUT.npz           # zs::radix_sort_pair / exclusive_scan / reduce with b200_exec()
+  python -m oracle.refcuda_runner g2p2g IN.npz OUT.npz      # the reference's own G2P2GTransfer (simulation/transfer/G2P2G.hpp:49-141) on
+                                                            # cuda_exec(): IN carries the particles, model (0 fcr, 1 von Mises), prm;
+                                                            # the grid velocity DOFs are node_field() of the node coordinates
 """
 import ctypes as C
 import json
@@ -29,6 +32,24 @@ SO = os.path.join(HERE, "_ref", "libzpcref_cuda.so")
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def node_field(keys):
+    """Grid velocity DOFs as a function of the node's integer coordinates only, so that two partitions with different block
+    numberings (the reference's insertion order, ours by key rank) hold the same field: keys [nb, 3] block coordinates (the
+    table's keys, SparsityOp.hpp:72-78: cell coordinate / 4) -> [nb * 64, 3] float32, cell id (x << 4) | (y << 2) | z inside a
+    block (geometry/Structure.hpp:49-61)."""
+    keys = np.asarray(keys, np.int64)
+    c = np.arange(64)
+    loc = np.stack([c >> 4, (c >> 2) & 3, c & 3], 1)                       # [64, 3]
+    node = (keys[:, None, :] * 4 + loc[None, :, :]).reshape(-1, 3)            # [nb * 64, 3]
+    out = np.empty((node.shape[0], 3), np.float32)
+    for d in range(3):
+        h = (node[:, 0] * 73856093 + node[:, 1] * 19349663 + node[:, 2] * 83492791 + d * 2654435761) & 0xFFFFFFFF
+        h = (h ^ (h >> 15)) * 2246822519 & 0xFFFFFFFF
+        h = (h ^ (h >> 13)) & 0xFFFFFF
+        out[:, d] = (h.astype(np.float64) / float(0xFFFFFF) * 2.0 - 1.0).astype(np.float32)
+    return out
 
 
 class RefCuda:
@@ -107,6 +128,24 @@ def main(argv):
         out = r.substep(P, float(z["dt"]), float(z["E"]), float(z["nu"]), float(z["gravity"]), int(z["mode"]))
         out.pop("stage_ms", None)
         np.savez(argv[2], **out)
+    elif argv[0] == "g2p2g":
+        z = np.load(argv[1])
+        P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}
+        n, dx = P["x"].shape[0], float(z["dx"])
+        L = r.L
+        L.zpcrefcuda_mpm_g2p2g.restype = C.c_int
+        h = C.c_void_p(L.zpcrefcuda_mpm_create(C.c_int(n), C.c_float(dx), C.c_int(max(n // 8, 64))))
+        L.zpcrefcuda_mpm_set_particles(h, _p(P["x"]), _p(P["v"]), _p(P["m"]), _p(P["C"]), _p(P["F"]))
+        nb = L.zpcrefcuda_mpm_partition(h)
+        keys = np.empty((nb, 3), np.int32)
+        L.zpcrefcuda_mpm_get_keys(h, _p(keys))
+        gridv = np.ascontiguousarray(node_field(keys))
+        gridr = np.zeros((nb * 64, 3), np.float32)
+        prm = np.ascontiguousarray(z["prm"], np.float32)
+        rc = L.zpcrefcuda_mpm_g2p2g(h, C.c_int(int(z["model"])), _p(prm), C.c_float(float(z["volume"])), C.c_float(float(z["dt"])), _p(gridv), _p(gridr))
+        assert rc == 0, rc
+        L.zpcrefcuda_mpm_destroy(h)
+        np.savez(argv[2], active_keys=keys, gridr=gridr.reshape(nb, 64, 3), nblocks=nb)
     elif argv[0] == "overlay":
         z = np.load(argv[1])
         P = {k: np.ascontiguousarray(z[k]) for k in ("x", "v", "m", "C", "F")}

@@ -367,6 +367,49 @@ def test_g2p2g_matches_the_restated_functor(oracle, model):
     assert np.array_equal(pars.x.cpu().numpy(), P["x"])
 
 
+@pytest.mark.parametrize("model", ["fcr", "vonmises"])
+def test_g2p2g_matches_the_references_own_functor(oracle, model, tmp_path):
+    """PINS G2P2G: the reference's own G2P2GTransfer (simulation/transfer/G2P2G.hpp:49-141), compiled by nvcc into
+    oracle/_ref/libzpcref_cuda.so with a plain three-floats-per-node DOF view (oracle/ref_driver_cuda.cu: the reference's DofView
+    does not compile, the functor only needs get / ref) and run on cuda_exec() in a process of its own, against
+    zpcb200_g2p2g_apic AND the restated oracle zo_g2p2g on the same particles and the same grid velocity field, by block key."""
+    import subprocess
+    import sys
+    from oracle.refcuda_runner import RefCuda, node_field
+    from zpc_b200 import api
+    if not RefCuda.available():
+        pytest.skip("oracle/_ref/libzpcref_cuda.so not built (make -C oracle refcuda, where /root/reference is mounted)")
+    P = synth.elastic_cube(8, 32, jitter_F=0.04, jitter_C=0.3, shuffle_seed=23)
+    dx = P["dx"]
+    kind, prm, m = {"fcr": (0, [E, NU], api.model_fcr(P["volume"], E, NU)),
+                    "vonmises": (1, [E, NU, 2946.0], api.model_vonmises(P["volume"], E, NU, 2946.0))}[model]
+    fin, fout = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(fin, dt=synth.DT, model=kind, prm=np.array(prm, np.float32), **P)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "oracle.refcuda_runner", "g2p2g", fin, fout], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    z = np.load(fout)
+    kr, want = grid_by_key(z["active_keys"], z["gridr"])
+    pars, table = build_partition(P)
+    ht = host_table(table)
+    nb = ht["nblocks"]
+    assert int(z["nblocks"]) == nb and np.array_equal(ht["active_keys"], kr)
+    gridv = node_field(ht["active_keys"])
+    gv, gr = torch.from_numpy(gridv).cuda(), torch.zeros(nb * 64, 3, device="cuda")
+    api.g2p2g_transfer(pars, table, dx, synth.DT, m, gv, gr)
+    torch.cuda.synchronize()
+    got = gr.cpu().numpy().reshape(nb, 64, 3)
+    scale = float(np.abs(want).max())
+    assert scale > 0
+    err = float(np.abs(got - want).max()) / scale
+    assert err <= RTOL_STRESS, "zpcb200_g2p2g_apic vs the reference's G2P2GTransfer: %g" % err
+    # the restatement the CPU tests use, pinned the same way
+    rest = oracle.g2p2g(kind, prm[2:] or [0], P, ht, dx, synth.DT, E, NU, P["volume"], gridv).reshape(nb, 64, 3)
+    err_o = float(np.abs(rest - want).max()) / scale
+    assert err_o <= RTOL_STRESS, "zo_g2p2g vs the reference's G2P2GTransfer: %g" % err_o
+    print("g2p2g %s: max err / max |r|  ours %.2e  oracle %.2e" % (model, err, err_o))
+
+
 def test_overlay_on_the_references_containers(oracle, tmp_path):
     """include/zpcb200/zs_overlay.cuh compiled against the unmodified reference headers (oracle/_ref/libzpcref_cuda.so): the
     reference's own Particles / HashTable / Grids on the device, the composed substep once through the reference's functors on

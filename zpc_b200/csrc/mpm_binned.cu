@@ -621,19 +621,25 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
 #pragma unroll
           for (int j = 0; j < 3; ++j) { acc[ch][j][0] = 0.f; acc[ch][j][1] = 0.f; acc[ch][j][2] = 0.f; }
         zpcs::sweep_plane(S.rec4, lo, hi, nmax, Lp, acc);
-        if (have) {
+        {
           const int c6 = g / 6, zc = g - 6 * c6, cyp = c6 % 6;                    // g = (cx' * 6 + cy') * 6 + cz'
           const int lx = sl + pi, ly0 = cyp - 3 * rh;                             // arena node (cx' + i, cy' + j, cz' + k), region-local
+          // one (j, k) at a time: inside a step every lane adds the same offset to its own (cell, plane), so the addresses differ;
+          // ACROSS steps two lanes do meet (cell z with k = 1 and cell z + 1 with k = 0 are the same node), and nothing but the warp
+          // barrier keeps the compiler from batching the loads of one step with the stores of another (compute-sanitizer racecheck
+          // flagged exactly that in the first version, profiles/r02_sanitizer.md)
 #pragma unroll
           for (int j = 0; j < 3; ++j)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              float *dstn = Pw + priv_idx(lx, ly0 + j, zc + k);
+              if (have) {
+                float *dstn = Pw + priv_idx(lx, ly0 + j, zc + k);
 #pragma unroll
-              for (int ch = 0; ch < 7; ++ch) dstn[ch * 160] += acc[ch][j][k];
+                for (int ch = 0; ch < 7; ++ch) dstn[ch * 160] += acc[ch][j][k];
+              }
+              __syncwarp();
             }
         }
-        __syncwarp();   // the next round's lanes may touch the nodes this round's lanes wrote (and the list is rebuilt per slab)
       }
     }
     __syncthreads();  // records are overwritten by the next chunk / the private copies are read by the merge
