@@ -31,6 +31,7 @@ void hm_stress(int model, int n, float volume, float mu, float lam, const float 
     for (int d = 0; d < 9; ++d) f[d] = F[9 * p + d];
     if (model == 0) zpcm::stress_fcr(volume, mu, lam, f, pf);
     else if (model == 10) zpcm::stress_fcr_lean(volume, mu, lam, f, pf);   // the binned fast path's arithmetic
+    else if (model == 11) zpcm::stress_fcr_lean<true>(volume, mu, lam, f, pf);   // ... with the converged-sweep skip (sweep variant 8)
     else if (model == 1) zpcm::stress_vonmises(volume, mu, lam, prm[0], f, pf);
     else if (model == 2) zpcm::stress_sand(volume, mu, lam, prm[0], prm[1], prm[2], prm[3] != 0.f, logJp[p], f, pf);
     else zpcm::stress_nacc(volume, mu, prm[0], prm[1], prm[2], prm[3], prm[4] != 0.f, logJp[p], f, pf);

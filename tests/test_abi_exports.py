@@ -93,7 +93,7 @@ def test_new_entries_host_side_behaviour():
     # kernel tuning hook: validated values only, -1 keeps
     a, b = ctypes.c_int(0), ctypes.c_int(0)
     assert L.zpcb200_get_tuning(ctypes.byref(a), ctypes.byref(b)) == 0 and (a.value, b.value) == (4, 1)
-    assert L.zpcb200_set_tuning(7, -1) == -1 and L.zpcb200_set_tuning(-1, 5) == -1
+    assert L.zpcb200_set_tuning(7, -1) == -1 and L.zpcb200_set_tuning(2, -1) == -1 and L.zpcb200_set_tuning(-1, 5) == -1
     assert L.zpcb200_set_tuning(3, 0) == 0
     L.zpcb200_get_tuning(ctypes.byref(a), ctypes.byref(b))
     assert (a.value, b.value) == (3, 0)

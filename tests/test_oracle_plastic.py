@@ -179,20 +179,20 @@ def _oracle_stress(o, model, F, lj, prm):
     return out, l
 
 
-@pytest.mark.parametrize("model", [0, 10, 1, 2, 3])
+@pytest.mark.parametrize("model", [0, 10, 11, 1, 2, 3])
 def test_device_math_on_the_host_tracks_the_oracle(oracle, oracle_fma, hostmath, model):
     """zpcm::stress_* (what the kernels run) vs the oracle on random F.  The device code orders the SVD's arithmetic
     differently, so it is held to the distance between two builds of the reference's own arithmetic (+ an fp32 floor)
     — measured here, per regime, against the stress scale of the sample."""
     rs = np.random.RandomState(40 + model)
-    prm = {0: dict(E=E, nu=NU), 10: dict(E=E, nu=NU), 1: dict(E=E, nu=NU, ys=300.0), 2: dict(SAND, E=E, nu=NU), 3: dict(NACC)}[model]
+    prm = {0: dict(E=E, nu=NU), 10: dict(E=E, nu=NU), 11: dict(E=E, nu=NU), 1: dict(E=E, nu=NU, ys=300.0), 2: dict(SAND, E=E, nu=NU), 3: dict(NACC)}[model]
     mu, lam = oracle.lame(prm["E"], prm["nu"])
     if model == 3:
         bm, msqr = oracle.nacc_consts(prm["E"], prm["nu"], prm["fa"])
         b, m = C.c_float(), C.c_float()
         hostmath.hm_nacc_consts(C.c_float(prm["E"]), C.c_float(prm["nu"]), C.c_float(prm["fa"]), C.c_int(3), C.byref(b), C.byref(m))
         assert (b.value, m.value) == (bm, msqr)
-    vec = {0: [0.0], 10: [0.0], 1: [300.0], 2: [SAND["cohesion"], SAND["beta"], SAND["yieldSurface"], 1.0],
+    vec = {0: [0.0], 10: [0.0], 11: [0.0], 1: [300.0], 2: [SAND["cohesion"], SAND["beta"], SAND["yieldSurface"], 1.0],
            3: [0, NACC["xi"], NACC["beta"], 0, 1.0]}[model]
     if model == 3:
         vec[0], vec[3] = bm, msqr
@@ -205,8 +205,8 @@ def test_device_math_on_the_host_tracks_the_oracle(oracle, oracle_fma, hostmath,
         lj = rs.uniform(-1.8, 0.2, n).astype(np.float32) if model == 3 else rs.uniform(-0.05, 0.02, n).astype(np.float32)
         got, l = np.empty((n, 9), np.float32), lj.copy()
         hostmath.hm_stress(C.c_int(model), C.c_int(n), C.c_float(1.0), C.c_float(mu), C.c_float(lam), _p(vec), _p(l), _p(F), _p(got))
-        want, lw = _oracle_stress(oracle, model % 10, F, lj, prm)       # 10 = stress_fcr_lean: the fixed-corotated stress as the binned P2G evaluates it
-        other, lo = _oracle_stress(oracle_fma, model % 10, F, lj, prm)
+        want, lw = _oracle_stress(oracle, 0 if model >= 10 else model, F, lj, prm)       # 10 = stress_fcr_lean: the fixed-corotated stress as the binned P2G evaluates it, 11 = with the converged-sweep skip
+        other, lo = _oracle_stress(oracle_fma, 0 if model >= 10 else model, F, lj, prm)
         # particles whose branch differs between the two reference builds sit on a branch boundary: not comparable
         stable = np.abs(lo - lw) <= 1e-5 * np.maximum(np.abs(lw), 1.0)
         assert stable.mean() > 0.98

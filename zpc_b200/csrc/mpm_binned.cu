@@ -37,6 +37,15 @@ constexpr int BIN_MAX = ZPCB200_BIN_MAX;
 #ifndef ZPC_P2G_NT
 #define ZPC_P2G_NT 256
 #endif
+#ifndef ZPC_P2G_MINB
+#define ZPC_P2G_MINB 4
+#endif
+#ifndef ZPC_P2G_EARLY   // 1: sweep variants >= 4 skip the Jacobi sweeps a whole warp has converged on (zpcm::stress_fcr_lean<true>)
+#define ZPC_P2G_EARLY 1
+#endif
+#ifndef ZPC_P2G_PIPE    // 1: sweep variants >= 4 compute the next chunk's records before the end-of-sweep barrier (measured: no gain, see below)
+#define ZPC_P2G_PIPE 0
+#endif
 constexpr int P2G_NT = ZPC_P2G_NT, P2G_NW = P2G_NT / 32;
 constexpr int CHUNK = P2G_NT;           // particles staged per pass (one record per thread)
 constexpr int NCOL6 = 36;               // (x,y) columns of home cells in [-1,4]^2: 16 nominal + 20 ring
@@ -78,15 +87,12 @@ struct P2GSmem {
   int ncells[2];                    // v4 sweep: non-empty cells of the current / next chunk
   unsigned char cells[2][NGRP + 7];
 };
-static_assert(sizeof(P2GSmem) <= 56 * 1024, "four CTAs per SM");
+static_assert(sizeof(P2GSmem) <= (227 * 1024) / ZPC_P2G_MINB - 1024, "ZPC_P2G_MINB CTAs per SM (227 KB, 1 KB reserved per CTA)");
 
 // sweep units in scheduling order: the 16 nominal columns first, then the 20 ring columns; c6 = (x+1)*6 + (y+1)
 __constant__ unsigned char c_unit_c6[NCOL6] = {7,  8,  9,  10, 13, 14, 15, 16, 19, 20, 21, 22, 25, 26, 27, 28,
                                               0,  1,  2,  3,  4,  5,  6,  11, 12, 17, 18, 23, 24, 29, 30, 31, 32, 33, 34, 35};
 
-#ifndef ZPC_P2G_MINB
-#define ZPC_P2G_MINB 4
-#endif
 // MODEL 0 = FixedCorotatedConfig, 1 = VonMisesFixedCorotatedConfig (yield_stress; P2G.hpp:89-90), 2 = DruckerPragerConfig,
 // 3 = NACCConfig (pp; the per-particle logJp lives in `scalar`, one float per particle in BIN order, read and written back by the
 // record phase like P2G.hpp:93,101), 4 = EquationOfStateConfig (pp.a = bulk, pp.b = viscosity; `scalar` = J, read only; the F
@@ -203,60 +209,73 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     if (l == 0) S.ncells[buf] = base;
   };
   if (VAR >= 4 && w == P2G_NW - 1 && n_fast > 0) build_cell_list(0, 0);
+  // One record per thread, computed into registers and stored to shared memory at the top of the chunk.  The stress and the affine
+  // coefficients need nothing from shared memory, so with ZPC_P2G_PIPE=1 the NEXT chunk's records are computed right after a warp runs
+  // out of sweep units, in the time it would otherwise wait at the end-of-sweep barrier (ncu, C3: 15 % of all warp samples sit at
+  // that barrier; 11 units for 8 warps).  Measured at C3 (benchmarks/r2_s2_call4.sh): 6.81 ms against 6.78 without — the other three
+  // CTAs of the SM already fill those slots, and carrying the record across the barrier costs 20 local stores; off by default.
+  float4 R[7];
+  auto compute_record = [&](int cb) {
+    const int pos = cb + tid;
+    if (pos < n_fast) {
+      const size_t s = pslot((size_t)p0 + gorder[pos]);
+      float F[9], K[9];
+      if constexpr (MODEL != 4) {
+#pragma unroll
+        for (int d = 0; d < 9; ++d) F[d] = pars[s + (ZPC_PB_F + d) * TS];
+      }
+      if constexpr (MODEL == 4) {
+        // stress from C and J (P2G.hpp:66-83); C is loaded again below for the affine part — the compiler merges the loads
+        const float J = scalar[(size_t)p0 + gorder[pos]];
+        float Cc[9];
+#pragma unroll
+        for (int d = 0; d < 9; ++d) Cc[d] = pars[s + (ZPC_PB_C + d) * TS];
+        zpcm::eos_contrib(Cc, J, volume, pp.a, pp.b, K);
+      } else if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, K);
+      else if constexpr (MODEL == 2 || MODEL == 3) {
+        float *lj = scalar + (size_t)p0 + gorder[pos];
+        float logJp = *lj;
+        if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, K);
+        else zpcm::stress_nacc(volume, mu, pp.a, pp.b, pp.c, pp.d, pp.flag != 0, logJp, F, K);
+        *lj = logJp;
+      } else zpcm::stress_fcr_lean<(VAR >= 4 && ZPC_P2G_EARLY != 0)>(volume * (-dt * D_inv), mu, lam, F, K);
+      if constexpr (MODEL != 0) {
+#pragma unroll
+        for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
+      }
+      float d0[3], loc[3], vel[3], C[9];
+      const float mass = pars[s + ZPC_PB_M * TS];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float X = zpcm::div_exact(pars[s + (ZPC_PB_X + d) * TS], dx, dx_inv);
+        const float lp = X - floorf(X - 0.5f);
+        d0[d] = lp;
+        loc[d] = lp * dx;
+        vel[d] = pars[s + (ZPC_PB_V + d) * TS];
+      }
+#pragma unroll
+      for (int d = 0; d < 9; ++d) C[d] = pars[s + (ZPC_PB_C + d) * TS];
+      // mv_d = W (A_d + sum_e B_de o_e), rhs_d = W (a_d + sum_e K_de o_e), o = stencil offset (0,1,2)^3
+      float A[3], a[3], B[9], Kd[9];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        A[d] = mass * (vel[d] - (C[d] * loc[0] + C[3 + d] * loc[1] + C[6 + d] * loc[2]));
+        a[d] = -(K[d] * loc[0] + K[3 + d] * loc[1] + K[6 + d] * loc[2]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { B[3 * d + e] = mass * C[d + 3 * e] * dx; Kd[3 * d + e] = K[d + 3 * e] * dx; }
+      }
+      zpcs::write_record<VAR>(R, d0, mass, A, a, B, Kd);
+    }
+  };
+  constexpr bool PIPE = VAR >= 4 && ZPC_P2G_PIPE != 0;
+  if (PIPE && n_fast > 0) compute_record(0);
   for (int cb = 0; cb < n_fast; cb += CHUNK) {
     const int buf = (cb / CHUNK) & 1;
-    {  // records
-      const int pos = cb + tid;
-      if (pos < n_fast) {
-        const size_t s = pslot((size_t)p0 + gorder[pos]);
-        float F[9], K[9];
-        if constexpr (MODEL != 4) {
+    if (!PIPE) compute_record(cb);
+    if (cb + tid < n_fast) {
+      float4 *dst = S.rec4 + zpcs::rec_at<VAR>(tid);
 #pragma unroll
-          for (int d = 0; d < 9; ++d) F[d] = pars[s + (ZPC_PB_F + d) * TS];
-        }
-        if constexpr (MODEL == 4) {
-          // stress from C and J (P2G.hpp:66-83); C is loaded again below for the affine part — the compiler merges the loads
-          const float J = scalar[(size_t)p0 + gorder[pos]];
-          float Cc[9];
-#pragma unroll
-          for (int d = 0; d < 9; ++d) Cc[d] = pars[s + (ZPC_PB_C + d) * TS];
-          zpcm::eos_contrib(Cc, J, volume, pp.a, pp.b, K);
-        } else if constexpr (MODEL == 1) zpcm::stress_vonmises(volume, mu, lam, yield_stress, F, K);
-        else if constexpr (MODEL == 2 || MODEL == 3) {
-          float *lj = scalar + (size_t)p0 + gorder[pos];
-          float logJp = *lj;
-          if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, K);
-          else zpcm::stress_nacc(volume, mu, pp.a, pp.b, pp.c, pp.d, pp.flag != 0, logJp, F, K);
-          *lj = logJp;
-        } else zpcm::stress_fcr_lean(volume * (-dt * D_inv), mu, lam, F, K);
-        if constexpr (MODEL != 0) {
-#pragma unroll
-          for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
-        }
-        float d0[3], loc[3], vel[3], C[9];
-        const float mass = pars[s + ZPC_PB_M * TS];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float X = zpcm::div_exact(pars[s + (ZPC_PB_X + d) * TS], dx, dx_inv);
-          const float lp = X - floorf(X - 0.5f);
-          d0[d] = lp;
-          loc[d] = lp * dx;
-          vel[d] = pars[s + (ZPC_PB_V + d) * TS];
-        }
-#pragma unroll
-        for (int d = 0; d < 9; ++d) C[d] = pars[s + (ZPC_PB_C + d) * TS];
-        // mv_d = W (A_d + sum_e B_de o_e), rhs_d = W (a_d + sum_e K_de o_e), o = stencil offset (0,1,2)^3
-        float4 *dst = S.rec4 + zpcs::rec_at<VAR>(tid);
-        float A[3], a[3], B[9], Kd[9];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          A[d] = mass * (vel[d] - (C[d] * loc[0] + C[3 + d] * loc[1] + C[6 + d] * loc[2]));
-          a[d] = -(K[d] * loc[0] + K[3 + d] * loc[1] + K[6 + d] * loc[2]);
-#pragma unroll
-          for (int e = 0; e < 3; ++e) { B[3 * d + e] = mass * C[d + 3 * e] * dx; Kd[3 * d + e] = K[d + 3 * e] * dx; }
-        }
-        zpcs::write_record<VAR>(dst, d0, mass, A, a, B, Kd);
-      }
+      for (int q = 0; q < 7; ++q) dst[q] = R[q];
     }
     __syncthreads();
     const int ce = min(cb + CHUNK, n_fast);
@@ -339,6 +358,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
         }
       }
     }
+    if (PIPE && cb + CHUNK < n_fast) compute_record(cb + CHUNK);   // registers only: overlaps the other warps' sweeps
     __syncthreads();
     if (tid == 0) S.next_unit = 0;  // ordered before the next sweep by the barrier after the next records phase
   }
@@ -445,7 +465,7 @@ __device__ __forceinline__ void particle_record(const float (&pd)[NCH], float *_
     if constexpr (MODEL == 2) zpcm::stress_sand(volume, mu, lam, pp.a, pp.b, pp.c, pp.flag != 0, logJp, F, K);
     else zpcm::stress_nacc(volume, mu, pp.a, pp.b, pp.c, pp.d, pp.flag != 0, logJp, F, K);
     if (live) *sc = logJp;
-  } else zpcm::stress_fcr_lean(volume * (-dt * D_inv), mu, lam, F, K);
+  } else zpcm::stress_fcr_lean<false>(volume * (-dt * D_inv), mu, lam, F, K);
   if constexpr (MODEL != 0) {
 #pragma unroll
     for (int d = 0; d < 9; ++d) K[d] = K[d] * -dt * D_inv;
@@ -721,11 +741,13 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
 
 // ----------------------------------------------------------------------------------------------------------------
 // One particle of the binned G2P: gather against the staged arena velocities sv (= G2PSmem::v), APIC C, advect pos.
+template <bool FAST_DIV = false>
 __device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int ky, int kz, const zpc_hashtable_view &tb,
                                                    const float *__restrict__ tiles, int nch, float dx, float dt, float D_inv,
-                                                   float (&pos)[3], float (&vel)[3], float (&C)[9], int *status = nullptr) {
+                                                   float (&pos)[3], float (&vel)[3], float (&C)[9], int *status = nullptr,
+                                                   float dx_inv = 0.f) {
   zpcm::Arena ar;
-  zpcm::arena_init(ar, dx, pos);
+  zpcm::arena_init<FAST_DIV>(ar, dx, pos, dx_inv);   // the staged kernel divides through 1/dx and two FMAs (same bits, no slow-path branch)
   const int ax0 = ar.corner[0] - 4 * kx, ay0 = ar.corner[1] - 4 * ky, az0 = ar.corner[2] - 4 * kz;
   float G[9];  // G[r + 3e] = sum W v_r o_e
   if ((unsigned)ax0 < 6u && (unsigned)ay0 < 6u && (unsigned)az0 < 6u) {
@@ -773,7 +795,15 @@ __device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int 
       G[r + 6] = ar.w[0][0] * pz[0][r] + ar.w[0][1] * pz[1][r] + ar.w[0][2] * pz[2][r];
     }
   } else {
-    zpcp::g2p_gather_particle(ar, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, nch, vel, G);
+    // the out-of-arena path is a call: it gets copies, so that the arena path keeps ar / vel / G in registers (passing them by
+    // reference put 27 local-memory stores per particle on the common path)
+    zpcm::Arena ar2 = ar;
+    float vel2[3], G2[9];
+    zpcp::g2p_gather_particle(ar2, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, nch, vel2, G2);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) vel[d] = vel2[d];
+#pragma unroll
+    for (int d = 0; d < 9; ++d) G[d] = G2[d];
   }
   // C[r + 3e] = D_inv * sum W v_r (o_e dx - local_e) = D_inv * (dx G_re - local_e v_r)
 #pragma unroll
@@ -1029,10 +1059,11 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
     if (mine) {
       const size_t s = pslot((size_t)gp);
       float vel[3], C[9], tmp[9];
-      g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C, status);
+      g2p_arena_particle<true>(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C, status, dx_inv);
       if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
-        const int cx = (int)floorf(pos[0] / dx - 0.5f) - 1 - 4 * kx, cy = (int)floorf(pos[1] / dx - 0.5f) - 1 - 4 * ky,
-                  cz = (int)floorf(pos[2] / dx - 0.5f) - 1 - 4 * kz;
+        const int cx = (int)floorf(zpcm::div_exact(pos[0], dx, dx_inv) - 0.5f) - 1 - 4 * kx,
+                  cy = (int)floorf(zpcm::div_exact(pos[1], dx, dx_inv) - 0.5f) - 1 - 4 * ky,
+                  cz = (int)floorf(zpcm::div_exact(pos[2], dx, dx_inv) - 0.5f) - 1 - 4 * kz;
         const int g = ((unsigned)(cx + 1) < 6u && (unsigned)(cy + 1) < 6u && (unsigned)(cz + 1) < 6u)
                           ? ((cx + 1) * 6 + (cy + 1)) * 6 + (cz + 1)
                           : GRP_FAR;
@@ -1239,7 +1270,9 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
 
 // Kernel variants (see zpcb200_set_tuning): defaults from the environment, once.
 struct Tuning {
-  int p2g_sweep;   // 4 = three cells x nine node columns per warp; 5 = the same on packed fp32 (FFMA2); 3 = one cell x 27 nodes
+  int p2g_sweep;   // 4 = three cells x nine node columns per warp (default: converged Jacobi sweeps skipped, next chunk's records computed
+                   // while the other warps finish their sweeps); 5 = the same on packed fp32 (FFMA2); 3 = one cell x 27 nodes, the
+                   // reference's four Jacobi sweeps always; 6 = plane sweep kernel (atomic-free private regions)
   int plane_prefetch;  // plane sweep: distance (in bins) of the L2 prefetch of a later CTA's particle lines, 0 = off (env ZPCB200_PLANE_PREFETCH)
   int g2p_staged;  // 0 = plain loads, 256-thread CTAs; 1 (= 64) | 64 | 128 | 256 = particle channels staged with TMA bulk copies, that many threads per CTA
 };
@@ -1247,7 +1280,7 @@ Tuning &tuning() {
   static Tuning t = [] {
     Tuning d = {4, 448, 1};
     if (const char *e = getenv("ZPCB200_PLANE_PREFETCH")) d.plane_prefetch = atoi(e);
-    if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = e[0] == '3' ? 3 : (e[0] == '5' ? 5 : (e[0] == '6' ? 6 : 4));
+    if (const char *e = getenv("ZPCB200_P2G_SWEEP")) d.p2g_sweep = (e[0] >= '3' && e[0] <= '6') ? e[0] - '0' : 4;
     if (const char *e = getenv("ZPCB200_G2P_STAGED")) d.g2p_staged = atoi(e);
     return d;
   }();
@@ -1282,7 +1315,9 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
     ZPC_CHECK_LAUNCH();
     return ZPCB200_OK;
   }
-  auto kern = variant == 3 ? p2g_binned_kernel<3, MODEL> : variant == 5 ? p2g_binned_kernel<5, MODEL> : p2g_binned_kernel<4, MODEL>;
+  auto kern = variant == 3   ? p2g_binned_kernel<3, MODEL>
+              : variant == 5 ? p2g_binned_kernel<5, MODEL>
+                             : p2g_binned_kernel<4, MODEL>;
   kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
       bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp, bins.status, halo);
@@ -1309,7 +1344,7 @@ static int g2p_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
 extern "C" {
 
 int zpcb200_set_tuning(int p2g_sweep, int g2p_staged) {
-  if ((p2g_sweep != 3 && p2g_sweep != 4 && p2g_sweep != 5 && p2g_sweep != 6 && p2g_sweep != -1) || (g2p_staged != -1 && g2p_staged != 0 && g2p_staged != 1 && g2p_staged != 64 && g2p_staged != 128 && g2p_staged != 256))
+  if (((p2g_sweep < 3 || p2g_sweep > 6) && p2g_sweep != -1) || (g2p_staged != -1 && g2p_staged != 0 && g2p_staged != 1 && g2p_staged != 64 && g2p_staged != 128 && g2p_staged != 256))
     return ZPCB200_E_BADARG;
   if (p2g_sweep != -1) tuning().p2g_sweep = p2g_sweep;
   if (g2p_staged != -1) tuning().g2p_staged = g2p_staged;
