@@ -47,12 +47,14 @@ typedef struct zpc_port {
 /* (cuda/execution/ExecutionPolicy.cuh: reduce :649-681, inclusive_scan :552-590,               */
 /*  exclusive_scan :601-632, radix_sort_pair :755-826, radix_sort :828-866).                     */
 /* <T> in {i32,u32,i64,f32,f64}; scans/reductions use the identities the reference's C ABI passes     */
-/* (py_interop/cuda/ExecutionPolicy.cpp:41-90): 0 for sum, numeric max for min, lowest for max.  */
+/* (py_interop/cuda/ExecutionPolicy.cpp:41-90): 0 for sum, 1 for prod (:48-54), numeric max for min, lowest for max. */
 /* `out` of a reduce is one element on the device.  Ranges are zpc_ports; n = last - first.      */
 /* ------------------------------------------------------------------------------------------ */
 #define ZPCB200_DECL_REDUCE_SCAN(S)                                                              \
   int zpcb200_reduce_sum_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_t n, \
                              zpc_stream_t stream);                                               \
+  int zpcb200_reduce_prod_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_t n, \
+                              zpc_stream_t stream);                                              \
   int zpcb200_reduce_min_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_t n, \
                              zpc_stream_t stream);                                               \
   int zpcb200_reduce_max_##S(void *temp, size_t *temp_bytes, zpc_port in, zpc_port out, size_t n, \
@@ -425,9 +427,11 @@ enum {
   ZPC_BINS_HOME_BLOCK_MISSING = 1,    /* bin / rebin: a particle's home block is not in the table (filed under block 0) */
   ZPC_BINS_BIN_CAPACITY = 2,          /* bin / rebin: more bins than binCapacity — numBins is set to 0, nothing will be transferred */
   ZPC_BINS_BLOCK_CAPACITY = 4,        /* bin / rebin: the table holds more blocks than binCapacity (blocks beyond it are dropped) */
-  ZPC_BINS_STENCIL_BLOCK_MISSING = 8  /* binned P2G / G2P: a block a particle's stencil reaches is absent from the partition: that
+  ZPC_BINS_STENCIL_BLOCK_MISSING = 8, /* binned P2G / G2P: a block a particle's stencil reaches is absent from the partition: that
                                          part of its mass / momentum is not transferred.  With partition = "with_rebin" this means a
                                          particle drifted by more than the extra ring since the last re-bin (re-bin more often) */
+  ZPC_BINS_TMA_TIMEOUT = 16           /* binned G2P: a TMA bulk copy did not complete within 2^20 timed-out waits (cannot happen with
+                                         consistent views); the kernel went on instead of trapping or hanging — results are invalid */
 };
 
 /* Sort AoS particles into bins (radix_sort_pair on the block rank + gather into AoSoA).  Requires a
@@ -544,6 +548,7 @@ void policy_set__b200(zpcb200_policy *, int device, zpc_stream_t stream, int syn
 int policy_last_error__b200(const zpcb200_policy *);
 #define ZPCB200_DECL_POLICY_PRIMS(T, CT)                                                          \
   void reduce_sum__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);   \
+  void reduce_prod__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);  \
   void reduce_min__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);   \
   void reduce_max__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last, zpc_port out);   \
   void exclusive_scan_sum__b200_##T##_1(zpcb200_policy *, zpc_port first, zpc_port last,          \

@@ -53,7 +53,7 @@ ZO_RADIX_IMPL(zo_radix_sort_i32, int32_t, uint32_t, 1, ZO_NO)
 ZO_RADIX_IMPL(zo_radix_sort_u64, uint64_t, uint64_t, 0, ZO_NO)
 
 /* scan / reduce: strictly left-to-right folds (ExecutionPolicy.hpp:245-274).  Identities as the
- * reference's C ABI passes them (py_interop/cuda/ExecutionPolicy.cpp:41-68): 0 for sum,
+ * reference's C ABI passes them (py_interop/cuda/ExecutionPolicy.cpp:41-68): 0 for sum, 1 for prod,
  * numeric max for min, numeric lowest for max. */
 #define ZO_SCAN_REDUCE_IMPL(S, T, TMAX, TLOW)                                  \
   void zo_exclusive_scan_sum_##S(const T *in, T *out, size_t n) {             \
@@ -68,6 +68,11 @@ ZO_RADIX_IMPL(zo_radix_sort_u64, uint64_t, uint64_t, 0, ZO_NO)
   void zo_reduce_sum_##S(const T *in, T *out, size_t n) {                     \
     T acc = 0;                                                                \
     for (size_t i = 0; i < n; ++i) acc = acc + in[i];                         \
+    *out = acc;                                                               \
+  }                                                                           \
+  void zo_reduce_prod_##S(const T *in, T *out, size_t n) {                    \
+    T acc = 1;                                                                \
+    for (size_t i = 0; i < n; ++i) acc = acc * in[i];                         \
     *out = acc;                                                               \
   }                                                                           \
   void zo_reduce_min_##S(const T *in, T *out, size_t n) {                     \

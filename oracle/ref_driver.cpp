@@ -353,6 +353,11 @@ ZPCREF_SORT_PAIR(u64, uint64_t)
     with_policy(nthreads,                                                                          \
                 [&](auto &pol, auto) { reduce(pol, in, e, out, (T)0, plus<T>{}); });          \
   }                                                                                                \
+  void zpcref_reduce_prod_##SUFFIX(int nthreads, const T *in, T *out, size_t n) {\
+    const T *e = in + n;\
+    with_policy(nthreads,                                                                          \
+                [&](auto &pol, auto) { reduce(pol, in, e, out, (T)1, multiplies<T>{}); });    \
+  }                                                                                                \
   void zpcref_reduce_min_##SUFFIX(int nthreads, const T *in, T *out, size_t n) {\
     const T *e = in + n;\
     with_policy(nthreads, [&](auto &pol, auto) {                                                   \

@@ -39,9 +39,35 @@ def test_reduce_int_exact(pol, oracle, kind, n):
     a = rand(kind, n, n + 1)
     d = dev(a)
     out = torch.zeros(1, dtype=tdt(kind), device="cuda")
-    for op in ("sum", "min", "max"):
+    for op in ("sum", "prod", "min", "max"):   # integer products wrap: associative, so the parallel fold is exact too
         pol.reduce(d, out, op)
         assert out.cpu().numpy()[0] == oracle.reduce(op, kind, a), (op, n)
+
+
+def test_reduce_prod_float_and_c_layer(pol, oracle):
+    """reduce_prod__b200_<T>_1 (py_interop/cuda/ExecutionPolicy.cpp:48-54: identity 1, zs::multiplies): floats near 1 so that the
+    product stays in range; the parallel fold re-associates, so it is held to n ulp-level steps of the sequential fold"""
+    import ctypes as C
+    from zpc_b200 import api
+    L = api.lib()
+    p = C.c_void_p(L.policy__b200())
+    L.policy_set__b200(p, 0, None, 1)
+    try:
+        for kind, npdt, tol in (("f32", np.float32, 2e-5), ("f64", np.float64, 1e-12)):
+            a = (1.0 + np.random.RandomState(9).uniform(-1e-3, 1e-3, 100003)).astype(npdt)
+            d = dev(a)
+            out = torch.zeros(1, dtype=tdt(kind), device="cuda")
+            pol.reduce(d, out, "prod")
+            want = oracle.reduce("prod", kind, a)
+            assert abs(out.item() / float(want) - 1.0) <= tol, (kind, out.item(), want)
+            out2 = torch.zeros_like(out)
+            getattr(L, "reduce_prod__b200_%s_1" % ("float" if kind == "f32" else "double"))(p, api.port(d), api.port(d, a.size), api.port(out2))
+            assert out2.item() == out.item()
+        e = torch.zeros(1, dtype=torch.int32, device="cuda")
+        L.reduce_prod__b200_int_1(p, api.port(e), api.port(e), api.port(e))      # empty range -> the identity
+        assert e.item() == 1
+    finally:
+        L.del_policy__b200(p)
 
 
 @pytest.mark.parametrize("n", [1, 2, 7, 16, 128, 1024, 2000000])

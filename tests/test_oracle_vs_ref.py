@@ -74,7 +74,7 @@ def test_primitives_vs_reference(oracle, ref, nthreads):
         if n:
             assert np.array_equal(oracle.scan("exclusive", "i32", x), ref.scan("exclusive", "i32", x, nthreads))
             assert np.array_equal(oracle.scan("inclusive", "i32", x), ref.scan("inclusive", "i32", x, nthreads))
-        for op in ("sum", "min", "max"):
+        for op in ("sum", "prod", "min", "max"):   # prod wraps mod 2^32 on both sides (py_interop/cuda/ExecutionPolicy.cpp:48-54)
             assert oracle.reduce(op, "i32", x) == ref.reduce(op, "i32", x, nthreads)
 
 
@@ -98,7 +98,7 @@ def test_f64_scan_reduce_match_reference(oracle, ref):
     for nthreads in (0,):
         assert np.array_equal(ref.scan("exclusive", "f64", a, nthreads), oracle.scan("exclusive", "f64", a))
         assert np.array_equal(ref.scan("inclusive", "f64", a, nthreads), oracle.scan("inclusive", "f64", a))
-        for op in ("sum", "min", "max"):
+        for op in ("sum", "prod", "min", "max"):
             assert ref.reduce(op, "f64", a, nthreads) == oracle.reduce(op, "f64", a)
 
 

@@ -112,7 +112,7 @@ class zpc_halo_view(C.Structure):
 
 
 # bits of zpc_bins_view.status (include/zpcb200.h)
-BINS_HOME_BLOCK_MISSING, BINS_BIN_CAPACITY, BINS_BLOCK_CAPACITY, BINS_STENCIL_BLOCK_MISSING = 1, 2, 4, 8
+BINS_HOME_BLOCK_MISSING, BINS_BIN_CAPACITY, BINS_BLOCK_CAPACITY, BINS_STENCIL_BLOCK_MISSING, BINS_TMA_TIMEOUT = 1, 2, 4, 8, 16
 
 
 _lib = None

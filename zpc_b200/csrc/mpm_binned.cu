@@ -953,14 +953,19 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+// A transaction that never completes (it cannot, short of a wrong byte count) must neither hang the GPU nor kill the context: after
+// 2^20 timed-out try_waits the thread raises ZPC_BINS_TMA_TIMEOUT in the bins' status word and goes on with whatever the stage holds.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity, int *status) {
   unsigned done = 0, spins = 0;
   while (!done) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
                  : "=r"(done)
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
-    if (!done && ++spins > (1u << 20)) __trap();  // never hang the GPU on a lost transaction
+    if (!done && ++spins > (1u << 20)) {
+      if (status) atomicOr(status, ZPC_BINS_TMA_TIMEOUT);
+      break;
+    }
   }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
@@ -1032,14 +1037,14 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
   for (int b = 0; b < 8; ++b)  // blocks missing from the partition read as zero velocity
     if (S.tile_id[b] < 0)
       for (int i = tid; i < 192; i += NT) (&S.v[b][0][0])[i] = 0.f;
-  mbar_wait(&S.bar_grid, 0);
+  mbar_wait(&S.bar_grid, 0, status);
   __syncthreads();
   const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
   const float *sv = &S.v[0][0][0];
   const int tl = tid >> 5, ln = tid & 31;
   for (int c = 0; c < nstages; ++c) {
     const int b = c & 1;
-    mbar_wait(&S.bar_stage[b], (unsigned)(c >> 1) & 1u);
+    mbar_wait(&S.bar_stage[b], (unsigned)(c >> 1) & 1u, status);
     const int gp = ((t0 + c * G2P_ST + tl) << 5) + ln;  // global particle slot of this thread
     const int i = gp - p0;                              // slot relative to the bin
     const bool mine = i >= 0 && i < np;

@@ -50,6 +50,9 @@ int policy_last_error__b200(const zpcb200_policy *p) { return p ? p->last_error 
   void reduce_sum__b200_##T##_1(zpcb200_policy *p, zpc_port first, zpc_port last, zpc_port out) {                     \
     run_with_scratch(p, [&](void *t, size_t *b) { return zpcb200_reduce_sum_##S(t, b, first, out, port_distance(first, last), p->stream); }); \
   }                                                                                                                   \
+  void reduce_prod__b200_##T##_1(zpcb200_policy *p, zpc_port first, zpc_port last, zpc_port out) {                    \
+    run_with_scratch(p, [&](void *t, size_t *b) { return zpcb200_reduce_prod_##S(t, b, first, out, port_distance(first, last), p->stream); }); \
+  }                                                                                                                   \
   void reduce_min__b200_##T##_1(zpcb200_policy *p, zpc_port first, zpc_port last, zpc_port out) {                     \
     run_with_scratch(p, [&](void *t, size_t *b) { return zpcb200_reduce_min_##S(t, b, first, out, port_distance(first, last), p->stream); }); \
   }                                                                                                                   \

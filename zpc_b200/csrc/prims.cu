@@ -25,6 +25,7 @@ namespace {
 // operators
 // ------------------------------------------------------------------------------------------------
 struct OpSum { template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return a + b; } };
+struct OpProd { template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return a * b; } };
 struct OpMin { template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return b < a ? b : a; } };
 struct OpMax { template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return b > a ? b : a; } };
 
@@ -801,6 +802,10 @@ extern "C" {
   int zpcb200_reduce_sum_##S(void *temp, size_t *tb, zpc_port in, zpc_port out, size_t n, zpc_stream_t st) {     \
     if (!tb) return ZPCB200_E_BADARG;                                                                           \
     return reduce_impl<T, OpSum>(temp, tb, in, out, n, (T)0, (cudaStream_t)st);                                 \
+  }                                                                                                             \
+  int zpcb200_reduce_prod_##S(void *temp, size_t *tb, zpc_port in, zpc_port out, size_t n, zpc_stream_t st) {    \
+    if (!tb) return ZPCB200_E_BADARG;                                                                           \
+    return reduce_impl<T, OpProd>(temp, tb, in, out, n, (T)1, (cudaStream_t)st);                                \
   }                                                                                                             \
   int zpcb200_reduce_min_##S(void *temp, size_t *tb, zpc_port in, zpc_port out, size_t n, zpc_stream_t st) {     \
     if (!tb) return ZPCB200_E_BADARG;                                                                           \
