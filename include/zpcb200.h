@@ -487,6 +487,20 @@ int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_gr
 int zpcb200_set_tuning(int p2g_sweep, int g2p_staged);
 int zpcb200_get_tuning(int *p2g_sweep_host, int *g2p_staged_host);
 
+/* Block-binned fast path on the SparseGrid (round 2).  The bins of zpcb200_bin_particles hold the particles of one 4^3-cell region;
+ * on side-8 blocks that region is one OCTANT of a block, so the same bins, cell-order cache and kernels serve both grids: the
+ * arena's eight [7][64] tiles are the octants {b, b+1}^3, read with 128-bit loads and added back with 128-bit vector reductions
+ * (an octant row of four z-cells is 16 contiguous bytes of the [numChannels][512] tile; Grids<f32,3,4> tiles are contiguous and
+ * go through TMA).  bins.binCapacity bounds 8 x the number of active blocks.  sg.numChannels >= 7 (P2G) / >= 4 (G2P); channel
+ * layout {m, v(3), rhs(3)} like the entries above.  order_out as in zpcb200_bin_particles / _rebin_particles_ordered. */
+int zpcb200_sg_bin_particles(void *temp, size_t *temp_bytes, zpc_particles_view pars, zpc_sparsegrid_view sg, zpc_bins_view bins,
+                             int *order_out, zpc_stream_t stream);
+int zpcb200_sg_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src, zpc_sparsegrid_view sg, zpc_bins_view dst,
+                               int *order_out, zpc_stream_t stream);
+int zpcb200_sg_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_fixed_corotated model,
+                                   zpc_stream_t stream);
+int zpcb200_sg_g2p_apic_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream);
+
 /* ---- multi-GPU one-ring halo, fused (SURVEY §8(e), §2.1 last paragraph; no reference counterpart) --------------------------
  * Every rank owns a receive buffer that its peers can address (peer-mapped over NVLink: torch symmetric memory, cudaIpc or
  * cuMem exports — the library only sees addresses): [2 halves][world senders][seg tiles][7 x 64 floats], all zero outside the

@@ -127,6 +127,87 @@ def test_sparsegrid_substep_matches_oracle_node_for_node(oracle, case, mode):
     check_particles(pars.to_host(), Po, dx, "sg g2p")
 
 
+@pytest.mark.parametrize("case", list(CASES))
+def test_sparsegrid_binned_fast_path_matches_oracle(oracle, case):
+    """block-binned fast path on side-8 blocks (bins = octants): bin -> P2G (smem arena, 128-bit vector reductions) -> grid update ->
+    G2P (TMA-staged particles, 128-bit arena loads), node for node against the oracle; then a second substep on the cell-order cache
+    and a re-bin + third substep, particle for particle against the any-order SparseGrid kernels fed with the same state"""
+    from zpc_b200 import api
+    P = _make(case)
+    n, dx = P["x"].shape[0], P["dx"]
+    pars, sg = _build(P)
+    t = _host_table(sg)
+    nb = t["nblocks"]
+    cap = 8 * nb + 64
+    bins, bins2 = api.ParticleBins(n, cap), api.ParticleBins(n, cap)
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    api.sg_bin_particles(pars, sg, bins, order)
+    torch.cuda.synchronize()
+    assert int(bins.status.item()) == 0
+    perm = order.cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    nbins = bins.num_bins.item()
+    bs = bins.bin_start[: nbins + 1].cpu().numpy()
+    assert bs[0] == 0 and bs[-1] == n and (np.diff(bs) > 0).all() and (np.diff(bs) <= api.BIN_MAX).all()
+    # every particle sits in the bin of its home octant: home cell = floor(x/dx + 0.5) - 2, octant key = home cell >> 2
+    bk = bins.bin_key[:nbins].cpu().numpy()
+    home = (np.floor(P["x"][perm].astype(np.float32) * np.float32(1.0 / dx) + np.float32(0.5)).astype(np.int64) - 2) >> 2
+    which = np.searchsorted(bs, np.arange(n), side="right") - 1
+    assert np.array_equal(bk[which], home)
+    model = api.model_fcr(P["volume"], E, NU)
+    api.sg_clean(sg)
+    api.sg_p2g_transfer(bins, sg, synth.DT, model)
+    g1 = sg.grid[:nb].cpu().numpy()
+    tab = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    Po = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in P.items()}
+    o1 = oracle.p2g(Po, tab, dx, synth.DT, E, NU, P["volume"])
+    code_o, val_o = _nodes(tab["active_keys"] * 4, o1, 4)
+    code_s, val_s = _nodes(t["active_keys"], g1, 8)
+    pos = np.searchsorted(code_s, code_o)
+    assert (pos < code_s.shape[0]).all() and np.array_equal(code_s[pos], code_o)
+    check_channels(val_s[pos], val_o, 1, "sg binned p2g", GRID_RTOL, strict_frac=0.99)
+    rest = np.ones(code_s.shape[0], bool)
+    rest[pos] = False
+    assert not val_s[rest].any()
+    assert abs(g1[:, 0].sum(dtype=np.float64) / P["m"].sum(dtype=np.float64) - 1) < 1e-5
+    mx = torch.zeros(1, device="cuda")
+    api.sg_compute_grid_velocity(sg, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    api.sg_g2p_transfer(bins, sg, synth.DT)
+    o2 = o1.copy()
+    oracle.grid_update(o2, synth.DT, (0.0, synth.GRAVITY, 0.0), 1)
+    oracle.g2p(Po, tab, o2, dx, synth.DT)
+    check_particles({k: bins.attr(k).cpu().numpy() for k in "xvCF"}, {k: Po[k][perm] for k in "xvCF"}, dx, "sg binned g2p")
+    assert int(bins.status.item()) == 0
+
+    def aos_step(state):
+        """one substep of the any-order SparseGrid kernels on a copy of `state` (dict of arrays in bin order)"""
+        Q = dict(P); Q.update(state)
+        pa = api.Particles(Q)
+        api.sg_partition_for_particles(api.vec3_port(pa.x), n, sg)
+        api.sg_clean(sg); api.sg_p2g_transfer(pa, sg, synth.DT, model)
+        api.sg_compute_grid_velocity(sg, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+        api.sg_g2p_transfer(pa, sg, synth.DT)
+        return pa.to_host()
+
+    cur = bins
+    for step, rebin in ((2, False), (3, True)):
+        state = {k: cur.attr(k).cpu().numpy() for k in "xvCF"}
+        state["m"] = cur.attr("m").cpu().numpy().reshape(-1)
+        want = aos_step(state)                                   # also rebuilds the partition on the current positions
+        if rebin:
+            o2_ = torch.empty(n, dtype=torch.int32, device="cuda")
+            other = bins2 if cur is bins else bins
+            api.sg_rebin_particles(cur, sg, other, order_out=o2_)
+            cur = other
+            want = {k: want[k][o2_.cpu().numpy()] for k in want}
+        api.sg_clean(sg); api.sg_p2g_transfer(cur, sg, synth.DT, model)
+        api.sg_compute_grid_velocity(sg, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+        api.sg_g2p_transfer(cur, sg, synth.DT)
+        torch.cuda.synchronize()
+        assert int(cur.status.item()) == 0, (step, int(cur.status.item()))
+        check_particles({k: cur.attr(k).cpu().numpy() for k in "xvCF"}, {k: want[k] for k in "xvCF"}, dx, "sg binned substep %d" % step, rtol=3e-5)
+
+
 def test_sparsegrid_accessors_match_oracle(oracle):
     from zpc_b200 import api
     P = _make("cube8_shuffled")

@@ -430,7 +430,23 @@ def sg_clean(sg, stream=None):
     _check(lib().zpcb200_sg_clean(sg.view(), _stream_ptr(stream)), "sg_clean")
 
 
+def sg_bin_particles(pars, sg, bins, order_out=None, stream=None):
+    """block-binned fast path on the SparseGrid: bins = octants (4^3 cells) of the side-8 blocks"""
+    _two_phase(lib().zpcb200_sg_bin_particles, (pars.view(), sg.view(), bins.view(),
+                                                C.c_void_p(order_out.data_ptr() if order_out is not None else None)), (), stream)
+
+
+def sg_rebin_particles(src, sg, dst, stream=None, order_out=None):
+    _two_phase(lib().zpcb200_sg_rebin_particles, (src.view(), sg.view(), dst.view(),
+                                                  C.c_void_p(order_out.data_ptr() if order_out is not None else None)), (), stream)
+
+
 def sg_p2g_transfer(pars, sg, dt, model, stream=None):
+    if isinstance(pars, ParticleBins):
+        if not isinstance(model, zpc_fixed_corotated):
+            raise ZpcError("the binned SparseGrid P2G serves the fixed-corotated model; use the any-order entry for the others")
+        _check(lib().zpcb200_sg_p2g_apic_fcr_binned(pars.view(), sg.view(), C.c_float(dt), model, _stream_ptr(stream)), "sg_p2g(binned)")
+        return
     if isinstance(model, zpc_fixed_corotated):
         _check(lib().zpcb200_sg_p2g_apic_fcr(pars.view(), sg.view(), C.c_float(dt), model, _stream_ptr(stream)), "sg_p2g")
         return
@@ -446,6 +462,9 @@ def sg_compute_grid_velocity(sg, dt, extf, mode, max_vel_sqr, stream=None):
 
 
 def sg_g2p_transfer(pars, sg, dt, stream=None, model=None):
+    if isinstance(pars, ParticleBins):
+        _check(lib().zpcb200_sg_g2p_apic_binned(pars.view(), sg.view(), C.c_float(dt), _stream_ptr(stream)), "sg_g2p(binned)")
+        return
     if isinstance(model, zpc_equation_of_state):
         _check(lib().zpcb200_sg_g2p_apic_eos(pars.view(), sg.view(), C.c_float(dt), _stream_ptr(stream)), "sg_g2p(eos)")
         return

@@ -56,6 +56,42 @@ constexpr int REC_F = 28;               // floats per particle record
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ size_t pslot(size_t i) { return ((i >> 5) * NCH) * TS + (i & 31); }  // channel 0 of particle i
 
+// ---- grid adaptors of the binned kernels --------------------------------------------------------------------------------------
+// The binned kernels think in VIRTUAL 4^3 blocks: a bin is the particles whose home cell lies in one, the arena is the 2x2x2 virtual
+// blocks {b, b+1}^3 staged as eight [7][64] tiles.  BinGridLegacy: a virtual block IS a block of Grids<f32,3,4> (HashTable keys =
+// block coordinates, tile = 1 792 contiguous bytes: TMA bulk copies / reductions).  BinGridSparse (round 2, SURVEY §8 a12 / (f) rank
+// 3): a virtual block is one octant of a side-8 block of SparseGrid<3,f32,8> (bht keys = block origins in cells, tile = [nch][512],
+// cell offset (x*8+y)*8+z, geometry/SparseGrid.hpp:275-309); id = (block number << 3) | octant.  An octant's row of four z-cells is 16
+// contiguous bytes, so the arena moves with 128-bit loads and 128-bit vector reductions (red.global.add.v4.f32) instead of TMA.
+struct BinGridLegacy {
+  static constexpr bool SPARSE = false;
+  zpc_hashtable_view tb;
+  __device__ __forceinline__ int query(int vx, int vy, int vz) const { return zpcm::table_query(vx, vy, vz, tb.tableSize, tb.keys, tb.indices); }
+  __device__ __forceinline__ int count() const { return *tb.cnt; }
+  __device__ __forceinline__ void key_of(int id, int &kx, int &ky, int &kz) const {
+    kx = tb.activeKeys[3 * (size_t)id]; ky = tb.activeKeys[3 * (size_t)id + 1]; kz = tb.activeKeys[3 * (size_t)id + 2];
+  }
+  __device__ __forceinline__ zpcp::LegacyGrid accessor(int *status) const { return zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}; }
+};
+struct BinGridSparse {
+  static constexpr bool SPARSE = true;
+  zpc_bht_view tb;
+  __device__ __forceinline__ int query(int vx, int vy, int vz) const {
+    const int bno = zpcm::bht_query((vx >> 1) << 3, (vy >> 1) << 3, (vz >> 1) << 3, tb);   // arithmetic shifts: floor for negative coordinates
+    return bno < 0 ? -1 : (bno << 3) | ((vx & 1) << 2) | ((vy & 1) << 1) | (vz & 1);
+  }
+  __device__ __forceinline__ int count() const { return *tb.cnt * 8; }
+  __device__ __forceinline__ void key_of(int id, int &kx, int &ky, int &kz) const {
+    const size_t b = (size_t)(id >> 3);
+    kx = (tb.activeKeys[3 * b] >> 2) + ((id >> 2) & 1); ky = (tb.activeKeys[3 * b + 1] >> 2) + ((id >> 1) & 1); kz = (tb.activeKeys[3 * b + 2] >> 2) + (id & 1);
+  }
+  __device__ __forceinline__ zpcp::SparseGrid8 accessor(int *status) const { return zpcp::SparseGrid8{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}; }
+  // float offset of row (x, y) (four z-cells) of channel ch of octant id in a [nch][512] tile array
+  __device__ __forceinline__ static size_t row_offset(int id, int nch, int ch, int x, int y) {
+    return ((size_t)(id >> 3) * nch + ch) * 512 + ((((id >> 2) & 1) * 4 + x) * 8 + (((id >> 1) & 1) * 4 + y)) * 8 + (id & 1) * 4;
+  }
+};
+
 
 // fused halo send (include/zpcb200.h: zpc_halo_view): the arena tile in shared memory at `tile_smem` was just added to grid block `id`;
 // if other ranks hold that block too, the same 1 792 bytes are reduce-added into its slot of their receive buffers (peer-mapped)
@@ -98,13 +134,14 @@ __constant__ unsigned char c_unit_c6[NCOL6] = {7,  8,  9,  10, 13, 14, 15, 16, 1
 // record phase like P2G.hpp:93,101), 4 = EquationOfStateConfig (pp.a = bulk, pp.b = viscosity; `scalar` = J, read only; the F
 // channels of the bins are not touched, P2G.hpp:66-87) — the model only enters
 // the records phase (and the stray path), the sweep and the write-back are the same
-template <int VAR, int MODEL = 0>
+template <int VAR, int MODEL = 0, class BG = BinGridLegacy>
 __global__ void __launch_bounds__(P2G_NT, ZPC_P2G_MINB)
 p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                   const int *__restrict__ numBins, const unsigned short *__restrict__ cellOrder,
-                  const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, zpc_hashtable_view tb,
+                  const unsigned short *__restrict__ cellStart, const int *__restrict__ cellOrderValid, BG bg,
                   float *__restrict__ tiles, float dx, float dt, float volume, float mu, float lam, int prefetch,
-                  float yield_stress, float *__restrict__ scalar, zpcm::PlasticPrm pp, int *__restrict__ status, zpc_halo_view halo) {
+                  float yield_stress, float *__restrict__ scalar, zpcm::PlasticPrm pp, int *__restrict__ status, zpc_halo_view halo,
+                  int nch = 7) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   P2GSmem &S = *reinterpret_cast<P2GSmem *>(smem_raw);
   const int bin = blockIdx.x;
@@ -125,7 +162,7 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
   }
 
   // ---- (0) arena blocks, zero the accumulation tiles ---------------------------------------------------
-  if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
+  if (tid < 8) S.tile_id[tid] = bg.query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1));
   {
     float4 *z = reinterpret_cast<float4 *>(S.out);
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -363,13 +400,31 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     if (tid == 0) S.next_unit = 0;  // ordered before the next sweep by the barrier after the next records phase
   }
 
-  // ---- (c) add the eight arena tiles to the grid: TMA bulk reductions --------------------------------------------
+  // ---- (c) add the eight arena tiles to the grid ------------------------------------------------------------------
+  if constexpr (BG::SPARSE) {
+    // SparseGrid: 8 tiles x 7 channels x 16 (x,y) rows of four z-cells, one 128-bit vector reduction each; rows nothing was added to are skipped
+    for (int q = tid; q < 8 * 112; q += P2G_NT) {
+      const int t = q / 112, r = q - 112 * t, ch = r >> 4, row = r & 15;
+      const int id = S.tile_id[t];
+      const float4 v = *reinterpret_cast<const float4 *>(S.out + t * 448 + ch * 64 + row * 4);
+      if (id >= 0 && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)) {
+        float *g = tiles + BG::row_offset(id, nch, ch, row >> 2, row & 3);
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+      }
+    }
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
   __syncthreads();
   bool remote = false;
   if (tid < 8) {
     const int id = S.tile_id[tid];
-    if (id >= 0) {
+    if (BG::SPARSE) {
+      if (id < 0 && status) {
+        bool any = false;
+        for (int c = 0; c < 64; ++c) any |= S.out[tid * 448 + c] != 0.f;
+        if (any) atomicOr(status, ZPC_BINS_STENCIL_BLOCK_MISSING);
+      }
+    } else if (id >= 0) {
       float *g = tiles + (size_t)id * 448;
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
                    "r"(smem_u32(S.out + tid * 448)), "r"(1792)
@@ -392,9 +447,9 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
     for (int d = 0; d < 3; ++d) { pos[d] = pars[s + (ZPC_PB_X + d) * TS]; vel[d] = pars[s + (ZPC_PB_V + d) * TS]; }
 #pragma unroll
     for (int d = 0; d < 9; ++d) { C[d] = pars[s + (ZPC_PB_C + d) * TS]; F[d] = pars[s + (ZPC_PB_F + d) * TS]; }
-    if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, mu, lam, yield_stress);
+    if constexpr (MODEL == 1) zpcp::p2g_scatter_particle_vm(pos, vel, mass, C, F, bg.accessor(status), tiles, nch, dx, dt, volume, mu, lam, yield_stress);
     else if constexpr (MODEL == 4) {
-      zpcp::p2g_scatter_particle_eos(pos, vel, mass, C, scalar[(size_t)p0 + gorder[t]], zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, pp.a, pp.b);
+      zpcp::p2g_scatter_particle_eos(pos, vel, mass, C, scalar[(size_t)p0 + gorder[t]], bg.accessor(status), tiles, nch, dx, dt, volume, pp.a, pp.b);
     } else if constexpr (MODEL >= 2) {
       float *lj = scalar + (size_t)p0 + gorder[t];
       float logJp = *lj, contrib[9];
@@ -403,8 +458,8 @@ p2g_binned_kernel(const float *__restrict__ pars, const int *__restrict__ binSta
       *lj = logJp;
 #pragma unroll
       for (int d = 0; d < 9; ++d) contrib[d] = contrib[d] * -dt * D_inv;
-      zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx);
-    } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, 7, dx, dt, volume, mu, lam);
+      zpcp::p2g_scatter_core(pos, vel, mass, C, contrib, bg.accessor(status), tiles, nch, dx);
+    } else zpcp::p2g_scatter_particle(pos, vel, mass, C, F, bg.accessor(status), tiles, nch, dx, dt, volume, mu, lam);
   }
   if (tid < 8) {
     // smem must outlive the bulk reads; a tile that also went to a peer waits for the writes themselves, so that the kernel's
@@ -741,8 +796,8 @@ p2g_plane_kernel(const float *__restrict__ pars, const int *__restrict__ binStar
 
 // ----------------------------------------------------------------------------------------------------------------
 // One particle of the binned G2P: gather against the staged arena velocities sv (= G2PSmem::v), APIC C, advect pos.
-template <bool FAST_DIV = false>
-__device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int ky, int kz, const zpc_hashtable_view &tb,
+template <bool FAST_DIV = false, class BG = BinGridLegacy>
+__device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int ky, int kz, const BG &bg,
                                                    const float *__restrict__ tiles, int nch, float dx, float dt, float D_inv,
                                                    float (&pos)[3], float (&vel)[3], float (&C)[9], int *status = nullptr,
                                                    float dx_inv = 0.f) {
@@ -799,7 +854,7 @@ __device__ __forceinline__ void g2p_arena_particle(const float *sv, int kx, int 
     // reference put 27 local-memory stores per particle on the common path)
     zpcm::Arena ar2 = ar;
     float vel2[3], G2[9];
-    zpcp::g2p_gather_particle(ar2, zpcp::LegacyGrid{tb, status, ZPC_BINS_STENCIL_BLOCK_MISSING}, tiles, nch, vel2, G2);
+    zpcp::g2p_gather_particle(ar2, bg.accessor(status), tiles, nch, vel2, G2);
 #pragma unroll
     for (int d = 0; d < 3; ++d) vel[d] = vel2[d];
 #pragma unroll
@@ -888,7 +943,7 @@ g2p_binned_kernel(float *__restrict__ pars, const int *__restrict__ binStart, co
       for (int d = 0; d < 9; ++d) Fo[d] = pars[s + (ZPC_PB_F + d) * TS];  // issued early: consumed after the contraction
     }
     float vel[3], C[9], tmp[9];
-    g2p_arena_particle(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C, status);
+    g2p_arena_particle(sv, kx, ky, kz, BinGridLegacy{tb}, tiles, nch, dx, dt, D_inv, pos, vel, C, status);
     if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
       const int cx = (int)floorf(pos[0] / dx - 0.5f) - 1 - 4 * kx, cy = (int)floorf(pos[1] / dx - 0.5f) - 1 - 4 * ky,
                 cz = (int)floorf(pos[2] / dx - 0.5f) - 1 - 4 * kz;
@@ -988,11 +1043,11 @@ static_assert(sizeof(G2PStagedSmem<256>) <= 48 * 1024, "static shared memory");
 
 // NT threads per CTA: small CTAs interleave their prologue / wait / store phases better — measured at C3:
 // 64 threads (15 CTAs/SM) 2.18 ms, 128 (8/SM) 2.30 ms, 256 (4/SM) 2.98 ms.
-template <int NT, bool EOS = false>
+template <int NT, bool EOS = false, class BG = BinGridLegacy>
 __global__ void __launch_bounds__(NT, 1024 / NT)
 g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binStart, const int *__restrict__ binKey,
                          const int *__restrict__ numBins, unsigned short *__restrict__ cellOrder,
-                         unsigned short *__restrict__ cellStart, zpc_hashtable_view tb, const float *__restrict__ tiles, int nch,
+                         unsigned short *__restrict__ cellStart, BG bg, const float *__restrict__ tiles, int nch,
                          float dx, float dt, float *__restrict__ scalar, int *__restrict__ status) {
   constexpr int G2P_ST = NT / 32;
   __shared__ __align__(128) G2PStagedSmem<NT> S;
@@ -1024,20 +1079,31 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
     if (nstages > 1) issue_stage(1);
   }
   const int kx = binKey[3 * bin], ky = binKey[3 * bin + 1], kz = binKey[3 * bin + 2];
-  if (tid < 8) S.tile_id[tid] = zpcm::table_query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1), tb.tableSize, tb.keys, tb.indices);
+  if (tid < 8) S.tile_id[tid] = bg.query(kx + (tid >> 2), ky + ((tid >> 1) & 1), kz + (tid & 1));
   for (int i = tid; i < NGRP + 3; i += NT) S.cnt[i] = 0;
   __syncthreads();
-  if (tid == 0) {
-    unsigned bytes = 0;
-    for (int b = 0; b < 8; ++b) bytes += S.tile_id[b] >= 0 ? 768u : 0u;
-    mbar_expect_tx(&S.bar_grid, bytes);
-    for (int b = 0; b < 8; ++b)
-      if (S.tile_id[b] >= 0) bulk_g2s(&S.v[b][0][0], tiles + ((size_t)S.tile_id[b] * nch + 1) * 64, 768, &S.bar_grid);
+  if constexpr (BG::SPARSE) {
+    // SparseGrid: the three velocity channels of the eight octants, 8 x 3 x 16 rows of four z-cells, one 128-bit load each
+    for (int q = tid; q < 8 * 48; q += NT) {
+      const int b = q / 48, r = q - 48 * b, c = r >> 4, row = r & 15;
+      const int id = S.tile_id[b];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);   // blocks missing from the partition read as zero velocity
+      if (id >= 0) v = *reinterpret_cast<const float4 *>(tiles + BG::row_offset(id, nch, 1 + c, row >> 2, row & 3));
+      *reinterpret_cast<float4 *>(&S.v[b][c][row * 4]) = v;
+    }
+  } else {
+    if (tid == 0) {
+      unsigned bytes = 0;
+      for (int b = 0; b < 8; ++b) bytes += S.tile_id[b] >= 0 ? 768u : 0u;
+      mbar_expect_tx(&S.bar_grid, bytes);
+      for (int b = 0; b < 8; ++b)
+        if (S.tile_id[b] >= 0) bulk_g2s(&S.v[b][0][0], tiles + ((size_t)S.tile_id[b] * nch + 1) * 64, 768, &S.bar_grid);
+    }
+    for (int b = 0; b < 8; ++b)  // blocks missing from the partition read as zero velocity
+      if (S.tile_id[b] < 0)
+        for (int i = tid; i < 192; i += NT) (&S.v[b][0][0])[i] = 0.f;
+    mbar_wait(&S.bar_grid, 0, status);
   }
-  for (int b = 0; b < 8; ++b)  // blocks missing from the partition read as zero velocity
-    if (S.tile_id[b] < 0)
-      for (int i = tid; i < 192; i += NT) (&S.v[b][0][0])[i] = 0.f;
-  mbar_wait(&S.bar_grid, 0, status);
   __syncthreads();
   const float dx_inv = 1.0f / dx, D_inv = 4.f * dx_inv * dx_inv;
   const float *sv = &S.v[0][0][0];
@@ -1064,7 +1130,7 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
     if (mine) {
       const size_t s = pslot((size_t)gp);
       float vel[3], C[9], tmp[9];
-      g2p_arena_particle<true>(sv, kx, ky, kz, tb, tiles, nch, dx, dt, D_inv, pos, vel, C, status, dx_inv);
+      g2p_arena_particle<true>(sv, kx, ky, kz, bg, tiles, nch, dx, dt, D_inv, pos, vel, C, status, dx_inv);
       if (cellOrder) {  // group of the NEW home cell, exactly as the binned P2G computes it from the stored position
         const int cx = (int)floorf(zpcm::div_exact(pos[0], dx, dx_inv) - 0.5f) - 1 - 4 * kx,
                   cy = (int)floorf(zpcm::div_exact(pos[1], dx, dx_inv) - 0.5f) - 1 - 4 * ky,
@@ -1122,8 +1188,8 @@ g2p_binned_staged_kernel(float *__restrict__ pars, const int *__restrict__ binSt
 // binning
 // ----------------------------------------------------------------------------------------------------------------
 // key = (block rank << 6) | cell id of the home cell ; val = particle index
-template <bool AOSOA>
-__global__ void bin_keys_kernel(const float *__restrict__ X, size_t n, float dxinv, zpc_hashtable_view tb, unsigned *keys,
+template <bool AOSOA, class BG>
+__global__ void bin_keys_kernel(const float *__restrict__ X, size_t n, float dxinv, BG bg, unsigned *keys,
                                 int *vals, int *err, int cap) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1137,7 +1203,7 @@ __global__ void bin_keys_kernel(const float *__restrict__ X, size_t n, float dxi
     for (int d = 0; d < 3; ++d) x[d] = X[3 * i + d];
   }
   const int c0 = zpcm::sparsity_coord(x[0], dxinv), c1 = zpcm::sparsity_coord(x[1], dxinv), c2 = zpcm::sparsity_coord(x[2], dxinv);
-  int b = zpcm::table_query(c0 >> 2, c1 >> 2, c2 >> 2, tb.tableSize, tb.keys, tb.indices);
+  int b = bg.query(c0 >> 2, c1 >> 2, c2 >> 2);
   if (b < 0) { if (err) atomicOr(err, ZPC_BINS_HOME_BLOCK_MISSING); b = 0; }
   if (b >= cap) { if (err) atomicOr(err, ZPC_BINS_BLOCK_CAPACITY); b = cap - 1; }   // keeps start[] / end[] in bounds and the sort's ebit honest
   keys[i] = ((unsigned)b << 6) | (unsigned)(((c0 & 3) << 4) | ((c1 & 3) << 2) | (c2 & 3));
@@ -1150,17 +1216,20 @@ __global__ void bin_bounds_kernel(const unsigned *__restrict__ keys, size_t n, i
   if (i == 0 || (keys[i - 1] >> 6) != b) start[b] = (int)i;
   if (i == n - 1 || (keys[i + 1] >> 6) != b) end[b] = (int)i + 1;
 }
-__global__ void bin_count_kernel(const int *start, const int *end, const int *cnt, int cap, int *nbins, int *err) {
+template <class BG>
+__global__ void bin_count_kernel(const int *start, const int *end, BG bg, int cap, int *nbins, int *err) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0 && err && *cnt > cap) atomicOr(err, ZPC_BINS_BLOCK_CAPACITY);
+  const int cnt = bg.count();
+  if (b == 0 && err && cnt > cap) atomicOr(err, ZPC_BINS_BLOCK_CAPACITY);
   if (b >= cap) return;
-  nbins[b] = b < *cnt ? (end[b] - start[b] + BIN_MAX - 1) / BIN_MAX : 0;
+  nbins[b] = b < cnt ? (end[b] - start[b] + BIN_MAX - 1) / BIN_MAX : 0;
 }
-__global__ void bin_fill_kernel(const int *start, const int *end, const int *nbins, const int *binoff, const int *cnt, int cap,
-                                const int *active_keys, int n, int *binStart, int *binKey, int *numBins, int binCapacity,
+template <class BG>
+__global__ void bin_fill_kernel(const int *start, const int *end, const int *nbins, const int *binoff, BG bg, int cap,
+                                int n, int *binStart, int *binKey, int *numBins, int binCapacity,
                                 int *err) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nb = min(*cnt, cap);
+  const int nb = min(bg.count(), cap);
   if (b == 0) {
     const int total = nb > 0 ? binoff[nb - 1] + nbins[nb - 1] : 0;
     if (total > binCapacity) { if (err) atomicOr(err, ZPC_BINS_BIN_CAPACITY); *numBins = 0; }
@@ -1169,11 +1238,13 @@ __global__ void bin_fill_kernel(const int *start, const int *end, const int *nbi
   if (b >= nb) return;
   const int k = nbins[b], o = binoff[b];
   if (o + k > binCapacity) return;
+  int kx = 0, ky = 0, kz = 0;
+  if (k > 0) bg.key_of(b, kx, ky, kz);
   for (int j = 0; j < k; ++j) {
     binStart[o + j] = start[b] + j * BIN_MAX;
-    binKey[3 * (o + j)] = active_keys[3 * b];
-    binKey[3 * (o + j) + 1] = active_keys[3 * b + 1];
-    binKey[3 * (o + j) + 2] = active_keys[3 * b + 2];
+    binKey[3 * (o + j)] = kx;
+    binKey[3 * (o + j) + 1] = ky;
+    binKey[3 * (o + j) + 2] = kz;
   }
 }
 // dst slot i <- src particle perm[i]
@@ -1214,8 +1285,8 @@ __global__ void gather_f32_kernel(const float *__restrict__ src, const int *__re
 int bit_length(unsigned v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
 
 // shared pipeline of bin_particles / rebin_particles
-template <bool SRC_AOSOA>
-int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const float *srcT, size_t n, zpc_hashtable_view tb, float dx,
+template <bool SRC_AOSOA, class BG = BinGridLegacy>
+int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const float *srcT, size_t n, BG tb, float dx,
                  zpc_bins_view dst, int *order_out, cudaStream_t s) {
   if (!temp_bytes) return ZPCB200_E_BADARG;
   if (dst.pars.numChannels != NCH || dst.binCapacity <= 0) return ZPCB200_E_BADARG;
@@ -1246,7 +1317,7 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
   if (dst.cellOrderValid) ZPC_CUDA(cudaMemsetAsync(dst.cellOrderValid, 0, sizeof(int), s));  // new slots: cache is stale
   const unsigned gp = (unsigned)((n + 255) / 256), gb = (unsigned)((cap + 255) / 256);
   if (n) {
-    bin_keys_kernel<SRC_AOSOA><<<gp, 256, 0, s>>>(SRC_AOSOA ? srcT : A.X, n, 1.0f / dx, tb, keys, vals, err, cap);
+    bin_keys_kernel<SRC_AOSOA, BG><<<gp, 256, 0, s>>>(SRC_AOSOA ? srcT : A.X, n, 1.0f / dx, tb, keys, vals, err, cap);
     ZPC_CHECK_LAUNCH();
     zpc_port pk = {keys, 0, 0, 0, 1}, pv = {vals, 0, 0, 0, 1}, psk = {skeys, 0, 0, 0, 1}, psv = {svals, 0, 0, 0, 1};
     size_t sb = sort_bytes;
@@ -1255,7 +1326,7 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
     bin_bounds_kernel<<<gp, 256, 0, s>>>(skeys, n, start, end);
     ZPC_CHECK_LAUNCH();
   }
-  bin_count_kernel<<<gb, 256, 0, s>>>(start, end, tb.cnt, cap, nbins, err);
+  bin_count_kernel<BG><<<gb, 256, 0, s>>>(start, end, tb, cap, nbins, err);
   ZPC_CHECK_LAUNCH();
   {
     zpc_port pi = {nbins, 0, 0, 0, 1}, po = {binoff, 0, 0, 0, 1};
@@ -1263,8 +1334,8 @@ int bin_pipeline(void *temp, size_t *temp_bytes, zpc_particles_view A, const flo
     rc = zpcb200_exclusive_scan_sum_i32(t + o_scan, &sb, pi, po, (size_t)cap, s);
     if (rc) return rc;
   }
-  bin_fill_kernel<<<gb, 256, 0, s>>>(start, end, nbins, binoff, tb.cnt, cap, tb.activeKeys, (int)n, dst.binStart, dst.binKey,
-                                      dst.numBins, dst.binCapacity, err);
+  bin_fill_kernel<BG><<<gb, 256, 0, s>>>(start, end, nbins, binoff, tb, cap, (int)n, dst.binStart, dst.binKey,
+                                          dst.numBins, dst.binCapacity, err);
   ZPC_CHECK_LAUNCH();
   if (n) {
     bin_gather_kernel<SRC_AOSOA><<<gp, 256, 0, s>>>(A, srcT, svals, n, dst.pars.base);
@@ -1325,7 +1396,7 @@ static int p2g_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
                              : p2g_binned_kernel<4, MODEL>;
   kern<<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart,
-      bins.cellOrderValid, tb, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp, bins.status, halo);
+      bins.cellOrderValid, BinGridLegacy{tb}, g.tiles, g.dx, dt, volume, mu, lam, variant == 3 ? 0 : 1, yield_stress, scalar, pp, bins.status, halo, 7);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }
@@ -1336,11 +1407,16 @@ static int g2p_binned_launch(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grid
     return ZPCB200_E_BADARG;
   const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
   const int staged = tuning().g2p_staged;
-  auto kern = staged == 128 ? g2p_binned_staged_kernel<128, EOS> : staged == 256 ? g2p_binned_staged_kernel<256, EOS> : staged ? g2p_binned_staged_kernel<64, EOS> : g2p_binned_kernel<EOS>;
+  auto kern = staged == 128 ? g2p_binned_staged_kernel<128, EOS> : staged == 256 ? g2p_binned_staged_kernel<256, EOS> : g2p_binned_staged_kernel<64, EOS>;
   const int nt = staged == 128 ? 128 : staged == 256 ? 256 : staged ? 64 : G2P_NT;
-  kern<<<bins.binCapacity, nt, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
-                                                              cache ? bins.cellOrder : nullptr, bins.cellStart, tb, g.tiles,
-                                                              g.numChannels, g.dx, dt, scalar, bins.status);
+  if (staged)
+    kern<<<bins.binCapacity, nt, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
+                                                                cache ? bins.cellOrder : nullptr, bins.cellStart, BinGridLegacy{tb}, g.tiles,
+                                                                g.numChannels, g.dx, dt, scalar, bins.status);
+  else
+    g2p_binned_kernel<EOS><<<bins.binCapacity, nt, 0, (cudaStream_t)stream>>>(bins.pars.base, bins.binStart, bins.binKey, bins.numBins,
+                                                                                  cache ? bins.cellOrder : nullptr, bins.cellStart, tb, g.tiles,
+                                                                                  g.numChannels, g.dx, dt, scalar, bins.status);
   ZPC_CHECK_LAUNCH();
   if (cache) ZPC_CUDA(cudaMemsetAsync(bins.cellOrderValid, 1, sizeof(int), (cudaStream_t)stream));  // non-zero = valid
   return ZPCB200_OK;
@@ -1365,13 +1441,13 @@ int zpcb200_bin_particles(void *temp, size_t *temp_bytes, zpc_particles_view par
                           zpc_bins_view bins, int *order_out, zpc_stream_t stream) {
   if (temp && pars.count && (!pars.X || !pars.V || !pars.M || !pars.C || !pars.F)) return ZPCB200_E_BADARG;
   if (temp && bins.pars.size < pars.count) return ZPCB200_E_BADARG;
-  return bin_pipeline<false>(temp, temp_bytes, pars, nullptr, pars.count, table, dx, bins, order_out, (cudaStream_t)stream);
+  return bin_pipeline<false>(temp, temp_bytes, pars, nullptr, pars.count, BinGridLegacy{table}, dx, bins, order_out, (cudaStream_t)stream);
 }
 int zpcb200_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src, zpc_hashtable_view table, float dx,
                             zpc_bins_view dst, zpc_stream_t stream) {
   zpc_particles_view none = {};
   if (temp && (src.pars.base == dst.pars.base || dst.pars.size < src.pars.size)) return ZPCB200_E_BADARG;
-  return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, table, dx, dst, nullptr, (cudaStream_t)stream);
+  return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, BinGridLegacy{table}, dx, dst, nullptr, (cudaStream_t)stream);
 }
 int zpcb200_gather_f32(const float *src, const int *idx, float *dst, size_t n, zpc_stream_t stream) {
   if (n && (!src || !idx || !dst || src == dst)) return ZPCB200_E_BADARG;
@@ -1418,7 +1494,7 @@ int zpcb200_rebin_particles_ordered(void *temp, size_t *temp_bytes, zpc_bins_vie
                                     zpc_bins_view dst, int *order_out, zpc_stream_t stream) {
   zpc_particles_view none = {};
   if (temp && (src.pars.base == dst.pars.base || dst.pars.size < src.pars.size)) return ZPCB200_E_BADARG;
-  return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, table, dx, dst, order_out, (cudaStream_t)stream);
+  return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, BinGridLegacy{table}, dx, dst, order_out, (cudaStream_t)stream);
 }
 int zpcb200_p2g_apic_vonmises_binned(zpc_bins_view bins, zpc_hashtable_view tb, zpc_grids_view g, float dt,
                                      zpc_vonmises_fixed_corotated model, zpc_stream_t stream) {
@@ -1440,3 +1516,69 @@ int zpcb200_g2p_apic_eos_binned(zpc_bins_view bins, float *J, zpc_hashtable_view
   return g2p_binned_launch<true>(bins, tb, g, dt, J, stream);
 }
 }
+
+// ---- block-binned fast path on SparseGrid<3,f32,8> (round 2; geometry/SparseGrid.hpp:16-188, 275-309) ------------------------------
+// Same bins, same kernels: a bin is one octant (4^3 cells) of a side-8 block, BinGridSparse maps octants to (block number, offset).
+namespace {
+bool sgb_uniform_dx(const zpc_sparsegrid_view &sg, float &dx) {
+  const float *M = sg.transform;
+  dx = M[0];
+  if (!(dx > 0.f) || M[5] != dx || M[10] != dx || M[15] != 1.f) return false;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      if (i != j && M[4 * i + j] != 0.f) return false;
+  return true;
+}
+bool sgb_table_ok(const zpc_bht_view &t) { return t.keys && t.indices && t.status && t.activeKeys && t.cnt && t.numBuckets * 16u == t.tableSize; }
+}  // namespace
+
+extern "C" {
+int zpcb200_sg_bin_particles(void *temp, size_t *temp_bytes, zpc_particles_view pars, zpc_sparsegrid_view sg, zpc_bins_view bins,
+                             int *order_out, zpc_stream_t stream) {
+  float dx;
+  if (!sgb_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  if (temp && (!sgb_table_ok(sg.table) || (pars.count && (!pars.X || !pars.V || !pars.M || !pars.C || !pars.F)))) return ZPCB200_E_BADARG;
+  if (temp && bins.pars.size < pars.count) return ZPCB200_E_BADARG;
+  return bin_pipeline<false>(temp, temp_bytes, pars, nullptr, pars.count, BinGridSparse{sg.table}, dx, bins, order_out, (cudaStream_t)stream);
+}
+int zpcb200_sg_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src, zpc_sparsegrid_view sg, zpc_bins_view dst, int *order_out,
+                               zpc_stream_t stream) {
+  float dx;
+  if (!sgb_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  if (temp && (!sgb_table_ok(sg.table) || !src.pars.base || !dst.pars.base || src.pars.base == dst.pars.base || dst.pars.size < src.pars.size)) return ZPCB200_E_BADARG;
+  zpc_particles_view none = {};
+  return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, BinGridSparse{sg.table}, dx, dst, order_out, (cudaStream_t)stream);
+}
+int zpcb200_sg_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_fixed_corotated model, zpc_stream_t stream) {
+  float dx;
+  if (!sgb_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  if (sg.numChannels < 7 || !sg.grid || !sgb_table_ok(sg.table) || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
+    return ZPCB200_E_BADARG;
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4, 0, BinGridSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    attr_set.store(true, std::memory_order_release);
+  }
+  float mu, lam;
+  zpcm::lame_host(model.E, model.nu, mu, lam);
+  const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
+  p2g_binned_kernel<4, 0, BinGridSparse><<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
+      bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart, bins.cellOrderValid,
+      BinGridSparse{sg.table}, sg.grid, dx, dt, model.volume, mu, lam, 1, 0.f, nullptr, zpcm::PlasticPrm{}, bins.status, zpc_halo_view{}, sg.numChannels);
+  ZPC_CHECK_LAUNCH();
+  return ZPCB200_OK;
+}
+int zpcb200_sg_g2p_apic_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream) {
+  float dx;
+  if (!sgb_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
+  if (sg.numChannels < 4 || !sg.grid || !sgb_table_ok(sg.table) || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
+    return ZPCB200_E_BADARG;
+  const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
+  g2p_binned_staged_kernel<64, false, BinGridSparse><<<bins.binCapacity, 64, 0, (cudaStream_t)stream>>>(
+      bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart, BinGridSparse{sg.table}, sg.grid,
+      sg.numChannels, dx, dt, nullptr, bins.status);
+  ZPC_CHECK_LAUNCH();
+  if (cache) ZPC_CUDA(cudaMemsetAsync(bins.cellOrderValid, 1, sizeof(int), (cudaStream_t)stream));  // non-zero = valid
+  return ZPCB200_OK;
+}
+}  // extern "C"

@@ -464,8 +464,11 @@ template <typename K, bool PAIRS, int ITEMS, bool FAST>
 #ifndef ZPC_RS_ITEMS4
 #define ZPC_RS_ITEMS4 16
 #endif
-#ifndef ZPC_RS_MINB4
-#define ZPC_RS_MINB4 3
+#ifndef ZPC_RS_MINB4   // CTAs per SM for 4-byte keys: 4 (64 registers) since the lane-mask ranking; 3 (80 registers) was right for the ballots
+#define ZPC_RS_MINB4 4
+#endif
+#ifndef ZPC_RS_MATCH_OR   // 1: ranking through shared-memory lane masks (atomicOr); 0: one ballot per digit bit
+#define ZPC_RS_MATCH_OR 1
 #endif
 __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? ZPC_RS_MINB4 : 2) rs_onesweep_kernel(PortAcc<K> kin, PortAcc<int> vin, PortAcc<K> kout,
                                                             PortAcc<int> vout, size_t n, int shift, unsigned mask, int nbits,
@@ -478,10 +481,19 @@ __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? ZPC_RS_MINB4 : 2) rs_o
   __shared__ unsigned wsum[RS_NW];
   __shared__ unsigned s_tile;
   __shared__ K skeys[TILE];
+#if ZPC_RS_MATCH_OR
+  // per-warp lane masks by digit, two items in flight; all zero between items.  They live in the staging buffer of the scatter phase,
+  // which starts after the ranking (two barriers later)
+  static_assert(sizeof(K) * TILE >= 2 * RS_NW * RS_BINS * sizeof(unsigned), "the match masks are overlaid on skeys");
+  unsigned (*warp_match)[RS_NW][RS_BINS] = reinterpret_cast<unsigned (*)[RS_NW][RS_BINS]>(skeys);
+#endif
   int *svals = reinterpret_cast<int *>(skeys);  // values staged after keys are written out (PAIRS, sizeof(K)>=4)
 
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   for (int i = threadIdx.x; i < RS_NW * RS_BINS; i += RS_NT) (&warp_hist[0][0])[i] = 0;
+#if ZPC_RS_MATCH_OR
+  for (int i = threadIdx.x; i < 2 * RS_NW * RS_BINS; i += RS_NT) (&warp_match[0][0][0])[i] = 0;
+#endif
   __syncthreads();
   const unsigned tile = s_tile;
   const size_t base = (size_t)tile * TILE;
@@ -494,9 +506,41 @@ __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? ZPC_RS_MINB4 : 2) rs_o
   unsigned rank[ITEMS];  // rank among same-digit keys of this warp (then of this tile)
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) key[i] = (wofs + 32 * i) < cnt_tile ? tk[wofs + 32 * i] : (K)0;
+  const bool full_tile = cnt_tile == TILE;  // CTA-uniform: every lane holds a key, no validity votes
+#if ZPC_RS_MATCH_OR
+  // Warp-synchronous stable ranking through shared-memory masks: every lane ORs its lane bit into the word of its digit (a native
+  // integer atomic, one pass of the data pipe), reads the word back = the set of lanes holding that digit, and the lowest of them
+  // clears the word and adds the group's size to the warp's digit counter.  About 20 instructions per key where one ballot per digit
+  // bit took 85 (ncu: 51 % of the pass's instructions, the pass is issue-bound); two items are in flight per step (two mask arrays)
+  // so that the shared-memory round trips of one overlap the other's.  MATCH.ANY would be one instruction, but its latency is long
+  // and poorly pipelined on sm_100 (the histogram pass spent 7.5 ms in it at 2^28).
+  {
+    unsigned *wm0 = &warp_match[0][w][0], *wm1 = &warp_match[1][w][0];
+    const unsigned lbit = 1u << l, lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < ITEMS; i += 2) {
+      const bool va = full_tile || (wofs + 32 * i) < cnt_tile, vb = full_tile || (wofs + 32 * (i + 1)) < cnt_tile;
+      const unsigned da = digit_of(key[i], shift, mask), db = digit_of(key[i + 1], shift, mask);
+      if (va) atomicOr(&wm0[da], lbit);
+      if (vb) atomicOr(&wm1[db], lbit);
+      __syncwarp();
+      const unsigned pa = va ? wm0[da] : 0u, pb = vb ? wm1[db] : 0u;
+      __syncwarp();   // every lane has read the masks before a leader clears them
+      const int la = __ffs(pa) - 1, lb = __ffs(pb) - 1;
+      unsigned ca = 0, cb = 0;
+      if (va && l == la) { wm0[da] = 0u; ca = atomicAdd(&warp_hist[w][da], (unsigned)__popc(pa)); }
+      __syncwarp();   // item i's counter updates are ordered before item i + 1's (stability)
+      if (vb && l == lb) { wm1[db] = 0u; cb = atomicAdd(&warp_hist[w][db], (unsigned)__popc(pb)); }
+      ca = __shfl_sync(0xffffffffu, ca, la < 0 ? 0 : la);
+      cb = __shfl_sync(0xffffffffu, cb, lb < 0 ? 0 : lb);
+      rank[i] = ca + (unsigned)__popc(pa & lt);
+      rank[i + 1] = cb + (unsigned)__popc(pb & lt);
+      __syncwarp();
+    }
+  }
+#else
   // warp-synchronous stable ranking: lanes holding the same digit are found with one ballot per digit bit
   // (MATCH.ANY has a long, poorly pipelined latency on sm_100), then one shared-memory counter per (warp, digit)
-  const bool full_tile = cnt_tile == TILE;  // CTA-uniform: every lane holds a key, no validity votes
   // (1) peer masks of all items first: 16 independent vote chains the scheduler can overlap.  Packed into rank[i]:
   //     bits 0-4 = same-digit lanes before this one, 5-9 = leader lane, 10-15 = group size.
 #pragma unroll
@@ -535,6 +579,7 @@ __global__ void __launch_bounds__(RS_NT, sizeof(K) == 4 ? ZPC_RS_MINB4 : 2) rs_o
     rank[i] = c + (rank[i] & 31u);
     __syncwarp();  // item i's counter updates are ordered before item i+1's
   }
+#endif
   __syncthreads();
   // per digit (thread d): exclusive prefix over warps, tile count
   {

@@ -110,7 +110,16 @@ def migrate_particles(attrs, dest, group=None):
     widths = [attrs[k].shape[1] if attrs[k].dim() == 2 else 1 for k in names]
     n = dest.numel()
     packed = torch.cat([attrs[k].reshape(n, -1) for k in names], dim=1) if n else torch.zeros(0, sum(widths), dtype=torch.float32, device=dest.device)
-    order = torch.argsort(dest, stable=True)   # host-side plumbing of a rare, collective operation (every few hundred substeps)
+    if dest.is_cuda and n:
+        # the library's own stable radix sort on the few bits a rank number has (one pass), not torch.argsort
+        from . import api
+        keys = dest.to(torch.int32)
+        ko, order32 = torch.empty_like(keys), torch.empty_like(keys)
+        api.cuda_exec().radix_sort_pair(keys, torch.arange(n, dtype=torch.int32, device=dest.device), ko, order32, kind="i32",
+                                        sbit=0, ebit=max(1, (world - 1).bit_length()))
+        order = order32.long()
+    else:
+        order = torch.argsort(dest, stable=True)   # the gloo / CPU tests of the host logic
     send_counts = torch.bincount(dest, minlength=world).to(torch.int64)
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
