@@ -83,13 +83,16 @@ ZPCB200_DECL_SORT(u64, uint64_t)
 
 /* merge_sort / merge_sort_pair (cuda/execution/ExecutionPolicy.cuh:686-760; host twins execution/ExecutionPolicy.hpp:
  * 285-455): stable ascending sort under operator<, IN PLACE, <T> in {i32,f32,f64} like the reference's C layer
- * (py_interop/cuda/ExecutionPolicy.cpp:100-112); values are i32.  -0.0 and +0.0 compare equal (their relative order is
+ * (py_interop/cuda/ExecutionPolicy.cpp:100-112) plus {u32,i64,u64} (the generic call takes any key type); values are i32.  -0.0 and +0.0 compare equal (their relative order is
  * kept); NaN keys sort by bit pattern. */
 #define ZPCB200_DECL_MERGE_SORT(S)                                                                  \
   int zpcb200_merge_sort_pair_##S(void *temp, size_t *temp_bytes, zpc_port keys, zpc_port vals,     \
                                   size_t n, zpc_stream_t stream);                                   \
   int zpcb200_merge_sort_##S(void *temp, size_t *temp_bytes, zpc_port keys, size_t n, zpc_stream_t stream);
 ZPCB200_DECL_MERGE_SORT(i32)
+ZPCB200_DECL_MERGE_SORT(u32)
+ZPCB200_DECL_MERGE_SORT(i64)
+ZPCB200_DECL_MERGE_SORT(u64)
 ZPCB200_DECL_MERGE_SORT(f32)
 ZPCB200_DECL_MERGE_SORT(f64)
 

@@ -119,5 +119,8 @@ ZO_SCAN_REDUCE_IMPL(f64, double, DBL_MAX, -DBL_MAX)
     free(k2); free(v2);                                                                           \
   }
 ZO_MERGE_IMPL(i32, int32_t)
+ZO_MERGE_IMPL(u32, uint32_t)
+ZO_MERGE_IMPL(i64, int64_t)
+ZO_MERGE_IMPL(u64, uint64_t)
 ZO_MERGE_IMPL(f32, float)
 ZO_MERGE_IMPL(f64, double)

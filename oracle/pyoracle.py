@@ -52,7 +52,7 @@ def _ptr(a):
 
 
 _KT = {"u32": np.uint32, "i32": np.int32, "u64": np.uint64}
-_ST = {"i32": np.int32, "u32": np.uint32, "i64": np.int64, "f32": np.float32, "f64": np.float64}
+_ST = {"i32": np.int32, "u32": np.uint32, "i64": np.int64, "u64": np.uint64, "f32": np.float32, "f64": np.float64}
 
 
 class Oracle:

@@ -244,7 +244,8 @@ def test_policy_object_abi():
 
 
 # ---- merge_sort(_pair): stable, in place, {i32, f32, f64} keys (ExecutionPolicy.cuh:686-760) ---------------------------
-MS_DT = {"i32": (np.int32, torch.int32), "f32": (np.float32, torch.float32), "f64": (np.float64, torch.float64)}
+MS_DT = {"i32": (np.int32, torch.int32), "f32": (np.float32, torch.float32), "f64": (np.float64, torch.float64),
+         "u32": (np.uint32, torch.uint32), "i64": (np.int64, torch.int64), "u64": (np.uint64, torch.uint64)}
 
 
 @pytest.mark.parametrize("kind", list(MS_DT))
@@ -253,7 +254,9 @@ def test_merge_sort_pair_matches_oracle(pol, oracle, kind, n):
     npdt, _ = MS_DT[kind]
     rs = np.random.RandomState(n + 3)
     k = rs.randint(-200, 200, size=n).astype(npdt)          # many duplicates: the value order proves stability
-    if kind != "i32":
+    if kind in ("u32", "i64", "u64"):                       # integers: the high bits take part (negatives wrap to the top of unsigned)
+        k = (k.astype(np.int64) * (1 << (20 if kind == "u32" else 40))).astype(npdt)
+    elif kind != "i32":
         k = (k * npdt(0.37)).astype(npdt)
         if n > 40:
             k[5] = -0.0; k[9] = 0.0; k[17] = -0.0; k[30] = np.inf; k[31] = -np.inf   # +-0 equal under <

@@ -764,6 +764,18 @@ template <> struct OrdKey<int32_t> {
   using U = uint32_t;
   static __device__ __forceinline__ U make(int32_t k) { return (uint32_t)k ^ 0x80000000u; }
 };
+template <> struct OrdKey<uint32_t> {
+  using U = uint32_t;
+  static __device__ __forceinline__ U make(uint32_t k) { return k; }
+};
+template <> struct OrdKey<int64_t> {
+  using U = uint64_t;
+  static __device__ __forceinline__ U make(int64_t k) { return (uint64_t)k ^ 0x8000000000000000ull; }
+};
+template <> struct OrdKey<uint64_t> {
+  using U = uint64_t;
+  static __device__ __forceinline__ U make(uint64_t k) { return k; }
+};
 template <> struct OrdKey<float> {
   using U = uint32_t;
   static __device__ __forceinline__ U make(float x) {
@@ -901,6 +913,9 @@ ZPC_DEF_SORT(u64, uint64_t)
     return merge_sort_impl<T, false>(temp, tb, keys, none, n, (cudaStream_t)st);                                \
   }
 ZPC_DEF_MERGE_SORT(i32, int32_t)
+ZPC_DEF_MERGE_SORT(u32, uint32_t)
+ZPC_DEF_MERGE_SORT(i64, int64_t)
+ZPC_DEF_MERGE_SORT(u64, uint64_t)
 ZPC_DEF_MERGE_SORT(f32, float)
 ZPC_DEF_MERGE_SORT(f64, double)
 
