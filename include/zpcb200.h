@@ -236,6 +236,12 @@ typedef struct zpc_collider {
 int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx,
                             zpc_hashtable_view table, int enlarge_lo, int enlarge_hi, int *overflow,
                             zpc_stream_t stream);
+/* the same with 64-bit block codes: block coordinates in [-2^20, 2^20) per axis (cells beyond +-2 048), about twice the scratch;
+ * the table, numbering rule (rank of the key) and every consumer are unchanged.  The default entry refuses such coordinates
+ * through *overflow. */
+int zpcb200_partition_build_wide(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx,
+                            zpc_hashtable_view table, int enlarge_lo, int enlarge_hi, int *overflow,
+                            zpc_stream_t stream);
 
 /* index_buckets_for_particles (simulation/particle/Query.tpp:9-58 = CleanSparsity + ComputeSparsity{blockLen 1, offset 0,
  * displacement} + SpatiallyCount + exclusive_scan + SpatiallyDistribute, SparsityOp.hpp:41-86, 115-195): `table` becomes the
@@ -247,6 +253,9 @@ int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n
 int zpcb200_index_buckets_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, float displacement,
                                 zpc_hashtable_view table, int *counts, int *offsets, int *indices, int *overflow,
                                 zpc_stream_t stream);
+int zpcb200_index_buckets_build_wide(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, float displacement,
+                                zpc_hashtable_view table, int *counts, int *offsets, int *indices, int *overflow,
+                                zpc_stream_t stream);  /* 64-bit cell codes: cells in [-2^20, 2^20) instead of [-512, 511] */
 
 /* CleanGridBlocks (simulation/grid/GridOp.hpp:54-69) over blocks [0, *cnt): every channel of every cell becomes 0.
  * ResetGrid (GridOp.hpp:166-182) is the same operation on one Grid of the Grids: this entry serves both. */
@@ -363,6 +372,8 @@ size_t zpcb200_bht_table_size(size_t expected_entries);
  * is deterministic: index = rank of the key in lexicographic order. */
 int zpcb200_sg_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, zpc_sparsegrid_view sg,
                                int enlarge_lo, int enlarge_hi, int *overflow, zpc_stream_t stream);
+int zpcb200_sg_partition_build_wide(void *temp, size_t *temp_bytes, zpc_port x, size_t n, zpc_sparsegrid_view sg,
+                               int enlarge_lo, int enlarge_hi, int *overflow, zpc_stream_t stream);  /* 64-bit block codes, as above */
 /* CleanGridBlocks / P2GTransfer<apic, FixedCorotated> / ComputeGridBlockVelocity / G2PTransfer<apic> on the SparseGrid
  * (same arithmetic as the Grids<f32,3,4> entries above; channels {m, v(3), rhs(3)}), AoS particles in any order. */
 int zpcb200_sg_clean(zpc_sparsegrid_view sg, zpc_stream_t stream);

@@ -29,7 +29,8 @@ __global__ void part_clear_table_kernel(int table_size, int *keys, int *indices,
 }
 
 // place key i (rank order) at the first free slot of ITS OWN probe sequence (any such placement is a valid table)
-__global__ void part_place_kernel(const unsigned *sorted, const int *list_cnt, int list_cap, int table_size, int *keys,
+template <class CODE>
+__global__ void part_place_kernel(const CODE *sorted, const int *list_cnt, int list_cap, int table_size, int *keys,
                                   int *indices, int *active_keys, int *cnt, int *overflow) {
   const int n = min(*list_cnt, list_cap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -52,20 +53,22 @@ __global__ void part_place_kernel(const unsigned *sorted, const int *list_cnt, i
 // ---- index_buckets_for_particles (simulation/particle/Query.tpp:9-58) ------------------------------------------------
 // cell of a particle: ComputeSparsity / SpatiallyCount / SpatiallyDistribute with blockLen 1, offset 0 (SparsityOp.hpp:71-76)
 __device__ __forceinline__ int bucket_cell(float x, float dxinv, float displacement) { return (int)floorf(x * dxinv + displacement); }
-__global__ void bucket_mark_kernel(PortAcc<const float> x, size_t n, float dxinv, float displacement, unsigned *set, unsigned set_mask,
-                                   unsigned *list, int list_cap, int *list_cnt, int *overflow) {
+template <class CODE>
+__global__ void bucket_mark_kernel(PortAcc<const float> x, size_t n, float dxinv, float displacement, CODE *set, unsigned set_mask,
+                                   CODE *list, int list_cap, int *list_cnt, int *overflow) {
+  constexpr CODE EMPTY = CodeTraits<CODE>::EMPTY;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
   for (size_t i0 = first; i0 < n; i0 += stride) {  // warp-uniform trip count
     const size_t i = i0 + (threadIdx.x & 31);
-    unsigned code = CODE_EMPTY;
+    CODE code = EMPTY;
     if (i < n && !code_pack(bucket_cell(x.at(i, 0), dxinv, displacement), bucket_cell(x.at(i, 1), dxinv, displacement),
                             bucket_cell(x.at(i, 2), dxinv, displacement), code)) {
-      code = CODE_EMPTY;
+      code = EMPTY;
       if (overflow) *overflow = 1;
     }
     const unsigned peers = __match_any_sync(0xffffffffu, code);
-    if (code != CODE_EMPTY && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+    if (code != EMPTY && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
       set_insert(code, set, set_mask, list, list_cap, list_cnt, overflow);
   }
 }
@@ -260,13 +263,15 @@ __global__ void halo_kernel(float *tiles, int nch_grid, const int *ids, int n, i
 
 extern "C" {
 
-int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, zpc_hashtable_view tb,
-                            int enlarge_lo, int enlarge_hi, int *overflow, zpc_stream_t stream) {
+}  // extern "C"
+template <class CODE>
+static int partition_build_impl(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, zpc_hashtable_view tb,
+                                int enlarge_lo, int enlarge_hi, int *overflow, zpc_stream_t stream) {
   if (!temp_bytes || tb.tableSize <= 0 || enlarge_hi < enlarge_lo || enlarge_hi - enlarge_lo > 8) return ZPCB200_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   // scratch set: power of two >= tableSize/2 ; list capacity = tableSize/8 block codes
   PartScratch L;
-  int rc = part_scratch_layout((size_t)tb.tableSize, L);
+  int rc = part_scratch_layout<CODE>((size_t)tb.tableSize, L);
   if (rc) return rc;
   if (!temp) { *temp_bytes = L.need; return ZPCB200_OK; }
   if (*temp_bytes < L.need) return ZPCB200_E_TEMP_TOO_SMALL;
@@ -274,23 +279,35 @@ int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n
   const int G = ZPC_SM_COUNT * 8;
   part_clear_table_kernel<<<G, 256, 0, s>>>(tb.tableSize, tb.keys, tb.indices, tb.status);
   ZPC_CHECK_LAUNCH();
-  rc = part_collect_sorted<2>(t, L, x, n, dx, enlarge_lo, enlarge_hi, overflow, s);
+  rc = part_collect_sorted<2, CODE>(t, L, x, n, dx, enlarge_lo, enlarge_hi, overflow, s);
   if (rc) return rc;
-  part_place_kernel<<<G, 256, 0, s>>>((const unsigned *)(t + L.off_sorted), (const int *)t, L.list_cap, tb.tableSize, tb.keys,
-                                       tb.indices, tb.activeKeys, tb.cnt, overflow);
+  part_place_kernel<CODE><<<G, 256, 0, s>>>((const CODE *)(t + L.off_sorted), (const int *)t, L.list_cap, tb.tableSize, tb.keys,
+                                             tb.indices, tb.activeKeys, tb.cnt, overflow);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
+}
+extern "C" {
+int zpcb200_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, zpc_hashtable_view tb,
+                            int enlarge_lo, int enlarge_hi, int *overflow, zpc_stream_t stream) {
+  return partition_build_impl<unsigned>(temp, temp_bytes, x, n, dx, tb, enlarge_lo, enlarge_hi, overflow, stream);
+}
+/* 64-bit block codes: block coordinates in [-2^20, 2^20) per axis instead of [-512, 511] */
+int zpcb200_partition_build_wide(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, zpc_hashtable_view tb,
+                                 int enlarge_lo, int enlarge_hi, int *overflow, zpc_stream_t stream) {
+  return partition_build_impl<unsigned long long>(temp, temp_bytes, x, n, dx, tb, enlarge_lo, enlarge_hi, overflow, stream);
 }
 
 static int bit_length_u(size_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
 
-int zpcb200_index_buckets_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, float displacement,
-                                zpc_hashtable_view tb, int *counts, int *offsets, int *indices, int *overflow, zpc_stream_t stream) {
+}  // extern "C"
+template <class CODE>
+static int index_buckets_build_impl(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, float displacement,
+                                    zpc_hashtable_view tb, int *counts, int *offsets, int *indices, int *overflow, zpc_stream_t stream) {
   if (!temp_bytes || tb.tableSize <= 0) return ZPCB200_E_BADARG;
   if (n > ((size_t)1 << 30)) return ZPCB200_E_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   PartScratch L;
-  int rc = part_scratch_layout((size_t)tb.tableSize, L);
+  int rc = part_scratch_layout<CODE>((size_t)tb.tableSize, L);
   if (rc) return rc;
   const int ebit = bit_length_u(n ? n - 1 : 0) > 0 ? bit_length_u(n - 1) : 1;   // bucket numbers are < n
   size_t sort_bytes = 0, scan_bytes = 0;
@@ -310,22 +327,21 @@ int zpcb200_index_buckets_build(void *temp, size_t *temp_bytes, zpc_port x, size
   part_clear_table_kernel<<<G, 256, 0, s>>>(tb.tableSize, tb.keys, tb.indices, tb.status);
   ZPC_CHECK_LAUNCH();
   int *counters = (int *)t;
-  unsigned *set = (unsigned *)(t + L.off_set), *list = (unsigned *)(t + L.off_list), *sorted = (unsigned *)(t + L.off_sorted);
-  part_clear_scratch_kernel<<<G, 256, 0, s>>>(set, (unsigned)L.set_n, list, L.list_cap, counters);
+  CODE *set = (CODE *)(t + L.off_set), *list = (CODE *)(t + L.off_list), *sorted = (CODE *)(t + L.off_sorted);
+  part_clear_scratch_kernel<CODE><<<G, 256, 0, s>>>(set, (unsigned)L.set_n, list, L.list_cap, counters);
   ZPC_CHECK_LAUNCH();
   const float dxinv = 1.0f / dx;
   if (n) {
-    bucket_mark_kernel<<<G, 256, 0, s>>>(PortAcc<const float>(x), n, dxinv, displacement, set, (unsigned)(L.set_n - 1), list, L.list_cap, counters,
-                                          overflow);
+    bucket_mark_kernel<CODE><<<G, 256, 0, s>>>(PortAcc<const float>(x), n, dxinv, displacement, set, (unsigned)(L.set_n - 1), list, L.list_cap,
+                                                counters, overflow);
     ZPC_CHECK_LAUNCH();
   }
   {
-    zpc_port pl = {list, 0, 0, 0, 1}, ps = {sorted, 0, 0, 0, 1};
     size_t sb = L.sort_bytes;
-    rc = zpcb200_radix_sort_u32(t + L.off_sort, &sb, pl, ps, (size_t)L.list_cap, 0, 30, stream);
+    rc = sort_codes<CODE>(t + L.off_sort, &sb, list, sorted, (size_t)L.list_cap, s);
     if (rc) return rc;
   }
-  part_place_kernel<<<G, 256, 0, s>>>(sorted, counters, L.list_cap, tb.tableSize, tb.keys, tb.indices, tb.activeKeys, tb.cnt, overflow);
+  part_place_kernel<CODE><<<G, 256, 0, s>>>(sorted, counters, L.list_cap, tb.tableSize, tb.keys, tb.indices, tb.activeKeys, tb.cnt, overflow);
   ZPC_CHECK_LAUNCH();
   // counts (n + 1 entries: buckets beyond table.size() stay 0), offsets = exclusive scan, indices = ids sorted by bucket (stable)
   ZPC_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), s));
@@ -348,6 +364,16 @@ int zpcb200_index_buckets_build(void *temp, size_t *temp_bytes, zpc_port x, size
     if (rc) return rc;
   }
   return ZPCB200_OK;
+}
+extern "C" {
+int zpcb200_index_buckets_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, float displacement,
+                                zpc_hashtable_view tb, int *counts, int *offsets, int *indices, int *overflow, zpc_stream_t stream) {
+  return index_buckets_build_impl<unsigned>(temp, temp_bytes, x, n, dx, displacement, tb, counts, offsets, indices, overflow, stream);
+}
+/* 64-bit cell codes: cell coordinates in [-2^20, 2^20) per axis instead of [-512, 511] */
+int zpcb200_index_buckets_build_wide(void *temp, size_t *temp_bytes, zpc_port x, size_t n, float dx, float displacement,
+                                     zpc_hashtable_view tb, int *counts, int *offsets, int *indices, int *overflow, zpc_stream_t stream) {
+  return index_buckets_build_impl<unsigned long long>(temp, temp_bytes, x, n, dx, displacement, tb, counts, offsets, indices, overflow, stream);
 }
 
 int zpcb200_clean_grid(zpc_grids_view g, const int *cnt, zpc_stream_t stream) {

@@ -33,7 +33,8 @@ __global__ void sg_clear_table_kernel(zpc_bht_view tb) {
 
 // key i (rank order) goes to the first of its three candidate buckets with room: slots 0..14 of a bucket are claimed
 // in order with a CAS on the index array (the reference's insert never uses slot 15: threshold = 14, Bht.hpp:41)
-__global__ void sg_place_kernel(const unsigned *sorted, const int *list_cnt, int list_cap, zpc_bht_view tb, int *overflow) {
+template <class CODE>
+__global__ void sg_place_kernel(const CODE *sorted, const int *list_cnt, int list_cap, zpc_bht_view tb, int *overflow) {
   const int n = min(*list_cnt, list_cap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int bx, by, bz;
@@ -194,14 +195,16 @@ size_t zpcb200_bht_table_size(size_t expected) {
   return n + (16 - n % 16);
 }
 
-int zpcb200_sg_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, zpc_sparsegrid_view sg, int enlarge_lo,
-                               int enlarge_hi, int *overflow, zpc_stream_t stream) {
+}  // extern "C"
+template <class CODE>
+static int sg_partition_build_impl(void *temp, size_t *temp_bytes, zpc_port x, size_t n, zpc_sparsegrid_view sg, int enlarge_lo,
+                                   int enlarge_hi, int *overflow, zpc_stream_t stream) {
   if (!temp_bytes || sg.table.tableSize < 16 || enlarge_hi < enlarge_lo || enlarge_hi - enlarge_lo > 8) return ZPCB200_E_BADARG;
   float dx;
   if (!sg_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   PartScratch L;
-  int rc = part_scratch_layout((size_t)sg.table.tableSize * 4, L);  // the bht holds up to tableSize/2 keys: list of tableSize/2 codes
+  int rc = part_scratch_layout<CODE>((size_t)sg.table.tableSize * 4, L);  // the bht holds up to tableSize/2 keys: list of tableSize/2 codes
   if (rc) return rc;
   if (!temp) { *temp_bytes = L.need; return ZPCB200_OK; }
   if (*temp_bytes < L.need) return ZPCB200_E_TEMP_TOO_SMALL;
@@ -214,11 +217,21 @@ int zpcb200_sg_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_
     sg_set_success_kernel<<<1, 1, 0, s>>>(sg.table.success);
     ZPC_CHECK_LAUNCH();
   }
-  rc = part_collect_sorted<3>(t, L, x, n, dx, enlarge_lo, enlarge_hi, overflow, s);
+  rc = part_collect_sorted<3, CODE>(t, L, x, n, dx, enlarge_lo, enlarge_hi, overflow, s);
   if (rc) return rc;
-  sg_place_kernel<<<G, 256, 0, s>>>((const unsigned *)(t + L.off_sorted), (const int *)t, L.list_cap, sg.table, overflow);
+  sg_place_kernel<CODE><<<G, 256, 0, s>>>((const CODE *)(t + L.off_sorted), (const int *)t, L.list_cap, sg.table, overflow);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
+}
+extern "C" {
+int zpcb200_sg_partition_build(void *temp, size_t *temp_bytes, zpc_port x, size_t n, zpc_sparsegrid_view sg, int enlarge_lo,
+                               int enlarge_hi, int *overflow, zpc_stream_t stream) {
+  return sg_partition_build_impl<unsigned>(temp, temp_bytes, x, n, sg, enlarge_lo, enlarge_hi, overflow, stream);
+}
+/* 64-bit block codes: block coordinates in [-2^20, 2^20) per axis */
+int zpcb200_sg_partition_build_wide(void *temp, size_t *temp_bytes, zpc_port x, size_t n, zpc_sparsegrid_view sg, int enlarge_lo,
+                                    int enlarge_hi, int *overflow, zpc_stream_t stream) {
+  return sg_partition_build_impl<unsigned long long>(temp, temp_bytes, x, n, sg, enlarge_lo, enlarge_hi, overflow, stream);
 }
 
 int zpcb200_tilevector_reorder_tiles(const float *src, float *dst, int numChannels, int tileLength, const int *map, size_t numTiles,
