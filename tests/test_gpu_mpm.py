@@ -80,6 +80,49 @@ def test_partition_matches_oracle(oracle, case):
     assert (ht["keys"][free] == np.iinfo(np.int32).max).all() and (table.status.cpu().numpy() == -1).all()
 
 
+def test_wide_block_codes_far_from_the_origin(oracle):
+    """a cloud 6 000 cells away from the origin: block coordinates ~1 500, outside the 10 bits per axis of the default block codes —
+    zpcb200_partition_build raises *overflow, zpcb200_partition_build_wide (3 x 21-bit codes in 64 bits) builds the same table the
+    oracle builds, and the whole substep on it matches the oracle"""
+    from zpc_b200 import api
+    P = synth.elastic_cube(8, 32, jitter_F=0.04, jitter_C=0.3, shuffle_seed=2, origin_cells=6000)
+    P["x"][:, 1] -= np.float32(9000 * P["dx"])          # and negative on one axis
+    n, dx = P["x"].shape[0], P["dx"]
+    pars = api.Particles(P)
+    table = api.HashTable(max(n // 8, 64))
+    api.partition_for_particles(api.vec3_port(pars.x), n, dx, table)
+    torch.cuda.synchronize()
+    assert table.overflow.item() == 1
+    table.overflow.zero_()
+    api.partition_for_particles(api.vec3_port(pars.x), n, dx, table, wide=True)
+    torch.cuda.synchronize()
+    assert table.overflow.item() == 0
+    ht = host_table(table)
+    tab_o = oracle.partition_build(P["x"], dx, oracle.table_size_for(max(n // 8, 1)))
+    ko = tab_o["active_keys"]
+    order = np.lexsort((ko[:, 2], ko[:, 1], ko[:, 0]))
+    assert ht["nblocks"] == tab_o["nblocks"] and np.array_equal(ht["active_keys"], ko[order])
+    assert np.abs(ht["active_keys"]).max() > 600
+    got = np.array([oracle.table_query(k, ht) for k in ht["active_keys"]])
+    assert np.array_equal(got, np.arange(ht["nblocks"]))
+    # the transfers do not care how the table was built: binned substep on it vs the oracle.  Positions are ~25 (6 000 cells of
+    # 1/256): an fp32 ulp there is 2e-6, 5e-4 of a cell — the parity rule's scales (max |x|) absorb that on both sides
+    bins = api.ParticleBins(n, max(ht["nblocks"] * 2, 64))
+    order_t = torch.empty(n, dtype=torch.int32, device="cuda")
+    api.bin_particles(pars, table, dx, bins, order_t)
+    grids = api.Grids(dx, ht["nblocks"])
+    api.clean_grid_blocks(grids, table)
+    api.p2g_transfer(bins, table, grids, synth.DT, api.model_fcr(P["volume"], E, NU))
+    o1, o2, omx, Po = run_oracle_on_table(oracle, P, ht, 1)
+    check_channels(grids.tiles.cpu().numpy(), o1, 1, "binned p2g far from the origin", GRID_RTOL, strict_frac=0.99)
+    mx = torch.zeros(1, device="cuda")
+    api.compute_grid_block_velocity(grids, table, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+    api.g2p_transfer(bins, table, grids, synth.DT)
+    perm = order_t.cpu().numpy()
+    check_particles({k: bins.attr(k).cpu().numpy() for k in "xvCF"}, {k: Po[k][perm] for k in "xvCF"}, dx, "binned g2p far from the origin")
+    assert int(bins.status.item()) == 0
+
+
 def test_partition_empty_and_aosoa_port(oracle):
     from zpc_b200 import api
     table = api.HashTable(64)

@@ -421,8 +421,8 @@ def sg_reorder_morton(sg, stream=None):
     return map_
 
 
-def sg_partition_for_particles(x_port, n, sg, stream=None, enlarge=(0, 2)):
-    _two_phase(lib().zpcb200_sg_partition_build, (x_port, C.c_size_t(n), sg.view(), C.c_int(enlarge[0]), C.c_int(enlarge[1]),
+def sg_partition_for_particles(x_port, n, sg, stream=None, enlarge=(0, 2), wide=False):
+    _two_phase(lib().zpcb200_sg_partition_build_wide if wide else lib().zpcb200_sg_partition_build, (x_port, C.c_size_t(n), sg.view(), C.c_int(enlarge[0]), C.c_int(enlarge[1]),
                                                   C.c_void_p(sg.table.overflow.data_ptr())), (), stream)
 
 
@@ -631,10 +631,10 @@ class IndexBuckets:
         return self.table.size()
 
 
-def index_buckets_for_particles(x_port, n, dx, displacement=0.5, stream=None, device="cuda", expected_cells=None):
+def index_buckets_for_particles(x_port, n, dx, displacement=0.5, stream=None, device="cuda", expected_cells=None, wide=False):
     """index_buckets_for_particles(policy, particles, dx, displacement) (simulation/particle/Query.tpp:9-58)"""
     ib = IndexBuckets(n, dx, device, expected_cells)
-    _two_phase(lib().zpcb200_index_buckets_build, (x_port, C.c_size_t(n), C.c_float(dx), C.c_float(displacement), ib.table.view(),
+    _two_phase(lib().zpcb200_index_buckets_build_wide if wide else lib().zpcb200_index_buckets_build, (x_port, C.c_size_t(n), C.c_float(dx), C.c_float(displacement), ib.table.view(),
                                                    C.c_void_p(ib.counts.data_ptr()), C.c_void_p(ib.offsets.data_ptr()),
                                                    C.c_void_p(ib.indices.data_ptr()), C.c_void_p(ib.table.overflow.data_ptr())), (),
                stream, device)
@@ -691,9 +691,10 @@ class LBvh:
 
 
 # ---- functors as free functions (policy = stream holder; all calls asynchronous) -------------------
-def partition_for_particles(x_port, n, dx, table, stream=None, enlarge=(0, 2)):
-    """SparsityCompute.tpp:6-24 / SparsityOp.hpp:41-112 (CleanSparsity, ComputeSparsity, EnlargeSparsity{lo,hi})."""
-    _two_phase(lib().zpcb200_partition_build, (x_port, C.c_size_t(n), C.c_float(dx), table.view(),
+def partition_for_particles(x_port, n, dx, table, stream=None, enlarge=(0, 2), wide=False):
+    """SparsityCompute.tpp:6-24 / SparsityOp.hpp:41-112 (CleanSparsity, ComputeSparsity, EnlargeSparsity{lo,hi}).
+    wide: 64-bit block codes (block coordinates up to +-2^20 instead of +-512)."""
+    _two_phase(lib().zpcb200_partition_build_wide if wide else lib().zpcb200_partition_build, (x_port, C.c_size_t(n), C.c_float(dx), table.view(),
                                                C.c_int(enlarge[0]), C.c_int(enlarge[1]),
                                                C.c_void_p(table.overflow.data_ptr())), (), stream)
 
