@@ -18,16 +18,27 @@ def _rel(a, b, floor):
     return float((np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)).max())
 
 
-def multi_gpu_parity(s=24, G=64, steps=6, rebin_every=3, migrate=False, e2e=False, transport="auto", rtol=5e-5, graph=False):
-    """-> dict(ok, world, steps, max_err per attribute, max_vel_err, transport, shared_blocks_rank0, migrated)"""
+def multi_gpu_parity(s=None, G=None, steps=6, rebin_every=3, migrate=False, e2e=False, transport="auto", rtol=5e-5, graph=False):
+    """-> dict(ok, world, steps, max_err per attribute, max_vel_err, transport, shared_blocks_rank0, migrated)
+
+    The cloud grows with the world size: every x-slab is at least 12 cells = 3 blocks wide (24^3 cells up to 2 ranks, 48^3 at 4, 96^3 at
+    8), so that a block and its ring are shared with at most ZPCB200_HALO_K = 4 other ranks — the fused halo's documented limit; thinner
+    slabs raise ZPC_HALO_TOO_MANY_PEERS (a 24^3 cloud on 8 ranks did).  dt scales with dx: the same CFL numbers and the same motion in cells
+    per substep at every size."""
     rank, world = dist.get_rank(), dist.get_world_size()
+    if s is None:
+        s = max(24, 12 * world)
+    if G is None:
+        G = 64
+        while G < s + 16:
+            G *= 2
     full = synth.elastic_cube(s, G, jitter_F=0.03, jitter_C=0.3)
     full["v"] *= 6.0                                  # particles cross cells, blocks and the slab cut
     n0 = full["m"].shape[0]
     full["m"] = (full["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)   # identity tag
     c0, c1 = synth.slab_cell_range(s, rank, world)
     P = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
-    dt = synth.DT * 10
+    dt = synth.DT * 10 * 64.0 / G
     sol = DistMpmSolver(P, P["dx"], P["volume"], dt, synth.GRAVITY, mode=1, rebin_every=rebin_every, transport=transport,
                         layout="aos" if e2e else "binned")
     if e2e:
@@ -55,8 +66,8 @@ def multi_gpu_parity(s=24, G=64, steps=6, rebin_every=3, migrate=False, e2e=Fals
             sol.substep()
     torch.cuda.synchronize()
     mine = {k: hin[k].numpy() for k in ("x", "v", "m", "C", "F")} if e2e else sol.local.particles_host()
-    gathered = [None] * world
-    dist.all_gather_object(gathered, mine)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)       # only rank 0 compares
     mx = float(sol.max_vel_sqr().item())
     moved_all = torch.tensor([moved], device="cuda", dtype=torch.int64)
     dist.all_reduce(moved_all)
