@@ -325,16 +325,17 @@ def main():
             gbs = bpp * n_local / (per_step[k] * 1e-3) / 1e9
             kern[k] = dict(ms=per_step[k], algorithmic_gbps=gbs, frac=gbs / hbm_peak)
     # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this config (per launch)
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if tr.get("config") == args.config and world == 1 and args.model == "fcr":
             traffic = tr["kernels"]["p2g_binned_kernel"]["dram_bytes"]
+            traffic_src = "profiles/r02_traffic.json: " + tr.get("source", "")   # a capture of this command under ncu, not this run
     except Exception:
         pass
     dom = "p2g"
     roof = dict(bound="hbm", kernel="p2g_binned_kernel", achieved=kern.get(dom, {}).get("algorithmic_gbps"), peak=hbm_peak, unit="GB/s",
-                frac=kern.get(dom, {}).get("frac"), traffic=traffic, peak_source=peak_src,
+                frac=kern.get(dom, {}).get("frac"), traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                 algorithmic_bytes_per_launch=bytes_pp[dom] * n_local)
     fused_bpp = sum(bytes_pp.values())
     fused_gbps = fused_bpp * n_local / (fused_ms * 1e-3) / 1e9 if fused_ms else None

@@ -514,6 +514,12 @@ int zpcb200_sg_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src
 int zpcb200_sg_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_fixed_corotated model,
                                    zpc_stream_t stream);
 int zpcb200_sg_g2p_apic_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream);
+/* the other constitutive models on the binned SparseGrid path: model_kind = ZPC_MODEL_*, model -> the matching struct (host memory);
+ * scalar = logJp (Drucker-Prager, NACC: read and written back) or J (equation of state: read) per particle in BIN order — permute it
+ * with the order a re-bin returns (zpcb200_gather_f32) —, NULL for the F-only models.  zpcb200_sg_g2p_apic_eos_binned advances J. */
+int zpcb200_sg_p2g_apic_model_binned(zpc_bins_view bins, float *scalar, zpc_sparsegrid_view sg, float dt, int model_kind,
+                                     const void *model, zpc_stream_t stream);
+int zpcb200_sg_g2p_apic_eos_binned(zpc_bins_view bins, float *J, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream);
 
 /* ---- multi-GPU one-ring halo, fused (SURVEY §8(e), §2.1 last paragraph; no reference counterpart) --------------------------
  * Every rank owns a receive buffer that its peers can address (peer-mapped over NVLink: torch symmetric memory, cudaIpc or

@@ -624,6 +624,52 @@ def test_sparsegrid_runs_every_model(oracle, model):
         check_channels(pars.J.cpu().numpy()[:, None], z["J"][:, None], 1, "sg eos J", 3e-5)
 
 
+@pytest.mark.parametrize("model", ["vonmises", "sand", "nacc", "eos"])
+def test_sparsegrid_binned_path_runs_every_model(oracle, model):
+    """zpcb200_sg_p2g_apic_model_binned / zpcb200_sg_g2p_apic_eos_binned: the binned kernels instantiated for SparseGrid<3,f32,8>
+    (bins = octants) with the model as the record phase's template parameter; same reference-generated goldens and tolerances as the
+    any-order SparseGrid test above; logJp / J live next to the bins in bin order"""
+    from tests.test_gpu_sparsegrid import _build, _host_table, _nodes
+    from zpc_b200 import api
+    name = {"vonmises": "mpm_cube6_vonmises", "sand": "mpm_cube6_sand", "nacc": "mpm_cube6_nacc", "eos": "mpm_cube6_eos"}[model]
+    z = np.load(os.path.join(G, name + ".npz"))
+    P = synth.elastic_cube(int(z["s"]), int(z["G"]), **dict(ast.literal_eval(str(z["kw"]))))
+    n, dx = P["x"].shape[0], P["dx"]
+    m = {"vonmises": lambda: api.model_vonmises(P["volume"], E, NU, float(z["ys"])),
+         "sand": lambda: api.model_drucker_prager(P["volume"], E, NU, SAND["cohesion"], SAND["beta"], SAND["volumeCorrection"], SAND["yieldSurface"]),
+         "nacc": lambda: api.model_nacc(P["volume"], NACC["E"], NACC["nu"], NACC["fa"], NACC["xi"], NACC["beta"], NACC["hardeningOn"]),
+         "eos": lambda: api.model_eos(P["volume"], 4.0e4, 7.15, 0.01)}[model]()
+    pars, sg = _build(P)
+    t = _host_table(sg)
+    nb = t["nblocks"]
+    bins = api.ParticleBins(n, 8 * nb + 64)
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    api.sg_bin_particles(pars, sg, bins, order)
+    perm = order.cpu().numpy()
+    if model in ("sand", "nacc"):
+        bins.logJp = torch.from_numpy(z["logJp_in"][perm].copy()).cuda()
+    if model == "eos":
+        bins.J = torch.from_numpy(z["J_in"][perm].copy()).cuda()
+    api.sg_clean(sg)
+    api.sg_p2g_transfer(bins, sg, synth.DT, m)
+    torch.cuda.synchronize()
+    assert int(bins.status.item()) == 0
+    g1 = sg.grid[:nb].cpu().numpy()
+    code_o, val_o = _nodes(z["active_keys"] * 4, z["grid_p2g"], 4)
+    code_s, val_s = _nodes(t["active_keys"], g1, 8)
+    pos = np.searchsorted(code_s, code_o)
+    assert (pos < code_s.shape[0]).all() and np.array_equal(code_s[pos], code_o)
+    rhs = {"vonmises": RTOL_STRESS, "sand": RTOL_STRESS, "nacc": 1e-3, "eos": RTOL}[model]
+    check_channels(val_s[pos], val_o, 1, "sg binned p2g " + model, [RTOL] * 4 + [rhs] * 3)
+    if model in ("sand", "nacc"):
+        assert np.abs(bins.logJp.cpu().numpy() - z["logJp"][perm]).max() <= 2e-5
+    if model == "eos":
+        mx = torch.zeros(1, device="cuda")
+        api.sg_compute_grid_velocity(sg, synth.DT, (0.0, synth.GRAVITY, 0.0), 1, mx)
+        api.sg_g2p_transfer(bins, sg, synth.DT, model=m)
+        check_channels(bins.J.cpu().numpy()[:, None], z["J"][perm][:, None], 1, "sg binned eos J", 3e-5)
+
+
 def test_grid_momentum_functors(oracle):
     """zpcb200_grid_momentum_to_velocity / zpcb200_grid_angular_momentum (GridOp.hpp:184-262) on the grid our own P2G leaves, against
     the oracle on that same grid: velocities bit for bit (one IEEE division and three products per cell), max |v|^2 to an ulp of the

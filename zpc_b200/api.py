@@ -443,9 +443,15 @@ def sg_rebin_particles(src, sg, dst, stream=None, order_out=None):
 
 def sg_p2g_transfer(pars, sg, dt, model, stream=None):
     if isinstance(pars, ParticleBins):
-        if not isinstance(model, zpc_fixed_corotated):
-            raise ZpcError("the binned SparseGrid P2G serves the fixed-corotated model; use the any-order entry for the others")
-        _check(lib().zpcb200_sg_p2g_apic_fcr_binned(pars.view(), sg.view(), C.c_float(dt), model, _stream_ptr(stream)), "sg_p2g(binned)")
+        if isinstance(model, zpc_fixed_corotated):
+            _check(lib().zpcb200_sg_p2g_apic_fcr_binned(pars.view(), sg.view(), C.c_float(dt), model, _stream_ptr(stream)), "sg_p2g(binned)")
+            return
+        kind = _MODEL_KIND[type(model)]
+        side = pars.logJp if kind in (2, 3) else pars.J if kind == 4 else None
+        if kind >= 2 and side is None:
+            raise ValueError("this model needs its per-particle scalar (logJp / J) in bin order next to the bins")
+        _check(lib().zpcb200_sg_p2g_apic_model_binned(pars.view(), C.c_void_p(side.data_ptr() if side is not None else None), sg.view(),
+                                                      C.c_float(dt), C.c_int(kind), C.byref(model), _stream_ptr(stream)), "sg_p2g(model, binned)")
         return
     if isinstance(model, zpc_fixed_corotated):
         _check(lib().zpcb200_sg_p2g_apic_fcr(pars.view(), sg.view(), C.c_float(dt), model, _stream_ptr(stream)), "sg_p2g")
@@ -463,6 +469,10 @@ def sg_compute_grid_velocity(sg, dt, extf, mode, max_vel_sqr, stream=None):
 
 def sg_g2p_transfer(pars, sg, dt, stream=None, model=None):
     if isinstance(pars, ParticleBins):
+        if isinstance(model, zpc_equation_of_state):
+            _check(lib().zpcb200_sg_g2p_apic_eos_binned(pars.view(), C.c_void_p(pars.J.data_ptr()), sg.view(), C.c_float(dt), _stream_ptr(stream)),
+                   "sg_g2p(eos, binned)")
+            return
         _check(lib().zpcb200_sg_g2p_apic_binned(pars.view(), sg.view(), C.c_float(dt), _stream_ptr(stream)), "sg_g2p(binned)")
         return
     if isinstance(model, zpc_equation_of_state):

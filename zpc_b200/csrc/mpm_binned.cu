@@ -1549,36 +1549,88 @@ int zpcb200_sg_rebin_particles(void *temp, size_t *temp_bytes, zpc_bins_view src
   zpc_particles_view none = {};
   return bin_pipeline<true>(temp, temp_bytes, none, src.pars.base, src.pars.size, BinGridSparse{sg.table}, dx, dst, order_out, (cudaStream_t)stream);
 }
-int zpcb200_sg_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_fixed_corotated model, zpc_stream_t stream) {
+}  // extern "C"
+template <int MODEL>
+static int sg_p2g_binned_launch(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, float volume, float E, float nu, float yield_stress,
+                                float *scalar, zpcm::PlasticPrm pp, zpc_stream_t stream) {
   float dx;
   if (!sgb_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
   if (sg.numChannels < 7 || !sg.grid || !sgb_table_ok(sg.table) || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
     return ZPCB200_E_BADARG;
   static std::atomic<bool> attr_set{false};
   if (!attr_set.load(std::memory_order_acquire)) {
-    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4, 0, BinGridSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
+    ZPC_CUDA(cudaFuncSetAttribute(p2g_binned_kernel<4, MODEL, BinGridSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2GSmem)));
     attr_set.store(true, std::memory_order_release);
   }
-  float mu, lam;
-  zpcm::lame_host(model.E, model.nu, mu, lam);
+  float mu = 0.f, lam = 0.f;
+  if (MODEL != 4) zpcm::lame_host(E, nu, mu, lam);
   const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
-  p2g_binned_kernel<4, 0, BinGridSparse><<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
+  p2g_binned_kernel<4, MODEL, BinGridSparse><<<bins.binCapacity, P2G_NT, sizeof(P2GSmem), (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart, bins.cellOrderValid,
-      BinGridSparse{sg.table}, sg.grid, dx, dt, model.volume, mu, lam, 1, 0.f, nullptr, zpcm::PlasticPrm{}, bins.status, zpc_halo_view{}, sg.numChannels);
+      BinGridSparse{sg.table}, sg.grid, dx, dt, volume, mu, lam, 1, yield_stress, scalar, pp, bins.status, zpc_halo_view{}, sg.numChannels);
   ZPC_CHECK_LAUNCH();
   return ZPCB200_OK;
 }
-int zpcb200_sg_g2p_apic_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream) {
+extern "C" {
+int zpcb200_sg_p2g_apic_fcr_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_fixed_corotated model, zpc_stream_t stream) {
+  return sg_p2g_binned_launch<0>(bins, sg, dt, model.volume, model.E, model.nu, 0.f, nullptr, zpcm::PlasticPrm{}, stream);
+}
+/* the other four constitutive models on the binned SparseGrid path: model_kind = ZPC_MODEL_*, model -> the matching struct (host memory),
+ * scalar = logJp (Drucker-Prager, NACC; read and written) or J (equation of state; read) per particle in BIN order, NULL otherwise */
+int zpcb200_sg_p2g_apic_model_binned(zpc_bins_view bins, float *scalar, zpc_sparsegrid_view sg, float dt, int model_kind, const void *model,
+                                     zpc_stream_t stream) {
+  if (!model) return ZPCB200_E_BADARG;
+  switch (model_kind) {
+    case ZPC_MODEL_FIXED_COROTATED: {
+      const auto &m = *(const zpc_fixed_corotated *)model;
+      return sg_p2g_binned_launch<0>(bins, sg, dt, m.volume, m.E, m.nu, 0.f, nullptr, zpcm::PlasticPrm{}, stream);
+    }
+    case ZPC_MODEL_VONMISES: {
+      const auto &m = *(const zpc_vonmises_fixed_corotated *)model;
+      return sg_p2g_binned_launch<1>(bins, sg, dt, m.volume, m.E, m.nu, m.yieldStress, nullptr, zpcm::PlasticPrm{}, stream);
+    }
+    case ZPC_MODEL_DRUCKER_PRAGER: {
+      const auto &m = *(const zpc_drucker_prager *)model;
+      if (!scalar) return ZPCB200_E_BADARG;
+      return sg_p2g_binned_launch<2>(bins, sg, dt, m.volume, m.E, m.nu, 0.f, scalar,
+                                     zpcm::PlasticPrm{m.cohesion, m.beta, m.yieldSurface, 0.f, m.volumeCorrection}, stream);
+    }
+    case ZPC_MODEL_NACC: {
+      const auto &m = *(const zpc_nacc *)model;
+      if (!scalar || m.dim != 3) return ZPCB200_E_BADARG;
+      return sg_p2g_binned_launch<3>(bins, sg, dt, m.volume, m.E, m.nu, 0.f, scalar,
+                                     zpcm::PlasticPrm{zpcm::nacc_bulk_host(m.E, m.nu), m.xi, m.beta, zpcm::nacc_msqr_host(m.fa, m.dim), m.hardeningOn}, stream);
+    }
+    case ZPC_MODEL_EOS: {
+      const auto &m = *(const zpc_equation_of_state *)model;
+      if (!scalar) return ZPCB200_E_BADARG;
+      return sg_p2g_binned_launch<4>(bins, sg, dt, m.volume, 0.f, 0.f, 0.f, scalar, zpcm::PlasticPrm{m.bulk, m.viscosity, 0.f, 0.f, 0}, stream);
+    }
+  }
+  return ZPCB200_E_BADARG;
+}
+}  // extern "C"
+template <bool EOS>
+static int sg_g2p_binned_launch(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, float *scalar, zpc_stream_t stream) {
   float dx;
   if (!sgb_uniform_dx(sg, dx)) return ZPCB200_E_UNSUPPORTED;
   if (sg.numChannels < 4 || !sg.grid || !sgb_table_ok(sg.table) || bins.pars.numChannels != NCH || !bins.binStart || !bins.binKey || !bins.numBins)
     return ZPCB200_E_BADARG;
   const bool cache = bins.cellOrder && bins.cellStart && bins.cellOrderValid;
-  g2p_binned_staged_kernel<64, false, BinGridSparse><<<bins.binCapacity, 64, 0, (cudaStream_t)stream>>>(
+  g2p_binned_staged_kernel<64, EOS, BinGridSparse><<<bins.binCapacity, 64, 0, (cudaStream_t)stream>>>(
       bins.pars.base, bins.binStart, bins.binKey, bins.numBins, cache ? bins.cellOrder : nullptr, bins.cellStart, BinGridSparse{sg.table}, sg.grid,
-      sg.numChannels, dx, dt, nullptr, bins.status);
+      sg.numChannels, dx, dt, scalar, bins.status);
   ZPC_CHECK_LAUNCH();
   if (cache) ZPC_CUDA(cudaMemsetAsync(bins.cellOrderValid, 1, sizeof(int), (cudaStream_t)stream));  // non-zero = valid
   return ZPCB200_OK;
+}
+extern "C" {
+int zpcb200_sg_g2p_apic_binned(zpc_bins_view bins, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream) {
+  return sg_g2p_binned_launch<false>(bins, sg, dt, nullptr, stream);
+}
+/* EquationOfStateConfig: J (one float per particle in bin order) is advanced instead of F (G2P.hpp:69-73) */
+int zpcb200_sg_g2p_apic_eos_binned(zpc_bins_view bins, float *J, zpc_sparsegrid_view sg, float dt, zpc_stream_t stream) {
+  if (!J) return ZPCB200_E_BADARG;
+  return sg_g2p_binned_launch<true>(bins, sg, dt, J, stream);
 }
 }  // extern "C"

@@ -39,8 +39,12 @@ def multi_gpu_parity(s=None, G=None, steps=6, rebin_every=3, migrate=False, e2e=
     c0, c1 = synth.slab_cell_range(s, rank, world)
     P = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
     dt = synth.DT * 10 * 64.0 / G
+    # blocks of a slab with the partition's extra ring (EnlargeSparsity{-1,3}): thin slabs hold many more blocks per particle than
+    # the solver's default capacity (n / 256) assumes
+    w_cells = (c1 - c0) // (s * s)
+    eb = max((w_cells // 4 + 6) * (s // 4 + 6) ** 2, 1024)
     sol = DistMpmSolver(P, P["dx"], P["volume"], dt, synth.GRAVITY, mode=1, rebin_every=rebin_every, transport=transport,
-                        layout="aos" if e2e else "binned")
+                        layout="aos" if e2e else "binned", expected_blocks=eb)
     if e2e:
         hin = {k: torch.from_numpy(P[k].copy()).pin_memory() for k in ("x", "v", "m", "C", "F")}
         hout = {k: torch.empty_like(hin[k]).pin_memory() for k in ("x", "v", "C", "F")}
@@ -76,7 +80,7 @@ def multi_gpu_parity(s=None, G=None, steps=6, rebin_every=3, migrate=False, e2e=
     if rank == 0:
         got = {k: np.concatenate([g[k] for g in gathered]) for k in ("x", "v", "m", "C", "F")}
         one = MpmSolver(full, full["dx"], full["volume"], dt, synth.GRAVITY, mode=1, layout="binned", rebin_every=rebin_every,
-                        partition="with_rebin")
+                        partition="with_rebin", expected_blocks=max((s // 4 + 6) ** 3, 1024))
         for _ in range(steps):
             one.substep()
         want = one.particles_host()
