@@ -419,8 +419,10 @@ class DistMpmSolver:
         new = migrate_particles(aos, dest, self.group)
         moved = int((dest != dist.get_rank(self.group)).sum().item())
         P = {k: v for k, v in new.items()}
+        # same block capacity as before (the halo maps and receive segments are sized by it; the default, n / 256, is too small
+        # for thin slabs with their partition ring)
         kw = dict(gravity=L.extf[1], mode=L.mode, layout="binned", rebin_every=L.rebin_every, device=dev, partition="with_rebin",
-                  model=L.model, colliders=L.colliders)
+                  model=L.model, colliders=L.colliders, expected_blocks=L.block_cap)
         step_no = L.step_no
         self.local = MpmSolver(P, L.dx, L.model.volume, L.dt, **kw)
         self.local.step_no = step_no
