@@ -219,7 +219,7 @@ def main():
             graphed = multi_gpu_parity(transport=args.halo, graph=True) if (args.graph == "auto" and plain["transport"] == "fused") else None
             mg_parity = dict(ok=bool(plain["ok"] and moved["ok"] and (graphed is None or graphed["ok"])), substeps=plain,
                              substeps_with_migration=moved, substeps_as_cuda_graph=graphed,
-                             what="N-GPU sharded substeps vs the single-GPU solver on the same 110 592-particle cloud (particles cross the "
+                             what="N-GPU sharded substeps vs the single-GPU solver on the same cloud, 24^3 .. 96^3 cells by world size (particles cross the "
                                   "slab cuts), all particle attributes within 5e-5 after 6 substeps; zpc_b200/selfcheck.py")
         except Exception as ex:   # collective: raised on every rank alike
             mg_parity = dict(ok=False, error=repr(ex))

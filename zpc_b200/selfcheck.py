@@ -35,7 +35,13 @@ def multi_gpu_parity(s=None, G=None, steps=6, rebin_every=3, migrate=False, e2e=
     full = synth.elastic_cube(s, G, jitter_F=0.03, jitter_C=0.3)
     full["v"] *= 6.0                                  # particles cross cells, blocks and the slab cut
     n0 = full["m"].shape[0]
-    full["m"] = (full["m"] * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)   # identity tag
+    # identity tag in the mass: consecutive float32 values (2^23 + i) x a power of two near the physical mass — exact and distinct for
+    # up to 2^23 particles (a relative step of 0.1 / n0 collapses into duplicates beyond ~1.6 M particles, and the stable argsort below
+    # then pairs different particles)
+    assert n0 <= (1 << 23), n0
+    m0 = float(full["m"].mean())
+    full["m"] = ((1 << 23) + np.arange(n0, dtype=np.int64)).astype(np.float32) * np.float32(2.0 ** np.round(np.log2(m0 / (1 << 23))))
+    assert np.unique(full["m"]).size == n0
     c0, c1 = synth.slab_cell_range(s, rank, world)
     P = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
     dt = synth.DT * 10 * 64.0 / G
