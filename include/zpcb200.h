@@ -492,8 +492,10 @@ int zpcb200_g2p_apic_binned(zpc_bins_view bins, zpc_hashtable_view table, zpc_gr
 
 /* Kernel variants of the two binned functors (same results up to fp32 re-association; kept selectable so that each
  * can be measured and parity-tested).  p2g_sweep: 4 = a warp sweeps three cells at a time, lanes = 3 cells x 9 (x,y)
- * node columns, three z-nodes per lane (default); 6 = the atomic-free plane sweep (lanes = 10 cells x 3 x-planes, a private arena copy per
- * warp region, no shared-memory atomics); 3 = one cell at a time, lanes = the 27 nodes.  g2p_staged: 1 = the
+ * node columns, three z-nodes per lane; the fixed-corotated stress skips the Jacobi sweeps a whole warp has converged on (default);
+ * 5 = the same sweep on packed fp32 arithmetic (FFMA2); 6 = the atomic-free plane sweep (lanes = 10 cells x 3 x-planes, a private
+ * arena copy per warp region, no shared-memory atomics); 3 = one cell at a time, lanes = the 27 nodes, the reference's four Jacobi
+ * sweeps always.  g2p_staged: 1 = the
  * particle channels G2P reads are staged with TMA bulk copies in 64-thread CTAs (default; 128 / 256 select that CTA
  * size instead); 0 = plain loads, 256-thread CTAs.
  * -1 leaves a setting unchanged.  Environment defaults: ZPCB200_P2G_SWEEP, ZPCB200_G2P_STAGED.  Not thread-safe
