@@ -5,7 +5,7 @@
 //   CudaExecutionPolicy + free functions reduce / exclusive_scan / inclusive_scan / radix_sort / radix_sort_pair
 //       <- cuda/execution/ExecutionPolicy.cuh:362-912, execution/ExecutionPolicy.hpp:684-781
 //          (chained setters device().stream().sync(); sync defaults to true; errors are latched, never thrown)
-//   plus<T>, getmax<T>, getmin<T>          <- ZpcFunctional.hpp:60-117
+//   plus<T>, multiplies<T>, getmax<T>, getmin<T>  <- ZpcFunctional.hpp:60-117
 //   Vector<T>                               <- container/Vector.hpp            (device memory, getVal/setVal)
 //   HashTable (i32,3,int)                   <- container/HashTable.hpp:15-206  (tableSize = next_2pow(n) * 16)
 //   Grids (f32,3,4) {m, v, rhs}             <- geometry/Structure.hpp:140-260
@@ -31,6 +31,7 @@ namespace zsb200 {
 template <typename T = void> struct plus {};
 template <typename T = void> struct getmax {};
 template <typename T = void> struct getmin {};
+template <typename T = void> struct multiplies {};
 
 template <typename T> struct Vector {  // device vector
   T *_ptr{nullptr};
@@ -115,6 +116,9 @@ struct CudaExecutionPolicy {
     if constexpr (std::is_same_v<Op<U>, plus<U>>) {
       ZSB_DISPATCH_T(zpcb200_reduce_sum_i32(t, b, in, out, n, _stream), zpcb200_reduce_sum_u32(t, b, in, out, n, _stream),
                      zpcb200_reduce_sum_i64(t, b, in, out, n, _stream), zpcb200_reduce_sum_f32(t, b, in, out, n, _stream))
+    } else if constexpr (std::is_same_v<Op<U>, multiplies<U>>) {
+      ZSB_DISPATCH_T(zpcb200_reduce_prod_i32(t, b, in, out, n, _stream), zpcb200_reduce_prod_u32(t, b, in, out, n, _stream),
+                     zpcb200_reduce_prod_i64(t, b, in, out, n, _stream), zpcb200_reduce_prod_f32(t, b, in, out, n, _stream))
     } else if constexpr (std::is_same_v<Op<U>, getmax<U>>) {
       ZSB_DISPATCH_T(zpcb200_reduce_max_i32(t, b, in, out, n, _stream), zpcb200_reduce_max_u32(t, b, in, out, n, _stream),
                      zpcb200_reduce_max_i64(t, b, in, out, n, _stream), zpcb200_reduce_max_f32(t, b, in, out, n, _stream))

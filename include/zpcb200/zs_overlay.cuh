@@ -3,7 +3,7 @@
 //
 //   zs::B200ExecutionPolicy / zs::b200_exec()   a CudaExecutionPolicy whose reduce / exclusive_scan / inclusive_scan /
 //       radix_sort / radix_sort_pair members go to libzpcb200 when the iterators are raw pointers or zs::Vector iterators and
-//       the operator is plus (reduce: plus / getmin / getmax) on {i32, u32, i64, f32, f64} — every other call, and every
+//       the operator is plus (reduce: plus / multiplies / getmin / getmax) on {i32, u32, i64, f32, f64} — every other call, and every
 //       policy(range, functor) launch, stays the reference's (members are hidden, not removed).  Generic code that is templated
 //       on the policy (zs::radix_sort_pair(pol, ...), LBvh::build(pol, ...), ...) needs no change: pass b200_exec().
 //   zs::b200::partition_for_particles / clean_grid_blocks / p2g / compute_grid_block_velocity / g2p
@@ -61,10 +61,11 @@ namespace zs {
     }
     using prim2_t = int (*)(void *, size_t *, zpc_port, zpc_port, size_t, zpc_stream_t);
     inline prim2_t reduce_entry(int op, int kind) {
-      static const prim2_t t[3][5] = {
+      static const prim2_t t[4][5] = {
           {zpcb200_reduce_sum_i32, zpcb200_reduce_sum_u32, zpcb200_reduce_sum_i64, zpcb200_reduce_sum_f32, zpcb200_reduce_sum_f64},
           {zpcb200_reduce_min_i32, zpcb200_reduce_min_u32, zpcb200_reduce_min_i64, zpcb200_reduce_min_f32, zpcb200_reduce_min_f64},
-          {zpcb200_reduce_max_i32, zpcb200_reduce_max_u32, zpcb200_reduce_max_i64, zpcb200_reduce_max_f32, zpcb200_reduce_max_f64}};
+          {zpcb200_reduce_max_i32, zpcb200_reduce_max_u32, zpcb200_reduce_max_i64, zpcb200_reduce_max_f32, zpcb200_reduce_max_f64},
+          {zpcb200_reduce_prod_i32, zpcb200_reduce_prod_u32, zpcb200_reduce_prod_i64, zpcb200_reduce_prod_f32, zpcb200_reduce_prod_f64}};
       return t[op][kind];
     }
     inline prim2_t scan_entry(bool inclusive, int kind) {
@@ -74,11 +75,12 @@ namespace zs {
                                        zpcb200_inclusive_scan_sum_f32, zpcb200_inclusive_scan_sum_f64}};
       return t[inclusive ? 1 : 0][kind];
     }
-    template <class Op, class T> constexpr int reduce_op() {  // 0 plus, 1 min, 2 max, -1 other
+    template <class Op, class T> constexpr int reduce_op() {  // 0 plus, 1 min, 2 max, 3 multiplies, -1 other
       using O = remove_cvref_t<Op>;
       if constexpr (is_same_v<O, plus<T>> || is_same_v<O, plus<void>>) return 0;
       else if constexpr (is_same_v<O, getmin<T>> || is_same_v<O, getmin<void>>) return 1;
       else if constexpr (is_same_v<O, getmax<T>> || is_same_v<O, getmax<void>>) return 2;
+      else if constexpr (is_same_v<O, multiplies<T>> || is_same_v<O, multiplies<void>>) return 3;
       else return -1;
     }
     inline zpc_port port_of(zpc_port p) { return p; }

@@ -204,3 +204,23 @@ def test_dist_solver_control_flow_over_gloo():
         p.join(300)
         assert p.exitcode == 0
     assert sorted(q.get(timeout=10) for _ in range(2)) == [0, 1]
+
+
+def test_self_check_cloud_and_identity_tags():
+    """zpc_b200/selfcheck.py: the check's cloud keeps every slab >= 3 blocks wide for 2..8 ranks, and its identity tags (masses) are
+    exact and distinct at the largest size — with the round-1 tag (a relative step of 0.1 / n) the 7 M-particle cloud of an 8-rank
+    run held duplicates and the comparison paired different particles"""
+    import numpy as np
+    from zpc_b200 import selfcheck, synth
+    for world in (2, 4, 8):
+        s, G = selfcheck.check_cloud(world)
+        assert s // world >= 12 and G >= s + 16
+        c0, c1 = synth.slab_cell_range(s, world - 1, world)
+        assert (c1 - c0) // (s * s) >= 12
+    s, G = selfcheck.check_cloud(8)
+    n0 = 8 * s ** 3
+    m = selfcheck.identity_masses(n0, 2.4e-4)
+    assert m.dtype == np.float32 and np.unique(m).size == n0 and 0.5 <= m[0] / 2.4e-4 <= 2.0 and m[-1] < 2 * m[0] * 1.0001
+    old = (np.float32(2.4e-4) * (1.0 + 0.1 * np.arange(n0) / n0)).astype(np.float32)
+    assert np.unique(old).size < n0
+

@@ -18,6 +18,24 @@ def _rel(a, b, floor):
     return float((np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)).max())
 
 
+def identity_masses(n0, m0):
+    """Identity tag in the mass: consecutive float32 values (2^23 + i) x a power of two near the physical mass m0 — exact and distinct
+    for up to 2^23 particles.  (A relative step of 0.1 / n0 collapses into duplicates beyond ~1.6 M particles, and the stable argsort
+    that pairs the N-GPU result with the single-GPU one then pairs different particles: the 96^3 cloud of an 8-rank check did.)"""
+    if n0 > (1 << 23):
+        raise ValueError("identity tags cover 2^23 particles")
+    return ((1 << 23) + np.arange(n0, dtype=np.int64)).astype(np.float32) * np.float32(2.0 ** np.round(np.log2(m0 / (1 << 23))))
+
+
+def check_cloud(world):
+    """(s, G): cells per side of the check's cube and of its domain for a world size — every x-slab at least 12 cells = 3 blocks wide"""
+    s = max(24, 12 * world)
+    G = 64
+    while G < s + 16:
+        G *= 2
+    return s, G
+
+
 def multi_gpu_parity(s=None, G=None, steps=6, rebin_every=3, migrate=False, e2e=False, transport="auto", rtol=5e-5, graph=False):
     """-> dict(ok, world, steps, max_err per attribute, max_vel_err, transport, shared_blocks_rank0, migrated)
 
@@ -26,22 +44,12 @@ def multi_gpu_parity(s=None, G=None, steps=6, rebin_every=3, migrate=False, e2e=
     slabs raise ZPC_HALO_TOO_MANY_PEERS (a 24^3 cloud on 8 ranks did).  dt scales with dx: the same CFL numbers and the same motion in cells
     per substep at every size."""
     rank, world = dist.get_rank(), dist.get_world_size()
-    if s is None:
-        s = max(24, 12 * world)
-    if G is None:
-        G = 64
-        while G < s + 16:
-            G *= 2
+    if s is None or G is None:
+        s, G = check_cloud(world)
     full = synth.elastic_cube(s, G, jitter_F=0.03, jitter_C=0.3)
     full["v"] *= 6.0                                  # particles cross cells, blocks and the slab cut
     n0 = full["m"].shape[0]
-    # identity tag in the mass: consecutive float32 values (2^23 + i) x a power of two near the physical mass — exact and distinct for
-    # up to 2^23 particles (a relative step of 0.1 / n0 collapses into duplicates beyond ~1.6 M particles, and the stable argsort below
-    # then pairs different particles)
-    assert n0 <= (1 << 23), n0
-    m0 = float(full["m"].mean())
-    full["m"] = ((1 << 23) + np.arange(n0, dtype=np.int64)).astype(np.float32) * np.float32(2.0 ** np.round(np.log2(m0 / (1 << 23))))
-    assert np.unique(full["m"]).size == n0
+    full["m"] = identity_masses(n0, float(full["m"].mean()))
     c0, c1 = synth.slab_cell_range(s, rank, world)
     P = {k: (np.ascontiguousarray(v[8 * c0:8 * c1]) if isinstance(v, np.ndarray) else v) for k, v in full.items()}
     dt = synth.DT * 10 * 64.0 / G
