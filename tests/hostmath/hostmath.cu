@@ -62,6 +62,20 @@ void hm_arena(int n, float dx, const float *x, int *corner, float *local, float 
     }
   }
 }
+// the same through the branch-free exact division of the binned G2P (arena_init<true>: 1/dx and two FMAs)
+void hm_arena_fastdiv(int n, float dx, const float *x, int *corner, float *local, float *w) {
+  const float dx_inv = 1.0f / dx;
+  for (int p = 0; p < n; ++p) {
+    zpcm::Arena a;
+    float pos[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+    zpcm::arena_init<true>(a, dx, pos, dx_inv);
+    for (int d = 0; d < 3; ++d) {
+      corner[3 * p + d] = a.corner[d];
+      local[3 * p + d] = a.local[d];
+      for (int k = 0; k < 3; ++k) w[9 * p + 3 * d + k] = a.w[d][k];
+    }
+  }
+}
 // the per-node functions of the LBvh build (what lbvh.cu's kernels call), run index by index with a host stable sort and scan in
 // place of the device primitives; box = the padded whole box (6 floats).  n > 2.
 void hm_lbvh_build(int n, const float *prims, const float *box, int *auxIndices, int *parents, int *levels, int *leafInds) {

@@ -240,3 +240,25 @@ def test_device_stencil_on_the_host_is_bit_exact(oracle, hostmath):
     assert np.array_equal(corner, cn)
     assert np.array_equal(_bits(local), _bits((lp * dx).astype(np.float32)))
     assert np.array_equal(_bits(w.reshape(n, 3, 3)), _bits(np.stack([w0, w1, w2], axis=2)))
+
+
+@pytest.mark.parametrize("dx", [1.0 / 64, 1.0 / 256, 0.01, 0.0371, 1.0 / 3])
+def test_exact_division_stencil_is_the_division_stencil(hostmath, dx):
+    """arena_init<true> (the binned G2P: x / dx as 1/dx and two FMAs, no slow-path branch) against arena_init (the IEEE division the
+    reference writes): corner, local offset and the nine weights bit for bit — positions near the origin, far from it (6 000 cells
+    out, where an ulp is 5e-4 of a cell), negative, and exactly on cell boundaries, for power-of-two and other cell sizes"""
+    rs = np.random.RandomState(11)
+    dx = np.float32(dx)
+    parts = [rs.uniform(-0.3, 1.3, (200000, 3)), rs.uniform(-200.0, 200.0, (200000, 3)), rs.uniform(5999, 6001, (100000, 3)) * float(dx),
+             (rs.randint(-5000, 5000, (100000, 3)) + rs.choice([0.0, 0.5], (100000, 3))) * float(dx)]
+    x = np.concatenate(parts).astype(np.float32)
+    n = x.shape[0]
+    out = []
+    for fn in (hostmath.hm_arena, hostmath.hm_arena_fastdiv):
+        corner, local, w = np.empty((n, 3), np.int32), np.empty((n, 3), np.float32), np.empty((n, 9), np.float32)
+        fn(C.c_int(n), C.c_float(dx), _p(x), _p(corner), _p(local), _p(w))
+        out.append((corner, local, w))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(_bits(out[0][1]), _bits(out[1][1]))
+    assert np.array_equal(_bits(out[0][2]), _bits(out[1][2]))
+
