@@ -319,8 +319,9 @@ int zpcb200_grid_update_bc(zpc_grids_view grids, zpc_hashtable_view table, float
  * (simulation/mpm/ImplicitMPM.hpp:32-59): gridv / gridr are the DOF vectors of dof_view<space, 3>(Vector<float>), three floats
  * per node, node = blockno * 64 + cellid.  C is gathered from gridv, the trial F = (I + dt C) F stays in registers (particles are
  * not modified, logJp is read only), W * (P F^T vol * D_inv) * (x_i - x_p) is ADDED to gridr (clear it first, like DofFill).
- * model_kind selects the struct `model` points to (host memory).  The reference's dof_view types do not compile under gcc 13, so
- * this entry is checked against a restatement of the source only (oracle zo_g2p2g: parity unpinned). */
+ * model_kind selects the struct `model` points to (host memory).  Parity: against the reference's own functor run on cuda_exec() with
+ * a plain three-floats-per-node DOF view (oracle/ref_driver_cuda.cu; its dof_view types do not compile under gcc 13, the functor only
+ * needs get / ref) for the fixed-corotated and von Mises models, against the restated oracle zo_g2p2g for all five. */
 int zpcb200_g2p2g_apic(zpc_particles_view pars, zpc_hashtable_view table, float dx, float dt, int model_kind, const void *model,
                        const float *gridv, float *gridr, zpc_stream_t stream);
 

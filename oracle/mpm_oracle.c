@@ -823,8 +823,10 @@ void zo_g2p(int n, float *x, float *v, float *C, float *F, float dx, float dt, i
 /* G2P2GTransfer::operator() (simulation/transfer/G2P2G.hpp:49-141): the matrix-free force evaluation of the implicit solver —
  * gather C from a grid DOF vector gridv (3 floats per node, node = blockno * 64 + cellid, :62-76), F_trial = (I + dt C) F
  * (:100-103, not stored), stress of the trial state (:104-121), scatter W * (contrib * D_inv) * xixp into the DOF vector gridr
- * (:123-138).  PARITY UNPINNED: the reference's dof_view types (types/View.h) do not compile under gcc 13 here, so no
- * reference output exists for this functor; this is a restatement of the source, checked against nothing but itself.
+ * (:123-138).  The reference's dof_view types (types/View.h) do not compile under gcc 13 here, so the HOST build of the reference
+ * cannot run this functor; it is pinned on the GPU instead (round 2): oracle/ref_driver_cuda.cu instantiates the unmodified
+ * G2P2GTransfer with a plain three-floats-per-node DOF view and tests/test_gpu_models.py compares this restatement with its output
+ * (fixed-corotated 2.6e-5, von Mises 2.4e-5 of max |r|: the distance between the reference's host and device arithmetic).
  * model 0 fixed-corotated, 1 von Mises {yield}, 2 Drucker-Prager {cohesion, beta, yieldSurface, volumeCorrection},
  * 3 NACC {xi, beta, hardeningOn, fa, dim}, 4 equation of state {bulk, viscosity} (Jp instead of F). */
 void zo_g2p2g(int model, const float *prm, int n, const float *x, const float *F, const float *Jp, const float *logJp,

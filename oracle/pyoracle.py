@@ -386,7 +386,7 @@ class Oracle:
         return out[:c].copy()
 
     def g2p2g(self, model, prm, P, tab, dx, dt, E, nu, volume, gridv):
-        """G2P2GTransfer (parity unpinned): gridv [nb*64, 3] -> gridr [nb*64, 3]"""
+        """G2P2GTransfer (pinned against the reference's own functor on the GPU, tests/test_gpu_models.py): gridv [nb*64, 3] -> gridr [nb*64, 3]"""
         n = P["x"].shape[0]
         prm = np.ascontiguousarray(prm, np.float32)
         gridv = np.ascontiguousarray(gridv, np.float32)

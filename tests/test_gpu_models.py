@@ -338,8 +338,8 @@ def test_against_the_references_own_cuda_path(oracle, tmp_path):
 
 @pytest.mark.parametrize("model", ["fcr", "vonmises", "nacc", "eos"])
 def test_g2p2g_matches_the_restated_functor(oracle, model):
-    """zpcb200_g2p2g_apic vs oracle.zo_g2p2g (a restatement of G2P2G.hpp:49-141 — parity unpinned, the reference's functor does not
-    compile here): force terms added to gridr, particles untouched"""
+    """zpcb200_g2p2g_apic vs oracle.zo_g2p2g (a restatement of G2P2G.hpp:49-141, itself pinned against the reference's own functor by
+    the next test) for the models the reference driver does not instantiate as well: force terms added to gridr, particles untouched"""
     from zpc_b200 import api
     P = synth.elastic_cube(8, 32, jitter_F=0.04, jitter_C=0.3, shuffle_seed=21)
     n, dx = P["x"].shape[0], P["dx"]

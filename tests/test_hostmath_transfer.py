@@ -109,10 +109,11 @@ def test_plastic_models_on_the_host(hm, oracle, model):
 
 @pytest.mark.parametrize("model", [0, 1, 2, 3, 4])
 def test_g2p2g_on_the_host_matches_the_restated_functor(hm, oracle, model):
-    """g2p2g_particle (the body of zpcb200_g2p2g_apic's kernel) vs oracle.zo_g2p2g for all five models.  PARITY UNPINNED: the
-    reference's G2P2G cannot be compiled here (types/View.h), the oracle is a restatement of simulation/transfer/G2P2G.hpp:49-141;
-    this test checks that the product code and that restatement agree, and that the functor does what its algebra says (a rigid
-    translation field gives C = 0, hence the stress of F itself)."""
+    """g2p2g_particle (the body of zpcb200_g2p2g_apic's kernel) vs oracle.zo_g2p2g for all five models.  The reference's G2P2G
+    cannot be compiled by gcc here (types/View.h); the oracle is a restatement of simulation/transfer/G2P2G.hpp:49-141 that the GPU
+    suite pins against the reference's own functor (test_g2p2g_matches_the_references_own_functor).  This CPU test checks that the
+    product code and the restatement agree, and that the functor does what its algebra says (a rigid translation field gives C = 0,
+    hence the stress of F itself)."""
     P = synth.elastic_cube(6, 32, jitter_F=0.04, jitter_C=0.3, shuffle_seed=21)
     n, dx = P["x"].shape[0], P["dx"]
     rs = np.random.RandomState(5)
