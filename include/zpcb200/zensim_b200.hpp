@@ -429,6 +429,100 @@ struct ApplyBoundaryConditionOnGridBlocks {
   Collider collider; HashTable &table; Grids &grids;
   int launch(const CudaExecutionPolicy &pol) { return zpcb200_apply_boundary(grids.view(), table.view(), collider.c, pol._stream); }
 };
+// ---- the block-binned fast path --------------------------------------------------------------------
+// Particles::particleBins (geometry/Structurefree.hpp:220: TileVector<f32,32>, channels m x(3) v(3) C(9) F(9)) sorted by home block,
+// plus the bin metadata, the cell-order cache G2P leaves for the next P2G, and the status word of include/zpcb200.h (ZPC_BINS_*).
+struct BinnedParticles {
+  size_t _n;
+  int _binCapacity;
+  Vector<float> tiles;
+  Vector<int> binStart, binKey, numBins, cellOrderValid, status;
+  Vector<unsigned short> cellOrder, cellStart;
+  BinnedParticles(size_t n, int binCapacity)
+      : _n{n}, _binCapacity{binCapacity}, tiles(((n + 31) / 32) * ZPC_PB_NCH * 32), binStart((size_t)binCapacity + 1),
+        binKey((size_t)binCapacity * 3), numBins(1), cellOrderValid(1), status(1), cellOrder(n ? n : 1),
+        cellStart((size_t)binCapacity * ZPCB200_CELL_GROUPS_PAD) {
+    numBins.setVal(0); cellOrderValid.setVal(0); status.setVal(0);
+    cudaMemset(tiles.data(), 0, sizeof(float) * tiles.size());
+  }
+  size_t size() const { return _n; }
+  int bins() const { return numBins.getVal(); }
+  int statusWord() const { return status.getVal(); }   // ZPC_BINS_* bits, 0 = fine
+  zpc_bins_view view() {
+    return zpc_bins_view{zpc_tilevector_view{tiles.data(), _n, ZPC_PB_NCH}, binStart.data(), binKey.data(), numBins.data(), _binCapacity,
+                         cellOrder.data(), cellStart.data(), cellOrderValid.data(), status.data()};
+  }
+};
+namespace detail {
+template <class Fn> inline int two_phase(const CudaExecutionPolicy &pol, Fn fn) {
+  size_t bytes = 0;
+  int rc = fn(nullptr, &bytes);
+  if (rc) return rc;
+  void *t = pol.scratch(bytes);
+  size_t cap = pol._scratchBytes;
+  return t ? fn(t, &cap) : (int)cudaErrorMemoryAllocation;
+}
+}  // namespace detail
+struct BinParticles {  // AoS Particles -> bins (needs a partition built from the same positions); orderOut[i] = AoS index of binned particle i
+  Particles &pars; HashTable &table; float dx; BinnedParticles &bins; int *orderOut{nullptr};
+  int launch(const CudaExecutionPolicy &pol) {
+    return detail::two_phase(pol, [&](void *t, size_t *b) { return zpcb200_bin_particles(t, b, pars.view(), table.view(), dx, bins.view(), orderOut, pol._stream); });
+  }
+};
+struct RebinParticles {  // after the particles moved: src -> dst, both binned (partition rebuilt from src's positions first)
+  BinnedParticles &src; HashTable &table; float dx; BinnedParticles &dst;
+  int launch(const CudaExecutionPolicy &pol) {
+    return detail::two_phase(pol, [&](void *t, size_t *b) { return zpcb200_rebin_particles(t, b, src.view(), table.view(), dx, dst.view(), pol._stream); });
+  }
+};
+struct PartitionForBinnedParticles {  // the partition from the positions of binned particles (AoSoA port on channel x)
+  BinnedParticles &bins; float dx; HashTable &table; int lo{0}, hi{2};
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_port x{bins.tiles.data() + ZPC_PB_X * 32, 0, 5, 31, ZPC_PB_NCH};
+    return detail::two_phase(pol, [&](void *t, size_t *b) {
+      return zpcb200_partition_build(t, b, x, bins.size(), dx, table.view(), lo, hi, table._overflow.data(), pol._stream);
+    });
+  }
+};
+struct UnbinParticles {  // bins -> AoS Particles, in bin order
+  BinnedParticles &bins; Particles &pars;
+  int launch(const CudaExecutionPolicy &pol) { return zpcb200_unbin_particles(bins.view(), pars.view(), pol._stream); }
+};
+struct P2GTransferBinned {  // P2GTransfer<apic, FixedCorotated> on the bins: smem arena, TMA bulk reduce write-back
+  float dt; FixedCorotatedConfig model; BinnedParticles &bins; HashTable &table; Grids &grids;
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
+    return zpcb200_p2g_apic_fcr_binned(bins.view(), table.view(), grids.view(), dt, m, pol._stream);
+  }
+};
+struct G2PTransferBinned {  // G2PTransfer<apic> on the bins: TMA-staged arena and particle rows; leaves the cell-order cache
+  float dt; Grids &grids; HashTable &table; BinnedParticles &bins;
+  int launch(const CudaExecutionPolicy &pol) { return zpcb200_g2p_apic_binned(bins.view(), table.view(), grids.view(), dt, pol._stream); }
+};
+// the same on SparseGrid<3,f32,8>: bins = octants of the side-8 blocks; binCapacity >= 8 x the number of active blocks
+struct SgBinParticles {
+  Particles &pars; SparseGrid &sg; BinnedParticles &bins; int *orderOut{nullptr};
+  int launch(const CudaExecutionPolicy &pol) {
+    return detail::two_phase(pol, [&](void *t, size_t *b) { return zpcb200_sg_bin_particles(t, b, pars.view(), sg.view(), bins.view(), orderOut, pol._stream); });
+  }
+};
+struct SgRebinParticles {
+  BinnedParticles &src; SparseGrid &sg; BinnedParticles &dst;
+  int launch(const CudaExecutionPolicy &pol) {
+    return detail::two_phase(pol, [&](void *t, size_t *b) { return zpcb200_sg_rebin_particles(t, b, src.view(), sg.view(), dst.view(), nullptr, pol._stream); });
+  }
+};
+struct SgP2GTransferBinned {
+  float dt; FixedCorotatedConfig model; BinnedParticles &bins; SparseGrid &sg;
+  int launch(const CudaExecutionPolicy &pol) {
+    zpc_fixed_corotated m{model.rho, model.volume, model.dim, model.E, model.nu};
+    return zpcb200_sg_p2g_apic_fcr_binned(bins.view(), sg.view(), dt, m, pol._stream);
+  }
+};
+struct SgG2PTransferBinned {
+  float dt; SparseGrid &sg; BinnedParticles &bins;
+  int launch(const CudaExecutionPolicy &pol) { return zpcb200_sg_g2p_apic_binned(bins.view(), sg.view(), dt, pol._stream); }
+};
 struct G2PTransfer {
   float dt; Grids &grids; HashTable &table; Particles &pars;
   int launch(const CudaExecutionPolicy &pol) { return zpcb200_g2p_apic(pars.view(), table.view(), grids.view(), dt, pol._stream); }

@@ -164,6 +164,70 @@ int main() {
     for (size_t i = 0; i < 9 * n; ++i) dFm = std::max(dFm, (double)std::fabs(sF[i] - F[i]));
     CHECK(dxm <= 1e-5 && dvm <= 1.2e-5 && dFm <= 1.1e-5, "SparseGrid g2p x/v/F");
     std::printf("SparseGrid substep ok: %zu blocks of 8^3, err x %.2e v %.2e F %.2e\n", sg.numBlocks(), dxm, dvm, dFm);
+
+    // the block-binned fast path through the mirror, on both grids: bin -> P2G -> update -> G2P -> unbin; binned particle i is
+    // AoS particle order[i], so the oracle's result (x, v, F above) is compared through that permutation
+    for (int which = 0; which < 2; ++which) {
+      Particles pars3(n), back(n);
+      {
+        std::mt19937 rng3(3);
+        std::vector<float> x3(3 * n), v3(3 * n), C3(9 * n), F3(9 * n);
+        size_t q3 = 0;
+        for (int i = 0; i < s; ++i) for (int j = 0; j < s; ++j) for (int k = 0; k < s; ++k) for (int q = 0; q < 8; ++q, ++q3) {
+          const int c3[3] = {i, j, k};
+          for (int d = 0; d < 3; ++d) {
+            x3[3 * q3 + d] = (7 + c3[d] + (((q >> (2 - d)) & 1) + U(rng3)) * 0.5f) * dx;
+            v3[3 * q3 + d] = (d == 1 ? -1.f : 0.f) + 0.2f * (U(rng3) - 0.5f);
+          }
+          for (int d = 0; d < 9; ++d) { C3[d + 9 * q3] = 0.3f * (U(rng3) - 0.5f); F3[d + 9 * q3] = (d % 4 == 0 ? 1.f : 0.f) + 0.04f * (U(rng3) - 0.5f); }
+        }
+        cudaMemcpy(pars3.X.data(), x3.data(), 12 * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(pars3.V.data(), v3.data(), 12 * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(pars3.M.data(), m.data(), 4 * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(pars3.C.data(), C3.data(), 36 * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(pars3.F.data(), F3.data(), 36 * n, cudaMemcpyHostToDevice);
+      }
+      Vector<int> order(n);
+      maxVel.setVal(0.f);
+      int nbins = 0, status = 0;
+      if (which == 0) {
+        HashTable table3(n / 8);
+        pol(PartitionForParticles{pars3, dx, table3});
+        Grids grids3(dx, table3.size());
+        BinnedParticles bins((size_t)n, 2 * table3.size() + 64);
+        pol(BinParticles{pars3, table3, dx, bins, order.data()});
+        pol(CleanGridBlocks{grids3, table3});
+        pol(P2GTransferBinned{dt, model, bins, table3, grids3});
+        pol(ComputeGridBlockVelocity{grids3, table3, dt, gravity, maxVel.data(), 1});
+        pol(G2PTransferBinned{dt, grids3, table3, bins});
+        pol(UnbinParticles{bins, back});
+        nbins = bins.bins(); status = bins.statusWord();
+      } else {
+        SparseGrid sg3(7, n / 16);
+        sg3.scale(dx);
+        pol(SgPartitionForParticles{pars3, sg3});
+        BinnedParticles bins((size_t)n, 8 * (int)sg3.numBlocks() + 64);
+        pol(SgBinParticles{pars3, sg3, bins, order.data()});
+        pol(SgCleanGridBlocks{sg3});
+        pol(SgP2GTransferBinned{dt, model, bins, sg3});
+        pol(SgComputeGridBlockVelocity{sg3, dt, gravity, maxVel.data(), 1});
+        pol(SgG2PTransferBinned{dt, sg3, bins});
+        pol(UnbinParticles{bins, back});
+        nbins = bins.bins(); status = bins.statusWord();
+      }
+      CHECK(pol.lastError() == 0 && status == 0 && nbins > 0, "latched error / status word on the binned path");
+      CHECK(std::fabs(maxVel.getVal() - mx) <= 1e-5f * mx, "binned maxVel");
+      auto ord = order.toHost();
+      auto bx = back.X.toHost(), bv = back.V.toHost(), bF = back.F.toHost();
+      double e1 = 0, e2 = 0, e3 = 0;
+      for (size_t i = 0; i < n; ++i) {
+        const size_t j = (size_t)ord[i];
+        for (int d = 0; d < 3; ++d) { e1 = std::max(e1, (double)std::fabs(bx[3 * i + d] - x[3 * j + d])); e2 = std::max(e2, (double)std::fabs(bv[3 * i + d] - v[3 * j + d])); }
+        for (int d = 0; d < 9; ++d) e3 = std::max(e3, (double)std::fabs(bF[9 * i + d] - F[9 * j + d]));
+      }
+      CHECK(e1 <= 1e-5 && e2 <= 1.2e-5 && e3 <= 1.1e-5, "binned g2p x/v/F");
+      std::printf("binned fast path on %s ok: %d bins, err x %.2e v %.2e F %.2e\n", which ? "SparseGrid<3,f32,8>" : "Grids<f32,3,4>", nbins, e1, e2, e3);
+    }
   }
   {  // merge_sort_pair: stable, in place, float keys with signed zeros
     const size_t n = 100003;
