@@ -408,11 +408,14 @@ def main():
         # every rank feeds its own shard from pinned host memory and reads it back: N PCIe links in parallel.  All ranks run the
         # same code on same-shaped data, so a failure is raised on every rank at the same point (no rank is left in a collective).
         try:
-            halo_obj = sol.halo
+            from zpc_b200.dist_solver import DistMpmSolver, HaloFused
+            # the AoS path exchanges with pack -> peer stores -> unpack-add; the fused halo (send inside the BINNED P2G's write-back) has
+            # no such entry, so the host-buffer solver builds its own peer-to-peer exchange when the fast path ran fused
+            halo_obj = None if isinstance(sol.halo, HaloFused) else sol.halo
             del sol
             torch.cuda.empty_cache()
-            from zpc_b200.dist_solver import DistMpmSolver
-            sol2 = DistMpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="aos", halo=halo_obj)
+            sol2 = DistMpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, layout="aos", halo=halo_obj,
+                                 transport="auto" if args.halo in ("auto", "fused") else args.halo)
             hin = {k: torch.from_numpy(P[k]).pin_memory() for k in ("x", "v", "m", "C", "F")}
             hout = {k: torch.empty_like(hin[k]).pin_memory() for k in ("x", "v", "C", "F")}
             bi = sum(hin[k].numel() * 4 for k in hin)
