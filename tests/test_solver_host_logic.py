@@ -121,6 +121,42 @@ def test_models_and_colliders_pick_the_right_entries(recorder):
         MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="aos", device="cpu", colliders=cols * 3)
 
 
+def test_status_words_are_read_at_every_rebin_and_after_every_graph_replay(recorder):
+    """the device status words (a stencil block missing from the partition, bin capacity, table overflow, whatever the owner
+    registered) reach the host at every re-bin and — the replayed re-bins cannot read back — once after every graph replay"""
+    P = synth.elastic_cube(4, 16)
+    sol = MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="binned", rebin_every=2, device="cpu", partition="with_rebin")
+    sol.substep()
+    sol.substep()
+    sol.bins.status.fill_(8)                              # raised by a P2G / G2P since the last re-bin
+    with pytest.raises(RuntimeError, match="stencil block"):
+        sol.substep()                                     # step_no 2: the re-bin reads the retired bins' word
+    assert int(sol.bins_alt.status.item()) == 0           # ... and clears it
+    extra = torch.zeros(1, dtype=torch.int32)
+    sol.extra_status.append((extra, "halo maps"))
+
+    class _Graph:
+        replays = 0
+
+        def replay(self):
+            self.replays += 1
+    sol._graph, sol._graph_len = _Graph(), 4
+    n0 = sol.step_no
+    sol.replay_cycle()
+    assert sol._graph.replays == 1 and sol.step_no == n0 + 4
+    sol.table.overflow.fill_(1)
+    with pytest.raises(RuntimeError, match="overflow"):
+        sol.replay_cycle()
+    sol.table.overflow.zero_()
+    extra.fill_(3)
+    with pytest.raises(RuntimeError, match=r"halo maps \(status 3\)"):
+        sol.replay_cycle()
+    assert int(extra.item()) == 0
+    sol.check_status = False                              # opt-out: nothing is read
+    sol.bins.status.fill_(2)
+    sol.replay_cycle()
+
+
 def test_particle_range_views_are_pointer_offsets():
     P = synth.elastic_cube(3, 16)
     P["logJp"] = np.zeros(P["x"].shape[0], np.float32)

@@ -467,6 +467,8 @@ class DistMpmSolver:
         self._graph.replay()
         self.local.step_no += self._graph_len
         self._cfl_reduced = False
+        if self.local.check_status:
+            self.local.check_status_words()
 
     def substep(self):
         L = self.local

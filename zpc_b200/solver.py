@@ -140,22 +140,26 @@ class MpmSolver:
         self.bins, self.bins_alt = self.bins_alt, self.bins
         self._mark("rebin")
         if self.check_status and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
-            # ONE D2H read per re-bin: the status word of the bins that just retired (a stencil block missing from the partition since
-            # the last re-bin = a particle out-ran the extra ring), of the new bins (capacity), the table's overflow flag and whatever
-            # the owner registered (multi-GPU: the halo maps)
-            words = [self.bins_alt.status, self.bins.status, self.table.overflow] + [t for t, _ in self.extra_status]
-            vals = torch.cat([w.reshape(1).to(torch.int32) for w in words]).tolist()
-            if any(vals):
-                if vals[0]:
-                    self.bins_alt.check_status("substeps since the last re-bin")
-                if vals[1]:
-                    self.bins.check_status("rebin_particles")
-                if vals[2]:
-                    raise RuntimeError("hash-grid partition overflow: raise expected_blocks")
-                for v, (t, what) in zip(vals[3:], self.extra_status):
-                    if v:
-                        t.zero_()
-                        raise RuntimeError("%s (status %d)" % (what, v))
+            self.check_status_words()
+
+    def check_status_words(self):
+        """ONE D2H read of every status word of the path: the bins that retired at the last re-bin (a stencil block missing from the
+        partition = a particle out-ran the extra ring), the current bins (capacity; strays since the re-bin), the table's overflow
+        flag and whatever the owner registered (multi-GPU: the halo maps).  Raises on the first word that is set.  Called at every
+        re-bin and after every graph replay (the replayed re-bins cannot read back to the host)."""
+        words = [self.bins_alt.status, self.bins.status, self.table.overflow] + [t for t, _ in self.extra_status]
+        vals = torch.cat([w.reshape(1).to(torch.int32) for w in words]).tolist()
+        if any(vals):
+            if vals[0]:
+                self.bins_alt.check_status("substeps up to the last re-bin")
+            if vals[1]:
+                self.bins.check_status("re-bin / substeps since the last re-bin")
+            if vals[2]:
+                raise RuntimeError("hash-grid partition overflow: raise expected_blocks")
+            for v, (t, what) in zip(vals[3:], self.extra_status):
+                if v:
+                    t.zero_()
+                    raise RuntimeError("%s (status %d)" % (what, v))
 
     def rebin_due(self):
         return self.layout == "binned" and self.step_no > 0 and self.rebin_every > 0 and self.step_no % self.rebin_every == 0
@@ -197,9 +201,11 @@ class MpmSolver:
         return k
 
     def replay_cycle(self):
-        """one graph launch = 2 * rebin_every substeps"""
+        """one graph launch = 2 * rebin_every substeps; the status words are read once per replay (one small D2H after it)"""
         self._graph.replay()
         self.step_no += self._graph_len
+        if self.check_status:
+            self.check_status_words()
 
     def substep_host(self, hin, hout, stream=None):
         """Reference-facing call with HOST buffers (pinned torch tensors x,v,m,C,F in; x,v,C,F out), any particle
