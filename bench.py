@@ -243,6 +243,10 @@ def main():
         sol = DistMpmSolver(P, P["dx"], P["volume"], synth.DT, synth.GRAVITY, mode=1, rebin_every=args.rebin_every,
                             transport=args.halo)
         n_local = sol.n
+        # the device status words (stray particles, capacities, halo maps) come back through an asynchronous copy, looked at one
+        # re-bin later and flushed after the timed region: at 1.4 ms per substep a host that stops at every re-bin cannot keep the
+        # GPUs fed (MpmSolver.check_status_words)
+        sol.local.status_mode = "deferred"
     torch.cuda.synchronize()
 
     def barrier():
@@ -294,6 +298,12 @@ def main():
         stage_steps = graph_len
     stage = sol.stage_times_ms()
     sol.stage_events = None
+    status_note = None
+    if world > 1:
+        try:
+            sol.local.flush_status()           # every outstanding read of the status words, and one of their final state
+        except RuntimeError as ex:
+            status_note = repr(ex)
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,6 +311,12 @@ def main():
         cnt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(cnt)
         launches = int(cnt.item())
+        bad = torch.tensor([1 if status_note else 0], device="cuda", dtype=torch.int64)
+        dist.all_reduce(bad)
+        status_words = dict(mode="deferred (asynchronous read-back, flushed after the timed region)", ranks_with_a_status_bit=int(bad.item()),
+                            rank0=status_note)
+    else:
+        status_words = dict(mode="read at every re-bin (blocking)", ranks_with_a_status_bit=0, rank0=None)   # a set bit raises there
     per_rank = None
     if dist is not None:
         # every rank's own stage times: the step is as slow as the slowest rank, the others wait at the barrier / the CFL reduction
@@ -359,7 +375,7 @@ def main():
                                             "p2p": "peer stores into symmetric memory over NVLink + device barrier"}.get(transport, "NCCL send/recv"))),
                     substeps_per_sec=1e3 / ms_per_step, roofline=roof, fused_step=fused, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches,
                     clocks=clocks, cuda_graph=dict(substeps_per_graph=graph_len, note=graph_note, stage_times="from one eager cycle after the timed region") if world > 1 else None,
-                    per_rank_stage_ms=per_rank, multi_gpu_parity=mg_parity, vs_reference_cuda=vs_refcuda, prims=prims)
+                    per_rank_stage_ms=per_rank, status_words=status_words, multi_gpu_parity=mg_parity, vs_reference_cuda=vs_refcuda, prims=prims)
 
     # the e2e leg at N > 1 is collective: if it has not finished after --e2e-timeout seconds (a rank stuck in a collective), rank 0
     # still prints the line — the device-resident numbers above are complete — and every rank leaves

@@ -858,6 +858,29 @@ def test_bins_status_word_reports_what_used_to_be_silent(oracle):
     with pytest.raises(RuntimeError, match="stencil block"):
         for _ in range(9):
             sol.substep()
+    # (e) status_mode="deferred": the same words through an asynchronous copy to pinned memory — the host never waits at a re-bin, the
+    # fault surfaces at a later re-bin or, at the latest, in flush_status() / particles_host()
+    sol = MpmSolver(Pf, dx, Pf["volume"], synth.DT, synth.GRAVITY, mode=1, layout="binned", rebin_every=8, partition="with_rebin")
+    sol.status_mode = "deferred"
+    with pytest.raises(RuntimeError, match="stencil block"):
+        for _ in range(9):
+            sol.substep()
+        sol.flush_status()
+    from zpc_b200.selfcheck import identity_masses
+    ok = synth.elastic_cube(6, 32, jitter_F=0.03, jitter_C=0.3)
+    ok["m"] = identity_masses(ok["m"].shape[0], float(ok["m"].mean()))      # pairs the particles whatever order the re-bins leave
+    a = MpmSolver(ok, dx, ok["volume"], synth.DT, synth.GRAVITY, mode=1, layout="binned", rebin_every=3, partition="with_rebin")
+    b = MpmSolver(ok, dx, ok["volume"], synth.DT, synth.GRAVITY, mode=1, layout="binned", rebin_every=3, partition="with_rebin")
+    b.status_mode = "deferred"
+    for _ in range(10):
+        a.substep()
+        b.substep()
+    b.flush_status()
+    assert b._status_pending == []
+    pa, pb = a.particles_host(), b.particles_host()
+    oa, ob = np.argsort(pa["m"], kind="stable"), np.argsort(pb["m"], kind="stable")
+    check_particles({k: pb[k][ob] for k in "xvCF"}, {k: pa[k][oa] for k in "xvCF"}, dx, "deferred vs synchronous status reads",
+                    rtol=5e-5)                           # same kernels; the float atomics order the sums differently run to run
 
 
 def test_graph_replay_with_a_side_array_equals_eager_substeps():

@@ -155,6 +155,19 @@ def test_status_words_are_read_at_every_rebin_and_after_every_graph_replay(recor
     sol.check_status = False                              # opt-out: nothing is read
     sol.bins.status.fill_(2)
     sol.replay_cycle()
+    sol.bins.status.zero_()
+    # deferred mode: the words are copied out asynchronously and looked at when the copy has landed (CPU tensors: at once)
+    sol.check_status, sol.status_mode = True, "deferred"
+    sol.replay_cycle()
+    assert sol._status_pending == []
+    sol.bins.status.fill_(8)
+    with pytest.raises(RuntimeError, match="since the last re-bin: a stencil block"):
+        sol.flush_status()
+    assert int(sol.bins.status.item()) == 0 and sol._status_pending == []
+    sol.flush_status()
+    sol.bins_alt.status.fill_(1)
+    with pytest.raises(RuntimeError, match="home block"):
+        sol.particles_host()                              # a host read of the results flushes first
 
 
 def test_particle_range_views_are_pointer_offsets():

@@ -575,15 +575,22 @@ class ParticleBins:
         st = int(self.status.item())
         if st:
             self.status.zero_()
-            names = [n for b, n in ((1, "a particle's home block is not in the partition"), (2, "more bins than binCapacity"),
-                                    (4, "more blocks than binCapacity"),
-                                    (8, "a stencil block is absent from the partition (particle drifted past the extra ring: re-bin more often)")) if st & b]
-            raise RuntimeError("%s: %s" % (what, "; ".join(names)))
+            raise RuntimeError("%s: %s" % (what, bins_status_text(st)))
 
     def attr(self, name):
         chn, w = {"m": (PB_M, 1), "x": (PB_X, 3), "v": (PB_V, 3), "C": (PB_C, 9), "F": (PB_F, 9)}[name]
         t = self.pars.channel(chn, w)
         return t[:, 0].contiguous() if w == 1 else t
+
+
+def bins_status_text(st):
+    """the ZPC_BINS_* bits of a zpc_bins_view.status word (include/zpcb200.h) in words"""
+    names = [n for b, n in ((BINS_HOME_BLOCK_MISSING, "a particle's home block is not in the partition"),
+                            (BINS_BIN_CAPACITY, "more bins than binCapacity"), (BINS_BLOCK_CAPACITY, "more blocks than binCapacity"),
+                            (BINS_STENCIL_BLOCK_MISSING, "a stencil block is absent from the partition (particle drifted past the extra "
+                                                         "ring: re-bin more often)"),
+                            (BINS_TMA_TIMEOUT, "a TMA transaction of the staged G2P did not complete")) if st & b]
+    return "; ".join(names) or "status %d" % st
 
 
 def set_tuning(p2g_sweep=-1, g2p_staged=-1):

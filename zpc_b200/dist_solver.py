@@ -424,8 +424,10 @@ class DistMpmSolver:
         kw = dict(gravity=L.extf[1], mode=L.mode, layout="binned", rebin_every=L.rebin_every, device=dev, partition="with_rebin",
                   model=L.model, colliders=L.colliders, expected_blocks=L.block_cap)
         step_no = L.step_no
+        L.flush_status()                               # deferred reads of the solver that retires
         self.local = MpmSolver(P, L.dx, L.model.volume, L.dt, **kw)
-        self.local.step_no = step_no
+        self.local.step_no, self.local.status_mode, self.local.check_status = step_no, L.status_mode, L.check_status
+        self.local.extra_status = L.extra_status       # the halo maps' status word stays registered
         self.n, self.table = self.local.n, self.local.table
         self._rebuild_topology()
         return moved

@@ -52,6 +52,8 @@ class MpmSolver:
         self.max_vel_sqr = torch.zeros(1, dtype=torch.float32, device=device)
         self.rebin_every = int(rebin_every)
         self.check_status = True      # read the device status words at every re-bin (one small D2H; off inside graph capture)
+        self.status_mode = "sync"     # | "deferred": asynchronous read-back, looked at one re-bin later (check_status_words)
+        self._status_pending = []
         self.extra_status = []        # [(device int tensor, message)] read together with them
         self.step_no = 0
         self.stage_events = None
@@ -142,24 +144,71 @@ class MpmSolver:
         if self.check_status and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
             self.check_status_words()
 
+    def _status_words(self):
+        # the bins that retired at the last re-bin (a stencil block missing from the partition = a particle out-ran the extra ring),
+        # the current bins (capacity; strays since the re-bin), the table's overflow flag, whatever the owner registered (multi-GPU:
+        # the halo maps)
+        return [self.bins_alt.status, self.bins.status, self.table.overflow] + [t for t, _ in self.extra_status]
+
+    def _raise_on_status(self, vals, owners):
+        """vals: the words as host ints; owners: the objects they were read from (the bins may have swapped roles since)"""
+        if not any(vals):
+            return
+        retired, current, table = owners[:3]
+        if vals[0]:
+            retired.status.zero_()
+            raise RuntimeError("%s: %s" % ("substeps up to the last re-bin", api.bins_status_text(vals[0])))
+        if vals[1]:
+            current.status.zero_()
+            raise RuntimeError("%s: %s" % ("re-bin / substeps since the last re-bin", api.bins_status_text(vals[1])))
+        if vals[2]:
+            raise RuntimeError("hash-grid partition overflow: raise expected_blocks")
+        for v, (t, what) in zip(vals[3:], owners[3:]):
+            if v:
+                t.zero_()
+                raise RuntimeError("%s (status %d)" % (what, v))
+
     def check_status_words(self):
-        """ONE D2H read of every status word of the path: the bins that retired at the last re-bin (a stencil block missing from the
-        partition = a particle out-ran the extra ring), the current bins (capacity; strays since the re-bin), the table's overflow
-        flag and whatever the owner registered (multi-GPU: the halo maps).  Raises on the first word that is set.  Called at every
-        re-bin and after every graph replay (the replayed re-bins cannot read back to the host)."""
-        words = [self.bins_alt.status, self.bins.status, self.table.overflow] + [t for t, _ in self.extra_status]
-        vals = torch.cat([w.reshape(1).to(torch.int32) for w in words]).tolist()
-        if any(vals):
-            if vals[0]:
-                self.bins_alt.check_status("substeps up to the last re-bin")
-            if vals[1]:
-                self.bins.check_status("re-bin / substeps since the last re-bin")
-            if vals[2]:
-                raise RuntimeError("hash-grid partition overflow: raise expected_blocks")
-            for v, (t, what) in zip(vals[3:], self.extra_status):
-                if v:
-                    t.zero_()
-                    raise RuntimeError("%s (status %d)" % (what, v))
+        """Reads every status word of the path and raises on the first that is set.  Called at every re-bin and after every graph
+        replay (the replayed re-bins cannot read back to the host).
+
+        status_mode "sync" (default): ONE blocking D2H read, the error surfaces at the re-bin that follows the fault.
+        status_mode "deferred": the words are copied to pinned host memory asynchronously and looked at once the copy has landed —
+        at a later re-bin / replay or in flush_status() — so the host never waits for the GPU on this path (at 8 GPUs a substep is
+        1.4 ms: a host that stops at every re-bin cannot enqueue fast enough).  particles_host() flushes."""
+        words = self._status_words()
+        owners = [self.bins_alt, self.bins, self.table] + list(self.extra_status)
+        dev = torch.cat([w.reshape(1).to(torch.int32) for w in words])
+        if self.status_mode != "deferred":
+            self._raise_on_status(dev.tolist(), owners)
+            return
+        if dev.is_cuda:
+            host = torch.empty(dev.numel(), dtype=torch.int32, pin_memory=True)
+            host.copy_(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        else:                                             # host-logic tests: tensors on the CPU, nothing to wait for
+            host, ev = dev.clone(), None
+        self._status_pending.append((ev, host, owners))
+        self.poll_status(block=False)
+
+    def poll_status(self, block=False):
+        """looks at the deferred reads that have landed (all of them when block=True); raises like check_status_words"""
+        while self._status_pending:
+            ev, host, owners = self._status_pending[0]
+            if ev is not None:
+                if block:
+                    ev.synchronize()
+                elif not ev.query():
+                    return
+            self._status_pending.pop(0)
+            self._raise_on_status(host.tolist(), owners)
+
+    def flush_status(self):
+        """deferred mode: one more read of the words as they are now, then wait for every outstanding read"""
+        if self.check_status and self.status_mode == "deferred" and self.layout == "binned":
+            self.check_status_words()
+        self.poll_status(block=True)
 
     def rebin_due(self):
         return self.layout == "binned" and self.step_no > 0 and self.rebin_every > 0 and self.step_no % self.rebin_every == 0
@@ -275,6 +324,7 @@ class MpmSolver:
     def particles_host(self):
         """AoS dict on the host, in the solver's CURRENT particle order."""
         if self.layout == "binned":
+            self.flush_status()
             out = {k: self.bins.attr(k).cpu().numpy() for k in ("x", "v", "m", "C", "F")}
             if self._side:
                 out[self._side] = getattr(self.bins, self._side).cpu().numpy()
