@@ -219,6 +219,22 @@ def _dist_worker(rank, world, port, q):
         step = ["clean_grid", "p2g_apic_fcr_binned", "grid_update", "g2p_apic_binned"]
         assert names == step * 2 + ["partition_build"] * 2 + ["rebin_particles"] * 2 + step, names
         sol2.max_vel_sqr()
+        # graph replay reads the status words afterwards (deferred: through an asynchronous copy; bench.py --gpus N runs on it)
+        class _Graph:
+            def replay(self):
+                pass
+        sol2._graph, sol2._graph_len, sol2.local.status_mode = _Graph(), 4, "deferred"
+        n0 = sol2.local.step_no
+        sol2.replay_cycle()
+        assert sol2.local.step_no == n0 + 4 and sol2.local._status_pending == []
+        sol2.local.table.overflow.fill_(1)
+        try:
+            sol2.replay_cycle()
+            raise AssertionError("the overflow flag went unnoticed")
+        except RuntimeError as ex:
+            assert "overflow" in str(ex)
+        sol2.local.table.overflow.zero_()
+        sol2.local.flush_status()
         # a collider and a per-particle scalar on the multi-GPU fast path: the fused boundary update and the J variant of the G2P
         # (this path used to call the plain update and the F variant whatever the solver was built with)
         Pj = {k: v for k, v in P.items() if k != "F"}
