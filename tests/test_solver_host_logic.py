@@ -121,6 +121,42 @@ def test_models_and_colliders_pick_the_right_entries(recorder):
         MpmSolver(P, P["dx"], P["volume"], synth.DT, layout="aos", device="cpu", colliders=cols * 3)
 
 
+def test_sparsegrid_solver_sequence_for_every_model(recorder):
+    """SgMpmSolver (SparseGrid<3,f32,8>, octant bins): the functor sequence of a substep, the re-bin cadence and — for the models that
+    carry a per-particle scalar — the side array following every re-bin through the library's own gather"""
+    from zpc_b200.sg_solver import SgMpmSolver
+    P = synth.elastic_cube(4, 16)
+    n = P["x"].shape[0]
+    def _names_sg():                                        # without the host helpers the SparseGrid constructor calls
+        return [c for c in _names(recorder) if c not in ("bht_table_size", "bht_params")]
+    sol = SgMpmSolver(P, P["dx"], P["volume"], synth.DT, rebin_every=2, device="cpu")
+    assert _names_sg() == ["sg_partition_build"] * 2 + ["sg_bin_particles"] * 2
+    step = ["sg_clean", "sg_p2g_apic_fcr_binned", "sg_grid_update", "sg_g2p_apic_binned"]
+    for i in range(5):
+        sol.substep()
+        got = _names_sg()
+        assert got == (["sg_partition_build"] * 2 + ["sg_rebin_particles"] * 2 if i in (2, 4) else []) + step, (i, got)
+    assert set(sol.particles_host()) == {"x", "v", "m", "C", "F"}
+    Pj = {k: v for k, v in P.items() if k != "F"}
+    Pj["J"] = np.ones(n, np.float32)
+    cases = ((api.model_vonmises(P["volume"]), P, None, "sg_g2p_apic_binned"),
+             (api.model_nacc(P["volume"]), dict(P, logJp=np.zeros(n, np.float32)), "logJp", "sg_g2p_apic_binned"),
+             (api.model_drucker_prager(P["volume"]), dict(P, logJp=np.zeros(n, np.float32)), "logJp", "sg_g2p_apic_binned"),
+             (api.model_eos(P["volume"]), Pj, "J", "sg_g2p_apic_eos_binned"))
+    for model, Q, side, g2p in cases:
+        s = SgMpmSolver(Q, P["dx"], P["volume"], synth.DT, rebin_every=2, device="cpu", model=model)
+        assert _names_sg() == ["sg_partition_build"] * 2 + ["sg_bin_particles"] * 2 + (["gather_f32"] if side else [])
+        step = ["sg_clean", "sg_p2g_apic_model_binned", "sg_grid_update", g2p]
+        for _ in range(3):
+            s.substep()
+        assert _names_sg() == step * 2 + ["sg_partition_build"] * 2 + ["sg_rebin_particles"] * 2 + (["gather_f32"] if side else []) + step
+        if side:
+            a, b = getattr(s.bins, side), getattr(s.bins_alt, side)
+            assert a is not None and b is not None and a.data_ptr() != b.data_ptr() and side in s.particles_host()
+    with pytest.raises(ValueError):
+        SgMpmSolver(P, P["dx"], P["volume"], synth.DT, device="cpu", model=api.model_nacc(P["volume"]))   # no logJp given
+
+
 def test_status_words_are_read_at_every_rebin_and_after_every_graph_replay(recorder):
     """the device status words (a stencil block missing from the partition, bin capacity, table overflow, whatever the owner
     registered) reach the host at every re-bin and — the replayed re-bins cannot read back — once after every graph replay"""

@@ -10,9 +10,10 @@ class SgMpmSolver:
     def __init__(self, P, dx, volume, dt, gravity=-9.8, mode=1, rebin_every=8, E=5.0e4, nu=0.4, expected_blocks=None, device="cuda",
                  model=None):
         self.model = model if model is not None else api.model_fcr(volume, E, nu)
-        if not isinstance(self.model, (api.zpc_fixed_corotated, api.zpc_vonmises_fixed_corotated)):
-            raise ValueError("SgMpmSolver carries no per-particle side array: fixed-corotated or von Mises (the entries for the other "
-                             "models exist: api.sg_p2g_transfer on ParticleBins with logJp / J)")
+        # per-particle scalar the model carries besides F: logJp (Drucker-Prager, NACC), J (equation of state) — kept next to the bins
+        # in bin order, two persistent buffers that ping-pong with bins / bins_alt (like MpmSolver)
+        self._side = ("logJp" if isinstance(self.model, (api.zpc_drucker_prager, api.zpc_nacc))
+                      else "J" if isinstance(self.model, api.zpc_equation_of_state) else None)
         self.dx, self.dt, self.mode = float(dx), float(dt), int(mode)
         self.extf = (0.0, float(gravity), 0.0)
         self.n = int(P["x"].shape[0])
@@ -30,6 +31,14 @@ class SgMpmSolver:
         self.bins, self.bins_alt = api.ParticleBins(self.n, cap, device), api.ParticleBins(self.n, cap, device)
         self.order = torch.empty(self.n, dtype=torch.int32, device=device)
         api.sg_bin_particles(aos, self.sg, self.bins, self.order)
+        if self._side:
+            src = getattr(aos, self._side)
+            if src is None:
+                raise ValueError("this model needs the per-particle %s attribute (P2G.hpp:67,93)" % self._side)
+            setattr(self.bins, self._side, torch.empty_like(src))
+            setattr(self.bins_alt, self._side, torch.empty_like(src))
+            api.gather_f32(src, self.order, getattr(self.bins, self._side))
+            self._rebin_order = torch.empty(self.n, dtype=torch.int32, device=device)
         self._check("sg_bin_particles")
 
     def _check(self, what):
@@ -55,7 +64,11 @@ class SgMpmSolver:
         self._mark("begin")
         api.sg_partition_for_particles(self.bins.pars.port(api.PB_X), self.n, self.sg)
         self._mark("partition")
-        api.sg_rebin_particles(self.bins, self.sg, self.bins_alt)
+        if self._side:   # the side array follows the permutation of the re-bin
+            api.sg_rebin_particles(self.bins, self.sg, self.bins_alt, order_out=self._rebin_order)
+            api.gather_f32(getattr(self.bins, self._side), self._rebin_order, getattr(self.bins_alt, self._side))
+        else:
+            api.sg_rebin_particles(self.bins, self.sg, self.bins_alt)
         self.bins, self.bins_alt = self.bins_alt, self.bins
         self._mark("rebin")
         if int(self.bins_alt.status.item()):
@@ -73,9 +86,12 @@ class SgMpmSolver:
         self.max_vel_sqr.zero_()
         api.sg_compute_grid_velocity(self.sg, self.dt, self.extf, self.mode, self.max_vel_sqr)
         self._mark("grid_update")
-        api.sg_g2p_transfer(self.bins, self.sg, self.dt)
+        api.sg_g2p_transfer(self.bins, self.sg, self.dt, model=self.model)    # the J variant for an equation of state
         self._mark("g2p")
         self.step_no += 1
 
     def particles_host(self):
-        return {k: self.bins.attr(k).cpu().numpy() for k in ("x", "v", "m", "C", "F")}
+        out = {k: self.bins.attr(k).cpu().numpy() for k in ("x", "v", "m", "C", "F")}
+        if self._side:
+            out[self._side] = getattr(self.bins, self._side).cpu().numpy()
+        return out
