@@ -220,6 +220,66 @@ def test_device_math_on_the_host_tracks_the_oracle(oracle, oracle_fma, hostmath,
         assert np.abs(l - lw)[stable].max() <= 1e-5
 
 
+def _rot(rs):
+    q, _ = np.linalg.qr(rs.standard_normal((3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+def _hm_fcr(hostmath, model, mu, lam, F):
+    n = F.shape[0]
+    got, vec, l = np.empty((n, 9), np.float32), np.zeros(1, np.float32), np.zeros(n, np.float32)
+    hostmath.hm_stress(C.c_int(model), C.c_int(n), C.c_float(1.0), C.c_float(mu), C.c_float(lam), _p(vec), _p(l), _p(F), _p(got))
+    return got
+
+
+def test_fast_path_stress_far_from_the_identity(oracle, hostmath):
+    """stress_fcr_lean (what the binned P2G evaluates; 11 = with the converged-sweep skip) against the oracle where the golden clouds
+    do not go: large rotations, stretches of 0.5 .. 2, a general U S V^T, inverted elements.  Held to the restated full SVD path
+    (model 0 = the reference's algorithm operation by operation) on the same inputs: the bulk within 2x of its distance to the
+    oracle.  Inverted elements whose two smaller |sigma| nearly coincide are ill-conditioned in the model itself (which singular
+    value carries the sign) — there the reference's own arithmetic is 1e-3 from the exact answer — so only the bulk is compared."""
+    rs = np.random.RandomState(5)
+    mu, lam = oracle.lame(E, NU)
+    n = 1500
+    regimes = {
+        "rotation x small stretch": [_rot(rs) @ (np.eye(3) + 0.03 * rs.standard_normal((3, 3))) for _ in range(n)],
+        "rotation x stretch": [(lambda q: q @ np.diag(np.exp(rs.uniform(-0.7, 0.7, 3))) @ q.T)(_rot(rs)) for _ in range(n)],
+        "general U S V^T": [_rot(rs) @ np.diag(np.exp(rs.uniform(-0.7, 0.7, 3))) @ _rot(rs) for _ in range(n)],
+        "inverted": [_rot(rs) @ np.diag(np.exp(rs.uniform(-0.3, 0.3, 3)) * np.array([1, 1, -1.0])) @ _rot(rs) for _ in range(n)],
+        "two equal sigmas": [_rot(rs) @ np.diag([1.2, 1.2, 0.7]) @ _rot(rs) for _ in range(n)],
+    }
+    for name, Fs in regimes.items():
+        F = np.array([f.T.reshape(9) for f in Fs], np.float32)
+        want = np.array([oracle.stress_fixedcorotated(1.0, E, NU, F[i]) for i in range(n)])
+        scale = float(np.abs(want).max())
+        full = np.abs(_hm_fcr(hostmath, 0, mu, lam, F) - want).max(1) / scale
+        for model in (10, 11):
+            dev = np.abs(_hm_fcr(hostmath, model, mu, lam, F) - want).max(1) / scale
+            assert np.percentile(dev, 99) <= 2.0 * np.percentile(full, 99) + 2e-6, (name, model, np.percentile(dev, 99), np.percentile(full, 99))
+            if name != "inverted":
+                assert dev.max() <= 3.0 * full.max() + 5e-6, (name, model, dev.max(), full.max())
+
+
+def test_fast_path_stress_stays_finite_on_degenerate_F(oracle, hostmath):
+    """exactly rank-deficient, zero and vanishing F (a collapsed particle): the reference's guarded Givens steps return finite numbers,
+    and so must the Gram-Schmidt form of the fast path — a NaN in one record would spread over the grid.  (The floor under the squared
+    column norms was 1e-30 at first: rsqrt_refined's Newton step overflows below ~1e-26 and turned these inputs into NaN.)"""
+    rs = np.random.RandomState(3)
+    mu, lam = oracle.lame(E, NU)
+    Fs = [_rot(rs) @ np.diag([1.0, 0.8, 0.0]) @ _rot(rs) for _ in range(100)] + [_rot(rs) @ np.diag([1.0, 0.0, 0.0]) @ _rot(rs) for _ in range(100)]
+    Fs += [np.diag(d) for d in ([1.0, 0.8, 0.0], [0.0, 1.0, 0.8], [1.0, 0.0, 0.8], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.0, 0.0, 0.0])]
+    Fs += [1e-20 * np.eye(3), 1e-12 * _rot(rs), 1e-6 * _rot(rs)]
+    F = np.array([np.asarray(f, np.float64).T.reshape(9) for f in Fs], np.float32)
+    want = np.array([oracle.stress_fixedcorotated(1.0, E, NU, F[i]) for i in range(F.shape[0])])
+    assert np.isfinite(want).all()
+    for model in (0, 10, 11):
+        got = _hm_fcr(hostmath, model, mu, lam, F)
+        assert np.isfinite(got).all(), (model, np.nonzero(~np.isfinite(got).all(1))[0])
+        assert np.abs(got - want).max() <= 1e-4 * 2.0 * mu, (model, np.abs(got - want).max())
+
+
 def test_device_stencil_on_the_host_is_bit_exact(oracle, hostmath):
     """zpcm::arena_init == LocalArena (simulation/Utils.hpp:51-70): base node, local offset, 3x3 weights — same
     expressions, no re-association, so the host build must agree bit for bit with an independent numpy restatement"""

@@ -363,7 +363,9 @@ ZPC_HD void stress_fcr_lean(float scale, float mu, float lam, const float (&F)[9
   ZPC_SWAPB(r1 < r2, b1, b2, r1, r2, false)
 #undef ZPC_SWAPB
   // Gram-Schmidt QR: u0 = b0 / |b0| ; u1 = (b1 - (u0.b1) u0) / |.| ; u2 = u0 x u1 ; sigma = (|b0|, |b1'|, u2.b2)
-  const float tiny2 = 1.e-30f;
+  // floor of the squared column norms: rsqrt_refined's Newton step forms r * (r * h) ~ 0.5 x^-3/2, which overflows fp32 below
+  // x ~ 1e-26 (an exactly rank-deficient or zero F then gave NaN where the reference's guarded Givens steps stay finite)
+  const float tiny2 = 1.e-24f;
   const float i0 = rsqrt_refined(fmaxf(r0, tiny2));
   const float u0[3] = {b0[0] * i0, b0[1] * i0, b0[2] * i0};
   const float sg0 = r0 * i0;
